@@ -1,0 +1,162 @@
+"""ctypes/numpy front for oracle/libtiramisu_oracle.so — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module (see oracle/tiramisu_oracle.c header).  The product
+package tiramisu_b200/ never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libtiramisu_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "tiramisu_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _p(a: np.ndarray):
+    assert a.flags["C_CONTIGUOUS"], "oracle wants C-contiguous arrays"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())
+
+
+def heat2d(inp: np.ndarray, form: str = "cpu") -> np.ndarray:
+    """form: 'cpu' = heat2d_tiramisu.cpp:68, 'gpu' = heat2dgpu_tiramisu.cpp:54."""
+    inp = np.ascontiguousarray(inp, dtype=np.float32)
+    H, W = inp.shape
+    out = np.empty_like(inp)
+    fn = {"cpu": lib().oracle_heat2d, "gpu": lib().oracle_heat2dgpu}[form]
+    fn(_p(inp), _p(out), C.c_int(H), C.c_int(W))
+    return out
+
+
+def heat2d_step(inp: np.ndarray, out: np.ndarray) -> np.ndarray:
+    """One Jacobi half-step of heat2d_dist (interior only; borders of `out` untouched)."""
+    H, W = inp.shape
+    lib().oracle_heat2d_step(_p(inp), _p(out), C.c_int(H), C.c_int(W))
+    return out
+
+
+def blurxy_u8(inp: np.ndarray) -> np.ndarray:
+    inp = np.ascontiguousarray(inp, dtype=np.uint8)
+    Cc, H, W = inp.shape
+    out = np.empty((Cc, H - 8, W - 8), dtype=np.uint8)
+    lib().oracle_blurxy_u8(_p(inp), _p(out), C.c_int(Cc), C.c_int(H), C.c_int(W))
+    return out
+
+
+def boxblur_u32(inp: np.ndarray) -> np.ndarray:
+    """inp: u32[rows+2][cols+2] -> u32[rows][cols] (vertical pass first; test_160)."""
+    inp = np.ascontiguousarray(inp, dtype=np.uint32)
+    rows, cols = inp.shape[0] - 2, inp.shape[1] - 2
+    out = np.empty((rows, cols), dtype=np.uint32)
+    lib().oracle_boxblur_u32(_p(inp), _p(out), C.c_int(rows), C.c_int(cols))
+    return out
+
+
+def blur_f32(inp: np.ndarray) -> np.ndarray:
+    inp = np.ascontiguousarray(inp, dtype=np.float32)
+    H, W = inp.shape
+    out = np.empty((H - 2, W - 2), dtype=np.float32)
+    lib().oracle_blur_f32(_p(inp), _p(out), C.c_int(H), C.c_int(W))
+    return out
+
+
+def sgemm(a: float, b: float, A: np.ndarray, B: np.ndarray, Cm: np.ndarray) -> np.ndarray:
+    """sgemm_tiramisu semantics: returns a*(A@B) + b*C with sequential-k fp32, no FMA."""
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    out = np.array(Cm, dtype=np.float32, order="C", copy=True)
+    N, K = A.shape
+    K2, M = B.shape
+    assert K == K2 and out.shape == (N, M)
+    lib().oracle_sgemm(C.c_int(N), C.c_int(M), C.c_int(K), C.c_float(a), C.c_float(b),
+                       _p(A), _p(B), _p(out))
+    return out
+
+
+def gemm_ld(A, B, Cm, M, N, K, alpha, beta, ldA=0, ldB=0, ldC=0, offA=0, offB=0, offC=0,
+            tA=False, tB=False, dtype=np.float32):
+    """tiramisu_cublas_{s,d}gemm contract on flat arrays; returns the updated flat C."""
+    A = np.ascontiguousarray(A, dtype=dtype).ravel()
+    B = np.ascontiguousarray(B, dtype=dtype).ravel()
+    out = np.array(Cm, dtype=dtype, copy=True).ravel()
+    u = C.c_uint64
+    if dtype == np.float32:
+        lib().oracle_gemm_ld(_p(A), _p(B), _p(out), u(M), u(N), u(K), C.c_float(alpha),
+                             C.c_float(beta), u(ldA), u(ldB), u(ldC), u(offA), u(offB), u(offC),
+                             C.c_int(int(tA)), C.c_int(int(tB)))
+    else:
+        lib().oracle_dgemm_ld(_p(A), _p(B), _p(out), u(M), u(N), u(K), C.c_double(alpha),
+                              C.c_double(beta), u(ldA), u(ldB), u(ldC), u(offA), u(offB), u(offC),
+                              C.c_int(int(tA)), C.c_int(int(tB)))
+    return out
+
+
+def matmul_u8(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    A = np.ascontiguousarray(A, dtype=np.uint8)
+    B = np.ascontiguousarray(B, dtype=np.uint8)
+    N = A.shape[0]
+    out = np.empty((N, N), dtype=np.uint8)
+    lib().oracle_matmul_u8(_p(A), _p(B), _p(out), C.c_int(N))
+    return out
+
+
+def conv_relu_maxpool(inp: np.ndarray, filt: np.ndarray, bias: np.ndarray) -> np.ndarray:
+    """inp f32[B][N+2][N+2][FIn], filt f32[FOut/8][3][3][FIn][8], bias f32[FOut]
+    -> f32[B][FOut/8][N/2][N/2][8]."""
+    inp = np.ascontiguousarray(inp, dtype=np.float32)
+    filt = np.ascontiguousarray(filt, dtype=np.float32)
+    bias = np.ascontiguousarray(bias, dtype=np.float32).ravel()
+    Bn, NP, _, FIn = inp.shape
+    FB = filt.shape[0]
+    N = NP - 2
+    out = np.empty((Bn, FB, N // 2, N // 2, 8), dtype=np.float32)
+    lib().oracle_conv_relu_maxpool(_p(inp), _p(filt), _p(bias), _p(out), C.c_int(Bn), C.c_int(N),
+                                   C.c_int(FIn), C.c_int(FB * 8))
+    return out
+
+
+def lstm(Weights: np.ndarray, biases: np.ndarray, x: np.ndarray) -> np.ndarray:
+    """Weights f32[L][2][4F][F] (0=R,1=W), biases f32[L][4F], x f32[T][B][F] -> y f32[T][B][F]."""
+    Weights = np.ascontiguousarray(Weights, dtype=np.float32)
+    biases = np.ascontiguousarray(biases, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    L, two, F4, F = Weights.shape
+    assert two == 2 and F4 == 4 * F
+    T, Bn, F2 = x.shape
+    assert F2 == F
+    y = np.empty_like(x)
+    lib().oracle_lstm(C.c_int(F), C.c_int(Bn), C.c_int(L), C.c_int(T), _p(Weights), _p(biases),
+                      _p(x), _p(y))
+    return y
+
+
+def transpose_f32(A: np.ndarray) -> np.ndarray:
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    r, c = A.shape
+    out = np.empty((c, r), dtype=np.float32)
+    lib().oracle_transpose_f32(_p(A), _p(out), C.c_int(r), C.c_int(c))
+    return out
