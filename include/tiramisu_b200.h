@@ -1,0 +1,148 @@
+/* tiramisu_b200.h — C ABI of the B200-native (sm_100a) backend for Tiramisu's hot path.
+ *
+ * Two nested boundaries, both plain C (pointers and sizes only), exported by
+ * tiramisu_b200/lib/libtiramisu_b200.so:
+ *
+ *  B1  generated-function ABI: `int <fn>(halide_buffer_t *...)`, the symbols the
+ *      reference's wrapper_*.cpp / *_wrapper.cpp harnesses link against.
+ *      Return 0 on success, non-zero on a validation error (message via
+ *      tiramisu_b200_last_error()).  Buffers may live on the host (->host, copies are
+ *      done inside, as the reference's generated code does) or on the device
+ *      (->host == NULL and ->device = CUDA pointer: no copies).
+ *
+ *  B2  runtime ABI: the tiramisu_cuda_* / tiramisu_cublas_* / tiramisu_address_of_* /
+ *      tiramisu_MPI_* shims that Tiramisu-generated host code calls
+ *      (reference: src/tiramisu_cuda_wrappers.cpp, src/tiramisu_externs.cpp,
+ *      src/tiramisu_mpi.cpp), plus per-kernel launchers on device pointers — the role of
+ *      the reference's `_kernel_<N>_wrapper` functions (src/tiramisu_codegen_cuda.cpp:855-866),
+ *      here named after what they compute.
+ *
+ * All launches go to the calling thread's stream (tiramisu_b200_set_stream; default
+ * cudaStreamPerThread — the reference compiles with --default-stream per-thread,
+ * src/tiramisu_codegen_cuda.cpp:1745).
+ */
+#ifndef TIRAMISU_B200_H
+#define TIRAMISU_B200_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#include "tiramisu_b200/halide_buffer.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ===================================================================== library control */
+const char *tiramisu_b200_version(void);
+/* Last error message recorded on any thread ("" if none). */
+const char *tiramisu_b200_last_error(void);
+/* 0 (default): CUDA failures print and exit(1) like src/tiramisu_cuda_wrappers.cpp:14-31.
+ * 1: they return non-zero / NULL instead. Returns the previous mode. */
+int tiramisu_b200_set_error_mode(int return_instead_of_exit);
+/* Launch stream of the calling thread (a cudaStream_t); NULL restores cudaStreamPerThread. */
+void tiramisu_b200_set_stream(void *cuda_stream);
+void *tiramisu_b200_get_stream(void);
+/* Number of kernels this library has launched since load (all threads). */
+uint64_t tiramisu_b200_kernel_launches(void);
+/* Release cached pool memory back to the driver. */
+int tiramisu_b200_pool_trim(void);
+
+/* ===================================================================== B2: runtime shims
+ * Same names and argument meaning as src/tiramisu_cuda_wrappers.cpp. */
+int tiramisu_cuda_memcpy_to_device(void *dst_dev, void *src_host, uint64_t bytes);   /* :34 blocking */
+int tiramisu_cuda_memcpy_to_host(void *dst_host, void *src_dev, uint64_t bytes);     /* :41 blocking */
+int tiramisu_cuda_memcpy_to_symbol(void *symbol, void *src_host, uint64_t bytes);    /* :48 */
+void *tiramisu_cuda_malloc(uint64_t bytes);                                          /* :55 pooled, stream-ordered */
+int tiramisu_cuda_free(void *ptr);                                                   /* :63 */
+int32_t tiramisu_cuda_stream_synchronize(int32_t dummy);                             /* :164 syncs the thread's stream */
+/* Stream-ordered variants used inside the generated functions (no host sync). */
+int tiramisu_cuda_memcpy_to_device_async(void *dst_dev, const void *src_host, uint64_t bytes);
+int tiramisu_cuda_memcpy_to_host_async(void *dst_host, const void *src_dev, uint64_t bytes);
+
+/* Row-major C[MxN] = alpha*op(A)*op(B) + beta*C on DEVICE pointers, element offsets, leading
+ * dimensions (0 => tight), transposes.  src/tiramisu_cuda_wrappers.cpp:74-115 / :121-162.
+ * fp32 runs on tcgen05 TF32 tiles (fp32 accumulate) when the operands are TMA-addressable
+ * (16-byte aligned bases and leading dimensions), else on an exact fp32 SIMT kernel. */
+int tiramisu_cublas_sgemm(float *A, float *B, float *C, uint64_t M, uint64_t N, uint64_t K,
+                          float alpha, float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC,
+                          uint64_t offsetA, uint64_t offsetB, uint64_t offsetC,
+                          bool transposeA, bool transposeB);
+int tiramisu_cublas_dgemm(double *A, double *B, double *C, uint64_t M, uint64_t N, uint64_t K,
+                          double alpha, double beta, uint64_t ldA, uint64_t ldB, uint64_t ldC,
+                          uint64_t offsetA, uint64_t offsetB, uint64_t offsetC,
+                          bool transposeA, bool transposeB);
+/* 0 = auto (tensor cores when addressable), 1 = force exact fp32 SIMT, 2 = force tcgen05
+ * (fails if not addressable).  Returns the previous mode. */
+int tiramisu_b200_set_gemm_mode(int mode);
+
+/* src/tiramisu_externs.cpp:8-54 */
+int8_t *tiramisu_address_of_int8(halide_buffer_t *buffer, unsigned long index);
+uint8_t *tiramisu_address_of_uint8(halide_buffer_t *buffer, unsigned long index);
+int16_t *tiramisu_address_of_int16(halide_buffer_t *buffer, unsigned long index);
+uint16_t *tiramisu_address_of_uint16(halide_buffer_t *buffer, unsigned long index);
+int32_t *tiramisu_address_of_int32(halide_buffer_t *buffer, unsigned long index);
+uint32_t *tiramisu_address_of_uint32(halide_buffer_t *buffer, unsigned long index);
+int64_t *tiramisu_address_of_int64(halide_buffer_t *buffer, unsigned long index);
+uint64_t *tiramisu_address_of_uint64(halide_buffer_t *buffer, unsigned long index);
+float *tiramisu_address_of_float32(halide_buffer_t *buffer, unsigned long index);
+double *tiramisu_address_of_float64(halide_buffer_t *buffer, unsigned long index);
+
+/* ===================================================================== B2: kernel launchers
+ * Device pointers, launched on the thread's stream, no synchronisation.  These replace the
+ * `_kernel_<N>_wrapper`s that src/tiramisu_codegen_cuda.cpp emits for each GPU loop nest. */
+
+/* 5-point stencil, alpha=0.3f beta=0.4f, borders of `out` written 0.
+ * form 0: heat2d_tiramisu.cpp:68      a*c + b*(((E+W)+S)+N)
+ * form 1: heat2dgpu_tiramisu.cpp:54   c*a + (((S+E)+N)+W)*b
+ * form 2: heat2d_dist_tiramisu.cpp:88 c*a + (((N+S)+W)+E)*b, borders of `out` NOT written
+ * Rows [row_begin,row_end) of an HxW grid are produced (a rank's shard); in/out point at row 0. */
+int tiramisu_b200_heat2d(const float *in, float *out, int32_t H, int32_t W, int32_t form,
+                         int32_t row_begin, int32_t row_end);
+/* 3x3 separable blurs.  f32: in[H][W] -> out[H-2][W-2] (horizontal first, /3.0f).
+ * u8 : blurxy_tiramisu.cpp:61,77   in[C][H][W] -> out[C][H-8][W-8], wraps mod 256.
+ * u32: tests/test_160.cpp:23-29    in[rows+2][cols+2] -> out[rows][cols], vertical first. */
+int tiramisu_b200_blur_f32(const float *in, float *out, int32_t H, int32_t W,
+                           int32_t row_begin, int32_t row_end);
+int tiramisu_b200_blurxy_u8(const uint8_t *in, uint8_t *out, int32_t C, int32_t H, int32_t W);
+int tiramisu_b200_boxblur_u32(const uint32_t *in, uint32_t *out, int32_t rows, int32_t cols);
+/* tutorials/developers/tutorial_04gpu.cpp: uint8 NxN matmul (wraps mod 256). */
+int tiramisu_b200_matmul_u8(const uint8_t *A, const uint8_t *B, uint8_t *C, int32_t N);
+/* tests/test_197.cpp (int32 fill) and tests/test_168.cpp (fp32 transpose) kernels. */
+int tiramisu_b200_fill_i32(int32_t *buf, uint64_t n, int32_t value);
+int tiramisu_b200_transpose_f32(const float *A, float *At, int32_t rows, int32_t cols);
+
+/* ===================================================================== B1: generated functions */
+/* benchmarks/halide/wrapper_heat2d.h:10 — in,out f32[H][W] (reference bakes 10000x10000). */
+int heat2d_tiramisu(halide_buffer_t *in, halide_buffer_t *out);
+/* benchmarks/halide/wrapper_heat2dgpu.cpp:44 — sizes i32[2] = {extent0 (W), extent1 (H)}. */
+int heat2dgpu_tiramisu(halide_buffer_t *sizes, halide_buffer_t *in, halide_buffer_t *out);
+/* benchmarks/halide/wrapper_blurxy.cpp:21 — in u8[3][H][W], out u8[3][H-8][W-8]. */
+int blurxy_tiramisu(halide_buffer_t *in, halide_buffer_t *out);
+/* fp32 blur of BASELINE config 2 (SURVEY.md §8 a8'): in f32[H][W], out f32[H-2][W-2]. */
+int blurxy_f32_tiramisu(halide_buffer_t *in, halide_buffer_t *out);
+/* tests/wrapper_test_160.h / benchmarks/automatic_comm: in u32[rows(+2)][cols+2], out u32[rows][cols].
+ * With a communicator up (tiramisu_MPI_init) the 2 halo rows are received from rank+1. */
+int boxblur(halide_buffer_t *in, halide_buffer_t *out);
+int blurautodist_tiramisu(halide_buffer_t *in, halide_buffer_t *out);
+/* benchmarks/linear_algebra/blas/level3/sgemm/cpu/sgemm_wrapper.h:13 — SIZES i32[3]={N,M,K},
+ * C[NxM] = a*(A[NxK]*B[KxM]) + b*C. */
+int sgemm_tiramisu(halide_buffer_t *SIZES, halide_buffer_t *alpha, halide_buffer_t *beta,
+                   halide_buffer_t *A, halide_buffer_t *B, halide_buffer_t *C);
+/* benchmarks/linear_algebra/blas/level3/sgemm/gpu/wrapper.h:6-11 — Consts f32[2]={alpha,beta};
+ * time_start/time_end f32[1] receive get_time() around the kernel when the caller provides it. */
+int matmul(halide_buffer_t *Consts, halide_buffer_t *A, halide_buffer_t *B, halide_buffer_t *C,
+           halide_buffer_t *time_start, halide_buffer_t *time_end);
+/* tests/wrapper_test_162.h..167.h — cublas_gemm / gpu_tile GEMM feature tests. */
+int test_162(halide_buffer_t *sizes, halide_buffer_t *params, halide_buffer_t *A,
+             halide_buffer_t *B, halide_buffer_t *C);
+int test_164(halide_buffer_t *sizes, halide_buffer_t *params, halide_buffer_t *transposes,
+             halide_buffer_t *A, halide_buffer_t *B, halide_buffer_t *C);
+int test_167(halide_buffer_t *A, halide_buffer_t *B, halide_buffer_t *C);
+int test_168(halide_buffer_t *A, halide_buffer_t *B);
+int test_197(halide_buffer_t *A, halide_buffer_t *B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIRAMISU_B200_H */

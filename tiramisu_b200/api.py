@@ -1,0 +1,118 @@
+"""Host-side mirror of the reference's generated-function interface (B1 in include/tiramisu_b200.h).
+
+Every function has the name and argument order of the `extern "C"` symbol the reference's wrapper
+programs call, takes numpy arrays / torch tensors where the C++ wrappers take Halide::Buffer, and
+calls straight through the C ABI.  Host arrays are copied to the GPU and back inside the call (as
+the reference's generated code does); CUDA tensors are used in place.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .halide import Buffer
+
+
+def _call(name, *objs):
+    bufs = [o if isinstance(o, Buffer) else Buffer(o) for o in objs]
+    rc = getattr(_lib.lib(), name)(*[b.ptr() for b in bufs])
+    _lib.check(rc, name)
+
+
+# ---- stencils -------------------------------------------------------------------------------------
+def heat2d_tiramisu(inp, out):
+    """benchmarks/halide/wrapper_heat2d.h:10 — in,out f32[H][W]."""
+    _call("heat2d_tiramisu", inp, out)
+
+
+def heat2dgpu_tiramisu(sizes, inp, out):
+    """benchmarks/halide/wrapper_heat2dgpu.cpp:44 — sizes i32[2] = {W, H}."""
+    _call("heat2dgpu_tiramisu", sizes, inp, out)
+
+
+def blurxy_tiramisu(inp, out):
+    """benchmarks/halide/wrapper_blurxy.cpp:21 — in u8[3][H][W], out u8[3][H-8][W-8]."""
+    _call("blurxy_tiramisu", inp, out)
+
+
+def blurxy_f32_tiramisu(inp, out):
+    """fp32 blur of BASELINE config 2 — in f32[H][W], out f32[H-2][W-2]."""
+    _call("blurxy_f32_tiramisu", inp, out)
+
+
+def boxblur(inp, out):
+    """tests/wrapper_test_160.h — in u32[rows+2][cols+2], out u32[rows][cols]."""
+    _call("boxblur", inp, out)
+
+
+def blurautodist_tiramisu(inp, out):
+    _call("blurautodist_tiramisu", inp, out)
+
+
+# ---- GEMMs ----------------------------------------------------------------------------------------
+def sgemm_tiramisu(SIZES, alpha, beta, A, B, Cm):
+    """sgemm/cpu/sgemm_wrapper.h:13 — SIZES i32[3] = {N, M, K}; C[NxM] = a*A[NxK]*B[KxM] + b*C."""
+    _call("sgemm_tiramisu", SIZES, alpha, beta, A, B, Cm)
+
+
+def matmul(Consts, A, B, Cm, time_start=None, time_end=None):
+    """sgemm/gpu/wrapper.h:6-11 — Consts f32[2] = {alpha, beta}."""
+    t0 = time_start if time_start is not None else np.zeros(1, np.float32)
+    t1 = time_end if time_end is not None else np.zeros(1, np.float32)
+    _call("matmul", Consts, A, B, Cm, t0, t1)
+
+
+def test_162(sizes, params, A, B, Cm):
+    _call("test_162", sizes, params, A, B, Cm)
+
+
+def test_164(sizes, params, transposes, A, B, Cm):
+    _call("test_164", sizes, params, transposes, A, B, Cm)
+
+
+def test_167(A, B, Cm):
+    _call("test_167", A, B, Cm)
+
+
+def test_168(A, B):
+    _call("test_168", A, B)
+
+
+def test_197(A, B):
+    _call("test_197", A, B)
+
+
+# ---- B2 runtime, for callers that manage device memory themselves ------------------------------------
+def set_stream(cuda_stream: int | None) -> None:
+    """Launch on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); None = per-thread default."""
+    _lib.lib().tiramisu_b200_set_stream(C.c_void_p(cuda_stream or 0))
+
+
+def synchronize() -> None:
+    _lib.check(_lib.lib().tiramisu_cuda_stream_synchronize(0), "tiramisu_cuda_stream_synchronize")
+
+
+def kernel_launches() -> int:
+    return int(_lib.lib().tiramisu_b200_kernel_launches())
+
+
+def set_gemm_mode(mode: int) -> int:
+    """0 auto, 1 exact fp32 SIMT, 2 force tcgen05 TF32."""
+    return int(_lib.lib().tiramisu_b200_set_gemm_mode(mode))
+
+
+def cublas_sgemm(A_ptr, B_ptr, C_ptr, M, N, K, alpha, beta, ldA=0, ldB=0, ldC=0, offA=0, offB=0, offC=0,
+                 tA=False, tB=False):
+    """tiramisu_cublas_sgemm on raw device pointers (src/tiramisu_cuda_wrappers.cpp:74)."""
+    rc = _lib.lib().tiramisu_cublas_sgemm(A_ptr, B_ptr, C_ptr, M, N, K, alpha, beta, ldA, ldB, ldC, offA, offB,
+                                          offC, tA, tB)
+    _lib.check(rc, "tiramisu_cublas_sgemm")
+
+
+def cublas_dgemm(A_ptr, B_ptr, C_ptr, M, N, K, alpha, beta, ldA=0, ldB=0, ldC=0, offA=0, offB=0, offC=0,
+                 tA=False, tB=False):
+    rc = _lib.lib().tiramisu_cublas_dgemm(A_ptr, B_ptr, C_ptr, M, N, K, alpha, beta, ldA, ldB, ldC, offA, offB,
+                                          offC, tA, tB)
+    _lib.check(rc, "tiramisu_cublas_dgemm")

@@ -1,0 +1,333 @@
+// functions.cu — B1: the `extern "C" int <fn>(halide_buffer_t*...)` entry points that the
+// reference's Tiramisu-generated objects export and its wrapper_*.cpp harnesses call
+// (SURVEY.md §8b).  Each one is the host-side program the reference's Halide-compiled x86 stub
+// runs around its kernels (src/tiramisu_codegen_halide.cpp:2469-2574): allocate device
+// temporaries, copy arguments in, launch, copy results out — here stream-ordered, pooled and
+// with a single synchronisation at the end.  Arguments may also be device-resident (see
+// common.cuh BufView), in which case nothing is copied.
+#include "common.cuh"
+#include "tiramisu_b200.h"
+
+#include <dlfcn.h>
+
+#include <chrono>
+#include <cstring>
+#include <vector>
+
+using namespace tb200;
+
+namespace tb200 {
+int gemm_f32(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,
+             uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tA, bool tB);
+}
+
+namespace {
+
+int bad(const char *fn, const char *what) {
+    set_last_error(std::string(fn) + ": " + what);
+    return 2;                                       // validation errors never exit
+}
+
+// Small parameter buffers (SIZES, alpha, Consts ...) are read on the host.
+template <class T>
+int read_params(const BufView &v, T *dst, int n)
+{
+    if (!v.on_device) {
+        memcpy(dst, v.ptr, sizeof(T) * n);
+        return 0;
+    }
+    TB200_CHECK(cudaMemcpyAsync(dst, v.ptr, sizeof(T) * n, cudaMemcpyDeviceToHost, stream()));
+    TB200_CHECK(cudaStreamSynchronize(stream()));
+    return 0;
+}
+
+int finish() { return check(cudaStreamSynchronize(stream()), "cudaStreamSynchronize"); }
+
+bool type_mismatch(const BufView &v, int bits)
+{
+    return v.ndim > 0 && v.elem_bits != 0 && v.elem_bits != bits;
+}
+
+// ---------------------------------------------------------------------------------------------
+int heat2d_common(const char *fn, halide_buffer_t *in, halide_buffer_t *out, int H, int W, int form)
+{
+    BufView vi, vo;
+    if (!view_of(in, &vi) || !view_of(out, &vo)) return bad(fn, "null buffer");
+    if (type_mismatch(vi, 32) || type_mismatch(vo, 32)) return bad(fn, "expected 32-bit float buffers");
+    if (vi.ndim >= 2) { W = (int)vi.extent[0]; H = (int)vi.extent[1]; }
+    if (vo.ndim >= 2 && (vo.extent[0] != W || vo.extent[1] != H)) return bad(fn, "in/out extents differ");
+    if (H < 1 || W < 1) return bad(fn, "empty grid");
+    const size_t bytes = (size_t)H * W * sizeof(float);
+    DeviceArg din, dout;
+    if (din.bind(vi, bytes, true) || dout.bind(vo, bytes, false)) return 1;
+    if (tiramisu_b200_heat2d(din.as<float>(), dout.as<float>(), H, W, form, 0, H)) return 1;
+    if (dout.copy_out()) return 1;
+    return finish();
+}
+
+template <class T>
+int blur_common(const char *fn, halide_buffer_t *in, halide_buffer_t *out, int C, int H, int W, int shrink,
+                int (*launch)(const T *, T *, int, int, int))
+{
+    BufView vi, vo;
+    if (!view_of(in, &vi) || !view_of(out, &vo)) return bad(fn, "null buffer");
+    if (type_mismatch(vi, 8 * (int)sizeof(T)) || type_mismatch(vo, 8 * (int)sizeof(T))) return bad(fn, "wrong element type");
+    if (vi.ndim >= 2) {
+        W = (int)vi.extent[0];
+        H = (int)vi.extent[1];
+        C = vi.ndim >= 3 ? (int)vi.extent[2] : 1;
+    }
+    if (H <= shrink || W <= shrink || C < 1) return bad(fn, "input smaller than the stencil");
+    if (vo.ndim >= 2 && (vo.extent[0] != W - shrink || vo.extent[1] != H - shrink)) return bad(fn, "output extent must be input - stencil");
+    DeviceArg din, dout;
+    if (din.bind(vi, (size_t)C * H * W * sizeof(T), true)) return 1;
+    if (dout.bind(vo, (size_t)C * (H - shrink) * (W - shrink) * sizeof(T), false)) return 1;
+    if (launch(din.as<T>(), dout.as<T>(), C, H, W)) return 1;
+    if (dout.copy_out()) return 1;
+    return finish();
+}
+
+int launch_blur_u8(const uint8_t *i, uint8_t *o, int C, int H, int W) { return tiramisu_b200_blurxy_u8(i, o, C, H, W); }
+int launch_blur_f32(const float *i, float *o, int, int H, int W) { return tiramisu_b200_blur_f32(i, o, H, W, 0, H - 2); }
+
+float now_ms()
+{
+    // The reference's generated code calls an extern get_time(int32) supplied by the wrapper
+    // (benchmarks/linear_algebra/blas/level3/sgemm/gpu/wrapper.cpp:16-21); use it when the host
+    // program exports it so both clocks agree, else a steady clock in ms.
+    typedef float (*get_time_fn)(int32_t);
+    static get_time_fn user = reinterpret_cast<get_time_fn>(dlsym(RTLD_DEFAULT, "get_time"));
+    if (user) return user(0);
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// C[MxN] = alpha*A*B + beta*C with host- or device-resident row-major operands.
+int gemm_buffers(const char *fn, const BufView &va, const BufView &vb, const BufView &vc, uint64_t M, uint64_t N,
+                 uint64_t K, float alpha, float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, uint64_t offA,
+                 uint64_t offB, uint64_t offC, bool tA, bool tB, size_t elemsA, size_t elemsB, size_t elemsC,
+                 float *t_start, float *t_end)
+{
+    (void)fn;
+    DeviceArg da, db, dc;
+    if (da.bind(va, elemsA * 4, true) || db.bind(vb, elemsB * 4, true) || dc.bind(vc, elemsC * 4, true)) return 1;
+    if (t_start) {
+        if (finish()) return 1;                       // reference: blocking copies, then get_time
+        *t_start = now_ms();
+    }
+    if (gemm_f32(da.as<float>() + offA, db.as<float>() + offB, dc.as<float>() + offC, M, N, K, alpha, beta, ldA,
+                 ldB, ldC, tA, tB))
+        return 1;
+    if (t_end) {
+        if (finish()) return 1;                       // final_sync, generator1.cpp:92
+        *t_end = now_ms();
+    }
+    if (dc.copy_out()) return 1;
+    return finish();
+}
+
+}  // namespace
+
+// =============================================================================== stencils
+TB200_API int heat2d_tiramisu(halide_buffer_t *in, halide_buffer_t *out)
+{
+    // benchmarks/halide/heat2d_tiramisu.cpp:29-30 bakes SIZE0 = SIZE1 = 10000
+    return heat2d_common(__func__, in, out, 10000, 10000, 0);
+}
+
+TB200_API int heat2dgpu_tiramisu(halide_buffer_t *sizes, halide_buffer_t *in, halide_buffer_t *out)
+{
+    BufView vs;
+    if (!view_of(sizes, &vs)) return bad(__func__, "null sizes buffer");
+    int32_t s[2];
+    if (read_params(vs, s, 2)) return 1;
+    // wrapper_heat2dgpu.cpp:32-34: size(0) = extent(0) (columns), size(1) = extent(1) (rows)
+    return heat2d_common(__func__, in, out, s[1], s[0], 1);
+}
+
+TB200_API int blurxy_tiramisu(halide_buffer_t *in, halide_buffer_t *out)
+{
+    // utils/images/rgb.png is 2112 x 3520 x 3
+    return blur_common<uint8_t>(__func__, in, out, 3, 3520, 2112, 8, launch_blur_u8);
+}
+
+TB200_API int blurxy_f32_tiramisu(halide_buffer_t *in, halide_buffer_t *out)
+{
+    return blur_common<float>(__func__, in, out, 1, 16384, 16384, 2, launch_blur_f32);
+}
+
+namespace tb200 {
+// comm.cu: halo rows for the distributed box blur (no-op without a communicator)
+int boxblur_halo_exchange(uint32_t *d_in, int rows, int cols);
+}
+
+static int boxblur_common(const char *fn, halide_buffer_t *in, halide_buffer_t *out, int rows, int cols)
+{
+    BufView vi, vo;
+    if (!view_of(in, &vi) || !view_of(out, &vo)) return bad(fn, "null buffer");
+    if (type_mismatch(vi, 32) || type_mismatch(vo, 32)) return bad(fn, "expected uint32 buffers");
+    if (vo.ndim >= 2) { cols = (int)vo.extent[0]; rows = (int)vo.extent[1]; }
+    if (rows < 1 || cols < 1) return bad(fn, "empty output");
+    if (vi.ndim >= 2 && (vi.extent[0] != cols + 2 || vi.extent[1] < rows + 2)) return bad(fn, "input must be [rows+2][cols+2] (2 halo rows)");
+    // The reference's receive buffer is grown by 2 halo rows (tests/wrapper_test_160.cpp:13:
+    // img(_COLS+2, _ROWS/10+2)); rows [rows, rows+2) are received from rank+1 when distributed.
+    const size_t in_bytes = (size_t)(rows + 2) * (cols + 2) * 4;
+    DeviceArg din, dout;
+    if (din.bind(vi, in_bytes, true) || dout.bind(vo, (size_t)rows * cols * 4, false)) return 1;
+    if (boxblur_halo_exchange(din.as<uint32_t>(), rows, cols)) return 1;
+    if (tiramisu_b200_boxblur_u32(din.as<uint32_t>(), dout.as<uint32_t>(), rows, cols)) return 1;
+    // gen_communication() stores the received halo in the caller's buffer (wrapper_test_160.cpp:39
+    // reads img(c, r+2) after the call), so copy the two halo rows back to a host-resident input.
+    if (din.staged()) {
+        const size_t off = (size_t)rows * (cols + 2);
+        if (tiramisu_cuda_memcpy_to_host_async(reinterpret_cast<uint32_t *>(vi.ptr) + off, din.as<uint32_t>() + off,
+                                               (size_t)2 * (cols + 2) * 4))
+            return 1;
+    }
+    if (dout.copy_out()) return 1;
+    return finish();
+}
+
+TB200_API int boxblur(halide_buffer_t *in, halide_buffer_t *out)
+{
+    return boxblur_common(__func__, in, out, 10, 10);           // tests/wrapper_test_160.h:8-9, 10 ranks
+}
+
+TB200_API int blurautodist_tiramisu(halide_buffer_t *in, halide_buffer_t *out)
+{
+    return boxblur_common(__func__, in, out, 100, 1000);        // benchmarks/automatic_comm/wrapper_blurautodist.h:6-8
+}
+
+// =============================================================================== GEMMs
+TB200_API int sgemm_tiramisu(halide_buffer_t *SIZES, halide_buffer_t *alpha, halide_buffer_t *beta,
+                             halide_buffer_t *A, halide_buffer_t *B, halide_buffer_t *C)
+{
+    BufView vs, val, vbe, va, vb, vc;
+    if (!view_of(SIZES, &vs) || !view_of(alpha, &val) || !view_of(beta, &vbe) || !view_of(A, &va) ||
+        !view_of(B, &vb) || !view_of(C, &vc))
+        return bad(__func__, "null buffer");
+    int32_t s[3];
+    float a, b;
+    if (read_params(vs, s, 3) || read_params(val, &a, 1) || read_params(vbe, &b, 1)) return 1;
+    // sgemm_generator.cpp:296-304: SIZES = {N, M, K}; A[N][K], B[K][M], C[N][M]
+    const int64_t N = s[0], M = s[1], K = s[2];
+    if (N < 0 || M < 0 || K < 0) return bad(__func__, "negative size");
+    if (va.ndim >= 2 && (va.extent[0] != K || va.extent[1] != N)) return bad(__func__, "A extents != {K, N}");
+    if (vb.ndim >= 2 && (vb.extent[0] != M || vb.extent[1] != K)) return bad(__func__, "B extents != {M, K}");
+    if (vc.ndim >= 2 && (vc.extent[0] != M || vc.extent[1] != N)) return bad(__func__, "C extents != {M, N}");
+    if (N == 0 || M == 0) return 0;
+    return gemm_buffers(__func__, va, vb, vc, N, M, K, a, b, K, M, M, 0, 0, 0, false, false, (size_t)N * K,
+                        (size_t)K * M, (size_t)N * M, nullptr, nullptr);
+}
+
+TB200_API int matmul(halide_buffer_t *Consts, halide_buffer_t *A, halide_buffer_t *B, halide_buffer_t *C,
+                     halide_buffer_t *time_start, halide_buffer_t *time_end)
+{
+    BufView vk, va, vb, vc, vt0, vt1;
+    if (!view_of(Consts, &vk) || !view_of(A, &va) || !view_of(B, &vb) || !view_of(C, &vc))
+        return bad(__func__, "null buffer");
+    float consts[2];
+    if (read_params(vk, consts, 2)) return 1;
+    // gpu/configuration.h:11-13 bakes M = N = K = 3072; wrapper.cpp:59-61: A_buf {K, M}, B_buf {N, K}
+    int64_t M = 3072, N = 3072, K = 3072;
+    if (va.ndim >= 2) { K = va.extent[0]; M = va.extent[1]; }
+    if (vb.ndim >= 2) {
+        N = vb.extent[0];
+        if (vb.extent[1] != K) return bad(__func__, "A and B disagree on K");
+    }
+    if (vc.ndim >= 2 && (vc.extent[0] != N || vc.extent[1] != M)) return bad(__func__, "C extents != {N, M}");
+    float t0 = 0.f, t1 = 0.f;
+    const bool timed = view_of(time_start, &vt0) && view_of(time_end, &vt1) && !vt0.on_device && !vt1.on_device;
+    int rc = gemm_buffers(__func__, va, vb, vc, M, N, K, consts[0], consts[1], K, N, N, 0, 0, 0, false, false,
+                          (size_t)M * K, (size_t)K * N, (size_t)M * N, timed ? &t0 : nullptr, timed ? &t1 : nullptr);
+    if (rc == 0 && timed) {
+        *reinterpret_cast<float *>(vt0.ptr) = t0;
+        *reinterpret_cast<float *>(vt1.ptr) = t1;
+    }
+    return rc;
+}
+
+// tests/test_162.cpp: sizes i32[3] = {M,N,K}, params f32[>=2] = {alpha, beta}; cublas_gemm(A,B,C)
+TB200_API int test_162(halide_buffer_t *sizes, halide_buffer_t *params, halide_buffer_t *A, halide_buffer_t *B,
+                       halide_buffer_t *C)
+{
+    BufView vs, vp, va, vb, vc;
+    if (!view_of(sizes, &vs) || !view_of(params, &vp) || !view_of(A, &va) || !view_of(B, &vb) || !view_of(C, &vc))
+        return bad(__func__, "null buffer");
+    int32_t s[3];
+    float pr[2];
+    if (read_params(vs, s, 3) || read_params(vp, pr, 2)) return 1;
+    const uint64_t M = s[0], N = s[1], K = s[2];
+    return gemm_buffers(__func__, va, vb, vc, M, N, K, pr[0], pr[1], K, N, N, 0, 0, 0, false, false, M * K, K * N,
+                        M * N, nullptr, nullptr);
+}
+
+// tests/test_164.cpp:10-29: sizes i32[12] = {M,N,K,rowsA,colsA,rowsB,colsB,rowsC,colsC,offA,offB,offC},
+// params = {alpha,beta}, transposes bool[2]; leading dimensions are the column counts.
+TB200_API int test_164(halide_buffer_t *sizes, halide_buffer_t *params, halide_buffer_t *transposes,
+                       halide_buffer_t *A, halide_buffer_t *B, halide_buffer_t *C)
+{
+    BufView vs, vp, vt, va, vb, vc;
+    if (!view_of(sizes, &vs) || !view_of(params, &vp) || !view_of(transposes, &vt) || !view_of(A, &va) ||
+        !view_of(B, &vb) || !view_of(C, &vc))
+        return bad(__func__, "null buffer");
+    int32_t s[12];
+    float pr[2];
+    uint8_t tr[2];
+    if (read_params(vs, s, 12) || read_params(vp, pr, 2) || read_params(vt, tr, 2)) return 1;
+    return gemm_buffers(__func__, va, vb, vc, s[0], s[1], s[2], pr[0], pr[1], s[4], s[6], s[8], s[9], s[10], s[11],
+                        tr[0] != 0, tr[1] != 0, (size_t)s[3] * s[4], (size_t)s[5] * s[6], (size_t)s[7] * s[8], nullptr,
+                        nullptr);
+}
+
+// tests/test_167.cpp (and 169-171): C[128][128] += A*B through gpu_tile'd loops
+TB200_API int test_167(halide_buffer_t *A, halide_buffer_t *B, halide_buffer_t *C)
+{
+    BufView va, vb, vc;
+    if (!view_of(A, &va) || !view_of(B, &vb) || !view_of(C, &vc)) return bad(__func__, "null buffer");
+    const uint64_t n = 128;
+    return gemm_buffers(__func__, va, vb, vc, n, n, n, 1.0f, 1.0f, n, n, n, 0, 0, 0, false, false, n * n, n * n, n * n,
+                        nullptr, nullptr);
+}
+
+// tests/test_168.cpp: B[256][128] = transpose(A[128][256])
+TB200_API int test_168(halide_buffer_t *A, halide_buffer_t *B)
+{
+    BufView va, vb;
+    if (!view_of(A, &va) || !view_of(B, &vb)) return bad(__func__, "null buffer");
+    int rows = 128, cols = 256;
+    if (va.ndim >= 2) { cols = (int)va.extent[0]; rows = (int)va.extent[1]; }
+    DeviceArg da, db;
+    if (da.bind(va, (size_t)rows * cols * 4, true) || db.bind(vb, (size_t)rows * cols * 4, false)) return 1;
+    if (tiramisu_b200_transpose_f32(da.as<float>(), db.as<float>(), rows, cols)) return 1;
+    if (db.copy_out()) return 1;
+    return finish();
+}
+
+// tests/test_197.cpp: for each t: allocate, copy in, fill (A := 1, B := 2), copy out, free.
+TB200_API int test_197(halide_buffer_t *A, halide_buffer_t *B)
+{
+    halide_buffer_t *bufs[2] = {A, B};
+    const int32_t vals[2] = {1, 2};
+    const int64_t def_side[2] = {512, 512}, def_t = 2;       // tests/test_197_defs.h
+    for (int b = 0; b < 2; b++) {
+        BufView v;
+        if (!view_of(bufs[b], &v)) return bad(__func__, "null buffer");
+        int64_t T = def_t, n = def_side[b] * def_side[b];
+        if (v.ndim >= 3) { n = v.extent[0] * v.extent[1]; T = v.extent[2]; }
+        for (int64_t t = 0; t < T; t++) {
+            int32_t *host_or_dev = reinterpret_cast<int32_t *>(v.ptr) + t * n;
+            if (v.on_device) {
+                if (tiramisu_b200_fill_i32(host_or_dev, (uint64_t)n, vals[b])) return 1;
+                continue;
+            }
+            int32_t *d = reinterpret_cast<int32_t *>(tiramisu_cuda_malloc((uint64_t)n * 4));
+            if (!d) return 1;
+            if (tiramisu_cuda_memcpy_to_device_async(d, host_or_dev, (uint64_t)n * 4)) return 1;
+            if (tiramisu_b200_fill_i32(d, (uint64_t)n, vals[b])) return 1;
+            if (tiramisu_cuda_memcpy_to_host_async(host_or_dev, d, (uint64_t)n * 4)) return 1;
+            if (tiramisu_cuda_free(d)) return 1;
+        }
+    }
+    return finish();
+}

@@ -1,0 +1,365 @@
+// gemm_tc.cu — fp32 GEMM on the 5th-generation tensor cores (tcgen05, kind::tf32, fp32
+// accumulators in TMEM), the sm_100a lowering of the contraction pattern
+//     c_acc(i,j,k) = c_acc(i,j,0) + A(i,k)*B(k,j);  C = acc*alpha + C*beta
+// (reference: benchmarks/linear_algebra/blas/level3/sgemm/gpu/generator1.cpp:68-72, which the
+// cuda_ast emitter turns into a 16x16-thread SIMT kernel with hand-staged __shared__ tiles, and
+// tiramisu_cublas_sgemm, src/tiramisu_cuda_wrappers.cpp:74-115).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer — cp.async.bulk.tensor loads of the A (128x32 fp32) and B (32xBN)
+//              k-slabs into a STAGES-deep ring of 128B-swizzled smem tiles, mbarrier expect_tx.
+//   warp 1   : MMA issuer — one thread issues 4 x tcgen05.mma (M=128,N=BN,K=8) per slab, frees
+//              each slab with tcgen05.commit, signals the epilogue with a final commit.
+//   warps 2-5: epilogue — tcgen05.ld the accumulator rows, apply alpha/beta, 128-bit stores.
+// fp32 operands are consumed in place as TF32 (the tensor core ignores the low 13 mantissa
+// bits), so there is no conversion pass over HBM.  A is K-major; B is either K-major ([N][K],
+// the transposeB / LSTM-weights case) or MN-major ([K][N], the plain row-major sgemm case), the
+// latter fetched as BN/32 boxes of 32(k) x 32(n) so that each box is one MN-major swizzle slab.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tiramisu_b200.h"
+
+#include <cstdlib>
+#include <mutex>
+
+using namespace tb200;
+
+namespace tb200 {
+
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link) ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
+                        const uint64_t *strides_bytes, const uint32_t *box, bool swizzle128)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail("make_tensor_map_f32", "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("make_tensor_map_f32", "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+
+}  // namespace tb200
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // 32 fp32 = one 128-byte swizzle row
+constexpr int UMMA_K = 8;              // kind::tf32
+constexpr int kThreads = 192;
+constexpr int A_TILE_BYTES = BM * BK * 4;
+
+template <int BN> struct Cfg {
+    static constexpr int B_TILE_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+    int M, N, K;
+    float alpha, beta;
+    float *C;
+    int64_t ldC;
+    int num_m, num_n, group_m;
+};
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         const GemmParams p)
+{
+    using C_ = Cfg<BN>;
+    constexpr int STAGES = C_::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + STAGES * A_TILE_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * C_::STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // grouped rasterisation: GROUP_M m-tiles share the same B panels while they are L2-resident
+    const int t = blockIdx.x;
+    const int tiles_per_group = p.group_m * p.num_n;
+    const int group = t / tiles_per_group;
+    const int first_m = group * p.group_m;
+    const int gsz = min(p.num_m - first_m, p.group_m);
+    const int tile_m = first_m + (t % tiles_per_group) % gsz;
+    const int tile_n = (t % tiles_per_group) / gsz;
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; s++) {
+                ptx::mbar_init(&full_bar[s], 1);
+                ptx::mbar_init(&empty_bar[s], 1);
+            }
+            ptx::mbar_init(tmem_full_bar, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, BN);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                ptx::mbar_arrive_expect_tx(&full_bar[s], C_::STAGE_BYTES);
+                const int k0 = kb * BK;
+                ptx::tma_load_2d(smem_a + s * A_TILE_BYTES, &map_a, &full_bar[s], k0, m0);
+                uint8_t *bdst = smem_b + s * C_::B_TILE_BYTES;
+                if (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; j++)
+                        ptx::tma_load_2d(bdst + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
+                } else {
+                    ptx::tma_load_2d(bdst, &map_b, &full_bar[s], k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, B_MN);
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                ptx::mbar_wait(&full_bar[s], ph);
+                ptx::tc_fence_after_sync();
+                const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_TILE_BYTES);
+                const uint32_t b_addr = ptx::smem_u32(smem_b + s * C_::B_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++) {
+                    // K-major, 128B swizzle: rows are 128 B apart, 8-row groups 1024 B apart; a K step
+                    // of 8 fp32 moves the start address 32 B inside the swizzled row.
+                    const uint64_t da = ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024);
+                    // MN-major, 128B swizzle: 32-column slabs are BK*128 B apart (leading offset), a K step
+                    // of 8 rows moves the start address 1024 B.
+                    const uint64_t db = B_MN ? ptx::make_smem_desc(b_addr + k * (UMMA_K * 128), BK * 128, 1024)
+                                             : ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024);
+                    ptx::mma_tf32_ss(tmem_base, da, db, idesc, (kb | k) != 0);
+                }
+                ptx::mma_commit(&empty_bar[s]);        // slab free once these MMAs retire
+            }
+            ptx::mma_commit(tmem_full_bar);            // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::tc_fence_after_sync();
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        float *crow = p.C + (size_t)row * p.ldC;
+        const bool use_c = p.beta != 0.0f;             // cuBLAS semantics: C not read when beta == 0
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            __syncwarp();                              // tcgen05.ld is .sync.aligned: whole warp, converged
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int col = n0 + c0 + j;
+                    if (col + 3 < p.N) {
+                        float4 o;
+                        o.x = __fmul_rn(__uint_as_float(r[j + 0]), p.alpha);
+                        o.y = __fmul_rn(__uint_as_float(r[j + 1]), p.alpha);
+                        o.z = __fmul_rn(__uint_as_float(r[j + 2]), p.alpha);
+                        o.w = __fmul_rn(__uint_as_float(r[j + 3]), p.alpha);
+                        float4 *dst = reinterpret_cast<float4 *>(crow + col);
+                        if (use_c) {
+                            const float4 c = *dst;
+                            o.x = __fadd_rn(o.x, __fmul_rn(c.x, p.beta));
+                            o.y = __fadd_rn(o.y, __fmul_rn(c.y, p.beta));
+                            o.z = __fadd_rn(o.z, __fmul_rn(c.z, p.beta));
+                            o.w = __fadd_rn(o.w, __fmul_rn(c.w, p.beta));
+                        }
+                        *dst = o;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (col + u < p.N) {
+                                float o = __fmul_rn(__uint_as_float(r[j + u]), p.alpha);
+                                if (use_c) o = __fadd_rn(o, __fmul_rn(crow[col + u], p.beta));
+                                crow[col + u] = o;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem_base, BN);
+    }
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <int BN, bool B_MN>
+int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, float alpha, float beta, int64_t ldA,
+              int64_t ldB, int64_t ldC)
+{
+    CUtensorMap map_a, map_b;
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        uint64_t str[1] = {(uint64_t)ldA * 4};
+        uint32_t box[2] = {BK, BM};
+        if (make_tensor_map_f32(&map_a, A, 2, dims, str, box)) return 1;
+    }
+    if (B_MN) {
+        uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
+        uint64_t str[1] = {(uint64_t)ldB * 4};
+        uint32_t box[2] = {32, BK};
+        if (make_tensor_map_f32(&map_b, B, 2, dims, str, box)) return 1;
+    } else {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)ldB * 4};
+        uint32_t box[2] = {BK, (uint32_t)BN};
+        if (make_tensor_map_f32(&map_b, B, 2, dims, str, box)) return 1;
+    }
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldC = ldC;
+    p.num_m = (M + BM - 1) / BM;
+    p.num_n = (N + BN - 1) / BN;
+    p.group_m = 16;
+    auto kern = tiramisu_sm100_gemm_tf32<BN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB200_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+        attr_set = true;
+    }
+    kern<<<p.num_m * p.num_n, kThreads, Cfg<BN>::SMEM_BYTES, stream()>>>(map_a, map_b, p);
+    return post_launch("tiramisu_sm100_gemm_tf32");
+}
+
+std::atomic<int> g_gemm_mode{0};
+
+}  // namespace
+
+namespace tb200 {
+
+int gemm_f32_exact(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha,
+                   float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tA, bool tB);
+
+// Can the tensor-core kernel address these operands?  TMA needs 16-byte aligned bases and row
+// pitches; the epilogue needs 16-byte aligned C rows.  A must be K-major (no transposeA).
+bool gemm_tc_addressable(const float *A, const float *B, const float *C, uint64_t M, uint64_t N, uint64_t K,
+                         uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tA, bool tB)
+{
+    (void)tB;
+    if (tA) return false;
+    if (M == 0 || N == 0 || K == 0) return false;
+    if (M > (1u << 30) || N > (1u << 30) || K > (1u << 30)) return false;
+    if (!aligned16(A) || !aligned16(B) || !aligned16(C)) return false;
+    if (ldA % 4 || ldB % 4 || ldC % 4) return false;
+    return true;
+}
+
+int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha,
+                float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tB)
+{
+    // Tile width: the widest BN that still yields at least one CTA per SM (148), else 64.
+    int bn = 64;
+    const uint64_t mt = (M + BM - 1) / BM;
+    const uint64_t sms = (uint64_t)sm_count();
+    if (mt * ((N + 255) / 256) >= sms) bn = 256;
+    else if (mt * ((N + 127) / 128) >= sms) bn = 128;
+    if (const char *e = getenv("TB200_GEMM_BN")) {
+        int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) bn = v;
+    }
+    const int m = (int)M, n = (int)N, k = (int)K;
+    if (tB) {
+        switch (bn) {
+        case 256: return launch_tc<256, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
+        case 128: return launch_tc<128, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
+        default: return launch_tc<64, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
+        }
+    }
+    switch (bn) {
+    case 256: return launch_tc<256, true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
+    case 128: return launch_tc<128, true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
+    default: return launch_tc<64, true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
+    }
+}
+
+int gemm_f32(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,
+             uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tA, bool tB)
+{
+    const int mode = g_gemm_mode.load();
+    const bool ok = gemm_tc_addressable(A, B, C, M, N, K, ldA, ldB, ldC, tA, tB);
+    if (mode == 2 && !ok) return fail("tiramisu_cublas_sgemm", "operands not addressable by the tcgen05 path");
+    if (mode != 1 && ok) return gemm_f32_tc(A, B, C, M, N, K, alpha, beta, ldA, ldB, ldC, tB);
+    return gemm_f32_exact(A, B, C, M, N, K, alpha, beta, ldA, ldB, ldC, tA, tB);
+}
+
+}  // namespace tb200
+
+TB200_API int tiramisu_b200_set_gemm_mode(int mode)
+{
+    if (mode < 0 || mode > 2) mode = 0;
+    return g_gemm_mode.exchange(mode);
+}
+
+TB200_API int tiramisu_cublas_sgemm(float *A, float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha,
+                                    float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, uint64_t offsetA,
+                                    uint64_t offsetB, uint64_t offsetC, bool transposeA, bool transposeB)
+{
+    if (!A || !B || !C) return fail(__func__, "null operand");
+    // src/tiramisu_cuda_wrappers.cpp:90-98: 0 means tightly packed
+    if (ldA == 0) ldA = transposeA ? M : K;
+    if (ldB == 0) ldB = transposeB ? K : N;
+    if (ldC == 0) ldC = N;
+    if (M == 0 || N == 0) return 0;
+    return gemm_f32(A + offsetA, B + offsetB, C + offsetC, M, N, K, alpha, beta, ldA, ldB, ldC, transposeA,
+                    transposeB);
+}

@@ -1,0 +1,362 @@
+// stencil.cu — HBM-bound 2D stencils of the hot path: heat2d (5-point) and the 3x3 separable
+// blurs (fp32 / uint8 / uint32).  Replaces the kernels the reference's cuda_ast emitter prints
+// for benchmarks/halide/heat2dgpu_tiramisu.cpp (32x32 smem tiles, 30x30 useful, scalar loads)
+// and restates the CPU-only blurxy / boxblur computations for the GPU.
+//
+// Design (sm_100a, HBM-bound): one thread owns a 4-wide column strip for RY consecutive output
+// rows; it issues all RY+2 128-bit row loads up front (memory-level parallelism), gets the
+// east/west neighbours of the centre row by warp shuffle (only the two edge lanes of a warp
+// touch memory again), and streams 128-bit results out with evict-first stores.  Input is read
+// ~(RY+2)/RY times from L2 and once from HBM; output is written once.  No shared memory: the
+// reuse window (3 rows x 4 columns) fits in registers.
+//
+// Arithmetic is done with __fmul_rn/__fadd_rn/__fdiv_rn in the reference's association order so
+// that fp32 results are bit-identical to the x86 path (which has no FMA,
+// src/tiramisu_codegen_halide.cpp:3988-3995).
+#include "common.cuh"
+#include "tiramisu_b200.h"
+
+using namespace tb200;
+
+namespace {
+
+constexpr float kAlpha = 0.3f;   // heat2d_tiramisu.cpp:26
+constexpr float kBeta = 0.4f;    // heat2d_tiramisu.cpp:27
+
+template <int FORM>
+__device__ __forceinline__ float heat_point(float c, float n, float s, float w, float e)
+{
+    if (FORM == 0) {            // heat2d_tiramisu.cpp:68   a*c + b*(((E+W)+S)+N)
+        float t = __fadd_rn(__fadd_rn(__fadd_rn(e, w), s), n);
+        return __fadd_rn(__fmul_rn(kAlpha, c), __fmul_rn(kBeta, t));
+    } else if (FORM == 1) {     // heat2dgpu_tiramisu.cpp:54 c*a + (((S+E)+N)+W)*b
+        float t = __fadd_rn(__fadd_rn(__fadd_rn(s, e), n), w);
+        return __fadd_rn(__fmul_rn(c, kAlpha), __fmul_rn(t, kBeta));
+    } else {                    // heat2d_dist_tiramisu.cpp:88 c*a + (((N+S)+W)+E)*b
+        float t = __fadd_rn(__fadd_rn(__fadd_rn(n, s), w), e);
+        return __fadd_rn(__fmul_rn(c, kAlpha), __fmul_rn(t, kBeta));
+    }
+}
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// ------------------------------------------------------------------------------------------------
+// heat2d, vector path: W % 4 == 0, 16-byte aligned rows.  grid = (ceil(W/4/128), ceil(rows/RY)).
+template <int FORM, int RY>
+__global__ void __launch_bounds__(128)
+tiramisu_sm100_heat2d_v4(const float *__restrict__ in, float *__restrict__ out, int H, int W,
+                         int row_begin, int row_end)
+{
+    const int lane = threadIdx.x & 31;
+    const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int y0 = row_begin + blockIdx.y * RY;
+    const bool col_ok = x < W;
+    const size_t Ws = (size_t)W;
+
+    // rows y0-1 .. y0+RY, all loads in flight before first use
+    float4 v[RY + 2];
+#pragma unroll
+    for (int r = 0; r < RY + 2; r++) {
+        const int y = y0 - 1 + r;
+        v[r] = (col_ok && y >= 0 && y < H && y <= row_end) ? ldg4(in + (size_t)y * Ws + x)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // west/east halo of the centre rows for the warp's edge lanes
+    float wl[RY], er[RY];
+#pragma unroll
+    for (int r = 0; r < RY; r++) {
+        const int y = y0 + r;
+        const bool row_ok = y < row_end && y < H;
+        wl[r] = (lane == 0 && col_ok && row_ok && x > 0) ? __ldg(in + (size_t)y * Ws + x - 1) : 0.f;
+        er[r] = (lane == 31 && col_ok && row_ok && x + 4 < W) ? __ldg(in + (size_t)y * Ws + x + 4) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < RY; r++) {
+        const int y = y0 + r;
+        const float4 c = v[r + 1], n = v[r], s = v[r + 2];
+        float wv = __shfl_up_sync(0xffffffffu, c.w, 1);
+        float ev = __shfl_down_sync(0xffffffffu, c.x, 1);
+        if (lane == 0) wv = wl[r];
+        if (lane == 31) ev = er[r];
+        if (!col_ok || y >= row_end || y >= H) continue;
+        float4 o;
+        o.x = heat_point<FORM>(c.x, n.x, s.x, wv, c.y);
+        o.y = heat_point<FORM>(c.y, n.y, s.y, c.x, c.z);
+        o.z = heat_point<FORM>(c.z, n.z, s.z, c.y, c.w);
+        o.w = heat_point<FORM>(c.w, n.w, s.w, c.z, ev);
+        float4 *dst = reinterpret_cast<float4 *>(out + (size_t)y * Ws + x);
+        if (FORM == 2) {
+            // Jacobi half-step: border cells of `out` keep their previous value
+            if (y == 0 || y == H - 1) continue;
+            if (x == 0 || x + 4 == W) {
+                float4 old = *dst;
+                if (x == 0) o.x = old.x;
+                if (x + 4 == W) o.w = old.w;
+            }
+        } else {
+            if (y == 0 || y == H - 1) o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (x == 0) o.x = 0.f;
+            if (x + 4 == W) o.w = 0.f;
+        }
+        __stcs(dst, o);
+    }
+}
+
+// heat2d, generic path (any W, any alignment): one thread per output element.
+template <int FORM>
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_heat2d_scalar(const float *__restrict__ in, float *__restrict__ out, int H, int W,
+                             int row_begin, int row_end)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = row_begin + blockIdx.y;
+    if (x >= W || y >= row_end) return;
+    const size_t i = (size_t)y * W + x;
+    const bool border = (y == 0 || y == H - 1 || x == 0 || x == W - 1);
+    if (border) {
+        if (FORM != 2) out[i] = 0.f;
+        return;
+    }
+    out[i] = heat_point<FORM>(__ldg(in + i), __ldg(in + i - W), __ldg(in + i + W), __ldg(in + i - 1),
+                              __ldg(in + i + 1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 blur (SURVEY.md §8 a8', restating blurxy_tiramisu.cpp:61,77 in fp32):
+//   bx  = ((in[y][x] + in[y][x+1]) + in[y][x+2]) / 3.0f ;  out = ((bx[y] + bx[y+1]) + bx[y+2]) / 3.0f
+// Vector path: W % 4 == 0 and 16-byte aligned input rows; output rows are (W-2) wide, so stores are
+// 8-byte aligned pairs.  A thread owns input columns [x, x+4) and produces output columns [x, x+4).
+__device__ __forceinline__ float blur3(float a, float b, float c)
+{
+    return __fdiv_rn(__fadd_rn(__fadd_rn(a, b), c), 3.0f);
+}
+
+template <int RY>
+__global__ void __launch_bounds__(128)
+tiramisu_sm100_blur_f32_v4(const float *__restrict__ in, float *__restrict__ out, int H, int W,
+                           int row_begin, int row_end)
+{
+    const int lane = threadIdx.x & 31;
+    const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int y0 = row_begin + blockIdx.y * RY;
+    const int OW = W - 2;
+    const bool col_ok = x < W;
+    const size_t Ws = (size_t)W;
+
+    float4 v[RY + 2];
+    float e0[RY + 2], e1[RY + 2];
+#pragma unroll
+    for (int r = 0; r < RY + 2; r++) {
+        const int y = y0 + r;
+        const bool ok = col_ok && y < H && y < row_end + 2;
+        v[r] = ok ? ldg4(in + (size_t)y * Ws + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool edge = ok && lane == 31 && x + 4 < W;      // W % 4 == 0 => x+5 < W too
+        e0[r] = edge ? __ldg(in + (size_t)y * Ws + x + 4) : 0.f;
+        e1[r] = edge ? __ldg(in + (size_t)y * Ws + x + 5) : 0.f;
+    }
+    float4 bx[RY + 2];
+#pragma unroll
+    for (int r = 0; r < RY + 2; r++) {
+        float n0 = __shfl_down_sync(0xffffffffu, v[r].x, 1);
+        float n1 = __shfl_down_sync(0xffffffffu, v[r].y, 1);
+        if (lane == 31) { n0 = e0[r]; n1 = e1[r]; }
+        bx[r].x = blur3(v[r].x, v[r].y, v[r].z);
+        bx[r].y = blur3(v[r].y, v[r].z, v[r].w);
+        bx[r].z = blur3(v[r].z, v[r].w, n0);
+        bx[r].w = blur3(v[r].w, n0, n1);
+    }
+#pragma unroll
+    for (int r = 0; r < RY; r++) {
+        const int y = y0 + r;
+        if (!col_ok || y >= row_end || y >= H - 2) continue;
+        float4 o;
+        o.x = blur3(bx[r].x, bx[r + 1].x, bx[r + 2].x);
+        o.y = blur3(bx[r].y, bx[r + 1].y, bx[r + 2].y);
+        o.z = blur3(bx[r].z, bx[r + 1].z, bx[r + 2].z);
+        o.w = blur3(bx[r].w, bx[r + 1].w, bx[r + 2].w);
+        float *dst = out + (size_t)y * OW + x;
+        __stcs(reinterpret_cast<float2 *>(dst), make_float2(o.x, o.y));
+        if (x + 2 < OW) __stcs(reinterpret_cast<float2 *>(dst + 2), make_float2(o.z, o.w));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_blur_f32_scalar(const float *__restrict__ in, float *__restrict__ out, int H, int W,
+                               int row_begin, int row_end)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = row_begin + blockIdx.y;
+    const int OW = W - 2;
+    if (x >= OW || y >= row_end || y >= H - 2) return;
+    float bx[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const float *q = in + (size_t)(y + r) * W + x;
+        bx[r] = blur3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+    }
+    out[(size_t)y * OW + x] = blur3(bx[0], bx[1], bx[2]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// uint8 blurxy (blurxy_tiramisu.cpp:61,77): every + and / is uint8 arithmetic (sums wrap mod 256).
+// One thread produces 4 consecutive output pixels of one row (6 input bytes from each of 3 rows).
+__device__ __forceinline__ unsigned blur3_u8(unsigned a, unsigned b, unsigned c)
+{
+    return (((((a + b) & 0xffu) + c) & 0xffu) / 3u);
+}
+
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_blurxy_u8(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int C, int H, int W)
+{
+    const int OH = H - 8, OW = W - 8;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    const int c = blockIdx.z;
+    if (x >= OW || y >= OH || c >= C) return;
+    const int nx = min(4, OW - x);
+    unsigned bx[3][4];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const uint8_t *q = in + ((size_t)c * H + (y + r)) * W + x;
+        unsigned p[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) p[k] = (k < nx + 2) ? (unsigned)__ldg(q + k) : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) bx[r][k] = blur3_u8(p[k], p[k + 1], p[k + 2]);
+    }
+    uint8_t *o = out + ((size_t)c * OH + y) * OW + x;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < nx) o[k] = (uint8_t)blur3_u8(bx[0][k], bx[1][k], bx[2][k]);
+}
+
+// uint32 box blur, vertical pass first (tests/test_160.cpp:23-29):
+//   bx[i][j] = (in[i][j]+in[i+1][j]+in[i+2][j])/3 ; out[i][j] = (bx[i][j]+bx[i][j+1]+bx[i][j+2])/3
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_boxblur_u32(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int rows, int cols)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= cols || i >= rows) return;
+    const int IW = cols + 2;
+    uint32_t bx[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const uint32_t *q = in + (size_t)i * IW + j + d;
+        bx[d] = ((__ldg(q) + __ldg(q + IW)) + __ldg(q + 2 * (size_t)IW)) / 3u;
+    }
+    out[(size_t)i * cols + j] = ((bx[0] + bx[1]) + bx[2]) / 3u;
+}
+
+__global__ void __launch_bounds__(256) tiramisu_sm100_fill_i32(int32_t *buf, uint64_t n, int32_t v)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        buf[i] = v;
+}
+
+// 32x32 smem-tiled transpose (tests/test_168.cpp: B[j][i] = A[i][j]).
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_transpose_f32(const float *__restrict__ A, float *__restrict__ At, int rows, int cols)
+{
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int y = by + r, x = bx + threadIdx.x;
+        if (y < rows && x < cols) tile[r][threadIdx.x] = A[(size_t)y * cols + x];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int y = bx + r, x = by + threadIdx.x;     // transposed coordinates
+        if (y < cols && x < rows) At[(size_t)y * rows + x] = tile[threadIdx.x][r];
+    }
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+constexpr int kHeatRY = 8;
+constexpr int kBlurRY = 6;
+
+template <int FORM>
+int launch_heat2d(const float *in, float *out, int H, int W, int rb, int re)
+{
+    const int rows = re - rb;
+    if (rows <= 0) return 0;
+    if (W % 4 == 0 && aligned16(in) && aligned16(out)) {
+        dim3 grid((W / 4 + 127) / 128, (rows + kHeatRY - 1) / kHeatRY);
+        tiramisu_sm100_heat2d_v4<FORM, kHeatRY><<<grid, 128, 0, stream()>>>(in, out, H, W, rb, re);
+        return post_launch("tiramisu_sm100_heat2d_v4");
+    }
+    dim3 grid((W + 255) / 256, rows);
+    tiramisu_sm100_heat2d_scalar<FORM><<<grid, 256, 0, stream()>>>(in, out, H, W, rb, re);
+    return post_launch("tiramisu_sm100_heat2d_scalar");
+}
+
+}  // namespace
+
+TB200_API int tiramisu_b200_heat2d(const float *in, float *out, int32_t H, int32_t W, int32_t form,
+                                   int32_t row_begin, int32_t row_end)
+{
+    if (!in || !out || H < 1 || W < 1 || row_begin < 0 || row_end > H || form < 0 || form > 2)
+        return fail(__func__, "bad argument");
+    if ((int64_t)row_end - row_begin > 65535LL * kHeatRY && W % 4 != 0)
+        return fail(__func__, "grid too tall for the scalar path");
+    switch (form) {
+    case 0: return launch_heat2d<0>(in, out, H, W, row_begin, row_end);
+    case 1: return launch_heat2d<1>(in, out, H, W, row_begin, row_end);
+    default: return launch_heat2d<2>(in, out, H, W, row_begin, row_end);
+    }
+}
+
+TB200_API int tiramisu_b200_blur_f32(const float *in, float *out, int32_t H, int32_t W,
+                                     int32_t row_begin, int32_t row_end)
+{
+    if (!in || !out || H < 3 || W < 3 || row_begin < 0 || row_end > H - 2)
+        return fail(__func__, "bad argument");
+    const int rows = row_end - row_begin;
+    if (rows <= 0) return 0;
+    if (W % 4 == 0 && aligned16(in) && aligned8(out)) {
+        dim3 grid((W / 4 + 127) / 128, (rows + kBlurRY - 1) / kBlurRY);
+        tiramisu_sm100_blur_f32_v4<kBlurRY><<<grid, 128, 0, stream()>>>(in, out, H, W, row_begin, row_end);
+        return post_launch("tiramisu_sm100_blur_f32_v4");
+    }
+    if (rows > 65535) return fail(__func__, "grid too tall for the scalar path");
+    dim3 grid((W - 2 + 255) / 256, rows);
+    tiramisu_sm100_blur_f32_scalar<<<grid, 256, 0, stream()>>>(in, out, H, W, row_begin, row_end);
+    return post_launch("tiramisu_sm100_blur_f32_scalar");
+}
+
+TB200_API int tiramisu_b200_blurxy_u8(const uint8_t *in, uint8_t *out, int32_t C, int32_t H, int32_t W)
+{
+    if (!in || !out || C < 1 || H < 9 || W < 9 || H - 8 > 65535 || C > 65535)
+        return fail(__func__, "bad argument");
+    dim3 grid(((W - 8 + 3) / 4 + 255) / 256, H - 8, C);
+    tiramisu_sm100_blurxy_u8<<<grid, 256, 0, stream()>>>(in, out, C, H, W);
+    return post_launch("tiramisu_sm100_blurxy_u8");
+}
+
+TB200_API int tiramisu_b200_boxblur_u32(const uint32_t *in, uint32_t *out, int32_t rows, int32_t cols)
+{
+    if (!in || !out || rows < 1 || cols < 1 || rows > 65535) return fail(__func__, "bad argument");
+    dim3 grid((cols + 255) / 256, rows);
+    tiramisu_sm100_boxblur_u32<<<grid, 256, 0, stream()>>>(in, out, rows, cols);
+    return post_launch("tiramisu_sm100_boxblur_u32");
+}
+
+TB200_API int tiramisu_b200_fill_i32(int32_t *buf, uint64_t n, int32_t value)
+{
+    if (!buf && n) return fail(__func__, "bad argument");
+    if (n == 0) return 0;
+    uint64_t want = (n + 255) / 256, cap = (uint64_t)sm_count() * 8;
+    const int blocks = (int)(want < cap ? want : cap);
+    tiramisu_sm100_fill_i32<<<blocks, 256, 0, stream()>>>(buf, n, value);
+    return post_launch("tiramisu_sm100_fill_i32");
+}
+
+TB200_API int tiramisu_b200_transpose_f32(const float *A, float *At, int32_t rows, int32_t cols)
+{
+    if (!A || !At || rows < 1 || cols < 1) return fail(__func__, "bad argument");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    tiramisu_sm100_transpose_f32<<<grid, dim3(32, 8), 0, stream()>>>(A, At, rows, cols);
+    return post_launch("tiramisu_sm100_transpose_f32");
+}
