@@ -112,6 +112,20 @@ int tiramisu_b200_matmul_u8(const uint8_t *A, const uint8_t *B, uint8_t *C, int3
 int tiramisu_b200_fill_i32(int32_t *buf, uint64_t n, int32_t value);
 int tiramisu_b200_transpose_f32(const float *A, float *At, int32_t rows, int32_t cols);
 
+/* conv(3x3)+ReLU+maxpool(2x2) block (conv_relu_maxpool_generator_tiramisu.cpp:28-49):
+ * input f32[B][N+2][N+2][FIn] pre-padded NHWC, filter f32[FOut/8][3][3][FIn][8], bias f32[FOut],
+ * output f32[B][FOut/8][N/2][N/2][8].  tcgen05 implicit GEMM (TF32) when FIn % 32 == 0, FOut == 64,
+ * N % 32 == 0; else an fp32 SIMT kernel in the reference's accumulation order (bit-exact). */
+int tiramisu_b200_conv_relu_maxpool(const float *input, const float *filter, const float *bias,
+                                    float *output, int32_t B, int32_t N, int32_t FIn, int32_t FOut);
+/* 0 auto, 1 exact fp32 SIMT, 2 force tcgen05.  Returns the previous mode. */
+int tiramisu_b200_set_conv_mode(int mode);
+/* Multi-layer LSTM forward (LSTM/cpu/generator.cpp:35-53): Weights f32[L][2][4F][F] (0 = R, 1 = W),
+ * biases f32[L][4F], x,y f32[T][B][F]; gate rows i,z,o,f. */
+int tiramisu_b200_lstm(const float *Weights, const float *biases, const float *x, float *y,
+                       int32_t F, int32_t B, int32_t L, int32_t T);
+int tiramisu_b200_set_lstm_mode(int mode);
+
 /* ===================================================================== B1: generated functions */
 /* benchmarks/halide/wrapper_heat2d.h:10 — in,out f32[H][W] (reference bakes 10000x10000). */
 int heat2d_tiramisu(halide_buffer_t *in, halide_buffer_t *out);
@@ -133,6 +147,12 @@ int sgemm_tiramisu(halide_buffer_t *SIZES, halide_buffer_t *alpha, halide_buffer
  * time_start/time_end f32[1] receive get_time() around the kernel when the caller provides it. */
 int matmul(halide_buffer_t *Consts, halide_buffer_t *A, halide_buffer_t *B, halide_buffer_t *C,
            halide_buffer_t *time_start, halide_buffer_t *time_end);
+/* benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/wrapper_nn_block.cpp:43-48 */
+int conv_relu_maxpool_block(halide_buffer_t *input, halide_buffer_t *filter, halide_buffer_t *bias,
+                            halide_buffer_t *output);
+/* benchmarks/DNN/blocks/LSTM/cpu/wrapper.h:6-10 — params i32[4] = {F, B, L, T} */
+int lstm(halide_buffer_t *params, halide_buffer_t *Weights, halide_buffer_t *biases, halide_buffer_t *x,
+         halide_buffer_t *y);
 /* tests/wrapper_test_162.h..167.h — cublas_gemm / gpu_tile GEMM feature tests. */
 int test_162(halide_buffer_t *sizes, halide_buffer_t *params, halide_buffer_t *A,
              halide_buffer_t *B, halide_buffer_t *C);

@@ -33,7 +33,8 @@ def test_header_declares_the_reference_symbols():
     for must in ("tiramisu_cuda_malloc", "tiramisu_cuda_free", "tiramisu_cuda_memcpy_to_device",
                  "tiramisu_cuda_memcpy_to_host", "tiramisu_cublas_sgemm", "tiramisu_cublas_dgemm",
                  "tiramisu_cuda_stream_synchronize", "tiramisu_address_of_float32", "heat2d_tiramisu",
-                 "heat2dgpu_tiramisu", "blurxy_tiramisu", "boxblur", "sgemm_tiramisu", "matmul"):
+                 "heat2dgpu_tiramisu", "blurxy_tiramisu", "boxblur", "sgemm_tiramisu", "matmul",
+                 "conv_relu_maxpool_block", "lstm"):
         assert must in names, must
 
 

@@ -1,0 +1,142 @@
+"""GPU parity of the DNN blocks (conv+ReLU+maxpool, LSTM) against the CPU oracle — through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import refdata
+
+pytestmark = pytest.mark.gpu
+
+TF32_RTOL = 1e-2          # TF32 tensor-core paths
+FP32_RTOL = 1e-5          # fp32-exact paths
+
+
+@pytest.fixture(scope="module")
+def api():
+    from tiramisu_b200 import api as _api
+    return _api
+
+
+def _rel(got, want):
+    return float(np.abs(got.astype(np.float64) - want).max() / max(1e-30, np.abs(want).max()))
+
+
+def _conv(api, inp, filt, bias):
+    B, NP, _, FIn = inp.shape
+    FB = filt.shape[0]
+    N = NP - 2
+    out = np.full((B, FB, N // 2, N // 2, 8), np.nan, np.float32)
+    api.conv_relu_maxpool_block(inp, filt, bias, out)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ conv
+@pytest.mark.parametrize("B,N,FIn,FOut", [(2, 16, 3, 16), (1, 8, 5, 8), (3, 10, 3, 32), (1, 32, 32, 64)])
+def test_conv_exact_mode_bit_exact(api, B, N, FIn, FOut):
+    """fp32 SIMT path in the reference's (bias; ky,kx,fin) order == oracle bit for bit.  The first
+    shape family is the reference's own default (FIn=3, configure.h:23-26)."""
+    prev = api.set_conv_mode(1)
+    try:
+        inp, filt, bias = refdata.conv_inputs(B, N, FIn, FOut)
+        assert np.array_equal(_conv(api, inp, filt, bias), oracle.conv_relu_maxpool(inp, filt, bias))
+    finally:
+        api.set_conv_mode(prev)
+
+
+@pytest.mark.parametrize("B,N,FIn", [(2, 32, 32), (1, 64, 64), (3, 96, 64)])
+def test_conv_tensor_path_small_ints_exact(api, B, N, FIn):
+    """Integer-valued operands are exact in TF32 with fp32 accumulation => equality with the oracle
+    checks the im2col addressing, the pooling shuffles and the output layout, not rounding."""
+    prev = api.set_conv_mode(2)
+    try:
+        rng = np.random.default_rng(3)
+        inp = rng.integers(-4, 5, (B, N + 2, N + 2, FIn)).astype(np.float32)
+        filt = rng.integers(-3, 4, (8, 3, 3, FIn, 8)).astype(np.float32)
+        bias = rng.integers(-8, 9, 64).astype(np.float32)
+        assert np.array_equal(_conv(api, inp, filt, bias), oracle.conv_relu_maxpool(inp, filt, bias))
+    finally:
+        api.set_conv_mode(prev)
+
+
+@pytest.mark.parametrize("B,N,FIn", [(2, 32, 64), (1, 64, 32)])
+def test_conv_tensor_path_wrapper_data(api, B, N, FIn):
+    """wrapper_nn_block.cpp:15-39 initialisation (srand(1), rand()%256-128)/127.f), TF32 tolerance."""
+    prev = api.set_conv_mode(2)
+    try:
+        inp, filt, bias = refdata.conv_inputs(B, N, FIn, 64)
+        got = _conv(api, inp, filt, bias)
+        want = oracle.conv_relu_maxpool(inp, filt, bias)
+        assert _rel(got, want) < TF32_RTOL
+        assert (got >= 0).all()
+    finally:
+        api.set_conv_mode(prev)
+
+
+def test_conv_config3_full_size(api):
+    """BASELINE config 3 (B=32, 224x224, 64->64) device-resident; the oracle checks images 0 and 31."""
+    import torch
+    B, N, FIn, FOut = 32, 224, 64, 64
+    rng = np.random.default_rng(33)
+    filt = (rng.integers(-128, 128, (8, 3, 3, FIn, 8)) / 127.0).astype(np.float32)
+    bias = (rng.integers(-128, 128, FOut) / 127.0).astype(np.float32)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    d_in = torch.rand((B, N + 2, N + 2, FIn), device="cuda", generator=g) * 2 - 1
+    d_f, d_b = torch.from_numpy(filt).cuda(), torch.from_numpy(bias).cuda()
+    d_out = torch.full((B, 8, N // 2, N // 2, 8), float("nan"), device="cuda")
+    api.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        api.conv_relu_maxpool_block(d_in, d_f, d_b, d_out)
+        torch.cuda.synchronize()
+    finally:
+        api.set_stream(None)
+    assert bool(torch.isfinite(d_out).all())
+    for n in (0, 31):
+        want = oracle.conv_relu_maxpool(d_in[n:n + 1].cpu().numpy(), filt, bias)
+        assert _rel(d_out[n:n + 1].cpu().numpy(), want) < TF32_RTOL
+
+
+# ------------------------------------------------------------------------------------------ LSTM
+def _lstm(api, W, b, x):
+    L, _, F4, F = W.shape
+    T, B, _ = x.shape
+    y = np.full_like(x, np.nan)
+    api.lstm(np.array([F, B, L, T], np.int32), W, b, x, y)
+    return y
+
+
+@pytest.mark.parametrize("F,B,L,T", [(32, 8, 4, 10), (20, 3, 2, 5), (64, 16, 1, 3)])
+def test_lstm_exact_mode(api, F, B, L, T):
+    """fp32 SIMT path in the reference's interleaved-j order; expf/tanhf differ from libm by ulps."""
+    prev = api.set_lstm_mode(1)
+    try:
+        W, b, x = refdata.lstm_inputs(F, B, L, T, scale=4.0)       # (32,8,4,10): LSTM/cpu/README.md:3
+        got = _lstm(api, W, b, x)
+        want = oracle.lstm(W, b, x)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=FP32_RTOL)
+    finally:
+        api.set_lstm_mode(prev)
+
+
+@pytest.mark.parametrize("F,B,L,T,scale", [(64, 16, 2, 5, 4.0), (128, 64, 4, 8, 8.0), (256, 100, 2, 3, 8.0),
+                                           (1024, 64, 4, 3, 32.0)])
+def test_lstm_tensor_path(api, F, B, L, T, scale):
+    """tcgen05 path (batched input GEMM + per-step recurrent GEMM with fused gates), TF32 tolerance.
+    Weights are scaled so the gates are not saturated."""
+    prev = api.set_lstm_mode(2)
+    try:
+        W, b, x = refdata.lstm_inputs(F, B, L, T, scale=scale)
+        got = _lstm(api, W, b, x)
+        want = oracle.lstm(W, b, x)
+        assert np.isfinite(got).all()
+        assert float(np.abs(got - want).max()) < TF32_RTOL * max(1.0, float(np.abs(want).max()))
+    finally:
+        api.set_lstm_mode(prev)
+
+
+def test_lstm_wrapper_data_saturated(api):
+    """The reference wrapper's raw initialisation (LSTM/cpu/wrapper.cpp:31-52, no scaling)."""
+    W, b, x = refdata.lstm_inputs(64, 8, 2, 6)
+    got = _lstm(api, W, b, x)
+    want = oracle.lstm(W, b, x)
+    # the reference itself accepts |diff| < 0.02 against MKL-DNN (cpu/wrapper.cpp:107)
+    assert float(np.abs(got - want).max()) < 0.02

@@ -76,7 +76,11 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_matmul_u8", C.c_int, vp, vp, vp, i32)
     sig("tiramisu_b200_fill_i32", C.c_int, vp, u64, i32)
     sig("tiramisu_b200_transpose_f32", C.c_int, vp, vp, i32, i32)
-    for name, n in (("heat2d_tiramisu", 2), ("heat2dgpu_tiramisu", 3), ("blurxy_tiramisu", 2),
+    sig("tiramisu_b200_conv_relu_maxpool", C.c_int, vp, vp, vp, vp, i32, i32, i32, i32)
+    sig("tiramisu_b200_set_conv_mode", C.c_int, C.c_int)
+    sig("tiramisu_b200_lstm", C.c_int, vp, vp, vp, vp, i32, i32, i32, i32)
+    sig("tiramisu_b200_set_lstm_mode", C.c_int, C.c_int)
+    for name, n in (("conv_relu_maxpool_block", 4), ("lstm", 5), ("heat2d_tiramisu", 2), ("heat2dgpu_tiramisu", 3), ("blurxy_tiramisu", 2),
                     ("blurxy_f32_tiramisu", 2), ("boxblur", 2), ("blurautodist_tiramisu", 2),
                     ("sgemm_tiramisu", 6), ("matmul", 6), ("test_162", 5), ("test_164", 6), ("test_167", 3),
                     ("test_168", 2), ("test_197", 2)):

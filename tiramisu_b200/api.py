@@ -84,6 +84,26 @@ def test_197(A, B):
     _call("test_197", A, B)
 
 
+# ---- DNN blocks -------------------------------------------------------------------------------------
+def conv_relu_maxpool_block(inp, filt, bias, out):
+    """Conv-ReLU-MaxPool/cpu/dense/wrapper_nn_block.cpp:43-48 — input f32[B][N+2][N+2][FIn],
+    filter f32[FOut/8][3][3][FIn][8], bias f32[FOut], output f32[B][FOut/8][N/2][N/2][8]."""
+    _call("conv_relu_maxpool_block", inp, filt, bias, out)
+
+
+def lstm(params, Weights, biases, x, y):
+    """LSTM/cpu/wrapper.h:6-10 — params i32[4] = {F, B, L, T}; Weights f32[L][2][4F][F]."""
+    _call("lstm", params, Weights, biases, x, y)
+
+
+def set_conv_mode(mode: int) -> int:
+    return int(_lib.lib().tiramisu_b200_set_conv_mode(mode))
+
+
+def set_lstm_mode(mode: int) -> int:
+    return int(_lib.lib().tiramisu_b200_set_lstm_mode(mode))
+
+
 # ---- B2 runtime, for callers that manage device memory themselves ------------------------------------
 def set_stream(cuda_stream: int | None) -> None:
     """Launch on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); None = per-thread default."""

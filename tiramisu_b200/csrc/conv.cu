@@ -1,0 +1,337 @@
+// conv.cu — the DNN conv(3x3) + ReLU + maxpool(2x2) block of
+// /root/reference/benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/conv_relu_maxpool_generator_tiramisu.cpp
+//   input  f32[B][N+2][N+2][FIn]  (pre-padded NHWC)        filter f32[FOut/8][3][3][FIn][8]
+//   bias   f32[FOut]                                       output f32[B][FOut/8][N/2][N/2][8]
+//   out = max(0, max over the 2x2 window of (bias + sum_{ky,kx,fin} in*w))      (:28-49)
+//
+// Two paths:
+//  * tiramisu_sm100_conv_block_exact — fp32 SIMT, accumulation in the reference's order
+//    (acc = bias; ky, kx, fin; separately rounded multiply and add) => bit-identical to the x86
+//    code.  Any shape.
+//  * tiramisu_sm100_conv_block_tf32 — implicit GEMM on tcgen05 (M = 128 pixels = 4 rows x 32
+//    columns, N = FOut, K = 9*FIn), TF32 inputs, fp32 accumulators in TMEM:
+//      - the im2col is done by TMA: for each filter tap (ky,kx) and 32-channel slab the producer
+//        issues four 4-D box loads {32 ch, 16 x, 2 y, 1 n} from the padded NHWC input, shifted by
+//        (kx, ky); each box is one 2x16-pixel patch = 32 accumulator rows = one epilogue warp.
+//      - the packed filter (9*FIn/32 slabs of FOut x 32, K-major) stays resident in shared memory
+//        for the whole persistent CTA; only activations stream through the 4-stage ring.
+//      - two accumulator buffers in TMEM: the epilogue of tile i overlaps the MMAs of tile i+1.
+//      - epilogue: tcgen05.ld, 2x2 max-pool with warp shuffles (the pool partners are lanes
+//        l^1 and l^16 of the same warp by construction of the boxes), + bias, ReLU, 32-byte stores
+//        straight into the blocked [FOut/8][..][8] output layout.  The conv output (4x larger
+//        than the pooled one) never touches HBM.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tiramisu_b200.h"
+
+using namespace tb200;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ exact SIMT
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_conv_block_exact(const float *__restrict__ in, const float *__restrict__ w,
+                                const float *__restrict__ bias, float *__restrict__ out, int B, int N, int FIn,
+                                int FOut)
+{
+    const int NO = N / 2, NP = N + 2, FB = FOut / 8;
+    const size_t total = (size_t)B * FB * NO * NO * 8;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (size_t)gridDim.x * blockDim.x) {
+        const int ff = (int)(o % 8);
+        size_t t = o / 8;
+        const int px = (int)(t % NO); t /= NO;
+        const int py = (int)(t % NO); t /= NO;
+        const int fb = (int)(t % FB);
+        const int n = (int)(t / FB);
+        float best = 0.0f;                                   // init_output: 0  (=> ReLU)
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                const int y = 2 * py + dy, x = 2 * px + dx;
+                float acc = bias[fb * 8 + ff];               // conv_init
+                for (int ky = 0; ky < 3; ky++)
+                    for (int kx = 0; kx < 3; kx++) {
+                        const float *ip = in + (((size_t)n * NP + (y + ky)) * NP + (x + kx)) * FIn;
+                        const float *wp = w + ((((size_t)fb * 3 + ky) * 3 + kx) * FIn) * 8 + ff;
+                        for (int c = 0; c < FIn; c++) acc = __fadd_rn(acc, __fmul_rn(__ldg(ip + c), __ldg(wp + c * 8)));
+                    }
+                best = fmaxf(best, acc);                     // maxpool: max(out, conv)
+            }
+        out[o] = best;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tcgen05 path
+constexpr int BK = 32;                       // channels per K slab (128 B)
+constexpr int UMMA_K = 8;
+constexpr int A_STAGES = 4;
+constexpr int A_TILE_BYTES = 128 * BK * 4;   // 16 KB: 4 boxes of 32 pixels x 128 B
+constexpr int kConvThreads = 192;
+
+// filter [FOut/8][3][3][FIn][8]  ->  Wp[(tap*KH + h)][fout][32]   (K-major slabs for the B operand)
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_conv_pack_filter(const float *__restrict__ w, float *__restrict__ wp, int FIn, int FOut)
+{
+    const int KH = FIn / BK;
+    const int total = 9 * KH * FOut * BK;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % BK;
+        int t = i / BK;
+        const int fo = t % FOut; t /= FOut;
+        const int h = t % KH;
+        const int tap = t / KH;
+        wp[i] = w[((((size_t)(fo / 8) * 9 + tap) * FIn) + (h * BK + c)) * 8 + (fo % 8)];
+    }
+}
+
+struct ConvParams {
+    int B, N, FIn, FOut;
+    int tiles_y, tiles_x, num_tiles;
+    const float *bias;
+    float *out;
+};
+
+template <int FOUT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+                               const ConvParams p)
+{
+    constexpr int W_SLAB_BYTES = FOUT * BK * 4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int KH = p.FIn / BK;
+    const int num_slabs = 9 * KH;
+    uint8_t *smem_w = smem;
+    uint8_t *smem_a = smem + num_slabs * W_SLAB_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_a + A_STAGES * A_TILE_BYTES);
+    uint64_t *empty_bar = full_bar + A_STAGES;
+    uint64_t *w_bar = empty_bar + A_STAGES;
+    uint64_t *tmem_full = w_bar + 1;        // [2]
+    uint64_t *tmem_empty = tmem_full + 2;   // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_in);
+        ptx::prefetch_tensormap(&map_w);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < A_STAGES; s++) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+            ptx::mbar_init(w_bar, 1);
+            for (int b = 0; b < 2; b++) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 4); }
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 2 * FOUT >= 32 ? 2 * FOUT : 32);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](int tile, int &n, int &y0, int &x0) {
+        x0 = (tile % p.tiles_x) * 32;
+        int t = tile / p.tiles_x;
+        y0 = (t % p.tiles_y) * 4;
+        n = t / p.tiles_y;
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(num_slabs * W_SLAB_BYTES));
+            for (int s = 0; s < num_slabs; s++) ptx::tma_load_2d(smem_w + s * W_SLAB_BYTES, &map_w, w_bar, 0, s * FOUT);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int n, y0, x0;
+                tile_coords(tile, n, y0, x0);
+                for (int tap = 0; tap < 9; tap++) {
+                    const int ky = tap / 3, kx = tap % 3;
+                    for (int h = 0; h < KH; h++, it++) {
+                        const int s = it % A_STAGES;
+                        const uint32_t ph = (it / A_STAGES) & 1;
+                        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                        ptx::mbar_arrive_expect_tx(&full_bar[s], A_TILE_BYTES);
+                        uint8_t *dst = smem_a + s * A_TILE_BYTES;
+#pragma unroll
+                        for (int box = 0; box < 4; box++)      // box = 2*yp + xh : rows [32*box, +32)
+                            ptx::tma_load_4d(dst + box * 4096, &map_in, &full_bar[s], h * BK,
+                                             x0 + 16 * (box & 1) + kx, y0 + 2 * (box >> 1) + ky, n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_tf32(128, FOUT, false, false);
+            ptx::mbar_wait(w_bar, 0);
+            ptx::tc_fence_after_sync();
+            uint32_t it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+                const uint32_t buf = local & 1;
+                ptx::mbar_wait(&tmem_empty[buf], ((local >> 1) & 1) ^ 1);   // epilogue drained this buffer
+                ptx::tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * FOUT;
+                for (int slab = 0; slab < num_slabs; slab++, it++) {
+                    const int s = it % A_STAGES;
+                    const uint32_t ph = (it / A_STAGES) & 1;
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_TILE_BYTES);
+                    const uint32_t b_addr = ptx::smem_u32(smem_w + slab * W_SLAB_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t da = ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024);
+                        const uint64_t db = ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024);
+                        ptx::mma_tf32_ss(d_tmem, da, db, idesc, (slab | k) != 0);
+                    }
+                    ptx::mma_commit(&empty_bar[s]);
+                }
+                ptx::mma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> max-pool -> +bias -> ReLU -> global =====
+        const int q = warp & 3;                       // box index = TMEM lane quarter
+        const int NO = p.N / 2, FB = FOUT / 8;
+        const int sel1 = lane & 1, sel16 = (lane >> 4) & 1;
+        uint32_t local = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+            const uint32_t buf = local & 1;
+            int n, y0, x0;
+            tile_coords(tile, n, y0, x0);
+            ptx::mbar_wait(&tmem_full[buf], (local >> 1) & 1);
+            ptx::tc_fence_after_sync();
+            constexpr int NCH = FOUT / 32;
+            float v[NCH][32];
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                uint32_t r[32];
+                __syncwarp();
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * FOUT + c * 32, r);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[c][j] = __uint_as_float(r[j]);
+            }
+            // accumulator buffer can be overwritten by the MMAs of the tile after next
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+
+            // 2x2 max-pool across lanes l^1 (x pair) and l^16 (y pair), reduce-scatter style: after the
+            // two exchanges each lane owns 16 of this chunk pair's columns.
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                float a[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const float keep = sel1 ? v[c][j + 16] : v[c][j];
+                    const float send = sel1 ? v[c][j] : v[c][j + 16];
+                    a[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                }
+                float b8[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float keep = sel16 ? a[j + 8] : a[j];
+                    const float send = sel16 ? a[j] : a[j + 8];
+                    b8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                }
+                // this lane now holds the pooled value of columns [col0, col0+8) = one FOut block of 8
+                const int col0 = c * 32 + sel1 * 16 + sel16 * 8;
+                const int fb = col0 >> 3;
+                const int py = (y0 >> 1) + (q >> 1);
+                const int px = (x0 >> 1) + 8 * (q & 1) + ((lane & 15) >> 1);
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) o[j] = fmaxf(__fadd_rn(b8[j], __ldg(p.bias + col0 + j)), 0.0f);
+                float *dst = p.out + ((((size_t)n * FB + fb) * NO + py) * NO + px) * 8;
+                reinterpret_cast<float4 *>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<float4 *>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem_base, 2 * FOUT >= 32 ? 2 * FOUT : 32);
+    }
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+std::atomic<int> g_conv_mode{0};          // 0 auto, 1 exact, 2 tensor
+
+template <int FOUT>
+int launch_conv_tc(const float *in, const float *filter, const float *bias, float *out, int B, int N, int FIn)
+{
+    const int KH = FIn / BK, num_slabs = 9 * KH;
+    float *wp = reinterpret_cast<float *>(pool_alloc((size_t)num_slabs * FOUT * BK * 4));
+    if (!wp) return 1;
+    tiramisu_sm100_conv_pack_filter<<<(num_slabs * FOUT * BK + 255) / 256, 256, 0, stream()>>>(filter, wp, FIn, FOUT);
+    if (post_launch("tiramisu_sm100_conv_pack_filter")) return 1;
+
+    CUtensorMap map_in, map_w;
+    {
+        const uint64_t NP = (uint64_t)N + 2;
+        uint64_t dims[4] = {(uint64_t)FIn, NP, NP, (uint64_t)B};
+        uint64_t str[3] = {(uint64_t)FIn * 4, NP * FIn * 4, NP * NP * FIn * 4};
+        uint32_t box[4] = {BK, 16, 2, 1};
+        if (make_tensor_map_f32(&map_in, in, 4, dims, str, box)) return 1;
+    }
+    {
+        uint64_t dims[2] = {BK, (uint64_t)num_slabs * FOUT};
+        uint64_t str[1] = {BK * 4};
+        uint32_t box[2] = {BK, FOUT};
+        if (make_tensor_map_f32(&map_w, wp, 2, dims, str, box)) return 1;
+    }
+    ConvParams p;
+    p.B = B; p.N = N; p.FIn = FIn; p.FOut = FOUT;
+    p.tiles_y = N / 4; p.tiles_x = N / 32;
+    p.num_tiles = B * p.tiles_y * p.tiles_x;
+    p.bias = bias; p.out = out;
+    const int smem = num_slabs * FOUT * BK * 4 + A_STAGES * A_TILE_BYTES + 1024 + 256;
+    auto kern = tiramisu_sm100_conv_block_tf32<FOUT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB200_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    kern<<<grid, kConvThreads, smem, stream()>>>(map_in, map_w, p);
+    int rc = post_launch("tiramisu_sm100_conv_block_tf32");
+    pool_free(wp);
+    return rc;
+}
+
+}  // namespace
+
+TB200_API int tiramisu_b200_set_conv_mode(int mode)
+{
+    if (mode < 0 || mode > 2) mode = 0;
+    return g_conv_mode.exchange(mode);
+}
+
+TB200_API int tiramisu_b200_conv_relu_maxpool(const float *input, const float *filter, const float *bias,
+                                              float *output, int32_t B, int32_t N, int32_t FIn, int32_t FOut)
+{
+    if (!input || !filter || !bias || !output || B < 1 || N < 2 || FIn < 1 || FOut < 8 || FOut % 8 || N % 2)
+        return fail(__func__, "bad argument (need FOut % 8 == 0, N even)");
+    const int mode = g_conv_mode.load();
+    const int num_slabs = 9 * (FIn / BK);
+    const bool tc_ok = FIn % BK == 0 && FOut == 64 && N % 32 == 0 && aligned16(input) && aligned16(output) &&
+                       (size_t)num_slabs * FOut * BK * 4 + A_STAGES * A_TILE_BYTES + 2048 <= 227 * 1024;
+    if (mode == 2 && !tc_ok) return fail(__func__, "shape not supported by the tcgen05 conv path");
+    if (mode != 1 && tc_ok) return launch_conv_tc<64>(input, filter, bias, output, B, N, FIn);
+    const size_t total = (size_t)B * (FOut / 8) * (N / 2) * (N / 2) * 8;
+    const size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 16;
+    tiramisu_sm100_conv_block_exact<<<(unsigned)(want < cap ? want : cap), 256, 0, stream()>>>(input, filter, bias,
+                                                                                              output, B, N, FIn, FOut);
+    return post_launch("tiramisu_sm100_conv_block_exact");
+}

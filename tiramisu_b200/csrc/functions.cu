@@ -331,3 +331,69 @@ TB200_API int test_197(halide_buffer_t *A, halide_buffer_t *B)
     }
     return finish();
 }
+
+// =============================================================================== DNN blocks
+// benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/wrapper_nn_block.cpp:13-16 — Halide extents
+// input {FIn, N+2, N+2, B}, filter {8, FIn, 3, 3, FOut/8}, bias {FOut}, output {8, N/2, N/2, FOut/8, B};
+// configure.h bakes B=32, N=224, FIn=3, FOut=32 when the buffers carry no metadata.
+TB200_API int conv_relu_maxpool_block(halide_buffer_t *input, halide_buffer_t *filter, halide_buffer_t *bias,
+                                      halide_buffer_t *output)
+{
+    BufView vi, vf, vb, vo;
+    if (!view_of(input, &vi) || !view_of(filter, &vf) || !view_of(bias, &vb) || !view_of(output, &vo))
+        return bad(__func__, "null buffer");
+    int B = 32, N = 224, FIn = 3, FOut = 32;
+    if (vi.ndim >= 4) {
+        FIn = (int)vi.extent[0]; N = (int)vi.extent[1] - 2; B = (int)vi.extent[3];
+        if (vi.extent[2] != vi.extent[1]) return bad(__func__, "input must be square (N+2 x N+2)");
+    }
+    if (vf.ndim >= 5) {
+        FOut = (int)vf.extent[4] * 8;
+        if (vf.extent[0] != 8 || vf.extent[1] != FIn || vf.extent[2] != 3 || vf.extent[3] != 3)
+            return bad(__func__, "filter extents != {8, FIn, 3, 3, FOut/8}");
+    } else if (vb.ndim >= 1) {
+        FOut = (int)vb.extent[0];
+    }
+    if (vo.ndim >= 5 && (vo.extent[0] != 8 || vo.extent[1] != N / 2 || vo.extent[2] != N / 2 ||
+                         vo.extent[3] != FOut / 8 || vo.extent[4] != B))
+        return bad(__func__, "output extents != {8, N/2, N/2, FOut/8, B}");
+    if (N < 2 || N % 2 || FOut % 8 || FIn < 1 || B < 1) return bad(__func__, "unsupported sizes");
+    const size_t NP = (size_t)N + 2;
+    DeviceArg di, df, db, dout;
+    if (di.bind(vi, (size_t)B * NP * NP * FIn * 4, true) || df.bind(vf, (size_t)FOut * 9 * FIn * 4, true) ||
+        db.bind(vb, (size_t)FOut * 4, true) || dout.bind(vo, (size_t)B * FOut * (N / 2) * (N / 2) * 4, false))
+        return 1;
+    if (tiramisu_b200_conv_relu_maxpool(di.as<float>(), df.as<float>(), db.as<float>(), dout.as<float>(), B, N, FIn,
+                                        FOut))
+        return 1;
+    if (dout.copy_out()) return 1;
+    return finish();
+}
+
+// benchmarks/DNN/blocks/LSTM/cpu/wrapper.h:6-10 — params i32[4] = {F, B, L, T}; Weights {F, 4F, 2, L};
+// biases {4F, L}; x, y {F, B, T}.
+TB200_API int lstm(halide_buffer_t *params, halide_buffer_t *Weights, halide_buffer_t *biases, halide_buffer_t *x,
+                   halide_buffer_t *y)
+{
+    BufView vp, vw, vb, vx, vy;
+    if (!view_of(params, &vp) || !view_of(Weights, &vw) || !view_of(biases, &vb) || !view_of(x, &vx) ||
+        !view_of(y, &vy))
+        return bad(__func__, "null buffer");
+    int32_t pr[4];
+    if (read_params(vp, pr, 4)) return 1;
+    const int F = pr[0], B = pr[1], L = pr[2], T = pr[3];
+    if (F < 1 || B < 1 || L < 1 || T < 1) return bad(__func__, "params must be positive {F, B, L, T}");
+    if (vw.ndim >= 4 && (vw.extent[0] != F || vw.extent[1] != 4 * F || vw.extent[2] != 2 || vw.extent[3] != L))
+        return bad(__func__, "Weights extents != {F, 4F, 2, L}");
+    if (vx.ndim >= 3 && (vx.extent[0] != F || vx.extent[1] != B || vx.extent[2] != T))
+        return bad(__func__, "x extents != {F, B, T}");
+    if (vy.ndim >= 3 && (vy.extent[0] != F || vy.extent[1] != B || vy.extent[2] != T))
+        return bad(__func__, "y extents != {F, B, T}");
+    DeviceArg dw, db, dx, dy;
+    if (dw.bind(vw, (size_t)L * 2 * 4 * F * F * 4, true) || db.bind(vb, (size_t)L * 4 * F * 4, true) ||
+        dx.bind(vx, (size_t)T * B * F * 4, true) || dy.bind(vy, (size_t)T * B * F * 4, false))
+        return 1;
+    if (tiramisu_b200_lstm(dw.as<float>(), db.as<float>(), dx.as<float>(), dy.as<float>(), F, B, L, T)) return 1;
+    if (dy.copy_out()) return 1;
+    return finish();
+}

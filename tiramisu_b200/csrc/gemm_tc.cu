@@ -46,7 +46,7 @@ static EncodeTiledFn encode_fn()
 }
 
 int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
-                        const uint64_t *strides_bytes, const uint32_t *box, bool swizzle128)
+                        const uint64_t *strides_bytes, const uint32_t *box, int swizzle)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail("make_tensor_map_f32", "cuTensorMapEncodeTiled unavailable");
@@ -56,7 +56,9 @@ int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint
     for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx,
                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    swizzle == kTmaSwizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                    : swizzle == kTmaSwizzle128Atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("make_tensor_map_f32", "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return 0;
@@ -85,6 +87,7 @@ struct GemmParams {
     float *C;
     int64_t ldC;
     int num_m, num_n, group_m;
+    uint32_t b_lbo, b_sbo;              // MN-major B descriptor offsets (bytes)
 };
 
 template <int BN, bool B_MN>
@@ -175,9 +178,11 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
                     // K-major, 128B swizzle: rows are 128 B apart, 8-row groups 1024 B apart; a K step
                     // of 8 fp32 moves the start address 32 B inside the swizzled row.
                     const uint64_t da = ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024);
-                    // MN-major, 128B swizzle: 32-column slabs are BK*128 B apart (leading offset), a K step
-                    // of 8 rows moves the start address 1024 B.
-                    const uint64_t db = B_MN ? ptx::make_smem_desc(b_addr + k * (UMMA_K * 128), BK * 128, 1024)
+                    // MN-major tf32 (128B swizzle, 32B atoms): rows are k (128 B = 32 columns each), 4-row
+                    // groups 512 B apart (stride offset), 32-column slabs BK*128 B apart (leading offset);
+                    // a K step of 8 rows moves the start address 1024 B.
+                    const uint64_t db = B_MN ? ptx::make_smem_desc(b_addr + k * (UMMA_K * 128), p.b_lbo, p.b_sbo,
+                                                                   ptx::kLayoutSw128Base32)
                                              : ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024);
                     ptx::mma_tf32_ss(tmem_base, da, db, idesc, (kb | k) != 0);
                 }
@@ -259,7 +264,9 @@ int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, flo
         uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
         uint64_t str[1] = {(uint64_t)ldB * 4};
         uint32_t box[2] = {32, BK};
-        if (make_tensor_map_f32(&map_b, B, 2, dims, str, box)) return 1;
+        // MN-major 32-bit operands need the 128B swizzle with 32-byte atoms (UMMA layout
+        // SWIZZLE_128B_BASE32B); the plain 128B swizzle is only valid for K-major tf32.
+        if (make_tensor_map_f32(&map_b, B, 2, dims, str, box, kTmaSwizzle128Atom32)) return 1;
     } else {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
         uint64_t str[1] = {(uint64_t)ldB * 4};
@@ -271,6 +278,10 @@ int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, flo
     p.num_m = (M + BM - 1) / BM;
     p.num_n = (N + BN - 1) / BN;
     p.group_m = 16;
+    p.b_lbo = BK * 128;
+    p.b_sbo = 512;
+    if (const char *e = getenv("TB200_DBG_B_LBO")) p.b_lbo = (uint32_t)atoi(e);     // descriptor bring-up only
+    if (const char *e = getenv("TB200_DBG_B_SBO")) p.b_sbo = (uint32_t)atoi(e);
     auto kern = tiramisu_sm100_gemm_tf32<BN, B_MN>;
     static bool attr_set = false;
     if (!attr_set) {

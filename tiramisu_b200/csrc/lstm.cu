@@ -1,0 +1,326 @@
+// lstm.cu — the multi-layer LSTM of /root/reference/benchmarks/DNN/blocks/LSTM/{cpu,gpu}/generator.cpp
+//   Weights f32[L][2][4F][F] (index 0 = R recurrent, 1 = W input), biases f32[L][4F],
+//   x,y f32[T][B][F]; gate rows [0,F)=i sigmoid, [F,2F)=z tanh, [2F,3F)=o sigmoid, [3F,4F)=f sigmoid;
+//   c = i*z + f*c_prev; h = tanh(c)*o; y = h of the last layer.            (cpu/generator.cpp:35-53)
+//
+// Two paths:
+//  * exact: fp32 SIMT kernels that follow the reference's single interleaved j loop
+//    (s = b; s = (s + R*h_prev) + W*h_below, cpu/generator.cpp:40-41) — any shape.
+//  * tensor (F % 32 == 0, B <= 128): per layer
+//      1. one large tcgen05 TF32 GEMM for the input contribution of ALL time steps
+//         Xg[T*B][4F] = H_below[T*B][F] * Wp^T           (what LSTM/gpu_lib batches over 10 steps, :64-72)
+//      2. per time step ONE kernel: recurrent GEMM h_prev[B][F] * Rp^T on tcgen05 with the
+//         pointwise gates fused into the epilogue (the reference launches 2 GEMM kernels + 1
+//         pointwise kernel per cell, LSTM/gpu/generator.cpp:85-131).  Weight rows are packed
+//         gate-interleaved (row 4u+g) so that the i,z,o,f pre-activations of a hidden unit are 4
+//         adjacent accumulator columns of the same thread.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tiramisu_b200.h"
+
+using namespace tb200;
+
+namespace tb200 {
+int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha,
+                float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tB);
+}
+
+namespace {
+
+__device__ __forceinline__ float sigmoid_ref(float v) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v))); }
+
+// ------------------------------------------------------------------------------------------------ exact SIMT
+// tmp[k][g] = b[g] + sum_j (R[g][j]*hprev[k][j] then W[g][j]*hbelow[k][j]), one warp per (k, 32 g's):
+// lanes own consecutive gate rows; j sequential per thread (reference order).
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_lstm_gates_exact(const float *__restrict__ R, const float *__restrict__ W,
+                                const float *__restrict__ b, const float *__restrict__ hprev,
+                                const float *__restrict__ hbelow, float *__restrict__ tmp, int F, int B)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (g >= 4 * F || k >= B) return;
+    const float *r = R + (size_t)g * F, *w = W + (size_t)g * F;
+    const float *hp = hprev + (size_t)k * F, *hb = hbelow + (size_t)k * F;
+    float s = b[g];
+    for (int j = 0; j < F; j++) {
+        s = __fadd_rn(s, __fmul_rn(__ldg(r + j), __ldg(hp + j)));
+        s = __fadd_rn(s, __fmul_rn(__ldg(w + j), __ldg(hb + j)));
+    }
+    tmp[(size_t)k * 4 * F + g] = s;
+}
+
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_lstm_pointwise(const float *__restrict__ tmp, const float *__restrict__ cprev,
+                              float *__restrict__ c, float *__restrict__ h, int F, int B)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * F) return;
+    const int k = idx / F, i = idx % F;
+    const float *t = tmp + (size_t)k * 4 * F;
+    const float gi = sigmoid_ref(t[i]);
+    const float gz = tanhf(t[i + F]);
+    const float go = sigmoid_ref(t[i + 2 * F]);
+    const float gf = sigmoid_ref(t[i + 3 * F]);
+    const float cv = __fadd_rn(__fmul_rn(gi, gz), __fmul_rn(gf, cprev[idx]));
+    c[idx] = cv;
+    h[idx] = __fmul_rn(tanhf(cv), go);
+}
+
+// ------------------------------------------------------------------------------------------------ tensor path
+// Weights [2][4F][F] -> packed [2][4F][F] with row p = 4*u + g  <-  row g*F + u ; bias likewise.
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_lstm_pack(const float *__restrict__ Wl, const float *__restrict__ bl, float *__restrict__ Wp,
+                         float *__restrict__ bp, int F)
+{
+    const size_t total4 = (size_t)2 * 4 * F * (F / 4);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const int j4 = (int)(i % (F / 4));
+        size_t t = i / (F / 4);
+        const int p = (int)(t % (4 * F));
+        const int m = (int)(t / (4 * F));
+        const int u = p >> 2, g = p & 3;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(Wl + ((size_t)m * 4 * F + (size_t)g * F + u) * F) + j4);
+        reinterpret_cast<float4 *>(Wp + ((size_t)m * 4 * F + p) * F)[j4] = v;
+        if (m == 0 && j4 == 0) bp[p] = bl[g * F + u];
+    }
+}
+
+constexpr int BM = 128, BK = 32, UMMA_K = 8, BN = 32, STAGES = 8;
+constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4, STAGE_BYTES = A_TILE + B_TILE;
+constexpr int kThreads = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+
+struct StepParams {
+    int B, F;               // batch rows (<= 128), hidden size
+    const float *xg;        // [B][4F] packed columns: input contribution of this time step
+    const float *bias;      // [4F] packed
+    const float *cprev;     // [B][F]
+    float *c, *h;           // [B][F]
+    float *y;               // optional second destination for h (last layer), may be null
+};
+
+// One LSTM cell step: gates[B][4F] = h_prev[B][F] * Rp^T (tcgen05, TF32) ; epilogue = Xg + bias,
+// sigmoid/tanh, c/h update.  grid = 4F/32 CTAs, each owning 8 hidden units.
+__global__ void __launch_bounds__(kThreads, 1)
+tiramisu_sm100_lstm_step_tf32(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_r,
+                              const StepParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_a = smem, *smem_b = smem + STAGES * A_TILE;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int num_kb = p.F / BK;
+
+    if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&map_h); ptx::prefetch_tensormap(&map_r); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; s++) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+            ptx::mbar_init(tmem_full, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 32);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % STAGES;
+                ptx::mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                ptx::tma_load_2d(smem_a + s * A_TILE, &map_h, &full_bar[s], kb * BK, 0);     // rows >= B: zero fill
+                ptx::tma_load_2d(smem_b + s * B_TILE, &map_r, &full_bar[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, false);
+            for (int kb = 0; kb < num_kb; kb++) {
+                const int s = kb % STAGES;
+                ptx::mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+                ptx::tc_fence_after_sync();
+                const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_TILE), b_addr = ptx::smem_u32(smem_b + s * B_TILE);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++)
+                    ptx::mma_tf32_ss(tmem_base, ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024),
+                                     ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024), idesc, (kb | k) != 0);
+                ptx::mma_commit(&empty_bar[s]);
+            }
+            ptx::mma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                 // batch index k
+        // operands of the pointwise part do not depend on the MMAs: fetch them while the GEMM runs
+        const bool ok = row < p.B;
+        float4 xg[8], bs[8], cp[2];
+        if (ok) {
+            const float4 *xp = reinterpret_cast<const float4 *>(p.xg + (size_t)row * 4 * p.F + n0);
+            const float4 *bp = reinterpret_cast<const float4 *>(p.bias + n0);
+            const float4 *cq = reinterpret_cast<const float4 *>(p.cprev + (size_t)row * p.F + n0 / 4);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { xg[j] = __ldg(xp + j); bs[j] = __ldg(bp + j); }
+            cp[0] = __ldg(cq); cp[1] = __ldg(cq + 1);
+        }
+        ptx::mbar_wait(tmem_full, 0);
+        ptx::tc_fence_after_sync();
+        uint32_t r[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), r);
+        ptx::tmem_ld_wait();
+        if (ok) {
+            float cn[8], hn[8];
+            const float cpv[8] = {cp[0].x, cp[0].y, cp[0].z, cp[0].w, cp[1].x, cp[1].y, cp[1].z, cp[1].w};
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                // columns 4u..4u+3 = pre-activations i, z, o, f of hidden unit n0/4 + u
+                const float si = __uint_as_float(r[4 * u + 0]) + xg[u].x + bs[u].x;
+                const float sz = __uint_as_float(r[4 * u + 1]) + xg[u].y + bs[u].y;
+                const float so = __uint_as_float(r[4 * u + 2]) + xg[u].z + bs[u].z;
+                const float sf = __uint_as_float(r[4 * u + 3]) + xg[u].w + bs[u].w;
+                const float gi = sigmoid_ref(si), gz = tanhf(sz), go = sigmoid_ref(so), gf = sigmoid_ref(sf);
+                cn[u] = __fadd_rn(__fmul_rn(gi, gz), __fmul_rn(gf, cpv[u]));
+                hn[u] = __fmul_rn(tanhf(cn[u]), go);
+            }
+            const size_t o = (size_t)row * p.F + n0 / 4;
+            reinterpret_cast<float4 *>(p.c + o)[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            reinterpret_cast<float4 *>(p.c + o)[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+            reinterpret_cast<float4 *>(p.h + o)[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            reinterpret_cast<float4 *>(p.h + o)[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            if (p.y) {
+                reinterpret_cast<float4 *>(p.y + o)[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                reinterpret_cast<float4 *>(p.y + o)[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            }
+        }
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem_base, 32);
+    }
+}
+
+std::atomic<int> g_lstm_mode{0};
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int lstm_exact(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y)
+{
+    const size_t BF = (size_t)B * F;
+    // buf_h[T+1][L+1][B][F], buf_c[T+1][L][B][F] as in cpu/generator.cpp:91-92
+    float *h = reinterpret_cast<float *>(pool_alloc((size_t)(T + 1) * (L + 1) * BF * 4));
+    float *c = reinterpret_cast<float *>(pool_alloc((size_t)(T + 1) * L * BF * 4));
+    float *tmp = reinterpret_cast<float *>(pool_alloc((size_t)B * 4 * F * 4));
+    if (!h || !c || !tmp) return 1;
+    auto H = [&](int m, int l) { return h + (((size_t)m + 1) * (L + 1) + ((size_t)l + 1)) * BF; };
+    auto C = [&](int m, int l) { return c + (((size_t)m + 1) * L + (size_t)l) * BF; };
+    TB200_CHECK(cudaMemsetAsync(h, 0, (size_t)(L + 1) * BF * 4, stream()));        // h(-1, l) = 0
+    TB200_CHECK(cudaMemsetAsync(c, 0, (size_t)L * BF * 4, stream()));              // c(-1, l) = 0
+    for (int m = 0; m < T; m++)                                                     // h(m, -1) = x(m)
+        TB200_CHECK(cudaMemcpyAsync(H(m, -1), x + (size_t)m * BF, BF * 4, cudaMemcpyDeviceToDevice, stream()));
+    for (int m = 0; m < T; m++)
+        for (int l = 0; l < L; l++) {
+            const float *R = Wt + ((size_t)l * 2 + 0) * 4 * F * F, *W = Wt + ((size_t)l * 2 + 1) * 4 * F * F;
+            dim3 grid((4 * F + 255) / 256, B);
+            tiramisu_sm100_lstm_gates_exact<<<grid, 256, 0, stream()>>>(R, W, bias + (size_t)l * 4 * F, H(m - 1, l),
+                                                                         H(m, l - 1), tmp, F, B);
+            if (post_launch("tiramisu_sm100_lstm_gates_exact")) return 1;
+            tiramisu_sm100_lstm_pointwise<<<(int)((BF + 255) / 256), 256, 0, stream()>>>(tmp, C(m - 1, l), C(m, l),
+                                                                                        H(m, l), F, B);
+            if (post_launch("tiramisu_sm100_lstm_pointwise")) return 1;
+        }
+    for (int m = 0; m < T; m++)
+        TB200_CHECK(cudaMemcpyAsync(y + (size_t)m * BF, H(m, L - 1), BF * 4, cudaMemcpyDeviceToDevice, stream()));
+    pool_free(h); pool_free(c); pool_free(tmp);
+    return 0;
+}
+
+int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y)
+{
+    const size_t BF = (size_t)B * F, TB = (size_t)T * B;
+    float *Wp = reinterpret_cast<float *>(pool_alloc((size_t)2 * 4 * F * F * 4));          // packed weights of one layer
+    float *bp = reinterpret_cast<float *>(pool_alloc((size_t)4 * F * 4));
+    float *xg = reinterpret_cast<float *>(pool_alloc(TB * 4 * F * 4));                     // input contributions, all steps
+    float *hs = reinterpret_cast<float *>(pool_alloc((size_t)2 * TB * F * 4));             // h of layer l (ping-pong by layer)
+    float *cs = reinterpret_cast<float *>(pool_alloc((size_t)2 * BF * 4));                 // c ping-pong by step
+    float *zero = reinterpret_cast<float *>(pool_alloc(BF * 4));
+    if (!Wp || !bp || !xg || !hs || !cs || !zero) return 1;
+    TB200_CHECK(cudaMemsetAsync(zero, 0, BF * 4, stream()));
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB200_CHECK(cudaFuncSetAttribute(tiramisu_sm100_lstm_step_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SMEM_BYTES));
+        attr_set = true;
+    }
+    for (int l = 0; l < L; l++) {
+        const float *below = (l == 0) ? x : hs + (size_t)((l - 1) & 1) * TB * F;           // [T*B][F]
+        float *hl = (l == L - 1) ? y : hs + (size_t)(l & 1) * TB * F;                       // last layer writes y directly
+        const size_t pk = (size_t)2 * 4 * F * (F / 4);
+        const size_t want = (pk + 255) / 256, cap = (size_t)sm_count() * 16;
+        tiramisu_sm100_lstm_pack<<<(unsigned)(want < cap ? want : cap), 256, 0, stream()>>>(
+            Wt + (size_t)l * 2 * 4 * F * F, bias + (size_t)l * 4 * F, Wp, bp, F);
+        if (post_launch("tiramisu_sm100_lstm_pack")) return 1;
+        // 1. input contribution of all T steps: Xg[T*B][4F] = below * Wp(W)^T
+        if (gemm_f32_tc(below, Wp + (size_t)4 * F * F, xg, TB, 4 * (uint64_t)F, F, 1.0f, 0.0f, F, F, 4 * (uint64_t)F,
+                        true))
+            return 1;
+        // 2. the recurrence
+        CUtensorMap map_r;
+        {
+            uint64_t dims[2] = {(uint64_t)F, 4 * (uint64_t)F};
+            uint64_t str[1] = {(uint64_t)F * 4};
+            uint32_t box[2] = {BK, BN};
+            if (make_tensor_map_f32(&map_r, Wp, 2, dims, str, box)) return 1;
+        }
+        for (int m = 0; m < T; m++) {
+            const float *hprev = (m == 0) ? zero : hl + (size_t)(m - 1) * BF;
+            CUtensorMap map_h;
+            uint64_t dims[2] = {(uint64_t)F, (uint64_t)B};
+            uint64_t str[1] = {(uint64_t)F * 4};
+            uint32_t box[2] = {BK, BM};
+            if (make_tensor_map_f32(&map_h, hprev, 2, dims, str, box)) return 1;
+            StepParams p;
+            p.B = B; p.F = F;
+            p.xg = xg + (size_t)m * B * 4 * F;
+            p.bias = bp;
+            p.cprev = (m == 0) ? zero : cs + (size_t)((m - 1) & 1) * BF;
+            p.c = cs + (size_t)(m & 1) * BF;
+            p.h = hl + (size_t)m * BF;
+            p.y = nullptr;
+            tiramisu_sm100_lstm_step_tf32<<<4 * F / BN, kThreads, SMEM_BYTES, stream()>>>(map_h, map_r, p);
+            if (post_launch("tiramisu_sm100_lstm_step_tf32")) return 1;
+        }
+    }
+    pool_free(Wp); pool_free(bp); pool_free(xg); pool_free(hs); pool_free(cs); pool_free(zero);
+    return 0;
+}
+
+}  // namespace
+
+TB200_API int tiramisu_b200_set_lstm_mode(int mode)
+{
+    if (mode < 0 || mode > 2) mode = 0;
+    return g_lstm_mode.exchange(mode);
+}
+
+TB200_API int tiramisu_b200_lstm(const float *Weights, const float *biases, const float *x, float *y, int32_t F,
+                                 int32_t B, int32_t L, int32_t T)
+{
+    if (!Weights || !biases || !x || !y || F < 1 || B < 1 || L < 1 || T < 1) return fail(__func__, "bad argument");
+    const int mode = g_lstm_mode.load();
+    const bool tc_ok = F % 32 == 0 && B <= 128 && aligned16(Weights) && aligned16(biases) && aligned16(x) && aligned16(y);
+    if (mode == 2 && !tc_ok) return fail(__func__, "shape not supported by the tcgen05 LSTM path");
+    if (mode != 1 && tc_ok) return lstm_tensor(F, B, L, T, Weights, biases, x, y);
+    return lstm_exact(F, B, L, T, Weights, biases, x, y);
+}

@@ -151,14 +151,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [32,46) stride-dim byte offset >> 4   [46,48) version = 1   [49,52) base offset
 //   [61,64) layout: 0 none, 1 128B(base 32B), 2 128B, 4 64B, 6 32B
 constexpr uint64_t kLayoutSw128 = 2;
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+constexpr uint64_t kLayoutSw128Base32 = 1;     // 128B swizzle of 32-byte atoms: MN-major 32-bit operands
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint64_t layout = kLayoutSw128)
 {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
-    d |= kLayoutSw128 << 61;
+    d |= layout << 61;
     return d;
 }
 
@@ -176,7 +178,8 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
 // ---- host: TMA tensor maps ------------------------------------------------------------------------
 // Encodes a tiled tensor map for a fp32 tensor of `rank` dims (innermost first) with 128-byte
 // swizzle.  strides_bytes has rank-1 entries (dims 1..rank-1).  Returns 0 on success.
+constexpr int kTmaSwizzleNone = 0, kTmaSwizzle128 = 1, kTmaSwizzle128Atom32 = 2;
 int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
-                        const uint64_t *strides_bytes, const uint32_t *box, bool swizzle128 = true);
+                        const uint64_t *strides_bytes, const uint32_t *box, int swizzle = kTmaSwizzle128);
 
 }  // namespace tb200

@@ -126,9 +126,22 @@ tiramisu_sm100_heat2d_scalar(const float *__restrict__ in, float *__restrict__ o
 //   bx  = ((in[y][x] + in[y][x+1]) + in[y][x+2]) / 3.0f ;  out = ((bx[y] + bx[y+1]) + bx[y+2]) / 3.0f
 // Vector path: W % 4 == 0 and 16-byte aligned input rows; output rows are (W-2) wide, so stores are
 // 8-byte aligned pairs.  A thread owns input columns [x, x+4) and produces output columns [x, x+4).
+// x / 3.0f, correctly rounded, in 3 FMA-pipe instructions instead of the ~10-instruction IEEE
+// division sequence (which made the blur kernel issue-bound: ncu r01 sm__throughput 80 %).
+// q = RN(x*RN(1/3)); r = x - 3q (exact in an FMA); q' = RN(q + r*RN(1/3)).  Verified bit-identical
+// to x / 3.0f for every finite fp32 including denormals (tools/verify_div3.c, exhaustive).
+__device__ __forceinline__ float div3(float x)
+{
+    const float y = 0.3333333432674407958984375f;      // RN(1/3)
+    const float q = __fmul_rn(x, y);
+    const float r = __fmaf_rn(-3.0f, q, x);
+    const float q2 = __fmaf_rn(r, y, q);
+    return (fabsf(x) < __int_as_float(0x7f800000)) ? q2 : q;   // inf/nan: r is NaN, q is already right
+}
+
 __device__ __forceinline__ float blur3(float a, float b, float c)
 {
-    return __fdiv_rn(__fadd_rn(__fadd_rn(a, b), c), 3.0f);
+    return div3(__fadd_rn(__fadd_rn(a, b), c));
 }
 
 template <int RY>

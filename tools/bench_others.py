@@ -45,9 +45,59 @@ def sgemm(torch, stream, peaks, sizes=(1024, 4096, 8192)):
     return out
 
 
+def conv(torch, stream, peaks):
+    """BASELINE config 3: conv+ReLU+maxpool N=32, 64->64, 3x3, 224x224 (device-resident)."""
+    from tiramisu_b200 import _lib
+    L = _lib.lib()
+    B, N, FIn, FOut = 32, 224, 64, 64
+    with torch.cuda.stream(stream):
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x = torch.rand((B, N + 2, N + 2, FIn), device="cuda", generator=g) * 2 - 1
+        w = torch.rand((FOut // 8, 3, 3, FIn, 8), device="cuda", generator=g) * 2 - 1
+        b = torch.rand((FOut,), device="cuda", generator=g) * 2 - 1
+        o = torch.empty((B, FOut // 8, N // 2, N // 2, 8), device="cuda")
+    stream.synchronize()
+
+    def fn():
+        _lib.check(L.tiramisu_b200_conv_relu_maxpool(x.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), B, N,
+                                                     FIn, FOut))
+
+    ms = _time(torch, stream, fn, iters=10)
+    flop = 2.0 * B * N * N * FOut * FIn * 9
+    tf32_peak = float(peaks.get("tf32_tflops", peaks["bf16_tflops"] / 2.0))
+    tfl = flop / (ms * 1e-3) / 1e12
+    return {"conv_relu_maxpool_32x224x224_64to64": {"ms": ms, "TFLOPs": tfl, "GFLOPs": tfl * 1e3,
+                                                    "frac_of_tf32_peak": tfl / tf32_peak,
+                                                    "bytes_GBps": (x.numel() + o.numel()) * 4 / (ms * 1e-3) / 1e9}}
+
+
+def lstm(torch, stream, peaks):
+    """BASELINE config 4: LSTM hidden=1024, 4 layers, seq=100, batch=64 (device-resident)."""
+    from tiramisu_b200 import _lib
+    L = _lib.lib()
+    F, B, Ly, T = 1024, 64, 4, 100
+    with torch.cuda.stream(stream):
+        g = torch.Generator(device="cuda").manual_seed(4)
+        W = (torch.rand((Ly, 2, 4 * F, F), device="cuda", generator=g) * 2 - 1) / 32
+        b = torch.rand((Ly, 4 * F), device="cuda", generator=g) * 2 - 1
+        x = torch.rand((T, B, F), device="cuda", generator=g) * 2 - 1
+        y = torch.empty_like(x)
+    stream.synchronize()
+
+    def fn():
+        _lib.check(L.tiramisu_b200_lstm(W.data_ptr(), b.data_ptr(), x.data_ptr(), y.data_ptr(), F, B, Ly, T))
+
+    ms = _time(torch, stream, fn, iters=5, warm=2)
+    flop = T * Ly * 2.0 * (2 * B * 4 * F * F)
+    tf32_peak = float(peaks.get("tf32_tflops", peaks["bf16_tflops"] / 2.0))
+    tfl = flop / (ms * 1e-3) / 1e12
+    return {"lstm_F1024_L4_T100_B64": {"ms": ms, "TFLOPs": tfl, "GFLOPs": tfl * 1e3,
+                                       "frac_of_tf32_peak": tfl / tf32_peak, "us_per_cell": ms * 1e3 / (T * Ly)}}
+
+
 def run(torch, stream, peaks):
     res = {}
-    for name, fn in (("sgemm", sgemm),):
+    for name, fn in (("sgemm", sgemm), ("conv", conv), ("lstm", lstm)):
         try:
             res.update(fn(torch, stream, peaks))
         except Exception as e:

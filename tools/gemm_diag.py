@@ -42,8 +42,15 @@ def main():
     api.set_gemm_mode(2)
     os.makedirs("gpurun_out", exist_ok=True)
     lines = []
-    for kind in ("eye", "ints", "rand"):
-        for tB in (True, False):
+    # MN-major B descriptor bring-up: which (leading, stride) byte offsets does the hardware want?
+    for lbo, sbo in ((4096, 512), (512, 4096), (4096, 1024), (1024, 4096), (128, 512), (512, 128)):
+        os.environ["TB200_DBG_B_LBO"], os.environ["TB200_DBG_B_SBO"] = str(lbo), str(sbo)
+        for (M, N, K) in ((128, 256, 32), (256, 512, 256)):
+            rel, nbad, where = run_case(M, N, K, False, 128, "ints")
+            lines.append(f"MN-major probe lbo={lbo} sbo={sbo} M={M} N={N} K={K} rel={rel:.3e} bad={nbad} {where}")
+    del os.environ["TB200_DBG_B_LBO"], os.environ["TB200_DBG_B_SBO"]
+    for kind in ("ints", "rand"):
+        for tB in (False, True):
             for bn in (64, 128, 256):
                 for (M, N, K) in ((128, 256, 32), (128, 256, 64), (256, 512, 256), (136, 264, 100), (1024, 1024, 1024)):
                     try:
