@@ -126,6 +126,43 @@ int tiramisu_b200_lstm(const float *Weights, const float *biases, const float *x
                        int32_t F, int32_t B, int32_t L, int32_t T);
 int tiramisu_b200_set_lstm_mode(int mode);
 
+/* ===================================================================== B2: distributed runtime
+ * NCCL over NVLink, one process per GPU, replacing src/tiramisu_mpi.cpp (MPI point-to-point).
+ * Same names and argument meaning as include/tiramisu/mpi_comm.h; data pointers may be device
+ * memory (sent in place) or host memory (staged).  Messages are stream-ordered. */
+int tiramisu_b200_comm_unique_id(void *out128);                 /* 128-byte NCCL id (rank 0) */
+int tiramisu_b200_comm_init(int32_t rank, int32_t world, const void *id128);
+int tiramisu_b200_comm_destroy(void);
+int tiramisu_b200_comm_rank(void);
+int tiramisu_b200_comm_size(void);
+int tiramisu_b200_comm_broadcast(void *dev_buf, uint64_t bytes, int32_t root);
+/* n send/recv pairs as ONE NCCL group; a peer < 0 skips that entry. */
+int tiramisu_b200_comm_exchange(int32_t n, const int32_t *send_peer, void *const *send_buf,
+                                const uint64_t *send_bytes, const int32_t *recv_peer,
+                                void *const *recv_buf, const uint64_t *recv_bytes);
+int tiramisu_MPI_init(void);                 /* src/tiramisu_mpi.cpp:8  reads torchrun's env; returns rank */
+void tiramisu_MPI_cleanup(void);             /* :19 */
+void tiramisu_MPI_global_barrier(void);      /* :23 */
+int tiramisu_MPI_Comm_rank(int offset);      /* :78 */
+void tiramisu_MPI_Wait(void *request);       /* :85 */
+#define TIRAMISU_B200_MPI_DECL(SUFFIX, T)                                                 \
+    void tiramisu_MPI_Send_##SUFFIX(int count, int dest, int tag, T *data);               \
+    void tiramisu_MPI_Ssend_##SUFFIX(int count, int dest, int tag, T *data);              \
+    void tiramisu_MPI_Isend_##SUFFIX(int count, int dest, int tag, T *data, long *reqs);  \
+    void tiramisu_MPI_Issend_##SUFFIX(int count, int dest, int tag, T *data, long *reqs); \
+    void tiramisu_MPI_Recv_##SUFFIX(int count, int source, int tag, T *store_in);         \
+    void tiramisu_MPI_Irecv_##SUFFIX(int count, int source, int tag, T *store_in, long *reqs);
+TIRAMISU_B200_MPI_DECL(int8, char)           /* src/tiramisu_mpi.cpp:96-192 */
+TIRAMISU_B200_MPI_DECL(int16, short)
+TIRAMISU_B200_MPI_DECL(int32, int)
+TIRAMISU_B200_MPI_DECL(int64, long)
+TIRAMISU_B200_MPI_DECL(uint8, unsigned char)
+TIRAMISU_B200_MPI_DECL(uint16, unsigned short)
+TIRAMISU_B200_MPI_DECL(uint32, unsigned int)
+TIRAMISU_B200_MPI_DECL(uint64, unsigned long)
+TIRAMISU_B200_MPI_DECL(f32, float)
+TIRAMISU_B200_MPI_DECL(f64, double)
+
 /* ===================================================================== B1: generated functions */
 /* benchmarks/halide/wrapper_heat2d.h:10 — in,out f32[H][W] (reference bakes 10000x10000). */
 int heat2d_tiramisu(halide_buffer_t *in, halide_buffer_t *out);

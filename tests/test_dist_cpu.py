@@ -1,0 +1,108 @@
+"""CPU (gloo, world_size 2 and 3) tests of the N>1 host logic: row sharding, halo plans and the
+halo exchange.  The per-shard compute is the oracle here (no GPU in this container); the same
+plan/exchange code drives the CUDA kernels on the GPU box (tests/test_gpu_dist.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from tiramisu_b200 import dist as tdist
+
+
+def test_row_shard_covers_and_balances():
+    for n, w in ((16384, 8), (10, 3), (3842, 4), (7, 7), (100, 1)):
+        spans = [tdist.row_shard(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_stencil_plan_halos():
+    p0 = tdist.stencil_plan(100, 4, 0, 1, 1)
+    p1 = tdist.stencil_plan(100, 4, 1, 1, 1)
+    p3 = tdist.stencil_plan(100, 4, 3, 1, 1)
+    assert (p0.top, p0.bottom) == (0, 1) and (p1.top, p1.bottom) == (1, 1) and (p3.top, p3.bottom) == (1, 0)
+    b = tdist.stencil_plan(1600, 16, 5, 0, 2)          # blurautodist: 2 rows from rank+1 only
+    assert (b.top, b.bottom, b.rows) == (0, 2, 100)
+    assert tdist.stencil_plan(100, 1, 0, 1, 1).local_rows == 100
+    with pytest.raises(ValueError):
+        tdist.stencil_plan(4, 4, 1, 0, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, H, W, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)
+        grid = rng.random((H, W), dtype=np.float32)          # every rank derives the same global grid
+        res = {}
+        # heat2d: 1 halo row each way
+        plan = tdist.stencil_plan(H, world, rank, 1, 1)
+        local = torch.zeros((plan.local_rows, W), dtype=torch.float32)
+        local[plan.top:plan.top + plan.rows] = torch.from_numpy(grid[plan.r0:plan.r1])
+        tdist.exchange_halos(local, plan, 1, 1)
+        out = oracle.heat2d(local.numpy(), "cpu")[plan.top:plan.top + plan.rows]
+        if rank == 0:
+            out[0] = 0                                       # global borders: first/last grid rows
+        if rank == world - 1:
+            out[-1] = 0
+        res["heat"] = (plan.r0, out)
+        # blur: 2 rows from below
+        bplan = tdist.stencil_plan(H, world, rank, 0, 2)
+        blocal = torch.zeros((bplan.local_rows, W), dtype=torch.float32)
+        blocal[:bplan.rows] = torch.from_numpy(grid[bplan.r0:bplan.r1])
+        tdist.exchange_halos(blocal, bplan, 0, 2)
+        res["blur"] = (bplan.r0, oracle.blur_f32(blocal.numpy()))
+        # uint32 box blur, the reference's distributed test (2-row halo from rank+1)
+        img = (np.arange(H)[:, None] + np.arange(W + 2)[None, :]).astype(np.uint32)
+        ulocal = torch.zeros((bplan.rows + 2, W + 2), dtype=torch.int32)
+        ulocal[:bplan.rows] = torch.from_numpy(img[bplan.r0:bplan.r1].view(np.int32))
+        uplan = tdist.HaloPlan(rank, world, bplan.r0, bplan.r1, 0, 2 if rank < world - 1 else 0)
+        tdist.exchange_halos(ulocal[:uplan.local_rows], uplan, 0, 2)
+        if rank == world - 1:                                # last rank fills its own halo (wrapper_test_160.cpp:19-28)
+            ulocal[bplan.rows:] = torch.from_numpy((np.arange(H, H + 2)[:, None] + np.arange(W + 2)[None, :]).astype(np.int32))
+        res["box"] = (bplan.r0, oracle.boxblur_u32(ulocal.numpy().view(np.uint32)))
+        q.put((rank, res))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_stencils_match_single_process(world):
+    import torch.multiprocessing as mp
+    from oracle import oracle
+    H, W = 50, 36
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, H, W, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(7)
+    grid = rng.random((H, W), dtype=np.float32)
+    heat = np.concatenate([got[r]["heat"][1] for r in range(world)])
+    assert np.array_equal(heat, oracle.heat2d(grid, "cpu"))
+    blur = np.concatenate([got[r]["blur"][1] for r in range(world)])
+    assert np.array_equal(blur, oracle.blur_f32(grid))
+    img = (np.arange(H + 2)[:, None] + np.arange(W + 2)[None, :]).astype(np.uint32)
+    box = np.concatenate([got[r]["box"][1] for r in range(world)])
+    assert np.array_equal(box, oracle.boxblur_u32(img))

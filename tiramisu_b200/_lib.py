@@ -80,6 +80,21 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_set_conv_mode", C.c_int, C.c_int)
     sig("tiramisu_b200_lstm", C.c_int, vp, vp, vp, vp, i32, i32, i32, i32)
     sig("tiramisu_b200_set_lstm_mode", C.c_int, C.c_int)
+    sig("tiramisu_b200_comm_unique_id", C.c_int, vp)
+    sig("tiramisu_b200_comm_init", C.c_int, i32, i32, vp)
+    sig("tiramisu_b200_comm_destroy", C.c_int)
+    sig("tiramisu_b200_comm_rank", C.c_int)
+    sig("tiramisu_b200_comm_size", C.c_int)
+    sig("tiramisu_b200_comm_broadcast", C.c_int, vp, u64, i32)
+    sig("tiramisu_MPI_init", C.c_int)
+    sig("tiramisu_MPI_cleanup", None)
+    sig("tiramisu_MPI_global_barrier", None)
+    sig("tiramisu_MPI_Comm_rank", C.c_int, C.c_int)
+    for t in ("int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64", "f32", "f64"):
+        for op in ("Send", "Ssend", "Recv"):
+            sig(f"tiramisu_MPI_{op}_{t}", None, C.c_int, C.c_int, C.c_int, vp)
+        for op in ("Isend", "Issend", "Irecv"):
+            sig(f"tiramisu_MPI_{op}_{t}", None, C.c_int, C.c_int, C.c_int, vp, vp)
     for name, n in (("conv_relu_maxpool_block", 4), ("lstm", 5), ("heat2d_tiramisu", 2), ("heat2dgpu_tiramisu", 3), ("blurxy_tiramisu", 2),
                     ("blurxy_f32_tiramisu", 2), ("boxblur", 2), ("blurautodist_tiramisu", 2),
                     ("sgemm_tiramisu", 6), ("matmul", 6), ("test_162", 5), ("test_164", 6), ("test_167", 3),

@@ -1,13 +1,348 @@
-// comm.cu — distributed runtime: replaces /root/reference/src/tiramisu_mpi.cpp (MPI point-to-point)
-// with NCCL over NVLink.  (first slice: communicator state only; see below)
+// comm.cu — distributed runtime: replaces /root/reference/src/tiramisu_mpi.cpp (MPI point-to-point
+// on MPI_COMM_WORLD) with NCCL over NVLink, one process per GPU.  Same entry points and argument
+// meaning as include/tiramisu/mpi_comm.h so that Tiramisu-generated distributed code
+// (tag_distribute_level + send/recv computations, src/tiramisu_core.cpp:8400-8469) links unchanged:
+//   tiramisu_MPI_init / cleanup / global_barrier / Comm_rank / Wait
+//   tiramisu_MPI_{Send,Ssend,Isend,Issend,Recv,Irecv}_{int8..uint64,f32,f64}
+// Messages are enqueued on the calling thread's stream (stream order replaces MPI's request
+// objects: the non-blocking variants are the same enqueue, tiramisu_MPI_Wait is a no-op for device
+// buffers).  Host buffers — what the reference's CPU code passes — are staged through a pooled
+// device bounce buffer.  NCCL is dlopen'ed lazily so the library has no link-time dependency on it.
+//
+// Bootstrap: tiramisu_b200_comm_init(rank, world, id) with an id from tiramisu_b200_comm_unique_id
+// shipped by any side channel (tiramisu_b200/dist.py uses torch.distributed), or tiramisu_MPI_init()
+// which reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT (torchrun's variables) and
+// exchanges the id over a TCP socket on MASTER_PORT+1 (TIRAMISU_B200_PORT overrides).
 #include "common.cuh"
 #include "tiramisu_b200.h"
 
+#include <arpa/inet.h>
+#include <dlfcn.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+using namespace tb200;
+
+namespace {
+
+// ---- minimal NCCL surface (ABI-stable since NCCL 2.7) -------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5, ncclFloat16 = 6,
+       ncclFloat32 = 7, ncclFloat64 = 8 };
+enum { ncclSum = 0 };
+
+struct Nccl {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+    bool ok = false;
+};
+
+Nccl &nccl()
+{
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);      // reuses torch's copy when already loaded
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+#define TB200_SYM(field, name) *(void **)(&n.field) = dlsym(h, name)
+        TB200_SYM(GetUniqueId, "ncclGetUniqueId");
+        TB200_SYM(CommInitRank, "ncclCommInitRank");
+        TB200_SYM(CommDestroy, "ncclCommDestroy");
+        TB200_SYM(Send, "ncclSend");
+        TB200_SYM(Recv, "ncclRecv");
+        TB200_SYM(GroupStart, "ncclGroupStart");
+        TB200_SYM(GroupEnd, "ncclGroupEnd");
+        TB200_SYM(Broadcast, "ncclBroadcast");
+        TB200_SYM(AllReduce, "ncclAllReduce");
+        TB200_SYM(GetErrorString, "ncclGetErrorString");
+#undef TB200_SYM
+        n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.Send && n.Recv && n.GroupStart && n.GroupEnd &&
+               n.Broadcast && n.AllReduce && n.GetErrorString;
+    });
+    return n;
+}
+
+struct CommState {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    float *scratch = nullptr;        // 1 float for the barrier all-reduce
+};
+CommState g_comm;
+std::mutex g_comm_mu;
+
+// The reference exits with code 28 on any MPI failure (src/tiramisu_mpi.cpp:70-76); we go through
+// tb200::fail so that the error mode (exit vs return) is honoured.
+int nccl_check(ncclResult_t r, const char *where)
+{
+    if (r == 0) return 0;
+    return fail(where, std::string("NCCL: ") + nccl().GetErrorString(r));
+}
+
+bool is_device_pointer(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int p2p(bool send, void *data, size_t bytes, int peer)
+{
+    if (!g_comm.comm) return fail(send ? "tiramisu_MPI_Send" : "tiramisu_MPI_Recv", "communicator not initialised");
+    if (peer < 0 || peer >= g_comm.world) return fail("tiramisu_MPI p2p", "peer rank out of range");
+    Nccl &n = nccl();
+    if (is_device_pointer(data)) {
+        return send ? nccl_check(n.Send(data, bytes, ncclInt8, peer, g_comm.comm, stream()), "ncclSend")
+                    : nccl_check(n.Recv(data, bytes, ncclInt8, peer, g_comm.comm, stream()), "ncclRecv");
+    }
+    // host buffer (the reference's MPI usage): bounce through pooled device memory
+    void *d = pool_alloc(bytes);
+    if (!d) return 1;
+    int rc = 0;
+    if (send) {
+        rc = tiramisu_cuda_memcpy_to_device_async(d, data, bytes);
+        if (!rc) rc = nccl_check(n.Send(d, bytes, ncclInt8, peer, g_comm.comm, stream()), "ncclSend");
+    } else {
+        rc = nccl_check(n.Recv(d, bytes, ncclInt8, peer, g_comm.comm, stream()), "ncclRecv");
+        if (!rc) rc = tiramisu_cuda_memcpy_to_host_async(data, d, bytes);
+        if (!rc) rc = check(cudaStreamSynchronize(stream()), "tiramisu_MPI_Recv");   // blocking receive into host memory
+    }
+    pool_free(d);
+    return rc;
+}
+
+// ---- TCP rendezvous for the unique id (single node, torchrun environment) -------------------------------
+int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+int exchange_id_tcp(int rank, int world, ncclUniqueId *id)
+{
+    const char *addr = getenv("MASTER_ADDR");
+    if (!addr) addr = "127.0.0.1";
+    const int port = env_int("TIRAMISU_B200_PORT", env_int("MASTER_PORT", 29500) + 1);
+    if (rank == 0) {
+        int srv = socket(AF_INET, SOCK_STREAM, 0);
+        if (srv < 0) return fail("tiramisu_MPI_init", "socket() failed");
+        int one = 1;
+        setsockopt(srv, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+        sockaddr_in sa{};
+        sa.sin_family = AF_INET;
+        sa.sin_addr.s_addr = htonl(INADDR_ANY);
+        sa.sin_port = htons((uint16_t)port);
+        if (bind(srv, (sockaddr *)&sa, sizeof(sa)) != 0 || listen(srv, world) != 0) {
+            close(srv);
+            return fail("tiramisu_MPI_init", "cannot listen on the rendezvous port");
+        }
+        for (int i = 1; i < world; i++) {
+            int c = accept(srv, nullptr, nullptr);
+            if (c < 0) { close(srv); return fail("tiramisu_MPI_init", "accept() failed"); }
+            size_t off = 0;
+            while (off < sizeof(*id)) {
+                ssize_t w = write(c, (const char *)id + off, sizeof(*id) - off);
+                if (w <= 0) { close(c); close(srv); return fail("tiramisu_MPI_init", "short write of the NCCL id"); }
+                off += (size_t)w;
+            }
+            close(c);
+        }
+        close(srv);
+        return 0;
+    }
+    sockaddr_in sa{};
+    sa.sin_family = AF_INET;
+    sa.sin_port = htons((uint16_t)port);
+    if (inet_pton(AF_INET, addr, &sa.sin_addr) != 1) {
+        hostent *he = gethostbyname(addr);
+        if (!he) return fail("tiramisu_MPI_init", "cannot resolve MASTER_ADDR");
+        memcpy(&sa.sin_addr, he->h_addr_list[0], sizeof(sa.sin_addr));
+    }
+    for (int attempt = 0; attempt < 600; attempt++) {           // up to ~60 s for rank 0 to come up
+        int c = socket(AF_INET, SOCK_STREAM, 0);
+        if (c < 0) return fail("tiramisu_MPI_init", "socket() failed");
+        if (connect(c, (sockaddr *)&sa, sizeof(sa)) == 0) {
+            size_t off = 0;
+            while (off < sizeof(*id)) {
+                ssize_t r = read(c, (char *)id + off, sizeof(*id) - off);
+                if (r <= 0) break;
+                off += (size_t)r;
+            }
+            close(c);
+            if (off == sizeof(*id)) return 0;
+            return fail("tiramisu_MPI_init", "short read of the NCCL id");
+        }
+        close(c);
+        usleep(100 * 1000);
+    }
+    return fail("tiramisu_MPI_init", "timed out connecting to rank 0");
+}
+
+}  // namespace
+
 namespace tb200 {
 
-int boxblur_halo_exchange(uint32_t *, int, int)
+// Halo rows of the distributed box blur (tests/test_160.cpp:53 gen_communication(); manual form
+// benchmarks/automatic_comm/blurautodist_ref.cpp:42-49): rank p sends its first 2 rows to rank p-1,
+// which stores them in rows [rows, rows+2) of its input.  One grouped exchange on the stream.
+int boxblur_halo_exchange(uint32_t *d_in, int rows, int cols)
 {
-    return 0;   // single process: the caller supplied the halo rows
+    if (!g_comm.comm || g_comm.world == 1) return 0;       // single process: the caller supplied the halo rows
+    Nccl &n = nccl();
+    const size_t row_bytes = (size_t)(cols + 2) * 4;
+    if (nccl_check(n.GroupStart(), "ncclGroupStart")) return 1;
+    int rc = 0;
+    if (g_comm.rank > 0)
+        rc |= nccl_check(n.Send(d_in, 2 * row_bytes, ncclInt8, g_comm.rank - 1, g_comm.comm, stream()), "ncclSend");
+    if (g_comm.rank < g_comm.world - 1)
+        rc |= nccl_check(n.Recv(d_in + (size_t)rows * (cols + 2), 2 * row_bytes, ncclInt8, g_comm.rank + 1,
+                                g_comm.comm, stream()),
+                         "ncclRecv");
+    rc |= nccl_check(n.GroupEnd(), "ncclGroupEnd");
+    return rc;
 }
 
 }  // namespace tb200
+
+// =============================================================================== communicator control
+TB200_API int tiramisu_b200_comm_unique_id(void *out128)
+{
+    if (!nccl().ok) return fail(__func__, "libnccl.so.2 not found");
+    return nccl_check(nccl().GetUniqueId(reinterpret_cast<ncclUniqueId *>(out128)), "ncclGetUniqueId");
+}
+
+TB200_API int tiramisu_b200_comm_init(int32_t rank, int32_t world, const void *id128)
+{
+    if (!nccl().ok) return fail(__func__, "libnccl.so.2 not found");
+    if (world < 1 || rank < 0 || rank >= world || !id128) return fail(__func__, "bad rank/world/id");
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    if (g_comm.comm) return fail(__func__, "communicator already initialised");
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    ncclComm_t c = nullptr;
+    if (nccl_check(nccl().CommInitRank(&c, world, id, rank), "ncclCommInitRank")) return 1;
+    g_comm.comm = c;
+    g_comm.rank = rank;
+    g_comm.world = world;
+    TB200_CHECK(cudaMalloc(&g_comm.scratch, sizeof(float)));
+    TB200_CHECK(cudaMemset(g_comm.scratch, 0, sizeof(float)));
+    return 0;
+}
+
+TB200_API int tiramisu_b200_comm_destroy(void)
+{
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    if (!g_comm.comm) return 0;
+    cudaStreamSynchronize(stream());
+    int rc = nccl_check(nccl().CommDestroy(g_comm.comm), "ncclCommDestroy");
+    cudaFree(g_comm.scratch);
+    g_comm = CommState();
+    return rc;
+}
+
+TB200_API int tiramisu_b200_comm_rank(void) { return g_comm.rank; }
+TB200_API int tiramisu_b200_comm_size(void) { return g_comm.world; }
+
+// Replicate `bytes` of device memory from `root` to every rank (B panels of the row-sharded sgemm,
+// conv / LSTM weights of the batch-sharded blocks).
+TB200_API int tiramisu_b200_comm_broadcast(void *dev_buf, uint64_t bytes, int32_t root)
+{
+    if (!g_comm.comm) return fail(__func__, "communicator not initialised");
+    return nccl_check(nccl().Broadcast(dev_buf, dev_buf, bytes, ncclInt8, root, g_comm.comm, stream()), "ncclBroadcast");
+}
+
+// Grouped send/recv: up to `n` messages enqueued as ONE NCCL group on the stream (no ordering
+// deadlocks between neighbours, one launch).  peer < 0 entries are skipped.
+TB200_API int tiramisu_b200_comm_exchange(int32_t n, const int32_t *send_peer, void *const *send_buf,
+                                          const uint64_t *send_bytes, const int32_t *recv_peer, void *const *recv_buf,
+                                          const uint64_t *recv_bytes)
+{
+    if (!g_comm.comm) return fail(__func__, "communicator not initialised");
+    Nccl &nc = nccl();
+    if (nccl_check(nc.GroupStart(), "ncclGroupStart")) return 1;
+    int rc = 0;
+    for (int i = 0; i < n; i++) {
+        if (send_peer[i] >= 0)
+            rc |= nccl_check(nc.Send(send_buf[i], send_bytes[i], ncclInt8, send_peer[i], g_comm.comm, stream()), "ncclSend");
+        if (recv_peer[i] >= 0)
+            rc |= nccl_check(nc.Recv(recv_buf[i], recv_bytes[i], ncclInt8, recv_peer[i], g_comm.comm, stream()), "ncclRecv");
+    }
+    rc |= nccl_check(nc.GroupEnd(), "ncclGroupEnd");
+    return rc;
+}
+
+// =============================================================================== src/tiramisu_mpi.cpp names
+TB200_API int tiramisu_MPI_init(void)
+{
+    // src/tiramisu_mpi.cpp:8-17: MPI_Init_thread(FUNNELED) and return the rank.
+    if (g_comm.comm) return g_comm.rank;
+    const int rank = env_int("RANK", 0), world = env_int("WORLD_SIZE", 1), local = env_int("LOCAL_RANK", rank);
+    if (check(cudaSetDevice(local), "tiramisu_MPI_init")) return -1;
+    ncclUniqueId id;
+    memset(&id, 0, sizeof(id));
+    if (rank == 0 && tiramisu_b200_comm_unique_id(&id)) return -1;
+    if (world > 1 && exchange_id_tcp(rank, world, &id)) return -1;
+    if (tiramisu_b200_comm_init(rank, world, &id)) return -1;
+    return rank;
+}
+
+TB200_API void tiramisu_MPI_cleanup(void) { tiramisu_b200_comm_destroy(); }      // :19-21 MPI_Finalize
+
+TB200_API void tiramisu_MPI_global_barrier(void)                                 // :23 MPI_Barrier
+{
+    if (!g_comm.comm) return;
+    if (nccl_check(nccl().AllReduce(g_comm.scratch, g_comm.scratch, 1, ncclFloat32, ncclSum, g_comm.comm, stream()),
+                   "ncclAllReduce"))
+        return;
+    check(cudaStreamSynchronize(stream()), "tiramisu_MPI_global_barrier");
+}
+
+TB200_API int tiramisu_MPI_Comm_rank(int offset) { return g_comm.rank + offset; }   // :78-83
+
+TB200_API void tiramisu_MPI_Wait(void *)                                            // :85-89
+{
+    // stream order already sequences the message; host-buffer receives synchronise inside p2p()
+}
+
+// src/tiramisu_mpi.cpp:96-192 — (count, peer, tag, data[, reqs]); tags are implicit in NCCL's
+// per-peer FIFO order, request handles are not needed (see tiramisu_MPI_Wait).
+#define TB200_MPI_TYPE(SUFFIX, T)                                                                                     \
+    TB200_API void tiramisu_MPI_Send_##SUFFIX(int count, int dest, int, T *data) { p2p(true, data, (size_t)count * sizeof(T), dest); }   \
+    TB200_API void tiramisu_MPI_Ssend_##SUFFIX(int count, int dest, int, T *data) { p2p(true, data, (size_t)count * sizeof(T), dest); }  \
+    TB200_API void tiramisu_MPI_Isend_##SUFFIX(int count, int dest, int, T *data, long *) { p2p(true, data, (size_t)count * sizeof(T), dest); }  \
+    TB200_API void tiramisu_MPI_Issend_##SUFFIX(int count, int dest, int, T *data, long *) { p2p(true, data, (size_t)count * sizeof(T), dest); } \
+    TB200_API void tiramisu_MPI_Recv_##SUFFIX(int count, int src, int, T *data) { p2p(false, data, (size_t)count * sizeof(T), src); }    \
+    TB200_API void tiramisu_MPI_Irecv_##SUFFIX(int count, int src, int, T *data, long *) { p2p(false, data, (size_t)count * sizeof(T), src); }
+
+TB200_MPI_TYPE(int8, char)
+TB200_MPI_TYPE(int16, short)
+TB200_MPI_TYPE(int32, int)
+TB200_MPI_TYPE(int64, long)
+TB200_MPI_TYPE(uint8, unsigned char)
+TB200_MPI_TYPE(uint16, unsigned short)
+TB200_MPI_TYPE(uint32, unsigned int)
+TB200_MPI_TYPE(uint64, unsigned long)
+TB200_MPI_TYPE(f32, float)
+TB200_MPI_TYPE(f64, double)
+
+// include/tiramisu/mpi_comm.h:6-8 declares these three OUTSIDE its extern "C" block, so wrappers
+// such as tests/wrapper_test_160.cpp:11 reference the C++-mangled names; export those spellings too.
+extern "C" __attribute__((visibility("default"), alias("tiramisu_MPI_init"))) int _Z17tiramisu_MPI_initv();
+extern "C" __attribute__((visibility("default"), alias("tiramisu_MPI_cleanup"))) void _Z20tiramisu_MPI_cleanupv();
+extern "C" __attribute__((visibility("default"), alias("tiramisu_MPI_global_barrier"))) void _Z27tiramisu_MPI_global_barrierv();

@@ -1,0 +1,103 @@
+"""Row/batch sharding and halo exchange for the paths that shard — the host-side
+logic that replaces tag_distribute_level + create_xfer/gen_communication in the reference
+(src/tiramisu_core.cpp:599-628, 8778-8900, 9101-9295) with static owner-computes tables.
+
+One process per GPU.  torch.distributed is plumbing only: NCCL send/recv (CUDA tensors) on the
+GPU box, gloo (CPU tensors) in the CPU tests — the exchange code is the same.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+from . import _lib
+
+
+def row_shard(n_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block partition of [0, n_rows) (1-D block distribution of the outermost loop,
+    src/tiramisu_core.cpp:8997-9044).  Remainder rows go to the lowest ranks."""
+    base, rem = divmod(n_rows, world)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)
+
+
+@dataclass(frozen=True)
+class HaloPlan:
+    """What rank `rank` must hold besides its own rows [r0, r1): `top` rows owned by rank-1 and
+    `bottom` rows owned by rank+1 (0 at the ends of the grid)."""
+    rank: int
+    world: int
+    r0: int
+    r1: int
+    top: int
+    bottom: int
+
+    @property
+    def rows(self) -> int:
+        return self.r1 - self.r0
+
+    @property
+    def local_rows(self) -> int:
+        return self.top + self.rows + self.bottom
+
+
+def stencil_plan(n_rows: int, world: int, rank: int, up: int, down: int) -> HaloPlan:
+    """A stencil that reads rows [y-up, y+down] of its input: heat2d up=down=1
+    (benchmarks/halide/heat2d_dist_tiramisu.cpp:133-153 exchanges 1 row each way), the blurs
+    up=0, down=2 (benchmarks/automatic_comm/blurautodist_ref.cpp:42-49: 2 rows from rank+1 only).
+    exchange sets = sender_owned ∩ (receiver_needed − receiver_owned)."""
+    r0, r1 = row_shard(n_rows, world, rank)
+    if r1 - r0 < max(up, down) and world > 1:
+        raise ValueError("shard thinner than the stencil halo")
+    return HaloPlan(rank, world, r0, r1, up if rank > 0 else 0, down if rank < world - 1 else 0)
+
+
+def exchange_halos(local, plan: HaloPlan, up: int, down: int, group=None):
+    """local: tensor [plan.local_rows, W] whose rows [top, top+rows) are owned.  Fills the halo rows
+    from the neighbours: my first `down` owned rows go to rank-1 (its bottom halo), my last `up`
+    owned rows go to rank+1 (its top halo).  One batched isend/irecv (a single NCCL group)."""
+    import torch.distributed as dist
+    if plan.world == 1:
+        return
+    ops = []
+    own0 = plan.top
+    own1 = plan.top + plan.rows
+    if plan.rank > 0:
+        if down:
+            ops.append(dist.P2POp(dist.isend, local[own0:own0 + down], plan.rank - 1, group))
+        if plan.top:
+            ops.append(dist.P2POp(dist.irecv, local[0:plan.top], plan.rank - 1, group))
+    if plan.rank < plan.world - 1:
+        if up:
+            ops.append(dist.P2POp(dist.isend, local[own1 - up:own1], plan.rank + 1, group))
+        if plan.bottom:
+            ops.append(dist.P2POp(dist.irecv, local[own1:own1 + plan.bottom], plan.rank + 1, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def batch_shard(batch: int, world: int, rank: int) -> tuple[int, int]:
+    """conv / LSTM shard over the batch dimension: independent units, no per-step communication."""
+    return row_shard(batch, world, rank)
+
+
+# ---- C-level communicator (tiramisu_MPI_* over NCCL), bootstrapped through torch.distributed ---------
+def comm_init_from_torch(group=None) -> int:
+    """Create the library's own NCCL communicator (used by boxblur's halo exchange and the
+    tiramisu_MPI_* shims), shipping the unique id over an existing torch.distributed group."""
+    import torch.distributed as dist
+    L = _lib.lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        _lib.check(L.tiramisu_b200_comm_unique_id(buf), "tiramisu_b200_comm_unique_id")
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0, group=group)
+    idbuf = (C.c_char * 128).from_buffer_copy(box[0])
+    _lib.check(L.tiramisu_b200_comm_init(rank, world, idbuf), "tiramisu_b200_comm_init")
+    return rank
+
+
+def comm_destroy() -> None:
+    _lib.check(_lib.lib().tiramisu_b200_comm_destroy(), "tiramisu_b200_comm_destroy")
