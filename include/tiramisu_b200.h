@@ -75,6 +75,10 @@ int tiramisu_cublas_dgemm(double *A, double *B, double *C, uint64_t M, uint64_t 
 /* 0 = auto (tensor cores when addressable), 1 = force exact fp32 SIMT, 2 = force tcgen05
  * (fails if not addressable).  Returns the previous mode. */
 int tiramisu_b200_set_gemm_mode(int mode);
+/* Which tcgen05 GEMM kernel the tensor path uses: 0 = auto (by problem size), 1 = one output tile
+ * per CTA, 2 = persistent single-CTA tiles (128x256), 3 = persistent CTA pairs (cta_group::2,
+ * 256x256).  Tuning/diagnostic knob; returns the previous value. */
+int tiramisu_b200_set_gemm_kernel(int kernel);
 
 /* src/tiramisu_externs.cpp:8-54 */
 int8_t *tiramisu_address_of_int8(halide_buffer_t *buffer, unsigned long index);
@@ -125,6 +129,9 @@ int tiramisu_b200_set_conv_mode(int mode);
 int tiramisu_b200_lstm(const float *Weights, const float *biases, const float *x, float *y,
                        int32_t F, int32_t B, int32_t L, int32_t T);
 int tiramisu_b200_set_lstm_mode(int mode);
+/* Recurrence engine of the tensor path: 0 = auto, 1 = one launch per cell, 2 = persistent layer
+ * kernel (recurrent weights resident in shared memory, device-wide step barrier). */
+int tiramisu_b200_set_lstm_kernel(int kernel);
 
 /* ===================================================================== B2: distributed runtime
  * NCCL over NVLink, one process per GPU, replacing src/tiramisu_mpi.cpp (MPI point-to-point).

@@ -88,6 +88,48 @@ def test_sgemm_tf32_random_within_tolerance(api, tensor, N, M, K):
     assert _rel_err(got, want) < TF32_RTOL
 
 
+# ------------------------------------------------------------------------------ every tcgen05 kernel variant
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("N,M,K", [(256, 256, 32), (512, 768, 256), (1024, 1024, 1024), (300, 700, 96),
+                                   (136, 264, 100), (2048, 512, 160)])
+def test_sgemm_each_kernel_small_int_exact(api, tensor, kernel, N, M, K):
+    """One-tile-per-CTA (1), persistent 128x256 (2) and persistent CTA-pair 256x256 (3) kernels all
+    give the oracle's result bit for bit on integer operands, including ragged tiles and K tails."""
+    prev = api.set_gemm_kernel(kernel)
+    try:
+        refdata.srand(kernel)
+        A = refdata.rand_small_ints((N, K))
+        B = refdata.rand_small_ints((K, M))
+        Cm = refdata.rand_small_ints((N, M))
+        got = _sgemm(api, N, M, K, 3.0, 2.0, A, B, Cm)
+        assert np.array_equal(got, oracle.sgemm(3.0, 2.0, A, B, Cm))
+    finally:
+        api.set_gemm_kernel(prev)
+
+
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_sgemm_persistent_many_tiles_per_cta(api, tensor, kernel):
+    """More tiles than SMs: every CTA loops (both TMEM accumulator buffers, ring wrap-around)."""
+    import torch
+    prev = api.set_gemm_kernel(kernel)
+    try:
+        M, N, K = 4096, 4608, 96
+        g = torch.Generator(device="cuda").manual_seed(7)
+        A = torch.randint(-4, 5, (M, K), device="cuda", generator=g).float()
+        B = torch.randint(-4, 5, (K, N), device="cuda", generator=g).float()
+        Cm = torch.randint(-4, 5, (M, N), device="cuda", generator=g).float()
+        want = 3.0 * (A.double() @ B.double()) + 2.0 * Cm.double()
+        api.set_stream(torch.cuda.current_stream().cuda_stream)
+        try:
+            api.cublas_sgemm(A.data_ptr(), B.data_ptr(), Cm.data_ptr(), M, N, K, 3.0, 2.0)
+            torch.cuda.synchronize()
+        finally:
+            api.set_stream(None)
+        assert bool((Cm.double() == want).all())
+    finally:
+        api.set_gemm_kernel(prev)
+
+
 def test_matmul_gpu_wrapper_check(api):
     """sgemm/gpu/wrapper.cpp: Consts={3,2}, rand()%10-5 operands, exact comparison; times recorded."""
     refdata.srand(0)

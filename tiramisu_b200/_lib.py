@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_kernel_launches", u64)
     sig("tiramisu_b200_pool_trim", C.c_int)
     sig("tiramisu_b200_set_gemm_mode", C.c_int, C.c_int)
+    sig("tiramisu_b200_set_gemm_kernel", C.c_int, C.c_int)
     sig("tiramisu_cuda_memcpy_to_device", C.c_int, vp, vp, u64)
     sig("tiramisu_cuda_memcpy_to_host", C.c_int, vp, vp, u64)
     sig("tiramisu_cuda_memcpy_to_symbol", C.c_int, vp, vp, u64)
@@ -80,6 +81,7 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_set_conv_mode", C.c_int, C.c_int)
     sig("tiramisu_b200_lstm", C.c_int, vp, vp, vp, vp, i32, i32, i32, i32)
     sig("tiramisu_b200_set_lstm_mode", C.c_int, C.c_int)
+    sig("tiramisu_b200_set_lstm_kernel", C.c_int, C.c_int)
     sig("tiramisu_b200_comm_unique_id", C.c_int, vp)
     sig("tiramisu_b200_comm_init", C.c_int, i32, i32, vp)
     sig("tiramisu_b200_comm_destroy", C.c_int)

@@ -104,6 +104,11 @@ def set_lstm_mode(mode: int) -> int:
     return int(_lib.lib().tiramisu_b200_set_lstm_mode(mode))
 
 
+def set_lstm_kernel(kernel: int) -> int:
+    """0 auto, 1 one launch per cell, 2 persistent layer kernel."""
+    return int(_lib.lib().tiramisu_b200_set_lstm_kernel(kernel))
+
+
 # ---- B2 runtime, for callers that manage device memory themselves ------------------------------------
 def set_stream(cuda_stream: int | None) -> None:
     """Launch on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); None = per-thread default."""
@@ -121,6 +126,11 @@ def kernel_launches() -> int:
 def set_gemm_mode(mode: int) -> int:
     """0 auto, 1 exact fp32 SIMT, 2 force tcgen05 TF32."""
     return int(_lib.lib().tiramisu_b200_set_gemm_mode(mode))
+
+
+def set_gemm_kernel(kernel: int) -> int:
+    """0 auto, 1 one-tile-per-CTA, 2 persistent 128x256, 3 persistent CTA pairs (cta_group::2)."""
+    return int(_lib.lib().tiramisu_b200_set_gemm_kernel(kernel))
 
 
 def cublas_sgemm(A_ptr, B_ptr, C_ptr, M, N, K, alpha, beta, ldA=0, ldB=0, ldC=0, offA=0, offB=0, offC=0,

@@ -48,6 +48,81 @@ bool type_mismatch(const BufView &v, int bits)
     return v.ndim > 0 && v.elem_bits != 0 && v.elem_bits != bits;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Host-resident stencil grids: a 3-stage row-chunk pipeline instead of copy-all / compute / copy-all.
+//   copy-in stream : H2D of the input rows chunk c needs (incl. its halo rows)
+//   launch stream  : the kernel on output rows [y0, y1) of chunk c   (the calling thread's stream)
+//   copy-out stream: D2H of those output rows
+// PCIe is full duplex, so chunk c+1 uploads while chunk c-1 downloads and chunk c computes; the
+// reference's generated host code copies everything in, runs, copies everything out
+// (src/tiramisu_codegen_halide.cpp:2559-2598).  Needs page-locked host buffers to overlap (with
+// pageable memory cudaMemcpyAsync degrades to staged copies — still correct).
+struct PipeStreams {
+    cudaStream_t up = nullptr, down = nullptr;
+    std::vector<cudaEvent_t> ev;
+    int ensure(size_t n_events)
+    {
+        if (!up) TB200_CHECK(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+        if (!down) TB200_CHECK(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+        while (ev.size() < n_events) {
+            cudaEvent_t e;
+            TB200_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev.push_back(e);
+        }
+        return 0;
+    }
+};
+thread_local PipeStreams t_pipe;
+
+constexpr size_t kPipelineMinBytes = (size_t)16 << 20;      // below this one copy each way is as fast
+constexpr size_t kPipelineChunkBytes = (size_t)32 << 20;
+
+// out row y (0 <= y < OH, OW elements wide) reads input rows [y - up, y + down] of the H x W input.
+template <class Launch>
+int stencil_pipelined(const char *fn, const float *h_in, float *h_out, int H, int W, int OH, int OW, int up, int down,
+                      Launch launch)
+{
+    (void)fn;
+    const size_t in_row = (size_t)W * 4, out_row = (size_t)OW * 4;
+    int rows_per_chunk = (int)(kPipelineChunkBytes / in_row);
+    if (rows_per_chunk < 64) rows_per_chunk = 64;
+    const int n_chunks = (OH + rows_per_chunk - 1) / rows_per_chunk;
+    if (t_pipe.ensure(2 * (size_t)n_chunks + 2)) return 1;
+    cudaStream_t s = stream();
+    float *d_in = reinterpret_cast<float *>(pool_alloc((size_t)H * in_row));
+    float *d_out = reinterpret_cast<float *>(pool_alloc((size_t)OH * out_row));
+    if (!d_in || !d_out) return 1;
+    cudaEvent_t e_alloc = t_pipe.ev[2 * n_chunks], e_fin = t_pipe.ev[2 * n_chunks + 1];
+    TB200_CHECK(cudaEventRecord(e_alloc, s));
+    TB200_CHECK(cudaStreamWaitEvent(t_pipe.up, e_alloc, 0));
+    TB200_CHECK(cudaStreamWaitEvent(t_pipe.down, e_alloc, 0));
+    int uploaded = 0;                                            // input rows [0, uploaded) are on the device
+    for (int c = 0; c < n_chunks; c++) {
+        const int y0 = c * rows_per_chunk, y1 = (y0 + rows_per_chunk < OH) ? y0 + rows_per_chunk : OH;
+        int need = y1 + down;                                    // last input row read by this chunk, + 1
+        if (need > H || c == n_chunks - 1) need = H;
+        if (need > uploaded) {
+            TB200_CHECK(cudaMemcpyAsync(d_in + (size_t)uploaded * W, h_in + (size_t)uploaded * W,
+                                        (size_t)(need - uploaded) * in_row, cudaMemcpyHostToDevice, t_pipe.up));
+            uploaded = need;
+        }
+        (void)up;                                                // rows above y0 were uploaded by earlier chunks
+        TB200_CHECK(cudaEventRecord(t_pipe.ev[2 * c], t_pipe.up));
+        TB200_CHECK(cudaStreamWaitEvent(s, t_pipe.ev[2 * c], 0));
+        if (launch(d_in, d_out, y0, y1)) return 1;
+        TB200_CHECK(cudaEventRecord(t_pipe.ev[2 * c + 1], s));
+        TB200_CHECK(cudaStreamWaitEvent(t_pipe.down, t_pipe.ev[2 * c + 1], 0));
+        TB200_CHECK(cudaMemcpyAsync(h_out + (size_t)y0 * OW, d_out + (size_t)y0 * OW, (size_t)(y1 - y0) * out_row,
+                                    cudaMemcpyDeviceToHost, t_pipe.down));
+    }
+    TB200_CHECK(cudaEventRecord(e_fin, t_pipe.down));
+    TB200_CHECK(cudaStreamWaitEvent(s, e_fin, 0));
+    pool_free(d_in);
+    pool_free(d_out);
+    return finish();
+}
+
 // ---------------------------------------------------------------------------------------------
 int heat2d_common(const char *fn, halide_buffer_t *in, halide_buffer_t *out, int H, int W, int form)
 {
@@ -58,6 +133,11 @@ int heat2d_common(const char *fn, halide_buffer_t *in, halide_buffer_t *out, int
     if (vo.ndim >= 2 && (vo.extent[0] != W || vo.extent[1] != H)) return bad(fn, "in/out extents differ");
     if (H < 1 || W < 1) return bad(fn, "empty grid");
     const size_t bytes = (size_t)H * W * sizeof(float);
+    if (!vi.on_device && !vo.on_device && bytes >= kPipelineMinBytes)
+        return stencil_pipelined(fn, reinterpret_cast<const float *>(vi.ptr), reinterpret_cast<float *>(vo.ptr), H, W, H,
+                                 W, 1, 1, [&](const float *di, float *dout_, int y0, int y1) {
+                                     return tiramisu_b200_heat2d(di, dout_, H, W, form, y0, y1);
+                                 });
     DeviceArg din, dout;
     if (din.bind(vi, bytes, true) || dout.bind(vo, bytes, false)) return 1;
     if (tiramisu_b200_heat2d(din.as<float>(), dout.as<float>(), H, W, form, 0, H)) return 1;
@@ -153,6 +233,18 @@ TB200_API int blurxy_tiramisu(halide_buffer_t *in, halide_buffer_t *out)
 
 TB200_API int blurxy_f32_tiramisu(halide_buffer_t *in, halide_buffer_t *out)
 {
+    BufView vi, vo;
+    if (view_of(in, &vi) && view_of(out, &vo) && !vi.on_device && !vo.on_device && vi.ndim == 2 && vo.ndim == 2 &&
+        !type_mismatch(vi, 32) && !type_mismatch(vo, 32)) {
+        const int W = (int)vi.extent[0], H = (int)vi.extent[1];
+        if (H > 2 && W > 2 && vo.extent[0] == W - 2 && vo.extent[1] == H - 2 &&
+            (size_t)H * W * 4 >= kPipelineMinBytes)
+            return stencil_pipelined(__func__, reinterpret_cast<const float *>(vi.ptr),
+                                     reinterpret_cast<float *>(vo.ptr), H, W, H - 2, W - 2, 0, 2,
+                                     [&](const float *di, float *dout_, int y0, int y1) {
+                                         return tiramisu_b200_blur_f32(di, dout_, H, W, y0, y1);
+                                     });
+    }
     return blur_common<float>(__func__, in, out, 1, 16384, 16384, 2, launch_blur_f32);
 }
 

@@ -247,6 +247,233 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
     }
 }
 
+
+// ================================================================================================
+// Persistent variant for large problems: one CTA (CG = 1) or one CTA pair (CG = 2, cta_group::2)
+// per SM / SM pair loops over 128*CG x 256 output tiles.
+//   warp 0    : TMA producer      warp 1 : MMA issuer (leader CTA only when CG = 2) + TMEM owner
+//   warps 2-9 : epilogue, two warps per TMEM lane quarter (each takes 128 of the 256 columns)
+// Two 256-column accumulator buffers fill TMEM (512 columns): the epilogue of tile i (TMEM ->
+// registers -> alpha/beta -> global) overlaps the MMAs of tile i+1, which the one-tile-per-CTA
+// kernel above cannot do (r01 ncu: tensor pipe idle during every epilogue, 4096^3 at 56 %).
+// CG = 2: the pair shares one 256 x 256 tile; each CTA loads its own 128 rows of A and 128 of the
+// 256 columns of B, so the L2 -> shared-memory traffic per FLOP drops by a third (TF32 operands
+// are 4 bytes wide: at 128 x 256 per CTA the fill rate, not the tensor pipe, is the limit).
+constexpr int P_BN = 256;
+constexpr int kThreadsP = 320;
+constexpr int kEpiWarps = 8;
+
+template <int CG> struct PCfg {
+    static constexpr int B_COLS = P_BN / CG;                       // B columns held by one CTA
+    static constexpr int B_TILE_BYTES = B_COLS * BK * 4;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES; // per CTA
+    static constexpr int STAGES = (CG == 2) ? 6 : 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int CG, bool B_MN>
+__global__ void __launch_bounds__(kThreadsP, 1)
+tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
+                                    const __grid_constant__ CUtensorMap map_b, const GemmParams p)
+{
+    using C_ = PCfg<CG>;
+    constexpr int STAGES = C_::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + STAGES * A_TILE_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * C_::STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full = empty_bar + STAGES;       // [2]
+    uint64_t *tmem_empty = tmem_full + 2;           // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x / CG;
+    const int num_clusters = gridDim.x / CG;
+    const int num_tiles = p.num_m * p.num_n;
+    const int num_kb = (p.K + BK - 1) / BK;
+    constexpr int TILE_M = BM * CG;
+
+    auto tile_origin = [&](int t, int &m0, int &n0) {
+        const int tiles_per_group = p.group_m * p.num_n;
+        const int group = t / tiles_per_group;
+        const int first_m = group * p.group_m;
+        const int gsz = min(p.num_m - first_m, p.group_m);
+        m0 = (first_m + (t % tiles_per_group) % gsz) * TILE_M;
+        n0 = ((t % tiles_per_group) / gsz) * P_BN;
+    };
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; s++) {
+                ptx::mbar_init(&full_bar[s], 1);
+                ptx::mbar_init(&empty_bar[s], 1);
+            }
+            for (int b = 0; b < 2; b++) {
+                ptx::mbar_init(&tmem_full[b], 1);
+                ptx::mbar_init(&tmem_empty[b], CG * kEpiWarps);
+            }
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        if (CG == 2) { ptx::tmem_alloc_cg2(tmem_slot, 512); ptx::tmem_relinquish_cg2(); }
+        else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    }
+    ptx::tc_fence_before_sync();
+    if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (every CTA loads its own A rows and its own share of B) =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                int m0, n0;
+                tile_origin(tile, m0, n0);
+                m0 += (int)cta_rank * BM;
+                n0 += (int)cta_rank * C_::B_COLS;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    // the pair's full barrier lives in the leader and expects both CTAs' bytes
+                    if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], CG * C_::STAGE_BYTES);
+                    const int k0 = kb * BK;
+                    uint8_t *adst = smem_a + s * A_TILE_BYTES;
+                    uint8_t *bdst = smem_b + s * C_::B_TILE_BYTES;
+                    if (CG == 2) {
+                        ptx::tma_load_2d_cg2(adst, &map_a, &full_bar[s], k0, m0);
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < C_::B_COLS / 32; j++)
+                                ptx::tma_load_2d_cg2(bdst + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
+                        } else {
+                            ptx::tma_load_2d_cg2(bdst, &map_b, &full_bar[s], k0, n0);
+                        }
+                    } else {
+                        ptx::tma_load_2d(adst, &map_a, &full_bar[s], k0, m0);
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < C_::B_COLS / 32; j++)
+                                ptx::tma_load_2d(bdst + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
+                        } else {
+                            ptx::tma_load_2d(bdst, &map_b, &full_bar[s], k0, n0);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = ptx::make_idesc_tf32(TILE_M, P_BN, false, B_MN);
+            uint32_t it = 0, local = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
+                const uint32_t buf = local & 1;
+                ptx::mbar_wait(&tmem_empty[buf], ((local >> 1) & 1) ^ 1);      // epilogue drained this buffer
+                ptx::tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + buf * P_BN;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_TILE_BYTES);
+                    const uint32_t b_addr = ptx::smem_u32(smem_b + s * C_::B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t da = ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024);
+                        const uint64_t db = B_MN ? ptx::make_smem_desc(b_addr + k * (UMMA_K * 128), p.b_lbo, p.b_sbo,
+                                                                       ptx::kLayoutSw128Base32)
+                                                 : ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024);
+                        if (CG == 2) ptx::mma_tf32_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
+                        else ptx::mma_tf32_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+                    }
+                    if (CG == 2) ptx::mma_commit_cg2(&empty_bar[s], 3); else ptx::mma_commit(&empty_bar[s]);
+                }
+                if (CG == 2) ptx::mma_commit_cg2(&tmem_full[buf], 3); else ptx::mma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global, overlapped with the next tile's MMAs =====
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;              // which 128 of the 256 accumulator columns
+        const bool use_c = p.beta != 0.0f;
+        uint32_t local = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
+            const uint32_t buf = local & 1;
+            int m0, n0;
+            tile_origin(tile, m0, n0);
+            const int row = m0 + (int)cta_rank * BM + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            float *crow = p.C + (size_t)row * p.ldC;
+            ptx::mbar_wait(&tmem_full[buf], (local >> 1) & 1);
+            ptx::tc_fence_after_sync();
+#pragma unroll 1
+            for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+                uint32_t r[32];
+                __syncwarp();
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * P_BN + (uint32_t)c0, r);
+                ptx::tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int col = n0 + c0 + j;
+                        if (col + 3 < p.N) {
+                            float4 o;
+                            o.x = __fmul_rn(__uint_as_float(r[j + 0]), p.alpha);
+                            o.y = __fmul_rn(__uint_as_float(r[j + 1]), p.alpha);
+                            o.z = __fmul_rn(__uint_as_float(r[j + 2]), p.alpha);
+                            o.w = __fmul_rn(__uint_as_float(r[j + 3]), p.alpha);
+                            float4 *dst = reinterpret_cast<float4 *>(crow + col);
+                            if (use_c) {
+                                const float4 c = *dst;
+                                o.x = __fadd_rn(o.x, __fmul_rn(c.x, p.beta));
+                                o.y = __fadd_rn(o.y, __fmul_rn(c.y, p.beta));
+                                o.z = __fadd_rn(o.z, __fmul_rn(c.z, p.beta));
+                                o.w = __fadd_rn(o.w, __fmul_rn(c.w, p.beta));
+                            }
+                            *dst = o;
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (col + u < p.N) {
+                                    float o = __fmul_rn(__uint_as_float(r[j + u]), p.alpha);
+                                    if (use_c) o = __fadd_rn(o, __fmul_rn(crow[col + u], p.beta));
+                                    crow[col + u] = o;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // this warp has read its part of the buffer: let the MMA issuer (in the leader) reuse it
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 2) ptx::mbar_arrive_remote(&tmem_empty[buf], 0);
+                else ptx::mbar_arrive(&tmem_empty[buf]);
+            }
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int BN, bool B_MN>
@@ -292,7 +519,63 @@ int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, flo
     return post_launch("tiramisu_sm100_gemm_tf32");
 }
 
+template <int CG, bool B_MN>
+int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N, int K, float alpha, float beta,
+                         int64_t ldA, int64_t ldB, int64_t ldC)
+{
+    using C_ = PCfg<CG>;
+    CUtensorMap map_a, map_b;
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        uint64_t str[1] = {(uint64_t)ldA * 4};
+        uint32_t box[2] = {BK, BM};
+        if (make_tensor_map_f32(&map_a, A, 2, dims, str, box)) return 1;
+    }
+    if (B_MN) {
+        uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
+        uint64_t str[1] = {(uint64_t)ldB * 4};
+        uint32_t box[2] = {32, BK};
+        if (make_tensor_map_f32(&map_b, B, 2, dims, str, box, kTmaSwizzle128Atom32)) return 1;
+    } else {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)ldB * 4};
+        uint32_t box[2] = {BK, (uint32_t)C_::B_COLS};
+        if (make_tensor_map_f32(&map_b, B, 2, dims, str, box)) return 1;
+    }
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldC = ldC;
+    p.num_m = (M + BM * CG - 1) / (BM * CG);
+    p.num_n = (N + P_BN - 1) / P_BN;
+    p.group_m = 16 / CG;
+    p.b_lbo = BK * 128;
+    p.b_sbo = 512;
+    auto kern = tiramisu_sm100_gemm_tf32_persistent<CG, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB200_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int num_tiles = p.num_m * p.num_n;
+    int clusters = sm_count() / CG;
+    if (clusters > num_tiles) clusters = num_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * CG));
+    cfg.blockDim = dim3(kThreadsP);
+    cfg.dynamicSmemBytes = C_::SMEM_BYTES;
+    cfg.stream = stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TB200_CHECK(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, p));
+    return post_launch("tiramisu_sm100_gemm_tf32_persistent");
+}
+
 std::atomic<int> g_gemm_mode{0};
+std::atomic<int> g_gemm_kernel{0};       // 0 auto, 1 one-tile-per-CTA, 2 persistent CG=1, 3 persistent CG=2
 
 }  // namespace
 
@@ -318,17 +601,34 @@ bool gemm_tc_addressable(const float *A, const float *B, const float *C, uint64_
 int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha,
                 float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tB)
 {
+    const int m = (int)M, n = (int)N, k = (int)K;
+    // Kernel choice: the persistent CTA-pair kernel once there is at least ~one 256x256 tile per SM
+    // pair, the persistent single-CTA kernel for mid sizes, the one-tile-per-CTA kernel below that.
+    int kernel = g_gemm_kernel.load();
+    if (const char *e = getenv("TB200_GEMM_KERNEL")) kernel = atoi(e);
+    const uint64_t sms = (uint64_t)sm_count();
+    if (kernel == 0) {
+        const uint64_t pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+        const uint64_t cta_tiles = ((M + 127) / 128) * ((N + 255) / 256);
+        if (pair_tiles * 2 >= sms) kernel = 3;
+        else if (cta_tiles >= sms) kernel = 2;
+        else kernel = 1;
+    }
+    if (kernel == 3)
+        return tB ? launch_tc_persistent<2, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC)
+                  : launch_tc_persistent<2, true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
+    if (kernel == 2)
+        return tB ? launch_tc_persistent<1, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC)
+                  : launch_tc_persistent<1, true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
     // Tile width: the widest BN that still yields at least one CTA per SM (148), else 64.
     int bn = 64;
     const uint64_t mt = (M + BM - 1) / BM;
-    const uint64_t sms = (uint64_t)sm_count();
     if (mt * ((N + 255) / 256) >= sms) bn = 256;
     else if (mt * ((N + 127) / 128) >= sms) bn = 128;
     if (const char *e = getenv("TB200_GEMM_BN")) {
         int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) bn = v;
     }
-    const int m = (int)M, n = (int)N, k = (int)K;
     if (tB) {
         switch (bn) {
         case 256: return launch_tc<256, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
@@ -359,6 +659,12 @@ TB200_API int tiramisu_b200_set_gemm_mode(int mode)
 {
     if (mode < 0 || mode > 2) mode = 0;
     return g_gemm_mode.exchange(mode);
+}
+
+TB200_API int tiramisu_b200_set_gemm_kernel(int kernel)
+{
+    if (kernel < 0 || kernel > 3) kernel = 0;
+    return g_gemm_kernel.exchange(kernel);
 }
 
 TB200_API int tiramisu_cublas_sgemm(float *A, float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha,

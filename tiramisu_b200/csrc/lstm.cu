@@ -212,7 +212,195 @@ tiramisu_sm100_lstm_step_tf32(const __grid_constant__ CUtensorMap map_h, const _
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Persistent layer kernel: ONE launch runs all T recurrent steps of a layer.
+//   grid = 4F/32 CTAs (128 at F = 1024), one per SM, in clusters of CL.
+//   * CTA j owns gate columns [32j, 32j+32) = hidden units [8j, 8j+8): its slice of the packed
+//     recurrent weights R (32 x F fp32 = 128 KB at F = 1024) is loaded into shared memory ONCE and
+//     stays there for the whole layer; the cell state c of its 8 units lives in registers.
+//   * per step: h[t-1] (B x F) streams through a shared-memory ring as the A operand (with CL > 1
+//     each CTA of the cluster fetches 1/CL of the rows and TMA-multicasts them to its peers, so
+//     the all-gather of h costs 1/CL of the L2 reads), tcgen05 TF32 MMAs accumulate the 32 gate
+//     pre-activations in TMEM, the epilogue adds the precomputed input contribution Xg + bias,
+//     applies the gates and writes h[t] (its 8 columns).
+//   * steps are separated by a device-wide barrier on an atomic counter (release/acquire at gpu
+//     scope + fence.proxy.async, because the next step reads h through the async proxy = TMA).
+// The reference launches 2 GEMM kernels + 1 pointwise kernel per cell (LSTM/gpu/generator.cpp:85-131)
+// and r01 of this backend launched one kernel per cell (15 us each, launch + weight re-fetch bound).
+constexpr int L_BN = 32;
+constexpr int L_RING_BYTES = 64 * 1024;
+constexpr int L_PAD_BYTES = 8 * 1024;          // M = 128 MMAs read 16 KB of A even when only 64 rows are live
+constexpr int L_MAX_STAGES = 8;
+
+struct LayerParams {
+    int B, F, T;
+    int a_rows;             // 64 (B <= 64) or 128: rows of h fetched per k-slab
+    const float *xg;        // [T*B][4F] packed gate columns: input contribution of every step
+    const float *bias;      // [4F] packed
+    float *h;               // [T][B][F] output of this layer
+    uint32_t *counter;      // device-wide step barrier, zero at launch
+};
+
+__device__ __forceinline__ void grid_wait(const uint32_t *ctr, uint32_t target)
+{
+    const long long t0 = clock64();
+    while (ptx::ld_acquire_gpu(ctr) < target) {
+        if (clock64() - t0 > (1ll << 31)) __trap();       // ~1 s: a protocol bug must not hang the box
+    }
+}
+
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+
+template <int CL>
+__global__ void __launch_bounds__(kThreads, 1)
+tiramisu_sm100_lstm_layer_tf32(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_r,
+                               const LayerParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int num_kb = p.F / BK;
+    uint8_t *smem_r = smem;                                   // num_kb slabs of [32 n][32 k] fp32, 4 KB each
+    uint8_t *ring = smem + (size_t)num_kb * 4096;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(ring + L_RING_BYTES + L_PAD_BYTES);
+    uint64_t *empty_bar = full_bar + L_MAX_STAGES;
+    uint64_t *r_bar = empty_bar + L_MAX_STAGES;
+    uint64_t *tmem_full = r_bar + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * L_BN;
+    const uint32_t stage_bytes = (uint32_t)p.a_rows * 128u;
+    const int stages = L_RING_BYTES / (int)stage_bytes;
+    const uint32_t rank = (CL > 1) ? ptx::cluster_ctarank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+
+    if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&map_h); ptx::prefetch_tensormap(&map_r); }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < L_MAX_STAGES; s++) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], CL); }
+            ptx::mbar_init(r_bar, 1);
+            ptx::mbar_init(tmem_full, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 32);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    if (CL > 1) ptx::cluster_sync(); else __syncthreads();    // peers' barriers exist before any multicast lands
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(r_bar, (uint32_t)num_kb * 4096u);
+            for (int kb = 0; kb < num_kb; kb++) ptx::tma_load_2d(smem_r + kb * 4096, &map_r, r_bar, kb * BK, n0);
+            const int rows_per_cta = p.a_rows / CL;
+            uint32_t it = 0;
+            for (int t = 1; t < p.T; t++) {
+                grid_wait(p.counter, (uint32_t)gridDim.x * (uint32_t)t);      // every CTA has published h[t-1]
+                ptx::fence_proxy_async_all();
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % stages;
+                    ptx::mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                    uint8_t *dst = ring + (size_t)s * stage_bytes;
+                    if (CL == 1)
+                        ptx::tma_load_3d(dst, &map_h, &full_bar[s], kb * BK, 0, t - 1);
+                    else
+                        ptx::tma_load_3d_multicast(dst + rank * rows_per_cta * 128, &map_h, &full_bar[s], kb * BK,
+                                                   (int)rank * rows_per_cta, t - 1, kMask);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, L_BN, false, false);
+            ptx::mbar_wait(r_bar, 0);
+            ptx::tc_fence_after_sync();
+            uint32_t it = 0;
+            for (int t = 1; t < p.T; t++) {
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % stages;
+                    ptx::mbar_wait(&full_bar[s], (it / stages) & 1);
+                    ptx::tc_fence_after_sync();
+                    const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * stage_bytes);
+                    const uint32_t b_addr = ptx::smem_u32(smem_r + kb * 4096);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++)
+                        ptx::mma_tf32_ss(tmem_base, ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024),
+                                         ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024), idesc, (kb | k) != 0);
+                    if (CL == 1) ptx::mma_commit(&empty_bar[s]); else ptx::mma_commit_multicast(&empty_bar[s], kMask);
+                }
+                ptx::mma_commit(tmem_full);
+            }
+        }
+    } else {
+        // ===== epilogue: gates, cell state in registers, h[t] out, publish =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                 // batch index
+        const bool ok = row < p.B;
+        float c[8];
+        float4 bs[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { c[u] = 0.0f; bs[u] = __ldg(reinterpret_cast<const float4 *>(p.bias + n0) + u); }
+        for (int t = 0; t < p.T; t++) {
+            float4 xg[8];
+            if (ok) {
+                const float4 *xp = reinterpret_cast<const float4 *>(p.xg + ((size_t)t * p.B + row) * 4 * p.F + n0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) xg[j] = __ldg(xp + j);
+            }
+            uint32_t r[32];
+            if (t > 0) {
+                ptx::mbar_wait(tmem_full, (uint32_t)(t - 1) & 1u);
+                ptx::tc_fence_after_sync();
+                __syncwarp();
+                ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), r);
+                ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) r[j] = 0u;       // h[-1] = 0: no recurrent contribution
+            }
+            if (ok) {
+                float hn[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    // columns 4u..4u+3 = pre-activations i, z, o, f of hidden unit n0/4 + u
+                    const float si = __uint_as_float(r[4 * u + 0]) + xg[u].x + bs[u].x;
+                    const float sz = __uint_as_float(r[4 * u + 1]) + xg[u].y + bs[u].y;
+                    const float so = __uint_as_float(r[4 * u + 2]) + xg[u].z + bs[u].z;
+                    const float sf = __uint_as_float(r[4 * u + 3]) + xg[u].w + bs[u].w;
+                    const float gi = sigmoid_fast(si), gz = ptx::tanh_approx(sz), go = sigmoid_fast(so),
+                                gf = sigmoid_fast(sf);
+                    c[u] = gi * gz + gf * c[u];
+                    hn[u] = ptx::tanh_approx(c[u]) * go;
+                }
+                float4 *dst = reinterpret_cast<float4 *>(p.h + ((size_t)t * p.B + row) * p.F + n0 / 4);
+                dst[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                dst[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                __threadfence();                       // h[t] visible device-wide before the counter moves
+            }
+            ptx::fence_proxy_async_all();
+            ptx::tc_fence_before_sync();               // TMEM reads done before the next step's MMAs overwrite
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps
+            if (warp == 2 && lane == 0) ptx::red_release_gpu_add(p.counter, 1u);
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    if (CL > 1) ptx::cluster_sync(); else __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem_base, 32);
+    }
+}
+
 std::atomic<int> g_lstm_mode{0};
+std::atomic<int> g_lstm_kernel{0};
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int lstm_exact(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y)
@@ -246,6 +434,78 @@ int lstm_exact(int F, int B, int L, int T, const float *Wt, const float *bias, c
     return 0;
 }
 
+
+size_t layer_smem_bytes(int F) { return (size_t)(F / BK) * 4096 + L_RING_BYTES + L_PAD_BYTES + 256 + 1024; }
+
+// Can the persistent layer kernel run this shape?  Its grid (4F/32 CTAs, one per SM) must be
+// co-resident for the device-wide step barrier, and the R slice + ring must fit in shared memory.
+bool layer_kernel_ok(int F, int B)
+{
+    return F % 32 == 0 && B <= 128 && 4 * F / L_BN <= sm_count() && layer_smem_bytes(F) <= 227 * 1024;
+}
+
+template <int CL>
+int launch_layer(const CUtensorMap &map_h, const CUtensorMap &map_r, const LayerParams &p, bool probe_only, bool *fits)
+{
+    auto kern = tiramisu_sm100_lstm_layer_tf32<CL>;
+    const size_t smem = layer_smem_bytes(p.F);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB200_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(4 * p.F / L_BN));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (probe_only) {
+        int n = 0;
+        if (CL > 1) {
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        } else {
+            n = sm_count();
+        }
+        *fits = n * CL >= (int)cfg.gridDim.x;
+        return 0;
+    }
+    TB200_CHECK(cudaLaunchKernelEx(&cfg, kern, map_h, map_r, p));
+    return post_launch("tiramisu_sm100_lstm_layer_tf32");
+}
+
+int layer_dispatch(int cl, const CUtensorMap &map_h, const CUtensorMap &map_r, const LayerParams &p, bool probe_only,
+                   bool *fits)
+{
+    switch (cl) {
+    case 4: return launch_layer<4>(map_h, map_r, p, probe_only, fits);
+    case 2: return launch_layer<2>(map_h, map_r, p, probe_only, fits);
+    default: return launch_layer<1>(map_h, map_r, p, probe_only, fits);
+    }
+}
+
+// Largest cluster size (4, 2, 1) whose whole grid is co-resident; TB200_LSTM_CLUSTER caps it.
+int pick_cluster(int F, int a_rows)
+{
+    int want = 4;
+    if (const char *e = getenv("TB200_LSTM_CLUSTER")) want = atoi(e);
+    LayerParams probe = {};
+    probe.F = F;
+    CUtensorMap dummy = {};
+    for (int cl = 4; cl >= 2; cl >>= 1) {
+        if (cl > want || (4 * F / L_BN) % cl || (a_rows / cl) % 8) continue;
+        bool fits = false;
+        if (layer_dispatch(cl, dummy, dummy, probe, true, &fits) == 0 && fits) return cl;
+    }
+    return 1;
+}
+
 int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y)
 {
     const size_t BF = (size_t)B * F, TB = (size_t)T * B;
@@ -255,8 +515,18 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
     float *hs = reinterpret_cast<float *>(pool_alloc((size_t)2 * TB * F * 4));             // h of layer l (ping-pong by layer)
     float *cs = reinterpret_cast<float *>(pool_alloc((size_t)2 * BF * 4));                 // c ping-pong by step
     float *zero = reinterpret_cast<float *>(pool_alloc(BF * 4));
-    if (!Wp || !bp || !xg || !hs || !cs || !zero) return 1;
+    uint32_t *counters = reinterpret_cast<uint32_t *>(pool_alloc((size_t)L * 4));
+    if (!Wp || !bp || !xg || !hs || !cs || !zero || !counters) return 1;
     TB200_CHECK(cudaMemsetAsync(zero, 0, BF * 4, stream()));
+    TB200_CHECK(cudaMemsetAsync(counters, 0, (size_t)L * 4, stream()));
+    // recurrence engine: the persistent layer kernel when the shape allows it (g_lstm_kernel: 0 auto,
+    // 1 = one launch per cell, 2 = persistent layer kernel)
+    int which = g_lstm_kernel.load();
+    if (const char *e = getenv("TB200_LSTM_KERNEL")) which = atoi(e);
+    const bool use_layer_kernel = which != 1 && layer_kernel_ok(F, B);
+    if (which == 2 && !use_layer_kernel) return fail("tiramisu_b200_lstm", "shape not supported by the persistent layer kernel");
+    const int a_rows = B <= 64 ? 64 : 128;
+    const int cl = use_layer_kernel ? pick_cluster(F, a_rows) : 1;
     static bool attr_set = false;
     if (!attr_set) {
         TB200_CHECK(cudaFuncSetAttribute(tiramisu_sm100_lstm_step_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -283,6 +553,20 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
             uint32_t box[2] = {BK, BN};
             if (make_tensor_map_f32(&map_r, Wp, 2, dims, str, box)) return 1;
         }
+        if (use_layer_kernel) {
+            // one persistent launch for all T steps
+            CUtensorMap map_h3;
+            uint64_t dims[3] = {(uint64_t)F, (uint64_t)B, (uint64_t)T};
+            uint64_t str[2] = {(uint64_t)F * 4, (uint64_t)B * F * 4};
+            uint32_t box[3] = {BK, (uint32_t)(a_rows / cl), 1};
+            if (make_tensor_map_f32(&map_h3, hl, 3, dims, str, box)) return 1;
+            LayerParams lp;
+            lp.B = B; lp.F = F; lp.T = T; lp.a_rows = a_rows;
+            lp.xg = xg; lp.bias = bp; lp.h = hl; lp.counter = counters + l;
+            bool unused = false;
+            if (layer_dispatch(cl, map_h3, map_r, lp, false, &unused)) return 1;
+            continue;
+        }
         for (int m = 0; m < T; m++) {
             const float *hprev = (m == 0) ? zero : hl + (size_t)(m - 1) * BF;
             CUtensorMap map_h;
@@ -302,6 +586,7 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
             if (post_launch("tiramisu_sm100_lstm_step_tf32")) return 1;
         }
     }
+    pool_free(counters);
     pool_free(Wp); pool_free(bp); pool_free(xg); pool_free(hs); pool_free(cs); pool_free(zero);
     return 0;
 }
@@ -312,6 +597,12 @@ TB200_API int tiramisu_b200_set_lstm_mode(int mode)
 {
     if (mode < 0 || mode > 2) mode = 0;
     return g_lstm_mode.exchange(mode);
+}
+
+TB200_API int tiramisu_b200_set_lstm_kernel(int kernel)
+{
+    if (kernel < 0 || kernel > 2) kernel = 0;
+    return g_lstm_kernel.exchange(kernel);
 }
 
 TB200_API int tiramisu_b200_lstm(const float *Weights, const float *biases, const float *x, float *y, int32_t F,
