@@ -43,11 +43,14 @@ def test_conv_exact_mode_bit_exact(api, B, N, FIn, FOut):
         api.set_conv_mode(prev)
 
 
-@pytest.mark.parametrize("B,N,FIn", [(2, 32, 32), (1, 64, 64), (3, 96, 64)])
-def test_conv_tensor_path_small_ints_exact(api, B, N, FIn):
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("B,N,FIn", [(2, 32, 32), (1, 64, 64), (3, 96, 64), (1, 16, 32), (2, 224, 64)])
+def test_conv_tensor_path_small_ints_exact(api, kernel, B, N, FIn):
     """Integer-valued operands are exact in TF32 with fp32 accumulation => equality with the oracle
-    checks the im2col addressing, the pooling shuffles and the output layout, not rounding."""
+    checks the im2col addressing (TMA boxes + tap-shifted descriptors of both staging variants),
+    the pooling shuffles and the output layout, not rounding."""
     prev = api.set_conv_mode(2)
+    prev_k = api.set_conv_kernel(kernel)
     try:
         rng = np.random.default_rng(3)
         inp = rng.integers(-4, 5, (B, N + 2, N + 2, FIn)).astype(np.float32)
@@ -56,6 +59,7 @@ def test_conv_tensor_path_small_ints_exact(api, B, N, FIn):
         assert np.array_equal(_conv(api, inp, filt, bias), oracle.conv_relu_maxpool(inp, filt, bias))
     finally:
         api.set_conv_mode(prev)
+        api.set_conv_kernel(prev_k)
 
 
 @pytest.mark.parametrize("B,N,FIn", [(2, 32, 64), (1, 64, 32)])

@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_transpose_f32", C.c_int, vp, vp, i32, i32)
     sig("tiramisu_b200_conv_relu_maxpool", C.c_int, vp, vp, vp, vp, i32, i32, i32, i32)
     sig("tiramisu_b200_set_conv_mode", C.c_int, C.c_int)
+    sig("tiramisu_b200_set_conv_kernel", C.c_int, C.c_int)
     sig("tiramisu_b200_lstm", C.c_int, vp, vp, vp, vp, i32, i32, i32, i32)
     sig("tiramisu_b200_set_lstm_mode", C.c_int, C.c_int)
     sig("tiramisu_b200_set_lstm_kernel", C.c_int, C.c_int)

@@ -100,6 +100,11 @@ def set_conv_mode(mode: int) -> int:
     return int(_lib.lib().tiramisu_b200_set_conv_mode(mode))
 
 
+def set_conv_kernel(kernel: int) -> int:
+    """0 auto, 1 = 8x16 tile (ky taps share a TMA tile), 2 = 16x8 tile (all nine taps share one)."""
+    return int(_lib.lib().tiramisu_b200_set_conv_kernel(kernel))
+
+
 def set_lstm_mode(mode: int) -> int:
     return int(_lib.lib().tiramisu_b200_set_lstm_mode(mode))
 

@@ -69,10 +69,24 @@ tiramisu_sm100_conv_block_exact(const float *__restrict__ in, const float *__res
 // ------------------------------------------------------------------------------------------------ tcgen05 path
 constexpr int BK = 32;                       // channels per K slab (128 B)
 constexpr int UMMA_K = 8;
-constexpr int A_STAGES = 4;
-constexpr int TILE_Y = 8, TILE_X = 16;       // output pixels per tile: M = 128 accumulator rows, r = y*16 + x
-constexpr int A_ROW_BYTES = TILE_X * BK * 4; // one image row of the tile: 16 px x 128 B = 2 KB
-constexpr int A_TILE_BYTES = (TILE_Y + 2) * A_ROW_BYTES;   // 20 KB: rows y0 .. y0+9 (all three ky taps)
+// Two activation-staging variants (template parameter ALLTAPS):
+//  false: tile 8 rows x 16 px; one TMA box {32 ch, 16 x, 10 y} per (kx, channel slab); the three ky
+//         taps are 1024-byte-aligned start-address shifts of the same tile (3.75x L2 re-fetch).
+//  true : tile 16 rows x 8 px; ONE TMA box {32 ch, 10 x, 18 y} per channel slab serves all nine taps:
+//         tap (ky,kx) starts (ky*10 + kx) pixel rows (128 B each) into the tile and its 8-pixel
+//         row groups are 10 pixels = 1280 B apart (the descriptor's stride-dimension offset).  The
+//         128B swizzle is a function of the absolute shared-memory address for both the TMA write
+//         and the MMA read, so unaligned row starts stay consistent (1.4x L2 re-fetch).
+template <bool ALLTAPS> struct Tile {
+    static constexpr int Y = ALLTAPS ? 16 : 8, X = ALLTAPS ? 8 : 16;
+    static constexpr int BOX_X = ALLTAPS ? 10 : 16, BOX_Y = Y + 2;
+    static constexpr int ROW_BYTES = BOX_X * BK * 4;                       // one image row of the staged tile
+    static constexpr int TILE_BYTES = BOX_Y * ROW_BYTES;                   // 20480 / 23040
+    static constexpr int STAGE_BYTES = (TILE_BYTES + 1023) / 1024 * 1024;  // stage bases stay 1024-aligned
+    static constexpr int STAGES = ALLTAPS ? 3 : 4;
+    static constexpr int SBO = ALLTAPS ? 1280 : 1024;                      // bytes between 8-pixel row groups
+    static constexpr int LOADS_KX = ALLTAPS ? 1 : 3;                       // TMA loads per channel slab
+};
 constexpr int kConvThreads = 192;
 
 // filter [FOut/8][3][3][FIn][8]  ->  Wp[(tap*KH + h)][fout][32]   (K-major slabs for the B operand)
@@ -96,14 +110,17 @@ struct ConvParams {
     int tiles_y, tiles_x, num_tiles;
     const float *bias;
     float *out;
+    int dbg_base_offset;          // bring-up knob: 1 = set the descriptor base-offset field to (addr >> 7) & 7
 };
 
-template <int FOUT>
+template <int FOUT, bool ALLTAPS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                                const ConvParams p)
 {
     constexpr int W_SLAB_BYTES = FOUT * BK * 4;
+    using T_ = Tile<ALLTAPS>;
+    constexpr int A_STAGES = T_::STAGES, A_TILE_BYTES = T_::STAGE_BYTES, TILE_X = T_::X, TILE_Y = T_::Y;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int KH = p.FIn / BK;
@@ -147,70 +164,83 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
     };
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer: whole warp, uniform control flow, one elected lane issues =====
+        if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(num_slabs * W_SLAB_BYTES));
             for (int s = 0; s < num_slabs; s++) ptx::tma_load_2d(smem_w + s * W_SLAB_BYTES, &map_w, w_bar, 0, s * FOUT);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                int n, y0, x0;
-                tile_coords(tile, n, y0, x0);
-                for (int kx = 0; kx < 3; kx++) {
-                    for (int h = 0; h < KH; h++, it++) {
-                        const int s = it % A_STAGES;
-                        const uint32_t ph = (it / A_STAGES) & 1;
-                        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-                        ptx::mbar_arrive_expect_tx(&full_bar[s], A_TILE_BYTES);
-                        // rows y0 .. y0+9, columns x0+kx .. x0+kx+15, channels [32h, 32h+32)
+        }
+        __syncwarp();
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int n, y0, x0;
+            tile_coords(tile, n, y0, x0);
+            for (int kx = 0; kx < T_::LOADS_KX; kx++) {
+                for (int h = 0; h < KH; h++, it++) {
+                    const int s = it % A_STAGES;
+                    const uint32_t ph = (it / A_STAGES) & 1;
+                    ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&full_bar[s], T_::TILE_BYTES);
+                        // rows y0 .. y0+TILE_Y+1, columns from x0+kx, channels [32h, 32h+32)
                         ptx::tma_load_4d(smem_a + s * A_TILE_BYTES, &map_in, &full_bar[s], h * BK, x0 + kx, y0, n);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_tf32(128, FOUT, false, false);
-            ptx::mbar_wait(w_bar, 0);
+        // ===== MMA issuer: whole warp, uniform control flow, one elected lane issues =====
+        constexpr uint32_t idesc = ptx::make_idesc_tf32(128, FOUT, false, false);
+        const uint32_t a_ring = ptx::smem_u32(smem_a);
+        const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_w), 16, 1024);
+        ptx::mbar_wait(w_bar, 0);
+        ptx::tc_fence_after_sync();
+        uint32_t it = 0, local = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+            const uint32_t buf = local & 1;
+            ptx::mbar_wait(&tmem_empty[buf], ((local >> 1) & 1) ^ 1);   // epilogue drained this buffer
             ptx::tc_fence_after_sync();
-            uint32_t it = 0, local = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
-                const uint32_t buf = local & 1;
-                ptx::mbar_wait(&tmem_empty[buf], ((local >> 1) & 1) ^ 1);   // epilogue drained this buffer
-                ptx::tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + buf * FOUT;
-                bool first = true;
-                for (int kx = 0; kx < 3; kx++) {
-                    for (int h = 0; h < KH; h++, it++) {
-                        const int s = it % A_STAGES;
-                        const uint32_t ph = (it / A_STAGES) & 1;
-                        ptx::mbar_wait(&full_bar[s], ph);
-                        ptx::tc_fence_after_sync();
-                        const uint32_t a_base = ptx::smem_u32(smem_a + s * A_TILE_BYTES);
+            const uint32_t d_tmem = tmem_base + buf * FOUT;
+            for (int lx = 0; lx < T_::LOADS_KX; lx++) {
+                for (int h = 0; h < KH; h++, it++) {
+                    const int s = it % A_STAGES;
+                    const uint32_t ph = (it / A_STAGES) & 1;
+                    ptx::mbar_wait(&full_bar[s], ph);
+                    ptx::tc_fence_after_sync();
+                    if (ptx::elect_one()) {
+                        const uint32_t a_base = a_ring + (uint32_t)s * A_TILE_BYTES;
+                        // with all nine taps in one tile the start is not 1024-aligned; bring-up knob for
+                        // the descriptor's base-offset field (see Tile<>)
+                        const bool first_unit = (lx | h) == 0;
 #pragma unroll
-                        for (int ky = 0; ky < 3; ky++) {
-                            // vertical tap: same tile, start ky image rows further down
-                            const uint32_t a_addr = a_base + ky * A_ROW_BYTES;
-                            const uint32_t b_addr = ptx::smem_u32(smem_w + ((ky * 3 + kx) * KH + h) * W_SLAB_BYTES);
+                        for (int t = 0; t < (ALLTAPS ? 9 : 3); t++) {
+                            const int ky = ALLTAPS ? t / 3 : t, kx = ALLTAPS ? t % 3 : lx;
+                            // tap shift inside the staged tile: ky image rows (+ kx pixels when all nine
+                            // taps share the tile)
+                            const uint32_t a_addr = a_base + ky * T_::ROW_BYTES + (ALLTAPS ? kx * 128 : 0);
+                            const uint32_t bo = (ALLTAPS && p.dbg_base_offset) ? ((a_addr >> 7) & 7u) : 0u;
+                            const uint64_t da = ptx::make_smem_desc(a_addr, 16, T_::SBO, ptx::kLayoutSw128, bo);
+                            const uint64_t db = ptx::desc_advance(db0, (uint32_t)(((ky * 3 + kx) * KH + h) * W_SLAB_BYTES));
 #pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; k++) {
-                                const uint64_t da = ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024);
-                                const uint64_t db = ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024);
-                                ptx::mma_tf32_ss(d_tmem, da, db, idesc, !first);
-                                first = false;
-                            }
+                            for (int k = 0; k < BK / UMMA_K; k++)
+                                ptx::mma_tf32_ss(d_tmem, ptx::desc_advance(da, k * (UMMA_K * 4)),
+                                                 ptx::desc_advance(db, k * (UMMA_K * 4)), idesc,
+                                                 !(first_unit && t == 0 && k == 0));
                         }
                         ptx::mma_commit(&empty_bar[s]);
+                        if (lx == T_::LOADS_KX - 1 && h == KH - 1) ptx::mma_commit(&tmem_full[buf]);
                     }
+                    __syncwarp();
                 }
-                ptx::mma_commit(&tmem_full[buf]);
             }
         }
     } else {
         // ===== epilogue: TMEM -> max-pool -> +bias -> ReLU -> global =====
         const int q = warp & 3;                       // TMEM lane quarter = image rows 2q, 2q+1 of the tile
         const int NO = p.N / 2, FB = FOUT / 8;
-        const int sel1 = lane & 1, sel16 = (lane >> 4) & 1;
+        // accumulator row r = y*TILE_X + x: the vertical pooling partner is TILE_X lanes away
+        constexpr int YSH = ALLTAPS ? 3 : 4;               // log2(TILE_X)
+        const int sel1 = lane & 1, sel16 = (lane >> YSH) & 1;
         uint32_t local = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
             const uint32_t buf = local & 1;
@@ -234,7 +264,7 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
 
-            // 2x2 max-pool across lanes l^1 (x pair) and l^16 (y pair), reduce-scatter style: after the
+            // 2x2 max-pool across lanes l^1 (x pair) and l^TILE_X (y pair), reduce-scatter style: after the
             // two exchanges each lane owns 16 of this chunk pair's columns.
 #pragma unroll
             for (int c = 0; c < NCH; c++) {
@@ -250,13 +280,14 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
                 for (int j = 0; j < 8; j++) {
                     const float keep = sel16 ? a[j + 8] : a[j];
                     const float send = sel16 ? a[j] : a[j + 8];
-                    b8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                    b8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, TILE_X));
                 }
                 // this lane now holds the pooled value of columns [col0, col0+8) = one FOut block of 8
                 const int col0 = c * 32 + sel1 * 16 + sel16 * 8;
                 const int fb = col0 >> 3;
-                const int py = (y0 >> 1) + q;                       // quarter q = tile rows 2q, 2q+1
-                const int px = (x0 >> 1) + ((lane & 15) >> 1);
+                // quarter q holds tile rows [q*32/TILE_X, +32/TILE_X); lane = (y % (32/TILE_X))*TILE_X + x
+                const int py = (y0 >> 1) + q * (16 / TILE_X) + (lane >> (YSH + 1));
+                const int px = (x0 >> 1) + ((lane & (TILE_X - 1)) >> 1);
                 float o[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) o[j] = fmaxf(__fadd_rn(b8[j], __ldg(p.bias + col0 + j)), 0.0f);
@@ -279,9 +310,12 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 std::atomic<int> g_conv_mode{0};          // 0 auto, 1 exact, 2 tensor
 
-template <int FOUT>
+std::atomic<int> g_conv_kernel{0};        // 0 auto (= 2), 1 ky-reuse tile (8x16), 2 all-taps tile (16x8)
+
+template <int FOUT, bool ALLTAPS>
 int launch_conv_tc(const float *in, const float *filter, const float *bias, float *out, int B, int N, int FIn)
 {
+    using T_ = Tile<ALLTAPS>;
     const int KH = FIn / BK, num_slabs = 9 * KH;
     float *wp = reinterpret_cast<float *>(pool_alloc((size_t)num_slabs * FOUT * BK * 4));
     if (!wp) return 1;
@@ -293,7 +327,7 @@ int launch_conv_tc(const float *in, const float *filter, const float *bias, floa
         const uint64_t NP = (uint64_t)N + 2;
         uint64_t dims[4] = {(uint64_t)FIn, NP, NP, (uint64_t)B};
         uint64_t str[3] = {(uint64_t)FIn * 4, NP * FIn * 4, NP * NP * FIn * 4};
-        uint32_t box[4] = {BK, TILE_X, TILE_Y + 2, 1};
+        uint32_t box[4] = {BK, (uint32_t)T_::BOX_X, (uint32_t)T_::BOX_Y, 1};
         if (make_tensor_map_f32(&map_in, in, 4, dims, str, box)) return 1;
     }
     {
@@ -304,11 +338,13 @@ int launch_conv_tc(const float *in, const float *filter, const float *bias, floa
     }
     ConvParams p;
     p.B = B; p.N = N; p.FIn = FIn; p.FOut = FOUT;
-    p.tiles_y = N / TILE_Y; p.tiles_x = N / TILE_X;
+    p.tiles_y = N / T_::Y; p.tiles_x = N / T_::X;
     p.num_tiles = B * p.tiles_y * p.tiles_x;
     p.bias = bias; p.out = out;
-    const int smem = num_slabs * FOUT * BK * 4 + A_STAGES * A_TILE_BYTES + 1024 + 256;
-    auto kern = tiramisu_sm100_conv_block_tf32<FOUT>;
+    p.dbg_base_offset = 0;
+    if (const char *e = getenv("TB200_CONV_BASE_OFFSET")) p.dbg_base_offset = atoi(e);
+    const int smem = num_slabs * FOUT * BK * 4 + T_::STAGES * T_::STAGE_BYTES + 1024 + 256;
+    auto kern = tiramisu_sm100_conv_block_tf32<FOUT, ALLTAPS>;
     static bool attr_set = false;
     if (!attr_set) {
         TB200_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -329,6 +365,12 @@ TB200_API int tiramisu_b200_set_conv_mode(int mode)
     return g_conv_mode.exchange(mode);
 }
 
+TB200_API int tiramisu_b200_set_conv_kernel(int kernel)
+{
+    if (kernel < 0 || kernel > 2) kernel = 0;
+    return g_conv_kernel.exchange(kernel);
+}
+
 TB200_API int tiramisu_b200_conv_relu_maxpool(const float *input, const float *filter, const float *bias,
                                               float *output, int32_t B, int32_t N, int32_t FIn, int32_t FOut)
 {
@@ -336,10 +378,15 @@ TB200_API int tiramisu_b200_conv_relu_maxpool(const float *input, const float *f
         return fail(__func__, "bad argument (need FOut % 8 == 0, N even)");
     const int mode = g_conv_mode.load();
     const int num_slabs = 9 * (FIn / BK);
-    const bool tc_ok = FIn % BK == 0 && FOut == 64 && N % TILE_X == 0 && aligned16(input) && aligned16(output) &&
-                       (size_t)num_slabs * FOut * BK * 4 + A_STAGES * A_TILE_BYTES + 2048 <= 227 * 1024;
+    const bool tc_ok = FIn % BK == 0 && FOut == 64 && N % 16 == 0 && aligned16(input) && aligned16(output) &&
+                       (size_t)num_slabs * FOut * BK * 4 + 4 * 20480 + 2048 <= 227 * 1024;
     if (mode == 2 && !tc_ok) return fail(__func__, "shape not supported by the tcgen05 conv path");
-    if (mode != 1 && tc_ok) return launch_conv_tc<64>(input, filter, bias, output, B, N, FIn);
+    if (mode != 1 && tc_ok) {
+        int kernel = g_conv_kernel.load();
+        if (const char *e = getenv("TB200_CONV_KERNEL")) kernel = atoi(e);
+        if (kernel == 1) return launch_conv_tc<64, false>(input, filter, bias, output, B, N, FIn);
+        return launch_conv_tc<64, true>(input, filter, bias, output, B, N, FIn);
+    }
     const size_t total = (size_t)B * (FOut / 8) * (N / 2) * (N / 2) * 8;
     const size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 16;
     tiramisu_sm100_conv_block_exact<<<(unsigned)(want < cap ? want : cap), 256, 0, stream()>>>(input, filter, bias,

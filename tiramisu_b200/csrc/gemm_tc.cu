@@ -143,12 +143,12 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        // ===== TMA producer: whole warp walks the ring (uniform control flow), one elected lane issues =====
+        for (int kb = 0; kb < num_kb; kb++) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+            if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&full_bar[s], C_::STAGE_BYTES);
                 const int k0 = kb * BK;
                 ptx::tma_load_2d(smem_a + s * A_TILE_BYTES, &map_a, &full_bar[s], k0, m0);
@@ -161,34 +161,36 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
                     ptx::tma_load_2d(bdst, &map_b, &full_bar[s], k0, n0);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, B_MN);
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                ptx::mbar_wait(&full_bar[s], ph);
-                ptx::tc_fence_after_sync();
-                const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_TILE_BYTES);
-                const uint32_t b_addr = ptx::smem_u32(smem_b + s * C_::B_TILE_BYTES);
+        // ===== MMA issuer: the whole warp walks the ring (uniform control flow), one elected lane issues =====
+        constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, B_MN);
+        // K-major, 128B swizzle: rows are 128 B apart, 8-row groups 1024 B apart; a K step of 8 fp32
+        // moves the start address 32 B inside the swizzled row.
+        // MN-major tf32 (128B swizzle, 32B atoms): rows are k (128 B = 32 columns each), 4-row groups
+        // 512 B apart (stride offset), 32-column slabs BK*128 B apart (leading offset); a K step of
+        // 8 rows moves the start address 1024 B.
+        const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), 16, 1024);
+        const uint64_t db0 = B_MN ? ptx::make_smem_desc(ptx::smem_u32(smem_b), p.b_lbo, p.b_sbo, ptx::kLayoutSw128Base32)
+                                  : ptx::make_smem_desc(ptx::smem_u32(smem_b), 16, 1024);
+        constexpr uint32_t kStepA = UMMA_K * 4, kStepB = B_MN ? UMMA_K * 128 : UMMA_K * 4;
+        for (int kb = 0; kb < num_kb; kb++) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            ptx::mbar_wait(&full_bar[s], ph);
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+                const uint64_t da = ptx::desc_advance(da0, (uint32_t)s * A_TILE_BYTES);
+                const uint64_t db = ptx::desc_advance(db0, (uint32_t)s * C_::B_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; k++) {
-                    // K-major, 128B swizzle: rows are 128 B apart, 8-row groups 1024 B apart; a K step
-                    // of 8 fp32 moves the start address 32 B inside the swizzled row.
-                    const uint64_t da = ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024);
-                    // MN-major tf32 (128B swizzle, 32B atoms): rows are k (128 B = 32 columns each), 4-row
-                    // groups 512 B apart (stride offset), 32-column slabs BK*128 B apart (leading offset);
-                    // a K step of 8 rows moves the start address 1024 B.
-                    const uint64_t db = B_MN ? ptx::make_smem_desc(b_addr + k * (UMMA_K * 128), p.b_lbo, p.b_sbo,
-                                                                   ptx::kLayoutSw128Base32)
-                                             : ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024);
-                    ptx::mma_tf32_ss(tmem_base, da, db, idesc, (kb | k) != 0);
-                }
+                for (int k = 0; k < BK / UMMA_K; k++)
+                    ptx::mma_tf32_ss(tmem_base, ptx::desc_advance(da, k * kStepA), ptx::desc_advance(db, k * kStepB),
+                                     idesc, (kb | k) != 0);
                 ptx::mma_commit(&empty_bar[s]);        // slab free once these MMAs retire
+                if (kb == num_kb - 1) ptx::mma_commit(tmem_full_bar);     // accumulator complete
             }
-            ptx::mma_commit(tmem_full_bar);            // accumulator complete
+            __syncwarp();
         }
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
@@ -333,8 +335,9 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer (every CTA loads its own A rows and its own share of B) =====
-        if (lane == 0) {
+        // ===== TMA producer (every CTA loads its own A rows and its own share of B); whole warp,
+        // uniform control flow, one elected lane issues =====
+        {
             uint32_t it = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 int m0, n0;
@@ -345,6 +348,7 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (ptx::elect_one()) {
                     // the pair's full barrier lives in the leader and expects both CTAs' bytes
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], CG * C_::STAGE_BYTES);
                     const int k0 = kb * BK;
@@ -369,13 +373,19 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                             ptx::tma_load_2d(bdst, &map_b, &full_bar[s], k0, n0);
                         }
                     }
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0 && leader) {
+        // ===== MMA issuer: whole warp, uniform control flow, one elected lane issues =====
+        if (leader) {
             constexpr uint32_t idesc = ptx::make_idesc_tf32(TILE_M, P_BN, false, B_MN);
+            const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), 16, 1024);
+            const uint64_t db0 = B_MN ? ptx::make_smem_desc(ptx::smem_u32(smem_b), p.b_lbo, p.b_sbo, ptx::kLayoutSw128Base32)
+                                      : ptx::make_smem_desc(ptx::smem_u32(smem_b), 16, 1024);
+            constexpr uint32_t kStepA = UMMA_K * 4, kStepB = B_MN ? UMMA_K * 128 : UMMA_K * 4;
             uint32_t it = 0, local = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
                 const uint32_t buf = local & 1;
@@ -387,20 +397,25 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                     const uint32_t ph = (it / STAGES) & 1;
                     ptx::mbar_wait(&full_bar[s], ph);
                     ptx::tc_fence_after_sync();
-                    const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_TILE_BYTES);
-                    const uint32_t b_addr = ptx::smem_u32(smem_b + s * C_::B_TILE_BYTES);
+                    if (ptx::elect_one()) {
+                        const uint64_t da = ptx::desc_advance(da0, (uint32_t)s * A_TILE_BYTES);
+                        const uint64_t db = ptx::desc_advance(db0, (uint32_t)s * C_::B_TILE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; k++) {
-                        const uint64_t da = ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024);
-                        const uint64_t db = B_MN ? ptx::make_smem_desc(b_addr + k * (UMMA_K * 128), p.b_lbo, p.b_sbo,
-                                                                       ptx::kLayoutSw128Base32)
-                                                 : ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024);
-                        if (CG == 2) ptx::mma_tf32_ss_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
-                        else ptx::mma_tf32_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / UMMA_K; k++) {
+                            if (CG == 2)
+                                ptx::mma_tf32_ss_cg2(d_tmem, ptx::desc_advance(da, k * kStepA),
+                                                     ptx::desc_advance(db, k * kStepB), idesc, (kb | k) != 0);
+                            else
+                                ptx::mma_tf32_ss(d_tmem, ptx::desc_advance(da, k * kStepA),
+                                                 ptx::desc_advance(db, k * kStepB), idesc, (kb | k) != 0);
+                        }
+                        if (CG == 2) ptx::mma_commit_cg2(&empty_bar[s], 3); else ptx::mma_commit(&empty_bar[s]);
+                        if (kb == num_kb - 1) {
+                            if (CG == 2) ptx::mma_commit_cg2(&tmem_full[buf], 3); else ptx::mma_commit(&tmem_full[buf]);
+                        }
                     }
-                    if (CG == 2) ptx::mma_commit_cg2(&empty_bar[s], 3); else ptx::mma_commit(&empty_bar[s]);
+                    __syncwarp();
                 }
-                if (CG == 2) ptx::mma_commit_cg2(&tmem_full[buf], 3); else ptx::mma_commit(&tmem_full[buf]);
             }
         }
     } else {

@@ -134,30 +134,35 @@ tiramisu_sm100_lstm_step_tf32(const __grid_constant__ CUtensorMap map_h, const _
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES;
-                ptx::mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+        for (int kb = 0; kb < num_kb; kb++) {
+            const int s = kb % STAGES;
+            ptx::mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+            if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                 ptx::tma_load_2d(smem_a + s * A_TILE, &map_h, &full_bar[s], kb * BK, 0);     // rows >= B: zero fill
                 ptx::tma_load_2d(smem_b + s * B_TILE, &map_r, &full_bar[s], kb * BK, n0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, false);
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES;
-                ptx::mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-                ptx::tc_fence_after_sync();
-                const uint32_t a_addr = ptx::smem_u32(smem_a + s * A_TILE), b_addr = ptx::smem_u32(smem_b + s * B_TILE);
+        // whole warp walks the ring (uniform control flow); one elected lane issues
+        constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, false);
+        const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), 16, 1024);
+        const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), 16, 1024);
+        for (int kb = 0; kb < num_kb; kb++) {
+            const int s = kb % STAGES;
+            ptx::mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+                const uint64_t da = ptx::desc_advance(da0, (uint32_t)s * A_TILE), db = ptx::desc_advance(db0, (uint32_t)s * B_TILE);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; k++)
-                    ptx::mma_tf32_ss(tmem_base, ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024),
-                                     ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024), idesc, (kb | k) != 0);
+                    ptx::mma_tf32_ss(tmem_base, ptx::desc_advance(da, k * (UMMA_K * 4)),
+                                     ptx::desc_advance(db, k * (UMMA_K * 4)), idesc, (kb | k) != 0);
                 ptx::mma_commit(&empty_bar[s]);
+                if (kb == num_kb - 1) ptx::mma_commit(tmem_full);
             }
-            ptx::mma_commit(tmem_full);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -293,18 +298,21 @@ tiramisu_sm100_lstm_layer_tf32(const __grid_constant__ CUtensorMap map_h, const 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer: whole warp, uniform control flow, one elected lane issues =====
+        if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(r_bar, (uint32_t)num_kb * 4096u);
             for (int kb = 0; kb < num_kb; kb++) ptx::tma_load_2d(smem_r + kb * 4096, &map_r, r_bar, kb * BK, n0);
-            const int rows_per_cta = p.a_rows / CL;
-            uint32_t it = 0;
-            for (int t = 1; t < p.T; t++) {
-                grid_wait(p.counter, (uint32_t)gridDim.x * (uint32_t)t);      // every CTA has published h[t-1]
-                ptx::fence_proxy_async_all();
-                for (int kb = 0; kb < num_kb; kb++, it++) {
-                    const int s = it % stages;
-                    ptx::mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+        }
+        __syncwarp();
+        const int rows_per_cta = p.a_rows / CL;
+        uint32_t it = 0;
+        for (int t = 1; t < p.T; t++) {
+            grid_wait(p.counter, (uint32_t)gridDim.x * (uint32_t)t);      // every CTA has published h[t-1]
+            ptx::fence_proxy_async_all();
+            for (int kb = 0; kb < num_kb; kb++, it++) {
+                const int s = it % stages;
+                ptx::mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+                if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
                     uint8_t *dst = ring + (size_t)s * stage_bytes;
                     if (CL == 1)
@@ -313,29 +321,33 @@ tiramisu_sm100_lstm_layer_tf32(const __grid_constant__ CUtensorMap map_h, const 
                         ptx::tma_load_3d_multicast(dst + rank * rows_per_cta * 128, &map_h, &full_bar[s], kb * BK,
                                                    (int)rank * rows_per_cta, t - 1, kMask);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, L_BN, false, false);
-            ptx::mbar_wait(r_bar, 0);
-            ptx::tc_fence_after_sync();
-            uint32_t it = 0;
-            for (int t = 1; t < p.T; t++) {
-                for (int kb = 0; kb < num_kb; kb++, it++) {
-                    const int s = it % stages;
-                    ptx::mbar_wait(&full_bar[s], (it / stages) & 1);
-                    ptx::tc_fence_after_sync();
-                    const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * stage_bytes);
-                    const uint32_t b_addr = ptx::smem_u32(smem_r + kb * 4096);
+        // ===== MMA issuer: whole warp, uniform control flow, one elected lane issues =====
+        constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, L_BN, false, false);
+        const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(ring), 16, 1024);
+        const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_r), 16, 1024);
+        ptx::mbar_wait(r_bar, 0);
+        ptx::tc_fence_after_sync();
+        uint32_t it = 0;
+        for (int t = 1; t < p.T; t++) {
+            for (int kb = 0; kb < num_kb; kb++, it++) {
+                const int s = it % stages;
+                ptx::mbar_wait(&full_bar[s], (it / stages) & 1);
+                ptx::tc_fence_after_sync();
+                if (ptx::elect_one()) {
+                    const uint64_t da = ptx::desc_advance(da0, (uint32_t)s * stage_bytes);
+                    const uint64_t db = ptx::desc_advance(db0, (uint32_t)kb * 4096u);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++)
-                        ptx::mma_tf32_ss(tmem_base, ptx::make_smem_desc(a_addr + k * (UMMA_K * 4), 16, 1024),
-                                         ptx::make_smem_desc(b_addr + k * (UMMA_K * 4), 16, 1024), idesc, (kb | k) != 0);
+                        ptx::mma_tf32_ss(tmem_base, ptx::desc_advance(da, k * (UMMA_K * 4)),
+                                         ptx::desc_advance(db, k * (UMMA_K * 4)), idesc, (kb | k) != 0);
                     if (CL == 1) ptx::mma_commit(&empty_bar[s]); else ptx::mma_commit_multicast(&empty_bar[s], kMask);
+                    if (kb == num_kb - 1) ptx::mma_commit(tmem_full);
                 }
-                ptx::mma_commit(tmem_full);
+                __syncwarp();
             }
         }
     } else {

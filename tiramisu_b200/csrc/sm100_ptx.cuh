@@ -274,9 +274,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr uint64_t kLayoutSw128 = 2;
 constexpr uint64_t kLayoutSw128Base32 = 1;     // 128B swizzle of 32-byte atoms: MN-major 32-bit operands
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint64_t layout = kLayoutSw128)
+                                                   uint64_t layout = kLayoutSw128, uint32_t base_offset = 0)
 {
     uint64_t d = 0;
+    d |= (uint64_t)(base_offset & 7u) << 49;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
@@ -284,6 +285,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= layout << 61;
     return d;
 }
+
+// Advance a descriptor's start address by `bytes` (multiple of 16; the sum must stay below 256 KB).
+// The MMA issue loops build ONE descriptor per operand tile and step it with immediate adds: the
+// issuing warp runs with warp-uniform control flow (elect_one() picks the lane), so descriptors
+// live in uniform registers and each tcgen05.mma costs a couple of scalar instructions.  (r01 ncu:
+// issuing from inside `if (lane == 0)` made ptxas wrap every UTCHMMA in an ELECT/BRA waterfall,
+// ~25 SASS instructions per MMA — the limit for N <= 64 tiles, where an MMA lasts 16-32 cycles.)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 
 // Instruction descriptor (32-bit) for kind::tf32, fp32 accumulate:
 //   [4,6) D format (1 = F32)  [7,10) A format (2 = TF32)  [10,13) B format (2 = TF32)
