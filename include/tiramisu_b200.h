@@ -133,7 +133,9 @@ int tiramisu_b200_lstm(const float *Weights, const float *biases, const float *x
                        int32_t F, int32_t B, int32_t L, int32_t T);
 int tiramisu_b200_set_lstm_mode(int mode);
 /* Recurrence engine of the tensor path: 0 = auto, 1 = one launch per cell, 2 = persistent layer
- * kernel (recurrent weights resident in shared memory, device-wide step barrier). */
+ * kernel, gate columns split across CTAs (recurrent weights resident in shared memory, device-wide
+ * step barrier), 3 = persistent layer kernel, K split across 4-CTA clusters with a distributed-
+ * shared-memory reduction (F % 128 == 0, B <= 64). */
 int tiramisu_b200_set_lstm_kernel(int kernel);
 
 /* ===================================================================== B2: distributed runtime

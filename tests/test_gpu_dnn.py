@@ -137,13 +137,17 @@ def test_lstm_tensor_path(api, F, B, L, T, scale):
         api.set_lstm_mode(prev)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("F,B,L,T,scale", [(64, 16, 2, 6, 4.0), (256, 100, 2, 5, 8.0), (128, 64, 3, 20, 8.0),
-                                           (1024, 64, 2, 6, 32.0)])
+                                           (1024, 64, 2, 6, 32.0), (256, 48, 2, 7, 8.0), (512, 64, 2, 5, 16.0),
+                                           (384, 5, 1, 4, 8.0)])
 def test_lstm_recurrence_engines(api, kernel, F, B, L, T, scale):
-    """Per-cell launches (1) and the persistent layer kernel (2: weights resident in shared memory,
-    cell state in registers, device-wide step barrier, multicast ring) against the oracle; T is
-    long enough for the ring and the barrier counter to wrap several times."""
+    """Per-cell launches (1), the N-split persistent layer kernel (2: weights resident in shared
+    memory, cell state in registers, device-wide step barrier, multicast ring) and the K-split
+    persistent layer kernel (3: cluster of 4, DSMEM reduction) against the oracle; T is long enough
+    for rings, barrier phases and the step counter to wrap several times."""
+    if kernel == 3 and (F % 128 or B > 64):
+        pytest.skip("K-split engine needs F % 128 == 0 and B <= 64")
     prev_m, prev_k = api.set_lstm_mode(2), api.set_lstm_kernel(kernel)
     try:
         W, b, x = refdata.lstm_inputs(F, B, L, T, scale=scale)
@@ -160,7 +164,7 @@ def test_lstm_engines_agree_full_width(api):
     """F=1024, B=64 (BASELINE config 4 shape, shorter sequence): both engines, same inputs."""
     W, b, x = refdata.lstm_inputs(1024, 64, 2, 12, scale=32.0)
     outs = []
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3):
         prev_m, prev_k = api.set_lstm_mode(2), api.set_lstm_kernel(kernel)
         try:
             outs.append(_lstm(api, W, b, x))
@@ -168,6 +172,7 @@ def test_lstm_engines_agree_full_width(api):
             api.set_lstm_mode(prev_m)
             api.set_lstm_kernel(prev_k)
     assert float(np.abs(outs[0] - outs[1]).max()) < 5e-3
+    assert float(np.abs(outs[0] - outs[2]).max()) < 5e-3
 
 
 def test_lstm_wrapper_data_saturated(api):

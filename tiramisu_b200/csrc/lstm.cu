@@ -245,6 +245,8 @@ struct LayerParams {
     const float *bias;      // [4F] packed
     float *h;               // [T][B][F] output of this layer
     uint32_t *counter;      // device-wide step barrier, zero at launch
+    int dbg;                // timing experiments only (TB200_LSTM_DBG): 1 = producers do not wait for the
+                            // step barrier, 2 = no recurrent loads/MMAs at all (results are then wrong)
 };
 
 __device__ __forceinline__ void grid_wait(const uint32_t *ctr, uint32_t target)
@@ -307,7 +309,7 @@ tiramisu_sm100_lstm_layer_tf32(const __grid_constant__ CUtensorMap map_h, const 
         const int rows_per_cta = p.a_rows / CL;
         uint32_t it = 0;
         for (int t = 1; t < p.T; t++) {
-            grid_wait(p.counter, (uint32_t)gridDim.x * (uint32_t)t);      // every CTA has published h[t-1]
+            if (!(p.dbg & 1)) grid_wait(p.counter, (uint32_t)gridDim.x * (uint32_t)t);      // every CTA has published h[t-1]
             ptx::fence_proxy_async_all();
             for (int kb = 0; kb < num_kb; kb++, it++) {
                 const int s = it % stages;
@@ -408,6 +410,234 @@ tiramisu_sm100_lstm_layer_tf32(const __grid_constant__ CUtensorMap map_h, const 
     if (warp == 1) {
         ptx::tc_fence_after_sync();
         ptx::tmem_dealloc(tmem_base, 32);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-split persistent layer kernel — the default recurrence engine (F % 128 == 0, B <= 64, F/8 <= #SMs).
+// The N-split kernel above issues 128 small MMAs (M=128 x N=32) per step behind a 32-slab ring:
+// r01 ncu shows the tensor pipe 9 % busy and each step bound by ring round trips + per-slab
+// synchronisation (12.8 us/step).  Here the operands are flipped and K is split across a cluster:
+//   * cluster j (4 CTAs) owns the 128 packed gate rows [128j, +128) = hidden units [32j, +32);
+//     CTA ks of the cluster keeps R[128 rows][K slice ks = F/4 columns] resident in shared memory
+//     (128 KB at F = 1024) as the A operand (M = 128);
+//   * per step the B operand is h[t-1][:, K slice] (64 x F/4 fp32 = 64 KB): the whole step's input
+//     is in flight at once (no ring reuse inside a step), and 4F/128 = 32 MMAs (N = 64) produce
+//     the partial pre-activations P_ks[128][64] in TMEM;
+//   * the four partials are reduced through distributed shared memory: warp q of every CTA pushes
+//     TMEM lane quarter q (gate rows [32q, +32)) into CTA q's receive buffer (st.shared::cluster,
+//     XOR-swizzled rows) and arrives on CTA q's mbarrier; CTA q sums them in a fixed order, adds
+//     Xg + bias, applies the gates for its 8 units x 64 batch entries (cell state in registers)
+//     and writes h[t];
+//   * steps are separated by the device-wide counter barrier (one fence per CTA, relaxed polling).
+constexpr int KS_CL = 4;
+constexpr int KS_RECV_BYTES = 4 * 32 * 64 * 4;     // [src CTA][gate row][batch], 32 KB
+
+struct KSplitParams {
+    int B, F, T;
+    const float *xg;        // [T*B][4F] packed gate columns
+    const float *bias;      // [4F] packed
+    float *h;               // [T][B][F]
+    uint32_t *counter;
+    int dbg;
+};
+
+__device__ __forceinline__ void grid_wait_relaxed(const uint32_t *ctr, uint32_t target)
+{
+    const long long t0 = clock64();
+    while (ptx::ld_relaxed_gpu(ctr) < target) {
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+    ptx::fence_acq_rel_gpu();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_r,
+                                 const KSplitParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int KB = p.F / (KS_CL * BK);                       // 32-column k-blocks per K slice (<= 8)
+    const int half = (KB + 1) / 2;
+    uint8_t *smem_r = smem;                                  // KB x [128 rows][32 k]  (16 KB each)
+    uint8_t *smem_h = smem_r + (size_t)KB * 16384;           // KB x [64 rows][32 k]   (8 KB each)
+    float *recv = reinterpret_cast<float *>(smem_h + (size_t)KB * 8192);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(recv) + KS_RECV_BYTES);   // [2]
+    uint64_t *r_bar = full_bar + 2;
+    uint64_t *tmem_full = r_bar + 1;
+    uint64_t *recv_bar = tmem_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(recv_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ks = ptx::cluster_ctarank();              // K slice of this CTA = its rank in the cluster
+    const int j = blockIdx.x / KS_CL;                        // gate-row group of the cluster
+    const int k_base = (int)ks * (p.F / KS_CL);
+
+    if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&map_h); ptx::prefetch_tensormap(&map_r); }
+    if (warp == 1) {
+        if (lane == 0) {
+            ptx::mbar_init(&full_bar[0], 1);
+            ptx::mbar_init(&full_bar[1], 1);
+            ptx::mbar_init(r_bar, 1);
+            ptx::mbar_init(tmem_full, 1);
+            ptx::mbar_init(recv_bar, KS_CL * 32);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 64);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    ptx::cluster_sync();                                     // peers' barriers exist before any remote arrive
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(r_bar, (uint32_t)KB * 16384u);
+            for (int kb = 0; kb < KB; kb++)
+                ptx::tma_load_2d(smem_r + kb * 16384, &map_r, r_bar, k_base + kb * BK, 128 * j);
+        }
+        __syncwarp();
+        for (int t = 1; t < p.T; t++) {
+            if (!(p.dbg & 1)) grid_wait_relaxed(p.counter, (uint32_t)gridDim.x * (uint32_t)t);   // h[t-1] is complete
+            ptx::fence_proxy_async_all();
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&full_bar[0], (uint32_t)half * 8192u);
+                for (int kb = 0; kb < half; kb++)
+                    ptx::tma_load_3d(smem_h + kb * 8192, &map_h, &full_bar[0], k_base + kb * BK, 0, t - 1);
+                if (KB > half) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[1], (uint32_t)(KB - half) * 8192u);
+                    for (int kb = half; kb < KB; kb++)
+                        ptx::tma_load_3d(smem_h + kb * 8192, &map_h, &full_bar[1], k_base + kb * BK, 0, t - 1);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = ptx::make_idesc_tf32(128, 64, false, false);
+        const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_r), 16, 1024);
+        const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_h), 16, 1024);
+        ptx::mbar_wait(r_bar, 0);
+        ptx::tc_fence_after_sync();
+        for (int t = 1; t < p.T; t++) {
+            const uint32_t ph = (uint32_t)(t - 1) & 1u;
+            ptx::mbar_wait(&full_bar[0], ph);
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+                for (int kb = 0; kb < half; kb++) {
+                    const uint64_t da = ptx::desc_advance(da0, (uint32_t)kb * 16384u), db = ptx::desc_advance(db0, (uint32_t)kb * 8192u);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++)
+                        ptx::mma_tf32_ss(tmem_base, ptx::desc_advance(da, k * (UMMA_K * 4)),
+                                         ptx::desc_advance(db, k * (UMMA_K * 4)), idesc, (kb | k) != 0);
+                }
+                if (KB == half) ptx::mma_commit(tmem_full);
+            }
+            __syncwarp();
+            if (KB > half) {
+                ptx::mbar_wait(&full_bar[1], ph);
+                ptx::tc_fence_after_sync();
+                if (ptx::elect_one()) {
+                    for (int kb = half; kb < KB; kb++) {
+                        const uint64_t da = ptx::desc_advance(da0, (uint32_t)kb * 16384u), db = ptx::desc_advance(db0, (uint32_t)kb * 8192u);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; k++)
+                            ptx::mma_tf32_ss(tmem_base, ptx::desc_advance(da, k * (UMMA_K * 4)),
+                                             ptx::desc_advance(db, k * (UMMA_K * 4)), idesc, true);
+                    }
+                    ptx::mma_commit(tmem_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue =====
+        const uint32_t q = (uint32_t)warp & 3u;        // TMEM lane quarter this warp reads = destination CTA of its rows
+        const int e = (int)q * 32 + lane;              // 0..127
+        const int b = e & 63;                          // batch entry this thread finalises
+        const int ug = e >> 6;                         // which 4 of the CTA's 8 hidden units
+        const bool ok = b < p.B;
+        const int p0 = 128 * j + 32 * (int)ks + 16 * ug;          // first packed gate column of this thread
+        const int u0 = 32 * j + 8 * (int)ks + 4 * ug;             // first hidden unit of this thread
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 bs[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) bs[u] = __ldg(reinterpret_cast<const float4 *>(p.bias + p0) + u);
+        // where this warp's TMEM rows go: CTA q, slot [src = ks][row = lane]
+        const uint32_t push_addr = ptx::mapa_u32(reinterpret_cast<uint8_t *>(recv) + ks * 8192u + (uint32_t)lane * 256u, q);
+        const uint32_t push_bar = ptx::mapa_u32(recv_bar, q);
+        for (int t = 0; t < p.T; t++) {
+            float4 xg[4];
+            if (ok) {
+                const float4 *xp = reinterpret_cast<const float4 *>(p.xg + ((size_t)t * p.B + b) * 4 * p.F + p0);
+#pragma unroll
+                for (int u = 0; u < 4; u++) xg[u] = __ldg(xp + u);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) xg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float acc[16];
+#pragma unroll
+            for (int a = 0; a < 16; a++) acc[a] = 0.0f;
+            if (t > 0) {
+                ptx::mbar_wait(tmem_full, (uint32_t)(t - 1) & 1u);
+                ptx::tc_fence_after_sync();
+                uint32_t v[64];
+                __syncwarp();
+                ptx::tmem_ld_32x32_nowait(tmem_base + ((q * 32u) << 16), v);
+                ptx::tmem_ld_32x32_nowait(tmem_base + ((q * 32u) << 16) + 32u, v + 32);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before_sync();
+                // push gate row (32q + lane) of this CTA's partial to its owner, 16-byte chunks XOR-swizzled by row
+#pragma unroll
+                for (int ch = 0; ch < 16; ch++)
+                    ptx::st_cluster_v4(push_addr + (uint32_t)((ch ^ (lane & 7)) * 16), __uint_as_float(v[4 * ch + 0]),
+                                       __uint_as_float(v[4 * ch + 1]), __uint_as_float(v[4 * ch + 2]),
+                                       __uint_as_float(v[4 * ch + 3]));
+                ptx::mbar_arrive_cluster_addr(push_bar);
+                // the four partials of my rows have landed
+                ptx::mbar_wait_cluster(recv_bar, (uint32_t)(t - 1) & 1u);
+#pragma unroll
+                for (int a = 0; a < 16; a++) {
+                    const int row = 16 * ug + a;
+                    const int col = ((((b >> 2) ^ (row & 7)) << 2) | (b & 3));
+                    float sum = recv[0 * 2048 + row * 64 + col];
+                    sum += recv[1 * 2048 + row * 64 + col];
+                    sum += recv[2 * 2048 + row * 64 + col];
+                    sum += recv[3 * 2048 + row * 64 + col];
+                    acc[a] = sum;
+                }
+            }
+            float hn[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float si = acc[4 * u + 0] + xg[u].x + bs[u].x;
+                const float sz = acc[4 * u + 1] + xg[u].y + bs[u].y;
+                const float so = acc[4 * u + 2] + xg[u].z + bs[u].z;
+                const float sf = acc[4 * u + 3] + xg[u].w + bs[u].w;
+                const float gi = sigmoid_fast(si), gz = ptx::tanh_approx(sz), go = sigmoid_fast(so), gf = sigmoid_fast(sf);
+                c[u] = gi * gz + gf * c[u];
+                hn[u] = ptx::tanh_approx(c[u]) * go;
+            }
+            if (ok)
+                *reinterpret_cast<float4 *>(p.h + ((size_t)t * p.B + b) * p.F + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            // publish h[t]: CTA-wide rendezvous of the writers, then ONE gpu-scope fence + counter increment
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (e == 0) {
+                ptx::fence_acq_rel_gpu();
+                ptx::red_relaxed_gpu_add(p.counter, 1u);
+            }
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    ptx::cluster_sync();                                     // nobody exits while peers may still push into it
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem_base, 64);
     }
 }
 
@@ -518,6 +748,52 @@ int pick_cluster(int F, int a_rows)
     return 1;
 }
 
+size_t ksplit_smem_bytes(int F) { return (size_t)(F / (KS_CL * BK)) * (16384 + 8192) + KS_RECV_BYTES + 256 + 1024; }
+
+// K-split engine: shape + co-residency (all F/8 CTAs, clusters of 4, must be resident for the step barrier)
+bool ksplit_ok(int F, int B)
+{
+    if (F % 128 != 0 || B > 64 || F / 8 > sm_count() || ksplit_smem_bytes(F) > 227 * 1024) return false;
+    static int cached_F = 0;
+    static bool cached = false;
+    if (cached_F == F) return cached;
+    auto kern = tiramisu_sm100_lstm_layer_ksplit;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(F / 8));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = ksplit_smem_bytes(F);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = KS_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    cached_F = F;
+    cached = n * KS_CL >= F / 8;
+    return cached;
+}
+
+int launch_ksplit(const CUtensorMap &map_h, const CUtensorMap &map_r, const KSplitParams &p)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.F / 8));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = ksplit_smem_bytes(p.F);
+    cfg.stream = stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = KS_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_ksplit, map_h, map_r, p));
+    return post_launch("tiramisu_sm100_lstm_layer_ksplit");
+}
+
 int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y)
 {
     const size_t BF = (size_t)B * F, TB = (size_t)T * B;
@@ -531,11 +807,13 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
     if (!Wp || !bp || !xg || !hs || !cs || !zero || !counters) return 1;
     TB200_CHECK(cudaMemsetAsync(zero, 0, BF * 4, stream()));
     TB200_CHECK(cudaMemsetAsync(counters, 0, (size_t)L * 4, stream()));
-    // recurrence engine: the persistent layer kernel when the shape allows it (g_lstm_kernel: 0 auto,
-    // 1 = one launch per cell, 2 = persistent layer kernel)
+    // recurrence engine (g_lstm_kernel: 0 auto, 1 = one launch per cell, 2 = persistent N-split layer
+    // kernel, 3 = persistent K-split layer kernel); auto prefers 3, then 2, then 1
     int which = g_lstm_kernel.load();
     if (const char *e = getenv("TB200_LSTM_KERNEL")) which = atoi(e);
-    const bool use_layer_kernel = which != 1 && layer_kernel_ok(F, B);
+    const bool use_ksplit = (which == 0 || which == 3) && ksplit_ok(F, B);
+    if (which == 3 && !use_ksplit) return fail("tiramisu_b200_lstm", "shape not supported by the K-split layer kernel");
+    const bool use_layer_kernel = !use_ksplit && which != 1 && which != 3 && layer_kernel_ok(F, B);
     if (which == 2 && !use_layer_kernel) return fail("tiramisu_b200_lstm", "shape not supported by the persistent layer kernel");
     const int a_rows = B <= 64 ? 64 : 128;
     const int cl = use_layer_kernel ? pick_cluster(F, a_rows) : 1;
@@ -565,6 +843,27 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
             uint32_t box[2] = {BK, BN};
             if (make_tensor_map_f32(&map_r, Wp, 2, dims, str, box)) return 1;
         }
+        if (use_ksplit) {
+            CUtensorMap map_h3, map_ra;
+            {
+                uint64_t dims[3] = {(uint64_t)F, (uint64_t)B, (uint64_t)T};
+                uint64_t str[2] = {(uint64_t)F * 4, (uint64_t)B * F * 4};
+                uint32_t box[3] = {BK, 64, 1};
+                if (make_tensor_map_f32(&map_h3, hl, 3, dims, str, box)) return 1;
+            }
+            {
+                uint64_t dims[2] = {(uint64_t)F, 4 * (uint64_t)F};
+                uint64_t str[1] = {(uint64_t)F * 4};
+                uint32_t box[2] = {BK, 128};
+                if (make_tensor_map_f32(&map_ra, Wp, 2, dims, str, box)) return 1;
+            }
+            KSplitParams kp;
+            kp.B = B; kp.F = F; kp.T = T; kp.xg = xg; kp.bias = bp; kp.h = hl; kp.counter = counters + l;
+            kp.dbg = 0;
+            if (const char *e = getenv("TB200_LSTM_DBG")) kp.dbg = atoi(e);
+            if (launch_ksplit(map_h3, map_ra, kp)) return 1;
+            continue;
+        }
         if (use_layer_kernel) {
             // one persistent launch for all T steps
             CUtensorMap map_h3;
@@ -575,6 +874,8 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
             LayerParams lp;
             lp.B = B; lp.F = F; lp.T = T; lp.a_rows = a_rows;
             lp.xg = xg; lp.bias = bp; lp.h = hl; lp.counter = counters + l;
+            lp.dbg = 0;
+            if (const char *e = getenv("TB200_LSTM_DBG")) lp.dbg = atoi(e);
             bool unused = false;
             if (layer_dispatch(cl, map_h3, map_r, lp, false, &unused)) return 1;
             continue;
@@ -613,7 +914,7 @@ TB200_API int tiramisu_b200_set_lstm_mode(int mode)
 
 TB200_API int tiramisu_b200_set_lstm_kernel(int kernel)
 {
-    if (kernel < 0 || kernel > 2) kernel = 0;
+    if (kernel < 0 || kernel > 3) kernel = 0;
     return g_lstm_kernel.exchange(kernel);
 }
 
