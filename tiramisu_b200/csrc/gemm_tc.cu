@@ -195,14 +195,31 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        ptx::mbar_wait(tmem_full_bar, 0);
-        ptx::tc_fence_after_sync();
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < p.M;
         float *crow = p.C + (size_t)row * p.ldC;
         const bool use_c = p.beta != 0.0f;             // cuBLAS semantics: C not read when beta == 0
+        // The beta*C operand does not depend on the MMAs: fetch the first 32-column chunk of this
+        // thread's C row while the main loop runs, and each further chunk one iteration ahead (at
+        // 1024^3 the whole kernel lasts a few microseconds and this latency was exposed, r01 ncu).
+        auto load_c = [&](int c0, float4 (&cv)[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int col = n0 + c0 + 4 * j;
+                cv[j] = (use_c && row_ok && col + 3 < p.N) ? *reinterpret_cast<const float4 *>(crow + col)
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 cnext[8];
+        load_c(0, cnext);
+        ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::tc_fence_after_sync();
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+            float4 ccur[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) ccur[j] = cnext[j];
+            if (c0 + 32 < BN) load_c(c0 + 32, cnext);
             uint32_t r[32];
             __syncwarp();                              // tcgen05.ld is .sync.aligned: whole warp, converged
             ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -217,15 +234,14 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
                         o.y = __fmul_rn(__uint_as_float(r[j + 1]), p.alpha);
                         o.z = __fmul_rn(__uint_as_float(r[j + 2]), p.alpha);
                         o.w = __fmul_rn(__uint_as_float(r[j + 3]), p.alpha);
-                        float4 *dst = reinterpret_cast<float4 *>(crow + col);
                         if (use_c) {
-                            const float4 c = *dst;
+                            const float4 c = ccur[j >> 2];
                             o.x = __fadd_rn(o.x, __fmul_rn(c.x, p.beta));
                             o.y = __fadd_rn(o.y, __fmul_rn(c.y, p.beta));
                             o.z = __fadd_rn(o.z, __fmul_rn(c.z, p.beta));
                             o.w = __fadd_rn(o.w, __fmul_rn(c.w, p.beta));
                         }
-                        *dst = o;
+                        *reinterpret_cast<float4 *>(crow + col) = o;
                     } else {
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
@@ -431,10 +447,27 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
             const int row = m0 + (int)cta_rank * BM + q * 32 + lane;
             const bool row_ok = row < p.M;
             float *crow = p.C + (size_t)row * p.ldC;
+            // beta*C does not depend on the MMAs: fetch each 32-column chunk one iteration ahead, the
+            // first one before waiting for the accumulator (matters for the last tile of a CTA,
+            // whose epilogue nothing overlaps)
+            auto load_c = [&](int c0, float4 (&cv)[8]) {
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const int col = n0 + c0 + 4 * jj;
+                    cv[jj] = (use_c && row_ok && col + 3 < p.N) ? *reinterpret_cast<const float4 *>(crow + col)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            float4 cnext[8];
+            load_c(half * 128, cnext);
             ptx::mbar_wait(&tmem_full[buf], (local >> 1) & 1);
             ptx::tc_fence_after_sync();
 #pragma unroll 1
             for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+                float4 ccur[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) ccur[jj] = cnext[jj];
+                if (c0 + 32 < half * 128 + 128) load_c(c0 + 32, cnext);
                 uint32_t r[32];
                 __syncwarp();
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * P_BN + (uint32_t)c0, r);
@@ -449,15 +482,14 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                             o.y = __fmul_rn(__uint_as_float(r[j + 1]), p.alpha);
                             o.z = __fmul_rn(__uint_as_float(r[j + 2]), p.alpha);
                             o.w = __fmul_rn(__uint_as_float(r[j + 3]), p.alpha);
-                            float4 *dst = reinterpret_cast<float4 *>(crow + col);
                             if (use_c) {
-                                const float4 c = *dst;
+                                const float4 c = ccur[j >> 2];
                                 o.x = __fadd_rn(o.x, __fmul_rn(c.x, p.beta));
                                 o.y = __fadd_rn(o.y, __fmul_rn(c.y, p.beta));
                                 o.z = __fadd_rn(o.z, __fmul_rn(c.z, p.beta));
                                 o.w = __fadd_rn(o.w, __fmul_rn(c.w, p.beta));
                             }
-                            *dst = o;
+                            *reinterpret_cast<float4 *>(crow + col) = o;
                         } else {
 #pragma unroll
                             for (int u = 0; u < 4; u++) {

@@ -18,6 +18,9 @@
 #include "sm100_ptx.cuh"
 #include "tiramisu_b200.h"
 
+#include <cstdio>
+#include <vector>
+
 using namespace tb200;
 
 namespace tb200 {
@@ -425,8 +428,8 @@ tiramisu_sm100_lstm_layer_tf32(const __grid_constant__ CUtensorMap map_h, const 
 //     is in flight at once (no ring reuse inside a step), and 4F/128 = 32 MMAs (N = 64) produce
 //     the partial pre-activations P_ks[128][64] in TMEM;
 //   * the four partials are reduced through distributed shared memory: warp q of every CTA pushes
-//     TMEM lane quarter q (gate rows [32q, +32)) into CTA q's receive buffer (st.shared::cluster,
-//     XOR-swizzled rows) and arrives on CTA q's mbarrier; CTA q sums them in a fixed order, adds
+//     TMEM lane quarter q (gate rows [32q, +32)) into CTA q's receive buffer with st.async
+//     (XOR-swizzled rows; every 16-byte store signals complete_tx on CTA q's mbarrier — no fences); CTA q sums them in a fixed order, adds
 //     Xg + bias, applies the gates for its 8 units x 64 batch entries (cell state in registers)
 //     and writes h[t];
 //   * steps are separated by the device-wide counter barrier (one fence per CTA, relaxed polling).
@@ -440,7 +443,19 @@ struct KSplitParams {
     float *h;               // [T][B][F]
     uint32_t *counter;
     int dbg;
+    unsigned long long *trace;   // optional [grid][T][8] %globaltimer stamps (TB200_LSTM_TRACE, bring-up only)
 };
+
+__device__ __forceinline__ unsigned long long globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define KS_TRACE(slot)                                                                              \
+    do {                                                                                            \
+        if (p.trace) p.trace[((size_t)blockIdx.x * p.T + t) * 8 + (slot)] = globaltimer();          \
+    } while (0)
 
 __device__ __forceinline__ void grid_wait_relaxed(const uint32_t *ctr, uint32_t target)
 {
@@ -480,7 +495,7 @@ tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, cons
             ptx::mbar_init(&full_bar[1], 1);
             ptx::mbar_init(r_bar, 1);
             ptx::mbar_init(tmem_full, 1);
-            ptx::mbar_init(recv_bar, KS_CL * 32);
+            ptx::mbar_init(recv_bar, 1);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -504,6 +519,7 @@ tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, cons
             if (!(p.dbg & 1)) grid_wait_relaxed(p.counter, (uint32_t)gridDim.x * (uint32_t)t);   // h[t-1] is complete
             ptx::fence_proxy_async_all();
             if (ptx::elect_one()) {
+                KS_TRACE(0);
                 ptx::mbar_arrive_expect_tx(&full_bar[0], (uint32_t)half * 8192u);
                 for (int kb = 0; kb < half; kb++)
                     ptx::tma_load_3d(smem_h + kb * 8192, &map_h, &full_bar[0], k_base + kb * BK, 0, t - 1);
@@ -527,6 +543,7 @@ tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, cons
             ptx::mbar_wait(&full_bar[0], ph);
             ptx::tc_fence_after_sync();
             if (ptx::elect_one()) {
+                KS_TRACE(1);
                 for (int kb = 0; kb < half; kb++) {
                     const uint64_t da = ptx::desc_advance(da0, (uint32_t)kb * 16384u), db = ptx::desc_advance(db0, (uint32_t)kb * 8192u);
 #pragma unroll
@@ -541,6 +558,7 @@ tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, cons
                 ptx::mbar_wait(&full_bar[1], ph);
                 ptx::tc_fence_after_sync();
                 if (ptx::elect_one()) {
+                    KS_TRACE(2);
                     for (int kb = half; kb < KB; kb++) {
                         const uint64_t da = ptx::desc_advance(da0, (uint32_t)kb * 16384u), db = ptx::desc_advance(db0, (uint32_t)kb * 8192u);
 #pragma unroll
@@ -583,8 +601,11 @@ tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, cons
 #pragma unroll
             for (int a = 0; a < 16; a++) acc[a] = 0.0f;
             if (t > 0) {
+                // arm this step's receive phase: 4 source CTAs x 32 rows x 256 B arrive as st.async transactions
+                if (e == 0) ptx::mbar_arrive_expect_tx(recv_bar, (uint32_t)KS_RECV_BYTES);
                 ptx::mbar_wait(tmem_full, (uint32_t)(t - 1) & 1u);
                 ptx::tc_fence_after_sync();
+                if (e == 0) KS_TRACE(3);
                 uint32_t v[64];
                 __syncwarp();
                 ptx::tmem_ld_32x32_nowait(tmem_base + ((q * 32u) << 16), v);
@@ -594,12 +615,13 @@ tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, cons
                 // push gate row (32q + lane) of this CTA's partial to its owner, 16-byte chunks XOR-swizzled by row
 #pragma unroll
                 for (int ch = 0; ch < 16; ch++)
-                    ptx::st_cluster_v4(push_addr + (uint32_t)((ch ^ (lane & 7)) * 16), __uint_as_float(v[4 * ch + 0]),
-                                       __uint_as_float(v[4 * ch + 1]), __uint_as_float(v[4 * ch + 2]),
-                                       __uint_as_float(v[4 * ch + 3]));
-                ptx::mbar_arrive_cluster_addr(push_bar);
+                    ptx::st_async_cluster_v4(push_addr + (uint32_t)((ch ^ (lane & 7)) * 16), push_bar,
+                                             __uint_as_float(v[4 * ch + 0]), __uint_as_float(v[4 * ch + 1]),
+                                             __uint_as_float(v[4 * ch + 2]), __uint_as_float(v[4 * ch + 3]));
+                if (e == 0) KS_TRACE(4);
                 // the four partials of my rows have landed
-                ptx::mbar_wait_cluster(recv_bar, (uint32_t)(t - 1) & 1u);
+                ptx::mbar_wait(recv_bar, (uint32_t)(t - 1) & 1u);
+                if (e == 0) KS_TRACE(5);
 #pragma unroll
                 for (int a = 0; a < 16; a++) {
                     const int row = 16 * ug + a;
@@ -625,10 +647,12 @@ tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, cons
             if (ok)
                 *reinterpret_cast<float4 *>(p.h + ((size_t)t * p.B + b) * p.F + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
             // publish h[t]: CTA-wide rendezvous of the writers, then ONE gpu-scope fence + counter increment
+            if (e == 0) KS_TRACE(6);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (e == 0) {
                 ptx::fence_acq_rel_gpu();
                 ptx::red_relaxed_gpu_add(p.counter, 1u);
+                KS_TRACE(7);
             }
         }
     }
@@ -860,8 +884,23 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
             KSplitParams kp;
             kp.B = B; kp.F = F; kp.T = T; kp.xg = xg; kp.bias = bp; kp.h = hl; kp.counter = counters + l;
             kp.dbg = 0;
+            kp.trace = nullptr;
             if (const char *e = getenv("TB200_LSTM_DBG")) kp.dbg = atoi(e);
+            const char *trace_path = (l == 0) ? getenv("TB200_LSTM_TRACE") : nullptr;    // bring-up: timeline of layer 0
+            const size_t trace_n = (size_t)(F / 8) * T * 8;
+            if (trace_path) {
+                kp.trace = reinterpret_cast<unsigned long long *>(pool_alloc(trace_n * 8));
+                if (!kp.trace) return 1;
+                TB200_CHECK(cudaMemsetAsync(kp.trace, 0, trace_n * 8, stream()));
+            }
             if (launch_ksplit(map_h3, map_ra, kp)) return 1;
+            if (trace_path) {
+                std::vector<unsigned long long> host(trace_n);
+                TB200_CHECK(cudaMemcpyAsync(host.data(), kp.trace, trace_n * 8, cudaMemcpyDeviceToHost, stream()));
+                TB200_CHECK(cudaStreamSynchronize(stream()));
+                if (FILE *f = fopen(trace_path, "wb")) { fwrite(host.data(), 8, trace_n, f); fclose(f); }
+                pool_free(kp.trace);
+            }
             continue;
         }
         if (use_layer_kernel) {

@@ -279,6 +279,14 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, f
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
 }
+// Asynchronous 16-byte store into a peer CTA's shared memory that signals completion (16 bytes of
+// complete_tx) on an mbarrier of that peer: producer/consumer over DSMEM without any fence.
+__device__ __forceinline__ void st_async_cluster_v4(uint32_t addr, uint32_t mbar_addr, float a, float b, float c, float d)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%2, %3, %4, %5}, [%1];"
+                 ::"r"(addr), "r"(mbar_addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
 // arrive (release at cluster scope: this thread's earlier DSMEM stores are visible to the waiter)
 __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t remote_bar_addr)
 {
