@@ -45,6 +45,21 @@ def measured_peaks() -> tuple[dict, str]:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic(kernel_file: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture of the
+    dominant kernel (profiles/), per launch, in bytes; None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", kernel_file)
+    if not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(path):
+        parts = line.split()
+        if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[2] in unit:
+            tot += float(parts[1]) * unit[parts[2]]
+    return tot or None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -151,6 +166,7 @@ def per_kernel_ms(torch, stream, fn, iters=10):
 
 
 def run_ours(args) -> None:
+    os.environ["NCCL_DEBUG"] = os.environ.get("TB200_NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
     import torch
     from tiramisu_b200 import _lib, api
 
@@ -166,66 +182,149 @@ def run_ours(args) -> None:
     peaks, peak_src = measured_peaks()
 
     # ---- shard: rows [r0, r1) of the GRID x GRID grid (strong scaling, BASELINE configs[1]) -------
+    # Each rank holds ONLY its row block plus halo rows: 1 row above (heat2d) and 2 rows below (blur
+    # reads y..y+2, heat2d y+1); every step starts with the halo exchange over NCCL (one grouped
+    # send/recv through the library's own communicator), as heat2d_dist / blurautodist do over MPI.
+    from tiramisu_b200 import dist as tdist
     N = GRID
-    r0, r1 = rank * N // world, (rank + 1) * N // world
-    with torch.cuda.stream(stream):
-        g = torch.Generator(device="cuda").manual_seed(1)
-        d_in = torch.rand((N, N), dtype=torch.float32, device="cuda", generator=g)
-        d_heat = torch.empty((N, N), dtype=torch.float32, device="cuda")
-        d_blur = torch.empty((N - 2, N - 2), dtype=torch.float32, device="cuda")
-    stream.synchronize()
+    r0, r1 = tdist.row_shard(N, world, rank)
+    top = 1 if rank > 0 else 0
+    bottom = 2 if rank < world - 1 else 0
+    rows = r1 - r0
     b0, b1 = min(r0, N - 2), min(r1, N - 2)
-    ip, hp, bp = d_in.data_ptr(), d_heat.data_ptr(), d_blur.data_ptr()
+    with torch.cuda.stream(stream):
+        g = torch.Generator(device="cuda").manual_seed(1 + rank)
+        d_loc = torch.zeros((top + rows + bottom, N), dtype=torch.float32, device="cuda")
+        d_loc[top:top + rows] = torch.rand((rows, N), dtype=torch.float32, device="cuda", generator=g)
+        d_heat = torch.empty((rows, N), dtype=torch.float32, device="cuda")
+        d_blur = torch.empty((max(b1 - b0, 1), N - 2), dtype=torch.float32, device="cuda")
+    stream.synchronize()
+    row_b = N * 4
+    # virtual row-0 pointers: the launchers index rows globally (row_begin/row_end are global rows)
+    ip = d_loc.data_ptr() - (r0 - top) * row_b
+    hp = d_heat.data_ptr() - r0 * row_b
+    bp = d_blur.data_ptr() - b0 * (N - 2) * 4
+    own = d_loc.data_ptr() + top * row_b                       # first owned row
 
-    def heat():
-        _lib.check(L.tiramisu_b200_heat2d(ip, hp, N, N, 0, r0, r1))
+    exchange = None
+    if world > 1:
+        import ctypes as C
+        tdist.comm_init_from_torch()
+        up, dn = rank - 1, rank + 1
+        sp = (C.c_int32 * 2)(up if rank > 0 else -1, dn if rank < world - 1 else -1)
+        sb = (C.c_void_p * 2)(own, own + (rows - 1) * row_b)                    # my first 2 rows up, my last row down
+        sn = (C.c_uint64 * 2)(2 * row_b, row_b)
+        rp = (C.c_int32 * 2)(up if rank > 0 else -1, dn if rank < world - 1 else -1)
+        rb = (C.c_void_p * 2)(d_loc.data_ptr(), own + rows * row_b)             # top halo (1 row), bottom halo (2 rows)
+        rn = (C.c_uint64 * 2)(row_b, 2 * row_b)
 
-    def blur():
-        _lib.check(L.tiramisu_b200_blur_f32(ip, bp, N, N, b0, b1))
+        def exchange():
+            _lib.check(L.tiramisu_b200_comm_exchange(2, sp, sb, sn, rp, rb, rn))
 
-    def step():
-        heat(); blur()
+    def heat(ya=r0, yb=r1):
+        if yb > ya:
+            _lib.check(L.tiramisu_b200_heat2d(ip, hp, N, N, 0, ya, yb))
+
+    def blur(ya=b0, yb=b1):
+        if yb > ya:
+            _lib.check(L.tiramisu_b200_blur_f32(ip, bp, N, N, ya, yb))
+
+    if world == 1:
+        def step():
+            heat(); blur()
+    else:
+        # Two streams per step: the comm stream does the halo exchange and then the few rows that read
+        # halo rows; the launch stream does the interior rows meanwhile and joins at the end.
+        comm_stream = torch.cuda.Stream()
+        ev_free, ev_done = torch.cuda.Event(), torch.cuda.Event()
+        hi0, hi1 = r0 + top, r1 - (1 if bottom else 0)          # heat2d rows that need no halo
+        bi1 = max(b0, b1 - (2 if bottom else 0))                # blur rows [b0, bi1) need no halo
+
+        def step():
+            ev_free.record(stream)                              # previous step's readers/writers are done
+            comm_stream.wait_event(ev_free)
+            api.set_stream(comm_stream.cuda_stream)
+            exchange()
+            heat(r0, hi0); heat(hi1, r1); blur(bi1, b1)
+            api.set_stream(stream.cuda_stream)
+            ev_done.record(comm_stream)
+            heat(hi0, hi1); blur(b0, bi1)
+            stream.wait_event(ev_done)
+
+    if world > 1:
+        # halo sanity: what I received must be what my neighbours own (checksums over the torch group)
+        step(); stream.synchronize()
+        mine = torch.stack([d_loc[top:top + 2].double().sum(), d_loc[top + rows - 1].double().sum(),
+                            d_loc[0:top].double().sum(), d_loc[top + rows:].double().sum()])
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        torch.distributed.all_gather(allv, mine)
+        if rank > 0:
+            assert abs(float(allv[rank - 1][1] - mine[2])) < 1e-6, "top halo != neighbour's last row"
+        if rank < world - 1:
+            assert abs(float(allv[rank + 1][0] - mine[3])) < 1e-6, "bottom halo != neighbour's first two rows"
 
     launches0 = api.kernel_launches()
     with ClockSampler(local) as clk:
         ms = time_steps(torch, stream, step, args.steps, args.warmup, world)
-    launches = (api.kernel_launches() - launches0) * world // (args.steps + args.warmup) * args.steps
+        launches = (api.kernel_launches() - launches0) * world // (args.steps + args.warmup) * args.steps
+        heat_ms, heat_best = per_kernel_ms(torch, stream, heat)
+        blur_ms, blur_best = per_kernel_ms(torch, stream, blur)
+        for _ in range(30):            # keep the GPU under the same load while nvidia-smi samples (100 ms period)
+            step()
+        stream.synchronize()
     bytes_step = alg_bytes(N, N)["step"]
     value = bytes_step / (ms * 1e-3) / 1e9
 
-    heat_ms, heat_best = per_kernel_ms(torch, stream, heat)
-    blur_ms, blur_best = per_kernel_ms(torch, stream, blur)
     heat_bytes = 2 * (r1 - r0) * N * 4
     blur_bytes = 4 * ((b1 - b0) * (N - 2) + (b1 - b0 + 2) * N)
     peak = float(peaks["hbm_gbs"])
     roof = {"kernel": "tiramisu_sm100_heat2d_v4", "bound": "hbm", "achieved": heat_bytes / (heat_ms * 1e-3) / 1e9,
-            "peak": peak, "unit": "GB/s", "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
-            "traffic": None, "ms": heat_ms}
+            "peak": peak, "unit": "GB/s", "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+            "traffic": ncu_traffic("r01_heat2d_ncu_full.txt") if world == 1 else None,
+            "traffic_source": "profiles/r01_heat2d_ncu_full.txt (ncu --set full, 16384^2, one launch)",
+            "algorithmic_bytes": heat_bytes, "ms": heat_ms}
     roof["frac"] = roof["achieved"] / peak
     kernels = {"heat2d": {"ms": heat_ms, "best_ms": heat_best, "GBps": roof["achieved"], "frac": roof["frac"]},
                "blur_f32": {"ms": blur_ms, "best_ms": blur_best, "GBps": blur_bytes / (blur_ms * 1e-3) / 1e9,
                             "frac": blur_bytes / (blur_ms * 1e-3) / 1e9 / peak}}
+    if exchange:
+        ex_ms, _ = per_kernel_ms(torch, stream, exchange)
+        kernels["halo_exchange"] = {"ms": ex_ms, "bytes_per_rank": 3 * row_b * (2 if 0 < rank < world - 1 else 1)}
+    d_in = d_loc
 
-    # ---- e2e: host buffers through the generated-function ABI (rank 0's shard only matters at N=1)
-    e2e = None
-    if world == 1:
-        h_in = torch.empty((N, N), dtype=torch.float32).pin_memory()
-        h_in.copy_(d_in)
-        h_heat = torch.empty((N, N), dtype=torch.float32).pin_memory()
-        h_blur = torch.empty((N - 2, N - 2), dtype=torch.float32).pin_memory()
+    # ---- e2e: the same step through the host-buffer generated-function ABI (pinned host memory; the
+    # H2D copy of the inputs and the D2H copy of the results are inside the timed region).  At N > 1
+    # every rank runs its own row block (+ halo rows, already on the host) as one grid.
+    LR = d_in.shape[0]
+    h_in = torch.empty((LR, N), dtype=torch.float32).pin_memory()
+    h_in.copy_(d_in)
+    h_heat = torch.empty((LR, N), dtype=torch.float32).pin_memory()
+    h_blur = torch.empty((LR - 2, N - 2), dtype=torch.float32).pin_memory()
 
-        def e2e_step():
-            api.heat2d_tiramisu(h_in, h_heat)
-            api.blurxy_f32_tiramisu(h_in, h_blur)
+    def e2e_step():
+        api.heat2d_tiramisu(h_in, h_heat)
+        api.blurxy_f32_tiramisu(h_in, h_blur)
 
+    e2e_step()
+    k = max(1, min(args.steps, 5))
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for _ in range(k):
         e2e_step()
-        k = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(k):
-            e2e_step()
-        dt = (time.perf_counter() - t0) / k
-        e2e = {"value": bytes_step / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": k,
-               "h2d_bytes_per_step": 2 * N * N * 4, "d2h_bytes_per_step": N * N * 4 + (N - 2) * (N - 2) * 4}
+    dt = (time.perf_counter() - t0) / k
+    e2e_bytes = float(alg_bytes(LR, N)["step"])
+    h2d, d2h = 2.0 * LR * N * 4, float(LR * N * 4 + (LR - 2) * (N - 2) * 4)
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dt = float(t.item())
+        tot = torch.tensor([e2e_bytes, h2d, d2h], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(tot)
+        e2e_bytes, h2d, d2h = (float(v) for v in tot.tolist())
+    e2e = {"value": e2e_bytes / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": k,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "how": "heat2d_tiramisu + blurxy_f32_tiramisu on pinned host buffers (row-chunk pipelined H2D | kernel | D2H)"}
 
     # ---- CPU baseline (rank 0, N=1): the oracle port on a bounded sample ---------------------------
     cpu = None
@@ -255,11 +354,13 @@ def run_ours(args) -> None:
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"heat2d + 3x3 blur fp32, {N}x{N} grid (BASELINE configs[1])",
-                           "sharding": f"rows/{world}", "l2": "inputs (1 GiB) >> L2, no flush"},
+                           "sharding": f"rows/{world}" + (", halo exchange over NCCL each step, overlapped with the interior rows" if world > 1 else ""),
+                           "l2": "inputs (1 GiB / n_gpus per rank) >> L2, no flush"},
                 "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clk.summary(), "others": others}
         print(json.dumps(line))
     if world > 1:
+        tdist.comm_destroy()
         torch.distributed.destroy_process_group()
 
 

@@ -655,11 +655,11 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
     if (const char *e = getenv("TB200_GEMM_KERNEL")) kernel = atoi(e);
     const uint64_t sms = (uint64_t)sm_count();
     if (kernel == 0) {
+        // measured (profiles/r01_results.md): the pair kernel wins from ~2048^2 outputs upwards even
+        // when it cannot fill every SM pair (2048^3: 416 vs 339 TFLOP/s); below that the one-tile-per-CTA
+        // kernel with narrow tiles (more CTAs, shorter critical path) is faster (1024^3: 147 vs 73).
         const uint64_t pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
-        const uint64_t cta_tiles = ((M + 127) / 128) * ((N + 255) / 256);
-        if (pair_tiles * 2 >= sms) kernel = 3;
-        else if (cta_tiles >= sms) kernel = 2;
-        else kernel = 1;
+        kernel = (pair_tiles * 2 * 5 >= sms * 4 && K >= 256) ? 3 : 1;
     }
     if (kernel == 3)
         return tB ? launch_tc_persistent<2, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC)

@@ -17,7 +17,27 @@ def _time(torch, stream, fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-def sgemm(torch, stream, peaks, sizes=(1024, 4096, 8192)):
+def cublas_tf32(torch, n, iters):
+    """Library reference point (context only, never on the product path): cuBLAS TF32 via torch.matmul."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.rand((n, n), device="cuda") * 2 - 1
+        b = torch.rand((n, n), device="cuda") * 2 - 1
+        for _ in range(3):
+            a @ b
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        return 2.0 * n ** 3 / (e0.elapsed_time(e1) / iters * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def sgemm(torch, stream, peaks, sizes=(1024, 2048, 4096, 8192, 16384)):
     from tiramisu_b200 import api
     out = {}
     tf32_peak = float(peaks.get("tf32_tflops", peaks["bf16_tflops"] / 2.0))
@@ -38,10 +58,17 @@ def sgemm(torch, stream, peaks, sizes=(1024, 4096, 8192)):
             idx[0] += 1
             api.cublas_sgemm(a.data_ptr(), b.data_ptr(), c.data_ptr(), n, n, n, 3.0, 2.0)
 
-        ms = _time(torch, stream, fn, iters=20 if n <= 4096 else 5)
+        ms = _time(torch, stream, fn, iters=20 if n <= 4096 else (5 if n <= 8192 else 3))
         tfl = 2.0 * n ** 3 / (ms * 1e-3) / 1e12
         out[f"sgemm_{n}"] = {"ms": ms, "TFLOPs": tfl, "GFLOPs": tfl * 1e3, "frac_of_tf32_peak": tfl / tf32_peak,
-                             "tf32_peak_TFLOPs": tf32_peak, "operand_sets": nsets}
+                             "tf32_peak_TFLOPs": tf32_peak, "operand_sets": nsets,
+                             "hbm_bound_ms": 16.0 * n * n / (float(peaks["hbm_gbs"]) * 1e9) * 1e3}
+        del sets
+        try:
+            out[f"sgemm_{n}"]["cublas_tf32_TFLOPs_same_run"] = cublas_tf32(torch, n, 20 if n <= 4096 else 3)
+        except Exception as e:  # context only
+            out[f"sgemm_{n}"]["cublas_tf32_TFLOPs_same_run"] = repr(e)
+        torch.cuda.empty_cache()
     return out
 
 
