@@ -648,6 +648,21 @@ bool gemm_tc_addressable(const float *A, const float *B, const float *C, uint64_
 int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha,
                 float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tB)
 {
+    // Very long K on a large output: run K panels of 4096 with beta = 1 accumulation.  Without a
+    // device-wide sync the persistent CTAs drift apart along K until the A/B slabs that concurrent
+    // tiles share fall out of L2 (16384^3: 547 TFLOP/s in one launch, 742 in four panels, r01);
+    // a panel boundary re-aligns them at the price of one extra read+write of C per panel.
+    if (K >= 12288 && M >= 4096 && N >= 4096 && !getenv("TB200_GEMM_NO_KPANELS")) {
+        const uint64_t panel = 4096;
+        for (uint64_t k0 = 0; k0 < K; k0 += panel) {
+            const uint64_t kk = (K - k0 < panel + panel / 2) ? K - k0 : panel;     // fold a short tail into the last panel
+            const float *Ap = A + k0;                                            // A is K-major (no transposeA here)
+            const float *Bp = tB ? B + k0 : B + k0 * ldB;
+            if (gemm_f32_tc(Ap, Bp, C, M, N, kk, alpha, k0 == 0 ? beta : 1.0f, ldA, ldB, ldC, tB)) return 1;
+            if (kk != panel) break;
+        }
+        return 0;
+    }
     const int m = (int)M, n = (int)N, k = (int)K;
     // Kernel choice: the persistent CTA-pair kernel once there is at least ~one 256x256 tile per SM
     // pair, the persistent single-CTA kernel for mid sizes, the one-tile-per-CTA kernel below that.

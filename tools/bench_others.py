@@ -122,11 +122,33 @@ def lstm(torch, stream, peaks):
                                        "frac_of_tf32_peak": tfl / tf32_peak, "us_per_cell": ms * 1e3 / (T * Ly)}}
 
 
+def _smi_clock():
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+        mhz, cap = [x.strip() for x in out.split(",")]
+        return {"sm_mhz_after": float(mhz), "sw_power_cap_after": cap}
+    except Exception:
+        return {}
+
+
 def run(torch, stream, peaks):
+    """Latency-bound items first, the power-hungry large GEMMs last, with a pause before each item: a
+    long TF32 GEMM leaves the part power-capped (clocks.sm ~900 MHz for a second or so, measured:
+    tools/clock_probe.py) and whatever runs next would be timed at half clock."""
+    import time
     res = {}
-    for name, fn in (("sgemm", sgemm), ("conv", conv), ("lstm", lstm)):
+    items = [("lstm", lambda: lstm(torch, stream, peaks)), ("conv", lambda: conv(torch, stream, peaks))]
+    items += [(f"sgemm_{n}", (lambda n=n: sgemm(torch, stream, peaks, sizes=(n,)))) for n in (1024, 2048, 4096, 8192, 16384)]
+    for name, fn in items:
+        time.sleep(1.0)
         try:
-            res.update(fn(torch, stream, peaks))
+            r = fn()
+            for v in r.values():
+                if isinstance(v, dict):
+                    v.update(_smi_clock())
+            res.update(r)
         except Exception as e:
             res[name] = {"error": repr(e)}
     return res
