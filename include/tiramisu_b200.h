@@ -125,7 +125,8 @@ int tiramisu_b200_conv_relu_maxpool(const float *input, const float *filter, con
 /* 0 auto, 1 exact fp32 SIMT, 2 force tcgen05.  Returns the previous mode. */
 int tiramisu_b200_set_conv_mode(int mode);
 /* Activation staging of the tcgen05 conv: 0 = auto, 1 = 8x16 tile, vertical taps share a TMA tile,
- * 2 = 16x8 tile, all nine taps share one TMA tile.  Returns the previous value. */
+ * 2 = 16x8 tile, all nine taps share one TMA tile, 3 = as 2 on CTA pairs (cta_group::2, M = 256, the
+ * filter split between the two CTAs).  Returns the previous value. */
 int tiramisu_b200_set_conv_kernel(int kernel);
 /* Multi-layer LSTM forward (LSTM/cpu/generator.cpp:35-53): Weights f32[L][2][4F][F] (0 = R, 1 = W),
  * biases f32[L][4F], x,y f32[T][B][F]; gate rows i,z,o,f. */

@@ -43,7 +43,7 @@ def test_conv_exact_mode_bit_exact(api, B, N, FIn, FOut):
         api.set_conv_mode(prev)
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("B,N,FIn", [(2, 32, 32), (1, 64, 64), (3, 96, 64), (1, 16, 32), (2, 224, 64)])
 def test_conv_tensor_path_small_ints_exact(api, kernel, B, N, FIn):
     """Integer-valued operands are exact in TF32 with fp32 accumulation => equality with the oracle

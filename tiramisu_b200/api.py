@@ -101,7 +101,8 @@ def set_conv_mode(mode: int) -> int:
 
 
 def set_conv_kernel(kernel: int) -> int:
-    """0 auto, 1 = 8x16 tile (ky taps share a TMA tile), 2 = 16x8 tile (all nine taps share one)."""
+    """0 auto, 1 = 8x16 tile (ky taps share a TMA tile), 2 = 16x8 tile (all nine taps share one),
+    3 = as 2 on CTA pairs (cta_group::2)."""
     return int(_lib.lib().tiramisu_b200_set_conv_kernel(kernel))
 
 

@@ -113,14 +113,25 @@ struct ConvParams {
     int dbg_base_offset;          // bring-up knob: 1 = set the descriptor base-offset field to (addr >> 7) & 7
 };
 
-template <int FOUT, bool ALLTAPS>
+// CG = 2: a CTA pair (cta_group::2) works on two pixel tiles at once as ONE M = 256 MMA; the
+// FOut = 64 filter columns are split between the two CTAs' shared memories (32 each), so every
+// MMA reads 4 KB of A + 1 KB of B per CTA instead of 4 + 2 (at N = 64 the shared-memory operand
+// reads, 6 KB per 32-cycle MMA, are what bounds the single-CTA kernel: 67 % of the tensor peak),
+// and the halved filter footprint (72 KB) leaves room for a 6-stage activation ring.
+template <int FOUT, bool ALLTAPS, int CG>
 __global__ void __launch_bounds__(kConvThreads, 1)
 tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                                const ConvParams p)
 {
-    constexpr int W_SLAB_BYTES = FOUT * BK * 4;
+    static_assert(CG == 1 || ALLTAPS, "the CTA-pair variant uses the all-taps tile");
+    constexpr int W_ROWS = FOUT / CG;                  // filter columns (B-operand rows) held by this CTA
+    constexpr int W_SLAB_BYTES = W_ROWS * BK * 4;
     using T_ = Tile<ALLTAPS>;
-    constexpr int A_STAGES = T_::STAGES, A_TILE_BYTES = T_::STAGE_BYTES, TILE_X = T_::X, TILE_Y = T_::Y;
+    constexpr int A_STAGES = (CG == 2) ? 6 : T_::STAGES;
+    constexpr int A_TILE_BYTES = T_::STAGE_BYTES, TILE_X = T_::X, TILE_Y = T_::Y;
+    const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int KH = p.FIn / BK;
@@ -144,17 +155,19 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
         if (lane == 0) {
             for (int s = 0; s < A_STAGES; s++) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
             ptx::mbar_init(w_bar, 1);
-            for (int b = 0; b < 2; b++) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 4); }
+            for (int b = 0; b < 2; b++) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 4 * CG); }
             ptx::fence_barrier_init();
         }
         __syncwarp();
-        ptx::tmem_alloc(tmem_slot, 2 * FOUT >= 32 ? 2 * FOUT : 32);
-        ptx::tmem_relinquish();
+        if (CG == 2) { ptx::tmem_alloc_cg2(tmem_slot, 2 * FOUT); ptx::tmem_relinquish_cg2(); }
+        else { ptx::tmem_alloc(tmem_slot, 2 * FOUT >= 32 ? 2 * FOUT : 32); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before_sync();
-    __syncthreads();
+    if (CG == 2) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    // tiles of this CTA: cluster c takes tile groups c, c + num_clusters, ...; CTA r of a pair the r-th tile of the group
+    const int first_tile = cluster_id * CG + (int)cta_rank, tile_step = num_clusters * CG;
 
     auto tile_coords = [&](int tile, int &n, int &y0, int &x0) {
         x0 = (tile % p.tiles_x) * TILE_X;
@@ -166,12 +179,16 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
     if (warp == 0) {
         // ===== TMA producer: whole warp, uniform control flow, one elected lane issues =====
         if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(num_slabs * W_SLAB_BYTES));
-            for (int s = 0; s < num_slabs; s++) ptx::tma_load_2d(smem_w + s * W_SLAB_BYTES, &map_w, w_bar, 0, s * FOUT);
+            // the pair's barriers live in the leader and expect both CTAs' bytes
+            if (leader) ptx::mbar_arrive_expect_tx(w_bar, (uint32_t)(CG * num_slabs * W_SLAB_BYTES));
+            for (int s = 0; s < num_slabs; s++) {
+                if (CG == 2) ptx::tma_load_2d_cg2(smem_w + s * W_SLAB_BYTES, &map_w, w_bar, 0, s * FOUT + (int)cta_rank * W_ROWS);
+                else ptx::tma_load_2d(smem_w + s * W_SLAB_BYTES, &map_w, w_bar, 0, s * FOUT);
+            }
         }
         __syncwarp();
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
             int n, y0, x0;
             tile_coords(tile, n, y0, x0);
             for (int kx = 0; kx < T_::LOADS_KX; kx++) {
@@ -180,23 +197,25 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
                     const uint32_t ph = (it / A_STAGES) & 1;
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     if (ptx::elect_one()) {
-                        ptx::mbar_arrive_expect_tx(&full_bar[s], T_::TILE_BYTES);
+                        if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], CG * T_::TILE_BYTES);
                         // rows y0 .. y0+TILE_Y+1, columns from x0+kx, channels [32h, 32h+32)
-                        ptx::tma_load_4d(smem_a + s * A_TILE_BYTES, &map_in, &full_bar[s], h * BK, x0 + kx, y0, n);
+                        if (CG == 2) ptx::tma_load_4d_cg2(smem_a + s * A_TILE_BYTES, &map_in, &full_bar[s], h * BK, x0 + kx, y0, n);
+                        else ptx::tma_load_4d(smem_a + s * A_TILE_BYTES, &map_in, &full_bar[s], h * BK, x0 + kx, y0, n);
                     }
                     __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: whole warp, uniform control flow, one elected lane issues =====
-        constexpr uint32_t idesc = ptx::make_idesc_tf32(128, FOUT, false, false);
+        // ===== MMA issuer (leader CTA of a pair): whole warp, uniform control flow, one elected lane issues =====
+        constexpr uint32_t idesc = ptx::make_idesc_tf32(128 * CG, FOUT, false, false);
         const uint32_t a_ring = ptx::smem_u32(smem_a);
         const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_w), 16, 1024);
+        if (leader) {
         ptx::mbar_wait(w_bar, 0);
         ptx::tc_fence_after_sync();
         uint32_t it = 0, local = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, local++) {
             const uint32_t buf = local & 1;
             ptx::mbar_wait(&tmem_empty[buf], ((local >> 1) & 1) ^ 1);   // epilogue drained this buffer
             ptx::tc_fence_after_sync();
@@ -222,17 +241,26 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
                             const uint64_t da = ptx::make_smem_desc(a_addr, 16, T_::SBO, ptx::kLayoutSw128, bo);
                             const uint64_t db = ptx::desc_advance(db0, (uint32_t)(((ky * 3 + kx) * KH + h) * W_SLAB_BYTES));
 #pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; k++)
-                                ptx::mma_tf32_ss(d_tmem, ptx::desc_advance(da, k * (UMMA_K * 4)),
-                                                 ptx::desc_advance(db, k * (UMMA_K * 4)), idesc,
-                                                 !(first_unit && t == 0 && k == 0));
+                            for (int k = 0; k < BK / UMMA_K; k++) {
+                                if (CG == 2)
+                                    ptx::mma_tf32_ss_cg2(d_tmem, ptx::desc_advance(da, k * (UMMA_K * 4)),
+                                                         ptx::desc_advance(db, k * (UMMA_K * 4)), idesc,
+                                                         !(first_unit && t == 0 && k == 0));
+                                else
+                                    ptx::mma_tf32_ss(d_tmem, ptx::desc_advance(da, k * (UMMA_K * 4)),
+                                                     ptx::desc_advance(db, k * (UMMA_K * 4)), idesc,
+                                                     !(first_unit && t == 0 && k == 0));
+                            }
                         }
-                        ptx::mma_commit(&empty_bar[s]);
-                        if (lx == T_::LOADS_KX - 1 && h == KH - 1) ptx::mma_commit(&tmem_full[buf]);
+                        if (CG == 2) ptx::mma_commit_cg2(&empty_bar[s], 3); else ptx::mma_commit(&empty_bar[s]);
+                        if (lx == T_::LOADS_KX - 1 && h == KH - 1) {
+                            if (CG == 2) ptx::mma_commit_cg2(&tmem_full[buf], 3); else ptx::mma_commit(&tmem_full[buf]);
+                        }
                     }
                     __syncwarp();
                 }
             }
+        }
         }
     } else {
         // ===== epilogue: TMEM -> max-pool -> +bias -> ReLU -> global =====
@@ -242,7 +270,7 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
         constexpr int YSH = ALLTAPS ? 3 : 4;               // log2(TILE_X)
         const int sel1 = lane & 1, sel16 = (lane >> YSH) & 1;
         uint32_t local = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, local++) {
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_step, local++) {
             const uint32_t buf = local & 1;
             int n, y0, x0;
             tile_coords(tile, n, y0, x0);
@@ -262,7 +290,9 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
             // accumulator buffer can be overwritten by the MMAs of the tile after next
             ptx::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+            if (lane == 0) {
+                if (CG == 2) ptx::mbar_arrive_remote(&tmem_empty[buf], 0); else ptx::mbar_arrive(&tmem_empty[buf]);
+            }
 
             // 2x2 max-pool across lanes l^1 (x pair) and l^TILE_X (y pair), reduce-scatter style: after the
             // two exchanges each lane owns 16 of this chunk pair's columns.
@@ -299,10 +329,10 @@ tiramisu_sm100_conv_block_tf32(const __grid_constant__ CUtensorMap map_in, const
     }
 
     ptx::tc_fence_before_sync();
-    __syncthreads();
+    if (CG == 2) ptx::cluster_sync(); else __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem_base, 2 * FOUT >= 32 ? 2 * FOUT : 32);
+        if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, 2 * FOUT); else ptx::tmem_dealloc(tmem_base, 2 * FOUT >= 32 ? 2 * FOUT : 32);
     }
 }
 
@@ -310,9 +340,9 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 std::atomic<int> g_conv_mode{0};          // 0 auto, 1 exact, 2 tensor
 
-std::atomic<int> g_conv_kernel{0};        // 0 auto (= 2), 1 ky-reuse tile (8x16), 2 all-taps tile (16x8)
+std::atomic<int> g_conv_kernel{0};        // 0 auto, 1 ky-reuse tile (8x16), 2 all-taps tile (16x8), 3 all-taps tile, CTA pairs
 
-template <int FOUT, bool ALLTAPS>
+template <int FOUT, bool ALLTAPS, int CG>
 int launch_conv_tc(const float *in, const float *filter, const float *bias, float *out, int B, int N, int FIn)
 {
     using T_ = Tile<ALLTAPS>;
@@ -333,7 +363,7 @@ int launch_conv_tc(const float *in, const float *filter, const float *bias, floa
     {
         uint64_t dims[2] = {BK, (uint64_t)num_slabs * FOUT};
         uint64_t str[1] = {BK * 4};
-        uint32_t box[2] = {BK, FOUT};
+        uint32_t box[2] = {BK, FOUT / CG};
         if (make_tensor_map_f32(&map_w, wp, 2, dims, str, box)) return 1;
     }
     ConvParams p;
@@ -343,16 +373,28 @@ int launch_conv_tc(const float *in, const float *filter, const float *bias, floa
     p.bias = bias; p.out = out;
     p.dbg_base_offset = 0;
     if (const char *e = getenv("TB200_CONV_BASE_OFFSET")) p.dbg_base_offset = atoi(e);
-    const int smem = num_slabs * FOUT * BK * 4 + T_::STAGES * T_::STAGE_BYTES + 1024 + 256;
-    auto kern = tiramisu_sm100_conv_block_tf32<FOUT, ALLTAPS>;
+    const int stages = (CG == 2) ? 6 : T_::STAGES;
+    const int smem = num_slabs * (FOUT / CG) * BK * 4 + stages * T_::STAGE_BYTES + 1024 + 256;
+    auto kern = tiramisu_sm100_conv_block_tf32<FOUT, ALLTAPS, CG>;
     static bool attr_set = false;
     if (!attr_set) {
         TB200_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    kern<<<grid, kConvThreads, smem, stream()>>>(map_in, map_w, p);
-    int rc = post_launch("tiramisu_sm100_conv_block_tf32");
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    grid = grid / CG * CG;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int rc = check(cudaLaunchKernelEx(&cfg, kern, map_in, map_w, p), "tiramisu_sm100_conv_block_tf32");
+    if (!rc) rc = post_launch("tiramisu_sm100_conv_block_tf32");
     pool_free(wp);
     return rc;
 }
@@ -367,7 +409,7 @@ TB200_API int tiramisu_b200_set_conv_mode(int mode)
 
 TB200_API int tiramisu_b200_set_conv_kernel(int kernel)
 {
-    if (kernel < 0 || kernel > 2) kernel = 0;
+    if (kernel < 0 || kernel > 3) kernel = 0;
     return g_conv_kernel.exchange(kernel);
 }
 
@@ -384,8 +426,9 @@ TB200_API int tiramisu_b200_conv_relu_maxpool(const float *input, const float *f
     if (mode != 1 && tc_ok) {
         int kernel = g_conv_kernel.load();
         if (const char *e = getenv("TB200_CONV_KERNEL")) kernel = atoi(e);
-        if (kernel == 1) return launch_conv_tc<64, false>(input, filter, bias, output, B, N, FIn);
-        return launch_conv_tc<64, true>(input, filter, bias, output, B, N, FIn);
+        if (kernel == 1) return launch_conv_tc<64, false, 1>(input, filter, bias, output, B, N, FIn);
+        if (kernel == 2) return launch_conv_tc<64, true, 1>(input, filter, bias, output, B, N, FIn);
+        return launch_conv_tc<64, true, 2>(input, filter, bias, output, B, N, FIn);      // tile count is even (N % 16 == 0)
     }
     const size_t total = (size_t)B * (FOut / 8) * (N / 2) * (N / 2) * 8;
     const size_t want = (total + 255) / 256, cap = (size_t)sm_count() * 16;
