@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 
 #include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -25,7 +26,21 @@ namespace {
 
 int bad(const char *fn, const char *what) {
     set_last_error(std::string(fn) + ": " + what);
+    // The reference's wrappers ignore the return code, so say it out loud as well.
+    fprintf(stderr, "tiramisu_b200: %s: %s\n", fn, what);
     return 2;                                       // validation errors never exit
+}
+
+// Does a 2-D buffer hold rows x cols elements?  The reference never looks at extents (image checks
+// are disabled, src/tiramisu_codegen_halide_lowering.cpp:157-159) and some of its wrappers declare
+// them transposed (sgemm_wrapper.cpp:157-160 builds A as Buffer(N, K) for the row-major A[N][K]),
+// so only the element count is enforced.
+bool holds(const BufView &v, int64_t rows, int64_t cols)
+{
+    if (v.ndim < 2) return true;                    // no metadata: trust the caller, like the reference
+    int64_t n = 1;
+    for (int i = 0; i < v.ndim; i++) n *= v.extent[i];
+    return n == rows * cols;
 }
 
 // Small parameter buffers (SIZES, alpha, Consts ...) are read on the host.
@@ -304,9 +319,9 @@ TB200_API int sgemm_tiramisu(halide_buffer_t *SIZES, halide_buffer_t *alpha, hal
     // sgemm_generator.cpp:296-304: SIZES = {N, M, K}; A[N][K], B[K][M], C[N][M]
     const int64_t N = s[0], M = s[1], K = s[2];
     if (N < 0 || M < 0 || K < 0) return bad(__func__, "negative size");
-    if (va.ndim >= 2 && (va.extent[0] != K || va.extent[1] != N)) return bad(__func__, "A extents != {K, N}");
-    if (vb.ndim >= 2 && (vb.extent[0] != M || vb.extent[1] != K)) return bad(__func__, "B extents != {M, K}");
-    if (vc.ndim >= 2 && (vc.extent[0] != M || vc.extent[1] != N)) return bad(__func__, "C extents != {M, N}");
+    if (!holds(va, N, K)) return bad(__func__, "A does not hold N x K elements");
+    if (!holds(vb, K, M)) return bad(__func__, "B does not hold K x M elements");
+    if (!holds(vc, N, M)) return bad(__func__, "C does not hold N x M elements");
     if (N == 0 || M == 0) return 0;
     return gemm_buffers(__func__, va, vb, vc, N, M, K, a, b, K, M, M, 0, 0, 0, false, false, (size_t)N * K,
                         (size_t)K * M, (size_t)N * M, nullptr, nullptr);
