@@ -149,6 +149,8 @@ int tiramisu_b200_comm_destroy(void);
 int tiramisu_b200_comm_rank(void);
 int tiramisu_b200_comm_size(void);
 int tiramisu_b200_comm_broadcast(void *dev_buf, uint64_t bytes, int32_t root);
+/* Same result for large buffers, as scatter from the root + in-place all-gather (bandwidth-optimal). */
+int tiramisu_b200_comm_broadcast_large(void *dev_buf, uint64_t bytes, int32_t root);
 /* n send/recv pairs as ONE NCCL group; a peer < 0 skips that entry. */
 int tiramisu_b200_comm_exchange(int32_t n, const int32_t *send_peer, void *const *send_buf,
                                 const uint64_t *send_bytes, const int32_t *recv_peer,

@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_comm_rank", C.c_int)
     sig("tiramisu_b200_comm_size", C.c_int)
     sig("tiramisu_b200_comm_broadcast", C.c_int, vp, u64, i32)
+    sig("tiramisu_b200_comm_broadcast_large", C.c_int, vp, u64, i32)
     sig("tiramisu_b200_comm_exchange", C.c_int, i32, C.POINTER(i32), C.POINTER(vp), C.POINTER(u64),
         C.POINTER(i32), C.POINTER(vp), C.POINTER(u64))
     sig("tiramisu_MPI_init", C.c_int)

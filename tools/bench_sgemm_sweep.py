@@ -30,6 +30,9 @@ def main():
     main_s, comm_s = torch.cuda.Stream(), torch.cuda.Stream()
     api.set_stream(main_s.cuda_stream)
     panels = int(os.environ.get("TB200_SWEEP_PANELS", "4"))
+    # ncclBroadcast by default; TB200_SWEEP_BCAST=sag selects the scatter + all-gather form (measured
+    # slower on 8 B200s: 3.85 vs 3.07 ms for the 1 GiB B of 16384^3, profiles/r01_sgemm_sweep_8gpu.jsonl)
+    bcast = L.tiramisu_b200_comm_broadcast_large if os.environ.get("TB200_SWEEP_BCAST") == "sag" else L.tiramisu_b200_comm_broadcast
 
     for n in sizes:
         r0, r1 = tdist.row_shard(n, world, rank)
@@ -50,7 +53,7 @@ def main():
                 comm_s.wait_event(ev_free)
                 api.set_stream(comm_s.cuda_stream)
                 for p in range(panels):
-                    _lib.check(L.tiramisu_b200_comm_broadcast(B.data_ptr() + p * kw * n * 4, kw * n * 4, 0))
+                    _lib.check(bcast(B.data_ptr() + p * kw * n * 4, kw * n * 4, 0))
                     evs[p].record(comm_s)
                 api.set_stream(main_s.cuda_stream)
             for p in range(panels):
@@ -88,6 +91,7 @@ def main():
         if rank == 0:
             fl = 2.0 * n ** 3
             print(json.dumps({"metric": "sgemm_TFLOPs", "n": n, "n_gpus": world, "panels": panels,
+                              "bcast": os.environ.get("TB200_SWEEP_BCAST", "nccl"),
                               "ms_step_bcast_pipelined": ms_pipe, "TFLOPs": fl / (ms_pipe * 1e-3) / 1e12,
                               "ms_gemm_only": ms_gemm, "TFLOPs_gemm_only": fl / (ms_gemm * 1e-3) / 1e12,
                               "bcast_bytes_per_rank": n * n * 4 if world > 1 else 0}), flush=True)

@@ -1,0 +1,112 @@
+"""Multi-GPU parity of the sharded paths against the single-process oracle.  One process per GPU:
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/dist_check.py
+
+Checks (bit-exact unless noted): distributed boxblur through the generated-function ABI with the
+halo rows received over the library's NCCL communicator (tests/test_160.cpp semantics); row-sharded
+heat2d with a grouped halo exchange; the scatter+all-gather broadcast; row-sharded sgemm with B
+broadcast from rank 0 (integer operands, exact on the TF32 path)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import oracle  # noqa: E402  (checker only)
+from tiramisu_b200 import _lib, api, dist as tdist  # noqa: E402
+
+
+def main():
+    os.environ["NCCL_DEBUG"] = os.environ.get("TB200_NCCL_DEBUG", "WARN")
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tdist.comm_init_from_torch()
+    L = _lib.lib()
+    stream = torch.cuda.Stream()
+    api.set_stream(stream.cuda_stream)
+    ok = True
+
+    # ---- 1. distributed box blur (uint32), halo rows come from rank+1 inside the call -------------------
+    rows_per, cols = 37, 1000
+    full = (np.arange((rows_per * world + 2) * (cols + 2), dtype=np.uint32).reshape(rows_per * world + 2, cols + 2) * 7) % 1013
+    want = oracle.boxblur_u32(full)[: rows_per * world]
+    loc = np.zeros((rows_per + 2, cols + 2), np.uint32)
+    loc[:rows_per] = full[rank * rows_per:(rank + 1) * rows_per]
+    if rank == world - 1:
+        loc[rows_per:] = full[world * rows_per:]            # the global bottom rows belong to the last rank
+    out = np.zeros((rows_per, cols), np.uint32)
+    d_in, d_out = torch.from_numpy(loc.view(np.int32)).cuda(), torch.from_numpy(out.view(np.int32)).cuda()
+    b_in, b_out = api.Buffer(d_in), api.Buffer(d_out)
+    b_in.raw.type.code = b_out.raw.type.code = 1
+    _lib.check(L.boxblur(b_in.ptr(), b_out.ptr()), "boxblur")
+    got = d_out.cpu().numpy().view(np.uint32)
+    good = np.array_equal(got, want[rank * rows_per:(rank + 1) * rows_per])
+    ok &= good
+    print(f"[rank {rank}] boxblur distributed: {'ok' if good else 'MISMATCH'}", flush=True)
+
+    # ---- 2. row-sharded heat2d with a grouped halo exchange ------------------------------------------------
+    H, W = 64 * world + 5, 1024
+    grid = np.random.default_rng(1).random((H, W), dtype=np.float32)
+    wantg = oracle.heat2d(grid, "cpu")
+    r0, r1 = tdist.row_shard(H, world, rank)
+    top, bot = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
+    rows = r1 - r0
+    d_loc = torch.zeros((top + rows + bot, W), device="cuda")
+    d_loc[top:top + rows] = torch.from_numpy(grid[r0:r1]).cuda()
+    d_o = torch.full((rows, W), float("nan"), device="cuda")
+    row_b = W * 4
+    own = d_loc.data_ptr() + top * row_b
+    sp = (C.c_int32 * 2)(rank - 1 if top else -1, rank + 1 if bot else -1)
+    sb = (C.c_void_p * 2)(own, own + (rows - 1) * row_b)
+    sn = (C.c_uint64 * 2)(row_b, row_b)
+    rp = (C.c_int32 * 2)(rank - 1 if top else -1, rank + 1 if bot else -1)
+    rb = (C.c_void_p * 2)(d_loc.data_ptr(), own + rows * row_b)
+    rn = (C.c_uint64 * 2)(row_b, row_b)
+    _lib.check(L.tiramisu_b200_comm_exchange(2, sp, sb, sn, rp, rb, rn))
+    _lib.check(L.tiramisu_b200_heat2d(d_loc.data_ptr() - (r0 - top) * row_b, d_o.data_ptr() - r0 * row_b, H, W, 0, r0, r1))
+    api.synchronize()
+    good = np.array_equal(d_o.cpu().numpy(), wantg[r0:r1])
+    ok &= good
+    print(f"[rank {rank}] heat2d row-sharded: {'ok' if good else 'MISMATCH'}", flush=True)
+
+    # ---- 3. scatter + all-gather broadcast ------------------------------------------------------------------
+    nbytes = 64 * 1024 * 1024 + 12345 * 4
+    src = torch.arange(nbytes // 4, dtype=torch.int32, device="cuda") * 3 + 1
+    buf = src.clone() if rank == 0 else torch.zeros_like(src)
+    _lib.check(L.tiramisu_b200_comm_broadcast_large(buf.data_ptr(), nbytes, 0))
+    api.synchronize()
+    good = bool(torch.equal(buf, src))
+    ok &= good
+    print(f"[rank {rank}] broadcast_large: {'ok' if good else 'MISMATCH'}", flush=True)
+
+    # ---- 4. row-sharded sgemm, B broadcast from rank 0 -----------------------------------------------------
+    n = 1024
+    rng = np.random.default_rng(7)
+    A = rng.integers(-4, 5, (n, n)).astype(np.float32)
+    B = rng.integers(-4, 5, (n, n)).astype(np.float32)
+    Cm = rng.integers(-4, 5, (n, n)).astype(np.float32)
+    wantc = 3.0 * (A.astype(np.float64) @ B.astype(np.float64)) + 2.0 * Cm
+    a0, a1 = tdist.row_shard(n, world, rank)
+    dA, dC = torch.from_numpy(A[a0:a1]).cuda(), torch.from_numpy(Cm[a0:a1]).cuda()
+    dB = torch.from_numpy(B).cuda() if rank == 0 else torch.zeros((n, n), device="cuda")
+    _lib.check(L.tiramisu_b200_comm_broadcast(dB.data_ptr(), n * n * 4, 0))
+    api.cublas_sgemm(dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), a1 - a0, n, n, 3.0, 2.0)
+    api.synchronize()
+    good = np.array_equal(dC.cpu().numpy().astype(np.float64), wantc[a0:a1])
+    ok &= good
+    print(f"[rank {rank}] sgemm row-sharded: {'ok' if good else 'MISMATCH'}", flush=True)
+
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+    tdist.comm_destroy()
+    torch.distributed.destroy_process_group()
+    if rank == 0:
+        print("DIST_CHECK_OK" if int(flag.item()) == 1 else "DIST_CHECK_FAILED", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
