@@ -137,17 +137,19 @@ def test_lstm_tensor_path(api, F, B, L, T, scale):
         api.set_lstm_mode(prev)
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 @pytest.mark.parametrize("F,B,L,T,scale", [(64, 16, 2, 6, 4.0), (256, 100, 2, 5, 8.0), (128, 64, 3, 20, 8.0),
                                            (1024, 64, 2, 6, 32.0), (256, 48, 2, 7, 8.0), (512, 64, 2, 5, 16.0),
-                                           (384, 5, 1, 4, 8.0)])
+                                           (384, 5, 1, 4, 8.0), (1024, 64, 4, 23, 32.0), (128, 64, 5, 37, 8.0)])
 def test_lstm_recurrence_engines(api, kernel, F, B, L, T, scale):
     """Per-cell launches (1), the N-split persistent layer kernel (2: weights resident in shared
-    memory, cell state in registers, device-wide step barrier, multicast ring) and the K-split
-    persistent layer kernel (3: cluster of 4, DSMEM reduction) against the oracle; T is long enough
-    for rings, barrier phases and the step counter to wrap several times."""
-    if kernel == 3 and (F % 128 or B > 64):
-        pytest.skip("K-split engine needs F % 128 == 0 and B <= 64")
+    memory, cell state in registers, device-wide step barrier, multicast ring), the TF32 K-split
+    persistent layer kernel (3: cluster of 4, DSMEM reduction) and the fp16 K-split kernel with
+    layer pairs overlapped (4: cluster of 2, chunk GEMMs of the upper layer's input contribution
+    following the lower layer's step counter) against the oracle; T is long enough for rings,
+    barrier phases, chunk boundaries and the step counter to wrap several times."""
+    if kernel in (3, 4) and (F % 128 or B > 64):
+        pytest.skip("K-split engines need F % 128 == 0 and B <= 64")
     prev_m, prev_k = api.set_lstm_mode(2), api.set_lstm_kernel(kernel)
     try:
         W, b, x = refdata.lstm_inputs(F, B, L, T, scale=scale)
@@ -164,7 +166,7 @@ def test_lstm_engines_agree_full_width(api):
     """F=1024, B=64 (BASELINE config 4 shape, shorter sequence): both engines, same inputs."""
     W, b, x = refdata.lstm_inputs(1024, 64, 2, 12, scale=32.0)
     outs = []
-    for kernel in (1, 2, 3):
+    for kernel in (1, 2, 3, 4):
         prev_m, prev_k = api.set_lstm_mode(2), api.set_lstm_kernel(kernel)
         try:
             outs.append(_lstm(api, W, b, x))
@@ -173,6 +175,35 @@ def test_lstm_engines_agree_full_width(api):
             api.set_lstm_kernel(prev_k)
     assert float(np.abs(outs[0] - outs[1]).max()) < 5e-3
     assert float(np.abs(outs[0] - outs[2]).max()) < 5e-3
+    assert float(np.abs(outs[0] - outs[3]).max()) < 5e-3
+
+
+_CFG4 = {}
+
+
+@pytest.mark.parametrize("pipe", ["0", "1"])
+def test_lstm_fp16_engine_config4(api, pipe, monkeypatch):
+    """BASELINE config 4 (F=1024, B=64, L=4, T=100) through the fp16 engine, one layer at a time and
+    with layer pairs overlapped: both must match the oracle and each other bit for bit (the
+    overlap changes the schedule, not the arithmetic)."""
+    monkeypatch.setenv("TB200_LSTM_PIPE", pipe)
+    W, b, x = refdata.lstm_inputs(1024, 64, 4, 100, scale=32.0)
+    prev_m, prev_k = api.set_lstm_mode(2), api.set_lstm_kernel(4)
+    try:
+        got = _lstm(api, W, b, x)
+        again = _lstm(api, W, b, x)
+    finally:
+        api.set_lstm_mode(prev_m)
+        api.set_lstm_kernel(prev_k)
+    assert np.array_equal(got, again)
+    if "want" not in _CFG4:
+        _CFG4["want"] = oracle.lstm(W, b, x)
+    want = _CFG4["want"]
+    assert np.isfinite(got).all()
+    assert float(np.abs(got - want).max()) < TF32_RTOL * max(1.0, float(np.abs(want).max()))
+    if "got" in _CFG4:
+        assert np.array_equal(_CFG4["got"], got)
+    _CFG4["got"] = got
 
 
 def test_lstm_wrapper_data_saturated(api):

@@ -32,6 +32,17 @@ int check(cudaError_t e, const char *where);                  // 0 on success
 // src/tiramisu_codegen_cuda.cpp:1745).  tiramisu_b200_set_stream() overrides it for the calling
 // thread, e.g. with torch's current stream.
 cudaStream_t stream();
+// Redirects stream() of the calling thread for a scope (fork/join onto auxiliary streams).
+class ScopedStream {
+public:
+    explicit ScopedStream(cudaStream_t s);
+    ~ScopedStream();
+    ScopedStream(const ScopedStream &) = delete;
+    ScopedStream &operator=(const ScopedStream &) = delete;
+private:
+    cudaStream_t prev_;
+    bool prev_set_;
+};
 
 // ---- launch accounting ----------------------------------------------------------------------
 extern std::atomic<uint64_t> g_kernel_launches;

@@ -64,6 +64,27 @@ int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint
     return 0;
 }
 
+int make_tensor_map_f16(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
+                        const uint64_t *strides_bytes, const uint32_t *box)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail("make_tensor_map_f16", "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("make_tensor_map_f16", "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+
+// Per-thread overrides used by callers that place GEMMs next to other resident kernels (the LSTM
+// layer pipeline runs its chunk GEMMs on the SMs the recurrence kernels leave free).
+static thread_local int t_hint_kernel = 0, t_hint_bn = 0;
+void gemm_tc_hint(int kernel, int bn) { t_hint_kernel = kernel; t_hint_bn = bn; }
+
 }  // namespace tb200
 
 namespace {
@@ -668,6 +689,7 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
     // pair, the persistent single-CTA kernel for mid sizes, the one-tile-per-CTA kernel below that.
     int kernel = g_gemm_kernel.load();
     if (const char *e = getenv("TB200_GEMM_KERNEL")) kernel = atoi(e);
+    if (t_hint_kernel) kernel = t_hint_kernel;
     const uint64_t sms = (uint64_t)sm_count();
     if (kernel == 0) {
         // measured (profiles/r01_results.md): the pair kernel wins from ~2048^2 outputs upwards even
@@ -691,6 +713,7 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
         int v = atoi(e);
         if (v == 64 || v == 128 || v == 256) bn = v;
     }
+    if (t_hint_bn == 64 || t_hint_bn == 128 || t_hint_bn == 256) bn = t_hint_bn;
     if (tB) {
         switch (bn) {
         case 256: return launch_tc<256, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);

@@ -18,6 +18,8 @@
 #include "sm100_ptx.cuh"
 #include "tiramisu_b200.h"
 
+#include <cuda_fp16.h>
+
 #include <cstdio>
 #include <vector>
 
@@ -26,6 +28,7 @@ using namespace tb200;
 namespace tb200 {
 int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha,
                 float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tB);
+void gemm_tc_hint(int kernel, int bn);
 }
 
 namespace {
@@ -665,6 +668,301 @@ tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp16 K-split layer kernel + layer-pair pipeline — the default engine (F % 128 == 0, F <= 1024, B <= 64).
+// The TF32 K-split kernel above needs every SM for ONE layer's recurrent weights (16 MB at
+// F = 1024), so the L x T cells run strictly one after another (400 dependent steps of ~6.3 us).
+// Here R and h are fed to the tensor core as fp16 (kind::f16: 11-bit significands, the same
+// operand precision as TF32, fp32 accumulate): a layer's R is 8 MB and fits in the shared memory
+// of F/16 = 64 CTAs, so TWO layers' recurrences are resident at once and layer l+1 runs a few
+// steps behind layer l:
+//   * cluster j (2 CTAs) owns the 128 packed gate rows [128j, +128); CTA ks keeps
+//     R16[128 rows][K slice ks = F/2] resident (128 KB) as the A operand; per step the B operand is
+//     h16[t-1][:, K slice] (64 x F/2 fp16 = 64 KB, all in flight at once), 32 MMAs (N = 64, K = 16);
+//   * the two partials meet through distributed shared memory: TMEM lane half hs goes to CTA hs
+//     (st.async + complete_tx), CTA ks finalises gate rows [64 ks, +64) = 16 hidden units x 64 batch
+//     entries with 8 epilogue warps, writes h[t] as fp32 (next layer's GEMM, y) and fp16 (own TMA);
+//   * steps are separated by the layer's own device-wide counter; the same counter tells the host-side
+//     pipeline (a polling kernel on another stream) how far the layer is, and `xg_ready` tells this
+//     kernel how many steps of its input contribution Xg the chunk GEMMs have produced so far.
+constexpr int H_CL = 2;
+constexpr int H_THREADS = 64 + 256;
+constexpr int H_RECV_BYTES = 2 * 64 * 64 * 4;      // [src CTA][gate row][batch], 32 KB
+
+struct H16Params {
+    int B, F, T;
+    const float *xg;            // [T*B][4F] packed gate columns (may still be in production, see xg_ready)
+    const float *bias;          // [4F] packed
+    float *h;                   // [T][B][F] fp32 output of this layer
+    __half *h16;                // [T][B][F] fp16 copy, the recurrence's own operand
+    uint32_t *counter;          // += gridDim.x per finished step
+    const uint32_t *xg_ready;   // null, or: number of leading time steps of xg that are complete
+    int dbg;
+    unsigned long long *trace;
+};
+
+__global__ void __launch_bounds__(H_THREADS, 1)
+tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_r,
+                              const H16Params p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int KB = p.F / (H_CL * 64);                        // 64-element (128-byte) k-blocks per K slice (<= 8)
+    const int half = (KB + 1) / 2;
+    uint8_t *smem_r = smem;                                  // KB x [128 rows][64 k] fp16 (16 KB each)
+    uint8_t *smem_h = smem_r + (size_t)KB * 16384;           // KB x [64 rows][64 k] fp16  (8 KB each)
+    float *recv = reinterpret_cast<float *>(smem_h + (size_t)KB * 8192);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(recv) + H_RECV_BYTES);   // [2]
+    uint64_t *r_bar = full_bar + 2;
+    uint64_t *tmem_full = r_bar + 1;
+    uint64_t *recv_bar = tmem_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(recv_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ks = ptx::cluster_ctarank();              // K slice of this CTA = its rank in the cluster
+    const int j = blockIdx.x / H_CL;                         // gate-row group of the cluster
+    const int k_base = (int)ks * (p.F / H_CL);
+
+    if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&map_h); ptx::prefetch_tensormap(&map_r); }
+    if (warp == 1) {
+        if (lane == 0) {
+            ptx::mbar_init(&full_bar[0], 1);
+            ptx::mbar_init(&full_bar[1], 1);
+            ptx::mbar_init(r_bar, 1);
+            ptx::mbar_init(tmem_full, 1);
+            ptx::mbar_init(recv_bar, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 64);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    ptx::cluster_sync();                                     // the peer's barriers exist before any remote store
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(r_bar, (uint32_t)KB * 16384u);
+            for (int kb = 0; kb < KB; kb++)
+                ptx::tma_load_2d(smem_r + kb * 16384, &map_r, r_bar, k_base + kb * 64, 128 * j);
+        }
+        __syncwarp();
+        for (int t = 1; t < p.T; t++) {
+            if (!(p.dbg & 1)) grid_wait_relaxed(p.counter, (uint32_t)gridDim.x * (uint32_t)t);   // h16[t-1] is complete
+            ptx::fence_proxy_async_all();
+            if (ptx::elect_one()) {
+                KS_TRACE(0);
+                ptx::mbar_arrive_expect_tx(&full_bar[0], (uint32_t)half * 8192u);
+                for (int kb = 0; kb < half; kb++)
+                    ptx::tma_load_3d(smem_h + kb * 8192, &map_h, &full_bar[0], k_base + kb * 64, 0, t - 1);
+                if (KB > half) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[1], (uint32_t)(KB - half) * 8192u);
+                    for (int kb = half; kb < KB; kb++)
+                        ptx::tma_load_3d(smem_h + kb * 8192, &map_h, &full_bar[1], k_base + kb * 64, 0, t - 1);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = ptx::make_idesc_f16(128, 64, false, false);
+        const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_r), 16, 1024);
+        const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_h), 16, 1024);
+        ptx::mbar_wait(r_bar, 0);
+        ptx::tc_fence_after_sync();
+        for (int t = 1; t < p.T; t++) {
+            const uint32_t ph = (uint32_t)(t - 1) & 1u;
+            ptx::mbar_wait(&full_bar[0], ph);
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+                KS_TRACE(1);
+                for (int kb = 0; kb < half; kb++) {
+                    const uint64_t da = ptx::desc_advance(da0, (uint32_t)kb * 16384u), db = ptx::desc_advance(db0, (uint32_t)kb * 8192u);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)                  // 4 x (K = 16 fp16 = 32 bytes) per 128-byte row
+                        ptx::mma_f16_ss(tmem_base, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc,
+                                        (kb | k) != 0);
+                }
+                if (KB == half) ptx::mma_commit(tmem_full);
+            }
+            __syncwarp();
+            if (KB > half) {
+                ptx::mbar_wait(&full_bar[1], ph);
+                ptx::tc_fence_after_sync();
+                if (ptx::elect_one()) {
+                    KS_TRACE(2);
+                    for (int kb = half; kb < KB; kb++) {
+                        const uint64_t da = ptx::desc_advance(da0, (uint32_t)kb * 16384u), db = ptx::desc_advance(db0, (uint32_t)kb * 8192u);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            ptx::mma_f16_ss(tmem_base, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc, true);
+                    }
+                    ptx::mma_commit(tmem_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue: 8 warps =====
+        const uint32_t q = (uint32_t)warp & 3u;            // TMEM lane quarter this warp may read
+        const uint32_t ch = (uint32_t)(warp - 2) >> 2;     // which 32 of the 64 batch columns it reads
+        const uint32_t dst_cta = q >> 1;                   // gate rows [64 dst, +64) are finalised by CTA dst
+        const int e = (warp - 2) * 32 + lane;              // 0..255
+        const int b = e & 63;                              // batch entry this thread finalises
+        const int ug = e >> 6;                             // which 4 of the CTA's 16 hidden units
+        const bool ok = b < p.B;
+        const int p0 = 128 * j + 64 * (int)ks + 16 * ug;           // first packed gate column of this thread
+        const int u0 = 32 * j + 16 * (int)ks + 4 * ug;             // first hidden unit of this thread
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 bs[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) bs[u] = __ldg(reinterpret_cast<const float4 *>(p.bias + p0) + u);
+        // where this warp's TMEM rows go: CTA dst, slot [src = ks][row = 32 (q & 1) + lane][batch 32 ch ..]
+        const uint32_t row_l = 32u * (q & 1u) + (uint32_t)lane;
+        const uint32_t push_addr = ptx::mapa_u32(reinterpret_cast<uint8_t *>(recv) + ks * 16384u + row_l * 256u, dst_cta);
+        const uint32_t push_bar = ptx::mapa_u32(recv_bar, dst_cta);
+        uint32_t ready = p.xg_ready ? 0u : 0xffffffffu;
+        for (int t = 0; t < p.T; t++) {
+            if ((uint32_t)t >= ready) {
+                // the chunk GEMM that produces Xg[t] (layer below still running) has not been seen yet
+                uint32_t v = 0;
+                if (lane == 0) {
+                    const long long t0 = clock64();
+                    while ((v = ptx::ld_acquire_gpu(p.xg_ready)) <= (uint32_t)t) {
+                        if (clock64() - t0 > (1ll << 32)) __trap();
+                        __nanosleep(200);
+                    }
+                }
+                ready = __shfl_sync(0xffffffffu, v, 0);
+            }
+            float4 xg[4];
+            if (ok) {
+                const float4 *xp = reinterpret_cast<const float4 *>(p.xg + ((size_t)t * p.B + b) * 4 * p.F + p0);
+#pragma unroll
+                for (int u = 0; u < 4; u++) xg[u] = __ldcg(xp + u);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) xg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float acc[16];
+#pragma unroll
+            for (int a = 0; a < 16; a++) acc[a] = 0.0f;
+            if (t > 0) {
+                // arm this step's receive phase: 2 source CTAs x 64 rows x 256 B arrive as st.async transactions
+                if (e == 0) ptx::mbar_arrive_expect_tx(recv_bar, (uint32_t)H_RECV_BYTES);
+                ptx::mbar_wait(tmem_full, (uint32_t)(t - 1) & 1u);
+                ptx::tc_fence_after_sync();
+                if (e == 0) KS_TRACE(3);
+                uint32_t v[32];
+                __syncwarp();
+                ptx::tmem_ld_32x32_nowait(tmem_base + ((q * 32u) << 16) + 32u * ch, v);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before_sync();
+                // push batch columns [32 ch, +32) of gate row (32q + lane): 16-byte chunks XOR-swizzled by row
+#pragma unroll
+                for (int cc = 0; cc < 8; cc++)
+                    ptx::st_async_cluster_v4(push_addr + (uint32_t)(((8 * (int)ch + cc) ^ (lane & 7)) * 16), push_bar,
+                                             __uint_as_float(v[4 * cc + 0]), __uint_as_float(v[4 * cc + 1]),
+                                             __uint_as_float(v[4 * cc + 2]), __uint_as_float(v[4 * cc + 3]));
+                if (e == 0) KS_TRACE(4);
+                // both partials of my rows have landed
+                ptx::mbar_wait(recv_bar, (uint32_t)(t - 1) & 1u);
+                if (e == 0) KS_TRACE(5);
+#pragma unroll
+                for (int a = 0; a < 16; a++) {
+                    const int row = 16 * ug + a;
+                    const int col = ((((b >> 2) ^ (row & 7)) << 2) | (b & 3));
+                    acc[a] = recv[0 * 4096 + row * 64 + col] + recv[1 * 4096 + row * 64 + col];
+                }
+            }
+            float hn[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float si = acc[4 * u + 0] + xg[u].x + bs[u].x;
+                const float sz = acc[4 * u + 1] + xg[u].y + bs[u].y;
+                const float so = acc[4 * u + 2] + xg[u].z + bs[u].z;
+                const float sf = acc[4 * u + 3] + xg[u].w + bs[u].w;
+                const float gi = sigmoid_fast(si), gz = ptx::tanh_approx(sz), go = sigmoid_fast(so), gf = sigmoid_fast(sf);
+                c[u] = gi * gz + gf * c[u];
+                hn[u] = ptx::tanh_approx(c[u]) * go;
+            }
+            if (ok) {
+                const size_t o = ((size_t)t * p.B + b) * p.F + u0;
+                *reinterpret_cast<float4 *>(p.h + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                const __half2 lo = __floats2half2_rn(hn[0], hn[1]), hi = __floats2half2_rn(hn[2], hn[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+                *reinterpret_cast<uint2 *>(p.h16 + o) = pk;
+            }
+            // publish h[t]: CTA-wide rendezvous of the writers (also: every reader is done with recv before
+            // the next step's pushes are triggered), then ONE gpu-scope fence + counter increment
+            if (e == 0) KS_TRACE(6);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (e == 0) {
+                ptx::fence_acq_rel_gpu();
+                ptx::red_relaxed_gpu_add(p.counter, 1u);
+                KS_TRACE(7);
+            }
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    ptx::cluster_sync();                                     // nobody exits while the peer may still push into it
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem_base, 64);
+    }
+}
+
+// R (fp32 [4F][F], row g*F+u) -> fp16 packed rows p = 4u+g ; W likewise but kept fp32 (B operand of the
+// TF32 input GEMM) ; bias packed.
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_lstm_pack16(const float *__restrict__ Wl, const float *__restrict__ bl, __half *__restrict__ R16,
+                           float *__restrict__ Wp, float *__restrict__ bp, int F)
+{
+    const size_t total4 = (size_t)2 * 4 * F * (F / 4);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const int j4 = (int)(i % (F / 4));
+        size_t t = i / (F / 4);
+        const int pr = (int)(t % (4 * F));
+        const int m = (int)(t / (4 * F));
+        const int u = pr >> 2, g = pr & 3;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(Wl + ((size_t)m * 4 * F + (size_t)g * F + u) * F) + j4);
+        if (m == 0) {
+            const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+            reinterpret_cast<uint2 *>(R16 + (size_t)pr * F)[j4] = pk;
+            if (j4 == 0) bp[pr] = bl[g * F + u];
+        } else {
+            reinterpret_cast<float4 *>(Wp + (size_t)pr * F)[j4] = v;
+        }
+    }
+}
+
+// Stream-side halves of the layer pipeline: a one-warp kernel that returns once *ctr >= target (the
+// layer below has published enough steps) and a one-thread kernel that publishes a value.
+__global__ void tiramisu_sm100_wait_counter(const uint32_t *ctr, uint32_t target)
+{
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ptx::ld_acquire_gpu(ctr) < target) {
+            if (clock64() - t0 > (1ll << 32)) __trap();
+            __nanosleep(500);
+        }
+    }
+}
+__global__ void tiramisu_sm100_publish(uint32_t *flag, uint32_t value)
+{
+    // stream order already guarantees that the producing GEMM has completed; release for the pollers
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
 std::atomic<int> g_lstm_mode{0};
 std::atomic<int> g_lstm_kernel{0};
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -818,8 +1116,212 @@ int launch_ksplit(const CUtensorMap &map_h, const CUtensorMap &map_r, const KSpl
     return post_launch("tiramisu_sm100_lstm_layer_ksplit");
 }
 
+// ---- fp16 engine: host side -----------------------------------------------------------------------
+size_t h16_smem_bytes(int F) { return (size_t)(F / (H_CL * 64)) * (16384 + 8192) + H_RECV_BYTES + 256 + 1024; }
+
+cudaLaunchConfig_t h16_config(int F, cudaLaunchAttribute *attr, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(F / 16));
+    cfg.blockDim = dim3(H_THREADS);
+    cfg.dynamicSmemBytes = h16_smem_bytes(F);
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = H_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cfg;
+}
+
+// Shape + co-residency.  *pair_ok: two layers' grids (2 x F/16 CTAs) fit next to each other with
+// SMs to spare for the chunk GEMMs.
+bool h16_ok(int F, int B, bool *pair_ok)
+{
+    *pair_ok = false;
+    if (F % 128 != 0 || F > 1024 || B > 64 || h16_smem_bytes(F) > 227 * 1024) return false;
+    static int cached_F = 0, cached_clusters = 0;
+    if (cached_F != F) {
+        auto kern = tiramisu_sm100_lstm_layer_h16;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        cudaLaunchAttribute attr[1];
+        cudaLaunchConfig_t cfg = h16_config(F, attr, nullptr);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        cached_F = F;
+        cached_clusters = n;
+    }
+    const int need = F / 16;
+    *pair_ok = cached_clusters * H_CL >= 2 * need + 8 && sm_count() >= 2 * need + 8;
+    return cached_clusters * H_CL >= need;
+}
+
+// Auxiliary streams + events of the layer pipeline, one set per host thread.
+struct PipeStreams {
+    cudaStream_t rec = nullptr, gemm = nullptr;
+    cudaEvent_t fork = nullptr, join_rec = nullptr, join_gemm = nullptr;
+    bool ok = false;
+    PipeStreams()
+    {
+        ok = cudaStreamCreateWithFlags(&rec, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&gemm, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&join_rec, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&join_gemm, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
+};
+
+int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y, bool pipeline)
+{
+    const size_t TB = (size_t)T * B;
+    const size_t wsz = (size_t)4 * F * F;
+    __half *R16 = reinterpret_cast<__half *>(pool_alloc((size_t)L * wsz * 2));             // packed recurrent weights, all layers
+    float *Wp = reinterpret_cast<float *>(pool_alloc((size_t)L * wsz * 4));                // packed input weights, all layers
+    float *bp = reinterpret_cast<float *>(pool_alloc((size_t)L * 4 * F * 4));
+    float *xg = reinterpret_cast<float *>(pool_alloc((size_t)2 * TB * 4 * F * 4));         // input contributions, by layer parity
+    float *hs = reinterpret_cast<float *>(pool_alloc((size_t)2 * TB * F * 4));             // h fp32, by layer parity
+    __half *h16 = reinterpret_cast<__half *>(pool_alloc((size_t)2 * TB * F * 2));          // h fp16, by layer parity
+    uint32_t *flags = reinterpret_cast<uint32_t *>(pool_alloc((size_t)2 * L * 4));         // [L] step counters, [L] xg_ready
+    if (!R16 || !Wp || !bp || !xg || !hs || !h16 || !flags) return 1;
+    uint32_t *counters = flags, *xg_ready = flags + L;
+    TB200_CHECK(cudaMemsetAsync(flags, 0, (size_t)2 * L * 4, stream()));
+    const int nctas = F / 16;
+    int chunk = 10;
+    if (const char *e = getenv("TB200_LSTM_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
+    int dbg = 0;
+    if (const char *e = getenv("TB200_LSTM_DBG")) dbg = atoi(e);
+
+    for (int l = 0; l < L; l++) {
+        const size_t pk = (size_t)2 * 4 * F * (F / 4);
+        const size_t want = (pk + 255) / 256, cap = (size_t)sm_count() * 16;
+        tiramisu_sm100_lstm_pack16<<<(unsigned)(want < cap ? want : cap), 256, 0, stream()>>>(
+            Wt + (size_t)l * 2 * wsz, bias + (size_t)l * 4 * F, R16 + (size_t)l * wsz, Wp + (size_t)l * wsz,
+            bp + (size_t)l * 4 * F, F);
+        if (post_launch("tiramisu_sm100_lstm_pack16")) return 1;
+    }
+
+    static thread_local PipeStreams *ps = nullptr;
+    if (pipeline && !ps) ps = new PipeStreams();
+    if (pipeline && !ps->ok) pipeline = false;
+
+    auto below_of = [&](int l) -> const float * { return l == 0 ? x : hs + (size_t)((l - 1) & 1) * TB * F; };
+    auto out_of = [&](int l) -> float * { return l == L - 1 ? y : hs + (size_t)(l & 1) * TB * F; };
+    auto xg_of = [&](int l) -> float * { return xg + (size_t)(l & 1) * TB * 4 * F; };
+
+    // recurrence of layer l on stream st
+    auto launch_rec = [&](int l, cudaStream_t st, const uint32_t *ready, unsigned long long *trace) -> int {
+        __half *hh = h16 + (size_t)(l & 1) * TB * F;
+        CUtensorMap map_h, map_r;
+        {
+            uint64_t dims[3] = {(uint64_t)F, (uint64_t)B, (uint64_t)T};
+            uint64_t str[2] = {(uint64_t)F * 2, (uint64_t)B * F * 2};
+            uint32_t box[3] = {64, 64, 1};
+            if (make_tensor_map_f16(&map_h, hh, 3, dims, str, box)) return 1;
+        }
+        {
+            uint64_t dims[2] = {(uint64_t)F, 4 * (uint64_t)F};
+            uint64_t str[1] = {(uint64_t)F * 2};
+            uint32_t box[2] = {64, 128};
+            if (make_tensor_map_f16(&map_r, R16 + (size_t)l * wsz, 2, dims, str, box)) return 1;
+        }
+        H16Params hp;
+        hp.B = B; hp.F = F; hp.T = T;
+        hp.xg = xg_of(l); hp.bias = bp + (size_t)l * 4 * F; hp.h = out_of(l); hp.h16 = hh;
+        hp.counter = counters + l; hp.xg_ready = ready; hp.dbg = dbg; hp.trace = trace;
+        cudaLaunchAttribute attr[1];
+        cudaLaunchConfig_t cfg = h16_config(F, attr, st);
+        TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16, map_h, map_r, hp));
+        return post_launch("tiramisu_sm100_lstm_layer_h16");
+    };
+    // Xg rows [t0*B, t1*B) of layer l = below * Wp(l)^T on the calling thread's current stream()
+    auto launch_xg = [&](int l, int t0, int t1) -> int {
+        return gemm_f32_tc(below_of(l) + (size_t)t0 * B * F, Wp + (size_t)l * wsz, xg_of(l) + (size_t)t0 * B * 4 * F,
+                           (uint64_t)(t1 - t0) * B, 4 * (uint64_t)F, F, 1.0f, 0.0f, F, F, 4 * (uint64_t)F, true);
+    };
+
+    const char *trace_path = getenv("TB200_LSTM_TRACE");                 // bring-up: step timeline of layer 0
+    const size_t trace_n = (size_t)nctas * T * 8;
+    unsigned long long *trace = nullptr;
+    if (trace_path) {
+        trace = reinterpret_cast<unsigned long long *>(pool_alloc(trace_n * 8));
+        if (!trace) return 1;
+        TB200_CHECK(cudaMemsetAsync(trace, 0, trace_n * 8, stream()));
+    }
+
+    cudaStream_t main_st = stream();
+    for (int l = 0; l < L;) {
+        // input contribution of layer l for all T steps: one full-chip GEMM
+        if (launch_xg(l, 0, T)) return 1;
+        const bool pair = pipeline && l + 1 < L;
+        if (!pair) {
+            if (launch_rec(l, main_st, nullptr, l == 0 ? trace : nullptr)) return 1;
+            l += 1;
+            continue;
+        }
+        // layers l and l+1 together: l on the main stream; the chunk GEMMs of Xg(l+1) follow l's step
+        // counter on ps->gemm (they run on the SMs the two recurrences leave free); l+1 on ps->rec
+        // consumes the chunks as they are published.
+        TB200_CHECK(cudaEventRecord(ps->fork, main_st));
+        TB200_CHECK(cudaStreamWaitEvent(ps->rec, ps->fork, 0));
+        TB200_CHECK(cudaStreamWaitEvent(ps->gemm, ps->fork, 0));
+        if (launch_rec(l, main_st, nullptr, l == 0 ? trace : nullptr)) return 1;
+        if (launch_rec(l + 1, ps->rec, xg_ready + (l + 1), nullptr)) return 1;
+        {
+            ScopedStream on(ps->gemm);
+            gemm_tc_hint(1, 256);
+            int rc = 0;
+            for (int t0 = 0, n = 0; t0 < T && !rc; n++) {
+                const int len = n == 0 ? (chunk < 4 ? chunk : 4) : (n == 1 ? (chunk < 6 ? chunk : 6) : chunk);
+                const int t1 = t0 + len < T ? t0 + len : T;
+                tiramisu_sm100_wait_counter<<<1, 32, 0, ps->gemm>>>(counters + l, (uint32_t)nctas * (uint32_t)t1);
+                rc = post_launch("tiramisu_sm100_wait_counter");
+                if (!rc) rc = launch_xg(l + 1, t0, t1);
+                if (!rc) {
+                    tiramisu_sm100_publish<<<1, 1, 0, ps->gemm>>>(xg_ready + (l + 1), (uint32_t)t1);
+                    rc = post_launch("tiramisu_sm100_publish");
+                }
+                t0 = t1;
+            }
+            gemm_tc_hint(0, 0);
+            if (rc) return 1;
+        }
+        TB200_CHECK(cudaEventRecord(ps->join_rec, ps->rec));
+        TB200_CHECK(cudaEventRecord(ps->join_gemm, ps->gemm));
+        TB200_CHECK(cudaStreamWaitEvent(main_st, ps->join_rec, 0));
+        TB200_CHECK(cudaStreamWaitEvent(main_st, ps->join_gemm, 0));
+        l += 2;
+    }
+    if (trace_path) {
+        std::vector<unsigned long long> host(trace_n);
+        TB200_CHECK(cudaMemcpyAsync(host.data(), trace, trace_n * 8, cudaMemcpyDeviceToHost, stream()));
+        TB200_CHECK(cudaStreamSynchronize(stream()));
+        if (FILE *f = fopen(trace_path, "wb")) { fwrite(host.data(), 8, trace_n, f); fclose(f); }
+        pool_free(trace);
+    }
+    pool_free(flags); pool_free(h16); pool_free(hs); pool_free(xg); pool_free(bp); pool_free(Wp); pool_free(R16);
+    return 0;
+}
+
 int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y)
 {
+    // recurrence engine (g_lstm_kernel: 0 auto, 1 = one launch per cell, 2 = persistent N-split layer
+    // kernel, 3 = persistent TF32 K-split layer kernel, 4 = fp16 K-split kernel with layer pairs
+    // overlapped (TB200_LSTM_PIPE=0: one layer at a time)); auto prefers 4, then 3, 2, 1
+    int which = g_lstm_kernel.load();
+    if (const char *e = getenv("TB200_LSTM_KERNEL")) which = atoi(e);
+    if (which == 0 || which == 4) {
+        bool pair_ok = false;
+        const bool ok = h16_ok(F, B, &pair_ok);
+        if (which == 4 && !ok) return fail("tiramisu_b200_lstm", "shape not supported by the fp16 K-split layer kernel");
+        if (ok) {
+            bool pipe = pair_ok;
+            if (const char *e = getenv("TB200_LSTM_PIPE")) pipe = pipe && atoi(e) != 0;
+            return lstm_h16(F, B, L, T, Wt, bias, x, y, pipe);
+        }
+    }
     const size_t BF = (size_t)B * F, TB = (size_t)T * B;
     float *Wp = reinterpret_cast<float *>(pool_alloc((size_t)2 * 4 * F * F * 4));          // packed weights of one layer
     float *bp = reinterpret_cast<float *>(pool_alloc((size_t)4 * F * 4));
@@ -831,10 +1333,6 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
     if (!Wp || !bp || !xg || !hs || !cs || !zero || !counters) return 1;
     TB200_CHECK(cudaMemsetAsync(zero, 0, BF * 4, stream()));
     TB200_CHECK(cudaMemsetAsync(counters, 0, (size_t)L * 4, stream()));
-    // recurrence engine (g_lstm_kernel: 0 auto, 1 = one launch per cell, 2 = persistent N-split layer
-    // kernel, 3 = persistent K-split layer kernel); auto prefers 3, then 2, then 1
-    int which = g_lstm_kernel.load();
-    if (const char *e = getenv("TB200_LSTM_KERNEL")) which = atoi(e);
     const bool use_ksplit = (which == 0 || which == 3) && ksplit_ok(F, B);
     if (which == 3 && !use_ksplit) return fail("tiramisu_b200_lstm", "shape not supported by the K-split layer kernel");
     const bool use_layer_kernel = !use_ksplit && which != 1 && which != 3 && layer_kernel_ok(F, B);
@@ -953,7 +1451,7 @@ TB200_API int tiramisu_b200_set_lstm_mode(int mode)
 
 TB200_API int tiramisu_b200_set_lstm_kernel(int kernel)
 {
-    if (kernel < 0 || kernel > 3) kernel = 0;
+    if (kernel < 0 || kernel > 4) kernel = 0;
     return g_lstm_kernel.exchange(kernel);
 }
 

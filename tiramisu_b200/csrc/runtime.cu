@@ -47,6 +47,17 @@ int check(cudaError_t e, const char *where)
 
 cudaStream_t stream() { return t_stream_set ? t_stream : cudaStreamPerThread; }
 
+ScopedStream::ScopedStream(cudaStream_t s) : prev_(t_stream), prev_set_(t_stream_set)
+{
+    t_stream = s;
+    t_stream_set = true;
+}
+ScopedStream::~ScopedStream()
+{
+    t_stream = prev_;
+    t_stream_set = prev_set_;
+}
+
 int post_launch(const char *kernel_name)
 {
     count_launch();

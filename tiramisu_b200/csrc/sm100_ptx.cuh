@@ -127,6 +127,18 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
+// Same with fp16 inputs (kind::f16, K = 16 per instruction): 11-bit significands like TF32 at half
+// the shared-memory footprint — what lets two LSTM layers' recurrent weights be resident at once.
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           bool accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier once all MMAs issued so far by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t *bar)
@@ -391,6 +403,13 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with fp16 A and B (format code 0), fp32 accumulate; same field layout as above.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major)
+{
+    return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
 }  // namespace ptx
 
 // ---- host: TMA tensor maps ------------------------------------------------------------------------
@@ -399,5 +418,8 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
 constexpr int kTmaSwizzleNone = 0, kTmaSwizzle128 = 1, kTmaSwizzle128Atom32 = 2;
 int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
                         const uint64_t *strides_bytes, const uint32_t *box, int swizzle = kTmaSwizzle128);
+// Same for an fp16 tensor (dims/box in elements, strides in bytes), 128-byte swizzle.
+int make_tensor_map_f16(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
+                        const uint64_t *strides_bytes, const uint32_t *box);
 
 }  // namespace tb200
