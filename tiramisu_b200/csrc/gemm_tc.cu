@@ -111,11 +111,16 @@ struct GemmParams {
     uint32_t b_lbo, b_sbo;              // MN-major B descriptor offsets (bytes)
 };
 
-template <int BN, bool B_MN>
+// F16: operands are fp16 (kind::f16, K = 16 per instruction, 64 elements per 128-byte swizzle row):
+// same tile bytes, ring and descriptors; only the K bookkeeping and the MMA kind differ.  Used by the
+// LSTM layer pipeline, whose upper layers take the fp16 copy of h as the A operand.
+template <int BN, bool B_MN, bool F16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                          const GemmParams p)
 {
+    static_assert(!(F16 && B_MN), "fp16 operands are K-major only");
+    constexpr int BKE = F16 ? 64 : BK;                 // elements per k-slab (128 bytes)
     using C_ = Cfg<BN>;
     constexpr int STAGES = C_::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -139,7 +144,7 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
     const int tile_m = first_m + (t % tiles_per_group) % gsz;
     const int tile_n = (t % tiles_per_group) / gsz;
     const int m0 = tile_m * BM, n0 = tile_n * BN;
-    const int num_kb = (p.K + BK - 1) / BK;
+    const int num_kb = (p.K + BKE - 1) / BKE;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
@@ -171,7 +176,7 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
             ptx::mbar_wait(&empty_bar[s], ph ^ 1);
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&full_bar[s], C_::STAGE_BYTES);
-                const int k0 = kb * BK;
+                const int k0 = kb * BKE;
                 ptx::tma_load_2d(smem_a + s * A_TILE_BYTES, &map_a, &full_bar[s], k0, m0);
                 uint8_t *bdst = smem_b + s * C_::B_TILE_BYTES;
                 if (B_MN) {
@@ -186,7 +191,7 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp walks the ring (uniform control flow), one elected lane issues =====
-        constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, B_MN);
+        constexpr uint32_t idesc = F16 ? ptx::make_idesc_f16(BM, BN, false, false) : ptx::make_idesc_tf32(BM, BN, false, B_MN);
         // K-major, 128B swizzle: rows are 128 B apart, 8-row groups 1024 B apart; a K step of 8 fp32
         // moves the start address 32 B inside the swizzled row.
         // MN-major tf32 (128B swizzle, 32B atoms): rows are k (128 B = 32 columns each), 4-row groups
@@ -205,9 +210,14 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
                 const uint64_t da = ptx::desc_advance(da0, (uint32_t)s * A_TILE_BYTES);
                 const uint64_t db = ptx::desc_advance(db0, (uint32_t)s * C_::B_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; k++)
-                    ptx::mma_tf32_ss(tmem_base, ptx::desc_advance(da, k * kStepA), ptx::desc_advance(db, k * kStepB),
-                                     idesc, (kb | k) != 0);
+                for (int k = 0; k < BK / UMMA_K; k++) {
+                    if (F16)
+                        ptx::mma_f16_ss(tmem_base, ptx::desc_advance(da, k * kStepA), ptx::desc_advance(db, k * kStepB),
+                                        idesc, (kb | k) != 0);
+                    else
+                        ptx::mma_tf32_ss(tmem_base, ptx::desc_advance(da, k * kStepA), ptx::desc_advance(db, k * kStepB),
+                                         idesc, (kb | k) != 0);
+                }
                 ptx::mma_commit(&empty_bar[s]);        // slab free once these MMAs retire
                 if (kb == num_kb - 1) ptx::mma_commit(tmem_full_bar);     // accumulator complete
             }
@@ -587,6 +597,40 @@ int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, flo
     return post_launch("tiramisu_sm100_gemm_tf32");
 }
 
+template <int BN>
+int launch_tc_f16(const void *A, const void *B, float *C, int M, int N, int K, float alpha, float beta, int64_t ldA,
+                  int64_t ldB, int64_t ldC)
+{
+    CUtensorMap map_a, map_b;
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        uint64_t str[1] = {(uint64_t)ldA * 2};
+        uint32_t box[2] = {64, BM};
+        if (make_tensor_map_f16(&map_a, A, 2, dims, str, box)) return 1;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)ldB * 2};
+        uint32_t box[2] = {64, (uint32_t)BN};
+        if (make_tensor_map_f16(&map_b, B, 2, dims, str, box)) return 1;
+    }
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldC = ldC;
+    p.num_m = (M + BM - 1) / BM;
+    p.num_n = (N + BN - 1) / BN;
+    p.group_m = 16;
+    p.b_lbo = 0;
+    p.b_sbo = 0;
+    auto kern = tiramisu_sm100_gemm_tf32<BN, false, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB200_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+        attr_set = true;
+    }
+    kern<<<p.num_m * p.num_n, kThreads, Cfg<BN>::SMEM_BYTES, stream()>>>(map_a, map_b, p);
+    return post_launch("tiramisu_sm100_gemm_f16");
+}
+
 template <int CG, bool B_MN>
 int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N, int K, float alpha, float beta,
                          int64_t ldA, int64_t ldB, int64_t ldC)
@@ -726,6 +770,18 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
     case 128: return launch_tc<128, true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
     default: return launch_tc<64, true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
     }
+}
+
+// C[M][N] (fp32) = alpha * A[M][K] * B[N][K]^T + beta * C with fp16 operands (both K-major, pitches in
+// elements, multiples of 8), fp32 accumulation; one 128 x 256 (or 128 x 128) tile per CTA.
+int gemm_f16_tc(const void *A16, const void *B16, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,
+                uint64_t ldA, uint64_t ldB, uint64_t ldC)
+{
+    if (!aligned16(A16) || !aligned16(B16) || !aligned16(C) || ldA % 8 || ldB % 8 || ldC % 4 || M == 0 || N == 0 || K == 0)
+        return fail("gemm_f16_tc", "operands not addressable by TMA");
+    if (N % 256 == 0 || N > 1024)
+        return launch_tc_f16<256>(A16, B16, C, (int)M, (int)N, (int)K, alpha, beta, ldA, ldB, ldC);
+    return launch_tc_f16<128>(A16, B16, C, (int)M, (int)N, (int)K, alpha, beta, ldA, ldB, ldC);
 }
 
 int gemm_f32(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,

@@ -15,8 +15,8 @@ for ch in 5 20; do
 done
 echo "== trace (kernel 4, serial and pipelined)"
 TB200_LSTM_KERNEL=4 TB200_LSTM_PIPE=0 TB200_LSTM_TRACE=gpurun_out/lstm_h16_trace_serial.bin timeout 300 python tools/run_one.py lstm > /dev/null 2>&1
-python tools/lstm_trace.py gpurun_out/lstm_h16_trace_serial.bin 100 2>&1 | tee gpurun_out/run20_lstm_h16_timeline_serial.txt
+python tools/lstm_trace.py gpurun_out/lstm_h16_trace_serial.bin 100 h16 2>&1 | tee gpurun_out/run20_lstm_h16_timeline_serial.txt
 TB200_LSTM_KERNEL=4 TB200_LSTM_PIPE=1 TB200_LSTM_TRACE=gpurun_out/lstm_h16_trace_pipe.bin timeout 300 python tools/run_one.py lstm > /dev/null 2>&1
-python tools/lstm_trace.py gpurun_out/lstm_h16_trace_pipe.bin 100 2>&1 | tee gpurun_out/run20_lstm_h16_timeline_pipe.txt
+python tools/lstm_trace.py gpurun_out/lstm_h16_trace_pipe.bin 100 h16 2>&1 | tee gpurun_out/run20_lstm_h16_timeline_pipe.txt
 rm -f gpurun_out/*.bin
 echo "== full gpu suite"; timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee gpurun_out/run20_pytest_all.log

@@ -13,5 +13,7 @@ for t in (5, 50, 90):
     for s in range(8):
         v = a[:, t, s] - ref
         print(f"   {names[s]:28s} min {v.min():6d}  median {int(np.median(v)):6d}  max {v.max():6d} ns")
+if len(sys.argv) > 3 and sys.argv[3] == "h16":
+    print("(h16 kernel: slot 'full[1] seen' = epilogue rendezvous passed, before the gpu-scope fence)")
 per = np.diff(a[:, 1:, 7].max(axis=0))
 print("median step period", np.median(per), "ns")
