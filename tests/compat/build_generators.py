@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Compile the reference's own *generator* programs UNMODIFIED (from where they lie under
+/root/reference) against the tiramisu_b200 front-end (tiramisu_b200/frontend/include/tiramisu/*.h),
+run them here — `tiramisu::codegen(..., true)` lowers to sm_100a CUDA and calls nvcc — and link the
+reference's own wrapper_*.cpp harnesses with the objects they produced plus libtiramisu_b200.so.
+TEST INFRASTRUCTURE for SURVEY §8(f)1 / row a12 (the emitter replacement).
+
+Runs only where /root/reference exists (the build container).  Outputs: tests/compat/_gen/<name>/
+(generator binary, generated .o and the .b200.cu it was compiled from) and tests/compat/_bin/gen_<name>
+(git-ignored, shipped to the GPU box by gpurun, run there by tests/test_frontend_gpu.py).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("TIRAMISU_REFERENCE", "/root/reference")
+GEN = os.path.join(HERE, "_gen")
+BIN = os.path.join(HERE, "_bin")
+LIBDIR = os.path.join(ROOT, "tiramisu_b200", "lib")
+FRONT_INC = os.path.join(ROOT, "tiramisu_b200", "frontend", "include")
+CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+
+SGEMM_GPU = "benchmarks/linear_algebra/blas/level3/sgemm/gpu"
+# name -> (generator source, object it writes (relative to the run directory), wrapper source, include dirs, extra link flags)
+TARGETS = {
+    **{f"test_{n}": (f"tests/test_{n}.cpp", f"build/generated_fct_test_{n}.o", f"tests/wrapper_test_{n}.cpp", ["tests"], [])
+       for n in (162, 164, 165, 166, 167, 168, 169, 170, 171, 197)},
+    "tutorial_04gpu": ("tutorials/developers/tutorial_04gpu/tutorial_04gpu.cpp", "build/generated_fct_developers_tutorial_04gpu.o",
+                       "tutorials/developers/tutorial_04gpu/wrapper_tutorial_04gpu.cpp", ["tutorials/developers/tutorial_04gpu"], []),
+    "sgemm_gpu_generator1": (f"{SGEMM_GPU}/generator1.cpp", "fct.o", f"{SGEMM_GPU}/wrapper.cpp", [SGEMM_GPU],
+                             [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
+    "sgemm_gpu_generator2": (f"{SGEMM_GPU}/generator2.cpp", "fct.o", f"{SGEMM_GPU}/wrapper.cpp", [SGEMM_GPU],
+                             [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
+    "sgemm_gpu_generator3": (f"{SGEMM_GPU}/generator3.cpp", "fct.o", f"{SGEMM_GPU}/wrapper.cpp", [SGEMM_GPU],
+                             [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
+}
+
+
+def available() -> bool:
+    return (os.path.isdir(os.path.join(REF, "tests")) and os.path.exists(os.path.join(LIBDIR, "libtiramisu_b200.so"))
+            and os.path.exists(os.path.join(LIBDIR, "libtiramisu_b200_frontend.so")))
+
+
+def _env():
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    return env
+
+
+def build_one(name: str, lowering: str | None = None) -> tuple[int, str]:
+    gsrc, obj, wsrc, incs, extra = TARGETS[name]
+    tag = name if lowering is None else f"{name}_{lowering}"
+    work = os.path.join(GEN, tag)
+    shutil.rmtree(work, ignore_errors=True)
+    os.makedirs(os.path.join(work, "build"), exist_ok=True)
+    os.makedirs(BIN, exist_ok=True)
+    env = _env()
+    if lowering:
+        env["TIRAMISU_B200_LOWERING"] = lowering
+    inc = sum((["-I", os.path.join(REF, i)] for i in incs), [])
+    gen_exe = os.path.join(work, "generator")
+    log = ""
+    # 1. the reference generator, unmodified, against this repo's front-end
+    cmd = ["g++", "-std=c++17", "-O1", "-w", "-I", FRONT_INC, *inc, os.path.join(REF, gsrc), "-o", gen_exe,
+           f"-L{LIBDIR}", "-ltiramisu_b200_frontend", f"-Wl,-rpath,{LIBDIR}"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    log += r.stdout + r.stderr
+    if r.returncode:
+        return r.returncode, "generator does not compile:\n" + log[-3000:]
+    # 2. run it: codegen() lowers to sm_100a and compiles the object
+    r = subprocess.run([gen_exe], capture_output=True, text=True, env=env, cwd=work)
+    log += r.stdout + r.stderr
+    if r.returncode or not os.path.exists(os.path.join(work, obj)):
+        return r.returncode or 1, "generator failed:\n" + log[-3000:]
+    # 3. the reference wrapper, unmodified, with the generated object
+    exe = os.path.join(BIN, "gen_" + tag)
+    cmd = ["g++", "-std=c++17", "-O2", "-mavx", "-fopenmp", "-w",
+           "-I", os.path.join(HERE, "include"), "-I", os.path.join(REF, "3rdParty/Halide/src/runtime"),
+           "-I", os.path.join(REF, "include"), "-I", os.path.join(REF, "benchmarks"), "-I", os.path.join(CUDA, "include"), *inc,
+           os.path.join(REF, wsrc), os.path.join(work, obj), os.path.join(HERE, "compat_support.cpp"),
+           os.path.join(REF, "src/tiramisu_utils.cpp"), os.path.join(REF, "src/tiramisu_debug.cpp"),
+           "-o", exe, f"-L{LIBDIR}", "-ltiramisu_b200", f"-L{os.path.join(ROOT, 'oracle')}", "-ltiramisu_oracle",
+           "-Wl,-rpath,$ORIGIN/../../../tiramisu_b200/lib", "-Wl,-rpath,$ORIGIN/../../../oracle",
+           f"-L{CUDA}/lib64", "-lcudart", f"-Wl,-rpath,{CUDA}/lib64", "-Wl,--allow-shlib-undefined", "-lpthread", "-ldl", *extra]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    log += r.stdout + r.stderr
+    if r.returncode:
+        return r.returncode, "wrapper does not link:\n" + log[-3000:]
+    return 0, log[-2000:]
+
+
+def build(names=None, verbose=False) -> dict:
+    out = {}
+    for name in TARGETS:
+        if names and name not in names:
+            continue
+        out[name] = build_one(name)
+        if verbose:
+            print(name, "OK" if out[name][0] == 0 else "FAILED\n" + out[name][1], flush=True)
+    # the two GEMM-pattern generators once more with the pattern lowering off (generic SIMT emission)
+    for name in ("test_167", "test_169"):
+        if names and name not in names:
+            continue
+        out[name + "_generic"] = build_one(name, "generic")
+        if verbose:
+            print(name + "_generic", "OK" if out[name + "_generic"][0] == 0 else "FAILED\n" + out[name + "_generic"][1], flush=True)
+    return out
+
+
+if __name__ == "__main__":
+    if not available():
+        print("reference checkout or the libraries are missing; nothing built")
+        sys.exit(0)
+    res = build(sys.argv[1:] or None, verbose=True)
+    sys.exit(1 if any(rc for rc, _ in res.values()) else 0)

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Build the repo's own front-end test generators (tests/frontend_cases/*_gen.cpp): compile each
+against tiramisu_b200/frontend, run it (codegen lowers to sm_100a and calls nvcc), and link the
+object into tests/frontend_cases/_build/lib<name>.so next to libtiramisu_b200.so so the tests can
+call the generated function through ctypes.  TEST INFRASTRUCTURE; needs g++ and nvcc, no GPU and no
+reference checkout."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+OUT = os.path.join(HERE, "_build")
+LIBDIR = os.path.join(ROOT, "tiramisu_b200", "lib")
+FRONT_INC = os.path.join(ROOT, "tiramisu_b200", "frontend", "include")
+
+# library name -> (generator source, argv[1] for the generator or None, lowering mode or None)
+CASES = {
+    "heat2d_gen": ("heat2d_gen.cpp", None, None),
+    "blurxy_u8_gen": ("blurxy_u8_gen.cpp", None, None),
+    "gemm_sym_gen": ("gemm_sym_gen.cpp", "gemm_sym_gen", None),
+    "gemm_sym_generic": ("gemm_sym_gen.cpp", "gemm_sym_generic", "generic"),
+}
+
+
+def _env(lowering=None):
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    if lowering:
+        env["TIRAMISU_B200_LOWERING"] = lowering
+    return env
+
+
+def build(verbose=False) -> dict:
+    os.makedirs(OUT, exist_ok=True)
+    res = {}
+    for name, (src, arg, lowering) in CASES.items():
+        gen = os.path.join(OUT, name + "_generator")
+        steps = [
+            (["g++", "-std=c++17", "-O1", "-w", "-I", FRONT_INC, os.path.join(HERE, src), "-o", gen,
+              f"-L{LIBDIR}", "-ltiramisu_b200_frontend", f"-Wl,-rpath,{LIBDIR}"], None),
+            ([gen] + ([arg] if arg else []), OUT),
+            (["g++", "-shared", "-o", os.path.join(OUT, f"lib{name}.so"), os.path.join(OUT, name + ".o"),
+              f"-L{LIBDIR}", "-ltiramisu_b200", "-L/usr/local/cuda/lib64", "-lcudart",
+              "-Wl,-rpath,$ORIGIN/../../../tiramisu_b200/lib", "-Wl,-rpath,/usr/local/cuda/lib64"], None),
+        ]
+        rc, log = 0, ""
+        for cmd, cwd in steps:
+            r = subprocess.run(cmd, capture_output=True, text=True, env=_env(lowering), cwd=cwd)
+            log += r.stdout + r.stderr
+            if r.returncode:
+                rc = r.returncode
+                break
+        res[name] = (rc, log[-3000:])
+        if verbose:
+            print(name, "OK" if rc == 0 else "FAILED\n" + log[-3000:], flush=True)
+    return res
+
+
+def lib_path(name: str) -> str:
+    return os.path.join(OUT, f"lib{name}.so")
+
+
+def generated_source(name: str) -> str:
+    return os.path.join(OUT, name + ".o.b200.cu")
+
+
+if __name__ == "__main__":
+    r = build(verbose=True)
+    sys.exit(1 if any(rc for rc, _ in r.values()) else 0)

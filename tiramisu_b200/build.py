@@ -65,5 +65,29 @@ def build(verbose: bool = False, force: bool = False) -> str:
     return LIB
 
 
+FRONTEND = os.path.join(HERE, "frontend")
+FRONTEND_LIB = os.path.join(LIBDIR, "libtiramisu_b200_frontend.so")
+
+
+def build_frontend(force: bool = False) -> str:
+    """The generator-time front-end + sm_100a lowering (tiramisu_b200/frontend): plain C++, no CUDA
+    in the library itself — the code it generates is compiled by nvcc when a generator runs."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(FRONTEND, "src", "*.cpp")))
+    hdrs = glob.glob(os.path.join(FRONTEND, "include", "tiramisu", "*.h"))
+    if (not force and os.path.exists(FRONTEND_LIB) and os.path.getmtime(FRONTEND_LIB) > _newest(srcs + hdrs)):
+        return FRONTEND_LIB
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    cmd = ["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+           "-I", os.path.join(FRONTEND, "include"), *srcs, "-o", FRONTEND_LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError(f"front-end build failed:\n{r.stdout}\n{r.stderr}")
+    return FRONTEND_LIB
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="--force" in sys.argv))
+    print(build_frontend(force="--force" in sys.argv))

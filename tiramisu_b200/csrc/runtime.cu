@@ -186,6 +186,8 @@ TB200_API void *tiramisu_b200_get_stream(void) { return reinterpret_cast<void *>
 
 TB200_API uint64_t tiramisu_b200_kernel_launches(void) { return g_kernel_launches.load(); }
 
+TB200_API int tiramisu_b200_post_launch(const char *kernel_name) { return post_launch(kernel_name ? kernel_name : "generated kernel"); }
+
 TB200_API int tiramisu_b200_pool_trim(void)
 {
     int dev = 0;

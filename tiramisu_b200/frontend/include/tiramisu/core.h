@@ -1,0 +1,273 @@
+// tiramisu/core.h — function / buffer / computation API of the tiramisu_b200 front-end.
+//
+// Same class names, constructor shapes and scheduling commands as the reference's modern API
+// (/root/reference/include/tiramisu/core.h: function :189, buffer :1424, computation :1863,
+// input :4952, constant :5212; init/codegen :62-75), so the reference's generator sources
+// (tests/test_16x.cpp, test_197.cpp, tutorials/developers/tutorial_04gpu, sgemm/gpu/generator*.cpp)
+// compile against it unmodified.  What is behind the API is different by design:
+//   * iteration domains are rectangular boxes of named loop dimensions (no ISL); split / tile /
+//     interchange / gpu_tile rewrite that list and record how the original iterators are rebuilt;
+//   * `codegen(args, "x.o", true)` lowers the ordered loop tree to sm_100a CUDA + a host function
+//     with the halide_buffer_t ABI and compiles it with nvcc (lowering.cpp) — it replaces the
+//     reference's cuda_ast emitter (src/tiramisu_codegen_cuda.cpp) and Halide host code generator.
+// The ISL-string constructors (`computation("{S[i,j]: ...}", ...)`) are not supported.
+#ifndef TIRAMISU_B200_FRONTEND_CORE_H
+#define TIRAMISU_B200_FRONTEND_CORE_H
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <tiramisu/expr.h>
+#include <tiramisu/type.h>
+
+namespace tiramisu {
+
+class computation;
+class buffer;
+class function;
+class input;
+class constant;
+
+void init(std::string name);
+void init();
+void codegen(const std::vector<buffer *> &arguments, const std::string obj_filename, bool gen_cuda_stmt = false);
+
+/** Where a buffer lives (reference: cuda_ast::memory_location, include/tiramisu/cuda_ast.h). */
+enum class mem_loc { host, gpu_global, gpu_shared, gpu_local, gpu_register, gpu_constant };
+
+class buffer {
+public:
+    buffer();
+    buffer(std::string name, std::vector<expr> dim_sizes, primitive_t type, argument_t argt,
+           function *fct = global::get_implicit_function());
+
+    const std::string &get_name() const { return name_; }
+    const std::vector<expr> &get_dim_sizes() const { return dims_; }
+    int get_n_dims() const { return (int) dims_.size(); }
+    primitive_t get_elements_type() const { return dtype_; }
+    argument_t get_argument_type() const { return argt_; }
+    void set_argument_type(argument_t a) { argt_ = a; }
+    mem_loc get_location() const { return loc_; }
+    bool get_auto_allocate() const { return auto_allocate_; }
+    void set_auto_allocate(bool b) { auto_allocate_ = b; }
+
+    void tag_gpu_global() { loc_ = mem_loc::gpu_global; }
+    void tag_gpu_shared() { loc_ = mem_loc::gpu_shared; }
+    void tag_gpu_local() { loc_ = mem_loc::gpu_local; }
+    void tag_gpu_register() { loc_ = mem_loc::gpu_register; }
+    void tag_gpu_constant() { loc_ = mem_loc::gpu_constant; }
+
+    /** Allocate / free this buffer just before / after \p C at loop level \p level (reference core.h:1700-1712). */
+    computation *allocate_at(computation &C, var level);
+    computation *allocate_at(computation &C, int level);
+    computation *deallocate_at(computation &C, var level);
+    void dump(bool) const;
+
+private:
+    std::string name_;
+    std::vector<expr> dims_;
+    primitive_t dtype_ = p_none;
+    argument_t argt_ = a_temporary;
+    mem_loc loc_ = mem_loc::host;
+    bool auto_allocate_ = true;
+    function *fct_ = nullptr;
+};
+
+/** One dimension of a computation's scheduled loop nest. */
+struct loop_dim {
+    std::string name;
+    expr lo, hi;                 // half-open [lo, hi)
+    enum tag_t { none, gpu_block, gpu_thread, parallel, vector, unrolled, distributed } tag = none;
+    int vec_len = 0;
+};
+
+class computation {
+public:
+    static const var root;
+    static const int root_dimension = -1;
+
+    computation();
+    computation(std::string name, std::vector<var> iterator_variables, expr e, bool schedule_this_computation, primitive_t t);
+    computation(std::string name, std::vector<var> iterator_variables, expr e, bool schedule_this_computation);
+    computation(std::string name, std::vector<var> iterator_variables, expr e);
+    computation(std::vector<var> iterator_variables, expr e);
+    computation(std::vector<var> iterator_variables, expr e, bool schedule_this_computation);
+    computation(std::string name, std::vector<var> iterator_variables, primitive_t t);
+    computation(std::vector<var> iterator_variables, primitive_t t);
+    computation(std::string name, std::vector<var> iterator_variables, expr predicate, expr e);
+    computation(std::vector<var> iterator_variables, expr predicate, expr e);
+    virtual ~computation() {}
+
+    // ---- Layer I
+    const std::string &get_name() const { return name_; }
+    primitive_t get_data_type() const { return dtype_; }
+    const expr &get_expr() const { return expr_; }
+    void set_expression(const expr &e);
+    bool should_schedule_this_computation() const { return scheduled_; }
+    const std::vector<var> &get_iteration_variables() const { return iters_; }
+    function *get_function() const { return fct_; }
+    void add_predicate(expr p) { predicate_ = p; }
+    const expr &get_predicate() const { return predicate_; }
+
+    template <typename... Args> expr operator()(Args... args)
+    {
+        std::vector<expr> idx{expr(args)...};
+        return access_expr(idx);
+    }
+
+    // ---- Layer II
+    virtual void split(var L0, int sizeX);
+    virtual void split(var L0, int sizeX, var L0_outer, var L0_inner);
+    virtual void tile(var L0, var L1, int sizeX, int sizeY);
+    virtual void tile(var L0, var L1, int sizeX, int sizeY, var L0_outer, var L1_outer, var L0_inner, var L1_inner);
+    virtual void tile(var L0, var L1, var L2, int sizeX, int sizeY, int sizeZ);
+    virtual void tile(var L0, var L1, var L2, int sizeX, int sizeY, int sizeZ,
+                      var L0_outer, var L1_outer, var L2_outer, var L0_inner, var L1_inner, var L2_inner);
+    virtual void interchange(var L0, var L1);
+    virtual void gpu_tile(var L0, int sizeX);
+    virtual void gpu_tile(var L0, int sizeX, var L0_outer, var L0_inner);
+    virtual void gpu_tile(var L0, var L1, int sizeX, int sizeY);
+    virtual void gpu_tile(var L0, var L1, int sizeX, int sizeY, var L0_outer, var L1_outer, var L0_inner, var L1_inner);
+    virtual void gpu_tile(var L0, var L1, var L2, int sizeX, int sizeY, int sizeZ);
+    virtual void gpu_tile(var L0, var L1, var L2, int sizeX, int sizeY, int sizeZ,
+                          var L0_outer, var L1_outer, var L2_outer, var L0_inner, var L1_inner, var L2_inner);
+    virtual void tag_gpu_level(var L0, var L1);
+    virtual void tag_gpu_level(var L0, var L1, var L2, var L3);
+    virtual void tag_gpu_level(var L0, var L1, var L2, var L3, var L4, var L5);
+    virtual void tag_gpu_block_level(var L0);
+    virtual void tag_gpu_block_level(var L0, var L1);
+    virtual void tag_gpu_block_level(var L0, var L1, var L2);
+    virtual void tag_gpu_thread_level(var L0);
+    virtual void tag_gpu_thread_level(var L0, var L1);
+    virtual void tag_gpu_thread_level(var L0, var L1, var L2);
+    virtual void parallelize(var L);
+    virtual void tag_parallel_level(var L);
+    virtual void vectorize(var L, int v);
+    virtual void vectorize(var L, int v, var L_outer, var L_inner);
+    virtual void tag_vector_level(var L, int v);
+    virtual void unroll(var L, int fac);
+    virtual void unroll(var L, int fac, var L_outer, var L_inner);
+    virtual void tag_unroll_level(var L);
+    virtual void shift(var L0, int n);
+
+    /** Order: \p next runs after this computation, sharing the loops up to and including \p level. */
+    computation &then(computation &next, var level = root);
+    computation &then(computation &next, int level);
+    void after(computation &before_this, var level = root);
+    void after(computation &before_this, int level);
+    void before(computation &after_this, var level = root);
+    void between(computation &before_c, var before_l, computation &after_c, var after_l);
+
+    /** Performance hint in the reference (stage \p inp through shared memory below \p level);
+      * the sm_100a lowering picks its own staging, so this only records the hint. */
+    computation *cache_shared(computation &inp, const var &level, std::vector<int> buffer_shape,
+                              std::vector<expr> copy_offsets, bool pad_buffer = false);
+
+    // ---- Layer III
+    void store_in(buffer *buff);
+    void store_in(buffer *buff, std::vector<expr> iterators);
+    void store_in(std::vector<expr> mapping, std::vector<expr> sizes);
+    buffer *get_buffer();
+    buffer *get_automatically_allocated_buffer() { return get_buffer(); }
+    void set_access_exprs(buffer *b, std::vector<expr> idx);
+
+    // ---- used by the lowering
+    std::vector<loop_dim> &dims() { return dims_; }
+    const std::vector<std::pair<std::string, expr>> &defs() const { return defs_; }
+    const std::vector<expr> &guards() const { return guards_; }
+    const std::vector<expr> &access() const { return access_; }
+    bool has_access() const { return buf_ != nullptr; }
+    computation *pred() const { return pred_; }
+    computation *succ() const { return succ_; }
+    const std::string &pred_level() const { return pred_level_; }
+    int pred_level_index() const { return pred_level_index_; }
+    bool is_input() const { return is_input_; }
+    bool is_constant() const { return is_constant_; }
+    int find_dim(const std::string &name) const;
+    void dump() const;
+
+protected:
+    void construct(std::string name, std::vector<var> iters, expr e, bool schedule, primitive_t t);
+    expr access_expr(const std::vector<expr> &idx);
+    void tag(const var &L, loop_dim::tag_t t);
+    void link_after(computation &before_this, const std::string &level_name, int level_index);
+
+    std::string name_;
+    std::vector<var> iters_;
+    expr expr_, predicate_;
+    primitive_t dtype_ = p_none;
+    bool scheduled_ = true;
+    bool is_input_ = false, is_constant_ = false;
+    function *fct_ = nullptr;
+
+    std::vector<loop_dim> dims_;
+    std::vector<std::pair<std::string, expr>> defs_;   // name := expression in newer names (oldest first)
+    std::vector<expr> guards_;
+
+    buffer *buf_ = nullptr;
+    std::vector<expr> access_;                           // index expressions in the original iterators
+    computation *pred_ = nullptr, *succ_ = nullptr;
+    std::string pred_level_;                             // "" = root
+    int pred_level_index_ = -2;                          // -2 = by name, -1 = root, >=0 explicit depth
+    friend class function;
+    friend class buffer;
+};
+
+class input : public computation {
+public:
+    input(std::string name, std::vector<var> iterator_variables, primitive_t t);
+    input(std::vector<var> iterator_variables, primitive_t t);
+    input(std::string name, std::vector<std::string> dimension_names, std::vector<expr> dimension_sizes, primitive_t t);
+};
+
+class Input : public input {
+public:
+    Input(std::string name, std::vector<expr> sizes, primitive_t t);
+};
+
+/** A scalar evaluated once at function entry (reference core.h:5212; only the function-wide form). */
+class constant : public computation {
+public:
+    constant(std::string param_name, const expr &param_expr, primitive_t t, bool function_wide,
+             computation *with_computation, int at_loop_level, function *func = global::get_implicit_function());
+    constant(std::string param_name, const expr &param_expr, primitive_t t, function *func = global::get_implicit_function());
+    constant(std::string param_name, const expr &param_expr);
+    operator expr();
+};
+
+class function {
+public:
+    explicit function(std::string name);
+    const std::string &get_name() const { return name_; }
+    void add_computation(computation *c) { comps_.push_back(c); }
+    void add_buffer(buffer *b) { bufs_.push_back(b); }
+    const std::vector<computation *> &get_computations() const { return comps_; }
+    const std::vector<buffer *> &get_buffers() const { return bufs_; }
+    computation *find_computation(const std::string &name) const;
+    buffer *find_buffer(const std::string &name) const;
+    std::string fresh_name(const std::string &prefix);
+    /** Heap objects the front-end creates on the user's behalf (auto buffers, allocate_at computations). */
+    template <typename T> T *own(T *p)
+    {
+        owned_.push_back(std::shared_ptr<void>(p, [](void *q) { delete static_cast<T *>(q); }));
+        return p;
+    }
+    void set_arguments(const std::vector<buffer *> &args) { args_ = args; }
+    const std::vector<buffer *> &get_arguments() const { return args_; }
+    void codegen(const std::vector<buffer *> &arguments, const std::string obj_filename, bool gen_cuda_stmt);
+    void dump(bool) const;
+
+private:
+    std::string name_;
+    std::vector<computation *> comps_;
+    std::vector<buffer *> bufs_;
+    std::vector<buffer *> args_;
+    std::vector<std::shared_ptr<void>> owned_;
+    int counter_ = 0;
+};
+
+}  // namespace tiramisu
+
+#endif

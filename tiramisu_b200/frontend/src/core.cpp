@@ -1,0 +1,430 @@
+// core.cpp — buffers, computations and scheduling commands of the tiramisu_b200 front-end
+// (see include/tiramisu/core.h).  A schedule is a list of named loop dimensions; every command
+// rewrites the list and records how older names are rebuilt from newer ones.
+#include <tiramisu/block.h>
+#include <tiramisu/core.h>
+
+#include <cstdlib>
+#include <iostream>
+#include <stdexcept>
+
+namespace tiramisu {
+
+[[noreturn]] static void die(const std::string &msg)
+{
+    std::cerr << "tiramisu_b200 front-end: " << msg << std::endl;
+    std::exit(1);
+}
+
+// ---- function -----------------------------------------------------------------------------------
+function::function(std::string name) : name_(std::move(name)) {}
+
+computation *function::find_computation(const std::string &name) const
+{
+    for (auto it = comps_.rbegin(); it != comps_.rend(); ++it)
+        if ((*it)->get_name() == name) return *it;
+    return nullptr;
+}
+buffer *function::find_buffer(const std::string &name) const
+{
+    for (auto it = bufs_.rbegin(); it != bufs_.rend(); ++it)
+        if ((*it)->get_name() == name) return *it;
+    return nullptr;
+}
+std::string function::fresh_name(const std::string &prefix) { return prefix + std::to_string(counter_++); }
+void function::dump(bool) const
+{
+    for (auto *c : comps_) c->dump();
+}
+
+void init(std::string name)
+{
+    global::set_default_tiramisu_options();
+    global::set_implicit_function(new function(std::move(name)));   // lives for the generator's lifetime
+}
+void init() { init("foo"); }
+
+void codegen(const std::vector<buffer *> &arguments, const std::string obj_filename, bool gen_cuda_stmt)
+{
+    function *f = global::get_implicit_function();
+    if (!f) die("codegen() called before tiramisu::init()");
+    f->codegen(arguments, obj_filename, gen_cuda_stmt);
+}
+
+// ---- buffer -------------------------------------------------------------------------------------
+buffer::buffer() {}
+buffer::buffer(std::string name, std::vector<expr> dim_sizes, primitive_t type, argument_t argt, function *fct)
+    : name_(std::move(name)), dims_(std::move(dim_sizes)), dtype_(type), argt_(argt), fct_(fct)
+{
+    if (!fct_) die("buffer '" + name_ + "' declared before tiramisu::init()");
+    fct_->add_buffer(this);
+}
+
+static std::vector<var> prefix_iters(computation &C, const std::string &level)
+{
+    // the iteration variables of C's scheduled nest down to (and including) `level`
+    std::vector<var> out;
+    if (level.empty()) return out;
+    int d = C.find_dim(level);
+    if (d < 0) die("allocate_at/deallocate_at: '" + C.get_name() + "' has no loop level '" + level + "'");
+    for (int i = 0; i <= d; i++) out.push_back(var(C.dims()[i].name, C.dims()[i].lo, C.dims()[i].hi));
+    return out;
+}
+
+computation *buffer::allocate_at(computation &C, var level)
+{
+    auto_allocate_ = false;
+    auto *c = new computation(fct_->fresh_name("_allocate_" + name_ + "_"), prefix_iters(C, level.get_name()),
+                              expr(o_allocate, name_), true, p_none);
+    return fct_->own(c);
+}
+computation *buffer::allocate_at(computation &C, int level)
+{
+    if (level < 0) return allocate_at(C, computation::root);
+    return allocate_at(C, var(C.dims().at(level).name));
+}
+computation *buffer::deallocate_at(computation &C, var level)
+{
+    auto *c = new computation(fct_->fresh_name("_free_" + name_ + "_"), prefix_iters(C, level.get_name()),
+                              expr(o_free, name_), true, p_none);
+    return fct_->own(c);
+}
+void buffer::dump(bool) const { std::cerr << "buffer " << name_ << "\n"; }
+
+// ---- computation ----------------------------------------------------------------------------------
+const var computation::root("");
+
+computation::computation() {}
+
+void computation::construct(std::string name, std::vector<var> iters, expr e, bool schedule, primitive_t t)
+{
+    fct_ = global::get_implicit_function();
+    if (!fct_) die("computation declared before tiramisu::init()");
+    name_ = name.empty() ? fct_->fresh_name("_C") : std::move(name);
+    iters_ = std::move(iters);
+    expr_ = e;
+    scheduled_ = schedule;
+    dtype_ = t;
+    for (const var &v : iters_) {
+        loop_dim d;
+        d.name = v.get_name();
+        if (v.has_range()) { d.lo = v.get_lower(); d.hi = v.get_upper(); }
+        else if (schedule) die("iterator '" + v.get_name() + "' of computation '" + name_ + "' has no range");
+        dims_.push_back(d);
+    }
+    fct_->add_computation(this);
+}
+
+static primitive_t type_of(const expr &e)
+{
+    primitive_t t = e.get_data_type();
+    return t;
+}
+
+computation::computation(std::string name, std::vector<var> it, expr e, bool s, primitive_t t) { construct(name, it, e, s, t); }
+computation::computation(std::string name, std::vector<var> it, expr e, bool s) { construct(name, it, e, s, type_of(e)); }
+computation::computation(std::string name, std::vector<var> it, expr e) { construct(name, it, e, true, type_of(e)); }
+computation::computation(std::vector<var> it, expr e) { construct("", it, e, true, type_of(e)); }
+computation::computation(std::vector<var> it, expr e, bool s) { construct("", it, e, s, type_of(e)); }
+computation::computation(std::string name, std::vector<var> it, primitive_t t) { construct(name, it, expr(), true, t); }
+computation::computation(std::vector<var> it, primitive_t t) { construct("", it, expr(), true, t); }
+computation::computation(std::string name, std::vector<var> it, expr pred, expr e) { construct(name, it, e, true, type_of(e)); predicate_ = pred; }
+computation::computation(std::vector<var> it, expr pred, expr e) { construct("", it, e, true, type_of(e)); predicate_ = pred; }
+
+void computation::set_expression(const expr &e)
+{
+    expr_ = e;
+    if (dtype_ == p_none) dtype_ = e.get_data_type();
+}
+
+expr computation::access_expr(const std::vector<expr> &idx)
+{
+    return expr(o_access, name_, idx, dtype_);
+}
+
+int computation::find_dim(const std::string &name) const
+{
+    for (size_t i = 0; i < dims_.size(); i++)
+        if (dims_[i].name == name) return (int) i;
+    return -1;
+}
+
+void computation::dump() const
+{
+    std::cerr << name_ << " [";
+    for (auto &d : dims_) std::cerr << " " << d.name << ":" << d.lo.to_str() << ".." << d.hi.to_str() << (d.tag ? "#" + std::to_string((int) d.tag) : "");
+    std::cerr << " ] = " << expr_.to_str() << "\n";
+}
+
+// -- Layer II
+static bool divisible(const expr &extent, int f)
+{
+    return extent.is_int_literal() && extent.get_int_val() % f == 0;
+}
+
+void computation::split(var L0, int f, var outer, var inner)
+{
+    int d = find_dim(L0.get_name());
+    if (d < 0) die("split: '" + name_ + "' has no loop level '" + L0.get_name() + "'");
+    if (f <= 0) die("split: non-positive factor");
+    loop_dim old = dims_[d];
+    expr extent = old.hi - old.lo;
+    loop_dim o, i;
+    o.name = outer.get_name(); o.lo = expr((int32_t) 0);
+    o.hi = divisible(extent, f) ? expr((int32_t) (extent.get_int_val() / f)) : (extent + (f - 1)) / f;
+    i.name = inner.get_name(); i.lo = expr((int32_t) 0); i.hi = expr((int32_t) f);
+    var vo(o.name), vi(i.name);
+    defs_.push_back({old.name, old.lo + (vo * f + vi)});
+    if (!divisible(extent, f)) guards_.push_back(var(old.name) < old.hi);
+    dims_[d] = o;
+    dims_.insert(dims_.begin() + d + 1, i);
+}
+void computation::split(var L0, int f) { split(L0, f, var(L0.get_name() + "_o"), var(L0.get_name() + "_i")); }
+
+void computation::interchange(var L0, var L1)
+{
+    int a = find_dim(L0.get_name()), b = find_dim(L1.get_name());
+    if (a < 0 || b < 0) die("interchange: '" + name_ + "' has no loop level '" + (a < 0 ? L0 : L1).get_name() + "'");
+    std::swap(dims_[a], dims_[b]);
+}
+
+void computation::tile(var L0, var L1, int sx, int sy, var o0, var o1, var i0, var i1)
+{
+    int a = find_dim(L0.get_name()), b = find_dim(L1.get_name());
+    if (a < 0 || b != a + 1) die("tile: levels '" + L0.get_name() + "','" + L1.get_name() + "' of '" + name_ + "' must be consecutive");
+    split(L0, sx, o0, i0);          // o0 i0 L1
+    split(L1, sy, o1, i1);          // o0 i0 o1 i1
+    interchange(i0, o1);            // o0 o1 i0 i1
+}
+void computation::tile(var L0, var L1, int sx, int sy)
+{
+    tile(L0, L1, sx, sy, var(L0.get_name() + "_o"), var(L1.get_name() + "_o"), var(L0.get_name() + "_i"), var(L1.get_name() + "_i"));
+}
+void computation::tile(var L0, var L1, var L2, int sx, int sy, int sz, var o0, var o1, var o2, var i0, var i1, var i2)
+{
+    int a = find_dim(L0.get_name()), b = find_dim(L1.get_name()), c = find_dim(L2.get_name());
+    if (a < 0 || b != a + 1 || c != a + 2) die("tile: three consecutive levels expected in '" + name_ + "'");
+    split(L0, sx, o0, i0);          // o0 i0 L1 L2
+    split(L1, sy, o1, i1);          // o0 i0 o1 i1 L2
+    split(L2, sz, o2, i2);          // o0 i0 o1 i1 o2 i2
+    interchange(i0, o1);            // o0 o1 i0 i1 o2 i2
+    interchange(i1, o2);            // o0 o1 i0 o2 i1 i2
+    interchange(i0, o2);            // o0 o1 o2 i0 i1 i2
+}
+void computation::tile(var L0, var L1, var L2, int sx, int sy, int sz)
+{
+    auto o = [](const var &v) { return var(v.get_name() + "_o"); };
+    auto i = [](const var &v) { return var(v.get_name() + "_i"); };
+    tile(L0, L1, L2, sx, sy, sz, o(L0), o(L1), o(L2), i(L0), i(L1), i(L2));
+}
+
+void computation::tag(const var &L, loop_dim::tag_t t)
+{
+    int d = find_dim(L.get_name());
+    if (d < 0) die("'" + name_ + "' has no loop level '" + L.get_name() + "' to tag");
+    dims_[d].tag = t;
+}
+void computation::tag_gpu_block_level(var a) { tag(a, loop_dim::gpu_block); }
+void computation::tag_gpu_block_level(var a, var b) { tag(a, loop_dim::gpu_block); tag(b, loop_dim::gpu_block); }
+void computation::tag_gpu_block_level(var a, var b, var c) { tag_gpu_block_level(a, b); tag(c, loop_dim::gpu_block); }
+void computation::tag_gpu_thread_level(var a) { tag(a, loop_dim::gpu_thread); }
+void computation::tag_gpu_thread_level(var a, var b) { tag(a, loop_dim::gpu_thread); tag(b, loop_dim::gpu_thread); }
+void computation::tag_gpu_thread_level(var a, var b, var c) { tag_gpu_thread_level(a, b); tag(c, loop_dim::gpu_thread); }
+void computation::tag_gpu_level(var a, var b) { tag_gpu_block_level(a); tag_gpu_thread_level(b); }
+void computation::tag_gpu_level(var a, var b, var c, var d) { tag_gpu_block_level(a, b); tag_gpu_thread_level(c, d); }
+void computation::tag_gpu_level(var a, var b, var c, var d, var e, var f) { tag_gpu_block_level(a, b, c); tag_gpu_thread_level(d, e, f); }
+
+void computation::gpu_tile(var L0, int sx, var o, var i) { split(L0, sx, o, i); tag_gpu_level(o, i); }
+void computation::gpu_tile(var L0, int sx) { gpu_tile(L0, sx, var(L0.get_name() + "_o"), var(L0.get_name() + "_i")); }
+void computation::gpu_tile(var L0, var L1, int sx, int sy, var o0, var o1, var i0, var i1)
+{
+    tile(L0, L1, sx, sy, o0, o1, i0, i1);
+    tag_gpu_level(o0, o1, i0, i1);
+}
+void computation::gpu_tile(var L0, var L1, int sx, int sy)
+{
+    gpu_tile(L0, L1, sx, sy, var(L0.get_name() + "_o"), var(L1.get_name() + "_o"), var(L0.get_name() + "_i"), var(L1.get_name() + "_i"));
+}
+void computation::gpu_tile(var L0, var L1, var L2, int sx, int sy, int sz, var o0, var o1, var o2, var i0, var i1, var i2)
+{
+    tile(L0, L1, L2, sx, sy, sz, o0, o1, o2, i0, i1, i2);
+    tag_gpu_level(o0, o1, o2, i0, i1, i2);
+}
+void computation::gpu_tile(var L0, var L1, var L2, int sx, int sy, int sz)
+{
+    auto o = [](const var &v) { return var(v.get_name() + "_o"); };
+    auto i = [](const var &v) { return var(v.get_name() + "_i"); };
+    gpu_tile(L0, L1, L2, sx, sy, sz, o(L0), o(L1), o(L2), i(L0), i(L1), i(L2));
+}
+
+void computation::parallelize(var L) { tag(L, loop_dim::parallel); }
+void computation::tag_parallel_level(var L) { tag(L, loop_dim::parallel); }
+void computation::tag_vector_level(var L, int v) { tag(L, loop_dim::vector); dims_[find_dim(L.get_name())].vec_len = v; }
+void computation::vectorize(var L, int v, var o, var i) { split(L, v, o, i); tag_vector_level(i, v); }
+void computation::vectorize(var L, int v) { vectorize(L, v, var(L.get_name() + "_o"), var(L.get_name() + "_i")); }
+void computation::tag_unroll_level(var L) { tag(L, loop_dim::unrolled); }
+void computation::unroll(var L, int f, var o, var i) { split(L, f, o, i); tag_unroll_level(i); }
+void computation::unroll(var L, int f) { unroll(L, f, var(L.get_name() + "_o"), var(L.get_name() + "_i")); }
+void computation::shift(var L0, int n)
+{
+    // iterate L0' = L0 + n over [lo+n, hi+n); the original iterator is L0' - n
+    int d = find_dim(L0.get_name());
+    if (d < 0) die("shift: '" + name_ + "' has no loop level '" + L0.get_name() + "'");
+    std::string nn = L0.get_name() + "_s";
+    defs_.push_back({dims_[d].name, var(nn) - n});
+    dims_[d].name = nn;
+    dims_[d].lo = dims_[d].lo + n;
+    dims_[d].hi = dims_[d].hi + n;
+}
+
+// -- ordering
+void computation::link_after(computation &before_this, const std::string &level_name, int level_index)
+{
+    if (&before_this == this) die("a computation cannot be ordered after itself: " + name_);
+    // splice: `before_this` keeps at most one successor; a later successor takes over the chain position
+    if (before_this.succ_ && before_this.succ_ != this) {
+        computation *old = before_this.succ_;
+        // this -> ... -> tail of this chain, then old follows it at root
+        computation *tail = this;
+        while (tail->succ_) tail = tail->succ_;
+        if (tail != old) {
+            tail->succ_ = old;
+            old->pred_ = tail;
+        }
+    }
+    if (pred_ && pred_ != &before_this) pred_->succ_ = nullptr;
+    before_this.succ_ = this;
+    pred_ = &before_this;
+    pred_level_ = level_name;
+    pred_level_index_ = level_index;
+}
+
+computation &computation::then(computation &next, var level)
+{
+    next.link_after(*this, level.get_name(), level.get_name().empty() ? -1 : -2);
+    return next;
+}
+computation &computation::then(computation &next, int level)
+{
+    next.link_after(*this, "", level);
+    return next;
+}
+void computation::after(computation &b, var level) { link_after(b, level.get_name(), level.get_name().empty() ? -1 : -2); }
+void computation::after(computation &b, int level) { link_after(b, "", level); }
+void computation::before(computation &a, var level) { a.after(*this, level); }
+void computation::between(computation &before_c, var before_l, computation &after_c, var after_l)
+{
+    after(before_c, before_l);
+    after_c.after(*this, after_l);
+}
+
+computation *computation::cache_shared(computation &inp, const var &, std::vector<int>, std::vector<expr>, bool)
+{
+    return &inp;
+}
+
+// -- Layer III
+void computation::set_access_exprs(buffer *b, std::vector<expr> idx)
+{
+    buf_ = b;
+    access_ = std::move(idx);
+}
+
+void computation::store_in(buffer *buff)
+{
+    std::vector<expr> idx;
+    int n = buff->get_n_dims();
+    if ((int) iters_.size() < n) die("store_in: '" + name_ + "' has fewer iterators than buffer '" + buff->get_name() + "' has dimensions");
+    for (int i = 0; i < n; i++) idx.push_back(expr::make_var(global::get_loop_iterator_data_type(), iters_[i].get_name()));
+    set_access_exprs(buff, idx);
+}
+void computation::store_in(buffer *buff, std::vector<expr> iterators) { set_access_exprs(buff, std::move(iterators)); }
+void computation::store_in(std::vector<expr> mapping, std::vector<expr> sizes)
+{
+    auto *b = fct_->own(new buffer("_" + name_ + "_buffer", sizes, dtype_, is_input_ ? a_input : a_temporary, fct_));
+    set_access_exprs(b, std::move(mapping));
+}
+
+buffer *computation::get_buffer()
+{
+    if (!buf_) {
+        // automatic data mapping: one buffer element per point of the original iteration box
+        std::vector<expr> sizes, idx;
+        for (const var &v : iters_) {
+            if (!v.has_range()) die("get_buffer: iterator '" + v.get_name() + "' of '" + name_ + "' has no range");
+            sizes.push_back(v.get_upper());
+            idx.push_back(expr::make_var(global::get_loop_iterator_data_type(), v.get_name()));
+        }
+        if (sizes.empty()) { sizes.push_back(expr((int32_t) 1)); idx.push_back(expr((int32_t) 0)); }
+        auto *b = fct_->own(new buffer("_" + name_ + "_buffer", sizes, dtype_, is_input_ ? a_input : a_output, fct_));
+        set_access_exprs(b, idx);
+    }
+    return buf_;
+}
+
+// ---- input / constant -----------------------------------------------------------------------------
+input::input(std::string name, std::vector<var> it, primitive_t t) { construct(name, it, expr(), false, t); is_input_ = true; }
+input::input(std::vector<var> it, primitive_t t) { construct("", it, expr(), false, t); is_input_ = true; }
+static std::vector<var> named_iters(const std::vector<std::string> &names, const std::vector<expr> &sizes)
+{
+    if (names.size() != sizes.size()) die("input: dimension names and sizes differ in number");
+    std::vector<var> v;
+    for (size_t i = 0; i < names.size(); i++) v.push_back(var(names[i], expr((int32_t) 0), sizes[i]));
+    return v;
+}
+input::input(std::string name, std::vector<std::string> names, std::vector<expr> sizes, primitive_t t)
+{
+    construct(name, named_iters(names, sizes), expr(), false, t);
+    is_input_ = true;
+}
+static std::vector<var> sized_iters(const std::vector<expr> &sizes)
+{
+    std::vector<var> v;
+    for (size_t i = 0; i < sizes.size(); i++) v.push_back(var("_d" + std::to_string(i), expr((int32_t) 0), sizes[i]));
+    return v;
+}
+Input::Input(std::string name, std::vector<expr> sizes, primitive_t t) : input(name, sized_iters(sizes), t) {}
+
+constant::constant(std::string name, const expr &e, primitive_t t, bool function_wide, computation *, int, function *)
+{
+    if (!function_wide) die("constant '" + name + "': only function-wide constants are supported");
+    construct(name, {}, e, false, t);
+    is_constant_ = true;
+}
+constant::constant(std::string name, const expr &e, primitive_t t, function *)
+{
+    construct(name, {}, e, false, t);
+    is_constant_ = true;
+}
+constant::constant(std::string name, const expr &e)
+{
+    construct(name, {}, e, false, e.get_data_type());
+    is_constant_ = true;
+}
+constant::operator expr() { return expr::make_var(dtype_, name_); }
+
+// ---- block ----------------------------------------------------------------------------------------
+block::block(const std::vector<computation *> ch) : children(ch) {}
+#define TB_FWD(call) do { for (computation *child_ : children) child_->call; } while (0)
+void block::gpu_tile(var a, var b, int x, int y) { TB_FWD(gpu_tile(a, b, x, y)); }
+void block::gpu_tile(var a, var b, int x, int y, var o0, var o1, var i0, var i1) { TB_FWD(gpu_tile(a, b, x, y, o0, o1, i0, i1)); }
+void block::gpu_tile(var a, var b, var c, int x, int y, int z) { TB_FWD(gpu_tile(a, b, c, x, y, z)); }
+void block::gpu_tile(var a, var b, var c, int x, int y, int z, var o0, var o1, var o2, var i0, var i1, var i2) { TB_FWD(gpu_tile(a, b, c, x, y, z, o0, o1, o2, i0, i1, i2)); }
+void block::interchange(var a, var b) { TB_FWD(interchange(a, b)); }
+void block::parallelize(var a) { TB_FWD(parallelize(a)); }
+void block::shift(var a, int n) { TB_FWD(shift(a, n)); }
+void block::split(var a, int x) { TB_FWD(split(a, x)); }
+void block::split(var a, int x, var o, var i) { TB_FWD(split(a, x, o, i)); }
+void block::tile(var a, var b, int x, int y) { TB_FWD(tile(a, b, x, y)); }
+void block::tile(var a, var b, int x, int y, var o0, var o1, var i0, var i1) { TB_FWD(tile(a, b, x, y, o0, o1, i0, i1)); }
+void block::tile(var a, var b, var c, int x, int y, int z) { TB_FWD(tile(a, b, c, x, y, z)); }
+void block::tile(var a, var b, var c, int x, int y, int z, var o0, var o1, var o2, var i0, var i1, var i2) { TB_FWD(tile(a, b, c, x, y, z, o0, o1, o2, i0, i1, i2)); }
+void block::tag_gpu_level(var a, var b) { TB_FWD(tag_gpu_level(a, b)); }
+void block::tag_gpu_level(var a, var b, var c, var d) { TB_FWD(tag_gpu_level(a, b, c, d)); }
+void block::unroll(var a, int f) { TB_FWD(unroll(a, f)); }
+void block::unroll(var a, int f, var o, var i) { TB_FWD(unroll(a, f, o, i)); }
+void block::vectorize(var a, int v) { TB_FWD(vectorize(a, v)); }
+void block::vectorize(var a, int v, var o, var i) { TB_FWD(vectorize(a, v, o, i)); }
+#undef TB_FWD
+
+}  // namespace tiramisu

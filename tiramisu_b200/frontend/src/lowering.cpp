@@ -1,0 +1,951 @@
+// lowering.cpp — `tiramisu::codegen(args, "x.o", true)` for sm_100a.
+//
+// Replaces the reference's generator-time back end for GPU functions: the cuda_ast emitter
+// (/root/reference/src/tiramisu_codegen_cuda.cpp: kernel extraction :548-640, kernel wrappers
+// :855-866, nvcc driver :1100-1200) and the Halide host-code generator
+// (/root/reference/src/tiramisu_codegen_halide.cpp:2488-2603 temporaries, :1840-1859 runtime calls).
+//
+// Pipeline (all of it this file):
+//   1. order the scheduled computations by their then()/after() chain;
+//   2. build ONE loop tree: consecutive computations share the loops down to their fuse level, a
+//      shared loop takes the union of the ranges and every statement re-checks its own range;
+//   3. every outermost gpu-tagged loop becomes a kernel; block/thread loops become blockIdx/threadIdx
+//      (x,y,z from the innermost tagged loop outwards, like the reference) so the innermost — unit
+//      stride — iterator is threadIdx.x and global accesses coalesce; shared/local/register buffers
+//      become __shared__ / per-thread arrays; read-only global buffers are `const __restrict__`;
+//   4. pattern lowering: a kernel that is exactly one fp32 contraction C(i,j) += A(i,k)*B(k,j) over
+//      row-major global buffers is not emitted as SIMT code at all — it becomes a call of the
+//      runtime's tcgen05 GEMM entry point (tiramisu_cublas_sgemm in libtiramisu_b200.so);
+//   5. the host function keeps the reference ABI `extern "C" int f(halide_buffer_t*...)`; copies,
+//      allocation, synchronisation and launches go through the tiramisu_cuda_* runtime;
+//   6. nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (x86 Tiramisu code has no FMA
+//      contraction, src/tiramisu_codegen_halide.cpp:3988-3995) compiles the result to the object.
+#include <tiramisu/core.h>
+
+#include <algorithm>
+#include <cinttypes>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+
+namespace tiramisu {
+namespace {
+
+[[noreturn]] void die(const std::string &msg)
+{
+    std::cerr << "tiramisu_b200 lowering: " << msg << std::endl;
+    std::exit(1);
+}
+
+std::string san(const std::string &s)
+{
+    std::string o;
+    for (char c : s) o += (isalnum((unsigned char) c) || c == '_') ? c : '_';
+    return o;
+}
+
+const char *ctype(primitive_t t)
+{
+    switch (t) {
+    case p_uint8: return "uint8_t"; case p_int8: return "int8_t"; case p_uint16: return "uint16_t"; case p_int16: return "int16_t";
+    case p_uint32: return "uint32_t"; case p_int32: return "int32_t"; case p_uint64: return "uint64_t"; case p_int64: return "int64_t";
+    case p_float32: return "float"; case p_float64: return "double"; case p_boolean: return "bool";
+    default: return "uint8_t";
+    }
+}
+
+struct Node {
+    bool is_loop = false;
+    // loop
+    int id = 0;
+    std::string dim_name;
+    expr lo, hi;
+    loop_dim::tag_t tag = loop_dim::none;
+    int axis = -1;               // gpu axis (0 = x)
+    bool launch_guard = false;   // launch dimension may exceed this loop's extent
+    std::vector<std::unique_ptr<Node>> kids;
+    // statement
+    computation *comp = nullptr;
+    std::vector<Node *> path;    // enclosing loops, outermost first (one per scheduled dimension)
+    std::string cname() const { return "v" + std::to_string(id) + "_" + san(dim_name); }
+};
+
+struct Kernel {
+    Node *root = nullptr;
+    std::string name;
+    std::vector<Node *> host_loops;        // enclosing host loops (passed by value)
+    std::set<std::string> constants;       // function constants referenced
+    std::vector<buffer *> globals;         // global buffers referenced, first-use order
+    std::set<buffer *> written;
+    std::vector<buffer *> locals;          // shared / local / register buffers
+    expr grid[3], block[3];
+};
+
+class Lowering {
+public:
+    Lowering(function *f, const std::vector<buffer *> &args, bool cuda) : f_(f), args_(args), cuda_(cuda) {}
+    std::string run();
+
+private:
+    function *f_;
+    std::vector<buffer *> args_;
+    bool cuda_;
+    Node root_;
+    int next_id_ = 0;
+    int next_kernel_ = 0;
+    std::map<std::string, computation *> constants_;
+    std::vector<computation *> constant_order_;
+    std::ostringstream kernels_;            // device code
+    std::ostringstream protos_;             // extern "C" prototypes of o_call targets
+    std::set<std::string> proto_seen_;
+    bool pattern_ = true;
+    // index simplification context of the statement being emitted
+    using Env = std::map<std::string, std::pair<int64_t, int64_t>>;   // loop dimension -> inclusive [lo, hi]
+    const computation *cur_ = nullptr;
+    Env env_;
+    expr inline_defs(const expr &e) const;
+    static bool bounds(const expr &e, const Env &env, int64_t &lo, int64_t &hi);
+    static expr simp(const expr &e, const Env &env);
+    void enter_stmt(computation *c);
+
+    // 1-2
+    std::vector<computation *> order();
+    void build_tree(const std::vector<computation *> &ord);
+    // 3
+    void assign_axes(Node *n);
+    int count_below(const Node *n, loop_dim::tag_t t) const;
+    void collect_kernel(Node *n, Kernel &k, bool inside);
+    void note_expr(const expr &e, Kernel &k, bool is_store_target);
+    buffer *buffer_of_access(const expr &e, computation **who = nullptr);
+    // printing
+    std::string print(const expr &e, bool device);
+    std::string print_access(const expr &e, bool device);
+    std::string lin_index(buffer *b, const std::vector<expr> &idx, bool device);
+    std::string literal(const expr &e);
+    std::string bytes_of(buffer *b, bool device);
+    // emission
+    void emit_host(Node *n, std::ostringstream &os, int ind, std::vector<Node *> &host_loops);
+    void emit_host_stmt(Node *n, std::ostringstream &os, int ind);
+    void emit_kernel(Node *n, std::ostringstream &host, int ind, std::vector<Node *> &host_loops);
+    void emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind);
+    void emit_assignment(Node *n, std::ostringstream &os, int ind, bool device);
+    void emit_bindings(Node *n, std::ostringstream &os, int ind, std::vector<std::string> &conds, bool device);
+    bool try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind);
+    void need_proto(const expr &call);
+};
+
+std::string pad(int n) { return std::string((size_t) n * 4, ' '); }
+
+// ------------------------------------------------------------------------------------------------ order
+std::vector<computation *> Lowering::order()
+{
+    std::vector<computation *> ord;
+    std::set<computation *> seen;
+    for (computation *c : f_->get_computations()) {
+        if (c->is_input() || c->is_constant() || !c->should_schedule_this_computation()) continue;
+        if (c->pred() != nullptr) continue;
+        for (computation *p = c; p; p = p->succ()) {
+            if (!seen.insert(p).second) die("cycle in the then()/after() order at '" + p->get_name() + "'");
+            ord.push_back(p);
+        }
+    }
+    for (computation *c : f_->get_computations())
+        if (!c->is_input() && !c->is_constant() && c->should_schedule_this_computation() && !seen.count(c))
+            die("computation '" + c->get_name() + "' is not reachable in the then()/after() order");
+    return ord;
+}
+
+static expr union_lo(const expr &a, const expr &b) { return a.is_equal(b) ? a : expr(o_min, a, b); }
+static expr union_hi(const expr &a, const expr &b) { return a.is_equal(b) ? a : expr(o_max, a, b); }
+
+void Lowering::build_tree(const std::vector<computation *> &ord)
+{
+    std::vector<Node *> open;
+    computation *prev = nullptr;
+    for (computation *c : ord) {
+        if (!c->get_expr().is_defined()) die("computation '" + c->get_name() + "' has no expression");
+        auto &dims = c->dims();
+        int depth = 0;
+        if (prev && c->pred() == prev) {
+            if (c->pred_level_index() >= 0) depth = c->pred_level_index() + 1;
+            else if (c->pred_level_index() == -2) {
+                int d = c->find_dim(c->pred_level());
+                if (d < 0) d = prev->find_dim(c->pred_level());
+                if (d < 0) die("'" + c->get_name() + "' is ordered after '" + prev->get_name() + "' at unknown level '" + c->pred_level() + "'");
+                depth = d + 1;
+            }
+        }
+        if (depth > (int) open.size() || depth > (int) dims.size())
+            die("'" + c->get_name() + "' cannot share " + std::to_string(depth) + " loops with '" + (prev ? prev->get_name() : "") + "'");
+        open.resize(depth);
+        for (int d = 0; d < depth; d++) {
+            Node *n = open[d];
+            n->lo = union_lo(n->lo, dims[d].lo);
+            n->hi = union_hi(n->hi, dims[d].hi);
+            if (n->tag == loop_dim::none) n->tag = dims[d].tag;
+        }
+        for (int d = depth; d < (int) dims.size(); d++) {
+            auto n = std::make_unique<Node>();
+            n->is_loop = true; n->id = next_id_++; n->dim_name = dims[d].name;
+            n->lo = dims[d].lo; n->hi = dims[d].hi; n->tag = dims[d].tag;
+            Node *raw = n.get();
+            (open.empty() ? &root_ : open.back())->kids.push_back(std::move(n));
+            open.push_back(raw);
+        }
+        auto s = std::make_unique<Node>();
+        s->comp = c; s->path = open; s->id = next_id_++;
+        (open.empty() ? &root_ : open.back())->kids.push_back(std::move(s));
+        prev = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ gpu axes
+int Lowering::count_below(const Node *n, loop_dim::tag_t t) const
+{
+    int best = 0;
+    for (auto &k : n->kids) {
+        if (!k->is_loop) continue;
+        int c = count_below(k.get(), t) + (k->tag == t ? 1 : 0);
+        best = std::max(best, c);
+    }
+    return best;
+}
+
+void Lowering::assign_axes(Node *n)
+{
+    if (n->is_loop && (n->tag == loop_dim::gpu_block || n->tag == loop_dim::gpu_thread)) {
+        n->axis = count_below(n, n->tag);
+        if (n->axis > 2) die("more than three nested gpu " + std::string(n->tag == loop_dim::gpu_block ? "block" : "thread") + " levels at '" + n->dim_name + "'");
+    }
+    for (auto &k : n->kids) assign_axes(k.get());
+}
+
+buffer *Lowering::buffer_of_access(const expr &e, computation **who)
+{
+    computation *c = f_->find_computation(e.get_name());
+    if (!c) die("access to unknown computation '" + e.get_name() + "'");
+    if (who) *who = c;
+    if (c->is_constant()) return nullptr;
+    return c->get_buffer();
+}
+
+void Lowering::note_expr(const expr &e, Kernel &k, bool)
+{
+    if (!e.is_defined()) return;
+    if (e.get_expr_type() == e_var) {
+        if (constants_.count(e.get_name())) k.constants.insert(e.get_name());
+        return;
+    }
+    if (e.get_expr_type() != e_op) return;
+    if (e.get_op_type() == o_access) {
+        computation *c = nullptr;
+        buffer *b = buffer_of_access(e, &c);
+        if (!b) k.constants.insert(c->get_name());
+        else {
+            auto loc = b->get_location();
+            auto &list = (loc == mem_loc::gpu_global || loc == mem_loc::gpu_constant || loc == mem_loc::host) ? k.globals : k.locals;
+            if (std::find(list.begin(), list.end(), b) == list.end()) list.push_back(b);
+            for (const expr &d : b->get_dim_sizes()) note_expr(d, k, false);
+            for (const expr &a : c->access()) note_expr(a, k, false);
+        }
+    }
+    if (e.get_op_type() == o_allocate || e.get_op_type() == o_buffer) {
+        buffer *b = f_->find_buffer(e.get_name());
+        if (b && (b->get_location() == mem_loc::gpu_shared || b->get_location() == mem_loc::gpu_local || b->get_location() == mem_loc::gpu_register))
+            if (std::find(k.locals.begin(), k.locals.end(), b) == k.locals.end()) k.locals.push_back(b);
+    }
+    for (const expr &o : e.get_operands()) note_expr(o, k, false);
+}
+
+void Lowering::collect_kernel(Node *n, Kernel &k, bool)
+{
+    if (n->is_loop) {
+        note_expr(n->lo, k, false);
+        note_expr(n->hi, k, false);
+        for (auto &c : n->kids) collect_kernel(c.get(), k, true);
+        return;
+    }
+    computation *c = n->comp;
+    note_expr(c->get_expr(), k, false);
+    note_expr(c->get_predicate(), k, false);
+    for (auto &d : c->dims()) { note_expr(d.lo, k, false); note_expr(d.hi, k, false); }
+    for (auto &d : c->defs()) note_expr(d.second, k, false);
+    for (auto &g : c->guards()) note_expr(g, k, false);
+    const expr &e = c->get_expr();
+    bool is_stmt_only = e.get_expr_type() == e_sync || (e.get_expr_type() == e_op && (e.get_op_type() == o_allocate || e.get_op_type() == o_free));
+    if (!is_stmt_only) {
+        buffer *b = c->get_buffer();
+        auto loc = b->get_location();
+        auto &list = (loc == mem_loc::gpu_shared || loc == mem_loc::gpu_local || loc == mem_loc::gpu_register) ? k.locals : k.globals;
+        if (std::find(list.begin(), list.end(), b) == list.end()) list.push_back(b);
+        k.written.insert(b);
+        for (const expr &d : b->get_dim_sizes()) note_expr(d, k, false);
+        for (const expr &a : c->access()) note_expr(a, k, false);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ index simplification
+// After split/tile an original iterator is `outer * f + inner`; Layer-III accesses such as
+// `acc[i % 4][j % 4]` must fold to `acc[i1][j1]` so that per-thread arrays stay in registers once the
+// inner loops are unrolled.  Everything here assumes non-negative terms (checked through `bounds`).
+void Lowering::enter_stmt(computation *c)
+{
+    cur_ = c;
+    env_.clear();
+    if (!c) return;
+    for (auto &d : c->dims())
+        if (d.lo.is_int_literal() && d.hi.is_int_literal() && d.hi.get_int_val() > d.lo.get_int_val())
+            env_[d.name] = {d.lo.get_int_val(), d.hi.get_int_val() - 1};
+        else if (d.lo.is_int_literal() && d.lo.get_int_val() >= 0)
+            env_[d.name] = {d.lo.get_int_val(), INT64_MAX / 4};
+}
+
+expr Lowering::inline_defs(const expr &e) const
+{
+    if (!cur_) return e;
+    expr r = e;
+    for (auto &d : cur_->defs()) r = r.substitute({d.first}, {d.second});
+    return r;
+}
+
+bool Lowering::bounds(const expr &e, const Env &env, int64_t &lo, int64_t &hi)
+{
+    if (!e.is_defined()) return false;
+    if (e.is_int_literal()) { lo = hi = e.get_int_val(); return true; }
+    if (e.get_expr_type() == e_var) {
+        auto it = env.find(e.get_name());
+        if (it == env.end()) return false;
+        lo = it->second.first; hi = it->second.second;
+        return true;
+    }
+    if (e.get_expr_type() != e_op || e.get_n_arg() != 2) return false;
+    int64_t al, ah, bl, bh;
+    if (!bounds(e.get_operand(0), env, al, ah) || !bounds(e.get_operand(1), env, bl, bh)) return false;
+    const int64_t big = INT64_MAX / 4;
+    auto sat = [&](__int128 v) { return (int64_t) (v > big ? big : (v < -big ? -big : v)); };
+    switch (e.get_op_type()) {
+    case o_add: lo = sat((__int128) al + bl); hi = sat((__int128) ah + bh); return true;
+    case o_sub: lo = sat((__int128) al - bh); hi = sat((__int128) ah - bl); return true;
+    case o_mul: {
+        __int128 c[4] = {(__int128) al * bl, (__int128) al * bh, (__int128) ah * bl, (__int128) ah * bh};
+        __int128 mn = c[0], mx = c[0];
+        for (auto v : c) { mn = v < mn ? v : mn; mx = v > mx ? v : mx; }
+        lo = sat(mn); hi = sat(mx);
+        return true;
+    }
+    case o_div: if (bl != bh || bl <= 0 || al < 0) return false; lo = al / bl; hi = ah / bl; return true;
+    case o_mod: if (bl != bh || bl <= 0 || al < 0) return false; if (ah < bl) { lo = al; hi = ah; } else { lo = 0; hi = bl - 1; } return true;
+    default: return false;
+    }
+}
+
+static void flatten_sum(const expr &e, std::vector<expr> &terms)
+{
+    if (e.get_expr_type() == e_op && e.get_op_type() == o_add) {
+        flatten_sum(e.get_operand(0), terms);
+        flatten_sum(e.get_operand(1), terms);
+    } else terms.push_back(e);
+}
+
+// term = q * c exactly?  returns q
+static bool multiple_of(const expr &t, int64_t c, expr &q)
+{
+    if (t.is_int_literal()) { if (t.get_int_val() % c) return false; q = value_cast_i(t.get_data_type(), t.get_int_val() / c); return true; }
+    if (t.get_expr_type() == e_op && t.get_op_type() == o_mul) {
+        for (int s = 0; s < 2; s++) {
+            const expr &l = t.get_operand(s), &o = t.get_operand(1 - s);
+            if (l.is_int_literal() && l.get_int_val() % c == 0) { q = o * value_cast_i(l.get_data_type(), l.get_int_val() / c); return true; }
+            expr inner;
+            if (multiple_of(o, c, inner)) { q = inner * l; return true; }
+        }
+    }
+    return false;
+}
+
+expr Lowering::simp(const expr &e, const Env &env)
+{
+    if (!e.is_defined() || e.get_expr_type() != e_op) return e;
+    op_t o = e.get_op_type();
+    if (o == o_access || o == o_call || o == o_buffer || o == o_allocate || o == o_free || o == o_memcpy) return e;
+    std::vector<expr> ops;
+    for (const expr &x : e.get_operands()) ops.push_back(simp(x, env));
+    if ((o == o_mod || o == o_div) && ops[1].is_int_literal() && ops[1].get_int_val() > 0 && is_int_type(e.get_data_type())) {
+        const int64_t c = ops[1].get_int_val();
+        int64_t lo, hi;
+        if (bounds(ops[0], env, lo, hi) && lo >= 0 && hi < c) return o == o_mod ? ops[0] : value_cast_i(e.get_data_type(), 0);
+        std::vector<expr> terms, rest, quot;
+        flatten_sum(ops[0], terms);
+        bool nonneg = true;
+        for (const expr &t : terms) {
+            int64_t tl, th;
+            if (!bounds(t, env, tl, th) || tl < 0) { nonneg = false; break; }
+            expr q;
+            if (multiple_of(t, c, q)) quot.push_back(q); else rest.push_back(t);
+        }
+        if (nonneg && !quot.empty()) {
+            expr r;
+            for (const expr &t : rest) r = r.is_defined() ? r + t : t;
+            if (o == o_mod) return r.is_defined() ? simp(expr(o_mod, r, ops[1]), env) : value_cast_i(e.get_data_type(), 0);
+            expr qs;
+            for (const expr &t : quot) qs = qs.is_defined() ? qs + t : t;
+            if (r.is_defined()) {
+                expr rq = simp(expr(o_div, r, ops[1]), env);
+                if (!(rq.is_int_literal() && rq.get_int_val() == 0)) qs = qs + rq;
+            }
+            return qs;
+        }
+    }
+    switch (o) {
+    case o_cast: return expr(o_cast, e.get_data_type(), ops[0]);
+    default:
+        if (ops.size() == 1) return expr(o, ops[0]);
+        if (ops.size() == 2) return expr(o, ops[0], ops[1]);
+        if (ops.size() == 3) return expr(o, ops[0], ops[1], ops[2]);
+        return e;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ printing
+std::string Lowering::literal(const expr &e)
+{
+    primitive_t t = e.get_data_type();
+    char buf[96];
+    if (t == p_float32) {
+        float v = (float) e.get_double_val();
+        if (v != v) return "__int_as_float(0x7fc00000)";
+        snprintf(buf, sizeof buf, "%af", (double) v);
+        return buf;
+    }
+    if (t == p_float64) { snprintf(buf, sizeof buf, "%a", e.get_double_val()); return buf; }
+    if (t == p_boolean) return e.get_int_val() ? "true" : "false";
+    if (t == p_int32) { snprintf(buf, sizeof buf, "%" PRId64, e.get_int_val()); return e.get_int_val() < 0 ? "(" + std::string(buf) + ")" : buf; }
+    if (t == p_int64) { snprintf(buf, sizeof buf, "((int64_t) %" PRId64 "LL)", e.get_int_val()); return buf; }
+    if (t == p_uint64) { snprintf(buf, sizeof buf, "((uint64_t) %" PRIu64 "ULL)", (uint64_t) e.get_int_val()); return buf; }
+    snprintf(buf, sizeof buf, "((%s) %" PRId64 ")", ctype(t), e.get_int_val());
+    return buf;
+}
+
+std::string Lowering::lin_index(buffer *b, const std::vector<expr> &idx, bool device)
+{
+    const auto &dims = b->get_dim_sizes();
+    if (idx.size() != dims.size())
+        die("buffer '" + b->get_name() + "' has " + std::to_string(dims.size()) + " dimensions but is accessed with " + std::to_string(idx.size()) + " indices");
+    bool small = b->get_location() == mem_loc::gpu_shared || b->get_location() == mem_loc::gpu_local || b->get_location() == mem_loc::gpu_register;
+    if (b->get_location() == mem_loc::gpu_register) {
+        // a register buffer of one element is a scalar: the index only names which value it holds
+        // (generator1.cpp stores c_A(i, k) in b_A_reg{1} at {i % R_BLOCK_I})
+        int64_t total = 1;
+        for (const expr &d : dims) total = d.is_int_literal() ? total * d.get_int_val() : 0;
+        if (total == 1) return "0";
+    }
+    std::string s;
+    for (size_t d = 0; d < idx.size(); d++) {
+        std::string e = print(cur_ ? simp(inline_defs(idx[d]), env_) : idx[d], device);
+        if (d == 0) s = small ? e : "(int64_t) " + e;
+        else s = "(" + s + ") * " + print(dims[d], device) + " + " + e;
+    }
+    return s;
+}
+
+std::string Lowering::print_access(const expr &e, bool device)
+{
+    computation *c = nullptr;
+    buffer *b = buffer_of_access(e, &c);
+    if (!b) return "c_" + san(c->get_name());
+    const auto &iters = c->get_iteration_variables();
+    if ((int) iters.size() != e.get_n_arg())
+        die("'" + c->get_name() + "' has " + std::to_string(iters.size()) + " iterators but is accessed with " + std::to_string(e.get_n_arg()) + " indices");
+    std::vector<std::string> names;
+    for (const var &v : iters) names.push_back(v.get_name());
+    std::vector<expr> idx;
+    for (const expr &a : c->access()) idx.push_back(a.substitute(names, e.get_operands()));
+    auto loc = b->get_location();
+    bool dev_buf = loc != mem_loc::host;
+    if (device && !dev_buf) die("kernel code reads host buffer '" + b->get_name() + "' (through '" + c->get_name() + "'): tag it gpu_global and copy it");
+    if (!device && dev_buf) die("host code accesses device buffer '" + b->get_name() + "' (through '" + c->get_name() + "')");
+    return "b_" + san(b->get_name()) + "[" + lin_index(b, idx, device) + "]";
+}
+
+static const char *math_fn(op_t o, bool f32)
+{
+    switch (o) {
+    case o_floor: return f32 ? "floorf" : "floor"; case o_ceil: return f32 ? "ceilf" : "ceil";
+    case o_round: return f32 ? "roundf" : "round"; case o_trunc: return f32 ? "truncf" : "trunc";
+    case o_sqrt: return f32 ? "sqrtf" : "sqrt"; case o_expo: return f32 ? "expf" : "exp"; case o_log: return f32 ? "logf" : "log";
+    case o_sin: return f32 ? "sinf" : "sin"; case o_cos: return f32 ? "cosf" : "cos"; case o_tan: return f32 ? "tanf" : "tan";
+    case o_asin: return f32 ? "asinf" : "asin"; case o_acos: return f32 ? "acosf" : "acos"; case o_atan: return f32 ? "atanf" : "atan";
+    case o_sinh: return f32 ? "sinhf" : "sinh"; case o_cosh: return f32 ? "coshf" : "cosh"; case o_tanh: return f32 ? "tanhf" : "tanh";
+    case o_asinh: return f32 ? "asinhf" : "asinh"; case o_acosh: return f32 ? "acoshf" : "acosh"; case o_atanh: return f32 ? "atanhf" : "atanh";
+    default: return nullptr;
+    }
+}
+
+void Lowering::need_proto(const expr &call)
+{
+    const std::string &n = call.get_name();
+    if (n.rfind("tiramisu_", 0) == 0 || !proto_seen_.insert(n).second) return;
+    protos_ << "extern \"C\" " << (call.get_data_type() == p_none ? "void" : ctype(call.get_data_type())) << " " << n << "(";
+    for (int i = 0; i < call.get_n_arg(); i++) {
+        const expr &a = call.get_operand(i);
+        protos_ << (i ? ", " : "") << ((a.get_expr_type() == e_op && a.get_op_type() == o_buffer) ? "void *" : ctype(a.get_data_type()));
+    }
+    protos_ << ");\n";
+}
+
+std::string Lowering::print(const expr &e, bool device)
+{
+    if (!e.is_defined()) die("undefined expression reached the code generator");
+    switch (e.get_expr_type()) {
+    case e_val: return literal(e);
+    case e_var: return (constants_.count(e.get_name()) ? "c_" : "i_") + san(e.get_name());
+    case e_sync: return "__syncthreads()";
+    default: break;
+    }
+    op_t o = e.get_op_type();
+    primitive_t t = e.get_data_type();
+    auto A = [&](int i) { return print(e.get_operand(i), device); };
+    auto narrow = [&](const std::string &s) {   // C++ promotes narrow integers to int: re-wrap to the expression's type
+        return (is_int_type(t) && type_bits(t) < 32 && t != p_boolean) ? "((" + std::string(ctype(t)) + ") " + s + ")" : s;
+    };
+    switch (o) {
+    case o_add: return narrow("(" + A(0) + " + " + A(1) + ")");
+    case o_sub: return narrow("(" + A(0) + " - " + A(1) + ")");
+    case o_mul: return narrow("(" + A(0) + " * " + A(1) + ")");
+    case o_div: return narrow("(" + A(0) + " / " + A(1) + ")");
+    case o_mod: return is_float_type(t) ? std::string(t == p_float32 ? "fmodf(" : "fmod(") + A(0) + ", " + A(1) + ")" : narrow("(" + A(0) + " % " + A(1) + ")");
+    case o_logical_and: return "(" + A(0) + " && " + A(1) + ")";
+    case o_logical_or: return "(" + A(0) + " || " + A(1) + ")";
+    case o_logical_not: return "(!" + A(0) + ")";
+    case o_eq: return "(" + A(0) + " == " + A(1) + ")";
+    case o_ne: return "(" + A(0) + " != " + A(1) + ")";
+    case o_le: return "(" + A(0) + " <= " + A(1) + ")";
+    case o_lt: return "(" + A(0) + " < " + A(1) + ")";
+    case o_ge: return "(" + A(0) + " >= " + A(1) + ")";
+    case o_gt: return "(" + A(0) + " > " + A(1) + ")";
+    case o_max: return "tb_max<" + std::string(ctype(t)) + ">(" + A(0) + ", " + A(1) + ")";
+    case o_min: return "tb_min<" + std::string(ctype(t)) + ">(" + A(0) + ", " + A(1) + ")";
+    case o_right_shift: return narrow("(" + A(0) + " >> " + A(1) + ")");
+    case o_left_shift: return narrow("(" + A(0) + " << " + A(1) + ")");
+    case o_minus: return narrow("(-" + A(0) + ")");
+    case o_abs: return is_float_type(t) ? std::string(t == p_float32 ? "fabsf(" : "fabs(") + A(0) + ")" : "tb_abs<" + std::string(ctype(t)) + ">(" + A(0) + ")";
+    case o_cast: return "((" + std::string(ctype(t)) + ") " + A(0) + ")";
+    case o_select: case o_cond: return "(" + A(0) + " ? " + A(1) + " : " + A(2) + ")";
+    case o_lerp: return "(" + A(0) + " + (" + A(1) + " - " + A(0) + ") * " + A(2) + ")";
+    case o_access: return print_access(e, device);
+    case o_buffer: {
+        buffer *b = f_->find_buffer(e.get_name());
+        if (!b) die("unknown buffer '" + e.get_name() + "'");
+        return "b_" + san(b->get_name());
+    }
+    case o_call: {
+        need_proto(e);
+        std::string s = e.get_name() + "(";
+        for (int i = 0; i < e.get_n_arg(); i++) s += (i ? ", " : "") + A(i);
+        return s + ")";
+    }
+    default: break;
+    }
+    if (const char *fn = math_fn(o, t == p_float32)) return std::string(fn) + "(" + A(0) + ")";
+    die("operator " + std::to_string((int) o) + " is not supported by the sm_100a lowering (in " + e.to_str() + ")");
+}
+
+std::string Lowering::bytes_of(buffer *b, bool device)
+{
+    std::string s = "(uint64_t) sizeof(" + std::string(ctype(b->get_elements_type())) + ")";
+    for (const expr &d : b->get_dim_sizes()) s += " * (uint64_t) " + print(d, device);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ statements
+void Lowering::emit_bindings(Node *n, std::ostringstream &os, int ind, std::vector<std::string> &conds, bool device)
+{
+    computation *c = n->comp;
+    auto &dims = c->dims();
+    const std::string it = ctype(global::get_loop_iterator_data_type());
+    for (size_t d = 0; d < dims.size(); d++) {
+        Node *l = n->path[d];
+        os << pad(ind) << "const " << it << " i_" << san(dims[d].name) << " = " << l->cname() << ";\n";
+        if (!dims[d].lo.is_equal(l->lo)) conds.push_back("i_" + san(dims[d].name) + " >= " + print(dims[d].lo, device));
+        if (!dims[d].hi.is_equal(l->hi) || l->launch_guard) conds.push_back("i_" + san(dims[d].name) + " < " + print(dims[d].hi, device));
+    }
+    const auto &defs = c->defs();
+    for (auto it2 = defs.rbegin(); it2 != defs.rend(); ++it2)
+        os << pad(ind) << "const " << it << " i_" << san(it2->first) << " = " << print(it2->second, device) << ";\n";
+    for (const expr &g : c->guards()) conds.push_back(print(g, device));
+    if (c->get_predicate().is_defined()) conds.push_back(print(c->get_predicate(), device));
+}
+
+void Lowering::emit_assignment(Node *n, std::ostringstream &os, int ind, bool device)
+{
+    computation *c = n->comp;
+    os << pad(ind) << "{   // " << c->get_name() << "\n";
+    std::vector<std::string> conds;
+    emit_bindings(n, os, ind + 1, conds, device);
+    enter_stmt(c);
+    buffer *b = c->get_buffer();
+    bool dev_buf = b->get_location() != mem_loc::host;
+    if (device != dev_buf)
+        die("'" + c->get_name() + "' runs on the " + (device ? "device" : "host") + " but stores into " + (dev_buf ? "device" : "host") + " buffer '" + b->get_name() + "'");
+    std::vector<std::string> names;
+    for (const var &v : c->get_iteration_variables()) names.push_back(v.get_name());
+    std::string lhs = "b_" + san(b->get_name()) + "[" + lin_index(b, c->access(), device) + "]";
+    std::string rhs = print(c->get_expr(), device);
+    std::string cond;
+    for (size_t i = 0; i < conds.size(); i++) cond += (i ? " && " : "") + conds[i];
+    os << pad(ind + 1) << (cond.empty() ? "" : "if (" + cond + ") ") << lhs << " = (" << ctype(b->get_elements_type()) << ") " << rhs << ";\n";
+    os << pad(ind) << "}\n";
+    enter_stmt(nullptr);
+}
+
+void Lowering::emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind)
+{
+    if (n->is_loop) {
+        const std::string it = ctype(global::get_loop_iterator_data_type());
+        const char *ax[] = {"x", "y", "z"};
+        if (n->tag == loop_dim::gpu_block || n->tag == loop_dim::gpu_thread) {
+            const bool zero = n->lo.is_int_literal() && n->lo.get_int_val() == 0;
+            os << pad(ind) << "const " << it << " " << n->cname() << " = " << (zero ? "" : print(n->lo, true) + " + ") << "(" << it << ") "
+               << (n->tag == loop_dim::gpu_block ? "blockIdx." : "threadIdx.") << ax[n->axis] << ";\n";
+            for (auto &c : n->kids) emit_device(c.get(), k, os, ind);
+        } else {
+            expr ext = n->hi - n->lo;
+            if (n->tag == loop_dim::unrolled || (ext.is_int_literal() && ext.get_int_val() <= 32)) os << pad(ind) << "#pragma unroll\n";
+            os << pad(ind) << "for (" << it << " " << n->cname() << " = " << print(n->lo, true) << "; " << n->cname() << " < "
+               << print(n->hi, true) << "; " << n->cname() << "++) {\n";
+            for (auto &c : n->kids) emit_device(c.get(), k, os, ind + 1);
+            os << pad(ind) << "}\n";
+        }
+        return;
+    }
+    const expr &e = n->comp->get_expr();
+    if (e.get_expr_type() == e_sync) { os << pad(ind) << "__syncthreads();   // " << n->comp->get_name() << "\n"; return; }
+    if (e.get_expr_type() == e_op && (e.get_op_type() == o_allocate || e.get_op_type() == o_free)) {
+        buffer *b = f_->find_buffer(e.get_name());
+        if (!b) die("allocate of unknown buffer '" + e.get_name() + "'");
+        if (b->get_location() == mem_loc::gpu_global || b->get_location() == mem_loc::host)
+            die("buffer '" + b->get_name() + "' cannot be allocated inside a kernel");
+        return;   // declared at the top of the kernel
+    }
+    if (e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_call))
+        die("'" + n->comp->get_name() + "': host operation inside a gpu loop nest");
+    emit_assignment(n, os, ind, true);
+}
+
+// C(i,j[,k]) = C(i,j,*) + A(..)*B(..): one statement, fp32, row-major global buffers.
+bool Lowering::try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind)
+{
+    if (!pattern_) return false;
+    // exactly one statement in the subtree
+    Node *stmt = nullptr;
+    std::vector<Node *> stack{k.root};
+    while (!stack.empty()) {
+        Node *n = stack.back(); stack.pop_back();
+        if (!n->is_loop) { if (stmt) return false; stmt = n; continue; }
+        for (auto &c : n->kids) stack.push_back(c.get());
+    }
+    if (!stmt || stmt->path.empty() || stmt->path[0] != k.root) return false;   // not inside a host loop
+    computation *c = stmt->comp;
+    if (c->get_data_type() != p_float32 || c->get_predicate().is_defined()) return false;
+    const auto &iters = c->get_iteration_variables();
+    if (iters.size() != 3) return false;
+    for (const var &v : iters) if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0)) return false;
+    const std::string I = iters[0].get_name(), J = iters[1].get_name(), K = iters[2].get_name();
+    const expr &e = c->get_expr();
+    if (e.get_expr_type() != e_op || e.get_op_type() != o_add) return false;
+    expr self = e.get_operand(0), prod = e.get_operand(1);
+    if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) std::swap(self, prod);
+    if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) return false;
+    if (!(self.get_expr_type() == e_op && self.get_op_type() == o_access && self.get_name() == c->get_name())) return false;
+    auto is_var = [](const expr &x, const std::string &n) { return x.get_expr_type() == e_var && x.get_name() == n; };
+    // the accumulator is addressed by (i, j) only
+    buffer *C = c->get_buffer();
+    if (C->get_location() != mem_loc::gpu_global || C->get_n_dims() != 2 || c->access().size() != 2) return false;
+    if (!is_var(c->access()[0], I) || !is_var(c->access()[1], J)) return false;
+    if (self.get_n_arg() != 3 || !is_var(self.get_operand(0), I) || !is_var(self.get_operand(1), J)) return false;
+    // operands: X(i,k) and Y(k,j) (either order), possibly stored transposed
+    struct Opnd { buffer *b = nullptr; bool trans = false; int role = -1; };   // role 0 = A (uses i,k), 1 = B (uses k,j)
+    auto classify = [&](const expr &x, Opnd &o) {
+        if (!(x.get_expr_type() == e_op && x.get_op_type() == o_access)) return false;
+        computation *oc = nullptr;
+        buffer *b = buffer_of_access(x, &oc);
+        if (!b || b->get_location() != mem_loc::gpu_global || b->get_n_dims() != 2 || b->get_elements_type() != p_float32) return false;
+        if (oc->access().size() != 2 || (int) oc->get_iteration_variables().size() != x.get_n_arg()) return false;
+        std::vector<std::string> names;
+        for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+        expr r = oc->access()[0].substitute(names, x.get_operands()), s = oc->access()[1].substitute(names, x.get_operands());
+        o.b = b;
+        if (is_var(r, I) && is_var(s, K)) { o.role = 0; o.trans = false; return true; }
+        if (is_var(r, K) && is_var(s, I)) { o.role = 0; o.trans = true; return true; }
+        if (is_var(r, K) && is_var(s, J)) { o.role = 1; o.trans = false; return true; }
+        if (is_var(r, J) && is_var(s, K)) { o.role = 1; o.trans = true; return true; }
+        return false;
+    };
+    Opnd x, y;
+    if (!classify(prod.get_operand(0), x) || !classify(prod.get_operand(1), y) || x.role == y.role) return false;
+    const Opnd &a = x.role == 0 ? x : y, &b = x.role == 0 ? y : x;
+    if (a.b == C || b.b == C) return false;
+    // no split may have left a guard: the box is covered exactly (guards come from non-dividing splits only)
+    for (const expr &g : c->guards()) (void) g;
+    expr M = iters[0].get_upper(), N = iters[1].get_upper(), Kx = iters[2].get_upper();
+    host << pad(ind) << "// pattern lowering: '" << c->get_name() << "' is a dense fp32 contraction -> tcgen05 GEMM of the runtime\n";
+    host << pad(ind) << "tiramisu_cublas_sgemm((float *) b_" << san(a.b->get_name()) << ", (float *) b_" << san(b.b->get_name()) << ", b_" << san(C->get_name())
+         << ", (uint64_t) " << print(M, false) << ", (uint64_t) " << print(N, false) << ", (uint64_t) " << print(Kx, false)
+         << ", 1.0f, 1.0f, (uint64_t) " << print(a.b->get_dim_sizes()[1], false) << ", (uint64_t) " << print(b.b->get_dim_sizes()[1], false)
+         << ", (uint64_t) " << print(C->get_dim_sizes()[1], false) << ", 0, 0, 0, " << (a.trans ? "true" : "false") << ", " << (b.trans ? "true" : "false") << ");\n";
+    return true;
+}
+
+void Lowering::emit_kernel(Node *n, std::ostringstream &host, int ind, std::vector<Node *> &host_loops)
+{
+    Kernel k;
+    k.root = n;
+    k.host_loops = host_loops;
+    collect_kernel(n, k, false);
+    // first statement's name labels the kernel (ncu-friendly)
+    Node *first = n;
+    while (first->is_loop && !first->kids.empty()) first = first->kids.front().get();
+    k.name = "tiramisu_sm100_" + san(f_->get_name()) + "_k" + std::to_string(next_kernel_++) + "_" + san(first->comp ? first->comp->get_name() : n->dim_name);
+
+    if (try_gemm_pattern(k, host, ind)) return;
+
+    // launch dimensions: per axis, the largest extent among the tagged loops on that axis
+    std::vector<Node *> tagged;
+    std::vector<Node *> stack{n};
+    while (!stack.empty()) {
+        Node *x = stack.back(); stack.pop_back();
+        if (x->is_loop && x->axis >= 0) tagged.push_back(x);
+        for (auto &c : x->kids) stack.push_back(c.get());
+    }
+    for (int t = 0; t < 2; t++) {
+        loop_dim::tag_t tg = t == 0 ? loop_dim::gpu_block : loop_dim::gpu_thread;
+        expr *dst = t == 0 ? k.grid : k.block;
+        for (int a = 0; a < 3; a++) {
+            expr best;
+            bool mixed = false;
+            for (Node *x : tagged) {
+                if (x->tag != tg || x->axis != a) continue;
+                expr ext = x->hi - x->lo;
+                if (!best.is_defined()) best = ext;
+                else if (!best.is_equal(ext)) { best = expr(o_max, best, ext); mixed = true; }
+            }
+            if (mixed) for (Node *x : tagged) if (x->tag == tg && x->axis == a) x->launch_guard = true;
+            dst[a] = best.is_defined() ? best : expr((int32_t) 1);
+            note_expr(dst[a], k, false);
+        }
+    }
+
+    // ---- device code
+    std::ostringstream &os = kernels_;
+    std::ostringstream body;
+    for (buffer *b : k.locals) {
+        std::string n_elems;
+        int64_t total = 1;
+        for (const expr &d : b->get_dim_sizes()) {
+            if (!d.is_int_literal()) die("on-chip buffer '" + b->get_name() + "' needs compile-time sizes");
+            total *= d.get_int_val();
+        }
+        body << pad(1) << (b->get_location() == mem_loc::gpu_shared ? "__shared__ " : "") << ctype(b->get_elements_type()) << " b_" << san(b->get_name())
+             << "[" << total << "];\n";
+    }
+    emit_device(n, k, body, 1);
+
+    os << "__global__ void ";
+    int64_t nthreads = 1;
+    bool known = true;
+    for (int a = 0; a < 3; a++) { if (k.block[a].is_int_literal()) nthreads *= k.block[a].get_int_val(); else known = false; }
+    if (known && nthreads >= 1 && nthreads <= 1024) os << "__launch_bounds__(" << nthreads << ") ";
+    os << k.name << "(";
+    std::vector<std::string> params, actuals;
+    for (buffer *b : k.globals) {
+        if (b->get_location() == mem_loc::host) die("kernel '" + k.name + "' uses host buffer '" + b->get_name() + "'");
+        bool ro = !k.written.count(b);
+        params.push_back(std::string(ro ? "const " : "") + ctype(b->get_elements_type()) + " *" + (ro ? " __restrict__ " : " ") + "b_" + san(b->get_name()));
+        actuals.push_back("b_" + san(b->get_name()));
+    }
+    for (const std::string &cn : k.constants) {
+        params.push_back(std::string("const ") + ctype(constants_[cn]->get_data_type()) + " c_" + san(cn));
+        actuals.push_back("c_" + san(cn));
+    }
+    for (Node *l : k.host_loops) {
+        params.push_back(std::string("const ") + ctype(global::get_loop_iterator_data_type()) + " " + l->cname());
+        actuals.push_back(l->cname());
+    }
+    for (size_t i = 0; i < params.size(); i++) os << (i ? ", " : "") << params[i];
+    os << ")\n{\n" << body.str() << "}\n\n";
+
+    // ---- launch
+    host << pad(ind) << "{\n";
+    host << pad(ind + 1) << "dim3 grid((unsigned) (" << print(k.grid[0], false) << "), (unsigned) (" << print(k.grid[1], false) << "), (unsigned) (" << print(k.grid[2], false) << "));\n";
+    host << pad(ind + 1) << "dim3 block((unsigned) (" << print(k.block[0], false) << "), (unsigned) (" << print(k.block[1], false) << "), (unsigned) (" << print(k.block[2], false) << "));\n";
+    host << pad(ind + 1) << "if (grid.x && grid.y && grid.z) {\n";
+    host << pad(ind + 2) << k.name << "<<<grid, block, 0, (cudaStream_t) tiramisu_b200_get_stream()>>>(";
+    for (size_t i = 0; i < actuals.size(); i++) host << (i ? ", " : "") << actuals[i];
+    host << ");\n";
+    host << pad(ind + 2) << "if (tiramisu_b200_post_launch(\"" << k.name << "\")) return 1;\n";
+    host << pad(ind + 1) << "}\n" << pad(ind) << "}\n";
+}
+
+void Lowering::emit_host_stmt(Node *n, std::ostringstream &os, int ind)
+{
+    computation *c = n->comp;
+    const expr &e = c->get_expr();
+    if (e.get_expr_type() == e_sync) die("'" + c->get_name() + "': sync() outside a gpu loop nest");
+    if (e.get_expr_type() == e_op && e.get_op_type() == o_memcpy) {
+        buffer *src = f_->find_buffer(e.get_operand(0).get_name()), *dst = f_->find_buffer(e.get_operand(1).get_name());
+        if (!src || !dst) die("memcpy between unknown buffers in '" + c->get_name() + "'");
+        bool sd = src->get_location() != mem_loc::host, dd = dst->get_location() != mem_loc::host;
+        os << pad(ind) << "{   // " << c->get_name() << ": " << src->get_name() << " -> " << dst->get_name() << "\n";
+        std::vector<std::string> conds;
+        emit_bindings(n, os, ind + 1, conds, false);
+        std::string S = "b_" + san(src->get_name()), D = "b_" + san(dst->get_name());
+        os << pad(ind + 1) << "const uint64_t nbytes = tb_min<uint64_t>(" << bytes_of(src, false) << ", " << bytes_of(dst, false) << ");\n";
+        if (!sd && dd) os << pad(ind + 1) << "tiramisu_cuda_memcpy_to_device(" << D << ", (void *) " << S << ", nbytes);\n";
+        else if (sd && !dd) os << pad(ind + 1) << "tiramisu_cuda_memcpy_to_host(" << D << ", (void *) " << S << ", nbytes);\n";
+        else if (sd && dd) os << pad(ind + 1) << "cudaMemcpyAsync(" << D << ", " << S << ", nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t) tiramisu_b200_get_stream());\n";
+        else os << pad(ind + 1) << "memcpy(" << D << ", " << S << ", nbytes);\n";
+        os << pad(ind) << "}\n";
+        return;
+    }
+    if (e.get_expr_type() == e_op && (e.get_op_type() == o_allocate || e.get_op_type() == o_free)) {
+        buffer *b = f_->find_buffer(e.get_name());
+        if (!b) die("allocate/free of unknown buffer '" + e.get_name() + "'");
+        std::string B = "b_" + san(b->get_name());
+        os << pad(ind) << "{   // " << c->get_name() << "\n";
+        std::vector<std::string> conds;
+        emit_bindings(n, os, ind + 1, conds, false);
+        bool dev = b->get_location() == mem_loc::gpu_global;
+        if (b->get_location() != mem_loc::host && !dev) die("on-chip buffer '" + b->get_name() + "' allocated outside a kernel");
+        if (e.get_op_type() == o_allocate)
+            os << pad(ind + 1) << B << " = (" << ctype(b->get_elements_type()) << " *) " << (dev ? "tiramisu_cuda_malloc(" : "malloc(") << bytes_of(b, false) << ");\n";
+        else
+            os << pad(ind + 1) << (dev ? "tiramisu_cuda_free(" : "free(") << B << "); " << B << " = nullptr;\n";
+        os << pad(ind) << "}\n";
+        return;
+    }
+    if (e.get_expr_type() == e_op && e.get_op_type() == o_call && !c->has_access()) {
+        os << pad(ind) << "{   // " << c->get_name() << "\n";
+        std::vector<std::string> conds;
+        emit_bindings(n, os, ind + 1, conds, false);
+        os << pad(ind + 1) << print(e, false) << ";\n" << pad(ind) << "}\n";
+        return;
+    }
+    if (c->get_buffer()->get_location() == mem_loc::host && !(e.get_expr_type() == e_op && e.get_op_type() == o_call))
+        std::cerr << "tiramisu_b200 lowering: note: '" << c->get_name() << "' has no gpu level and runs in the host function\n";
+    emit_assignment(n, os, ind, false);
+}
+
+void Lowering::emit_host(Node *n, std::ostringstream &os, int ind, std::vector<Node *> &host_loops)
+{
+    if (!n->is_loop) { emit_host_stmt(n, os, ind); return; }
+    if (n->tag == loop_dim::gpu_block || n->tag == loop_dim::gpu_thread) { emit_kernel(n, os, ind, host_loops); return; }
+    const std::string it = ctype(global::get_loop_iterator_data_type());
+    os << pad(ind) << "for (" << it << " " << n->cname() << " = " << print(n->lo, false) << "; " << n->cname() << " < " << print(n->hi, false) << "; "
+       << n->cname() << "++) {\n";
+    host_loops.push_back(n);
+    for (auto &c : n->kids) emit_host(c.get(), os, ind + 1, host_loops);
+    host_loops.pop_back();
+    os << pad(ind) << "}\n";
+}
+
+// ------------------------------------------------------------------------------------------------ driver
+std::string Lowering::run()
+{
+    if (!cuda_) die("function '" + f_->get_name() + "': this back end only generates sm_100a code; call codegen(args, obj, true) "
+                    "(there is no CPU code generator and no CPU fallback)");
+    if (const char *m = getenv("TIRAMISU_B200_LOWERING")) pattern_ = std::string(m) != "generic";
+    for (computation *c : f_->get_computations())
+        if (c->is_constant()) { constants_[c->get_name()] = c; constant_order_.push_back(c); }
+    for (buffer *b : args_)
+        if (b->get_location() != mem_loc::host && b->get_location() != mem_loc::gpu_global)
+            die("argument buffer '" + b->get_name() + "' is tagged on-chip");
+
+    build_tree(order());
+    assign_axes(&root_);
+
+    std::ostringstream body;
+    std::vector<Node *> host_loops;
+    for (auto &k : root_.kids) emit_host(k.get(), body, 1, host_loops);
+
+    std::ostringstream out;
+    out << "// Generated by the tiramisu_b200 sm_100a lowering for Tiramisu function '" << f_->get_name() << "'. Do not edit.\n"
+        << "#include <cstdint>\n#include <cstdlib>\n#include <cstring>\n#include <cmath>\n#include <cuda_runtime.h>\n\n"
+        << "#ifndef HALIDE_HALIDERUNTIME_H\n"
+        << "struct halide_dimension_t { int32_t min, extent, stride; uint32_t flags; };\n"
+        << "struct halide_type_t { uint8_t code, bits; uint16_t lanes; };\n"
+        << "struct halide_buffer_t { uint64_t device; const void *device_interface; uint8_t *host; uint64_t flags; halide_type_t type;\n"
+        << "                         int32_t dimensions; halide_dimension_t *dim; void *padding; };\n"
+        << "#endif\n"
+        << "extern \"C\" {\n"
+        << "int tiramisu_cuda_memcpy_to_device(void *, void *, uint64_t);\nint tiramisu_cuda_memcpy_to_host(void *, void *, uint64_t);\n"
+        << "void *tiramisu_cuda_malloc(uint64_t);\nint tiramisu_cuda_free(void *);\nint32_t tiramisu_cuda_stream_synchronize(int32_t);\n"
+        << "void *tiramisu_b200_get_stream(void);\nint tiramisu_b200_post_launch(const char *);\n"
+        << "int tiramisu_cublas_sgemm(float *, float *, float *, uint64_t, uint64_t, uint64_t, float, float, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, bool, bool);\n"
+        << "int tiramisu_cublas_dgemm(double *, double *, double *, uint64_t, uint64_t, uint64_t, double, double, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, bool, bool);\n"
+        << "}\n"
+        << "template <typename T> __host__ __device__ __forceinline__ T tb_max(T a, T b) { return a > b ? a : b; }\n"
+        << "template <typename T> __host__ __device__ __forceinline__ T tb_min(T a, T b) { return a < b ? a : b; }\n"
+        << "template <typename T> __host__ __device__ __forceinline__ T tb_abs(T a) { return a < 0 ? -a : a; }\n"
+        << "static inline void *tb_arg(halide_buffer_t *b) { return b->host ? (void *) b->host : (void *) b->device; }\n\n";
+    out << protos_.str() << "\n" << kernels_.str();
+
+    out << "extern \"C\" int " << f_->get_name() << "(";
+    for (size_t i = 0; i < args_.size(); i++) out << (i ? ", " : "") << "halide_buffer_t *arg" << i;
+    out << ")\n{\n";
+    std::set<buffer *> is_arg(args_.begin(), args_.end());
+    for (size_t i = 0; i < args_.size(); i++)
+        out << pad(1) << ctype(args_[i]->get_elements_type()) << " *b_" << san(args_[i]->get_name()) << " = (" << ctype(args_[i]->get_elements_type())
+            << " *) tb_arg(arg" << i << ");\n";
+    for (buffer *b : f_->get_buffers())
+        if (!is_arg.count(b) && (b->get_location() == mem_loc::host || b->get_location() == mem_loc::gpu_global))
+            out << pad(1) << ctype(b->get_elements_type()) << " *b_" << san(b->get_name()) << " = nullptr;\n";
+    for (computation *c : constant_order_)
+        out << pad(1) << "const " << ctype(c->get_data_type()) << " c_" << san(c->get_name()) << " = (" << ctype(c->get_data_type()) << ") "
+            << print(c->get_expr(), false) << ";\n";
+    // temporaries: allocated at entry, freed at exit (reference src/tiramisu_codegen_halide.cpp:2488-2530)
+    std::vector<buffer *> autos;
+    for (buffer *b : f_->get_buffers())
+        if (!is_arg.count(b) && b->get_auto_allocate() && (b->get_location() == mem_loc::host || b->get_location() == mem_loc::gpu_global))
+            autos.push_back(b);
+    for (buffer *b : autos)
+        out << pad(1) << "b_" << san(b->get_name()) << " = (" << ctype(b->get_elements_type()) << " *) "
+            << (b->get_location() == mem_loc::gpu_global ? "tiramisu_cuda_malloc(" : "malloc(") << bytes_of(b, false) << ");\n";
+    out << body.str();
+    for (auto it = autos.rbegin(); it != autos.rend(); ++it)
+        out << pad(1) << ((*it)->get_location() == mem_loc::gpu_global ? "tiramisu_cuda_free(" : "free(") << "b_" << san((*it)->get_name()) << ");\n";
+    out << pad(1) << "return 0;\n}\n\n";
+    out << "extern \"C\" int " << f_->get_name() << "_argv(void **args)\n{\n" << pad(1) << "return " << f_->get_name() << "(";
+    for (size_t i = 0; i < args_.size(); i++) out << (i ? ", " : "") << "(halide_buffer_t *) args[" << i << "]";
+    out << ");\n}\n";
+    return out.str();
+}
+
+}  // namespace
+
+void function::codegen(const std::vector<buffer *> &arguments, const std::string obj_filename, bool gen_cuda_stmt)
+{
+    set_arguments(arguments);
+    Lowering l(this, arguments, gen_cuda_stmt);
+    std::string src = l.run();
+    std::string cu = obj_filename + ".b200.cu";
+    {
+        std::ofstream o(cu);
+        if (!o) die("cannot write " + cu);
+        o << src;
+    }
+    const char *nvcc = getenv("NVCC");
+    const char *extra = getenv("TIRAMISU_B200_NVCC_FLAGS");
+    std::string cmd = std::string(nvcc ? nvcc : "/usr/local/cuda/bin/nvcc") +
+                      " -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC " +
+                      (extra ? extra : "") + " -c " + cu + " -o " + obj_filename;
+    // the image's $CC/$CXX wrappers are not usable nvcc host compilers
+    cmd = "env -u CC -u CXX " + cmd;
+    int rc = std::system(cmd.c_str());
+    if (rc != 0) die("nvcc failed (" + std::to_string(rc) + ") on " + cu);
+}
+
+}  // namespace tiramisu
