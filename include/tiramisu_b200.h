@@ -112,6 +112,30 @@ int tiramisu_b200_heat2d(const float *in, float *out, int32_t H, int32_t W, int3
  * u32: tests/test_160.cpp:23-29    in[rows+2][cols+2] -> out[rows][cols], vertical first. */
 int tiramisu_b200_blur_f32(const float *in, float *out, int32_t H, int32_t W,
                            int32_t row_begin, int32_t row_end);
+
+/* Row-sharded grids: halo rows are read IN PLACE from the neighbours' HBM through
+ * peer mappings (tiramisu_b200_comm_alloc_symmetric) instead of being exchanged before the sweep —
+ * replaces the four MPI transfers per sweep of benchmarks/halide/heat2d_dist_tiramisu.cpp:133-153
+ * and the two of benchmarks/automatic_comm/blurautodist_ref.cpp:42-61.  The rank owns global rows
+ * [lo, hi); `up` points at row lo-1 as the upper neighbour stores it, `dn` at row hi (and hi+1) as
+ * the lower neighbour stores them; either may be NULL at the ends of the grid.
+ * Iterated sweeps: with `flags` set (4 ints of symmetric memory, zero-initialised), the first / last
+ * row block of the launch waits until flags[0] / flags[1] >= wait_value and the launch publishes
+ * signal_value to *sig_up / *sig_dn (the neighbours' flags[1] / flags[0]) when those blocks retire. */
+typedef struct tiramisu_b200_halo {
+    const float *up;
+    const float *dn;
+    int32_t lo, hi;
+    int32_t *flags;
+    int32_t *sig_up;
+    int32_t *sig_dn;
+    int32_t wait_value;
+    int32_t signal_value;
+} tiramisu_b200_halo_t;
+int tiramisu_b200_heat2d_peer(const float *in, float *out, int32_t H, int32_t W, int32_t form,
+                              int32_t row_begin, int32_t row_end, const tiramisu_b200_halo_t *halo);
+int tiramisu_b200_blur_f32_peer(const float *in, float *out, int32_t H, int32_t W,
+                                int32_t row_begin, int32_t row_end, const tiramisu_b200_halo_t *halo);
 int tiramisu_b200_blurxy_u8(const uint8_t *in, uint8_t *out, int32_t C, int32_t H, int32_t W);
 int tiramisu_b200_boxblur_u32(const uint32_t *in, uint32_t *out, int32_t rows, int32_t cols);
 /* tutorials/developers/tutorial_04gpu.cpp: uint8 NxN matmul (wraps mod 256). */
@@ -159,6 +183,12 @@ int tiramisu_b200_comm_broadcast_large(void *dev_buf, uint64_t bytes, int32_t ro
 int tiramisu_b200_comm_exchange(int32_t n, const int32_t *send_peer, void *const *send_buf,
                                 const uint64_t *send_bytes, const int32_t *recv_peer,
                                 void *const *recv_buf, const uint64_t *recv_bytes);
+/* Symmetric device memory: every rank allocates `bytes` (cudaMalloc), the CUDA IPC handles are
+ * all-gathered over the NCCL communicator and every peer's allocation is mapped into this process.
+ * peers[r] (world entries, caller-provided) is rank r's block as addressable from this GPU over
+ * NVLink; peers[rank] == *local.  Collective: every rank must call it, in the same order. */
+int tiramisu_b200_comm_alloc_symmetric(uint64_t bytes, void **local, void **peers);
+int tiramisu_b200_comm_free_symmetric(void *local);
 int tiramisu_MPI_init(void);                 /* src/tiramisu_mpi.cpp:8  reads torchrun's env; returns rank */
 void tiramisu_MPI_cleanup(void);             /* :19 */
 void tiramisu_MPI_global_barrier(void);      /* :23 */

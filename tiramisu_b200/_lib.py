@@ -32,6 +32,14 @@ assert C.sizeof(HalideBuffer) == 56 and C.sizeof(HalideDimension) == 16
 _lib = None
 
 
+class Halo(C.Structure):
+    """tiramisu_b200_halo_t (include/tiramisu_b200.h): where a row-sharded stencil finds the rows its
+    neighbours own, and the optional sweep handshake."""
+    _fields_ = [("up", C.c_void_p), ("dn", C.c_void_p), ("lo", C.c_int32), ("hi", C.c_int32),
+                ("flags", C.c_void_p), ("sig_up", C.c_void_p), ("sig_dn", C.c_void_p),
+                ("wait_value", C.c_int32), ("signal_value", C.c_int32)]
+
+
 def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
@@ -92,6 +100,11 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_comm_broadcast_large", C.c_int, vp, u64, i32)
     sig("tiramisu_b200_comm_exchange", C.c_int, i32, C.POINTER(i32), C.POINTER(vp), C.POINTER(u64),
         C.POINTER(i32), C.POINTER(vp), C.POINTER(u64))
+    sig("tiramisu_b200_comm_alloc_symmetric", C.c_int, u64, C.POINTER(vp), C.POINTER(vp))
+    sig("tiramisu_b200_comm_free_symmetric", C.c_int, vp)
+    sig("tiramisu_b200_heat2d_peer", C.c_int, vp, vp, i32, i32, i32, i32, i32, C.POINTER(Halo))
+    sig("tiramisu_b200_blur_f32_peer", C.c_int, vp, vp, i32, i32, i32, i32, C.POINTER(Halo))
+    sig("tiramisu_b200_post_launch", C.c_int, C.c_char_p)
     sig("tiramisu_MPI_init", C.c_int)
     sig("tiramisu_MPI_cleanup", None)
     sig("tiramisu_MPI_global_barrier", None)

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 using namespace tb200;
 
@@ -320,6 +321,70 @@ TB200_API int tiramisu_b200_comm_exchange(int32_t n, const int32_t *send_peer, v
     }
     rc |= nccl_check(nc.GroupEnd(), "ncclGroupEnd");
     return rc;
+}
+
+// ---- symmetric memory over CUDA IPC --------------------------------------------------------------
+// The stencil kernels read halo rows straight out of the neighbours' HBM (stencil.cu: Halo); this is
+// the mapping that makes a neighbour's rows addressable.  cudaMalloc (not the stream-ordered pool:
+// pool memory cannot be exported through cudaIpcGetMemHandle), handles all-gathered through the
+// communicator itself so that any host program — torchrun or the reference's MPI-style wrappers
+// after tiramisu_MPI_init() — can use it.
+namespace {
+struct SymBlock { void *local; std::vector<void *> opened; };
+std::vector<SymBlock> g_sym;
+}
+
+TB200_API int tiramisu_b200_comm_alloc_symmetric(uint64_t bytes, void **local, void **peers)
+{
+    if (!local || !peers || bytes == 0) return fail(__func__, "bad argument");
+    if (!g_comm.comm) return fail(__func__, "communicator not initialised");
+    const int world = g_comm.world, rank = g_comm.rank;
+    void *mine = nullptr;
+    TB200_CHECK(cudaMalloc(&mine, bytes));
+    TB200_CHECK(cudaMemset(mine, 0, bytes));
+    cudaIpcMemHandle_t h;
+    TB200_CHECK(cudaIpcGetMemHandle(&h, mine));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    char *d_all = nullptr;
+    TB200_CHECK(cudaMalloc(&d_all, (size_t)world * 64));
+    TB200_CHECK(cudaMemcpyAsync(d_all + (size_t)rank * 64, &h, 64, cudaMemcpyHostToDevice, stream()));
+    if (nccl_check(nccl().AllGather(d_all + (size_t)rank * 64, d_all, 64, ncclInt8, g_comm.comm, stream()), "ncclAllGather")) return 1;
+    std::vector<cudaIpcMemHandle_t> all(world);
+    TB200_CHECK(cudaMemcpyAsync(all.data(), d_all, (size_t)world * 64, cudaMemcpyDeviceToHost, stream()));
+    TB200_CHECK(cudaStreamSynchronize(stream()));
+    cudaFree(d_all);
+    SymBlock blk{mine, {}};
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { peers[r] = mine; continue; }
+        void *p = nullptr;
+        TB200_CHECK(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+        peers[r] = p;
+        blk.opened.push_back(p);
+    }
+    *local = mine;
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    g_sym.push_back(blk);
+    return 0;
+}
+
+TB200_API int tiramisu_b200_comm_free_symmetric(void *local)
+{
+    SymBlock blk{nullptr, {}};
+    {
+        std::lock_guard<std::mutex> lk(g_comm_mu);
+        for (size_t i = 0; i < g_sym.size(); i++)
+            if (g_sym[i].local == local) { blk = g_sym[i]; g_sym.erase(g_sym.begin() + i); break; }
+    }
+    if (!blk.local) return fail(__func__, "not a symmetric block");
+    TB200_CHECK(cudaStreamSynchronize(stream()));
+    for (void *p : blk.opened) cudaIpcCloseMemHandle(p);
+    // every rank must have unmapped before the owner frees: rendezvous through the communicator
+    if (g_comm.comm) {
+        if (nccl_check(nccl().AllReduce(g_comm.scratch, g_comm.scratch, 1, ncclFloat32, ncclSum, g_comm.comm, stream()), "ncclAllReduce")) return 1;
+        TB200_CHECK(cudaStreamSynchronize(stream()));
+    }
+    TB200_CHECK(cudaFree(blk.local));
+    return 0;
 }
 
 // =============================================================================== src/tiramisu_mpi.cpp names

@@ -40,14 +40,88 @@ __device__ __forceinline__ float heat_point(float c, float n, float s, float w, 
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
+// ---- row-sharded grids: halo rows read in place from the neighbours' memory ------------------------
+// A rank owns rows [lo, hi) of the global grid.  Row lo-1 lives in the upper neighbour's HBM and rows
+// hi, hi+1 in the lower neighbour's; both allocations are mapped into this process (CUDA IPC over
+// NVLink, comm.cu: tiramisu_b200_comm_alloc_symmetric), so the stencil kernel fetches them with
+// ordinary loads while it streams its own rows — the halo "exchange" of heat2d_dist / blurautodist
+// (benchmarks/halide/heat2d_dist_tiramisu.cpp:133-153: four MPI transfers per sweep) is fused into
+// the sweep and costs no launch and no staging buffer.
+// For iterated sweeps (even/odd Jacobi) the same launch carries the neighbour handshake: the CTAs
+// of the first / last row block wait until the neighbour has finished the previous sweep (its
+// boundary rows are written, and it no longer reads ours), and the last of them to retire publishes
+// this rank's sweep count into the neighbours' flag words with a system-scope release.
+using Halo = tiramisu_b200_halo_t;   // include/tiramisu_b200.h
+
+template <bool PEER>
+__device__ __forceinline__ const float *halo_row(const float *in, const Halo &h, int y, size_t Ws, bool &remote)
+{
+    remote = false;
+    if (PEER) {
+        if (h.up && y < h.lo) { remote = true; return h.up + (ptrdiff_t)(y - (h.lo - 1)) * (ptrdiff_t)Ws; }
+        if (h.dn && y >= h.hi) { remote = true; return h.dn + (size_t)(y - h.hi) * Ws; }
+    }
+    return in + (size_t)y * Ws;
+}
+// Rows owned by this rank go through the non-coherent path; a neighbour's rows were written by
+// another GPU (possibly during this very stream of sweeps), so they are fetched with
+// cache-volatile loads, ordered after the acquire in halo_wait.
+__device__ __forceinline__ float4 ld_row4(const float *p, bool remote)
+{
+    return remote ? __ldcv(reinterpret_cast<const float4 *>(p)) : ldg4(p);
+}
+__device__ __forceinline__ float ld_row1(const float *p, bool remote) { return remote ? __ldcv(p) : __ldg(p); }
+
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// first / last row block of the launch: wait for the neighbour's previous sweep (bounded: a protocol
+// bug must trap, not hang the box)
+__device__ __forceinline__ void halo_wait(const Halo &h, bool first, bool last)
+{
+    if (h.flags == nullptr) return;
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        if (first && h.up) while (ld_acquire_sys(h.flags + 0) < h.wait_value) if (clock64() - t0 > 4000000000LL) __trap();
+        if (last && h.dn) while (ld_acquire_sys(h.flags + 1) < h.wait_value) if (clock64() - t0 > 4000000000LL) __trap();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void halo_signal(const Halo &h, bool first, bool last)
+{
+    if (h.flags == nullptr) return;
+    __syncthreads();                                   // every store of this CTA is issued
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (first && h.sig_up && atomicAdd(h.flags + 2, 1) == (int)gridDim.x - 1) {
+            h.flags[2] = 0;
+            st_release_sys(h.sig_up, h.signal_value);
+        }
+        if (last && h.sig_dn && atomicAdd(h.flags + 3, 1) == (int)gridDim.x - 1) {
+            h.flags[3] = 0;
+            st_release_sys(h.sig_dn, h.signal_value);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // heat2d, vector path: W % 4 == 0, 16-byte aligned rows.  grid = (ceil(W/4/128), ceil(rows/RY)).
-template <int FORM, int RY>
+template <int FORM, int RY, bool PEER = false>
 __global__ void __launch_bounds__(128)
 tiramisu_sm100_heat2d_v4(const float *__restrict__ in, float *__restrict__ out, int H, int W,
-                         int row_begin, int row_end)
+                         int row_begin, int row_end, const Halo halo = Halo{})
 {
     const int lane = threadIdx.x & 31;
+    if (PEER) halo_wait(halo, blockIdx.y == 0, blockIdx.y == gridDim.y - 1);
     const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
     const int y0 = row_begin + blockIdx.y * RY;
     const bool col_ok = x < W;
@@ -58,8 +132,9 @@ tiramisu_sm100_heat2d_v4(const float *__restrict__ in, float *__restrict__ out, 
 #pragma unroll
     for (int r = 0; r < RY + 2; r++) {
         const int y = y0 - 1 + r;
-        v[r] = (col_ok && y >= 0 && y < H && y <= row_end) ? ldg4(in + (size_t)y * Ws + x)
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool remote;
+        const float *row = halo_row<PEER>(in, halo, y, Ws, remote);
+        v[r] = (col_ok && y >= 0 && y < H && y <= row_end) ? ld_row4(row + x, remote) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     // west/east halo of the centre rows for the warp's edge lanes
     float wl[RY], er[RY];
@@ -78,7 +153,7 @@ tiramisu_sm100_heat2d_v4(const float *__restrict__ in, float *__restrict__ out, 
         float ev = __shfl_down_sync(0xffffffffu, c.x, 1);
         if (lane == 0) wv = wl[r];
         if (lane == 31) ev = er[r];
-        if (!col_ok || y >= row_end || y >= H) continue;
+        if (!col_ok || y >= row_end || y >= H) continue;   // (warp-uniform in y; no barrier below depends on it)
         float4 o;
         o.x = heat_point<FORM>(c.x, n.x, s.x, wv, c.y);
         o.y = heat_point<FORM>(c.y, n.y, s.y, c.x, c.z);
@@ -100,6 +175,7 @@ tiramisu_sm100_heat2d_v4(const float *__restrict__ in, float *__restrict__ out, 
         }
         __stcs(dst, o);
     }
+    if (PEER) halo_signal(halo, blockIdx.y == 0, blockIdx.y == gridDim.y - 1);
 }
 
 // heat2d, generic path (any W, any alignment): one thread per output element.
@@ -144,10 +220,10 @@ __device__ __forceinline__ float blur3(float a, float b, float c)
     return div3(__fadd_rn(__fadd_rn(a, b), c));
 }
 
-template <int RY>
+template <int RY, bool PEER = false>
 __global__ void __launch_bounds__(128)
 tiramisu_sm100_blur_f32_v4(const float *__restrict__ in, float *__restrict__ out, int H, int W,
-                           int row_begin, int row_end)
+                           int row_begin, int row_end, const Halo halo = Halo{})
 {
     const int lane = threadIdx.x & 31;
     const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
@@ -162,10 +238,12 @@ tiramisu_sm100_blur_f32_v4(const float *__restrict__ in, float *__restrict__ out
     for (int r = 0; r < RY + 2; r++) {
         const int y = y0 + r;
         const bool ok = col_ok && y < H && y < row_end + 2;
-        v[r] = ok ? ldg4(in + (size_t)y * Ws + x) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool remote;
+        const float *row = halo_row<PEER>(in, halo, y, Ws, remote);
+        v[r] = ok ? ld_row4(row + x, remote) : make_float4(0.f, 0.f, 0.f, 0.f);
         const bool edge = ok && lane == 31 && x + 4 < W;      // W % 4 == 0 => x+5 < W too
-        e0[r] = edge ? __ldg(in + (size_t)y * Ws + x + 4) : 0.f;
-        e1[r] = edge ? __ldg(in + (size_t)y * Ws + x + 5) : 0.f;
+        e0[r] = edge ? ld_row1(row + x + 4, remote) : 0.f;
+        e1[r] = edge ? ld_row1(row + x + 5, remote) : 0.f;
     }
     float4 bx[RY + 2];
 #pragma unroll
@@ -291,15 +369,20 @@ constexpr int kHeatRY = 8;
 constexpr int kBlurRY = 6;
 
 template <int FORM>
-int launch_heat2d(const float *in, float *out, int H, int W, int rb, int re)
+int launch_heat2d(const float *in, float *out, int H, int W, int rb, int re, const Halo *halo = nullptr)
 {
     const int rows = re - rb;
     if (rows <= 0) return 0;
     if (W % 4 == 0 && aligned16(in) && aligned16(out)) {
         dim3 grid((W / 4 + 127) / 128, (rows + kHeatRY - 1) / kHeatRY);
+        if (halo) {
+            tiramisu_sm100_heat2d_v4<FORM, kHeatRY, true><<<grid, 128, 0, stream()>>>(in, out, H, W, rb, re, *halo);
+            return post_launch("tiramisu_sm100_heat2d_v4<peer>");
+        }
         tiramisu_sm100_heat2d_v4<FORM, kHeatRY><<<grid, 128, 0, stream()>>>(in, out, H, W, rb, re);
         return post_launch("tiramisu_sm100_heat2d_v4");
     }
+    if (halo) return fail("tiramisu_b200_heat2d_peer", "peer halos need W % 4 == 0 and 16-byte aligned rows");
     dim3 grid((W + 255) / 256, rows);
     tiramisu_sm100_heat2d_scalar<FORM><<<grid, 256, 0, stream()>>>(in, out, H, W, rb, re);
     return post_launch("tiramisu_sm100_heat2d_scalar");
@@ -319,6 +402,43 @@ TB200_API int tiramisu_b200_heat2d(const float *in, float *out, int32_t H, int32
     case 1: return launch_heat2d<1>(in, out, H, W, row_begin, row_end);
     default: return launch_heat2d<2>(in, out, H, W, row_begin, row_end);
     }
+}
+
+static int check_halo(const tiramisu_b200_halo_t *h, int row_begin, int row_end, const char *who)
+{
+    if (!h) return fail(who, "halo descriptor is null");
+    if (h->lo > row_begin || h->hi < row_end || h->lo >= h->hi) return fail(who, "rows to compute lie outside the owned block [lo, hi)");
+    if ((h->up && (reinterpret_cast<uintptr_t>(h->up) & 15u)) || (h->dn && (reinterpret_cast<uintptr_t>(h->dn) & 15u)))
+        return fail(who, "peer halo rows must be 16-byte aligned");
+    if (h->flags == nullptr && (h->sig_up || h->sig_dn)) return fail(who, "signal targets without local flags");
+    return 0;
+}
+
+TB200_API int tiramisu_b200_heat2d_peer(const float *in, float *out, int32_t H, int32_t W, int32_t form,
+                                        int32_t row_begin, int32_t row_end, const tiramisu_b200_halo_t *halo)
+{
+    if (!in || !out || H < 1 || W < 1 || row_begin < 0 || row_end > H || form < 0 || form > 2)
+        return fail(__func__, "bad argument");
+    if (check_halo(halo, row_begin, row_end, __func__)) return 1;
+    switch (form) {
+    case 0: return launch_heat2d<0>(in, out, H, W, row_begin, row_end, halo);
+    case 1: return launch_heat2d<1>(in, out, H, W, row_begin, row_end, halo);
+    default: return launch_heat2d<2>(in, out, H, W, row_begin, row_end, halo);
+    }
+}
+
+TB200_API int tiramisu_b200_blur_f32_peer(const float *in, float *out, int32_t H, int32_t W,
+                                          int32_t row_begin, int32_t row_end, const tiramisu_b200_halo_t *halo)
+{
+    if (!in || !out || H < 3 || W < 3 || row_begin < 0 || row_end > H - 2)
+        return fail(__func__, "bad argument");
+    if (check_halo(halo, row_begin, row_end, __func__)) return 1;
+    const int rows = row_end - row_begin;
+    if (rows <= 0) return 0;
+    if (!(W % 4 == 0 && aligned16(in) && aligned8(out))) return fail(__func__, "peer halos need W % 4 == 0 and aligned rows");
+    dim3 grid((W / 4 + 127) / 128, (rows + kBlurRY - 1) / kBlurRY);
+    tiramisu_sm100_blur_f32_v4<kBlurRY, true><<<grid, 128, 0, stream()>>>(in, out, H, W, row_begin, row_end, *halo);
+    return post_launch("tiramisu_sm100_blur_f32_v4<peer>");
 }
 
 TB200_API int tiramisu_b200_blur_f32(const float *in, float *out, int32_t H, int32_t W,

@@ -101,3 +101,63 @@ def comm_init_from_torch(group=None) -> int:
 
 def comm_destroy() -> None:
     _lib.check(_lib.lib().tiramisu_b200_comm_destroy(), "tiramisu_b200_comm_destroy")
+
+
+# ---- peer-memory row blocks: halo rows are read in place over NVLink ---------------------------------
+class SymmetricRows:
+    """Rank-local block of `rows_max` x `width` fp32 rows in symmetric device memory
+    (tiramisu_b200_comm_alloc_symmetric): every rank's block is mapped into every process, so a
+    stencil launch reads its neighbours' boundary rows directly (stencil.cu: Halo) — the fused form
+    of heat2d_dist's / blurautodist's send/recv exchange.  `n_buffers` equal blocks are carved out
+    of one allocation (even/odd Jacobi buffers); 4 flag words per rank follow them.
+
+    Collective constructor: every rank must call it with the same arguments."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, rows_max: int, width: int, n_buffers: int = 1):
+        L = _lib.lib()
+        self.world = L.tiramisu_b200_comm_size()
+        self.rank = L.tiramisu_b200_comm_rank()
+        self.width = width
+        self.block_bytes = ((rows_max * width * 4 + 255) // 256) * 256
+        self.n_buffers = n_buffers
+        self.bytes = self.block_bytes * n_buffers + self.FLAG_BYTES
+        local = C.c_void_p()
+        peers = (C.c_void_p * self.world)()
+        _lib.check(L.tiramisu_b200_comm_alloc_symmetric(self.bytes, C.byref(local), peers), "comm_alloc_symmetric")
+        self.local = local.value
+        self.peers = [peers[r] for r in range(self.world)]
+
+    def buffer(self, i: int = 0, rank: int | None = None) -> int:
+        """Device address of buffer i of `rank`'s block (default: mine) as seen from this GPU."""
+        base = self.local if rank is None else self.peers[rank]
+        return base + i * self.block_bytes
+
+    def flags(self, rank: int | None = None) -> int:
+        base = self.local if rank is None else self.peers[rank]
+        return base + self.n_buffers * self.block_bytes
+
+    def halo(self, i: int, r0: int, r1: int, rows_of, sync: bool = False, wait_value: int = 0,
+             signal_value: int = 0) -> "_lib.Halo":
+        """Descriptor for a sweep over my rows [r0, r1) of buffer i.  rows_of(rank) -> (r0, r1) of a
+        neighbour (to find its last row / first rows inside its block)."""
+        h = _lib.Halo()
+        row_b = self.width * 4
+        h.lo, h.hi = r0, r1
+        if self.rank > 0:
+            u0, u1 = rows_of(self.rank - 1)
+            h.up = self.buffer(i, self.rank - 1) + (u1 - 1 - u0) * row_b
+        if self.rank < self.world - 1:
+            h.dn = self.buffer(i, self.rank + 1)
+        if sync:
+            h.flags = self.flags()
+            h.sig_up = self.flags(self.rank - 1) + 4 if self.rank > 0 else None
+            h.sig_dn = self.flags(self.rank + 1) + 0 if self.rank < self.world - 1 else None
+            h.wait_value, h.signal_value = wait_value, signal_value
+        return h
+
+    def free(self) -> None:
+        if self.local:
+            _lib.check(_lib.lib().tiramisu_b200_comm_free_symmetric(self.local), "comm_free_symmetric")
+            self.local = None
