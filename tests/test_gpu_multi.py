@@ -1,6 +1,8 @@
 """Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): tools/dist_check.py under
 torchrun — distributed boxblur through the ABI, row-sharded heat2d with NCCL halo exchange,
-scatter+all-gather broadcast, row-sharded sgemm — all bit-exact against the single-process oracle."""
+scatter+all-gather broadcast, row-sharded sgemm, and the peer-memory halo path (heat2d / fp32 blur
+reading the neighbours' rows in place over NVLink, 12 even/odd Jacobi sweeps of heat2d_dist with the
+neighbour handshake inside the sweep kernels) — all bit-exact against the single-process oracle."""
 import os
 import subprocess
 import sys

@@ -115,13 +115,11 @@ __device__ __forceinline__ void halo_signal(const Halo &h, bool first, bool last
 
 // ------------------------------------------------------------------------------------------------
 // heat2d, vector path: W % 4 == 0, 16-byte aligned rows.  grid = (ceil(W/4/128), ceil(rows/RY)).
-template <int FORM, int RY, bool PEER = false>
-__global__ void __launch_bounds__(128)
-tiramisu_sm100_heat2d_v4(const float *__restrict__ in, float *__restrict__ out, int H, int W,
-                         int row_begin, int row_end, const Halo halo = Halo{})
+template <int FORM, int RY, bool PEER>
+__device__ __forceinline__ void heat2d_v4_body(const float *__restrict__ in, float *__restrict__ out, int H, int W,
+                                               int row_begin, int row_end, const Halo &halo)
 {
     const int lane = threadIdx.x & 31;
-    if (PEER) halo_wait(halo, blockIdx.y == 0, blockIdx.y == gridDim.y - 1);
     const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
     const int y0 = row_begin + blockIdx.y * RY;
     const bool col_ok = x < W;
@@ -175,7 +173,26 @@ tiramisu_sm100_heat2d_v4(const float *__restrict__ in, float *__restrict__ out, 
         }
         __stcs(dst, o);
     }
-    if (PEER) halo_signal(halo, blockIdx.y == 0, blockIdx.y == gridDim.y - 1);
+}
+
+// Only the first and the last row block of a launch can touch a neighbour's rows: they take the
+// halo-aware instantiation (per-row pointer select, volatile loads, handshake); every other CTA runs
+// the instruction stream of the single-GPU kernel unchanged.
+template <int FORM, int RY, bool PEER = false>
+__global__ void __launch_bounds__(128)
+tiramisu_sm100_heat2d_v4(const float *__restrict__ in, float *__restrict__ out, int H, int W,
+                         int row_begin, int row_end, const Halo halo = Halo{})
+{
+    if (PEER) {
+        const bool first = blockIdx.y == 0, last = blockIdx.y == gridDim.y - 1;
+        if (first || last) {
+            halo_wait(halo, first, last);
+            heat2d_v4_body<FORM, RY, true>(in, out, H, W, row_begin, row_end, halo);
+            halo_signal(halo, first, last);
+            return;
+        }
+    }
+    heat2d_v4_body<FORM, RY, false>(in, out, H, W, row_begin, row_end, halo);
 }
 
 // heat2d, generic path (any W, any alignment): one thread per output element.
@@ -220,10 +237,9 @@ __device__ __forceinline__ float blur3(float a, float b, float c)
     return div3(__fadd_rn(__fadd_rn(a, b), c));
 }
 
-template <int RY, bool PEER = false>
-__global__ void __launch_bounds__(128)
-tiramisu_sm100_blur_f32_v4(const float *__restrict__ in, float *__restrict__ out, int H, int W,
-                           int row_begin, int row_end, const Halo halo = Halo{})
+template <int RY, bool PEER>
+__device__ __forceinline__ void blur_f32_v4_body(const float *__restrict__ in, float *__restrict__ out, int H, int W,
+                                                 int row_begin, int row_end, const Halo &halo)
 {
     const int lane = threadIdx.x & 31;
     const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
@@ -269,6 +285,20 @@ tiramisu_sm100_blur_f32_v4(const float *__restrict__ in, float *__restrict__ out
         __stcs(reinterpret_cast<float2 *>(dst), make_float2(o.x, o.y));
         if (x + 2 < OW) __stcs(reinterpret_cast<float2 *>(dst + 2), make_float2(o.z, o.w));
     }
+}
+
+template <int RY, bool PEER = false>
+__global__ void __launch_bounds__(128, PEER ? 8 : 0)      // the halo-aware copy of the body must not cost the interior CTAs occupancy
+tiramisu_sm100_blur_f32_v4(const float *__restrict__ in, float *__restrict__ out, int H, int W,
+                           int row_begin, int row_end, const Halo halo = Halo{})
+{
+    // row blocks whose RY+2 input rows reach past the owned block (the last one, and the one before it
+    // when the last block is short) read the lower neighbour's rows
+    if (PEER && row_begin + (int)blockIdx.y * RY + RY + 2 > halo.hi) {
+        blur_f32_v4_body<RY, true>(in, out, H, W, row_begin, row_end, halo);
+        return;
+    }
+    blur_f32_v4_body<RY, false>(in, out, H, W, row_begin, row_end, halo);
 }
 
 __global__ void __launch_bounds__(256)

@@ -100,63 +100,64 @@ def main():
     print(f"[rank {rank}] sgemm row-sharded: {'ok' if good else 'MISMATCH'}", flush=True)
 
     # ---- 5. peer-memory halos: no exchange, the sweep reads the neighbours' rows over NVLink ---------------
-    Hp, Wp = 48 * world + 7, 2048
-    gridp = np.random.default_rng(21).random((Hp, Wp), dtype=np.float32)
-    rows_of = lambda r: tdist.row_shard(Hp, world, r)
-    p0, p1 = rows_of(rank)
-    sym = tdist.SymmetricRows(max(rows_of(r)[1] - rows_of(r)[0] for r in range(world)), Wp, n_buffers=2)
-    rowb = Wp * 4
-    mine = np.ascontiguousarray(gridp[p0:p1])
+    for Hp in (48 * world + 7, 49 * world, 13 * world + 1):      # row counts that leave short last row blocks
+        Wp = 2048
+        gridp = np.random.default_rng(21).random((Hp, Wp), dtype=np.float32)
+        rows_of = lambda r: tdist.row_shard(Hp, world, r)
+        p0, p1 = rows_of(rank)
+        sym = tdist.SymmetricRows(max(rows_of(r)[1] - rows_of(r)[0] for r in range(world)), Wp, n_buffers=2)
+        rowb = Wp * 4
+        mine = np.ascontiguousarray(gridp[p0:p1])
 
-    def h2d(dst, arr):          # blocking copies of the runtime (tiramisu_cuda_memcpy_to_device / _to_host)
-        _lib.check(L.tiramisu_cuda_memcpy_to_device(C.c_void_p(dst), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        def h2d(dst, arr):          # blocking copies of the runtime (tiramisu_cuda_memcpy_to_device / _to_host)
+            _lib.check(L.tiramisu_cuda_memcpy_to_device(C.c_void_p(dst), arr.ctypes.data_as(C.c_void_p), arr.nbytes))
 
-    def d2h(arr, src):
-        _lib.check(L.tiramisu_cuda_memcpy_to_host(arr.ctypes.data_as(C.c_void_p), C.c_void_p(src), arr.nbytes))
+        def d2h(arr, src):
+            _lib.check(L.tiramisu_cuda_memcpy_to_host(arr.ctypes.data_as(C.c_void_p), C.c_void_p(src), arr.nbytes))
 
-    h2d(sym.buffer(0), mine)
-    torch.cuda.synchronize()
-    torch.distributed.barrier()
-    # (a) single sweep, forms of configs[1]: heat2d + fp32 blur
-    d_o = torch.full((p1 - p0, Wp), float("nan"), device="cuda")
-    h = sym.halo(0, p0, p1, rows_of)
-    _lib.check(L.tiramisu_b200_heat2d_peer(sym.buffer(0) - p0 * rowb, d_o.data_ptr() - p0 * rowb, Hp, Wp, 0, p0, p1, C.byref(h)))
-    api.synchronize()
-    good = np.array_equal(d_o.cpu().numpy(), oracle.heat2d(gridp, "cpu")[p0:p1])
-    ok &= good
-    print(f"[rank {rank}] heat2d peer halos: {'ok' if good else 'MISMATCH'}", flush=True)
-    q0, q1 = min(p0, Hp - 2), min(p1, Hp - 2)
-    d_b = torch.full((max(q1 - q0, 1), Wp - 2), float("nan"), device="cuda")
-    _lib.check(L.tiramisu_b200_blur_f32_peer(sym.buffer(0) - p0 * rowb, d_b.data_ptr() - q0 * (Wp - 2) * 4, Hp, Wp, q0, q1, C.byref(h)))
-    api.synchronize()
-    good = np.array_equal(d_b.cpu().numpy()[: q1 - q0], oracle.blur_f32(gridp)[q0:q1])
-    ok &= good
-    print(f"[rank {rank}] blur_f32 peer halos: {'ok' if good else 'MISMATCH'}", flush=True)
-    # (b) iterated even/odd Jacobi (heat2d_dist_tiramisu.cpp:88-153), ITERS sweeps back to back on the
-    # stream, neighbours synchronised only through the flag words inside the sweep kernels
-    iters = 12
-    h2d(sym.buffer(1), mine)                                         # both buffers start as the input (borders persist)
-    torch.cuda.synchronize()
-    torch.distributed.barrier()
-    for t in range(iters):
-        a, b = t % 2, (t + 1) % 2
-        h = sym.halo(a, p0, p1, rows_of, sync=True, wait_value=t, signal_value=t + 1)
-        _lib.check(L.tiramisu_b200_heat2d_peer(sym.buffer(a) - p0 * rowb, sym.buffer(b) - p0 * rowb, Hp, Wp, 2, p0, p1, C.byref(h)))
-    api.synchronize()
-    ev, od = gridp.copy(), gridp.copy()
-    for t in range(iters):
-        if t % 2 == 0:
-            oracle.heat2d_step(ev, od)
-        else:
-            oracle.heat2d_step(od, ev)
-    want_j = ev if iters % 2 == 0 else od
-    got_j = np.empty((p1 - p0, Wp), np.float32)
-    d2h(got_j, sym.buffer(iters % 2))
-    good = np.array_equal(got_j, want_j[p0:p1])
-    ok &= good
-    print(f"[rank {rank}] heat2d_dist {iters} Jacobi sweeps, flag handshake in the kernels: {'ok' if good else 'MISMATCH'}", flush=True)
-    torch.distributed.barrier()
-    sym.free()
+        h2d(sym.buffer(0), mine)
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        # (a) single sweep, forms of configs[1]: heat2d + fp32 blur
+        d_o = torch.full((p1 - p0, Wp), float("nan"), device="cuda")
+        h = sym.halo(0, p0, p1, rows_of)
+        _lib.check(L.tiramisu_b200_heat2d_peer(sym.buffer(0) - p0 * rowb, d_o.data_ptr() - p0 * rowb, Hp, Wp, 0, p0, p1, C.byref(h)))
+        api.synchronize()
+        good = np.array_equal(d_o.cpu().numpy(), oracle.heat2d(gridp, "cpu")[p0:p1])
+        ok &= good
+        print(f"[rank {rank}] heat2d peer halos H={Hp}: {'ok' if good else 'MISMATCH'}", flush=True)
+        q0, q1 = min(p0, Hp - 2), min(p1, Hp - 2)
+        d_b = torch.full((max(q1 - q0, 1), Wp - 2), float("nan"), device="cuda")
+        _lib.check(L.tiramisu_b200_blur_f32_peer(sym.buffer(0) - p0 * rowb, d_b.data_ptr() - q0 * (Wp - 2) * 4, Hp, Wp, q0, q1, C.byref(h)))
+        api.synchronize()
+        good = np.array_equal(d_b.cpu().numpy()[: q1 - q0], oracle.blur_f32(gridp)[q0:q1])
+        ok &= good
+        print(f"[rank {rank}] blur_f32 peer halos H={Hp}: {'ok' if good else 'MISMATCH'}", flush=True)
+        # (b) iterated even/odd Jacobi (heat2d_dist_tiramisu.cpp:88-153), ITERS sweeps back to back on the
+        # stream, neighbours synchronised only through the flag words inside the sweep kernels
+        iters = 12
+        h2d(sym.buffer(1), mine)                                         # both buffers start as the input (borders persist)
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        for t in range(iters):
+            a, b = t % 2, (t + 1) % 2
+            h = sym.halo(a, p0, p1, rows_of, sync=True, wait_value=t, signal_value=t + 1)
+            _lib.check(L.tiramisu_b200_heat2d_peer(sym.buffer(a) - p0 * rowb, sym.buffer(b) - p0 * rowb, Hp, Wp, 2, p0, p1, C.byref(h)))
+        api.synchronize()
+        ev, od = gridp.copy(), gridp.copy()
+        for t in range(iters):
+            if t % 2 == 0:
+                oracle.heat2d_step(ev, od)
+            else:
+                oracle.heat2d_step(od, ev)
+        want_j = ev if iters % 2 == 0 else od
+        got_j = np.empty((p1 - p0, Wp), np.float32)
+        d2h(got_j, sym.buffer(iters % 2))
+        good = np.array_equal(got_j, want_j[p0:p1])
+        ok &= good
+        print(f"[rank {rank}] heat2d_dist H={Hp} {iters} Jacobi sweeps, flag handshake in the kernels: {'ok' if good else 'MISMATCH'}", flush=True)
+        torch.distributed.barrier()
+        sym.free()
 
     flag = torch.tensor([1 if ok else 0], device="cuda")
     torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
