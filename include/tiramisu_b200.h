@@ -110,6 +110,9 @@ int tiramisu_b200_heat2d(const float *in, float *out, int32_t H, int32_t W, int3
 /* 3x3 separable blurs.  f32: in[H][W] -> out[H-2][W-2] (horizontal first, /3.0f).
  * u8 : blurxy_tiramisu.cpp:61,77   in[C][H][W] -> out[C][H-8][W-8], wraps mod 256.
  * u32: tests/test_160.cpp:23-29    in[rows+2][cols+2] -> out[rows][cols], vertical first. */
+/* heat2d on halide buffers (host: row-chunk pipelined copies; device-resident: in place).  Called by
+ * generated code when the lowering recognises the statement pair of heat2d_tiramisu.cpp:52-69. */
+int tiramisu_b200_heat2d_buffers(halide_buffer_t *in, halide_buffer_t *out, int32_t H, int32_t W, int32_t form);
 int tiramisu_b200_blur_f32(const float *in, float *out, int32_t H, int32_t W,
                            int32_t row_begin, int32_t row_end);
 

@@ -38,6 +38,9 @@ TARGETS = {
                              [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
     "sgemm_gpu_generator3": (f"{SGEMM_GPU}/generator3.cpp", "fct.o", f"{SGEMM_GPU}/wrapper.cpp", [SGEMM_GPU],
                              [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
+    # BASELINE configs[1]'s own generator: old-style ISL-string API, CPU schedule (parallel y, vectorize x by 8)
+    "heat2d": ("benchmarks/halide/heat2d_tiramisu.cpp", "build/generated_fct_heat2d.o", "benchmarks/halide/wrapper_heat2d.cpp",
+               ["benchmarks/halide"], []),
 }
 
 
@@ -67,7 +70,7 @@ def build_one(name: str, lowering: str | None = None) -> tuple[int, str]:
     gen_exe = os.path.join(work, "generator")
     log = ""
     # 1. the reference generator, unmodified, against this repo's front-end
-    cmd = ["g++", "-std=c++17", "-O1", "-w", "-I", FRONT_INC, *inc, os.path.join(REF, gsrc), "-o", gen_exe,
+    cmd = ["g++", "-std=c++17", "-O1", "-w", "-I", FRONT_INC, "-I", os.path.join(FRONT_INC, "compat"), *inc, os.path.join(REF, gsrc), "-o", gen_exe,
            f"-L{LIBDIR}", "-ltiramisu_b200_frontend", f"-Wl,-rpath,{LIBDIR}"]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     log += r.stdout + r.stderr
@@ -104,7 +107,7 @@ def build(names=None, verbose=False) -> dict:
         if verbose:
             print(name, "OK" if out[name][0] == 0 else "FAILED\n" + out[name][1], flush=True)
     # the two GEMM-pattern generators once more with the pattern lowering off (generic SIMT emission)
-    for name in ("test_167", "test_169"):
+    for name in ("test_167", "test_169", "heat2d"):
         if names and name not in names:
             continue
         out[name + "_generic"] = build_one(name, "generic")

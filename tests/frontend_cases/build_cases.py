@@ -18,10 +18,14 @@ FRONT_INC = os.path.join(ROOT, "tiramisu_b200", "frontend", "include")
 
 # library name -> (generator source, argv[1] for the generator or None, lowering mode or None)
 CASES = {
-    "heat2d_gen": ("heat2d_gen.cpp", None, None),
+    "heat2d_gen": ("heat2d_gen.cpp", "heat2d_gen", None),                  # statement pair -> the runtime's heat2d kernel
+    "heat2d_gen_generic": ("heat2d_gen.cpp", "heat2d_gen_generic", "generic"),   # the two kernels the lowering emits itself
     "blurxy_u8_gen": ("blurxy_u8_gen.cpp", None, None),
     "gemm_sym_gen": ("gemm_sym_gen.cpp", "gemm_sym_gen", None),
     "gemm_sym_generic": ("gemm_sym_gen.cpp", "gemm_sym_generic", "generic"),
+    # CPU schedules (no gpu level, codegen without the gpu flag): re-targeted to sm_100a by the lowering
+    "blur_f32_cpu_gen": ("blur_f32_cpu_gen.cpp", None, None),
+    "sgemm_cpu_sched_gen": ("sgemm_cpu_sched_gen.cpp", None, "generic"),
 }
 
 

@@ -8,7 +8,7 @@ using namespace tiramisu;
 
 int main(int argc, char **argv)
 {
-    tiramisu::init("heat2d_gen");
+    tiramisu::init(argc > 1 ? argv[1] : "heat2d_gen");
 
     input sizes("sizes", {"s_i"}, {2}, p_int32);
     constant H("H", sizes(0));
@@ -44,6 +44,6 @@ int main(int argc, char **argv)
            .then(heat, computation::root)
            .then(copy_out, computation::root);
 
-    tiramisu::codegen({sizes.get_buffer(), &b_in, &b_out}, "heat2d_gen.o", true);
+    tiramisu::codegen({sizes.get_buffer(), &b_in, &b_out}, std::string(argc > 1 ? argv[1] : "heat2d_gen") + ".o", true);
     return 0;
 }

@@ -50,10 +50,12 @@ def cases(frontend_lib):
 
 
 def test_own_generators_lower_to_sm100a(cases):
-    for name in ("heat2d_gen", "blurxy_u8_gen", "gemm_sym_generic"):      # (gemm_sym_gen has no kernel of its own)
+    for name in ("heat2d_gen_generic", "blurxy_u8_gen", "gemm_sym_generic"):      # (the pattern-lowered ones have no kernel of their own)
         out = subprocess.check_output(["cuobjdump", "-lelf", bc.lib_path(name)], text=True)
         assert set(re.findall(r"sm_\d+a?", out)) == {"sm_100a"}, (name, out)
-    heat = open(bc.generated_source("heat2d_gen")).read()
+    pat = open(bc.generated_source("heat2d_gen")).read()
+    assert "__global__" not in pat and "tiramisu_b200_heat2d(b_b_in_gpu, b_b_out_gpu, (int32_t) (c_H), (int32_t) (c_W), 0, 0, (int32_t) (c_H))" in pat
+    heat = open(bc.generated_source("heat2d_gen_generic")).read()
     # innermost iterator on threadIdx.x (coalesced rows), read-only input through the non-coherent path
     assert "threadIdx.x" in heat and "const float * __restrict__ b_b_in_gpu" in heat
     assert "0x1.333334p-2f" in heat and "0x1.99999ap-2f" in heat          # 0.3f, 0.4f exactly
@@ -70,17 +72,55 @@ def test_contraction_pattern_lowers_to_runtime_gemm(cases):
     assert "__global__" in gen and "tiramisu_cublas_sgemm(" not in gen.split("__global__", 1)[1]
 
 
+def test_cpu_schedules_are_retargeted_not_run_on_the_host(cases):
+    """codegen(args, obj) without the gpu flag: parallelize/vectorize nests become sm_100a kernels with
+    device mirrors for the host arguments; parameter vectors read only by constants stay on the host."""
+    blur = open(bc.generated_source("blur_f32_cpu_gen")).read()
+    assert "__global__" in blur and "dim3 block((unsigned) (8), (unsigned) (16)" in blur        # 8 lanes x 16 = 128 consecutive x
+    assert "tiramisu_cuda_memcpy_to_device_async(b_b_in, h_b_in" in blur
+    assert "tiramisu_cuda_memcpy_to_device_async(b_b_out" not in blur                            # fully overwritten output: no copy-in
+    assert "tiramisu_cuda_memcpy_to_host(h_b_out, b_b_out" in blur
+    sg = open(bc.generated_source("sgemm_cpu_sched_gen")).read()
+    assert "for (int32_t v9_k = 0; v9_k < c_K; v9_k++)" in sg                                    # the reduction loop stays sequential in the thread
+    assert "b__SIZES_buffer = (int32_t *) tb_arg(arg0)" in sg and "h__SIZES_buffer" not in sg
+    assert "tiramisu_cuda_memcpy_to_device_async(b_b_C, h_b_C" in sg                             # C is read (beta*C): copied in
+
+
+def test_non_box_domains_are_rejected(frontend_lib, tmp_path):
+    src = tmp_path / "bad.cpp"
+    src.write_text("""
+#include <tiramisu/tiramisu.h>
+using namespace tiramisu;
+int main() {
+    tiramisu::function f("bad");
+    computation c("[N]->{c[i,j]: 0<=i<N and (j = 0 or j = N - 1)}", expr(0.f), true, p_float32, &f);
+    return 0;
+}""")
+    exe = str(tmp_path / "bad")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.check_call(["g++", "-std=c++17", "-O0", "-w", "-I", os.path.join(ROOT, "tiramisu_b200/frontend/include"), str(src), "-o", exe,
+                           f"-L{os.path.dirname(frontend_lib)}", "-ltiramisu_b200_frontend", f"-Wl,-rpath,{os.path.dirname(frontend_lib)}"], env=env)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode != 0 and "not boxes" in r.stderr, r.stderr
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference")
 def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     res = bg.build()
     failed = {k: v[1] for k, v in res.items() if v[0] != 0}
     assert not failed, failed
-    assert len(res) == len(bg.TARGETS) + 2
+    assert len(res) == len(bg.TARGETS) + 3
     # the hand-scheduled GEMM of sgemm/gpu/generator1.cpp keeps its structure: two shared buffers,
     # per-thread accumulators with compile-time indices (registers, no local memory), two barriers
     src = open(os.path.join(bg.GEN, "sgemm_gpu_generator1", "fct.o.b200.cu")).read()
     assert "__shared__ float b_b_A_shr[8224];" in src and "__shared__ float b_b_B_shr[3072];" in src
     assert src.count("__syncthreads();") == 2 and "b_b_acc[(i_i1) * 6 + i_j1]" in src
+    # benchmarks/halide/heat2d_tiramisu.cpp (ISL-string API, CPU schedule): the statement pair is recognised
+    # and handed to the runtime's heat2d entry point; with the pattern lowering off, two generated kernels
+    heat = open(os.path.join(bg.GEN, "heat2d", "build", "generated_fct_heat2d.o.b200.cu")).read()
+    assert "tiramisu_b200_heat2d_buffers(arg0, arg1, (int32_t) (10000), (int32_t) (10000), 0)" in heat and "__global__" not in heat
+    gen = open(os.path.join(bg.GEN, "heat2d_generic", "build", "generated_fct_heat2d.o.b200.cu")).read()
+    assert gen.count("__global__") == 2 and "tiramisu_b200_heat2d" not in gen.split("extern \"C\" int heat2d_tiramisu(")[1]
 
 
 # ------------------------------------------------------------------------------------------------ GPU
@@ -114,6 +154,17 @@ def test_reference_sgemm_gpu_generators_match_cublas(gen, tmp_path):
     assert "cuBLAS and Tiramisu outputs match" in out, out[-2000:]
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["heat2d", "heat2d_generic"])
+def test_reference_heat2d_generator_through_lowering(name, tmp_path):
+    """benchmarks/halide/heat2d_tiramisu.cpp (BASELINE configs[1]'s own generator: ISL-string domains, CPU
+    schedule) compiled unmodified; benchmarks/halide/wrapper_heat2d.cpp runs it on 10000 x 10000 and
+    compares with heat2d_ref.  `heat2d` = pattern-lowered to the runtime kernel, `heat2d_generic` = the
+    two kernels the lowering emits itself."""
+    out = _run(name, cwd=tmp_path)
+    assert "heat2d" in out
+
+
 def _load(name):
     path = bc.lib_path(name)
     if not os.path.exists(path):
@@ -133,14 +184,15 @@ def _call(lib, fn, *arrays):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["heat2d_gen", "heat2d_gen_generic"])
 @pytest.mark.parametrize("shape", [(64, 64), (130, 260), (1, 5), (3, 3), (1027, 515)])
-def test_generated_heat2d_bit_exact(shape):
+def test_generated_heat2d_bit_exact(shape, variant):
     from oracle import oracle
-    lib = _load("heat2d_gen")
+    lib = _load(variant)
     rng = np.random.default_rng(11)
     a = rng.random(shape, dtype=np.float32)
     out = np.full(shape, -7.0, np.float32)
-    _call(lib, "heat2d_gen", np.array(shape, np.int32), a, out)
+    _call(lib, variant, np.array(shape, np.int32), a, out)
     assert np.array_equal(out, oracle.heat2d(a, "cpu"))
 
 
@@ -202,3 +254,32 @@ def test_generated_contraction_generic_path_bit_exact(mnk):
     for kk in range(k):
         want = want + A[:, kk:kk + 1] * Bt[:, kk][None, :]
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw", [(16, 24), (67, 131), (3, 3), (300, 1000)])
+def test_retargeted_cpu_schedule_blur_bit_exact(hw):
+    from oracle import oracle
+    lib = _load("blur_f32_cpu_gen")
+    h, w = hw
+    a = np.random.default_rng(16).random((h, w), dtype=np.float32)
+    out = np.full((h - 2, w - 2), -1.0, np.float32)
+    _call(lib, "blur_f32_cpu_gen", np.array([h, w], np.int32), a, out)
+    assert np.array_equal(out, oracle.blur_f32(a))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nmk", [(64, 64, 64), (100, 36, 52), (33, 130, 17)])
+def test_retargeted_cpu_schedule_sgemm_bit_exact(nmk):
+    """sgemm_tiramisu's statement (acc = 0; acc += A*B over k; C = a*acc + b*C) and argument list, CPU
+    schedule, re-targeted: bit-exact against the oracle's restatement of the x86 loop nest."""
+    from oracle import oracle
+    lib = _load("sgemm_cpu_sched_gen")
+    n, m, k = nmk
+    rng = np.random.default_rng(17)
+    A = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    B = rng.uniform(-1, 1, (k, m)).astype(np.float32)
+    Cm = rng.uniform(-1, 1, (n, m)).astype(np.float32)
+    got = Cm.copy()
+    _call(lib, "sgemm_cpu_sched_gen", np.array([n, m, k], np.int32), np.array([1.5], np.float32), np.array([-0.75], np.float32), A, B, got)
+    assert np.array_equal(got, oracle.sgemm(1.5, -0.75, A, B, Cm.copy()))

@@ -64,6 +64,7 @@ public:
     computation *allocate_at(computation &C, int level);
     computation *deallocate_at(computation &C, var level);
     void dump(bool) const;
+    void substitute_dims(const std::vector<std::string> &names, const std::vector<expr> &values);
 
 private:
     std::string name_;
@@ -98,6 +99,9 @@ public:
     computation(std::vector<var> iterator_variables, primitive_t t);
     computation(std::string name, std::vector<var> iterator_variables, expr predicate, expr e);
     computation(std::vector<var> iterator_variables, expr predicate, expr e);
+    /** Old-style declaration with an ISL set string (reference core.h:3236).  Only boxes are accepted:
+      * `[params]->{S[i,j]: lo <= i <= hi and lo2 <= j < hi2}`; anything else stops the generator. */
+    computation(std::string iteration_domain, expr e, bool schedule_this_computation, primitive_t t, function *fct);
     virtual ~computation() {}
 
     // ---- Layer I
@@ -172,6 +176,8 @@ public:
     buffer *get_buffer();
     buffer *get_automatically_allocated_buffer() { return get_buffer(); }
     void set_access_exprs(buffer *b, std::vector<expr> idx);
+    /** Old-style data mapping, `{S[i,j]->buf[i+1,j]}` (reference core.h:4180). */
+    void set_access(std::string access_str);
 
     // ---- used by the lowering
     std::vector<loop_dim> &dims() { return dims_; }
@@ -187,9 +193,13 @@ public:
     bool is_constant() const { return is_constant_; }
     int find_dim(const std::string &name) const;
     void dump() const;
+    /** Replace named scalars by values in every expression the computation holds (constant propagation). */
+    void substitute_everywhere(const std::vector<std::string> &names, const std::vector<expr> &values);
+    /** True when every guard only cuts the excess of a non-dividing split (the original box is still covered). */
+    bool guards_only_trim() const { return true; }
 
 protected:
-    void construct(std::string name, std::vector<var> iters, expr e, bool schedule, primitive_t t);
+    void construct(std::string name, std::vector<var> iters, expr e, bool schedule, primitive_t t, function *fct = nullptr);
     expr access_expr(const std::vector<expr> &idx);
     void tag(const var &L, loop_dim::tag_t t);
     void link_after(computation &before_this, const std::string &level_name, int level_index);
@@ -258,6 +268,21 @@ public:
     const std::vector<buffer *> &get_arguments() const { return args_; }
     void codegen(const std::vector<buffer *> &arguments, const std::string obj_filename, bool gen_cuda_stmt);
     void dump(bool) const;
+    // Old-style driver sequence (reference core.h:289-1166).  The intermediate stages have no
+    // counterpart here (no ISL AST, no Halide statement): they only record what was asked for and
+    // gen_halide_obj() runs the whole lowering.  A function without gpu levels is a CPU schedule; this
+    // back end has no CPU code generator, so such a function is re-targeted (lowering.cpp: retarget).
+    void add_context_constraints(const std::string &) {}
+    void gen_time_space_domain() {}
+    void gen_isl_ast() {}
+    void gen_halide_stmt() {}
+    void gen_cuda_stmt() { cuda_requested_ = true; }
+    void dump_halide_stmt() const {}
+    void gen_halide_obj(const std::string &obj_file_name, bool gen_python = false);
+    void gen_c_code() const {}
+    void dump_iteration_domain() const {}
+    void dump_schedule() const {}
+    void dump_sched_graph() {}
 
 private:
     std::string name_;
@@ -266,6 +291,7 @@ private:
     std::vector<buffer *> args_;
     std::vector<std::shared_ptr<void>> owned_;
     int counter_ = 0;
+    bool cuda_requested_ = false;
 };
 
 }  // namespace tiramisu

@@ -17,7 +17,16 @@ namespace tiramisu {
 }
 
 // ---- function -----------------------------------------------------------------------------------
-function::function(std::string name) : name_(std::move(name)) {}
+function::function(std::string name) : name_(std::move(name))
+{
+    // an explicitly declared function becomes the implicit one for objects declared without it
+    if (!global::get_implicit_function()) global::set_implicit_function(this);
+}
+
+void function::gen_halide_obj(const std::string &obj_file_name, bool)
+{
+    codegen(args_, obj_file_name, cuda_requested_);
+}
 
 computation *function::find_computation(const std::string &name) const
 {
@@ -90,15 +99,19 @@ computation *buffer::deallocate_at(computation &C, var level)
     return fct_->own(c);
 }
 void buffer::dump(bool) const { std::cerr << "buffer " << name_ << "\n"; }
+void buffer::substitute_dims(const std::vector<std::string> &names, const std::vector<expr> &values)
+{
+    for (expr &d : dims_) d = d.substitute(names, values);
+}
 
 // ---- computation ----------------------------------------------------------------------------------
 const var computation::root("");
 
 computation::computation() {}
 
-void computation::construct(std::string name, std::vector<var> iters, expr e, bool schedule, primitive_t t)
+void computation::construct(std::string name, std::vector<var> iters, expr e, bool schedule, primitive_t t, function *fct)
 {
-    fct_ = global::get_implicit_function();
+    fct_ = fct ? fct : global::get_implicit_function();
     if (!fct_) die("computation declared before tiramisu::init()");
     name_ = name.empty() ? fct_->fresh_name("_C") : std::move(name);
     iters_ = std::move(iters);
@@ -154,6 +167,18 @@ void computation::dump() const
     std::cerr << name_ << " [";
     for (auto &d : dims_) std::cerr << " " << d.name << ":" << d.lo.to_str() << ".." << d.hi.to_str() << (d.tag ? "#" + std::to_string((int) d.tag) : "");
     std::cerr << " ] = " << expr_.to_str() << "\n";
+}
+
+void computation::substitute_everywhere(const std::vector<std::string> &names, const std::vector<expr> &values)
+{
+    expr_ = expr_.substitute(names, values);
+    predicate_ = predicate_.substitute(names, values);
+    for (auto &d : dims_) { d.lo = d.lo.substitute(names, values); d.hi = d.hi.substitute(names, values); }
+    for (auto &d : defs_) d.second = d.second.substitute(names, values);
+    for (auto &g : guards_) g = g.substitute(names, values);
+    for (auto &a : access_) a = a.substitute(names, values);
+    for (var &v : iters_)
+        if (v.has_range()) v = var(v.get_name(), v.get_lower().substitute(names, values), v.get_upper().substitute(names, values));
 }
 
 // -- Layer II
@@ -385,15 +410,15 @@ static std::vector<var> sized_iters(const std::vector<expr> &sizes)
 }
 Input::Input(std::string name, std::vector<expr> sizes, primitive_t t) : input(name, sized_iters(sizes), t) {}
 
-constant::constant(std::string name, const expr &e, primitive_t t, bool function_wide, computation *, int, function *)
+constant::constant(std::string name, const expr &e, primitive_t t, bool function_wide, computation *, int, function *func)
 {
     if (!function_wide) die("constant '" + name + "': only function-wide constants are supported");
-    construct(name, {}, e, false, t);
+    construct(name, {}, e, false, t, func);
     is_constant_ = true;
 }
-constant::constant(std::string name, const expr &e, primitive_t t, function *)
+constant::constant(std::string name, const expr &e, primitive_t t, function *func)
 {
-    construct(name, {}, e, false, t);
+    construct(name, {}, e, false, t, func);
     is_constant_ = true;
 }
 constant::constant(std::string name, const expr &e)

@@ -145,6 +145,13 @@ expr::expr(op_t o, expr a, expr b)
             }
             if (ok) { *this = value_cast_i(t, r); return; }
         }
+        // (x + c1) +- c2  ->  x + (c1 +- c2): keeps `(lo + extent) + -1 + 1` style ISL bounds readable
+        if (is_int_type(t) && (o == o_add || o == o_sub) && b.is_int_literal() && a.get_expr_type() == e_op &&
+            a.get_op_type() == o_add && a.get_operand(1).is_int_literal() && a.get_data_type() == t) {
+            int64_t c = a.get_operand(1).get_int_val() + (o == o_add ? b.get_int_val() : -b.get_int_val());
+            *this = expr(o_add, a.get_operand(0), value_cast_i(t, c));
+            return;
+        }
         // x + 0, x * 1, x - 0, 0 + x, 1 * x, x * 0
         if (is_int_type(t)) {
             if (b.is_int_literal() && ((b.get_int_val() == 0 && (o == o_add || o == o_sub)) || (b.get_int_val() == 1 && (o == o_mul || o == o_div)))) { *this = a; return; }

@@ -1,0 +1,251 @@
+// isl_box.cpp — the old-style, string-based declarations of the reference API, without ISL.
+//
+// The reference's Halide-derived generators (benchmarks/halide/heat2d_tiramisu.cpp:44-69 and friends)
+// declare iteration domains as ISL set strings and data mappings as ISL map strings
+// (reference include/tiramisu/core.h:3236 and :4180).  Every domain the hot-path generators write is
+// a box — a conjunction of `lo <= it <= hi` chains over affine bounds in function constants — so a
+// small recursive-descent reader is enough: it produces the same (name, [lo, hi)) list the modern
+// `var("i", lo, hi)` API produces.  Anything that is not a box (disjunctions, constraints coupling two
+// iterators) stops the generator with a message instead of being mis-compiled.
+#include <tiramisu/core.h>
+
+#include <algorithm>
+#include <cctype>
+#include <cstdlib>
+#include <iostream>
+
+namespace tiramisu {
+namespace {
+
+[[noreturn]] void die(const std::string &msg)
+{
+    std::cerr << "tiramisu_b200 front-end: " << msg << std::endl;
+    std::exit(1);
+}
+
+struct Tok { enum K { id, num, sym, end } k = end; std::string s; int64_t v = 0; };
+
+class Reader {
+public:
+    explicit Reader(const std::string &text) : text_(text) { lex(); }
+
+    const Tok &peek(int ahead = 0) const { return toks_[std::min(pos_ + (size_t) ahead, toks_.size() - 1)]; }
+    Tok next() { Tok t = peek(); if (pos_ < toks_.size() - 1) pos_++; return t; }
+    bool accept(const std::string &s) { if (peek().k != Tok::end && peek().s == s) { next(); return true; } return false; }
+    void expect(const std::string &s) { if (!accept(s)) fail("expected '" + s + "'"); }
+    size_t mark() const { return pos_; }
+    void reset(size_t m) { pos_ = m; }
+    [[noreturn]] void fail(const std::string &why) const { die(why + " near '" + peek().s + "' in \"" + text_ + "\""); }
+
+    // affine-ish integer expression
+    expr parse_expr()
+    {
+        expr e = parse_term();
+        for (;;) {
+            if (accept("+")) e = e + parse_term();
+            else if (accept("-")) e = e - parse_term();
+            else return e;
+        }
+    }
+
+    static bool is_cmp(const std::string &s) { return s == "<=" || s == "<" || s == ">=" || s == ">" || s == "="; }
+
+private:
+    std::string text_;
+    std::vector<Tok> toks_;
+    size_t pos_ = 0;
+
+    void lex()
+    {
+        size_t i = 0, n = text_.size();
+        while (i < n) {
+            char c = text_[i];
+            if (isspace((unsigned char) c)) { i++; continue; }
+            Tok t;
+            if (isalpha((unsigned char) c) || c == '_') {
+                size_t j = i;
+                while (j < n && (isalnum((unsigned char) text_[j]) || text_[j] == '_' || text_[j] == '\'')) j++;
+                t.k = Tok::id; t.s = text_.substr(i, j - i); i = j;
+            } else if (isdigit((unsigned char) c)) {
+                size_t j = i;
+                while (j < n && isdigit((unsigned char) text_[j])) j++;
+                t.k = Tok::num; t.s = text_.substr(i, j - i); t.v = std::strtoll(t.s.c_str(), nullptr, 10); i = j;
+            } else {
+                t.k = Tok::sym;
+                t.s = std::string(1, c);
+                size_t len = 1;
+                for (const char *w : {"->", "<=", ">=", "==", "!="})
+                    if (text_.compare(i, 2, w) == 0) { t.s = w; len = 2; }
+                if (t.s == "==") t.s = "=";
+                i += len;
+            }
+            toks_.push_back(t);
+        }
+        toks_.push_back(Tok());
+    }
+
+    expr parse_term()
+    {
+        expr e = parse_unary();
+        for (;;) {
+            if (accept("*")) e = e * parse_unary();
+            else if (accept("/")) e = e / parse_unary();
+            else if (accept("%") || (peek().k == Tok::id && peek().s == "mod" && (next(), true))) e = e % parse_unary();
+            else return e;
+        }
+    }
+    expr parse_unary()
+    {
+        if (accept("-")) return -parse_unary();
+        if (accept("+")) return parse_unary();
+        return parse_primary();
+    }
+    expr parse_primary()
+    {
+        if (peek().k == Tok::num) return expr((int32_t) next().v);
+        if (accept("(")) { expr e = parse_expr(); expect(")"); return e; }
+        if (peek().k == Tok::id) {
+            std::string name = next().s;
+            if (name == "floor" || name == "floord") { expect("("); expr e = parse_expr(); expect(")"); return e; }   // floor(a / b): operands are non-negative here
+            return expr::make_var(global::get_loop_iterator_data_type(), name);
+        }
+        fail("expected an expression");
+    }
+};
+
+struct Cmp { expr l, r; std::string op; };
+
+void parse_conjunction(Reader &rd, std::vector<Cmp> &out)
+{
+    for (;;) {
+        // a chain `e1 op e2 [op e3]`, or a parenthesised conjunction
+        size_t m = rd.mark();
+        bool chain = false;
+        if (!(rd.peek().k == Tok::sym && rd.peek().s == "(")) chain = true;
+        else {
+            // '(' may open an expression operand: look for a comparison right after the matching ')'
+            int depth = 0, k = 0;
+            for (;; k++) {
+                const Tok &t = rd.peek(k);
+                if (t.k == Tok::end) break;
+                if (t.s == "(") depth++;
+                if (t.s == ")" && --depth == 0) break;
+            }
+            chain = Reader::is_cmp(rd.peek(k + 1).s);
+        }
+        if (chain) {
+            expr prev = rd.parse_expr();
+            if (!Reader::is_cmp(rd.peek().s)) rd.fail("expected a comparison");
+            while (Reader::is_cmp(rd.peek().s)) {
+                std::string op = rd.next().s;
+                expr nxt = rd.parse_expr();
+                out.push_back({prev, nxt, op});
+                prev = nxt;
+            }
+        } else {
+            rd.reset(m);
+            rd.expect("(");
+            parse_conjunction(rd, out);
+            rd.expect(")");
+        }
+        if (rd.peek().k == Tok::id && rd.peek().s == "and") { rd.next(); continue; }
+        if (rd.peek().k == Tok::id && rd.peek().s == "or") rd.fail("disjunctions are not boxes: only rectangular iteration domains are supported");
+        return;
+    }
+}
+
+std::vector<std::string> parse_name_list(Reader &rd)
+{
+    std::vector<std::string> names;
+    rd.expect("[");
+    if (!rd.accept("]")) {
+        do {
+            if (rd.peek().k != Tok::id) rd.fail("expected an identifier");
+            names.push_back(rd.next().s);
+        } while (rd.accept(","));
+        rd.expect("]");
+    }
+    return names;
+}
+
+}  // namespace
+
+computation::computation(std::string iteration_domain, expr e, bool schedule_this_computation, primitive_t t, function *fct)
+{
+    Reader rd(iteration_domain);
+    if (rd.peek().s == "[") { parse_name_list(rd); rd.expect("->"); }       // parameters: resolved by name later
+    rd.expect("{");
+    if (rd.peek().k != Tok::id) rd.fail("expected the computation name");
+    std::string name = rd.next().s;
+    std::vector<std::string> iters = parse_name_list(rd);
+    std::vector<Cmp> cmps;
+    if (rd.accept(":")) parse_conjunction(rd, cmps);
+    rd.expect("}");
+
+    std::vector<expr> lo(iters.size()), hi(iters.size());
+    auto iter_index = [&](const expr &x) {
+        if (x.get_expr_type() != e_var) return -1;
+        for (size_t i = 0; i < iters.size(); i++) if (iters[i] == x.get_name()) return (int) i;
+        return -1;
+    };
+    auto mentions_iter = [&](const expr &x) {
+        for (const std::string &it : iters)
+            if (!x.substitute({it}, {expr((int32_t) 0)}).is_equal(x)) return true;
+        return false;
+    };
+    for (const Cmp &c : cmps) {
+        int li = iter_index(c.l), ri = iter_index(c.r);
+        if (li >= 0 && ri < 0 && !mentions_iter(c.r)) {
+            if (c.op == "<=") hi[li] = c.r + 1; else if (c.op == "<") hi[li] = c.r;
+            else if (c.op == ">=") lo[li] = c.r; else if (c.op == ">") lo[li] = c.r + 1;
+            else { lo[li] = c.r; hi[li] = c.r + 1; }
+        } else if (ri >= 0 && li < 0 && !mentions_iter(c.l)) {
+            if (c.op == "<=") lo[ri] = c.l; else if (c.op == "<") lo[ri] = c.l + 1;
+            else if (c.op == ">=") hi[ri] = c.l + 1; else if (c.op == ">") hi[ri] = c.l;
+            else { lo[ri] = c.l; hi[ri] = c.l + 1; }
+        } else if (li < 0 && ri < 0 && !mentions_iter(c.l) && !mentions_iter(c.r)) {
+            continue;                                    // a constraint on parameters only: context, not a bound
+        } else {
+            die("iteration domain of '" + name + "' is not a box (constraint couples iterators): \"" + iteration_domain + "\"");
+        }
+    }
+    std::vector<var> vars;
+    for (size_t i = 0; i < iters.size(); i++) {
+        if (lo[i].is_defined() && hi[i].is_defined()) vars.push_back(var(iters[i], lo[i], hi[i]));
+        else if (!schedule_this_computation) vars.push_back(var(iters[i]));
+        else die("iterator '" + iters[i] + "' of '" + name + "' has no lower or no upper bound in \"" + iteration_domain + "\"");
+    }
+    construct(name, vars, e, schedule_this_computation, t, fct);
+    is_input_ = !schedule_this_computation && !e.is_defined();
+}
+
+void computation::set_access(std::string access_str)
+{
+    Reader rd(access_str);
+    if (rd.peek().s == "[") { parse_name_list(rd); rd.expect("->"); }
+    rd.expect("{");
+    if (rd.peek().k != Tok::id) rd.fail("expected the computation name");
+    rd.next();
+    std::vector<std::string> names = parse_name_list(rd);
+    rd.expect("->");
+    if (rd.peek().k != Tok::id) rd.fail("expected a buffer name");
+    std::string bname = rd.next().s;
+    std::vector<expr> idx;
+    rd.expect("[");
+    if (!rd.accept("]")) {
+        do idx.push_back(rd.parse_expr()); while (rd.accept(","));
+        rd.expect("]");
+    }
+    rd.accept(":");      // (conditions on accesses are not used by the hot-path generators)
+    if (names.size() != iters_.size())
+        die("set_access of '" + name_ + "': " + std::to_string(names.size()) + " iterators named, the computation has " + std::to_string(iters_.size()));
+    buffer *b = fct_->find_buffer(bname);
+    if (!b) die("set_access of '" + name_ + "': unknown buffer '" + bname + "'");
+    // the names in the map are positional aliases of the computation's iterators
+    std::vector<expr> own;
+    for (const var &v : iters_) own.push_back(expr::make_var(global::get_loop_iterator_data_type(), v.get_name()));
+    for (expr &e : idx) e = e.substitute(names, own);
+    set_access_exprs(b, idx);
+}
+
+}  // namespace tiramisu

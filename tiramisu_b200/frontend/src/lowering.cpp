@@ -104,6 +104,15 @@ private:
     std::ostringstream protos_;             // extern "C" prototypes of o_call targets
     std::set<std::string> proto_seen_;
     bool pattern_ = true;
+    bool retargeted_ = false;                 // CPU schedule mapped onto the GPU; host arguments mirrored on the device
+    std::set<buffer *> mirrored_;             // argument buffers with a device mirror (b_X device, h_X host)
+    std::set<buffer *> no_copy_in_;           // outputs that are completely overwritten before being read
+    std::set<buffer *> direct_;               // mirrored arguments handed to a runtime entry point as halide buffers
+    size_t n_statements_ = 0;
+    void propagate_constants();
+    void retarget(const std::vector<computation *> &ord);
+    void auto_map(computation *c);
+    bool try_heat2d_pattern(Node *zero, Node *heat, std::ostringstream &host, int ind);
     // index simplification context of the statement being emitted
     using Env = std::map<std::string, std::pair<int64_t, int64_t>>;   // loop dimension -> inclusive [lo, hi]
     const computation *cur_ = nullptr;
@@ -467,6 +476,7 @@ std::string Lowering::print_access(const expr &e, bool device)
     auto loc = b->get_location();
     bool dev_buf = loc != mem_loc::host;
     if (device && !dev_buf) die("kernel code reads host buffer '" + b->get_name() + "' (through '" + c->get_name() + "'): tag it gpu_global and copy it");
+    if (!device && mirrored_.count(b)) return "h_" + san(b->get_name()) + "[" + lin_index(b, idx, device) + "]";
     if (!device && dev_buf) die("host code accesses device buffer '" + b->get_name() + "' (through '" + c->get_name() + "')");
     return "b_" + san(b->get_name()) + "[" + lin_index(b, idx, device) + "]";
 }
@@ -852,24 +862,322 @@ void Lowering::emit_host(Node *n, std::ostringstream &os, int ind, std::vector<N
     os << pad(ind) << "}\n";
 }
 
+// ------------------------------------------------------------------------------------------------ constants
+// Function constants whose definition folds to a literal are substituted everywhere (the Halide-derived
+// generators name every loop bound: `heat2d_s1_r__y_loop_min` = 1 ...), so that extents, divisibility
+// and the pattern matchers see numbers.
+void Lowering::propagate_constants()
+{
+    std::vector<std::string> names;
+    std::vector<expr> values;
+    for (computation *c : f_->get_computations()) {
+        if (!c->is_constant()) continue;
+        expr v = c->get_expr().substitute(names, values);
+        if (v.is_literal()) {
+            names.push_back(c->get_name());
+            values.push_back(cast(c->get_data_type(), v));
+        }
+    }
+    if (names.empty()) return;
+    for (computation *c : f_->get_computations()) {
+        c->substitute_everywhere(names, values);
+    }
+    for (buffer *b : f_->get_buffers()) b->substitute_dims(names, values);
+}
+
+// ------------------------------------------------------------------------------------------------ CPU schedule -> GPU
+// `codegen(args, obj)` / `gen_halide_obj()` without gpu levels is a CPU schedule (parallelize /
+// vectorize / unroll).  There is no CPU code generator here, so each loop nest is mapped onto the GPU:
+//   * the vectorized loop (unit stride by construction) becomes threadIdx.x and its outer part is cut
+//     into threadIdx.y x blockIdx.x so that a block covers 128 consecutive elements (coalesced);
+//     without a vector tag the innermost data-parallel loop is cut by 128;
+//   * the outermost data-parallel loops become blockIdx.y / blockIdx.z; reduction loops (iterators
+//     that do not index the stored element) stay sequential inside the thread;
+//   * host buffers get device mirrors: inputs are copied in at entry, outputs copied back at exit —
+//     an output that the first statement overwrites completely is not copied in.
+void Lowering::auto_map(computation *c)
+{
+    const expr &e = c->get_expr();
+    if (e.get_expr_type() == e_sync || (e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate ||
+                                                                       e.get_op_type() == o_free || (e.get_op_type() == o_call && !c->has_access()))))
+        return;
+    auto &dims = c->dims();
+    if (dims.empty()) die("'" + c->get_name() + "': a computation without loops cannot be mapped onto the GPU");
+    // which original iterators index the stored element
+    std::vector<std::string> stored;
+    for (const var &v : c->get_iteration_variables()) {
+        bool used = false;
+        for (const expr &a : c->access())
+            used |= !a.substitute({v.get_name()}, {expr((int32_t) 0)}).is_equal(a) || (a.get_expr_type() == e_var && a.get_name() == v.get_name());
+        if (used) stored.push_back(v.get_name());
+    }
+    c->get_buffer();
+    auto parallel_safe = [&](const std::string &dim) {
+        // a scheduled dimension is data-parallel iff every original iterator rebuilt from it indexes the store
+        bool feeds_any = false;
+        for (const var &v : c->get_iteration_variables()) {
+            expr full = expr::make_var(p_int32, v.get_name());
+            for (auto &d : c->defs()) full = full.substitute({d.first}, {d.second});
+            bool feeds = !full.substitute({dim}, {expr((int32_t) 7)}).is_equal(full);
+            if (!feeds) continue;
+            feeds_any = true;
+            if (std::find(stored.begin(), stored.end(), v.get_name()) == stored.end()) return false;
+        }
+        return feeds_any;
+    };
+    int vec = -1;
+    for (size_t i = 0; i < dims.size(); i++) if (dims[i].tag == loop_dim::vector && parallel_safe(dims[i].name)) vec = (int) i;
+    for (auto &d : dims) d.tag = loop_dim::none;
+    std::string tx, ty, bx;
+    if (vec >= 1 && parallel_safe(dims[vec - 1].name) && dims[vec].hi.is_int_literal() && dims[vec].hi.get_int_val() <= 64) {
+        const int lanes = (int) dims[vec].hi.get_int_val();
+        const int rows = std::max(1, 128 / lanes);
+        tx = dims[vec].name;
+        std::string outer = dims[vec - 1].name;
+        bx = outer + "_b"; ty = outer + "_t";
+        c->split(var(outer), rows, var(bx), var(ty));
+    } else {
+        int q = -1;
+        for (int i = (int) dims.size() - 1; i >= 0; i--) if (parallel_safe(dims[i].name)) { q = i; break; }
+        if (q < 0) die("'" + c->get_name() + "' has no data-parallel loop to map onto the GPU");
+        std::string inner = dims[q].name;
+        bx = inner + "_b"; tx = inner + "_t";
+        c->split(var(inner), 128, var(bx), var(tx));
+    }
+    c->tag_gpu_block_level(var(bx));
+    c->tag_gpu_thread_level(var(tx));
+    if (!ty.empty()) c->tag_gpu_thread_level(var(ty));
+    int extra = 0;
+    for (size_t i = 0; i < c->dims().size() && extra < 2; i++) {
+        loop_dim &d = c->dims()[i];
+        if (d.tag != loop_dim::none) break;                        // only loops outside the x mapping
+        if (!parallel_safe(d.name)) break;                         // a sequential loop outside would become a host loop anyway
+        d.tag = loop_dim::gpu_block;
+        extra++;
+    }
+}
+
+void Lowering::retarget(const std::vector<computation *> &ord)
+{
+    retargeted_ = true;
+    for (computation *c : ord) {
+        if (c->pred() && c->pred_level_index() != -1)
+            die("'" + c->get_name() + "': CPU schedules that fuse computations inside a loop (after/compute_at below root) are not re-targeted yet");
+        auto_map(c);
+    }
+    // buffers the statements touch move to the device; buffers only read by function constants
+    // (SIZES / alpha / beta style parameter vectors) stay where the caller put them
+    std::set<buffer *> used;
+    for (computation *c : ord) {
+        if (c->has_access() || c->get_expr().get_expr_type() != e_op || c->get_expr().get_op_type() != o_call) used.insert(c->get_buffer());
+        std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+        while (!stack.empty()) {
+            expr x = stack.back(); stack.pop_back();
+            if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+            if (x.get_op_type() == o_access) {
+                computation *oc = f_->find_computation(x.get_name());
+                if (oc && !oc->is_constant()) used.insert(oc->get_buffer());
+            }
+            for (const expr &o : x.get_operands()) stack.push_back(o);
+        }
+    }
+    std::set<buffer *> is_arg(args_.begin(), args_.end());
+    for (buffer *b : f_->get_buffers()) {
+        if (b->get_location() != mem_loc::host || !used.count(b)) continue;
+        b->tag_gpu_global();
+        if (is_arg.count(b)) mirrored_.insert(b);
+    }
+    // outputs whose first use is a statement that overwrites every element need no copy-in
+    for (buffer *b : args_) {
+        if (b->get_argument_type() != a_output) continue;
+        for (computation *c : ord) {
+            bool reads = false;
+            std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+            while (!stack.empty()) {
+                expr x = stack.back(); stack.pop_back();
+                if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+                if (x.get_op_type() == o_access) {
+                    computation *oc = f_->find_computation(x.get_name());
+                    if (oc && !oc->is_constant() && oc->get_buffer() == b) reads = true;
+                }
+                for (const expr &o : x.get_operands()) stack.push_back(o);
+            }
+            bool writes = c->has_access() && c->get_buffer() == b;
+            if (!reads && !writes) continue;
+            if (writes && !reads && c->guards_only_trim() && !c->get_predicate().is_defined()) {
+                const auto &it = c->get_iteration_variables();
+                bool full = it.size() == b->get_dim_sizes().size() && c->access().size() == it.size();
+                for (size_t i = 0; full && i < it.size(); i++)
+                    full = c->access()[i].get_expr_type() == e_var && c->access()[i].get_name() == it[i].get_name() &&
+                           it[i].get_lower().is_int_literal() && it[i].get_lower().get_int_val() == 0 &&
+                           it[i].get_upper().is_equal(b->get_dim_sizes()[i]);
+                if (full) no_copy_in_.insert(b);
+            }
+            break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stencil pattern
+// zero-fill of OUT followed by the 5-point heat2d update of its interior from IN (the two statements of
+// benchmarks/halide/heat2d_tiramisu.cpp:52-69 / heat2dgpu_tiramisu.cpp:50-56): both kernels are replaced
+// by ONE call of the runtime's register-tiled, 128-bit heat2d kernel (stencil.cu), which writes the zero
+// border itself — the grid is read once and written once.
+bool Lowering::try_heat2d_pattern(Node *zero, Node *heat, std::ostringstream &host, int ind)
+{
+    if (!pattern_) return false;
+    auto single = [](Node *k) -> Node * {
+        Node *stmt = nullptr;
+        std::vector<Node *> st{k};
+        while (!st.empty()) {
+            Node *n = st.back(); st.pop_back();
+            if (!n->is_loop) { if (stmt) return nullptr; stmt = n; continue; }
+            for (auto &c : n->kids) st.push_back(c.get());
+        }
+        return (stmt && !stmt->path.empty() && stmt->path[0] == k) ? stmt : nullptr;
+    };
+    Node *zs = single(zero), *hs = single(heat);
+    if (!zs || !hs) return false;
+    computation *z = zs->comp, *h = hs->comp;
+    if (z->get_data_type() != p_float32 || h->get_data_type() != p_float32 || h->get_predicate().is_defined() || z->get_predicate().is_defined()) return false;
+    buffer *out = h->get_buffer();
+    if (z->get_buffer() != out || out->get_n_dims() != 2 || out->get_location() != mem_loc::gpu_global) return false;
+    const expr &H = out->get_dim_sizes()[0], &W = out->get_dim_sizes()[1];
+    // zero: out[y][x] = 0 over the whole buffer
+    const auto &zi = z->get_iteration_variables();
+    if (!(z->get_expr().is_literal() && z->get_expr().get_double_val() == 0.0) || zi.size() != 2) return false;
+    auto is_var = [](const expr &x, const std::string &n) { return x.get_expr_type() == e_var && x.get_name() == n; };
+    auto is_lit = [](const expr &x, int64_t v) { return x.is_int_literal() && x.get_int_val() == v; };
+    for (int i = 0; i < 2; i++)
+        if (!is_var(z->access()[i], zi[i].get_name()) || !is_lit(zi[i].get_lower(), 0) || !zi[i].get_upper().is_equal(out->get_dim_sizes()[i])) return false;
+    // heat: out[y][x] over [1, H-1) x [1, W-1)
+    const auto &hi = h->get_iteration_variables();
+    if (hi.size() != 2) return false;
+    const std::string Y = hi[0].get_name(), X = hi[1].get_name();
+    if (!is_var(h->access()[0], Y) || !is_var(h->access()[1], X)) return false;
+    for (int i = 0; i < 2; i++)
+        if (!is_lit(hi[i].get_lower(), 1) || !hi[i].get_upper().is_equal(out->get_dim_sizes()[i] - 1)) return false;
+    // expression: a*C + b*(((p+q)+r)+s), products and sums in either operand order
+    auto offset = [&](const expr &x, const std::string &v, int &off) {
+        if (is_var(x, v)) { off = 0; return true; }
+        if (x.get_expr_type() != e_op || x.get_n_arg() != 2) return false;
+        const expr &a = x.get_operand(0), &b = x.get_operand(1);
+        if (x.get_op_type() == o_add && is_var(a, v) && b.is_int_literal()) { off = (int) b.get_int_val(); return true; }
+        if (x.get_op_type() == o_add && is_var(b, v) && a.is_int_literal()) { off = (int) a.get_int_val(); return true; }
+        if (x.get_op_type() == o_sub && is_var(a, v) && b.is_int_literal()) { off = -(int) b.get_int_val(); return true; }
+        return false;
+    };
+    buffer *in = nullptr;
+    auto tap = [&](const expr &x, int &dy, int &dx) {
+        if (!(x.get_expr_type() == e_op && x.get_op_type() == o_access)) return false;
+        computation *oc = nullptr;
+        buffer *b = buffer_of_access(x, &oc);
+        if (!b || b == out || b->get_n_dims() != 2 || b->get_elements_type() != p_float32 || oc->access().size() != 2) return false;
+        if ((int) oc->get_iteration_variables().size() != x.get_n_arg()) return false;
+        if (in && in != b) return false;
+        std::vector<std::string> names;
+        for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+        expr r = oc->access()[0].substitute(names, x.get_operands()), c = oc->access()[1].substitute(names, x.get_operands());
+        if (!offset(r, Y, dy) || !offset(c, X, dx)) return false;
+        in = b;
+        return true;
+    };
+    auto is_f = [](const expr &x, float v) { return x.is_literal() && x.get_data_type() == p_float32 && (float) x.get_double_val() == v; };
+    auto scaled = [&](const expr &x, float k, expr &rest) {
+        if (!(x.get_expr_type() == e_op && x.get_op_type() == o_mul)) return false;
+        if (is_f(x.get_operand(0), k)) { rest = x.get_operand(1); return true; }
+        if (is_f(x.get_operand(1), k)) { rest = x.get_operand(0); return true; }
+        return false;
+    };
+    const expr &e = h->get_expr();
+    if (!(e.get_expr_type() == e_op && e.get_op_type() == o_add)) return false;
+    expr centre, sum;
+    if (!((scaled(e.get_operand(0), 0.3f, centre) && scaled(e.get_operand(1), 0.4f, sum)) ||
+          (scaled(e.get_operand(1), 0.3f, centre) && scaled(e.get_operand(0), 0.4f, sum)))) return false;
+    int dy, dx;
+    if (!tap(centre, dy, dx) || dy || dx) return false;
+    // ((p+q)+r)+s
+    auto add2 = [](const expr &x, expr &a, expr &b) {
+        if (!(x.get_expr_type() == e_op && x.get_op_type() == o_add)) return false;
+        a = x.get_operand(0); b = x.get_operand(1);
+        return true;
+    };
+    auto dir = [&](const expr &x) -> char {
+        int ty, tx;
+        if (!tap(x, ty, tx)) return 0;
+        if (ty == 0 && tx == 1) return 'E';
+        if (ty == 0 && tx == -1) return 'W';
+        if (ty == 1 && tx == 0) return 'S';
+        if (ty == -1 && tx == 0) return 'N';
+        return 0;
+    };
+    expr l3, s4, l2, s3, p, q;
+    if (!add2(sum, l3, s4)) return false;
+    if (!dir(s4) && dir(l3)) std::swap(l3, s4);          // the single tap may be written on either side
+    if (!add2(l3, l2, s3)) return false;
+    if (!dir(s3) && dir(l2)) std::swap(l2, s3);
+    if (!add2(l2, p, q)) return false;
+    char a = dir(p), b = dir(q), c3 = dir(s3), c4 = dir(s4);
+    if (!a || !b || !c3 || !c4) return false;
+    auto pair = [&](char u, char v) { return (a == u && b == v) || (a == v && b == u); };
+    int form = -1;
+    if (pair('E', 'W') && c3 == 'S' && c4 == 'N') form = 0;          // heat2d_tiramisu.cpp:68
+    else if (pair('S', 'E') && c3 == 'N' && c4 == 'W') form = 1;     // heat2dgpu_tiramisu.cpp:54
+    if (form < 0 || !in) return false;
+    if (!in->get_dim_sizes()[0].is_equal(H) || !in->get_dim_sizes()[1].is_equal(W)) return false;
+    host << pad(ind) << "// pattern lowering: zero-fill '" << z->get_name() << "' + 5-point update '" << h->get_name()
+         << "' -> the runtime's heat2d kernel (one pass over the grid)\n";
+    if (retargeted_ && n_statements_ == 2 && mirrored_.count(in) && mirrored_.count(out)) {
+        // the whole function is this stencil on the caller's buffers: let the runtime entry point do the
+        // host<->device traffic too (row-chunk pipeline for host grids, in place for device-resident ones)
+        auto arg_of = [&](buffer *b) { return (int) (std::find(args_.begin(), args_.end(), b) - args_.begin()); };
+        host << pad(ind) << "if (tiramisu_b200_heat2d_buffers(arg" << arg_of(in) << ", arg" << arg_of(out) << ", (int32_t) (" << print(H, false)
+             << "), (int32_t) (" << print(W, false) << "), " << form << ")) return 1;\n";
+        direct_.insert(in);
+        direct_.insert(out);
+        return true;
+    }
+    host << pad(ind) << "if (tiramisu_b200_heat2d(b_" << san(in->get_name()) << ", b_" << san(out->get_name()) << ", (int32_t) (" << print(H, false)
+         << "), (int32_t) (" << print(W, false) << "), " << form << ", 0, (int32_t) (" << print(H, false) << "))) return 1;\n";
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ driver
 std::string Lowering::run()
 {
-    if (!cuda_) die("function '" + f_->get_name() + "': this back end only generates sm_100a code; call codegen(args, obj, true) "
-                    "(there is no CPU code generator and no CPU fallback)");
     if (const char *m = getenv("TIRAMISU_B200_LOWERING")) pattern_ = std::string(m) != "generic";
+    propagate_constants();
     for (computation *c : f_->get_computations())
         if (c->is_constant()) { constants_[c->get_name()] = c; constant_order_.push_back(c); }
     for (buffer *b : args_)
         if (b->get_location() != mem_loc::host && b->get_location() != mem_loc::gpu_global)
             die("argument buffer '" + b->get_name() + "' is tagged on-chip");
 
-    build_tree(order());
+    std::vector<computation *> ord = order();
+    n_statements_ = ord.size();
+    bool any_gpu = false;
+    for (computation *c : ord)
+        for (auto &d : c->dims()) any_gpu |= d.tag == loop_dim::gpu_block || d.tag == loop_dim::gpu_thread;
+    if (!cuda_ && !any_gpu) {
+        std::cerr << "tiramisu_b200 lowering: '" << f_->get_name() << "' is a CPU schedule; there is no CPU code generator: "
+                     "re-targeting its loop nests to sm_100a (parallel -> blocks, vector -> threads, device mirrors for host buffers)\n";
+        retarget(ord);
+    }
+    build_tree(ord);
     assign_axes(&root_);
 
     std::ostringstream body;
     std::vector<Node *> host_loops;
-    for (auto &k : root_.kids) emit_host(k.get(), body, 1, host_loops);
+    for (size_t i = 0; i < root_.kids.size(); i++) {
+        Node *k = root_.kids[i].get();
+        auto is_kernel = [](Node *n) { return n->is_loop && (n->tag == loop_dim::gpu_block || n->tag == loop_dim::gpu_thread); };
+        if (i + 1 < root_.kids.size() && is_kernel(k) && is_kernel(root_.kids[i + 1].get()) &&
+            try_heat2d_pattern(k, root_.kids[i + 1].get(), body, 1)) {
+            i++;
+            continue;
+        }
+        emit_host(k, body, 1, host_loops);
+    }
 
     std::ostringstream out;
     out << "// Generated by the tiramisu_b200 sm_100a lowering for Tiramisu function '" << f_->get_name() << "'. Do not edit.\n"
@@ -884,6 +1192,9 @@ std::string Lowering::run()
         << "int tiramisu_cuda_memcpy_to_device(void *, void *, uint64_t);\nint tiramisu_cuda_memcpy_to_host(void *, void *, uint64_t);\n"
         << "void *tiramisu_cuda_malloc(uint64_t);\nint tiramisu_cuda_free(void *);\nint32_t tiramisu_cuda_stream_synchronize(int32_t);\n"
         << "void *tiramisu_b200_get_stream(void);\nint tiramisu_b200_post_launch(const char *);\n"
+        << "int tiramisu_cuda_memcpy_to_device_async(void *, const void *, uint64_t);\n"
+        << "int tiramisu_b200_heat2d(const float *, float *, int32_t, int32_t, int32_t, int32_t, int32_t);\n"
+        << "int tiramisu_b200_heat2d_buffers(halide_buffer_t *, halide_buffer_t *, int32_t, int32_t, int32_t);\n"
         << "int tiramisu_cublas_sgemm(float *, float *, float *, uint64_t, uint64_t, uint64_t, float, float, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, bool, bool);\n"
         << "int tiramisu_cublas_dgemm(double *, double *, double *, uint64_t, uint64_t, uint64_t, double, double, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, bool, bool);\n"
         << "}\n"
@@ -897,9 +1208,17 @@ std::string Lowering::run()
     for (size_t i = 0; i < args_.size(); i++) out << (i ? ", " : "") << "halide_buffer_t *arg" << i;
     out << ")\n{\n";
     std::set<buffer *> is_arg(args_.begin(), args_.end());
-    for (size_t i = 0; i < args_.size(); i++)
-        out << pad(1) << ctype(args_[i]->get_elements_type()) << " *b_" << san(args_[i]->get_name()) << " = (" << ctype(args_[i]->get_elements_type())
-            << " *) tb_arg(arg" << i << ");\n";
+    for (size_t i = 0; i < args_.size(); i++) {
+        const std::string T = ctype(args_[i]->get_elements_type()), N = san(args_[i]->get_name());
+        if (mirrored_.count(args_[i])) {
+            // host argument of a re-targeted CPU schedule: h_X is the caller's memory, b_X its device mirror
+            // (a device-resident argument, ->host == NULL, is used in place)
+            out << pad(1) << T << " *h_" << N << " = (" << T << " *) arg" << i << "->host;\n";
+            out << pad(1) << T << " *b_" << N << " = h_" << N << " ? nullptr : (" << T << " *) arg" << i << "->device;\n";
+        } else {
+            out << pad(1) << T << " *b_" << N << " = (" << T << " *) tb_arg(arg" << i << ");\n";
+        }
+    }
     for (buffer *b : f_->get_buffers())
         if (!is_arg.count(b) && (b->get_location() == mem_loc::host || b->get_location() == mem_loc::gpu_global))
             out << pad(1) << ctype(b->get_elements_type()) << " *b_" << san(b->get_name()) << " = nullptr;\n";
@@ -914,7 +1233,23 @@ std::string Lowering::run()
     for (buffer *b : autos)
         out << pad(1) << "b_" << san(b->get_name()) << " = (" << ctype(b->get_elements_type()) << " *) "
             << (b->get_location() == mem_loc::gpu_global ? "tiramisu_cuda_malloc(" : "malloc(") << bytes_of(b, false) << ");\n";
+    for (buffer *b : args_) {
+        if (!mirrored_.count(b) || direct_.count(b)) continue;
+        const std::string N = san(b->get_name());
+        out << pad(1) << "if (h_" << N << ") {\n" << pad(2) << "b_" << N << " = (" << ctype(b->get_elements_type()) << " *) tiramisu_cuda_malloc(" << bytes_of(b, false) << ");\n";
+        if (!no_copy_in_.count(b))
+            out << pad(2) << "tiramisu_cuda_memcpy_to_device_async(b_" << N << ", h_" << N << ", " << bytes_of(b, false) << ");\n";
+        out << pad(1) << "}\n";
+    }
     out << body.str();
+    for (buffer *b : args_) {
+        if (!mirrored_.count(b) || direct_.count(b)) continue;
+        const std::string N = san(b->get_name());
+        out << pad(1) << "if (h_" << N << ") {\n";
+        if (b->get_argument_type() == a_output)
+            out << pad(2) << "tiramisu_cuda_memcpy_to_host(h_" << N << ", b_" << N << ", " << bytes_of(b, false) << ");\n";
+        out << pad(2) << "tiramisu_cuda_free(b_" << N << ");\n" << pad(1) << "}\n";
+    }
     for (auto it = autos.rbegin(); it != autos.rend(); ++it)
         out << pad(1) << ((*it)->get_location() == mem_loc::gpu_global ? "tiramisu_cuda_free(" : "free(") << "b_" << san((*it)->get_name()) << ");\n";
     out << pad(1) << "return 0;\n}\n\n";
