@@ -38,6 +38,15 @@ TARGETS = {
                              [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
     "sgemm_gpu_generator3": (f"{SGEMM_GPU}/generator3.cpp", "fct.o", f"{SGEMM_GPU}/wrapper.cpp", [SGEMM_GPU],
                              [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
+    # chain of two contractions: zero-init + reduction fused per kernel -> two runtime GEMM calls
+    "chain_mm": ("benchmarks/linear_algebra/chain_mm/gpu/generator.cpp", "fct.o", "benchmarks/linear_algebra/chain_mm/gpu/wrapper.cpp",
+                 ["benchmarks/linear_algebra/chain_mm/gpu"], [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
+    # the LSTM block: the x86 statement (unscheduled, loops fused at the layer level; re-targeted) and the
+    # reference's hand-scheduled GPU version (shared-memory GEMMs + pointwise kernel per cell).  The GPU
+    # wrapper needs cuDNN, so that object is linked into a shared library and driven from the tests.
+    "lstm_cpu": ("benchmarks/DNN/blocks/LSTM/cpu/generator.cpp", "lstm.o", "benchmarks/DNN/blocks/LSTM/cpu/wrapper.cpp",
+                 ["benchmarks/DNN/blocks/LSTM/cpu"], []),
+    "lstm_gpu": ("benchmarks/DNN/blocks/LSTM/gpu/generator.cpp", "lstm.o", None, ["benchmarks/DNN/blocks/LSTM/gpu"], []),
     # BASELINE configs[1]'s own generator: old-style ISL-string API, CPU schedule (parallel y, vectorize x by 8)
     "heat2d": ("benchmarks/halide/heat2d_tiramisu.cpp", "build/generated_fct_heat2d.o", "benchmarks/halide/wrapper_heat2d.cpp",
                ["benchmarks/halide"], []),
@@ -81,6 +90,12 @@ def build_one(name: str, lowering: str | None = None) -> tuple[int, str]:
     log += r.stdout + r.stderr
     if r.returncode or not os.path.exists(os.path.join(work, obj)):
         return r.returncode or 1, "generator failed:\n" + log[-3000:]
+    if wsrc is None:
+        so = os.path.join(BIN, f"libgen_{tag}.so")
+        r = subprocess.run(["g++", "-shared", "-o", so, os.path.join(work, obj), f"-L{LIBDIR}", "-ltiramisu_b200", f"-L{CUDA}/lib64", "-lcudart",
+                            "-Wl,-rpath,$ORIGIN/../../../tiramisu_b200/lib", f"-Wl,-rpath,{CUDA}/lib64"], capture_output=True, text=True, env=env)
+        log += r.stdout + r.stderr
+        return (r.returncode, ("shared library does not link:\n" if r.returncode else "") + log[-2000:])
     # 3. the reference wrapper, unmodified, with the generated object
     exe = os.path.join(BIN, "gen_" + tag)
     cmd = ["g++", "-std=c++17", "-O2", "-mavx", "-fopenmp", "-w",
@@ -107,7 +122,7 @@ def build(names=None, verbose=False) -> dict:
         if verbose:
             print(name, "OK" if out[name][0] == 0 else "FAILED\n" + out[name][1], flush=True)
     # the two GEMM-pattern generators once more with the pattern lowering off (generic SIMT emission)
-    for name in ("test_167", "test_169", "heat2d"):
+    for name in ("test_167", "test_169", "heat2d", "chain_mm"):
         if names and name not in names:
             continue
         out[name + "_generic"] = build_one(name, "generic")

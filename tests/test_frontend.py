@@ -109,7 +109,16 @@ def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     res = bg.build()
     failed = {k: v[1] for k, v in res.items() if v[0] != 0}
     assert not failed, failed
-    assert len(res) == len(bg.TARGETS) + 3
+    assert len(res) == len(bg.TARGETS) + 4
+    # chain_mm/gpu/generator.cpp: two fused (zero-init + reduction) kernels -> two runtime GEMM calls, beta = 0
+    cm = open(os.path.join(bg.GEN, "chain_mm", "fct.o.b200.cu")).read()
+    assert cm.count("if (tiramisu_cublas_sgemm(") == 2 and "__global__" not in cm and cm.count("1.0f, 0.0f,") == 2
+    # LSTM/cpu/generator.cpp: time and layer loops stay host loops, 13 statements inside them become kernels
+    lc = open(os.path.join(bg.GEN, "lstm_cpu", "lstm.o.b200.cu")).read()
+    assert lc.count("__global__") == 15 and "for (int32_t v15_m = 0; v15_m < c_seq_length; v15_m++)" in lc
+    # LSTM/gpu/generator.cpp: the hand-scheduled version keeps its 4 launches per cell and its shared tiles
+    lg = open(os.path.join(bg.GEN, "lstm_gpu", "lstm.o.b200.cu")).read()
+    assert lg.count("__global__") == 6 and "__shared__ float b_b_m1_R_shr[256];" in lg and "__shared__ float b_b_m1_h_shr[272];" in lg
     # the hand-scheduled GEMM of sgemm/gpu/generator1.cpp keeps its structure: two shared buffers,
     # per-thread accumulators with compile-time indices (registers, no local memory), two barriers
     src = open(os.path.join(bg.GEN, "sgemm_gpu_generator1", "fct.o.b200.cu")).read()
@@ -163,6 +172,60 @@ def test_reference_heat2d_generator_through_lowering(name, tmp_path):
     two kernels the lowering emits itself."""
     out = _run(name, cwd=tmp_path)
     assert "heat2d" in out
+
+
+@pytest.mark.gpu
+def test_reference_chain_mm_generator(tmp_path):
+    """chain_mm/gpu.  The wrapper's own check is an exact comparison with an fp32 CPU loop
+    on rand()%10 operands whose sums exceed 2^24, so it is run on the generated SIMT kernels
+    (TIRAMISU_B200_LOWERING=generic: same sequential k order, no FMA); the pattern-lowered object (two
+    tcgen05 GEMM calls) runs the benchmark loop."""
+    out = _run("chain_mm_generic", args=("1", "1"), cwd=tmp_path)
+    assert "succeeded" in out.lower() or "passed" in out.lower(), out[-2000:]
+    out = _run("chain_mm", args=("5", "0"), cwd=tmp_path)
+    assert "matmul done" in out.lower(), out[-2000:]
+
+
+@pytest.mark.gpu
+def test_reference_lstm_cpu_generator_retargeted(tmp_path):
+    """LSTM/cpu/generator.cpp (row a10: the x86 statement, unscheduled, fused at the layer level) re-targeted
+    by the lowering; LSTM/cpu/wrapper.cpp (F=32, B=8, L=4, T=100) compares with mkldnn_result.txt at
+    |diff| < 0.02 — produced here by the oracle, as in tests/test_compat_wrappers.py."""
+    from oracle import oracle
+    from tests import refdata
+    W, b, x = refdata.lstm_inputs(32, 8, 4, 100)
+    want = oracle.lstm(W, b, x)
+    with open(tmp_path / "mkldnn_result.txt", "w") as f:
+        for v in want.reshape(-1):
+            f.write(f"{float(v):.9g}\n")
+    out = _run("lstm_cpu", cwd=tmp_path)
+    pct = [ln for ln in out.splitlines() if "Percentage of correctness" in ln]
+    assert pct and float(pct[0].split()[-1]) >= 99.0, out[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fblt", [(32, 16, 2, 6), (64, 32, 3, 4)])
+def test_reference_lstm_gpu_generator(fblt):
+    """LSTM/gpu/generator.cpp (row a11: the reference's hand-scheduled GPU LSTM — prefetching shared-memory
+    GEMM kernels + one pointwise kernel per cell) lowered faithfully and called through its
+    lstm(params, Weights, biases, x, y) ABI; compared with the oracle at 1e-5 (weights scaled by 1/16 so
+    the gates do not saturate; libm vs CUDA expf/tanhf differ in the last ulps)."""
+    from oracle import oracle
+    path = os.path.join(bg.BIN, "libgen_lstm_gpu.so")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not built")
+    from tiramisu_b200 import _lib
+    _lib.lib()
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    F, B, L, T = fblt
+    rng = np.random.default_rng(18)
+    Wt = (rng.uniform(-1, 1, (L, 2, 4 * F, F)) / 16).astype(np.float32)
+    bias = rng.uniform(-1, 1, (L, 4 * F)).astype(np.float32)
+    x = rng.uniform(-1, 1, (T, B, F)).astype(np.float32)
+    y = np.zeros((T, B, F), np.float32)
+    _call(lib, "lstm", np.array([F, B, L, T], np.int32), Wt, bias, x, y)
+    want = oracle.lstm(Wt, bias, x)
+    assert np.abs(y - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), np.abs(y - want).max()
 
 
 def _load(name):

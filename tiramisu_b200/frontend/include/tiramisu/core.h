@@ -14,6 +14,7 @@
 #ifndef TIRAMISU_B200_FRONTEND_CORE_H
 #define TIRAMISU_B200_FRONTEND_CORE_H
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>

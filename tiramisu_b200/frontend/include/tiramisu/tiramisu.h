@@ -5,6 +5,7 @@
 #include <tiramisu/type.h>
 #include <tiramisu/expr.h>
 #include <tiramisu/core.h>
+#include <tiramisu/block.h>
 #include <tiramisu/debug.h>
 #include <tiramisu/utils.h>
 #endif

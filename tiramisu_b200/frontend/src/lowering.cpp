@@ -111,7 +111,8 @@ private:
     size_t n_statements_ = 0;
     void propagate_constants();
     void retarget(const std::vector<computation *> &ord);
-    void auto_map(computation *c);
+    void auto_map(computation *c, int shared_depth);
+    static int fuse_depth(computation *prev, computation *c);
     bool try_heat2d_pattern(Node *zero, Node *heat, std::ostringstream &host, int ind);
     // index simplification context of the statement being emitted
     using Env = std::map<std::string, std::pair<int64_t, int64_t>>;   // loop dimension -> inclusive [lo, hi]
@@ -169,6 +170,21 @@ std::vector<computation *> Lowering::order()
     return ord;
 }
 
+// number of loops `c` shares with its predecessor in the order
+int Lowering::fuse_depth(computation *prev, computation *c)
+{
+    if (!prev || c->pred() != prev) return 0;
+    int depth = 0;
+    if (c->pred_level_index() >= 0) depth = c->pred_level_index() + 1;
+    else if (c->pred_level_index() == -2) {
+        int d = c->find_dim(c->pred_level());
+        if (d < 0) d = prev->find_dim(c->pred_level());
+        if (d < 0) die("'" + c->get_name() + "' is ordered after '" + prev->get_name() + "' at unknown level '" + c->pred_level() + "'");
+        depth = d + 1;
+    }
+    return std::min(depth, std::min((int) prev->dims().size(), (int) c->dims().size()));
+}
+
 static expr union_lo(const expr &a, const expr &b) { return a.is_equal(b) ? a : expr(o_min, a, b); }
 static expr union_hi(const expr &a, const expr &b) { return a.is_equal(b) ? a : expr(o_max, a, b); }
 
@@ -179,18 +195,10 @@ void Lowering::build_tree(const std::vector<computation *> &ord)
     for (computation *c : ord) {
         if (!c->get_expr().is_defined()) die("computation '" + c->get_name() + "' has no expression");
         auto &dims = c->dims();
-        int depth = 0;
-        if (prev && c->pred() == prev) {
-            if (c->pred_level_index() >= 0) depth = c->pred_level_index() + 1;
-            else if (c->pred_level_index() == -2) {
-                int d = c->find_dim(c->pred_level());
-                if (d < 0) d = prev->find_dim(c->pred_level());
-                if (d < 0) die("'" + c->get_name() + "' is ordered after '" + prev->get_name() + "' at unknown level '" + c->pred_level() + "'");
-                depth = d + 1;
-            }
-        }
-        if (depth > (int) open.size() || depth > (int) dims.size())
-            die("'" + c->get_name() + "' cannot share " + std::to_string(depth) + " loops with '" + (prev ? prev->get_name() : "") + "'");
+        int depth = fuse_depth(prev, c);
+        // a level deeper than the predecessor's own nest only orders the two (reference generators write
+        // `copy.then(kernel_stmt, i1)` after a loop-less copy): share what both have
+        depth = std::min(depth, std::min((int) open.size(), (int) dims.size()));
         open.resize(depth);
         for (int d = 0; d < depth; d++) {
             Node *n = open[d];
@@ -646,39 +654,59 @@ void Lowering::emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind)
     emit_assignment(n, os, ind, true);
 }
 
-// C(i,j[,k]) = C(i,j,*) + A(..)*B(..): one statement, fp32, row-major global buffers.
+// Dense fp32 contraction over row-major global buffers:
+//     [ X(I,J) = 0 ]   X(.., R ..) = X(..) + P(I,R) * Q(R,J)
+// (one statement, or a zero-init fused in front of it as in chain_mm/gpu/generator.cpp:38-43; the
+// reduction iterator R may sit anywhere in the iterator list, operands may be stored transposed).
+// The kernel is not emitted: it becomes one call of the runtime's tcgen05 GEMM, beta = 1 (accumulate
+// into what the buffer holds) or beta = 0 (the zero-init is part of the pattern).
 bool Lowering::try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind)
 {
     if (!pattern_) return false;
-    // exactly one statement in the subtree
-    Node *stmt = nullptr;
-    std::vector<Node *> stack{k.root};
-    while (!stack.empty()) {
-        Node *n = stack.back(); stack.pop_back();
-        if (!n->is_loop) { if (stmt) return false; stmt = n; continue; }
-        for (auto &c : n->kids) stack.push_back(c.get());
+    std::vector<Node *> stmts;
+    {
+        std::vector<Node *> order{k.root};
+        for (size_t i = 0; i < order.size(); i++) {           // pre-order, children left to right
+            Node *n = order[i];
+            if (!n->is_loop) { stmts.push_back(n); continue; }
+            size_t at = i + 1;
+            for (auto &c : n->kids) order.insert(order.begin() + (at++), c.get());
+        }
     }
-    if (!stmt || stmt->path.empty() || stmt->path[0] != k.root) return false;   // not inside a host loop
+    if (stmts.empty() || stmts.size() > 2) return false;
+    for (Node *s : stmts) if (s->path.empty() || s->path[0] != k.root) return false;          // not inside a host loop
+    Node *stmt = stmts.back();
     computation *c = stmt->comp;
-    if (c->get_data_type() != p_float32 || c->get_predicate().is_defined()) return false;
+    if (c->get_data_type() != p_float32 || c->get_predicate().is_defined() || !c->get_expr().is_defined()) return false;
     const auto &iters = c->get_iteration_variables();
     if (iters.size() != 3) return false;
     for (const var &v : iters) if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0)) return false;
-    const std::string I = iters[0].get_name(), J = iters[1].get_name(), K = iters[2].get_name();
+    auto is_var = [](const expr &x, const std::string &n) { return x.get_expr_type() == e_var && x.get_name() == n; };
+    // the stored element is addressed by two of the three iterators; the third is the reduction
+    buffer *C = c->get_buffer();
+    if (C->get_location() != mem_loc::gpu_global || C->get_n_dims() != 2 || c->access().size() != 2) return false;
+    if (c->access()[0].get_expr_type() != e_var || c->access()[1].get_expr_type() != e_var) return false;
+    const std::string I = c->access()[0].get_name(), J = c->access()[1].get_name();
+    std::string R;
+    expr M, N, Kx;
+    for (const var &v : iters) {
+        if (v.get_name() == I) M = v.get_upper();
+        else if (v.get_name() == J) N = v.get_upper();
+        else { R = v.get_name(); Kx = v.get_upper(); }
+    }
+    if (I == J || R.empty() || !M.is_defined() || !N.is_defined() || !Kx.is_defined()) return false;
     const expr &e = c->get_expr();
     if (e.get_expr_type() != e_op || e.get_op_type() != o_add) return false;
     expr self = e.get_operand(0), prod = e.get_operand(1);
     if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) std::swap(self, prod);
     if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) return false;
     if (!(self.get_expr_type() == e_op && self.get_op_type() == o_access && self.get_name() == c->get_name())) return false;
-    auto is_var = [](const expr &x, const std::string &n) { return x.get_expr_type() == e_var && x.get_name() == n; };
-    // the accumulator is addressed by (i, j) only
-    buffer *C = c->get_buffer();
-    if (C->get_location() != mem_loc::gpu_global || C->get_n_dims() != 2 || c->access().size() != 2) return false;
-    if (!is_var(c->access()[0], I) || !is_var(c->access()[1], J)) return false;
-    if (self.get_n_arg() != 3 || !is_var(self.get_operand(0), I) || !is_var(self.get_operand(1), J)) return false;
-    // operands: X(i,k) and Y(k,j) (either order), possibly stored transposed
-    struct Opnd { buffer *b = nullptr; bool trans = false; int role = -1; };   // role 0 = A (uses i,k), 1 = B (uses k,j)
+    std::vector<std::string> own;
+    for (const var &v : iters) own.push_back(v.get_name());
+    if (self.get_n_arg() != 3) return false;
+    if (!is_var(c->access()[0].substitute(own, self.get_operands()), I) || !is_var(c->access()[1].substitute(own, self.get_operands()), J)) return false;
+    // operands: P(I,R) and Q(R,J) in either order, possibly stored transposed
+    struct Opnd { buffer *b = nullptr; bool trans = false; int role = -1; };   // role 0 = uses (I,R), 1 = uses (R,J)
     auto classify = [&](const expr &x, Opnd &o) {
         if (!(x.get_expr_type() == e_op && x.get_op_type() == o_access)) return false;
         computation *oc = nullptr;
@@ -689,24 +717,35 @@ bool Lowering::try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind)
         for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
         expr r = oc->access()[0].substitute(names, x.get_operands()), s = oc->access()[1].substitute(names, x.get_operands());
         o.b = b;
-        if (is_var(r, I) && is_var(s, K)) { o.role = 0; o.trans = false; return true; }
-        if (is_var(r, K) && is_var(s, I)) { o.role = 0; o.trans = true; return true; }
-        if (is_var(r, K) && is_var(s, J)) { o.role = 1; o.trans = false; return true; }
-        if (is_var(r, J) && is_var(s, K)) { o.role = 1; o.trans = true; return true; }
+        if (is_var(r, I) && is_var(s, R)) { o.role = 0; o.trans = false; return true; }
+        if (is_var(r, R) && is_var(s, I)) { o.role = 0; o.trans = true; return true; }
+        if (is_var(r, R) && is_var(s, J)) { o.role = 1; o.trans = false; return true; }
+        if (is_var(r, J) && is_var(s, R)) { o.role = 1; o.trans = true; return true; }
         return false;
     };
     Opnd x, y;
     if (!classify(prod.get_operand(0), x) || !classify(prod.get_operand(1), y) || x.role == y.role) return false;
     const Opnd &a = x.role == 0 ? x : y, &b = x.role == 0 ? y : x;
     if (a.b == C || b.b == C) return false;
-    // no split may have left a guard: the box is covered exactly (guards come from non-dividing splits only)
-    for (const expr &g : c->guards()) (void) g;
-    expr M = iters[0].get_upper(), N = iters[1].get_upper(), Kx = iters[2].get_upper();
-    host << pad(ind) << "// pattern lowering: '" << c->get_name() << "' is a dense fp32 contraction -> tcgen05 GEMM of the runtime\n";
-    host << pad(ind) << "tiramisu_cublas_sgemm((float *) b_" << san(a.b->get_name()) << ", (float *) b_" << san(b.b->get_name()) << ", b_" << san(C->get_name())
+    // optional zero-init of the same elements fused in front
+    bool zero_init = false;
+    if (stmts.size() == 2) {
+        computation *z = stmts[0]->comp;
+        const auto &zi = z->get_iteration_variables();
+        if (!z->has_access() && !z->get_expr().is_defined()) return false;
+        if (z->get_buffer() != C || zi.size() != 2 || z->get_predicate().is_defined()) return false;
+        if (!(z->get_expr().is_literal() && z->get_expr().get_double_val() == 0.0)) return false;
+        if (!is_var(z->access()[0], zi[0].get_name()) || !is_var(z->access()[1], zi[1].get_name())) return false;
+        if (!zi[0].get_upper().is_equal(M) || !zi[1].get_upper().is_equal(N)) return false;
+        for (const var &v : zi) if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0)) return false;
+        zero_init = true;
+    }
+    host << pad(ind) << "// pattern lowering: '" << c->get_name() << "' is a dense fp32 contraction"
+         << (zero_init ? " (zero-init fused: beta = 0)" : "") << " -> tcgen05 GEMM of the runtime\n";
+    host << pad(ind) << "if (tiramisu_cublas_sgemm((float *) b_" << san(a.b->get_name()) << ", (float *) b_" << san(b.b->get_name()) << ", b_" << san(C->get_name())
          << ", (uint64_t) " << print(M, false) << ", (uint64_t) " << print(N, false) << ", (uint64_t) " << print(Kx, false)
-         << ", 1.0f, 1.0f, (uint64_t) " << print(a.b->get_dim_sizes()[1], false) << ", (uint64_t) " << print(b.b->get_dim_sizes()[1], false)
-         << ", (uint64_t) " << print(C->get_dim_sizes()[1], false) << ", 0, 0, 0, " << (a.trans ? "true" : "false") << ", " << (b.trans ? "true" : "false") << ");\n";
+         << ", 1.0f, " << (zero_init ? "0.0f" : "1.0f") << ", (uint64_t) " << print(a.b->get_dim_sizes()[1], false) << ", (uint64_t) " << print(b.b->get_dim_sizes()[1], false)
+         << ", (uint64_t) " << print(C->get_dim_sizes()[1], false) << ", 0, 0, 0, " << (a.trans ? "true" : "false") << ", " << (b.trans ? "true" : "false") << ")) return 1;\n";
     return true;
 }
 
@@ -895,7 +934,7 @@ void Lowering::propagate_constants()
 //     that do not index the stored element) stay sequential inside the thread;
 //   * host buffers get device mirrors: inputs are copied in at entry, outputs copied back at exit —
 //     an output that the first statement overwrites completely is not copied in.
-void Lowering::auto_map(computation *c)
+void Lowering::auto_map(computation *c, int shared_depth)
 {
     const expr &e = c->get_expr();
     if (e.get_expr_type() == e_sync || (e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate ||
@@ -925,11 +964,19 @@ void Lowering::auto_map(computation *c)
         }
         return feeds_any;
     };
+    // loops shared with a neighbour in the order (fused nests: the time / layer loops of the LSTM) stay
+    // sequential host loops around the kernels; only the statement's own loops are mapped
     int vec = -1;
-    for (size_t i = 0; i < dims.size(); i++) if (dims[i].tag == loop_dim::vector && parallel_safe(dims[i].name)) vec = (int) i;
+    for (size_t i = shared_depth; i < dims.size(); i++) if (dims[i].tag == loop_dim::vector && parallel_safe(dims[i].name)) vec = (int) i;
     for (auto &d : dims) d.tag = loop_dim::none;
+    if ((int) dims.size() == shared_depth) {
+        // nothing of its own to map: run the statement as a one-thread kernel inside the shared host loops
+        loop_dim one; one.name = "_one_" + c->get_name(); one.lo = expr((int32_t) 0); one.hi = expr((int32_t) 1); one.tag = loop_dim::gpu_block;
+        dims.push_back(one);
+        return;
+    }
     std::string tx, ty, bx;
-    if (vec >= 1 && parallel_safe(dims[vec - 1].name) && dims[vec].hi.is_int_literal() && dims[vec].hi.get_int_val() <= 64) {
+    if (vec >= shared_depth + 1 && parallel_safe(dims[vec - 1].name) && dims[vec].hi.is_int_literal() && dims[vec].hi.get_int_val() <= 64) {
         const int lanes = (int) dims[vec].hi.get_int_val();
         const int rows = std::max(1, 128 / lanes);
         tx = dims[vec].name;
@@ -938,7 +985,7 @@ void Lowering::auto_map(computation *c)
         c->split(var(outer), rows, var(bx), var(ty));
     } else {
         int q = -1;
-        for (int i = (int) dims.size() - 1; i >= 0; i--) if (parallel_safe(dims[i].name)) { q = i; break; }
+        for (int i = (int) dims.size() - 1; i >= shared_depth; i--) if (parallel_safe(dims[i].name)) { q = i; break; }
         if (q < 0) die("'" + c->get_name() + "' has no data-parallel loop to map onto the GPU");
         std::string inner = dims[q].name;
         bx = inner + "_b"; tx = inner + "_t";
@@ -948,7 +995,7 @@ void Lowering::auto_map(computation *c)
     c->tag_gpu_thread_level(var(tx));
     if (!ty.empty()) c->tag_gpu_thread_level(var(ty));
     int extra = 0;
-    for (size_t i = 0; i < c->dims().size() && extra < 2; i++) {
+    for (size_t i = shared_depth; i < c->dims().size() && extra < 2; i++) {
         loop_dim &d = c->dims()[i];
         if (d.tag != loop_dim::none) break;                        // only loops outside the x mapping
         if (!parallel_safe(d.name)) break;                         // a sequential loop outside would become a host loop anyway
@@ -960,11 +1007,13 @@ void Lowering::auto_map(computation *c)
 void Lowering::retarget(const std::vector<computation *> &ord)
 {
     retargeted_ = true;
-    for (computation *c : ord) {
-        if (c->pred() && c->pred_level_index() != -1)
-            die("'" + c->get_name() + "': CPU schedules that fuse computations inside a loop (after/compute_at below root) are not re-targeted yet");
-        auto_map(c);
+    std::vector<int> shared(ord.size(), 0);
+    for (size_t i = 0; i < ord.size(); i++) {
+        int with_prev = i ? fuse_depth(ord[i - 1], ord[i]) : 0;
+        int with_next = i + 1 < ord.size() ? fuse_depth(ord[i], ord[i + 1]) : 0;
+        shared[i] = std::max(with_prev, with_next);
     }
+    for (size_t i = 0; i < ord.size(); i++) auto_map(ord[i], shared[i]);
     // buffers the statements touch move to the device; buffers only read by function constants
     // (SIZES / alpha / beta style parameter vectors) stay where the caller put them
     std::set<buffer *> used;
