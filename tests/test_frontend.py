@@ -76,12 +76,13 @@ def test_cpu_schedules_are_retargeted_not_run_on_the_host(cases):
     """codegen(args, obj) without the gpu flag: parallelize/vectorize nests become sm_100a kernels with
     device mirrors for the host arguments; parameter vectors read only by constants stay on the host."""
     blur = open(bc.generated_source("blur_f32_cpu_gen")).read()
-    assert "__global__" in blur and "dim3 block((unsigned) (8), (unsigned) (16)" in blur        # 8 lanes x 16 = 128 consecutive x
+    assert "__global__" in blur and "dim3 block((unsigned) (8), (unsigned) (32)" in blur        # 8 lanes x 32 = 256 consecutive x
+    assert "i_yo_r" in blur and "#pragma unroll" in blur                                         # 8 rows per thread
     assert "tiramisu_cuda_memcpy_to_device_async(b_b_in, h_b_in" in blur
     assert "tiramisu_cuda_memcpy_to_device_async(b_b_out" not in blur                            # fully overwritten output: no copy-in
     assert "tiramisu_cuda_memcpy_to_host(h_b_out, b_b_out" in blur
     sg = open(bc.generated_source("sgemm_cpu_sched_gen")).read()
-    assert "for (int32_t v9_k = 0; v9_k < c_K; v9_k++)" in sg                                    # the reduction loop stays sequential in the thread
+    assert re.search(r"for \(int32_t v\d+_k = 0; v\d+_k < c_K; v\d+_k\+\+\)", sg)                     # the reduction loop stays sequential in the thread
     assert "b__SIZES_buffer = (int32_t *) tb_arg(arg0)" in sg and "h__SIZES_buffer" not in sg
     assert "tiramisu_cuda_memcpy_to_device_async(b_b_C, h_b_C" in sg                             # C is read (beta*C): copied in
 
@@ -115,7 +116,7 @@ def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     assert cm.count("if (tiramisu_cublas_sgemm(") == 2 and "__global__" not in cm and cm.count("1.0f, 0.0f,") == 2
     # LSTM/cpu/generator.cpp: time and layer loops stay host loops, 13 statements inside them become kernels
     lc = open(os.path.join(bg.GEN, "lstm_cpu", "lstm.o.b200.cu")).read()
-    assert lc.count("__global__") == 15 and "for (int32_t v15_m = 0; v15_m < c_seq_length; v15_m++)" in lc
+    assert lc.count("__global__") == 15 and re.search(r"for \(int32_t v\d+_m = 0; v\d+_m < c_seq_length; v\d+_m\+\+\)", lc)
     # LSTM/gpu/generator.cpp: the hand-scheduled version keeps its 4 launches per cell and its shared tiles
     lg = open(os.path.join(bg.GEN, "lstm_gpu", "lstm.o.b200.cu")).read()
     assert lg.count("__global__") == 6 and "__shared__ float b_b_m1_R_shr[256];" in lg and "__shared__ float b_b_m1_h_shr[272];" in lg
