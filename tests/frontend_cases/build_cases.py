@@ -25,7 +25,8 @@ CASES = {
     "gemm_sym_generic": ("gemm_sym_gen.cpp", "gemm_sym_generic", "generic"),
     # CPU schedules (no gpu level, codegen without the gpu flag): re-targeted to sm_100a by the lowering
     "blur_f32_cpu_gen": ("blur_f32_cpu_gen.cpp", None, None),
-    "sgemm_cpu_sched_gen": ("sgemm_cpu_sched_gen.cpp", None, "generic"),
+    "sgemm_cpu_sched_gen": ("sgemm_cpu_sched_gen.cpp", "sgemm_cpu_sched_gen", "generic"),   # three SIMT kernels, bit-exact
+    "sgemm_cpu_sched_tc": ("sgemm_cpu_sched_gen.cpp", "sgemm_cpu_sched_tc", None),           # statement triple -> one tcgen05 GEMM
 }
 
 

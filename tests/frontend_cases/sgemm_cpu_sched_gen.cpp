@@ -9,7 +9,7 @@ using namespace tiramisu;
 
 int main(int argc, char **argv)
 {
-    tiramisu::init("sgemm_cpu_sched_gen");
+    tiramisu::init(argc > 1 ? argv[1] : "sgemm_cpu_sched_gen");
 
     input SIZES("SIZES", {"s_i"}, {3}, p_int32);
     input alpha("alpha", {"a_i"}, {1}, p_float32);
@@ -42,6 +42,7 @@ int main(int argc, char **argv)
     }
     acc_init.then(acc, computation::root).then(C, computation::root);
 
-    tiramisu::codegen({SIZES.get_buffer(), alpha.get_buffer(), beta.get_buffer(), &b_A, &b_B, &b_C}, "sgemm_cpu_sched_gen.o");
+    tiramisu::codegen({SIZES.get_buffer(), alpha.get_buffer(), beta.get_buffer(), &b_A, &b_B, &b_C},
+                      std::string(argc > 1 ? argv[1] : "sgemm_cpu_sched_gen") + ".o");
     return 0;
 }

@@ -87,6 +87,14 @@ def test_cpu_schedules_are_retargeted_not_run_on_the_host(cases):
     assert "tiramisu_cuda_memcpy_to_device_async(b_b_C, h_b_C" in sg                             # C is read (beta*C): copied in
 
 
+def test_sgemm_statement_triple_lowers_to_one_gemm_call(cases):
+    tc = open(bc.generated_source("sgemm_cpu_sched_tc")).read()
+    call = [ln for ln in tc.splitlines() if ln.strip().startswith("if (tiramisu_cublas_sgemm(")]
+    assert len(call) == 1 and "__global__" not in tc
+    assert "(uint64_t) c_N, (uint64_t) c_M, (uint64_t) c_K, c_a, c_b," in call[0]          # alpha = a, beta = b of the statement
+    assert open(bc.generated_source("sgemm_cpu_sched_gen")).read().count("__global__") == 3
+
+
 def test_non_box_domains_are_rejected(frontend_lib, tmp_path):
     src = tmp_path / "bad.cpp"
     src.write_text("""
@@ -350,3 +358,28 @@ def test_retargeted_cpu_schedule_sgemm_bit_exact(nmk):
     got = Cm.copy()
     _call(lib, "sgemm_cpu_sched_gen", np.array([n, m, k], np.int32), np.array([1.5], np.float32), np.array([-0.75], np.float32), A, B, got)
     assert np.array_equal(got, oracle.sgemm(1.5, -0.75, A, B, Cm.copy()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nmk", [(128, 128, 128), (100, 36, 52), (256, 320, 192)])
+def test_sgemm_statement_triple_on_tensor_cores(nmk):
+    """The same generator with the pattern lowering on: acc = 0; acc += A*B; C = a*acc + b*C becomes one
+    runtime GEMM call (tcgen05 TF32).  Exact on integer-valued operands (the reference's own test data
+    style), 1e-2 relative on random ones."""
+    from oracle import oracle
+    lib = _load("sgemm_cpu_sched_tc")
+    n, m, k = nmk
+    rng = np.random.default_rng(19)
+    A = rng.integers(-5, 5, (n, k)).astype(np.float32)
+    B = rng.integers(-5, 5, (k, m)).astype(np.float32)
+    Cm = rng.integers(-5, 5, (n, m)).astype(np.float32)
+    got = Cm.copy()
+    _call(lib, "sgemm_cpu_sched_tc", np.array([n, m, k], np.int32), np.array([3], np.float32), np.array([2], np.float32), A, B, got)
+    assert np.array_equal(got, oracle.sgemm(3.0, 2.0, A, B, Cm.copy()))
+    A = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    B = rng.uniform(-1, 1, (k, m)).astype(np.float32)
+    Cm = rng.uniform(-1, 1, (n, m)).astype(np.float32)
+    got = Cm.copy()
+    _call(lib, "sgemm_cpu_sched_tc", np.array([n, m, k], np.int32), np.array([1.5], np.float32), np.array([-0.75], np.float32), A, B, got)
+    want = oracle.sgemm(1.5, -0.75, A, B, Cm.copy())
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-2

@@ -14,6 +14,7 @@
 // that fp32 results are bit-identical to the x86 path (which has no FMA,
 // src/tiramisu_codegen_halide.cpp:3988-3995).
 #include "common.cuh"
+#include <cstdlib>
 #include "tiramisu_b200.h"
 
 using namespace tb200;
@@ -479,8 +480,17 @@ TB200_API int tiramisu_b200_blur_f32(const float *in, float *out, int32_t H, int
     const int rows = row_end - row_begin;
     if (rows <= 0) return 0;
     if (W % 4 == 0 && aligned16(in) && aligned8(out)) {
-        dim3 grid((W / 4 + 127) / 128, (rows + kBlurRY - 1) / kBlurRY);
-        tiramisu_sm100_blur_f32_v4<kBlurRY><<<grid, 128, 0, stream()>>>(in, out, H, W, row_begin, row_end);
+        // rows per thread: tuning knob for bring-up (TB200_BLUR_RY = 4 | 6 | 8 | 10); 6 is the measured best
+        static const int ry = [] { const char *e = getenv("TB200_BLUR_RY"); return e ? atoi(e) : kBlurRY; }();
+        dim3 grid((W / 4 + 127) / 128, (rows + ry - 1) / ry);
+        switch (ry) {
+        case 4: tiramisu_sm100_blur_f32_v4<4><<<grid, 128, 0, stream()>>>(in, out, H, W, row_begin, row_end); break;
+        case 8: tiramisu_sm100_blur_f32_v4<8><<<grid, 128, 0, stream()>>>(in, out, H, W, row_begin, row_end); break;
+        case 10: tiramisu_sm100_blur_f32_v4<10><<<grid, 128, 0, stream()>>>(in, out, H, W, row_begin, row_end); break;
+        default:
+            grid.y = (rows + kBlurRY - 1) / kBlurRY;
+            tiramisu_sm100_blur_f32_v4<kBlurRY><<<grid, 128, 0, stream()>>>(in, out, H, W, row_begin, row_end);
+        }
         return post_launch("tiramisu_sm100_blur_f32_v4");
     }
     if (rows > 65535) return fail(__func__, "grid too tall for the scalar path");

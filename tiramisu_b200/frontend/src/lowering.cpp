@@ -145,7 +145,12 @@ private:
     void emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind);
     void emit_assignment(Node *n, std::ostringstream &os, int ind, bool device);
     void emit_bindings(Node *n, std::ostringstream &os, int ind, std::vector<std::string> &conds, bool device);
+    struct Contraction { buffer *C = nullptr, *A = nullptr, *B = nullptr; bool tA = false, tB = false; expr M, N, K; };
+    bool match_contraction(computation *c, Contraction &m);
+    bool match_zero_fill(computation *z, buffer *C, const expr &M, const expr &N);
+    void emit_sgemm_call(std::ostringstream &host, int ind, const Contraction &m, buffer *C, const std::string &alpha, const std::string &beta);
     bool try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind);
+    bool try_sgemm_triple(Node *kz, Node *kr, Node *ks, const std::vector<computation *> &ord, std::ostringstream &host, int ind);
     void need_proto(const expr &call);
 };
 
@@ -660,23 +665,20 @@ void Lowering::emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind)
 // reduction iterator R may sit anywhere in the iterator list, operands may be stored transposed).
 // The kernel is not emitted: it becomes one call of the runtime's tcgen05 GEMM, beta = 1 (accumulate
 // into what the buffer holds) or beta = 0 (the zero-init is part of the pattern).
-bool Lowering::try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind)
+static std::vector<Node *> statements_of(Node *root)
 {
-    if (!pattern_) return false;
-    std::vector<Node *> stmts;
-    {
-        std::vector<Node *> order{k.root};
-        for (size_t i = 0; i < order.size(); i++) {           // pre-order, children left to right
-            Node *n = order[i];
-            if (!n->is_loop) { stmts.push_back(n); continue; }
-            size_t at = i + 1;
-            for (auto &c : n->kids) order.insert(order.begin() + (at++), c.get());
-        }
+    std::vector<Node *> stmts, order{root};
+    for (size_t i = 0; i < order.size(); i++) {               // pre-order, children left to right
+        Node *n = order[i];
+        if (!n->is_loop) { stmts.push_back(n); continue; }
+        size_t at = i + 1;
+        for (auto &c : n->kids) order.insert(order.begin() + (at++), c.get());
     }
-    if (stmts.empty() || stmts.size() > 2) return false;
-    for (Node *s : stmts) if (s->path.empty() || s->path[0] != k.root) return false;          // not inside a host loop
-    Node *stmt = stmts.back();
-    computation *c = stmt->comp;
+    return stmts;
+}
+
+bool Lowering::match_contraction(computation *c, Contraction &m)
+{
     if (c->get_data_type() != p_float32 || c->get_predicate().is_defined() || !c->get_expr().is_defined()) return false;
     const auto &iters = c->get_iteration_variables();
     if (iters.size() != 3) return false;
@@ -688,23 +690,26 @@ bool Lowering::try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind)
     if (c->access()[0].get_expr_type() != e_var || c->access()[1].get_expr_type() != e_var) return false;
     const std::string I = c->access()[0].get_name(), J = c->access()[1].get_name();
     std::string R;
-    expr M, N, Kx;
     for (const var &v : iters) {
-        if (v.get_name() == I) M = v.get_upper();
-        else if (v.get_name() == J) N = v.get_upper();
-        else { R = v.get_name(); Kx = v.get_upper(); }
+        if (v.get_name() == I) m.M = v.get_upper();
+        else if (v.get_name() == J) m.N = v.get_upper();
+        else { R = v.get_name(); m.K = v.get_upper(); }
     }
-    if (I == J || R.empty() || !M.is_defined() || !N.is_defined() || !Kx.is_defined()) return false;
+    if (I == J || R.empty() || !m.M.is_defined() || !m.N.is_defined() || !m.K.is_defined()) return false;
     const expr &e = c->get_expr();
     if (e.get_expr_type() != e_op || e.get_op_type() != o_add) return false;
     expr self = e.get_operand(0), prod = e.get_operand(1);
     if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) std::swap(self, prod);
     if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) return false;
-    if (!(self.get_expr_type() == e_op && self.get_op_type() == o_access && self.get_name() == c->get_name())) return false;
-    std::vector<std::string> own;
-    for (const var &v : iters) own.push_back(v.get_name());
-    if (self.get_n_arg() != 3) return false;
-    if (!is_var(c->access()[0].substitute(own, self.get_operands()), I) || !is_var(c->access()[1].substitute(own, self.get_operands()), J)) return false;
+    if (!(self.get_expr_type() == e_op && self.get_op_type() == o_access)) return false;
+    {   // the accumulator operand: this computation itself, or another computation stored at the same element
+        computation *sc = nullptr;
+        buffer *sb = buffer_of_access(self, &sc);
+        if (sb != C || sc->access().size() != 2 || (int) sc->get_iteration_variables().size() != self.get_n_arg()) return false;
+        std::vector<std::string> names;
+        for (const var &v : sc->get_iteration_variables()) names.push_back(v.get_name());
+        if (!is_var(sc->access()[0].substitute(names, self.get_operands()), I) || !is_var(sc->access()[1].substitute(names, self.get_operands()), J)) return false;
+    }
     // operands: P(I,R) and Q(R,J) in either order, possibly stored transposed
     struct Opnd { buffer *b = nullptr; bool trans = false; int role = -1; };   // role 0 = uses (I,R), 1 = uses (R,J)
     auto classify = [&](const expr &x, Opnd &o) {
@@ -727,25 +732,120 @@ bool Lowering::try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind)
     if (!classify(prod.get_operand(0), x) || !classify(prod.get_operand(1), y) || x.role == y.role) return false;
     const Opnd &a = x.role == 0 ? x : y, &b = x.role == 0 ? y : x;
     if (a.b == C || b.b == C) return false;
-    // optional zero-init of the same elements fused in front
-    bool zero_init = false;
-    if (stmts.size() == 2) {
-        computation *z = stmts[0]->comp;
-        const auto &zi = z->get_iteration_variables();
-        if (!z->has_access() && !z->get_expr().is_defined()) return false;
-        if (z->get_buffer() != C || zi.size() != 2 || z->get_predicate().is_defined()) return false;
-        if (!(z->get_expr().is_literal() && z->get_expr().get_double_val() == 0.0)) return false;
-        if (!is_var(z->access()[0], zi[0].get_name()) || !is_var(z->access()[1], zi[1].get_name())) return false;
-        if (!zi[0].get_upper().is_equal(M) || !zi[1].get_upper().is_equal(N)) return false;
-        for (const var &v : zi) if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0)) return false;
-        zero_init = true;
-    }
+    m.C = C; m.A = a.b; m.B = b.b; m.tA = a.trans; m.tB = b.trans;
+    return true;
+}
+
+// X(i,j) = 0 over exactly [0,M) x [0,N) of buffer C
+bool Lowering::match_zero_fill(computation *z, buffer *C, const expr &M, const expr &N)
+{
+    auto is_var = [](const expr &x, const std::string &n) { return x.get_expr_type() == e_var && x.get_name() == n; };
+    const auto &zi = z->get_iteration_variables();
+    if (!z->get_expr().is_defined() || z->get_predicate().is_defined() || zi.size() != 2) return false;
+    if (z->get_buffer() != C || z->access().size() != 2) return false;
+    if (!(z->get_expr().is_literal() && z->get_expr().get_double_val() == 0.0)) return false;
+    if (!is_var(z->access()[0], zi[0].get_name()) || !is_var(z->access()[1], zi[1].get_name())) return false;
+    if (!zi[0].get_upper().is_equal(M) || !zi[1].get_upper().is_equal(N)) return false;
+    for (const var &v : zi) if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0)) return false;
+    return true;
+}
+
+void Lowering::emit_sgemm_call(std::ostringstream &host, int ind, const Contraction &m, buffer *C, const std::string &alpha, const std::string &beta)
+{
+    host << pad(ind) << "if (tiramisu_cublas_sgemm((float *) b_" << san(m.A->get_name()) << ", (float *) b_" << san(m.B->get_name()) << ", b_" << san(C->get_name())
+         << ", (uint64_t) " << print(m.M, false) << ", (uint64_t) " << print(m.N, false) << ", (uint64_t) " << print(m.K, false)
+         << ", " << alpha << ", " << beta << ", (uint64_t) " << print(m.A->get_dim_sizes()[1], false) << ", (uint64_t) " << print(m.B->get_dim_sizes()[1], false)
+         << ", (uint64_t) " << print(C->get_dim_sizes()[1], false) << ", 0, 0, 0, " << (m.tA ? "true" : "false") << ", " << (m.tB ? "true" : "false") << ")) return 1;\n";
+}
+
+bool Lowering::try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind)
+{
+    if (!pattern_) return false;
+    std::vector<Node *> stmts = statements_of(k.root);
+    if (stmts.empty() || stmts.size() > 2) return false;
+    for (Node *s : stmts) if (s->path.empty() || s->path[0] != k.root) return false;          // not inside a host loop
+    computation *c = stmts.back()->comp;
+    Contraction m;
+    if (!match_contraction(c, m)) return false;
+    const bool zero_init = stmts.size() == 2;
+    if (zero_init && !match_zero_fill(stmts[0]->comp, m.C, m.M, m.N)) return false;
     host << pad(ind) << "// pattern lowering: '" << c->get_name() << "' is a dense fp32 contraction"
          << (zero_init ? " (zero-init fused: beta = 0)" : "") << " -> tcgen05 GEMM of the runtime\n";
-    host << pad(ind) << "if (tiramisu_cublas_sgemm((float *) b_" << san(a.b->get_name()) << ", (float *) b_" << san(b.b->get_name()) << ", b_" << san(C->get_name())
-         << ", (uint64_t) " << print(M, false) << ", (uint64_t) " << print(N, false) << ", (uint64_t) " << print(Kx, false)
-         << ", 1.0f, " << (zero_init ? "0.0f" : "1.0f") << ", (uint64_t) " << print(a.b->get_dim_sizes()[1], false) << ", (uint64_t) " << print(b.b->get_dim_sizes()[1], false)
-         << ", (uint64_t) " << print(C->get_dim_sizes()[1], false) << ", 0, 0, 0, " << (a.trans ? "true" : "false") << ", " << (b.trans ? "true" : "false") << ")) return 1;\n";
+    emit_sgemm_call(host, ind, m, m.C, "1.0f", zero_init ? "0.0f" : "1.0f");
+    return true;
+}
+
+// The sgemm_tiramisu statement triple (benchmarks/linear_algebra/blas/level3/sgemm/cpu/sgemm_generator.cpp:90-110)
+// as three consecutive kernels:  T = 0;  T += A*B over k;  C = a*T + b*C   ->   one runtime GEMM call with
+// alpha = a, beta = b.  T must be a temporary nobody reads afterwards.
+bool Lowering::try_sgemm_triple(Node *kz, Node *kr, Node *ks, const std::vector<computation *> &ord, std::ostringstream &host, int ind)
+{
+    if (!pattern_) return false;
+    auto single = [](Node *k) -> Node * {
+        std::vector<Node *> st = statements_of(k);
+        return (st.size() == 1 && !st[0]->path.empty() && st[0]->path[0] == k) ? st[0] : nullptr;
+    };
+    Node *z = single(kz), *r = single(kr), *s = single(ks);
+    if (!z || !r || !s) return false;
+    Contraction m;
+    if (!match_contraction(r->comp, m) || !match_zero_fill(z->comp, m.C, m.M, m.N)) return false;
+    buffer *T = m.C;
+    if (T->get_argument_type() != a_temporary) return false;
+    // S: C(i,j) = a * T(i,j) + b * C(i,j)
+    computation *sc = s->comp;
+    const auto &si = sc->get_iteration_variables();
+    auto is_var = [](const expr &x, const std::string &n) { return x.get_expr_type() == e_var && x.get_name() == n; };
+    if (sc->get_data_type() != p_float32 || sc->get_predicate().is_defined() || si.size() != 2 || sc->access().size() != 2) return false;
+    buffer *C = sc->get_buffer();
+    if (C == T || C == m.A || C == m.B || C->get_location() != mem_loc::gpu_global || C->get_n_dims() != 2) return false;
+    if (!is_var(sc->access()[0], si[0].get_name()) || !is_var(sc->access()[1], si[1].get_name())) return false;
+    if (!si[0].get_upper().is_equal(m.M) || !si[1].get_upper().is_equal(m.N)) return false;
+    for (const var &v : si) if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0)) return false;
+    const expr &e = sc->get_expr();
+    if (!(e.get_expr_type() == e_op && e.get_op_type() == o_add)) return false;
+    auto element_of = [&](const expr &x) -> buffer * {     // access resolving to element (i,j) of a 2-D buffer
+        if (!(x.get_expr_type() == e_op && x.get_op_type() == o_access)) return nullptr;
+        computation *oc = nullptr;
+        buffer *b = buffer_of_access(x, &oc);
+        if (!b || oc->access().size() != 2 || (int) oc->get_iteration_variables().size() != x.get_n_arg()) return nullptr;
+        std::vector<std::string> names;
+        for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+        if (!is_var(oc->access()[0].substitute(names, x.get_operands()), si[0].get_name()) ||
+            !is_var(oc->access()[1].substitute(names, x.get_operands()), si[1].get_name())) return nullptr;
+        return b;
+    };
+    auto scalar = [&](const expr &x) { return x.get_data_type() == p_float32 && (x.is_literal() || (x.get_expr_type() == e_var && constants_.count(x.get_name()))); };
+    auto scaled = [&](const expr &x, expr &k, buffer *&b) {
+        if (!(x.get_expr_type() == e_op && x.get_op_type() == o_mul)) return false;
+        for (int side = 0; side < 2; side++)
+            if (scalar(x.get_operand(side)) && (b = element_of(x.get_operand(1 - side)))) { k = x.get_operand(side); return true; }
+        return false;
+    };
+    expr k0, k1;
+    buffer *b0 = nullptr, *b1 = nullptr;
+    if (!scaled(e.get_operand(0), k0, b0) || !scaled(e.get_operand(1), k1, b1)) return false;
+    if (b0 == C && b1 == T) { std::swap(k0, k1); std::swap(b0, b1); }
+    if (b0 != T || b1 != C) return false;
+    // nobody reads T after the triple
+    bool after = false;
+    for (computation *c : ord) {
+        if (c == sc) { after = true; continue; }
+        if (!after) continue;
+        std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+        while (!stack.empty()) {
+            expr x = stack.back(); stack.pop_back();
+            if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+            if (x.get_op_type() == o_access) {
+                computation *oc = f_->find_computation(x.get_name());
+                if (oc && !oc->is_constant() && oc->get_buffer() == T) return false;
+            }
+            if (x.get_op_type() == o_buffer && x.get_name() == T->get_name()) return false;
+            for (const expr &o : x.get_operands()) stack.push_back(o);
+        }
+    }
+    host << pad(ind) << "// pattern lowering: '" << z->comp->get_name() << "' = 0; '" << r->comp->get_name() << "' += A*B; '" << sc->get_name()
+         << "' = a*acc + b*C  (the sgemm_tiramisu statement) -> one tcgen05 GEMM call of the runtime\n";
+    emit_sgemm_call(host, ind, m, C, print(k0, false), print(k1, false));
     return true;
 }
 
@@ -1243,6 +1343,11 @@ std::string Lowering::run()
         if (i + 1 < root_.kids.size() && is_kernel(k) && is_kernel(root_.kids[i + 1].get()) &&
             try_heat2d_pattern(k, root_.kids[i + 1].get(), body, 1)) {
             i++;
+            continue;
+        }
+        if (i + 2 < root_.kids.size() && is_kernel(k) && is_kernel(root_.kids[i + 1].get()) && is_kernel(root_.kids[i + 2].get()) &&
+            try_sgemm_triple(k, root_.kids[i + 1].get(), root_.kids[i + 2].get(), ord, body, 1)) {
+            i += 2;
             continue;
         }
         emit_host(k, body, 1, host_loops);
