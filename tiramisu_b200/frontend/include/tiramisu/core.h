@@ -155,6 +155,7 @@ public:
     virtual void unroll(var L, int fac);
     virtual void unroll(var L, int fac, var L_outer, var L_inner);
     virtual void tag_unroll_level(var L);
+    virtual void tag_unroll_level(var L, int) { tag_unroll_level(L); }
     virtual void shift(var L0, int n);
 
     /** Order: \p next runs after this computation, sharing the loops up to and including \p level. */
@@ -176,6 +177,7 @@ public:
     void store_in(std::vector<expr> mapping, std::vector<expr> sizes);
     buffer *get_buffer();
     buffer *get_automatically_allocated_buffer() { return get_buffer(); }
+    void allocate_and_map_buffer_automatically(argument_t type = a_temporary) { get_buffer()->set_argument_type(type); }
     void set_access_exprs(buffer *b, std::vector<expr> idx);
     /** Old-style data mapping, `{S[i,j]->buf[i+1,j]}` (reference core.h:4180). */
     void set_access(std::string access_str);
@@ -267,7 +269,7 @@ public:
     }
     void set_arguments(const std::vector<buffer *> &args) { args_ = args; }
     const std::vector<buffer *> &get_arguments() const { return args_; }
-    void codegen(const std::vector<buffer *> &arguments, const std::string obj_filename, bool gen_cuda_stmt);
+    void codegen(const std::vector<buffer *> &arguments, const std::string obj_filename, bool gen_cuda_stmt = false);
     void dump(bool) const;
     // Old-style driver sequence (reference core.h:289-1166).  The intermediate stages have no
     // counterpart here (no ISL AST, no Halide statement): they only record what was asked for and
@@ -281,6 +283,13 @@ public:
     void dump_halide_stmt() const {}
     void gen_halide_obj(const std::string &obj_file_name, bool gen_python = false);
     void gen_c_code() const {}
+    /** Buffers are mapped lazily (computation::get_buffer): nothing to do ahead of time. */
+    void allocate_and_map_buffers_automatically() {}
+    void compute_bounds() {}
+    void dump_dep_graph() {}
+    void dump_halide_IR() const {}
+    void dump_time_processor_domain() const {}
+    void dump_trimmed_time_processor_domain() const {}
     void dump_iteration_domain() const {}
     void dump_schedule() const {}
     void dump_sched_graph() {}

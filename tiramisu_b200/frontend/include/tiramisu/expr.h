@@ -33,6 +33,7 @@ class global {
 public:
     static void set_default_tiramisu_options();
     static void set_loop_iterator_type(primitive_t t);
+    static void set_loop_iterator_default_data_type(primitive_t t) { set_loop_iterator_type(t); }
     static primitive_t get_loop_iterator_data_type();
     static function *get_implicit_function();
     static void set_implicit_function(function *f);

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <cstdint>
 #include <cstdlib>
 #include <iostream>
 
@@ -154,14 +155,22 @@ void parse_conjunction(Reader &rd, std::vector<Cmp> &out)
     }
 }
 
-std::vector<std::string> parse_name_list(Reader &rd)
+// `fixed` (optional) receives, per position, the literal written in place of an iterator name
+// (`{S[i,j,0]}`: a dimension pinned to one value), or INT64_MIN for a named iterator.
+std::vector<std::string> parse_name_list(Reader &rd, std::vector<int64_t> *fixed = nullptr)
 {
     std::vector<std::string> names;
     rd.expect("[");
     if (!rd.accept("]")) {
         do {
+            if (rd.peek().k == Tok::num && fixed) {
+                fixed->push_back(rd.next().v);
+                names.push_back("_fixed" + std::to_string(names.size()));
+                continue;
+            }
             if (rd.peek().k != Tok::id) rd.fail("expected an identifier");
             names.push_back(rd.next().s);
+            if (fixed) fixed->push_back(INT64_MIN);
         } while (rd.accept(","));
         rd.expect("]");
     }
@@ -177,12 +186,15 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
     rd.expect("{");
     if (rd.peek().k != Tok::id) rd.fail("expected the computation name");
     std::string name = rd.next().s;
-    std::vector<std::string> iters = parse_name_list(rd);
+    std::vector<int64_t> fixed;
+    std::vector<std::string> iters = parse_name_list(rd, &fixed);
     std::vector<Cmp> cmps;
     if (rd.accept(":")) parse_conjunction(rd, cmps);
     rd.expect("}");
 
     std::vector<expr> lo(iters.size()), hi(iters.size());
+    for (size_t i = 0; i < iters.size(); i++)
+        if (fixed[i] != INT64_MIN) { lo[i] = expr((int32_t) fixed[i]); hi[i] = expr((int32_t) (fixed[i] + 1)); }
     auto iter_index = [&](const expr &x) {
         if (x.get_expr_type() != e_var) return -1;
         for (size_t i = 0; i < iters.size(); i++) if (iters[i] == x.get_name()) return (int) i;
@@ -226,7 +238,8 @@ void computation::set_access(std::string access_str)
     rd.expect("{");
     if (rd.peek().k != Tok::id) rd.fail("expected the computation name");
     rd.next();
-    std::vector<std::string> names = parse_name_list(rd);
+    std::vector<int64_t> fixed;
+    std::vector<std::string> names = parse_name_list(rd, &fixed);
     rd.expect("->");
     if (rd.peek().k != Tok::id) rd.fail("expected a buffer name");
     std::string bname = rd.next().s;

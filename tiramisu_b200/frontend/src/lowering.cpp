@@ -107,6 +107,7 @@ private:
     bool retargeted_ = false;                 // CPU schedule mapped onto the GPU; host arguments mirrored on the device
     std::set<buffer *> mirrored_;             // argument buffers with a device mirror (b_X device, h_X host)
     std::set<buffer *> no_copy_in_;           // outputs that are completely overwritten before being read
+    std::set<buffer *> written_args_;         // mirrored arguments some statement stores into (copied back whatever their declared type)
     std::set<buffer *> direct_;               // mirrored arguments handed to a runtime entry point as halide buffers
     size_t n_statements_ = 0;
     void propagate_constants();
@@ -558,7 +559,7 @@ std::string Lowering::print(const expr &e, bool device)
     case o_abs: return is_float_type(t) ? std::string(t == p_float32 ? "fabsf(" : "fabs(") + A(0) + ")" : "tb_abs<" + std::string(ctype(t)) + ">(" + A(0) + ")";
     case o_cast: return "((" + std::string(ctype(t)) + ") " + A(0) + ")";
     case o_select: case o_cond: return "(" + A(0) + " ? " + A(1) + " : " + A(2) + ")";
-    case o_lerp: return "(" + A(0) + " + (" + A(1) + " - " + A(0) + ") * " + A(2) + ")";
+    case o_lerp: return "tb_lerp<" + std::string(ctype(t)) + ">(" + A(0) + ", " + A(1) + ", " + A(2) + ")";
     case o_access: return print_access(e, device);
     case o_buffer: {
         buffer *b = f_->find_buffer(e.get_name());
@@ -1041,7 +1042,14 @@ void Lowering::auto_map(computation *c, int shared_depth)
                                                                        e.get_op_type() == o_free || (e.get_op_type() == o_call && !c->has_access()))))
         return;
     auto &dims = c->dims();
-    if (dims.empty()) die("'" + c->get_name() + "': a computation without loops cannot be mapped onto the GPU");
+    auto one_thread = [&]() {
+        // nothing to spread over threads (a scalar statement, or every loop carries a dependence): the
+        // statement's own loops run sequentially inside a one-thread kernel
+        loop_dim one; one.name = "_one_" + c->get_name(); one.lo = expr((int32_t) 0); one.hi = expr((int32_t) 1); one.tag = loop_dim::gpu_block;
+        for (auto &d : dims) d.tag = loop_dim::none;
+        dims.insert(dims.begin() + shared_depth, one);
+    };
+    if (dims.empty()) { one_thread(); return; }
     // which original iterators index the stored element
     std::vector<std::string> stored;
     for (const var &v : c->get_iteration_variables()) {
@@ -1069,12 +1077,7 @@ void Lowering::auto_map(computation *c, int shared_depth)
     int vec = -1;
     for (size_t i = shared_depth; i < dims.size(); i++) if (dims[i].tag == loop_dim::vector && parallel_safe(dims[i].name)) vec = (int) i;
     for (auto &d : dims) d.tag = loop_dim::none;
-    if ((int) dims.size() == shared_depth) {
-        // nothing of its own to map: run the statement as a one-thread kernel inside the shared host loops
-        loop_dim one; one.name = "_one_" + c->get_name(); one.lo = expr((int32_t) 0); one.hi = expr((int32_t) 1); one.tag = loop_dim::gpu_block;
-        dims.push_back(one);
-        return;
-    }
+    if ((int) dims.size() == shared_depth) { one_thread(); return; }
     std::string tx, ty, bx;
     if (vec >= shared_depth + 1 && parallel_safe(dims[vec - 1].name) && dims[vec].hi.is_int_literal() && dims[vec].hi.get_int_val() <= 64) {
         const int lanes = (int) dims[vec].hi.get_int_val();
@@ -1086,7 +1089,7 @@ void Lowering::auto_map(computation *c, int shared_depth)
     } else {
         int q = -1;
         for (int i = (int) dims.size() - 1; i >= shared_depth; i--) if (parallel_safe(dims[i].name)) { q = i; break; }
-        if (q < 0) die("'" + c->get_name() + "' has no data-parallel loop to map onto the GPU");
+        if (q < 0) { one_thread(); return; }
         std::string inner = dims[q].name;
         bx = inner + "_b"; tx = inner + "_t";
         c->split(var(inner), 256, var(bx), var(tx));
@@ -1138,7 +1141,10 @@ void Lowering::retarget(const std::vector<computation *> &ord)
     // (SIZES / alpha / beta style parameter vectors) stay where the caller put them
     std::set<buffer *> used;
     for (computation *c : ord) {
-        if (c->has_access() || c->get_expr().get_expr_type() != e_op || c->get_expr().get_op_type() != o_call) used.insert(c->get_buffer());
+        if (c->has_access() || c->get_expr().get_expr_type() != e_op || c->get_expr().get_op_type() != o_call) {
+            used.insert(c->get_buffer());
+            written_args_.insert(c->get_buffer());
+        }
         std::vector<expr> stack{c->get_expr(), c->get_predicate()};
         while (!stack.empty()) {
             expr x = stack.back(); stack.pop_back();
@@ -1355,7 +1361,7 @@ std::string Lowering::run()
 
     std::ostringstream out;
     out << "// Generated by the tiramisu_b200 sm_100a lowering for Tiramisu function '" << f_->get_name() << "'. Do not edit.\n"
-        << "#include <cstdint>\n#include <cstdlib>\n#include <cstring>\n#include <cmath>\n#include <cuda_runtime.h>\n\n"
+        << "#include <cstdint>\n#include <cstdlib>\n#include <cstring>\n#include <cmath>\n#include <type_traits>\n#include <cuda_runtime.h>\n\n"
         << "#ifndef HALIDE_HALIDERUNTIME_H\n"
         << "struct halide_dimension_t { int32_t min, extent, stride; uint32_t flags; };\n"
         << "struct halide_type_t { uint8_t code, bits; uint16_t lanes; };\n"
@@ -1375,6 +1381,11 @@ std::string Lowering::run()
         << "template <typename T> __host__ __device__ __forceinline__ T tb_max(T a, T b) { return a > b ? a : b; }\n"
         << "template <typename T> __host__ __device__ __forceinline__ T tb_min(T a, T b) { return a < b ? a : b; }\n"
         << "template <typename T> __host__ __device__ __forceinline__ T tb_abs(T a) { return a < 0 ? -a : a; }\n"
+        << "// Halide's lerp: an unsigned integer weight is a fixed-point fraction of its type's maximum\n"
+        << "template <typename T, typename W> __host__ __device__ __forceinline__ T tb_lerp(T a, T b, W w) {\n"
+        << "    const double wf = std::is_floating_point<W>::value ? (double) w : (double) w / (double) (W) ~(W) 0;\n"
+        << "    const double r = (double) a * (1.0 - wf) + (double) b * wf;\n"
+        << "    return std::is_floating_point<T>::value ? (T) r : (T) (r + 0.5);\n}\n"
         << "static inline void *tb_arg(halide_buffer_t *b) { return b->host ? (void *) b->host : (void *) b->device; }\n\n";
     out << protos_.str() << "\n" << kernels_.str();
 
@@ -1420,7 +1431,7 @@ std::string Lowering::run()
         if (!mirrored_.count(b) || direct_.count(b)) continue;
         const std::string N = san(b->get_name());
         out << pad(1) << "if (h_" << N << ") {\n";
-        if (b->get_argument_type() == a_output)
+        if (b->get_argument_type() == a_output || written_args_.count(b))
             out << pad(2) << "tiramisu_cuda_memcpy_to_host(h_" << N << ", b_" << N << ", " << bytes_of(b, false) << ");\n";
         out << pad(2) << "tiramisu_cuda_free(b_" << N << ");\n" << pad(1) << "}\n";
     }
