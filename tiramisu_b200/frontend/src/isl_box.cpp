@@ -108,6 +108,10 @@ private:
         if (peek().k == Tok::id) {
             std::string name = next().s;
             if (name == "floor" || name == "floord") { expect("("); expr e = parse_expr(); expect(")"); return e; }   // floor(a / b): operands are non-negative here
+            if ((name == "min" || name == "max") && peek().s == "(") {                                               // clamped accesses
+                expect("("); expr a = parse_expr(); expect(","); expr b = parse_expr(); expect(")");
+                return expr(name == "min" ? o_min : o_max, a, b);
+            }
             return expr::make_var(global::get_loop_iterator_data_type(), name);
         }
         fail("expected an expression");

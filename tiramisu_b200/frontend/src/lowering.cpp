@@ -112,6 +112,7 @@ private:
     size_t n_statements_ = 0;
     void propagate_constants();
     void retarget(const std::vector<computation *> &ord);
+    void mirror_buffers(const std::vector<computation *> &ord, bool gpu_only);
     void auto_map(computation *c, int shared_depth);
     static int fuse_depth(computation *prev, computation *c);
     bool try_heat2d_pattern(Node *zero, Node *heat, std::ostringstream &host, int ind);
@@ -1127,25 +1128,28 @@ void Lowering::auto_map(computation *c, int shared_depth)
     }
 }
 
-void Lowering::retarget(const std::vector<computation *> &ord)
+// Host buffers touched by device statements move to the device: arguments get a mirror (b_X device,
+// h_X host, copies at entry / exit), temporaries are simply allocated there.  Buffers only read by function
+// constants (SIZES / alpha / beta style parameter vectors) stay where the caller put them.
+// `gpu_only`: consider only statements that carry gpu levels (old-style gpu tests that tag loops but keep
+// plain host buffers, reference tests/test_17.cpp) — the rest of such a function stays host code.
+void Lowering::mirror_buffers(const std::vector<computation *> &ord, bool gpu_only)
 {
-    retargeted_ = true;
-    std::vector<int> shared(ord.size(), 0);
-    for (size_t i = 0; i < ord.size(); i++) {
-        int with_prev = i ? fuse_depth(ord[i - 1], ord[i]) : 0;
-        int with_next = i + 1 < ord.size() ? fuse_depth(ord[i], ord[i + 1]) : 0;
-        shared[i] = std::max(with_prev, with_next);
-    }
-    for (size_t i = 0; i < ord.size(); i++) auto_map(ord[i], shared[i]);
-    // buffers the statements touch move to the device; buffers only read by function constants
-    // (SIZES / alpha / beta style parameter vectors) stay where the caller put them
+    auto on_gpu = [](computation *c) {
+        for (auto &d : c->dims()) if (d.tag == loop_dim::gpu_block || d.tag == loop_dim::gpu_thread) return true;
+        return false;
+    };
     std::set<buffer *> used;
     for (computation *c : ord) {
-        if (c->has_access() || c->get_expr().get_expr_type() != e_op || c->get_expr().get_op_type() != o_call) {
+        if (gpu_only && !on_gpu(c)) continue;
+        const expr &e = c->get_expr();
+        const bool stmt_only = e.get_expr_type() == e_sync || (e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate || e.get_op_type() == o_free));
+        if (!stmt_only && (c->has_access() || e.get_expr_type() != e_op || e.get_op_type() != o_call)) {
             used.insert(c->get_buffer());
             written_args_.insert(c->get_buffer());
         }
         std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+        for (auto &d : c->dims()) { stack.push_back(d.lo); stack.push_back(d.hi); }
         while (!stack.empty()) {
             expr x = stack.back(); stack.pop_back();
             if (!x.is_defined() || x.get_expr_type() != e_op) continue;
@@ -1162,6 +1166,19 @@ void Lowering::retarget(const std::vector<computation *> &ord)
         b->tag_gpu_global();
         if (is_arg.count(b)) mirrored_.insert(b);
     }
+}
+
+void Lowering::retarget(const std::vector<computation *> &ord)
+{
+    retargeted_ = true;
+    std::vector<int> shared(ord.size(), 0);
+    for (size_t i = 0; i < ord.size(); i++) {
+        int with_prev = i ? fuse_depth(ord[i - 1], ord[i]) : 0;
+        int with_next = i + 1 < ord.size() ? fuse_depth(ord[i], ord[i + 1]) : 0;
+        shared[i] = std::max(with_prev, with_next);
+    }
+    for (size_t i = 0; i < ord.size(); i++) auto_map(ord[i], shared[i]);
+    mirror_buffers(ord, false);
     // outputs whose first use is a statement that overwrites every element need no copy-in
     for (buffer *b : args_) {
         if (b->get_argument_type() != a_output) continue;
@@ -1337,6 +1354,8 @@ std::string Lowering::run()
         std::cerr << "tiramisu_b200 lowering: '" << f_->get_name() << "' is a CPU schedule; there is no CPU code generator: "
                      "re-targeting its loop nests to sm_100a (parallel -> blocks, vector -> threads, device mirrors for host buffers)\n";
         retarget(ord);
+    } else if (any_gpu) {
+        mirror_buffers(ord, true);          // gpu-tagged statements over plain host buffers (no memcpy computations)
     }
     build_tree(ord);
     assign_axes(&root_);
