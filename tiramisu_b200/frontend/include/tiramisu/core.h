@@ -66,6 +66,10 @@ public:
     computation *deallocate_at(computation &C, var level);
     void dump(bool) const;
     void substitute_dims(const std::vector<std::string> &names, const std::vector<expr> &values);
+    void replace_dim(const expr &from, const expr &to)
+    {
+        for (expr &d : dims_) if (d.is_equal(from)) d = to;
+    }
 
 private:
     std::string name_;

@@ -225,6 +225,7 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
             die("iteration domain of '" + name + "' is not a box (constraint couples iterators): \"" + iteration_domain + "\"");
         }
     }
+    if (!e.is_defined()) schedule_this_computation = false;      // a declaration only (input / wrapper computation)
     std::vector<var> vars;
     for (size_t i = 0; i < iters.size(); i++) {
         if (lo[i].is_defined() && hi[i].is_defined()) vars.push_back(var(iters[i], lo[i], hi[i]));

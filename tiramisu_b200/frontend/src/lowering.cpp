@@ -111,6 +111,9 @@ private:
     std::set<buffer *> direct_;               // mirrored arguments handed to a runtime entry point as halide buffers
     size_t n_statements_ = 0;
     void propagate_constants();
+    void hoist_buffer_extents();
+    struct ExtentRewrite { buffer *b; expr from, to; };
+    std::vector<ExtentRewrite> extent_rewrites_;
     void retarget(const std::vector<computation *> &ord);
     void mirror_buffers(const std::vector<computation *> &ord, bool gpu_only);
     void auto_map(computation *c, int shared_depth);
@@ -457,6 +460,11 @@ std::string Lowering::literal(const expr &e)
 std::string Lowering::lin_index(buffer *b, const std::vector<expr> &idx, bool device)
 {
     const auto &dims = b->get_dim_sizes();
+    if (idx.empty() && !dims.empty()) {
+        // `store_in(&buf, {})`: the computation owns the buffer's first element (reference tests/test_106.cpp:21)
+        std::vector<expr> zeros(dims.size(), expr((int32_t) 0));
+        return lin_index(b, zeros, device);
+    }
     if (idx.size() != dims.size())
         die("buffer '" + b->get_name() + "' has " + std::to_string(dims.size()) + " dimensions but is accessed with " + std::to_string(idx.size()) + " indices");
     bool small = b->get_location() == mem_loc::gpu_shared || b->get_location() == mem_loc::gpu_local || b->get_location() == mem_loc::gpu_register;
@@ -1007,6 +1015,36 @@ void Lowering::emit_host(Node *n, std::ostringstream &os, int ind, std::vector<N
 // Function constants whose definition folds to a literal are substituted everywhere (the Halide-derived
 // generators name every loop bound: `heat2d_s1_r__y_loop_min` = 1 ...), so that extents, divisibility
 // and the pattern matchers see numbers.
+// A buffer extent written as an access (`buffer S0_b("S0_b", {N_input(0), N_input(0)}, ...)`, reference
+// tests/test_87.cpp:50) would make every kernel dereference a host parameter vector: such extents are
+// evaluated once at function entry, like declared constants.
+void Lowering::hoist_buffer_extents()
+{
+    int n = 0;
+    for (buffer *b : f_->get_buffers()) {
+        std::vector<std::string> names;
+        std::vector<expr> values;
+        for (const expr &d : b->get_dim_sizes()) {
+            bool has_access = false;
+            std::vector<expr> stack{d};
+            while (!stack.empty()) {
+                expr x = stack.back(); stack.pop_back();
+                if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+                if (x.get_op_type() == o_access) {
+                    computation *oc = f_->find_computation(x.get_name());
+                    if (oc && !oc->is_constant()) has_access = true;
+                }
+                for (const expr &o : x.get_operands()) stack.push_back(o);
+            }
+            if (!has_access) continue;
+            std::string cname = "_extent" + std::to_string(n++) + "_" + b->get_name();
+            f_->own(new constant(cname, d, global::get_loop_iterator_data_type(), true, nullptr, 0, f_));
+            extent_rewrites_.push_back({b, d, expr::make_var(global::get_loop_iterator_data_type(), cname)});
+        }
+    }
+    for (auto &rw : extent_rewrites_) rw.b->replace_dim(rw.from, rw.to);
+}
+
 void Lowering::propagate_constants()
 {
     std::vector<std::string> names;
@@ -1338,6 +1376,7 @@ bool Lowering::try_heat2d_pattern(Node *zero, Node *heat, std::ostringstream &ho
 std::string Lowering::run()
 {
     if (const char *m = getenv("TIRAMISU_B200_LOWERING")) pattern_ = std::string(m) != "generic";
+    hoist_buffer_extents();
     propagate_constants();
     for (computation *c : f_->get_computations())
         if (c->is_constant()) { constants_[c->get_name()] = c; constant_order_.push_back(c); }
