@@ -46,6 +46,7 @@ TARGETS = {
     # wrapper needs cuDNN, so that object is linked into a shared library and driven from the tests.
     "lstm_cpu": ("benchmarks/DNN/blocks/LSTM/cpu/generator.cpp", "lstm.o", "benchmarks/DNN/blocks/LSTM/cpu/wrapper.cpp",
                  ["benchmarks/DNN/blocks/LSTM/cpu"], []),
+    "lstm_cpu_so": ("benchmarks/DNN/blocks/LSTM/cpu/generator.cpp", "lstm.o", None, ["benchmarks/DNN/blocks/LSTM/cpu"], []),
     "lstm_gpu": ("benchmarks/DNN/blocks/LSTM/gpu/generator.cpp", "lstm.o", None, ["benchmarks/DNN/blocks/LSTM/gpu"], []),
     # the same generator with PATCHES["lstm_gpu_fixed"] applied to a scratch copy (see there)
     "lstm_gpu_fixed": ("benchmarks/DNN/blocks/LSTM/gpu/generator.cpp", "lstm.o", None, ["benchmarks/DNN/blocks/LSTM/gpu"], []),
@@ -144,7 +145,7 @@ def build(names=None, verbose=False) -> dict:
     import concurrent.futures as cf
     jobs = [(n, None) for n in TARGETS if not names or n in names]
     # the pattern-lowered generators once more with the pattern lowering off (generic SIMT emission)
-    jobs += [(n, "generic") for n in ("test_167", "test_169", "heat2d", "chain_mm") if not names or n in names]
+    jobs += [(n, "generic") for n in ("test_167", "test_169", "heat2d", "chain_mm", "lstm_cpu", "lstm_cpu_so") if not names or n in names]
     out = {}
     with cf.ThreadPoolExecutor(max_workers=min(6, max(1, len(jobs)))) as ex:
         futs = {ex.submit(build_one, n, low): (n if low is None else f"{n}_{low}") for n, low in jobs}

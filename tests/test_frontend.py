@@ -118,12 +118,15 @@ def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     res = bg.build()
     failed = {k: v[1] for k, v in res.items() if v[0] != 0}
     assert not failed, failed
-    assert len(res) == len(bg.TARGETS) + 4          # + the generic-lowering variants
+    assert len(res) == len(bg.TARGETS) + 6          # + the generic-lowering variants
     # chain_mm/gpu/generator.cpp: two fused (zero-init + reduction) kernels -> two runtime GEMM calls, beta = 0
     cm = open(os.path.join(bg.GEN, "chain_mm", "fct.o.b200.cu")).read()
     assert cm.count("if (tiramisu_cublas_sgemm(") == 2 and "__global__" not in cm and cm.count("1.0f, 0.0f,") == 2
     # LSTM/cpu/generator.cpp: time and layer loops stay host loops, 13 statements inside them become kernels
     lc = open(os.path.join(bg.GEN, "lstm_cpu", "lstm.o.b200.cu")).read()
+    # the gate pre-activations (a matrix-vector product per output) get the warp-shuffle reduction lowering
+    assert "__shfl_xor_sync(0xffffffffu, acc, off)" in lc and "shuffle reduction" in lc
+    assert "__shfl_xor_sync" not in open(os.path.join(bg.GEN, "lstm_cpu_generic", "lstm.o.b200.cu")).read()
     assert lc.count("__global__") == 15 and re.search(r"for \(int32_t v\d+_m = 0; v\d+_m < c_seq_length; v\d+_m\+\+\)", lc)
     # LSTM/gpu/generator.cpp: the hand-scheduled version keeps its 4 launches per cell and its shared tiles
     lg = open(os.path.join(bg.GEN, "lstm_gpu", "lstm.o.b200.cu")).read()
@@ -220,9 +223,36 @@ def test_reference_lstm_cpu_generator_retargeted(tmp_path):
     with open(tmp_path / "mkldnn_result.txt", "w") as f:
         for v in want.reshape(-1):
             f.write(f"{float(v):.9g}\n")
-    out = _run("lstm_cpu", cwd=tmp_path)
-    pct = [ln for ln in out.splitlines() if "Percentage of correctness" in ln]
-    assert pct and float(pct[0].split()[-1]) >= 99.0, out[-2000:]
+    # the +-1 weights make the 100-step recurrence chaotic: the statement-order (generic) object is held to
+    # 99 %, the one whose gate sums are re-associated by the warp-shuffle reduction to the TF32 path's 97 %
+    for name, floor in (("lstm_cpu_generic", 99.0), ("lstm_cpu", 97.0)):
+        out = _run(name, cwd=tmp_path)
+        pct = [ln for ln in out.splitlines() if "Percentage of correctness" in ln]
+        assert pct and float(pct[0].split()[-1]) >= floor, (name, out[-2000:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,tol", [("lstm_cpu_so", 1e-5), ("lstm_cpu_so_generic", 1e-5)])
+def test_reference_lstm_cpu_generator_against_oracle(variant, tol):
+    """Same generator through its lstm(params, Weights, biases, x, y) ABI with weights scaled by 1/16 (gates do
+    not saturate): both lowerings agree with the oracle to 1e-5 (libm vs CUDA expf/tanhf, and the
+    re-associated gate sums of the warp-shuffle reduction)."""
+    from oracle import oracle
+    path = os.path.join(bg.BIN, f"libgen_{variant}.so")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not built")
+    from tiramisu_b200 import _lib
+    _lib.lib()
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    F, B, L, T = 96, 5, 3, 7
+    rng = np.random.default_rng(20)
+    Wt = (rng.uniform(-1, 1, (L, 2, 4 * F, F)) / 16).astype(np.float32)
+    bias = rng.uniform(-1, 1, (L, 4 * F)).astype(np.float32)
+    x = rng.uniform(-1, 1, (T, B, F)).astype(np.float32)
+    y = np.zeros((T, B, F), np.float32)
+    _call(lib, "lstm", np.array([F, B, L, T], np.int32), Wt, bias, x, y)
+    want = oracle.lstm(Wt, bias, x)
+    assert np.abs(y - want).max() <= tol * max(1.0, np.abs(want).max()), np.abs(y - want).max()
 
 
 @pytest.mark.gpu

@@ -87,6 +87,7 @@ struct loop_dim {
     expr lo, hi;                 // half-open [lo, hi)
     enum tag_t { none, gpu_block, gpu_thread, parallel, vector, unrolled, distributed } tag = none;
     int vec_len = 0;
+    bool warp_reduce = false;    // lowering: reduction loop strided over the 32 lanes of a warp, combined by shuffles
 };
 
 class computation {

@@ -68,6 +68,7 @@ struct Node {
     loop_dim::tag_t tag = loop_dim::none;
     int axis = -1;               // gpu axis (0 = x)
     bool launch_guard = false;   // launch dimension may exceed this loop's extent
+    bool warp_reduce = false;    // reduction loop strided over the lanes of a warp (see Lowering::warp_reduction_terms)
     std::vector<std::unique_ptr<Node>> kids;
     // statement
     computation *comp = nullptr;
@@ -117,6 +118,8 @@ private:
     void retarget(const std::vector<computation *> &ord);
     void mirror_buffers(const std::vector<computation *> &ord, bool gpu_only);
     void auto_map(computation *c, int shared_depth);
+    bool warp_reduction_terms(computation *c, const std::string &r, std::vector<expr> *summands);
+    void emit_warp_reduction(Node *loop, std::ostringstream &os, int ind);
     static int fuse_depth(computation *prev, computation *c);
     bool try_heat2d_pattern(Node *zero, Node *heat, std::ostringstream &host, int ind);
     // index simplification context of the statement being emitted
@@ -219,7 +222,7 @@ void Lowering::build_tree(const std::vector<computation *> &ord)
         for (int d = depth; d < (int) dims.size(); d++) {
             auto n = std::make_unique<Node>();
             n->is_loop = true; n->id = next_id_++; n->dim_name = dims[d].name;
-            n->lo = dims[d].lo; n->hi = dims[d].hi; n->tag = dims[d].tag;
+            n->lo = dims[d].lo; n->hi = dims[d].hi; n->tag = dims[d].tag; n->warp_reduce = dims[d].warp_reduce;
             Node *raw = n.get();
             (open.empty() ? &root_ : open.back())->kids.push_back(std::move(n));
             open.push_back(raw);
@@ -645,6 +648,8 @@ void Lowering::emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind)
             os << pad(ind) << "const " << it << " " << n->cname() << " = " << (zero ? "" : print(n->lo, true) + " + ") << "(" << it << ") "
                << (n->tag == loop_dim::gpu_block ? "blockIdx." : "threadIdx.") << ax[n->axis] << ";\n";
             for (auto &c : n->kids) emit_device(c.get(), k, os, ind);
+        } else if (n->warp_reduce && n->kids.size() == 1 && !n->kids.front()->is_loop) {
+            emit_warp_reduction(n, os, ind);
         } else {
             expr ext = n->hi - n->lo;
             if (n->tag == loop_dim::unrolled || (ext.is_int_literal() && ext.get_int_val() <= 32)) os << pad(ind) << "#pragma unroll\n";
@@ -913,7 +918,7 @@ void Lowering::emit_kernel(Node *n, std::ostringstream &host, int ind, std::vect
     }
     emit_device(n, k, body, 1);
 
-    os << "__global__ void ";
+    os << "static __global__ void ";          // internal linkage (as the reference emits): two generated objects in one process may reuse names
     int64_t nthreads = 1;
     bool known = true;
     for (int a = 0; a < 3; a++) { if (k.block[a].is_int_literal()) nthreads *= k.block[a].get_int_val(); else known = false; }
@@ -1074,6 +1079,111 @@ void Lowering::propagate_constants()
 //     that do not index the stored element) stay sequential inside the thread;
 //   * host buffers get device mirrors: inputs are copied in at entry, outputs copied back at exit —
 //     an output that the first statement overwrites completely is not copied in.
+// Warp-shuffle reduction (pattern mode only: it re-associates the sum).  A statement
+//     X(..) = X(..) + t1(.., r) + t2(.., r) ...
+// whose reduction iterator r is the unit-stride index of everything that reads it (a matrix-vector
+// product against row-major operands: the gate pre-activations of benchmarks/DNN/blocks/LSTM/cpu/
+// generator.cpp:40-41) would, mapped one output per thread, make the 32 lanes of a warp read 32
+// different rows.  Instead one warp owns one output: lane L accumulates r = L, L+32, ... in a register
+// (coalesced 128-byte reads), the partial sums are combined with __shfl_xor_sync and lane 0 adds the result to X.
+bool Lowering::warp_reduction_terms(computation *c, const std::string &r, std::vector<expr> *summands)
+{
+    const expr &e = c->get_expr();
+    if (!e.is_defined() || e.get_expr_type() != e_op || e.get_op_type() != o_add || !c->has_access()) return false;
+    std::vector<expr> terms, stack{e};
+    while (!stack.empty()) {              // flatten the left-leaning + chain, keeping the written order
+        expr x = stack.back(); stack.pop_back();
+        if (x.get_expr_type() == e_op && x.get_op_type() == o_add) { stack.push_back(x.get_operand(1)); stack.push_back(x.get_operand(0)); }
+        else terms.push_back(x);
+    }
+    auto mentions = [&](const expr &x, const std::string &v) { return !x.substitute({v}, {expr((int32_t) 0)}).is_equal(x) || (x.get_expr_type() == e_var && x.get_name() == v); };
+    int self = -1;
+    for (size_t t = 0; t < terms.size(); t++) {
+        const expr &x = terms[t];
+        if (!(x.get_expr_type() == e_op && x.get_op_type() == o_access)) continue;
+        computation *oc = nullptr;
+        buffer *b = buffer_of_access(x, &oc);
+        if (b != c->get_buffer() || oc->access().size() != c->access().size() || (int) oc->get_iteration_variables().size() != x.get_n_arg()) continue;
+        std::vector<std::string> names;
+        for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+        bool same = true;
+        for (size_t q = 0; q < c->access().size(); q++) same &= oc->access()[q].substitute(names, x.get_operands()).is_equal(c->access()[q]);
+        if (same) { if (self >= 0) return false; self = (int) t; }
+    }
+    if (self < 0 || terms.size() < 2) return false;
+    for (const expr &a : c->access()) if (mentions(a, r)) return false;
+    // every access that reads r reads it as its last (unit-stride) index, and nothing else may read the buffer written
+    bool any = false;
+    for (size_t t = 0; t < terms.size(); t++) {
+        if ((int) t == self) continue;
+        std::vector<expr> st{terms[t]};
+        while (!st.empty()) {
+            expr x = st.back(); st.pop_back();
+            if (!x.is_defined()) continue;
+            if (x.get_expr_type() == e_var && x.get_name() == r) return false;          // r used as a value
+            if (x.get_expr_type() != e_op) continue;
+            if (x.get_op_type() == o_access) {
+                computation *oc = nullptr;
+                buffer *b = buffer_of_access(x, &oc);
+                if (!b) continue;
+                if (b == c->get_buffer()) return false;
+                if ((int) oc->get_iteration_variables().size() != x.get_n_arg() || oc->access().empty()) return false;
+                std::vector<std::string> names;
+                for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+                for (size_t q = 0; q < oc->access().size(); q++) {
+                    expr idx = oc->access()[q].substitute(names, x.get_operands());
+                    const bool last = q + 1 == oc->access().size();
+                    if (!mentions(idx, r)) continue;
+                    if (!last || !(idx.get_expr_type() == e_var && idx.get_name() == r)) return false;
+                    any = true;
+                }
+                continue;
+            }
+            for (const expr &o : x.get_operands()) st.push_back(o);
+        }
+        if (summands) summands->push_back(terms[t]);
+    }
+    return any;
+}
+
+void Lowering::emit_warp_reduction(Node *loop, std::ostringstream &os, int ind)
+{
+    Node *stmt = loop->kids.front().get();
+    computation *c = stmt->comp;
+    std::vector<expr> summands;
+    if (!warp_reduction_terms(c, loop->dim_name, &summands)) die("internal: warp reduction of '" + c->get_name() + "' no longer matches");
+    const std::string it = ctype(global::get_loop_iterator_data_type()), T = ctype(c->get_data_type());
+    Node *lane = nullptr;
+    for (Node *p : stmt->path) if (p->dim_name == "_lane_" + c->get_name()) lane = p;
+    if (!lane) die("internal: warp reduction of '" + c->get_name() + "' has no lane dimension");
+    os << pad(ind) << "{   // " << c->get_name() << ": one warp per element, '" << loop->dim_name << "' strided over the lanes, shuffle reduction\n";
+    os << pad(ind + 1) << T << " acc = (" << T << ") 0;\n";
+    os << pad(ind + 1) << "for (" << it << " " << loop->cname() << " = " << print(loop->lo, true) << " + " << lane->cname() << "; " << loop->cname() << " < "
+       << print(loop->hi, true) << "; " << loop->cname() << " += 32) {\n";
+    std::vector<std::string> conds;
+    emit_bindings(stmt, os, ind + 2, conds, true);
+    enter_stmt(c);
+    std::string cond;
+    for (size_t i = 0; i < conds.size(); i++) cond += (i ? " && " : "") + conds[i];
+    if (!cond.empty()) os << pad(ind + 2) << "if (" << cond << ") {\n";
+    for (const expr &t : summands) os << pad(ind + 2 + !cond.empty()) << "acc = acc + " << print(t, true) << ";\n";
+    if (!cond.empty()) os << pad(ind + 2) << "}\n";
+    os << pad(ind + 1) << "}\n";
+    os << pad(ind + 1) << "#pragma unroll\n" << pad(ind + 1) << "for (int off = 16; off > 0; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);\n";
+    // the store: bindings of the outer dimensions only (the reduction iterator is not part of the element's address)
+    os << pad(ind + 1) << "if (" << lane->cname() << " == 0) {\n";
+    os << pad(ind + 2) << "const " << it << " " << loop->cname() << " = " << print(loop->lo, true) << ";\n";
+    std::vector<std::string> conds2;
+    emit_bindings(stmt, os, ind + 2, conds2, true);
+    std::string cond2;
+    for (size_t i = 0; i < conds2.size(); i++) cond2 += (i ? " && " : "") + conds2[i];
+    buffer *b = c->get_buffer();
+    std::string lhs = "b_" + san(b->get_name()) + "[" + lin_index(b, c->access(), true) + "]";
+    os << pad(ind + 2) << (cond2.empty() ? "" : "if (" + cond2 + ") ") << lhs << " = (" << T << ") (" << lhs << " + acc);\n";
+    os << pad(ind + 1) << "}\n" << pad(ind) << "}\n";
+    enter_stmt(nullptr);
+}
+
 void Lowering::auto_map(computation *c, int shared_depth)
 {
     const expr &e = c->get_expr();
@@ -1089,6 +1199,29 @@ void Lowering::auto_map(computation *c, int shared_depth)
         dims.insert(dims.begin() + shared_depth, one);
     };
     if (dims.empty()) { one_thread(); return; }
+    // A statement that reads the buffer it writes at another element than its own (in-place updates such as
+    // reference tests/test_20.cpp: S1(i,j) = S0(i,j) + S0(9,9), all in buf0) carries a dependence between its
+    // iterations; without a dependence test the only safe mapping keeps its order: one thread.
+    if (c->has_access()) {
+        std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+        while (!stack.empty()) {
+            expr x = stack.back(); stack.pop_back();
+            if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+            if (x.get_op_type() == o_access) {
+                computation *oc = f_->find_computation(x.get_name());
+                if (oc && !oc->is_constant() && oc->get_buffer() == c->get_buffer()) {
+                    bool same = oc->access().size() == c->access().size() && (int) oc->get_iteration_variables().size() == x.get_n_arg();
+                    if (same) {
+                        std::vector<std::string> names;
+                        for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+                        for (size_t q = 0; q < c->access().size(); q++) same &= oc->access()[q].substitute(names, x.get_operands()).is_equal(c->access()[q]);
+                    }
+                    if (!same) { one_thread(); return; }
+                }
+            }
+            for (const expr &o : x.get_operands()) stack.push_back(o);
+        }
+    }
     // which original iterators index the stored element
     std::vector<std::string> stored;
     for (const var &v : c->get_iteration_variables()) {
@@ -1117,6 +1250,34 @@ void Lowering::auto_map(computation *c, int shared_depth)
     for (size_t i = shared_depth; i < dims.size(); i++) if (dims[i].tag == loop_dim::vector && parallel_safe(dims[i].name)) vec = (int) i;
     for (auto &d : dims) d.tag = loop_dim::none;
     if ((int) dims.size() == shared_depth) { one_thread(); return; }
+    // warp-shuffle reduction: the innermost loop is the only reduction and is unit stride in what it reads
+    if (pattern_ && is_float_type(c->get_data_type()) && (int) dims.size() >= shared_depth + 2) {
+        const loop_dim &rd = dims.back();
+        int n_red = 0, q = -1;
+        for (int i = shared_depth; i < (int) dims.size(); i++) if (!parallel_safe(dims[i].name)) n_red++;
+        for (int i = (int) dims.size() - 2; i >= shared_depth; i--) if (parallel_safe(dims[i].name)) { q = i; break; }
+        expr ext = rd.hi - rd.lo;
+        const bool long_enough = !ext.is_int_literal() || ext.get_int_val() >= 64;
+        const bool is_iter = std::any_of(c->get_iteration_variables().begin(), c->get_iteration_variables().end(), [&](const var &v) { return v.get_name() == rd.name; });
+        if (n_red == 1 && q >= 0 && !parallel_safe(rd.name) && is_iter && long_enough && c->guards().empty() && warp_reduction_terms(c, rd.name, nullptr)) {
+            const std::string inner = dims[q].name, red = rd.name;
+            c->split(var(inner), 8, var(inner + "_b"), var(inner + "_t"));          // 8 warps (outputs) per block
+            c->tag_gpu_block_level(var(inner + "_b"));
+            c->tag_gpu_thread_level(var(inner + "_t"));
+            loop_dim lane; lane.name = "_lane_" + c->get_name(); lane.lo = expr((int32_t) 0); lane.hi = expr((int32_t) 32); lane.tag = loop_dim::gpu_thread;
+            auto &dd = c->dims();
+            dd.insert(dd.end() - 1, lane);                                          // just outside the reduction loop: the innermost thread level (x)
+            dd.back().warp_reduce = true;
+            int extra = 0;
+            for (size_t i = shared_depth; i < dd.size() && extra < 2; i++) {
+                if (dd[i].tag != loop_dim::none || !parallel_safe(dd[i].name)) break;
+                dd[i].tag = loop_dim::gpu_block;
+                extra++;
+            }
+            (void) red;
+            return;
+        }
+    }
     std::string tx, ty, bx;
     if (vec >= shared_depth + 1 && parallel_safe(dims[vec - 1].name) && dims[vec].hi.is_int_literal() && dims[vec].hi.get_int_val() <= 64) {
         const int lanes = (int) dims[vec].hi.get_int_val();
