@@ -25,6 +25,8 @@ CASES = {
     "gemm_sym_generic": ("gemm_sym_gen.cpp", "gemm_sym_generic", "generic"),
     # CPU schedules (no gpu level, codegen without the gpu flag): re-targeted to sm_100a by the lowering
     "blur_f32_cpu_gen": ("blur_f32_cpu_gen.cpp", None, None),
+    "matvec_cpu_gen": ("matvec_cpu_gen.cpp", "matvec_cpu_gen", None),                      # warp-shuffle reduction
+    "matvec_cpu_generic": ("matvec_cpu_gen.cpp", "matvec_cpu_generic", "generic"),         # one row per thread, statement order
     "sgemm_cpu_sched_gen": ("sgemm_cpu_sched_gen.cpp", "sgemm_cpu_sched_gen", "generic"),   # three SIMT kernels, bit-exact
     "sgemm_cpu_sched_tc": ("sgemm_cpu_sched_gen.cpp", "sgemm_cpu_sched_tc", None),           # statement triple -> one tcgen05 GEMM
 }

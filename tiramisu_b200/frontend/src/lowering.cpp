@@ -153,8 +153,9 @@ private:
     void emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind);
     void emit_assignment(Node *n, std::ostringstream &os, int ind, bool device);
     void emit_bindings(Node *n, std::ostringstream &os, int ind, std::vector<std::string> &conds, bool device);
-    struct Contraction { buffer *C = nullptr, *A = nullptr, *B = nullptr; bool tA = false, tB = false; expr M, N, K; };
+    struct Contraction { buffer *C = nullptr, *A = nullptr, *B = nullptr; bool tA = false, tB = false; expr M, N, K, offA, offB, offC; };
     bool match_contraction(computation *c, Contraction &m);
+    bool match_contractions(computation *c, std::vector<Contraction> &out, std::vector<std::string> *outer);
     bool match_zero_fill(computation *z, buffer *C, const expr &M, const expr &N);
     void emit_sgemm_call(std::ostringstream &host, int ind, const Contraction &m, buffer *C, const std::string &alpha, const std::string &beta);
     bool try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind);
@@ -692,62 +693,126 @@ static std::vector<Node *> statements_of(Node *root)
     return stmts;
 }
 
-bool Lowering::match_contraction(computation *c, Contraction &m)
+// Generalised matcher.  The statement may have more iterators than (I, J, R): the others ("outer" iterators:
+// the time / layer loops around an LSTM cell) must not index rows or columns — they may only appear in the
+// leading indices of higher-dimensional buffers, where they select a 2-D slice (an element offset).  The sum may
+// hold several products: each becomes one GEMM call accumulating into the same element (beta = 1).
+bool Lowering::match_contractions(computation *c, std::vector<Contraction> &out, std::vector<std::string> *outer)
 {
-    if (c->get_data_type() != p_float32 || c->get_predicate().is_defined() || !c->get_expr().is_defined()) return false;
+    if (c->get_data_type() != p_float32 || c->get_predicate().is_defined() || !c->get_expr().is_defined() || !c->has_access()) return false;
     const auto &iters = c->get_iteration_variables();
-    if (iters.size() != 3) return false;
-    for (const var &v : iters) if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0)) return false;
+    if (iters.size() < 3) return false;
     auto is_var = [](const expr &x, const std::string &n) { return x.get_expr_type() == e_var && x.get_name() == n; };
-    // the stored element is addressed by two of the three iterators; the third is the reduction
+    auto mentions = [](const expr &x, const std::string &v) { return !x.substitute({v}, {expr((int32_t) 0)}).is_equal(x) || (x.get_expr_type() == e_var && x.get_name() == v); };
     buffer *C = c->get_buffer();
-    if (C->get_location() != mem_loc::gpu_global || C->get_n_dims() != 2 || c->access().size() != 2) return false;
-    if (c->access()[0].get_expr_type() != e_var || c->access()[1].get_expr_type() != e_var) return false;
-    const std::string I = c->access()[0].get_name(), J = c->access()[1].get_name();
-    std::string R;
-    for (const var &v : iters) {
-        if (v.get_name() == I) m.M = v.get_upper();
-        else if (v.get_name() == J) m.N = v.get_upper();
-        else { R = v.get_name(); m.K = v.get_upper(); }
+    const size_t nc = c->access().size();
+    if (C->get_location() != mem_loc::gpu_global || nc < 2 || (size_t) C->get_n_dims() != nc) return false;
+    if (c->access()[nc - 2].get_expr_type() != e_var || c->access()[nc - 1].get_expr_type() != e_var) return false;
+    const std::string I = c->access()[nc - 2].get_name(), J = c->access()[nc - 1].get_name();
+    if (I == J) return false;
+    // flatten the sum
+    std::vector<expr> terms, stack{c->get_expr()};
+    while (!stack.empty()) {
+        expr x = stack.back(); stack.pop_back();
+        if (x.get_expr_type() == e_op && x.get_op_type() == o_add) { stack.push_back(x.get_operand(1)); stack.push_back(x.get_operand(0)); }
+        else terms.push_back(x);
     }
-    if (I == J || R.empty() || !m.M.is_defined() || !m.N.is_defined() || !m.K.is_defined()) return false;
-    const expr &e = c->get_expr();
-    if (e.get_expr_type() != e_op || e.get_op_type() != o_add) return false;
-    expr self = e.get_operand(0), prod = e.get_operand(1);
-    if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) std::swap(self, prod);
-    if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) return false;
-    if (!(self.get_expr_type() == e_op && self.get_op_type() == o_access)) return false;
-    {   // the accumulator operand: this computation itself, or another computation stored at the same element
-        computation *sc = nullptr;
-        buffer *sb = buffer_of_access(self, &sc);
-        if (sb != C || sc->access().size() != 2 || (int) sc->get_iteration_variables().size() != self.get_n_arg()) return false;
-        std::vector<std::string> names;
-        for (const var &v : sc->get_iteration_variables()) names.push_back(v.get_name());
-        if (!is_var(sc->access()[0].substitute(names, self.get_operands()), I) || !is_var(sc->access()[1].substitute(names, self.get_operands()), J)) return false;
-    }
-    // operands: P(I,R) and Q(R,J) in either order, possibly stored transposed
-    struct Opnd { buffer *b = nullptr; bool trans = false; int role = -1; };   // role 0 = uses (I,R), 1 = uses (R,J)
-    auto classify = [&](const expr &x, Opnd &o) {
+    if (terms.size() < 2) return false;
+    // resolve an access to (buffer, index tuple in this statement's iterators)
+    auto resolve = [&](const expr &x, buffer *&b, std::vector<expr> &idx) {
         if (!(x.get_expr_type() == e_op && x.get_op_type() == o_access)) return false;
         computation *oc = nullptr;
-        buffer *b = buffer_of_access(x, &oc);
-        if (!b || b->get_location() != mem_loc::gpu_global || b->get_n_dims() != 2 || b->get_elements_type() != p_float32) return false;
-        if (oc->access().size() != 2 || (int) oc->get_iteration_variables().size() != x.get_n_arg()) return false;
+        b = buffer_of_access(x, &oc);
+        if (!b || (int) oc->get_iteration_variables().size() != x.get_n_arg() || oc->access().size() != (size_t) b->get_n_dims()) return false;
         std::vector<std::string> names;
         for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
-        expr r = oc->access()[0].substitute(names, x.get_operands()), s = oc->access()[1].substitute(names, x.get_operands());
-        o.b = b;
-        if (is_var(r, I) && is_var(s, R)) { o.role = 0; o.trans = false; return true; }
-        if (is_var(r, R) && is_var(s, I)) { o.role = 0; o.trans = true; return true; }
-        if (is_var(r, R) && is_var(s, J)) { o.role = 1; o.trans = false; return true; }
-        if (is_var(r, J) && is_var(s, R)) { o.role = 1; o.trans = true; return true; }
-        return false;
+        idx.clear();
+        for (const expr &a : oc->access()) idx.push_back(a.substitute(names, x.get_operands()));
+        return true;
     };
-    Opnd x, y;
-    if (!classify(prod.get_operand(0), x) || !classify(prod.get_operand(1), y) || x.role == y.role) return false;
-    const Opnd &a = x.role == 0 ? x : y, &b = x.role == 0 ? y : x;
-    if (a.b == C || b.b == C) return false;
-    m.C = C; m.A = a.b; m.B = b.b; m.tA = a.trans; m.tB = b.trans;
+    // the reduction iterator: the one (other than I, J) that indexes the last two dimensions of an operand
+    std::string R;
+    int self = -1;
+    for (size_t t = 0; t < terms.size(); t++) {
+        buffer *b; std::vector<expr> idx;
+        if (resolve(terms[t], b, idx) && b == C && idx.size() == nc) {
+            bool same = true;
+            for (size_t q = 0; q < nc; q++) same &= idx[q].is_equal(c->access()[q]);
+            if (same) { if (self >= 0) return false; self = (int) t; continue; }
+        }
+    }
+    if (self < 0) return false;
+    struct Opnd { buffer *b = nullptr; bool trans = false; int role = -1; expr off; };
+    auto lead_offset = [&](buffer *b, const std::vector<expr> &idx, expr &off) {
+        // element offset of the 2-D slice selected by the leading indices; they must not move with I, J or R
+        const auto &d = b->get_dim_sizes();
+        off = expr((int32_t) 0);
+        for (size_t q = 0; q + 2 < idx.size(); q++) {
+            if (mentions(idx[q], I) || mentions(idx[q], J) || (!R.empty() && mentions(idx[q], R))) return false;
+            off = off * cast(p_int64, d[q]) + cast(p_int64, idx[q]);
+        }
+        if (idx.size() > 2) off = off * cast(p_int64, d[idx.size() - 2]) * cast(p_int64, d[idx.size() - 1]);
+        return true;
+    };
+    for (size_t t = 0; t < terms.size(); t++) {
+        if ((int) t == self) continue;
+        const expr &prod = terms[t];
+        if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) return false;
+        Opnd o[2];
+        for (int side = 0; side < 2; side++) {
+            buffer *b; std::vector<expr> idx;
+            if (!resolve(prod.get_operand(side), b, idx) || b == C || idx.size() < 2) return false;
+            if (b->get_location() != mem_loc::gpu_global || b->get_elements_type() != p_float32) return false;
+            const expr &r = idx[idx.size() - 2], &s2 = idx[idx.size() - 1];
+            if (r.get_expr_type() != e_var || s2.get_expr_type() != e_var) return false;
+            // which of I / J it carries decides the role; the other variable is the reduction
+            auto other_is_R = [&](const std::string &cand) {
+                if (cand == I || cand == J) return false;
+                if (R.empty()) R = cand;
+                return R == cand;
+            };
+            o[side].b = b;
+            if (is_var(r, I) && other_is_R(s2.get_name())) { o[side].role = 0; o[side].trans = false; }
+            else if (is_var(s2, I) && other_is_R(r.get_name())) { o[side].role = 0; o[side].trans = true; }
+            else if (is_var(s2, J) && other_is_R(r.get_name())) { o[side].role = 1; o[side].trans = false; }
+            else if (is_var(r, J) && other_is_R(s2.get_name())) { o[side].role = 1; o[side].trans = true; }
+            else return false;
+            if (!lead_offset(b, idx, o[side].off)) return false;
+        }
+        if (o[0].role == o[1].role) return false;
+        const Opnd &a = o[0].role == 0 ? o[0] : o[1], &b = o[0].role == 0 ? o[1] : o[0];
+        Contraction m;
+        m.C = C; m.A = a.b; m.B = b.b; m.tA = a.trans; m.tB = b.trans; m.offA = a.off; m.offB = b.off;
+        out.push_back(m);
+    }
+    if (out.empty() || R.empty()) return false;
+    expr offC;
+    {
+        std::vector<expr> idx(c->access().begin(), c->access().end());
+        if (!lead_offset(C, idx, offC)) return false;
+    }
+    expr M, N, K;
+    std::vector<std::string> outer_names;
+    for (const var &v : iters) {
+        if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0) && (v.get_name() == I || v.get_name() == J || v.get_name() == R)) return false;
+        if (v.get_name() == I) M = v.get_upper();
+        else if (v.get_name() == J) N = v.get_upper();
+        else if (v.get_name() == R) K = v.get_upper();
+        else outer_names.push_back(v.get_name());
+    }
+    if (!M.is_defined() || !N.is_defined() || !K.is_defined()) return false;
+    if (!outer_names.empty() && !outer) return false;
+    if (outer) *outer = outer_names;
+    for (Contraction &m : out) { m.M = M; m.N = N; m.K = K; m.offC = offC; }
+    return true;
+}
+
+bool Lowering::match_contraction(computation *c, Contraction &m)
+{
+    std::vector<Contraction> all;
+    if (!match_contractions(c, all, nullptr) || all.size() != 1) return false;
+    if (c->get_iteration_variables().size() != 3 || all[0].C->get_n_dims() != 2 || all[0].A->get_n_dims() != 2 || all[0].B->get_n_dims() != 2) return false;
+    m = all[0];
     return true;
 }
 
@@ -767,10 +832,12 @@ bool Lowering::match_zero_fill(computation *z, buffer *C, const expr &M, const e
 
 void Lowering::emit_sgemm_call(std::ostringstream &host, int ind, const Contraction &m, buffer *C, const std::string &alpha, const std::string &beta)
 {
+    auto ld = [&](buffer *b) { return print(b->get_dim_sizes().back(), false); };
+    auto off = [&](const expr &o) { return o.is_defined() ? "(uint64_t) (" + print(o, false) + ")" : std::string("0"); };
     host << pad(ind) << "if (tiramisu_cublas_sgemm((float *) b_" << san(m.A->get_name()) << ", (float *) b_" << san(m.B->get_name()) << ", b_" << san(C->get_name())
          << ", (uint64_t) " << print(m.M, false) << ", (uint64_t) " << print(m.N, false) << ", (uint64_t) " << print(m.K, false)
-         << ", " << alpha << ", " << beta << ", (uint64_t) " << print(m.A->get_dim_sizes()[1], false) << ", (uint64_t) " << print(m.B->get_dim_sizes()[1], false)
-         << ", (uint64_t) " << print(C->get_dim_sizes()[1], false) << ", 0, 0, 0, " << (m.tA ? "true" : "false") << ", " << (m.tB ? "true" : "false") << ")) return 1;\n";
+         << ", " << alpha << ", " << beta << ", (uint64_t) " << ld(m.A) << ", (uint64_t) " << ld(m.B) << ", (uint64_t) " << ld(C)
+         << ", " << off(m.offA) << ", " << off(m.offB) << ", " << off(C == m.C ? m.offC : expr()) << ", " << (m.tA ? "true" : "false") << ", " << (m.tB ? "true" : "false") << ")) return 1;\n";
 }
 
 bool Lowering::try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind)
@@ -778,15 +845,27 @@ bool Lowering::try_gemm_pattern(Kernel &k, std::ostringstream &host, int ind)
     if (!pattern_) return false;
     std::vector<Node *> stmts = statements_of(k.root);
     if (stmts.empty() || stmts.size() > 2) return false;
-    for (Node *s : stmts) if (s->path.empty() || s->path[0] != k.root) return false;          // not inside a host loop
-    computation *c = stmts.back()->comp;
-    Contraction m;
-    if (!match_contraction(c, m)) return false;
+    Node *stmt = stmts.back();
+    computation *c = stmt->comp;
+    std::vector<Contraction> all;
+    std::vector<std::string> outer;
+    if (!match_contractions(c, all, &outer)) return false;
+    // outer iterators must be exactly the host loops around the kernel (in order), untouched by splits
+    size_t n_host = 0;
+    while (n_host < stmt->path.size() && stmt->path[n_host] != k.root) n_host++;
+    if (n_host == stmt->path.size() || n_host != outer.size()) return false;
+    for (size_t i = 0; i < n_host; i++)
+        if (c->dims()[i].name != outer[i]) return false;
+    for (Node *s : stmts) if (s->path.size() <= n_host || s->path[n_host] != k.root) return false;
     const bool zero_init = stmts.size() == 2;
-    if (zero_init && !match_zero_fill(stmts[0]->comp, m.C, m.M, m.N)) return false;
-    host << pad(ind) << "// pattern lowering: '" << c->get_name() << "' is a dense fp32 contraction"
+    if (zero_init && (n_host != 0 || all.size() != 1 || !match_zero_fill(stmts[0]->comp, all[0].C, all[0].M, all[0].N))) return false;
+    host << pad(ind) << "{   // pattern lowering: '" << c->get_name() << "' is " << (all.size() > 1 ? std::to_string(all.size()) + " dense fp32 contractions" : "a dense fp32 contraction")
          << (zero_init ? " (zero-init fused: beta = 0)" : "") << " -> tcgen05 GEMM of the runtime\n";
-    emit_sgemm_call(host, ind, m, m.C, "1.0f", zero_init ? "0.0f" : "1.0f");
+    const std::string it = ctype(global::get_loop_iterator_data_type());
+    for (size_t i = 0; i < n_host; i++)
+        host << pad(ind + 1) << "const " << it << " i_" << san(c->dims()[i].name) << " = " << stmt->path[i]->cname() << ";\n";
+    for (const Contraction &m : all) emit_sgemm_call(host, ind + 1, m, m.C, "1.0f", zero_init ? "0.0f" : "1.0f");
+    host << pad(ind) << "}\n";
     return true;
 }
 
