@@ -197,6 +197,8 @@ public:
     computation *succ() const { return succ_; }
     const std::string &pred_level() const { return pred_level_; }
     int pred_level_index() const { return pred_level_index_; }
+    /** Lowering: share loops 0..level_index with the predecessor in the order (nest fusion). */
+    void set_pred_level_index(int level_index) { pred_level_index_ = level_index; }
     bool is_input() const { return is_input_; }
     bool is_constant() const { return is_constant_; }
     int find_dim(const std::string &name) const;

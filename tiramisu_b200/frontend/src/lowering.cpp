@@ -118,6 +118,10 @@ private:
     void retarget(const std::vector<computation *> &ord);
     void mirror_buffers(const std::vector<computation *> &ord, bool gpu_only);
     void auto_map(computation *c, int shared_depth);
+    void fuse_pointwise_nests(const std::vector<computation *> &ord, const std::vector<int> &shared);
+    struct Access { buffer *b; std::vector<expr> idx; bool write; };
+    std::vector<Access> accesses_of(computation *c);
+    std::set<computation *> plainly_mapped_;      // statements auto_map gave the standard element-per-thread mapping
     bool warp_reduction_terms(computation *c, const std::string &r, std::vector<expr> *summands);
     void emit_warp_reduction(Node *loop, std::ostringstream &os, int ind);
     static int fuse_depth(computation *prev, computation *c);
@@ -1404,6 +1408,11 @@ void Lowering::auto_map(computation *c, int shared_depth)
         d.tag = loop_dim::gpu_block;
         extra++;
     }
+    // pointwise (no sequential loop left inside): a candidate for nest fusion
+    bool pointwise = true;
+    for (size_t i = shared_depth; i < c->dims().size(); i++)
+        pointwise &= c->dims()[i].tag == loop_dim::gpu_block || c->dims()[i].tag == loop_dim::gpu_thread || c->dims()[i].tag == loop_dim::unrolled;
+    if (pointwise) plainly_mapped_.insert(c);
 }
 
 // Host buffers touched by device statements move to the device: arguments get a mirror (b_X device,
@@ -1446,6 +1455,119 @@ void Lowering::mirror_buffers(const std::vector<computation *> &ord, bool gpu_on
     }
 }
 
+// ------------------------------------------------------------------------------------------------ nest fusion
+// Consecutive statements of a re-targeted CPU schedule that run over the same box, got the same mapping and only
+// exchange values element-wise (the nine pointwise statements of an LSTM cell, LSTM/cpu/generator.cpp:43-51) are
+// fused into ONE kernel: a launch per statement costs more than the statement.  Legality without a dependence
+// analysis: every two accesses to the same buffer inside the group (at least one of them a write) must either
+// use identical index expressions — same thread, program order — or differ by a non-zero constant in a
+// dimension that does not depend on the mapped iterators (c(m-1) read while c(m) is written: never the same
+// element inside one kernel instance).
+std::vector<Lowering::Access> Lowering::accesses_of(computation *c)
+{
+    std::vector<Access> out;
+    if (c->has_access()) out.push_back({c->get_buffer(), std::vector<expr>(c->access().begin(), c->access().end()), true});
+    std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+    while (!stack.empty()) {
+        expr x = stack.back(); stack.pop_back();
+        if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+        if (x.get_op_type() == o_access) {
+            computation *oc = f_->find_computation(x.get_name());
+            if (oc && !oc->is_constant() && (int) oc->get_iteration_variables().size() == x.get_n_arg()) {
+                std::vector<std::string> names;
+                for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+                Access a{oc->get_buffer(), {}, false};
+                for (const expr &i : oc->access()) a.idx.push_back(i.substitute(names, x.get_operands()));
+                out.push_back(a);
+            }
+        }
+        for (const expr &o : x.get_operands()) stack.push_back(o);
+    }
+    return out;
+}
+
+static bool affine_form(const expr &e, std::map<std::string, int64_t> &coef, int64_t &cst, int64_t scale = 1)
+{
+    if (!e.is_defined()) return false;
+    if (e.is_int_literal()) { cst += scale * e.get_int_val(); return true; }
+    if (e.get_expr_type() == e_var) { coef[e.get_name()] += scale; return true; }
+    if (e.get_expr_type() != e_op) return false;
+    switch (e.get_op_type()) {
+    case o_add: return affine_form(e.get_operand(0), coef, cst, scale) && affine_form(e.get_operand(1), coef, cst, scale);
+    case o_sub: return affine_form(e.get_operand(0), coef, cst, scale) && affine_form(e.get_operand(1), coef, cst, -scale);
+    case o_minus: return affine_form(e.get_operand(0), coef, cst, -scale);
+    case o_mul:
+        if (e.get_operand(0).is_int_literal()) return affine_form(e.get_operand(1), coef, cst, scale * e.get_operand(0).get_int_val());
+        if (e.get_operand(1).is_int_literal()) return affine_form(e.get_operand(0), coef, cst, scale * e.get_operand(1).get_int_val());
+        return false;
+    default: return false;
+    }
+}
+
+void Lowering::fuse_pointwise_nests(const std::vector<computation *> &ord, const std::vector<int> &shared)
+{
+    auto same_dims = [](computation *a, computation *b) {
+        if (a->dims().size() != b->dims().size()) return false;
+        for (size_t i = 0; i < a->dims().size(); i++) {
+            const loop_dim &x = a->dims()[i], &y = b->dims()[i];
+            if (x.name != y.name || x.tag != y.tag || !x.lo.is_equal(y.lo) || !x.hi.is_equal(y.hi) || x.warp_reduce || y.warp_reduce) return false;
+        }
+        if (a->guards().size() != b->guards().size() || a->defs().size() != b->defs().size()) return false;
+        for (size_t i = 0; i < a->guards().size(); i++) if (!a->guards()[i].is_equal(b->guards()[i])) return false;
+        for (size_t i = 0; i < a->defs().size(); i++) if (a->defs()[i].first != b->defs()[i].first || !a->defs()[i].second.is_equal(b->defs()[i].second)) return false;
+        return true;
+    };
+    std::vector<computation *> group;
+    std::vector<Access> group_acc;
+    for (size_t i = 0; i < ord.size(); i++) {
+        computation *c = ord[i];
+        const bool candidate = plainly_mapped_.count(c) && !c->get_predicate().is_defined();
+        bool joined = false;
+        if (candidate && !group.empty() && shared[i] == shared[i - 1] && same_dims(group.back(), c) &&
+            (shared[i] == 0 || fuse_depth(ord[i - 1], c) >= shared[i])) {
+            // mapped iterators = the original iterators rebuilt from the dimensions below the shared host loops
+            std::set<std::string> mapped;
+            for (size_t d = shared[i]; d < c->dims().size(); d++) mapped.insert(c->dims()[d].name);
+            for (auto &df : c->defs()) mapped.insert(df.first);
+            auto uses_mapped = [&](const expr &x) {
+                for (const std::string &m : mapped)
+                    if (!x.substitute({m}, {expr((int32_t) 0)}).is_equal(x) || (x.get_expr_type() == e_var && x.get_name() == m)) return true;
+                return false;
+            };
+            std::vector<Access> mine = accesses_of(c);
+            bool legal = true;
+            for (const Access &p : mine) {
+                for (const Access &q : group_acc) {
+                    if (p.b != q.b || (!p.write && !q.write)) continue;
+                    bool identical = p.idx.size() == q.idx.size();
+                    for (size_t k = 0; identical && k < p.idx.size(); k++) identical = p.idx[k].is_equal(q.idx[k]);
+                    if (identical) continue;
+                    bool disjoint = false;
+                    for (size_t k = 0; !disjoint && k < std::min(p.idx.size(), q.idx.size()); k++) {
+                        if (uses_mapped(p.idx[k]) || uses_mapped(q.idx[k])) continue;
+                        std::map<std::string, int64_t> coef; int64_t cst = 0;
+                        if (!affine_form(p.idx[k] - q.idx[k], coef, cst)) continue;
+                        bool vars = false;
+                        for (auto &kv : coef) vars |= kv.second != 0;
+                        disjoint = !vars && cst != 0;
+                    }
+                    if (!disjoint) legal = false;
+                }
+            }
+            if (legal) {
+                c->set_pred_level_index((int) c->dims().size() - 1);
+                group.push_back(c);
+                group_acc.insert(group_acc.end(), mine.begin(), mine.end());
+                joined = true;
+            }
+        }
+        if (!joined) {
+            group.clear(); group_acc.clear();
+            if (candidate) { group.push_back(c); group_acc = accesses_of(c); }
+        }
+    }
+}
+
 void Lowering::retarget(const std::vector<computation *> &ord)
 {
     retargeted_ = true;
@@ -1456,6 +1578,7 @@ void Lowering::retarget(const std::vector<computation *> &ord)
         shared[i] = std::max(with_prev, with_next);
     }
     for (size_t i = 0; i < ord.size(); i++) auto_map(ord[i], shared[i]);
+    if (pattern_) fuse_pointwise_nests(ord, shared);
     mirror_buffers(ord, false);
     // outputs whose first use is a statement that overwrites every element need no copy-in
     for (buffer *b : args_) {
