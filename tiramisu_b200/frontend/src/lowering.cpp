@@ -119,6 +119,8 @@ private:
     void mirror_buffers(const std::vector<computation *> &ord, bool gpu_only);
     void auto_map(computation *c, int shared_depth);
     void fuse_pointwise_nests(const std::vector<computation *> &ord, const std::vector<int> &shared);
+    void distribute_parallel_shared_loops(const std::vector<computation *> &ord);
+    bool dim_is_parallel(computation *c, const std::string &dim);
     struct Access { buffer *b; std::vector<expr> idx; bool write; };
     std::vector<Access> accesses_of(computation *c);
     std::set<computation *> plainly_mapped_;      // statements auto_map gave the standard element-per-thread mapping
@@ -1267,6 +1269,80 @@ void Lowering::emit_warp_reduction(Node *loop, std::ostringstream &os, int ind)
     enter_stmt(nullptr);
 }
 
+// A scheduled dimension is data-parallel iff every original iterator rebuilt from it indexes the stored element
+// (each iteration writes its own element); a dimension that feeds no original iterator is not.
+bool Lowering::dim_is_parallel(computation *c, const std::string &dim)
+{
+    if (!c->has_access() && !c->get_expr().is_defined()) return false;
+    c->get_buffer();
+    bool feeds_any = false;
+    for (const var &v : c->get_iteration_variables()) {
+        expr full = expr::make_var(p_int32, v.get_name());
+        for (auto &d : c->defs()) full = full.substitute({d.first}, {d.second});
+        const bool feeds = !full.substitute({dim}, {expr((int32_t) 7)}).is_equal(full);
+        if (!feeds) continue;
+        feeds_any = true;
+        bool stored = false;
+        for (const expr &a : c->access())
+            stored |= !a.substitute({v.get_name()}, {expr((int32_t) 0)}).is_equal(a) || (a.get_expr_type() == e_var && a.get_name() == v.get_name());
+        if (!stored) return false;
+    }
+    return feeds_any;
+}
+
+// Loop distribution for re-targeting.  A CPU schedule that fuses statements inside loops (`S1.after(S0, j)`) keeps
+// those loops as host loops around one kernel per statement — a launch per iteration.  When the innermost shared
+// loops are data parallel for every statement of the fused run and the statements only exchange values
+// element-wise (every two accesses to one buffer, one of them a write, use identical index expressions), running
+// S0 over the whole box and then S1 is equivalent: the shared loops are un-fused down to the outermost one that
+// must stay sequential, each statement is mapped over its full box, and nest fusion may join identical ones again
+// inside ONE kernel (reference tests/test_94.cpp, test_155.cpp).
+void Lowering::distribute_parallel_shared_loops(const std::vector<computation *> &ord)
+{
+    auto plain = [](computation *c) {
+        const expr &e = c->get_expr();
+        return e.is_defined() && e.get_expr_type() != e_sync &&
+               !(e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate || e.get_op_type() == o_free || e.get_op_type() == o_call));
+    };
+    size_t i = 0;
+    while (i < ord.size()) {
+        // a maximal run of consecutive statements that share at least one loop with their predecessor
+        size_t j = i + 1;
+        while (j < ord.size() && fuse_depth(ord[j - 1], ord[j]) > 0) j++;
+        if (j - i >= 2) {
+            bool ok = true;
+            for (size_t k = i; k < j; k++) ok &= plain(ord[k]) && !ord[k]->get_predicate().is_defined();
+            // how many leading loops the whole run shares
+            int common = INT32_MAX;
+            for (size_t k = i + 1; k < j; k++) common = std::min(common, fuse_depth(ord[k - 1], ord[k]));
+            // keep = the shared loops that must stay sequential: everything down to the innermost non-parallel one
+            int keep = 0;
+            if (ok) {
+                for (int d = 0; d < common; d++)
+                    for (size_t k = i; k < j; k++)
+                        if (!dim_is_parallel(ord[k], ord[k]->dims()[d].name)) keep = d + 1;
+                // element-wise exchange only
+                std::vector<Access> seen;
+                for (size_t k = i; k < j && ok; k++) {
+                    std::vector<Access> mine = accesses_of(ord[k]);
+                    for (const Access &p : mine)
+                        for (const Access &q : seen) {
+                            if (p.b != q.b || (!p.write && !q.write)) continue;
+                            bool identical = p.idx.size() == q.idx.size();
+                            for (size_t t = 0; identical && t < p.idx.size(); t++) identical = p.idx[t].is_equal(q.idx[t]);
+                            if (!identical) ok = false;
+                        }
+                    seen.insert(seen.end(), mine.begin(), mine.end());
+                }
+            }
+            if (ok && keep < common)
+                for (size_t k = i + 1; k < j; k++)
+                    if (fuse_depth(ord[k - 1], ord[k]) > keep) ord[k]->set_pred_level_index(keep - 1);
+        }
+        i = j;
+    }
+}
+
 void Lowering::auto_map(computation *c, int shared_depth)
 {
     const expr &e = c->get_expr();
@@ -1305,28 +1381,8 @@ void Lowering::auto_map(computation *c, int shared_depth)
             for (const expr &o : x.get_operands()) stack.push_back(o);
         }
     }
-    // which original iterators index the stored element
-    std::vector<std::string> stored;
-    for (const var &v : c->get_iteration_variables()) {
-        bool used = false;
-        for (const expr &a : c->access())
-            used |= !a.substitute({v.get_name()}, {expr((int32_t) 0)}).is_equal(a) || (a.get_expr_type() == e_var && a.get_name() == v.get_name());
-        if (used) stored.push_back(v.get_name());
-    }
     c->get_buffer();
-    auto parallel_safe = [&](const std::string &dim) {
-        // a scheduled dimension is data-parallel iff every original iterator rebuilt from it indexes the store
-        bool feeds_any = false;
-        for (const var &v : c->get_iteration_variables()) {
-            expr full = expr::make_var(p_int32, v.get_name());
-            for (auto &d : c->defs()) full = full.substitute({d.first}, {d.second});
-            bool feeds = !full.substitute({dim}, {expr((int32_t) 7)}).is_equal(full);
-            if (!feeds) continue;
-            feeds_any = true;
-            if (std::find(stored.begin(), stored.end(), v.get_name()) == stored.end()) return false;
-        }
-        return feeds_any;
-    };
+    auto parallel_safe = [&](const std::string &dim) { return dim_is_parallel(c, dim); };
     // loops shared with a neighbour in the order (fused nests: the time / layer loops of the LSTM) stay
     // sequential host loops around the kernels; only the statement's own loops are mapped
     int vec = -1;
@@ -1571,6 +1627,7 @@ void Lowering::fuse_pointwise_nests(const std::vector<computation *> &ord, const
 void Lowering::retarget(const std::vector<computation *> &ord)
 {
     retargeted_ = true;
+    if (pattern_) distribute_parallel_shared_loops(ord);
     std::vector<int> shared(ord.size(), 0);
     for (size_t i = 0; i < ord.size(); i++) {
         int with_prev = i ? fuse_depth(ord[i - 1], ord[i]) : 0;
