@@ -170,6 +170,7 @@ private:
 };
 
 std::string pad(int n) { return std::string((size_t) n * 4, ' '); }
+bool affine_form(const expr &e, std::map<std::string, int64_t> &coef, int64_t &cst, int64_t scale = 1);
 
 // ------------------------------------------------------------------------------------------------ order
 std::vector<computation *> Lowering::order()
@@ -1282,9 +1283,16 @@ bool Lowering::dim_is_parallel(computation *c, const std::string &dim)
         const bool feeds = !full.substitute({dim}, {expr((int32_t) 7)}).is_equal(full);
         if (!feeds) continue;
         feeds_any = true;
+        // ... and indexes it injectively: an index such as y/2 or i%4 sends several iterations to one element
+        // (the 2x2 max-pool of conv_relu_maxpool_generator_tiramisu.cpp:104 is a reduction over y and x)
         bool stored = false;
-        for (const expr &a : c->access())
-            stored |= !a.substitute({v.get_name()}, {expr((int32_t) 0)}).is_equal(a) || (a.get_expr_type() == e_var && a.get_name() == v.get_name());
+        for (const expr &a : c->access()) {
+            const bool uses = !a.substitute({v.get_name()}, {expr((int32_t) 0)}).is_equal(a) || (a.get_expr_type() == e_var && a.get_name() == v.get_name());
+            if (!uses) continue;
+            std::map<std::string, int64_t> coef; int64_t cst = 0;
+            if (!affine_form(a, coef, cst) || coef[v.get_name()] == 0) return false;
+            stored = true;
+        }
         if (!stored) return false;
     }
     return feeds_any;
@@ -1542,7 +1550,7 @@ std::vector<Lowering::Access> Lowering::accesses_of(computation *c)
     return out;
 }
 
-static bool affine_form(const expr &e, std::map<std::string, int64_t> &coef, int64_t &cst, int64_t scale = 1)
+bool affine_form(const expr &e, std::map<std::string, int64_t> &coef, int64_t &cst, int64_t scale)
 {
     if (!e.is_defined()) return false;
     if (e.is_int_literal()) { cst += scale * e.get_int_val(); return true; }
