@@ -168,6 +168,23 @@ def test_reference_feature_tests_build_through_the_frontend(frontend_lib):
     assert sum(v == "built" for v in status.values()) >= len(expected["pass"])
 
 
+@pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference")
+def test_conv_block_generator_is_refused_not_miscompiled(frontend_lib, tmp_path):
+    """benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/conv_relu_maxpool_generator_tiramisu.cpp compiles against
+    the front-end (view, split/interchange/vectorize, fused register buffer) but its schedule fuses four statements
+    inside loops that carry the 2x2 max-pool reduction: re-targeted, that is millions of launches — the lowering
+    stops with a message.  The block stays a hand-registered entry point (conv.cu)."""
+    d = "benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense"
+    exe = str(tmp_path / "gen")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    inc = os.path.join(ROOT, "tiramisu_b200/frontend/include")
+    subprocess.check_call(["g++", "-std=c++17", "-O0", "-w", "-I", inc, "-I", os.path.join(inc, "compat"), "-I", os.path.join(bg.REF, d),
+                           os.path.join(bg.REF, d, "conv_relu_maxpool_generator_tiramisu.cpp"), "-o", exe,
+                           f"-L{os.path.dirname(frontend_lib)}", "-ltiramisu_b200_frontend", f"-Wl,-rpath,{os.path.dirname(frontend_lib)}"], env=env)
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=tmp_path, env=env)
+    assert r.returncode != 0 and "times per call" in r.stderr, r.stderr[-600:]
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _run(name, args=(), cwd=None, timeout=900):
     exe = os.path.join(bg.BIN, "gen_" + name)

@@ -170,6 +170,11 @@ public:
     void after(computation &before_this, int level);
     void before(computation &after_this, var level = root);
     void between(computation &before_c, var before_l, computation &after_c, var after_l);
+    /** Fuse with \p comp in the same loops down to \p level and run after it (reference core.h: fuse_after). */
+    void fuse_after(var level, computation &comp) { after(comp, level); }
+    /** Allocation scope of the computation's buffer.  Temporaries are allocated once per call here
+      * (pooled), which is what any scope is equivalent to functionally: recorded as a no-op. */
+    void store_at(computation &, var) {}
 
     /** Performance hint in the reference (stage \p inp through shared memory below \p level);
       * the sm_100a lowering picks its own staging, so this only records the hint. */
@@ -240,6 +245,13 @@ public:
     input(std::string name, std::vector<var> iterator_variables, primitive_t t);
     input(std::vector<var> iterator_variables, primitive_t t);
     input(std::string name, std::vector<std::string> dimension_names, std::vector<expr> dimension_sizes, primitive_t t);
+};
+
+/** A named window onto a buffer: declared like an input, mapped with store_in (reference core.h:5159). */
+class view : public input {
+public:
+    view(std::string name, std::vector<var> iterator_variables, primitive_t t) : input(name, iterator_variables, t) {}
+    view(std::string name, std::vector<var> iterator_variables, buffer *b) : input(name, iterator_variables, b->get_elements_type()) { store_in(b); }
 };
 
 class Input : public input {

@@ -955,6 +955,20 @@ void Lowering::emit_kernel(Node *n, std::ostringstream &host, int ind, std::vect
     Kernel k;
     k.root = n;
     k.host_loops = host_loops;
+    {   // a kernel inside host loops is launched once per iteration: refuse programs where that is millions of
+        // launches (a CPU schedule whose fused loops had to stay sequential) instead of emitting code that runs for hours
+        double launches = 1;
+        for (Node *l : host_loops) {
+            expr ext = l->hi - l->lo;
+            if (ext.is_int_literal()) launches *= (double) std::max<int64_t>(1, ext.get_int_val());
+        }
+        if (launches > 2e6) {
+            Node *first_stmt = n;
+            while (first_stmt->is_loop && !first_stmt->kids.empty()) first_stmt = first_stmt->kids.front().get();
+            die("'" + (first_stmt->comp ? first_stmt->comp->get_name() : n->dim_name) + "' would be launched " + std::to_string((long long) launches) +
+                " times per call: the schedule fuses it inside loops that carry dependences between its statements, which this back end keeps as host loops");
+        }
+    }
     collect_kernel(n, k, false);
     // first statement's name labels the kernel (ncu-friendly)
     Node *first = n;
