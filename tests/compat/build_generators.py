@@ -50,6 +50,10 @@ TARGETS = {
     "lstm_gpu": ("benchmarks/DNN/blocks/LSTM/gpu/generator.cpp", "lstm.o", None, ["benchmarks/DNN/blocks/LSTM/gpu"], []),
     # the same generator with PATCHES["lstm_gpu_fixed"] applied to a scratch copy (see there)
     "lstm_gpu_fixed": ("benchmarks/DNN/blocks/LSTM/gpu/generator.cpp", "lstm.o", None, ["benchmarks/DNN/blocks/LSTM/gpu"], []),
+    # the conv + ReLU + max-pool block (row a9): CPU schedule with fused register buffer; recognised as an idiom from
+    # Layers I/III and lowered to the runtime's fused kernel (with the pattern lowering off the generator is refused)
+    "conv_block": ("benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/conv_relu_maxpool_generator_tiramisu.cpp", "conv_relu_maxpool_tiramisu.o",
+                   "benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/wrapper_nn_block.cpp", ["benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense"], []),
     # BASELINE configs[1]'s own generator: old-style ISL-string API, CPU schedule (parallel y, vectorize x by 8)
     "heat2d": ("benchmarks/halide/heat2d_tiramisu.cpp", "build/generated_fct_heat2d.o", "benchmarks/halide/wrapper_heat2d.cpp",
                ["benchmarks/halide"], []),

@@ -126,6 +126,9 @@ def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     failed = {k: v[1] for k, v in res.items() if v[0] != 0}
     assert not failed, failed
     assert len(res) == len(bg.TARGETS) + 6          # + the generic-lowering variants
+    cb = open(os.path.join(bg.GEN, "conv_block", "conv_relu_maxpool_tiramisu.o.b200.cu")).read()
+    assert "tiramisu_b200_conv_relu_maxpool(b__c_input_buffer, b__conv_filter_buffer, b__conv_bias_buffer, b_output_buf, 32, 224, 3, 32)" in cb
+    assert "__global__" not in cb
     # chain_mm/gpu/generator.cpp: two fused (zero-init + reduction) kernels -> two runtime GEMM calls, beta = 0
     cm = open(os.path.join(bg.GEN, "chain_mm", "fct.o.b200.cu")).read()
     assert cm.count("if (tiramisu_cublas_sgemm(") == 2 and "__global__" not in cm and cm.count("1.0f, 0.0f,") == 2
@@ -309,6 +312,24 @@ def test_reference_lstm_gpu_generator(fblt):
     _call(lib, "lstm", np.array([F, B, L, T], np.int32), Wt, bias, x, y)
     want = oracle.lstm(Wt, bias, x)
     assert np.abs(y - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), np.abs(y - want).max()
+
+
+@pytest.mark.gpu
+def test_reference_conv_block_generator(tmp_path):
+    """conv_relu_maxpool_generator_tiramisu.cpp (row a9; repo configuration B=32, N=224, FIn=3, FOut=32) compiled
+    unmodified, recognised as the conv + ReLU + max-pool idiom and lowered to the runtime's fused kernel;
+    wrapper_nn_block.cpp (srand(1) inputs, 101 runs) compares its output with mkl_result.txt at 1e-4 per element —
+    the file is produced here by the oracle on the same inputs, as the MKL program cannot run."""
+    from oracle import oracle
+    from tests import refdata
+    inp, filt, bias = refdata.conv_inputs(32, 224, 3, 32)
+    want = oracle.conv_relu_maxpool(inp, filt, bias)                   # [B][FOut/8][N/2][N/2][8]
+    # the wrapper reads n, fout, y, x with fout = 8*fb + ff
+    flat = np.ascontiguousarray(want.transpose(0, 1, 4, 2, 3)).reshape(-1)
+    np.savetxt(tmp_path / "mkl_result.txt", flat, fmt="%.10g")
+    out = _run("conv_block", cwd=tmp_path, timeout=1200)
+    pct = [ln for ln in out.splitlines() if "Percentage of correctness" in ln]
+    assert pct and float(pct[0].split()[-1].rstrip("%")) >= 99.99, out[-1500:]
 
 
 def _load(name):

@@ -128,6 +128,7 @@ private:
     void emit_warp_reduction(Node *loop, std::ostringstream &os, int ind);
     static int fuse_depth(computation *prev, computation *c);
     bool try_heat2d_pattern(Node *zero, Node *heat, std::ostringstream &host, int ind);
+    bool try_conv_block_idiom(const std::vector<computation *> &ord, std::ostringstream &host);
     // index simplification context of the statement being emitted
     using Env = std::map<std::string, std::pair<int64_t, int64_t>>;   // loop dimension -> inclusive [lo, hi]
     const computation *cur_ = nullptr;
@@ -1813,6 +1814,151 @@ bool Lowering::try_heat2d_pattern(Node *zero, Node *heat, std::ostringstream &ho
          << "), (int32_t) (" << print(W, false) << "), " << form << ", 0, (int32_t) (" << print(H, false) << "))) return 1;\n";
     return true;
 }
+// ------------------------------------------------------------------------------------------------ conv block idiom
+// The whole conv + ReLU + max-pool block of benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/
+// conv_relu_maxpool_generator_tiramisu.cpp:28-49, recognised from Layers I and III only (what is computed and where
+// it is stored; the CPU schedule of Layer II only orders it):
+//     Z: OUT[n][fb][yo][xo][ff] = 0                                    over the whole output
+//     I: R[..] = BIAS[fb][ff]
+//     C: R[..] = R[..] + IN[n][y+ky][x+kx][fin] * W[fb][ky][kx][fin][ff]      (ky, kx in [0,3), fin in [0,FIn))
+//     P: OUT[n][fb][y/2][x/2][ff] = max(OUT[same element], R[..])
+// plus dead statements (the weight "prefetch" copy).  That is the runtime's fused implicit-GEMM conv kernel
+// (conv.cu: tcgen05 when the shape allows, the exact SIMT kernel otherwise), so the function body becomes one call.
+bool Lowering::try_conv_block_idiom(const std::vector<computation *> &ord, std::ostringstream &host)
+{
+    if (!pattern_) return false;
+    auto is_var = [](const expr &x) { return x.get_expr_type() == e_var; };
+    auto resolve = [&](const expr &x, buffer *&b, std::vector<expr> &idx) {
+        if (!(x.get_expr_type() == e_op && x.get_op_type() == o_access)) return false;
+        computation *oc = nullptr;
+        b = buffer_of_access(x, &oc);
+        if (!b || (int) oc->get_iteration_variables().size() != x.get_n_arg() || oc->access().size() != (size_t) b->get_n_dims()) return false;
+        std::vector<std::string> names;
+        for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+        idx.clear();
+        for (const expr &a : oc->access()) idx.push_back(a.substitute(names, x.get_operands()));
+        return true;
+    };
+    auto same = [](const std::vector<expr> &a, const std::vector<expr> &b) {
+        if (a.size() != b.size()) return false;
+        for (size_t i = 0; i < a.size(); i++) if (!a[i].is_equal(b[i])) return false;
+        return true;
+    };
+    auto lit = [](const expr &e, int64_t &v) { if (!e.is_int_literal()) return false; v = e.get_int_val(); return true; };
+    auto range_is = [&](computation *c, const std::string &name, int64_t hi) {
+        for (const var &v : c->get_iteration_variables())
+            if (v.get_name() == name) { int64_t l, h; return lit(v.get_lower(), l) && lit(v.get_upper(), h) && l == 0 && h == hi; }
+        return false;
+    };
+    // P: the only max statement
+    computation *P = nullptr, *C = nullptr, *I = nullptr, *Z = nullptr;
+    for (computation *c : ord)
+        if (c->get_expr().get_expr_type() == e_op && c->get_expr().get_op_type() == o_max && c->get_data_type() == p_float32) { if (P) return false; P = c; }
+    if (!P || !P->has_access()) return false;
+    buffer *OUT = P->get_buffer(), *R = nullptr, *IN = nullptr, *W = nullptr, *BIAS = nullptr;
+    if (OUT->get_n_dims() != 5 || P->access().size() != 5) return false;
+    std::string n, fb, y, x, ff;
+    {
+        const auto &a = P->access();
+        auto half = [&](const expr &e, std::string &v) {
+            if (!(e.get_expr_type() == e_op && e.get_op_type() == o_div && is_var(e.get_operand(0)) && e.get_operand(1).is_int_literal() && e.get_operand(1).get_int_val() == 2)) return false;
+            v = e.get_operand(0).get_name();
+            return true;
+        };
+        if (!is_var(a[0]) || !is_var(a[1]) || !half(a[2], y) || !half(a[3], x) || !is_var(a[4])) return false;
+        n = a[0].get_name(); fb = a[1].get_name(); ff = a[4].get_name();
+        buffer *b0, *b1; std::vector<expr> i0, i1;
+        if (!resolve(P->get_expr().get_operand(0), b0, i0) || !resolve(P->get_expr().get_operand(1), b1, i1)) return false;
+        if (b0 != OUT) { std::swap(b0, b1); std::swap(i0, i1); }
+        if (b0 != OUT || b1 == OUT || !same(i0, std::vector<expr>(a.begin(), a.end()))) return false;
+        R = b1;
+    }
+    std::vector<expr> r_idx_P;
+    { buffer *b; std::vector<expr> i0; const expr &e = P->get_expr();
+      if (resolve(e.get_operand(0), b, i0) && b == R) r_idx_P = i0; else if (resolve(e.get_operand(1), b, i0) && b == R) r_idx_P = i0; else return false; }
+    // C, I, Z and the dead rest
+    std::string ky, kx, fin;
+    for (computation *c : ord) {
+        if (c == P || !c->has_access()) { if (c != P) return false; continue; }
+        buffer *b = c->get_buffer();
+        const expr &e = c->get_expr();
+        if (b == R && e.get_expr_type() == e_op && e.get_op_type() == o_add) {
+            if (C) return false;
+            // self + IN * W
+            expr self = e.get_operand(0), prod = e.get_operand(1);
+            if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) std::swap(self, prod);
+            if (!(prod.get_expr_type() == e_op && prod.get_op_type() == o_mul)) return false;
+            buffer *sb; std::vector<expr> si;
+            if (!resolve(self, sb, si) || sb != R || !same(si, std::vector<expr>(c->access().begin(), c->access().end()))) return false;
+            buffer *b0, *b1; std::vector<expr> i0, i1;
+            if (!resolve(prod.get_operand(0), b0, i0) || !resolve(prod.get_operand(1), b1, i1)) return false;
+            if (i0.size() == 5) { std::swap(b0, b1); std::swap(i0, i1); }
+            if (i0.size() != 4 || i1.size() != 5) return false;
+            for (const expr &q : i1) if (!is_var(q)) return false;
+            if (i1[0].get_name() != fb || i1[4].get_name() != ff) return false;
+            ky = i1[1].get_name(); kx = i1[2].get_name(); fin = i1[3].get_name();
+            auto sum_of = [&](const expr &q, const std::string &a, const std::string &bb) {
+                return q.get_expr_type() == e_op && q.get_op_type() == o_add && is_var(q.get_operand(0)) && is_var(q.get_operand(1)) &&
+                       ((q.get_operand(0).get_name() == a && q.get_operand(1).get_name() == bb) || (q.get_operand(0).get_name() == bb && q.get_operand(1).get_name() == a));
+            };
+            if (!is_var(i0[0]) || i0[0].get_name() != n || !sum_of(i0[1], y, ky) || !sum_of(i0[2], x, kx) || !is_var(i0[3]) || i0[3].get_name() != fin) return false;
+            if (!same(std::vector<expr>(c->access().begin(), c->access().end()), r_idx_P)) return false;
+            IN = b0; W = b1; C = c;
+        } else if (b == R) {
+            if (I) return false;
+            buffer *bb; std::vector<expr> bi;
+            if (!resolve(e, bb, bi) || bi.size() != 2 || !is_var(bi[0]) || !is_var(bi[1]) || bi[0].get_name() != fb || bi[1].get_name() != ff) return false;
+            if (!same(std::vector<expr>(c->access().begin(), c->access().end()), r_idx_P)) return false;
+            BIAS = bb; I = c;
+        } else if (b == OUT) {
+            if (Z || !(e.is_literal() && e.get_double_val() == 0.0) || c->get_iteration_variables().size() != 5) return false;
+            for (int q = 0; q < 5; q++) {
+                const var &v = c->get_iteration_variables()[q];
+                if (!(c->access()[q].get_expr_type() == e_var && c->access()[q].get_name() == v.get_name())) return false;
+                if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0) || !v.get_upper().is_equal(OUT->get_dim_sizes()[q])) return false;
+            }
+            Z = c;
+        }
+    }
+    if (!C || !I || !Z || !IN || !W || !BIAS) return false;
+    if (IN == OUT || W == OUT || BIAS == OUT || IN->get_n_dims() != 4 || W->get_n_dims() != 5 || BIAS->get_n_dims() != 2) return false;
+    // program order: Z and I before C before P
+    auto pos = [&](computation *c) { return std::find(ord.begin(), ord.end(), c) - ord.begin(); };
+    if (!(pos(Z) < pos(C) && pos(I) < pos(C) && pos(C) < pos(P))) return false;
+    // everything else is dead: writes a buffer nobody reads and none of the five above
+    std::set<buffer *> core{OUT, R, IN, W, BIAS};
+    for (computation *c : ord) {
+        if (c == P || c == C || c == I || c == Z) continue;
+        buffer *b = c->get_buffer();
+        if (core.count(b)) return false;
+        for (computation *d : ord)
+            for (const Access &a : accesses_of(d)) if (!a.write && a.b == b) return false;
+    }
+    // shapes: all literal, consistent with the runtime entry point
+    int64_t B, FOB, HO, WO, F8, Bi, Hp, Wp, FIn, w0, w1, w2, w3, w4, bb0, bb1;
+    const auto &od = OUT->get_dim_sizes(); const auto &id = IN->get_dim_sizes(); const auto &wd = W->get_dim_sizes(); const auto &bd = BIAS->get_dim_sizes();
+    if (!lit(od[0], B) || !lit(od[1], FOB) || !lit(od[2], HO) || !lit(od[3], WO) || !lit(od[4], F8) || !lit(id[0], Bi) || !lit(id[1], Hp) || !lit(id[2], Wp) || !lit(id[3], FIn) ||
+        !lit(wd[0], w0) || !lit(wd[1], w1) || !lit(wd[2], w2) || !lit(wd[3], w3) || !lit(wd[4], w4) || !lit(bd[0], bb0) || !lit(bd[1], bb1)) return false;
+    const int64_t N = 2 * HO;
+    if (F8 != 8 || HO != WO || Bi != B || Hp != N + 2 || Wp != N + 2 || w0 != FOB || w1 != 3 || w2 != 3 || w3 != FIn || w4 != 8 || bb0 != FOB || bb1 != 8) return false;
+    if (!range_is(C, n, B) || !range_is(C, fb, FOB) || !range_is(C, y, N) || !range_is(C, x, N) || !range_is(C, ky, 3) || !range_is(C, kx, 3) || !range_is(C, fin, FIn) || !range_is(C, ff, 8)) return false;
+    if (!range_is(P, n, B) || !range_is(P, fb, FOB) || !range_is(P, y, N) || !range_is(P, x, N) || !range_is(P, ff, 8)) return false;
+    if (!range_is(I, n, B) || !range_is(I, fb, FOB) || !range_is(I, y, N) || !range_is(I, x, N) || !range_is(I, ff, 8)) return false;
+    for (computation *c : {C, P, I, Z}) if (c->get_predicate().is_defined()) return false;
+    for (buffer *b : {IN, W, BIAS, OUT}) if (b->get_elements_type() != p_float32 || b->get_location() != mem_loc::host) return false;
+    std::set<buffer *> is_arg(args_.begin(), args_.end());
+    for (buffer *b : {IN, W, BIAS, OUT}) if (!is_arg.count(b)) return false;
+    // the four tensors live on the device for the call; OUT is written completely
+    retargeted_ = true;
+    for (buffer *b : {IN, W, BIAS, OUT}) { b->tag_gpu_global(); mirrored_.insert(b); }
+    no_copy_in_.insert(OUT);
+    written_args_.insert(OUT);
+    host << pad(1) << "// idiom lowering: zero-init + bias + 3x3 convolution + max(out, .) over 2x2 windows = the conv + ReLU + max-pool block\n"
+         << pad(1) << "// ('" << Z->get_name() << "', '" << I->get_name() << "', '" << C->get_name() << "', '" << P->get_name() << "') -> the runtime's fused implicit-GEMM kernel\n"
+         << pad(1) << "if (tiramisu_b200_conv_relu_maxpool(b_" << san(IN->get_name()) << ", b_" << san(W->get_name()) << ", b_" << san(BIAS->get_name()) << ", b_" << san(OUT->get_name())
+         << ", " << B << ", " << N << ", " << FIn << ", " << FOB * 8 << ")) return 1;\n";
+    return true;
+}
 
 // ------------------------------------------------------------------------------------------------ driver
 std::string Lowering::run()
@@ -1831,17 +1977,22 @@ std::string Lowering::run()
     bool any_gpu = false;
     for (computation *c : ord)
         for (auto &d : c->dims()) any_gpu |= d.tag == loop_dim::gpu_block || d.tag == loop_dim::gpu_thread;
-    if (!cuda_ && !any_gpu) {
+    std::ostringstream idiom_body;
+    const bool whole_function_idiom = !cuda_ && !any_gpu && try_conv_block_idiom(ord, idiom_body);
+    if (whole_function_idiom) {
+        std::cerr << "tiramisu_b200 lowering: '" << f_->get_name() << "' is the conv + ReLU + max-pool block: lowered to the runtime's fused kernel\n";
+    } else if (!cuda_ && !any_gpu) {
         std::cerr << "tiramisu_b200 lowering: '" << f_->get_name() << "' is a CPU schedule; there is no CPU code generator: "
                      "re-targeting its loop nests to sm_100a (parallel -> blocks, vector -> threads, device mirrors for host buffers)\n";
         retarget(ord);
     } else if (any_gpu) {
         mirror_buffers(ord, true);          // gpu-tagged statements over plain host buffers (no memcpy computations)
     }
-    build_tree(ord);
+    if (!whole_function_idiom) build_tree(ord);
     assign_axes(&root_);
 
     std::ostringstream body;
+    body << idiom_body.str();
     std::vector<Node *> host_loops;
     for (size_t i = 0; i < root_.kids.size(); i++) {
         Node *k = root_.kids[i].get();
@@ -1875,6 +2026,7 @@ std::string Lowering::run()
         << "int tiramisu_cuda_memcpy_to_device_async(void *, const void *, uint64_t);\n"
         << "int tiramisu_b200_heat2d(const float *, float *, int32_t, int32_t, int32_t, int32_t, int32_t);\n"
         << "int tiramisu_b200_heat2d_buffers(halide_buffer_t *, halide_buffer_t *, int32_t, int32_t, int32_t);\n"
+        << "int tiramisu_b200_conv_relu_maxpool(const float *, const float *, const float *, float *, int32_t, int32_t, int32_t, int32_t);\n"
         << "int tiramisu_cublas_sgemm(float *, float *, float *, uint64_t, uint64_t, uint64_t, float, float, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, bool, bool);\n"
         << "int tiramisu_cublas_dgemm(double *, double *, double *, uint64_t, uint64_t, uint64_t, double, double, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, bool, bool);\n"
         << "}\n"
