@@ -172,11 +172,12 @@ def test_reference_feature_tests_build_through_the_frontend(frontend_lib):
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference")
-def test_conv_block_generator_is_refused_not_miscompiled(frontend_lib, tmp_path):
+def test_conv_block_generator_idiom_or_refusal(frontend_lib, tmp_path):
     """benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/conv_relu_maxpool_generator_tiramisu.cpp compiles against
-    the front-end (view, split/interchange/vectorize, fused register buffer) but its schedule fuses four statements
-    inside loops that carry the 2x2 max-pool reduction: re-targeted, that is millions of launches — the lowering
-    stops with a message.  The block stays a hand-registered entry point (conv.cu)."""
+    the front-end (view, split/interchange/vectorize, fused register buffer).  Default lowering: the whole function
+    is recognised as the conv + ReLU + max-pool idiom (one runtime call).  With the pattern lowerings off the
+    schedule would have to be re-targeted as written — four statements fused inside the loops of the 2x2 max-pool
+    reduction, millions of launches — and the lowering stops with a message instead."""
     d = "benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense"
     exe = str(tmp_path / "gen")
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
@@ -184,8 +185,11 @@ def test_conv_block_generator_is_refused_not_miscompiled(frontend_lib, tmp_path)
     subprocess.check_call(["g++", "-std=c++17", "-O0", "-w", "-I", inc, "-I", os.path.join(inc, "compat"), "-I", os.path.join(bg.REF, d),
                            os.path.join(bg.REF, d, "conv_relu_maxpool_generator_tiramisu.cpp"), "-o", exe,
                            f"-L{os.path.dirname(frontend_lib)}", "-ltiramisu_b200_frontend", f"-Wl,-rpath,{os.path.dirname(frontend_lib)}"], env=env)
-    r = subprocess.run([exe], capture_output=True, text=True, cwd=tmp_path, env=env)
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=tmp_path, env=dict(env, TIRAMISU_B200_LOWERING="generic"))
     assert r.returncode != 0 and "times per call" in r.stderr, r.stderr[-600:]
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=tmp_path, env=env)
+    assert r.returncode == 0 and "lowered to the runtime's fused kernel" in r.stderr, r.stderr[-600:]
+    assert "tiramisu_b200_conv_relu_maxpool(" in open(tmp_path / "conv_relu_maxpool_tiramisu.o.b200.cu").read()
 
 
 # ------------------------------------------------------------------------------------------------ GPU
