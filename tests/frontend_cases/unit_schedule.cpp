@@ -83,6 +83,28 @@ int main()
     computation *al = tmp.allocate_at(body, t);
     CHECK(al->dims().size() == 1 && al->dims()[0].name == "t" && !tmp.get_auto_allocate());
 
+    // old-style declarations: ISL box strings
+    {
+        tiramisu::function f("isl_unit");
+        constant N("N", expr((int32_t) 10), p_int32, true, nullptr, 0, &f);
+        computation S("[N]->{S[i,j]: 0<=i<N and 2<=j<=(N + -1)}", expr((uint8_t) 1), true, p_uint8, &f);
+        CHECK(names(S) == "i,j");
+        CHECK(S.dims()[0].lo.is_int_literal() && S.dims()[0].lo.get_int_val() == 0);
+        CHECK(S.dims()[0].hi.get_expr_type() == e_var && S.dims()[0].hi.get_name() == "N");
+        CHECK(S.dims()[1].lo.get_int_val() == 2);
+        CHECK(S.dims()[1].hi.get_expr_type() == e_var && S.dims()[1].hi.get_name() == "N");     // (N + -1) + 1 folds back to N
+        computation T("{T[i,0,k]: (0 <= i <= 7) and (1 <= k < 4)}", expr((uint8_t) 2), true, p_uint8, &f);
+        CHECK(T.dims().size() == 3 && T.dims()[1].lo.get_int_val() == 0 && T.dims()[1].hi.get_int_val() == 1);   // pinned dimension
+        CHECK(T.dims()[0].hi.get_int_val() == 8 && T.dims()[2].lo.get_int_val() == 1 && T.dims()[2].hi.get_int_val() == 4);
+        computation In("[N]->{In[a,b]}", expr(), false, p_uint8, &f);                                // a declaration only
+        CHECK(In.is_input());
+        buffer buf("buf", {expr(10), expr(12)}, p_uint8, a_output, &f);
+        S.set_access("[N]->{S[a,b]->buf[a + 1, min(b, 9)]}");                                         // positional aliases, clamp
+        CHECK(S.access().size() == 2 && S.get_buffer() == &buf);
+        CHECK(S.access()[0].get_op_type() == o_add && S.access()[0].get_operand(0).get_name() == "i");
+        CHECK(S.access()[1].get_op_type() == o_min && S.access()[1].get_operand(0).get_name() == "j");
+    }
+
     if (failures) return 1;
     std::printf("unit_schedule ok\n");
     return 0;
