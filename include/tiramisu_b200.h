@@ -45,7 +45,7 @@ void tiramisu_b200_set_stream(void *cuda_stream);
 void *tiramisu_b200_get_stream(void);
 /* Number of kernels this library has launched since load (all threads). */
 uint64_t tiramisu_b200_kernel_launches(void);
-/* Called by code the sm_100a lowering generates (tiramisu_b200/frontend/src/lowering.cpp) right after
+/* Called by code the sm_100a lowering generates (tiramisu_b200/frontend/src/lowering_emit.cpp) right after
  * each `<<<>>>` launch: counts the launch and reports a launch error like the reference's kernel
  * wrappers do (src/tiramisu_codegen_cuda.cpp:855-866).  Returns 0 on success. */
 int tiramisu_b200_post_launch(const char *kernel_name);

@@ -1,6 +1,6 @@
 // y = A x + y0 with a CPU schedule (TEST INFRASTRUCTURE, written for this repo): the reduction iterator j is the
 // unit-stride index of both operands, so the pattern lowering maps one warp per output row and combines the
-// lanes' partial sums with shuffles (tiramisu_b200/frontend/src/lowering.cpp: warp_reduction_terms);
+// lanes' partial sums with shuffles (tiramisu_b200/frontend/src/lowering_retarget.cpp: warp_reduction_terms);
 // TIRAMISU_B200_LOWERING=generic keeps one row per thread and the statement's own summation order.
 #include <tiramisu/tiramisu.h>
 

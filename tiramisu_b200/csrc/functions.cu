@@ -163,7 +163,7 @@ int heat2d_common(const char *fn, halide_buffer_t *in, halide_buffer_t *out, int
 }  // namespace
 
 // Entry point for code the sm_100a lowering generates when it recognises the heat2d statement pair in a
-// function whose arguments are host buffers (tiramisu_b200/frontend/src/lowering.cpp): same
+// function whose arguments are host buffers (tiramisu_b200/frontend/src/lowering_patterns.cpp): same
 // host/device handling as the hand-registered heat2d_tiramisu — large host grids go through the
 // row-chunk H2D | kernel | D2H pipeline.
 TB200_API int tiramisu_b200_heat2d_buffers(halide_buffer_t *in, halide_buffer_t *out, int32_t H, int32_t W, int32_t form)

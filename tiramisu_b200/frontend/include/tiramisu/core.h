@@ -8,7 +8,7 @@
 //   * iteration domains are rectangular boxes of named loop dimensions (no ISL); split / tile /
 //     interchange / gpu_tile rewrite that list and record how the original iterators are rebuilt;
 //   * `codegen(args, "x.o", true)` lowers the ordered loop tree to sm_100a CUDA + a host function
-//     with the halide_buffer_t ABI and compiles it with nvcc (lowering.cpp) — it replaces the
+//     with the halide_buffer_t ABI and compiles it with nvcc (src/lowering*.cpp) — it replaces the
 //     reference's cuda_ast emitter (src/tiramisu_codegen_cuda.cpp) and Halide host code generator.
 // The ISL-string constructors (`computation("{S[i,j]: ...}", ...)`) are not supported.
 #ifndef TIRAMISU_B200_FRONTEND_CORE_H
@@ -293,7 +293,7 @@ public:
     // Old-style driver sequence (reference core.h:289-1166).  The intermediate stages have no
     // counterpart here (no ISL AST, no Halide statement): they only record what was asked for and
     // gen_halide_obj() runs the whole lowering.  A function without gpu levels is a CPU schedule; this
-    // back end has no CPU code generator, so such a function is re-targeted (lowering.cpp: retarget).
+    // back end has no CPU code generator, so such a function is re-targeted (lowering_retarget.cpp).
     void add_context_constraints(const std::string &) {}
     void gen_time_space_domain() {}
     void gen_isl_ast() {}

@@ -1,0 +1,582 @@
+// lowering_retarget.cpp — CPU schedules re-targeted to sm_100a (see lowering.h).
+#include "lowering.h"
+
+namespace tiramisu {
+namespace lowering_detail {
+
+// ------------------------------------------------------------------------------------------------ constants
+// Function constants whose definition folds to a literal are substituted everywhere (the Halide-derived
+// generators name every loop bound: `heat2d_s1_r__y_loop_min` = 1 ...), so that extents, divisibility
+// and the pattern matchers see numbers.
+// A buffer extent written as an access (`buffer S0_b("S0_b", {N_input(0), N_input(0)}, ...)`, reference
+// tests/test_87.cpp:50) would make every kernel dereference a host parameter vector: such extents are
+// evaluated once at function entry, like declared constants.
+void Lowering::hoist_buffer_extents()
+{
+    int n = 0;
+    for (buffer *b : f_->get_buffers()) {
+        std::vector<std::string> names;
+        std::vector<expr> values;
+        for (const expr &d : b->get_dim_sizes()) {
+            bool has_access = false;
+            std::vector<expr> stack{d};
+            while (!stack.empty()) {
+                expr x = stack.back(); stack.pop_back();
+                if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+                if (x.get_op_type() == o_access) {
+                    computation *oc = f_->find_computation(x.get_name());
+                    if (oc && !oc->is_constant()) has_access = true;
+                }
+                for (const expr &o : x.get_operands()) stack.push_back(o);
+            }
+            if (!has_access) continue;
+            std::string cname = "_extent" + std::to_string(n++) + "_" + b->get_name();
+            f_->own(new constant(cname, d, global::get_loop_iterator_data_type(), true, nullptr, 0, f_));
+            extent_rewrites_.push_back({b, d, expr::make_var(global::get_loop_iterator_data_type(), cname)});
+        }
+    }
+    for (auto &rw : extent_rewrites_) rw.b->replace_dim(rw.from, rw.to);
+}
+
+void Lowering::propagate_constants()
+{
+    std::vector<std::string> names;
+    std::vector<expr> values;
+    for (computation *c : f_->get_computations()) {
+        if (!c->is_constant()) continue;
+        expr v = c->get_expr().substitute(names, values);
+        if (v.is_literal()) {
+            names.push_back(c->get_name());
+            values.push_back(cast(c->get_data_type(), v));
+        }
+    }
+    if (names.empty()) return;
+    for (computation *c : f_->get_computations()) {
+        c->substitute_everywhere(names, values);
+    }
+    for (buffer *b : f_->get_buffers()) b->substitute_dims(names, values);
+}
+
+// ------------------------------------------------------------------------------------------------ CPU schedule -> GPU
+// `codegen(args, obj)` / `gen_halide_obj()` without gpu levels is a CPU schedule (parallelize /
+// vectorize / unroll).  There is no CPU code generator here, so each loop nest is mapped onto the GPU:
+//   * the vectorized loop (unit stride by construction) becomes threadIdx.x and its outer part is cut
+//     into threadIdx.y x blockIdx.x so that a block covers 128 consecutive elements (coalesced);
+//     without a vector tag the innermost data-parallel loop is cut by 128;
+//   * the outermost data-parallel loops become blockIdx.y / blockIdx.z; reduction loops (iterators
+//     that do not index the stored element) stay sequential inside the thread;
+//   * host buffers get device mirrors: inputs are copied in at entry, outputs copied back at exit —
+//     an output that the first statement overwrites completely is not copied in.
+// Warp-shuffle reduction (pattern mode only: it re-associates the sum).  A statement
+//     X(..) = X(..) + t1(.., r) + t2(.., r) ...
+// whose reduction iterator r is the unit-stride index of everything that reads it (a matrix-vector
+// product against row-major operands: the gate pre-activations of benchmarks/DNN/blocks/LSTM/cpu/
+// generator.cpp:40-41) would, mapped one output per thread, make the 32 lanes of a warp read 32
+// different rows.  Instead one warp owns one output: lane L accumulates r = L, L+32, ... in a register
+// (coalesced 128-byte reads), the partial sums are combined with __shfl_xor_sync and lane 0 adds the result to X.
+bool Lowering::warp_reduction_terms(computation *c, const std::string &r, std::vector<expr> *summands)
+{
+    const expr &e = c->get_expr();
+    if (!e.is_defined() || e.get_expr_type() != e_op || e.get_op_type() != o_add || !c->has_access()) return false;
+    std::vector<expr> terms, stack{e};
+    while (!stack.empty()) {              // flatten the left-leaning + chain, keeping the written order
+        expr x = stack.back(); stack.pop_back();
+        if (x.get_expr_type() == e_op && x.get_op_type() == o_add) { stack.push_back(x.get_operand(1)); stack.push_back(x.get_operand(0)); }
+        else terms.push_back(x);
+    }
+    auto mentions = [&](const expr &x, const std::string &v) { return !x.substitute({v}, {expr((int32_t) 0)}).is_equal(x) || (x.get_expr_type() == e_var && x.get_name() == v); };
+    int self = -1;
+    for (size_t t = 0; t < terms.size(); t++) {
+        const expr &x = terms[t];
+        if (!(x.get_expr_type() == e_op && x.get_op_type() == o_access)) continue;
+        computation *oc = nullptr;
+        buffer *b = buffer_of_access(x, &oc);
+        if (b != c->get_buffer() || oc->access().size() != c->access().size() || (int) oc->get_iteration_variables().size() != x.get_n_arg()) continue;
+        std::vector<std::string> names;
+        for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+        bool same = true;
+        for (size_t q = 0; q < c->access().size(); q++) same &= oc->access()[q].substitute(names, x.get_operands()).is_equal(c->access()[q]);
+        if (same) { if (self >= 0) return false; self = (int) t; }
+    }
+    if (self < 0 || terms.size() < 2) return false;
+    for (const expr &a : c->access()) if (mentions(a, r)) return false;
+    // every access that reads r reads it as its last (unit-stride) index, and nothing else may read the buffer written
+    bool any = false;
+    for (size_t t = 0; t < terms.size(); t++) {
+        if ((int) t == self) continue;
+        std::vector<expr> st{terms[t]};
+        while (!st.empty()) {
+            expr x = st.back(); st.pop_back();
+            if (!x.is_defined()) continue;
+            if (x.get_expr_type() == e_var && x.get_name() == r) return false;          // r used as a value
+            if (x.get_expr_type() != e_op) continue;
+            if (x.get_op_type() == o_access) {
+                computation *oc = nullptr;
+                buffer *b = buffer_of_access(x, &oc);
+                if (!b) continue;
+                if (b == c->get_buffer()) return false;
+                if ((int) oc->get_iteration_variables().size() != x.get_n_arg() || oc->access().empty()) return false;
+                std::vector<std::string> names;
+                for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+                for (size_t q = 0; q < oc->access().size(); q++) {
+                    expr idx = oc->access()[q].substitute(names, x.get_operands());
+                    const bool last = q + 1 == oc->access().size();
+                    if (!mentions(idx, r)) continue;
+                    if (!last || !(idx.get_expr_type() == e_var && idx.get_name() == r)) return false;
+                    any = true;
+                }
+                continue;
+            }
+            for (const expr &o : x.get_operands()) st.push_back(o);
+        }
+        if (summands) summands->push_back(terms[t]);
+    }
+    return any;
+}
+
+void Lowering::emit_warp_reduction(Node *loop, std::ostringstream &os, int ind)
+{
+    Node *stmt = loop->kids.front().get();
+    computation *c = stmt->comp;
+    std::vector<expr> summands;
+    if (!warp_reduction_terms(c, loop->dim_name, &summands)) die("internal: warp reduction of '" + c->get_name() + "' no longer matches");
+    const std::string it = ctype(global::get_loop_iterator_data_type()), T = ctype(c->get_data_type());
+    Node *lane = nullptr;
+    for (Node *p : stmt->path) if (p->dim_name == "_lane_" + c->get_name()) lane = p;
+    if (!lane) die("internal: warp reduction of '" + c->get_name() + "' has no lane dimension");
+    os << pad(ind) << "{   // " << c->get_name() << ": one warp per element, '" << loop->dim_name << "' strided over the lanes, shuffle reduction\n";
+    os << pad(ind + 1) << T << " acc = (" << T << ") 0;\n";
+    os << pad(ind + 1) << "for (" << it << " " << loop->cname() << " = " << print(loop->lo, true) << " + " << lane->cname() << "; " << loop->cname() << " < "
+       << print(loop->hi, true) << "; " << loop->cname() << " += 32) {\n";
+    std::vector<std::string> conds;
+    emit_bindings(stmt, os, ind + 2, conds, true);
+    enter_stmt(c);
+    std::string cond;
+    for (size_t i = 0; i < conds.size(); i++) cond += (i ? " && " : "") + conds[i];
+    if (!cond.empty()) os << pad(ind + 2) << "if (" << cond << ") {\n";
+    for (const expr &t : summands) os << pad(ind + 2 + !cond.empty()) << "acc = acc + " << print(t, true) << ";\n";
+    if (!cond.empty()) os << pad(ind + 2) << "}\n";
+    os << pad(ind + 1) << "}\n";
+    os << pad(ind + 1) << "#pragma unroll\n" << pad(ind + 1) << "for (int off = 16; off > 0; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);\n";
+    // the store: bindings of the outer dimensions only (the reduction iterator is not part of the element's address)
+    os << pad(ind + 1) << "if (" << lane->cname() << " == 0) {\n";
+    os << pad(ind + 2) << "const " << it << " " << loop->cname() << " = " << print(loop->lo, true) << ";\n";
+    std::vector<std::string> conds2;
+    emit_bindings(stmt, os, ind + 2, conds2, true);
+    std::string cond2;
+    for (size_t i = 0; i < conds2.size(); i++) cond2 += (i ? " && " : "") + conds2[i];
+    buffer *b = c->get_buffer();
+    std::string lhs = "b_" + san(b->get_name()) + "[" + lin_index(b, c->access(), true) + "]";
+    os << pad(ind + 2) << (cond2.empty() ? "" : "if (" + cond2 + ") ") << lhs << " = (" << T << ") (" << lhs << " + acc);\n";
+    os << pad(ind + 1) << "}\n" << pad(ind) << "}\n";
+    enter_stmt(nullptr);
+}
+
+// A scheduled dimension is data-parallel iff every original iterator rebuilt from it indexes the stored element
+// (each iteration writes its own element); a dimension that feeds no original iterator is not.
+bool Lowering::dim_is_parallel(computation *c, const std::string &dim)
+{
+    if (!c->has_access() && !c->get_expr().is_defined()) return false;
+    c->get_buffer();
+    bool feeds_any = false;
+    for (const var &v : c->get_iteration_variables()) {
+        expr full = expr::make_var(p_int32, v.get_name());
+        for (auto &d : c->defs()) full = full.substitute({d.first}, {d.second});
+        const bool feeds = !full.substitute({dim}, {expr((int32_t) 7)}).is_equal(full);
+        if (!feeds) continue;
+        feeds_any = true;
+        // ... and indexes it injectively: an index such as y/2 or i%4 sends several iterations to one element
+        // (the 2x2 max-pool of conv_relu_maxpool_generator_tiramisu.cpp:104 is a reduction over y and x)
+        bool stored = false;
+        for (const expr &a : c->access()) {
+            const bool uses = !a.substitute({v.get_name()}, {expr((int32_t) 0)}).is_equal(a) || (a.get_expr_type() == e_var && a.get_name() == v.get_name());
+            if (!uses) continue;
+            std::map<std::string, int64_t> coef; int64_t cst = 0;
+            if (!affine_form(a, coef, cst) || coef[v.get_name()] == 0) return false;
+            stored = true;
+        }
+        if (!stored) return false;
+    }
+    return feeds_any;
+}
+
+// Loop distribution for re-targeting.  A CPU schedule that fuses statements inside loops (`S1.after(S0, j)`) keeps
+// those loops as host loops around one kernel per statement — a launch per iteration.  When the innermost shared
+// loops are data parallel for every statement of the fused run and the statements only exchange values
+// element-wise (every two accesses to one buffer, one of them a write, use identical index expressions), running
+// S0 over the whole box and then S1 is equivalent: the shared loops are un-fused down to the outermost one that
+// must stay sequential, each statement is mapped over its full box, and nest fusion may join identical ones again
+// inside ONE kernel (reference tests/test_94.cpp, test_155.cpp).
+void Lowering::distribute_parallel_shared_loops(const std::vector<computation *> &ord)
+{
+    auto plain = [](computation *c) {
+        const expr &e = c->get_expr();
+        return e.is_defined() && e.get_expr_type() != e_sync &&
+               !(e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate || e.get_op_type() == o_free || e.get_op_type() == o_call));
+    };
+    size_t i = 0;
+    while (i < ord.size()) {
+        // a maximal run of consecutive statements that share at least one loop with their predecessor
+        size_t j = i + 1;
+        while (j < ord.size() && fuse_depth(ord[j - 1], ord[j]) > 0) j++;
+        if (j - i >= 2) {
+            bool ok = true;
+            for (size_t k = i; k < j; k++) ok &= plain(ord[k]) && !ord[k]->get_predicate().is_defined();
+            // how many leading loops the whole run shares
+            int common = INT32_MAX;
+            for (size_t k = i + 1; k < j; k++) common = std::min(common, fuse_depth(ord[k - 1], ord[k]));
+            // keep = the shared loops that must stay sequential: everything down to the innermost non-parallel one
+            int keep = 0;
+            if (ok) {
+                for (int d = 0; d < common; d++)
+                    for (size_t k = i; k < j; k++)
+                        if (!dim_is_parallel(ord[k], ord[k]->dims()[d].name)) keep = d + 1;
+                // element-wise exchange only
+                std::vector<Access> seen;
+                for (size_t k = i; k < j && ok; k++) {
+                    std::vector<Access> mine = accesses_of(ord[k]);
+                    for (const Access &p : mine)
+                        for (const Access &q : seen) {
+                            if (p.b != q.b || (!p.write && !q.write)) continue;
+                            bool identical = p.idx.size() == q.idx.size();
+                            for (size_t t = 0; identical && t < p.idx.size(); t++) identical = p.idx[t].is_equal(q.idx[t]);
+                            if (!identical) ok = false;
+                        }
+                    seen.insert(seen.end(), mine.begin(), mine.end());
+                }
+            }
+            if (ok && keep < common)
+                for (size_t k = i + 1; k < j; k++)
+                    if (fuse_depth(ord[k - 1], ord[k]) > keep) ord[k]->set_pred_level_index(keep - 1);
+        }
+        i = j;
+    }
+}
+
+void Lowering::auto_map(computation *c, int shared_depth)
+{
+    const expr &e = c->get_expr();
+    if (e.get_expr_type() == e_sync || (e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate ||
+                                                                       e.get_op_type() == o_free || (e.get_op_type() == o_call && !c->has_access()))))
+        return;
+    auto &dims = c->dims();
+    auto one_thread = [&]() {
+        // nothing to spread over threads (a scalar statement, or every loop carries a dependence): the
+        // statement's own loops run sequentially inside a one-thread kernel
+        loop_dim one; one.name = "_one_" + c->get_name(); one.lo = expr((int32_t) 0); one.hi = expr((int32_t) 1); one.tag = loop_dim::gpu_block;
+        for (auto &d : dims) d.tag = loop_dim::none;
+        dims.insert(dims.begin() + shared_depth, one);
+    };
+    if (dims.empty()) { one_thread(); return; }
+    // A statement that reads the buffer it writes at another element than its own (in-place updates such as
+    // reference tests/test_20.cpp: S1(i,j) = S0(i,j) + S0(9,9), all in buf0) carries a dependence between its
+    // iterations; without a dependence test the only safe mapping keeps its order: one thread.
+    if (c->has_access()) {
+        std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+        while (!stack.empty()) {
+            expr x = stack.back(); stack.pop_back();
+            if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+            if (x.get_op_type() == o_access) {
+                computation *oc = f_->find_computation(x.get_name());
+                if (oc && !oc->is_constant() && oc->get_buffer() == c->get_buffer()) {
+                    bool same = oc->access().size() == c->access().size() && (int) oc->get_iteration_variables().size() == x.get_n_arg();
+                    if (same) {
+                        std::vector<std::string> names;
+                        for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+                        for (size_t q = 0; q < c->access().size(); q++) same &= oc->access()[q].substitute(names, x.get_operands()).is_equal(c->access()[q]);
+                    }
+                    if (!same) { one_thread(); return; }
+                }
+            }
+            for (const expr &o : x.get_operands()) stack.push_back(o);
+        }
+    }
+    c->get_buffer();
+    auto parallel_safe = [&](const std::string &dim) { return dim_is_parallel(c, dim); };
+    // loops shared with a neighbour in the order (fused nests: the time / layer loops of the LSTM) stay
+    // sequential host loops around the kernels; only the statement's own loops are mapped
+    int vec = -1;
+    for (size_t i = shared_depth; i < dims.size(); i++) if (dims[i].tag == loop_dim::vector && parallel_safe(dims[i].name)) vec = (int) i;
+    for (auto &d : dims) d.tag = loop_dim::none;
+    if ((int) dims.size() == shared_depth) { one_thread(); return; }
+    // warp-shuffle reduction: the innermost loop is the only reduction and is unit stride in what it reads
+    if (pattern_ && is_float_type(c->get_data_type()) && (int) dims.size() >= shared_depth + 2) {
+        const loop_dim &rd = dims.back();
+        int n_red = 0, q = -1;
+        for (int i = shared_depth; i < (int) dims.size(); i++) if (!parallel_safe(dims[i].name)) n_red++;
+        for (int i = (int) dims.size() - 2; i >= shared_depth; i--) if (parallel_safe(dims[i].name)) { q = i; break; }
+        expr ext = rd.hi - rd.lo;
+        const bool long_enough = !ext.is_int_literal() || ext.get_int_val() >= 64;
+        const bool is_iter = std::any_of(c->get_iteration_variables().begin(), c->get_iteration_variables().end(), [&](const var &v) { return v.get_name() == rd.name; });
+        if (n_red == 1 && q >= 0 && !parallel_safe(rd.name) && is_iter && long_enough && c->guards().empty() && warp_reduction_terms(c, rd.name, nullptr)) {
+            const std::string inner = dims[q].name, red = rd.name;
+            c->split(var(inner), 8, var(inner + "_b"), var(inner + "_t"));          // 8 warps (outputs) per block
+            c->tag_gpu_block_level(var(inner + "_b"));
+            c->tag_gpu_thread_level(var(inner + "_t"));
+            loop_dim lane; lane.name = "_lane_" + c->get_name(); lane.lo = expr((int32_t) 0); lane.hi = expr((int32_t) 32); lane.tag = loop_dim::gpu_thread;
+            auto &dd = c->dims();
+            dd.insert(dd.end() - 1, lane);                                          // just outside the reduction loop: the innermost thread level (x)
+            dd.back().warp_reduce = true;
+            int extra = 0;
+            for (size_t i = shared_depth; i < dd.size() && extra < 2; i++) {
+                if (dd[i].tag != loop_dim::none || !parallel_safe(dd[i].name)) break;
+                dd[i].tag = loop_dim::gpu_block;
+                extra++;
+            }
+            (void) red;
+            return;
+        }
+    }
+    std::string tx, ty, bx;
+    if (vec >= shared_depth + 1 && parallel_safe(dims[vec - 1].name) && dims[vec].hi.is_int_literal() && dims[vec].hi.get_int_val() <= 64) {
+        const int lanes = (int) dims[vec].hi.get_int_val();
+        const int rows = std::max(1, 256 / lanes);
+        tx = dims[vec].name;
+        std::string outer = dims[vec - 1].name;
+        bx = outer + "_b"; ty = outer + "_t";
+        c->split(var(outer), rows, var(bx), var(ty));
+    } else {
+        int q = -1;
+        for (int i = (int) dims.size() - 1; i >= shared_depth; i--) if (parallel_safe(dims[i].name)) { q = i; break; }
+        if (q < 0) { one_thread(); return; }
+        std::string inner = dims[q].name;
+        bx = inner + "_b"; tx = inner + "_t";
+        c->split(var(inner), 256, var(bx), var(tx));
+    }
+    c->tag_gpu_block_level(var(bx));
+    c->tag_gpu_thread_level(var(tx));
+    if (!ty.empty()) c->tag_gpu_thread_level(var(ty));
+    // Coarsening: one element per thread makes a 10000 x 10000 sweep 800k tiny CTAs and the launch rate,
+    // not HBM, the limit (measured: 412 us for a 400 MB fill).  The data-parallel loop just outside the
+    // x mapping is cut by 8: the outer part becomes a block index, the inner part an unrolled loop in the
+    // thread (8 independent row accesses in flight per thread, neighbouring rows of a stencil shared).
+    {
+        int y = -1;
+        for (size_t i = shared_depth; i < c->dims().size(); i++) {
+            const loop_dim &d = c->dims()[i];
+            if (d.tag != loop_dim::none) break;
+            if (parallel_safe(d.name)) y = (int) i; else break;
+        }
+        if (y >= 0) {
+            const loop_dim d = c->dims()[y];
+            expr ext = d.hi - d.lo;
+            if (!ext.is_int_literal() || ext.get_int_val() >= 32) {
+                c->split(var(d.name), 8, var(d.name + "_o"), var(d.name + "_r"));
+                c->tag_unroll_level(var(d.name + "_r"));
+            }
+        }
+    }
+    int extra = 0;
+    for (size_t i = shared_depth; i < c->dims().size() && extra < 2; i++) {
+        loop_dim &d = c->dims()[i];
+        if (d.tag != loop_dim::none) break;                        // only loops outside the x mapping
+        if (!parallel_safe(d.name)) break;                         // a sequential loop outside would become a host loop anyway
+        d.tag = loop_dim::gpu_block;
+        extra++;
+    }
+    // pointwise (no sequential loop left inside): a candidate for nest fusion
+    bool pointwise = true;
+    for (size_t i = shared_depth; i < c->dims().size(); i++)
+        pointwise &= c->dims()[i].tag == loop_dim::gpu_block || c->dims()[i].tag == loop_dim::gpu_thread || c->dims()[i].tag == loop_dim::unrolled;
+    if (pointwise) plainly_mapped_.insert(c);
+}
+
+// Host buffers touched by device statements move to the device: arguments get a mirror (b_X device,
+// h_X host, copies at entry / exit), temporaries are simply allocated there.  Buffers only read by function
+// constants (SIZES / alpha / beta style parameter vectors) stay where the caller put them.
+// `gpu_only`: consider only statements that carry gpu levels (old-style gpu tests that tag loops but keep
+// plain host buffers, reference tests/test_17.cpp) — the rest of such a function stays host code.
+void Lowering::mirror_buffers(const std::vector<computation *> &ord, bool gpu_only)
+{
+    auto on_gpu = [](computation *c) {
+        for (auto &d : c->dims()) if (d.tag == loop_dim::gpu_block || d.tag == loop_dim::gpu_thread) return true;
+        return false;
+    };
+    std::set<buffer *> used;
+    for (computation *c : ord) {
+        if (gpu_only && !on_gpu(c)) continue;
+        const expr &e = c->get_expr();
+        const bool stmt_only = e.get_expr_type() == e_sync || (e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate || e.get_op_type() == o_free));
+        if (!stmt_only && (c->has_access() || e.get_expr_type() != e_op || e.get_op_type() != o_call)) {
+            used.insert(c->get_buffer());
+            written_args_.insert(c->get_buffer());
+        }
+        std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+        for (auto &d : c->dims()) { stack.push_back(d.lo); stack.push_back(d.hi); }
+        while (!stack.empty()) {
+            expr x = stack.back(); stack.pop_back();
+            if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+            if (x.get_op_type() == o_access) {
+                computation *oc = f_->find_computation(x.get_name());
+                if (oc && !oc->is_constant()) used.insert(oc->get_buffer());
+            }
+            for (const expr &o : x.get_operands()) stack.push_back(o);
+        }
+    }
+    std::set<buffer *> is_arg(args_.begin(), args_.end());
+    for (buffer *b : f_->get_buffers()) {
+        if (b->get_location() != mem_loc::host || !used.count(b)) continue;
+        b->tag_gpu_global();
+        if (is_arg.count(b)) mirrored_.insert(b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ nest fusion
+// Consecutive statements of a re-targeted CPU schedule that run over the same box, got the same mapping and only
+// exchange values element-wise (the nine pointwise statements of an LSTM cell, LSTM/cpu/generator.cpp:43-51) are
+// fused into ONE kernel: a launch per statement costs more than the statement.  Legality without a dependence
+// analysis: every two accesses to the same buffer inside the group (at least one of them a write) must either
+// use identical index expressions — same thread, program order — or differ by a non-zero constant in a
+// dimension that does not depend on the mapped iterators (c(m-1) read while c(m) is written: never the same
+// element inside one kernel instance).
+std::vector<Lowering::Access> Lowering::accesses_of(computation *c)
+{
+    std::vector<Access> out;
+    if (c->has_access()) out.push_back({c->get_buffer(), std::vector<expr>(c->access().begin(), c->access().end()), true});
+    std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+    while (!stack.empty()) {
+        expr x = stack.back(); stack.pop_back();
+        if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+        if (x.get_op_type() == o_access) {
+            computation *oc = f_->find_computation(x.get_name());
+            if (oc && !oc->is_constant() && (int) oc->get_iteration_variables().size() == x.get_n_arg()) {
+                std::vector<std::string> names;
+                for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+                Access a{oc->get_buffer(), {}, false};
+                for (const expr &i : oc->access()) a.idx.push_back(i.substitute(names, x.get_operands()));
+                out.push_back(a);
+            }
+        }
+        for (const expr &o : x.get_operands()) stack.push_back(o);
+    }
+    return out;
+}
+
+bool affine_form(const expr &e, std::map<std::string, int64_t> &coef, int64_t &cst, int64_t scale)
+{
+    if (!e.is_defined()) return false;
+    if (e.is_int_literal()) { cst += scale * e.get_int_val(); return true; }
+    if (e.get_expr_type() == e_var) { coef[e.get_name()] += scale; return true; }
+    if (e.get_expr_type() != e_op) return false;
+    switch (e.get_op_type()) {
+    case o_add: return affine_form(e.get_operand(0), coef, cst, scale) && affine_form(e.get_operand(1), coef, cst, scale);
+    case o_sub: return affine_form(e.get_operand(0), coef, cst, scale) && affine_form(e.get_operand(1), coef, cst, -scale);
+    case o_minus: return affine_form(e.get_operand(0), coef, cst, -scale);
+    case o_mul:
+        if (e.get_operand(0).is_int_literal()) return affine_form(e.get_operand(1), coef, cst, scale * e.get_operand(0).get_int_val());
+        if (e.get_operand(1).is_int_literal()) return affine_form(e.get_operand(0), coef, cst, scale * e.get_operand(1).get_int_val());
+        return false;
+    default: return false;
+    }
+}
+
+void Lowering::fuse_pointwise_nests(const std::vector<computation *> &ord, const std::vector<int> &shared)
+{
+    auto same_dims = [](computation *a, computation *b) {
+        if (a->dims().size() != b->dims().size()) return false;
+        for (size_t i = 0; i < a->dims().size(); i++) {
+            const loop_dim &x = a->dims()[i], &y = b->dims()[i];
+            if (x.name != y.name || x.tag != y.tag || !x.lo.is_equal(y.lo) || !x.hi.is_equal(y.hi) || x.warp_reduce || y.warp_reduce) return false;
+        }
+        if (a->guards().size() != b->guards().size() || a->defs().size() != b->defs().size()) return false;
+        for (size_t i = 0; i < a->guards().size(); i++) if (!a->guards()[i].is_equal(b->guards()[i])) return false;
+        for (size_t i = 0; i < a->defs().size(); i++) if (a->defs()[i].first != b->defs()[i].first || !a->defs()[i].second.is_equal(b->defs()[i].second)) return false;
+        return true;
+    };
+    std::vector<computation *> group;
+    std::vector<Access> group_acc;
+    for (size_t i = 0; i < ord.size(); i++) {
+        computation *c = ord[i];
+        const bool candidate = plainly_mapped_.count(c) && !c->get_predicate().is_defined();
+        bool joined = false;
+        if (candidate && !group.empty() && shared[i] == shared[i - 1] && same_dims(group.back(), c) &&
+            (shared[i] == 0 || fuse_depth(ord[i - 1], c) >= shared[i])) {
+            // mapped iterators = the original iterators rebuilt from the dimensions below the shared host loops
+            std::set<std::string> mapped;
+            for (size_t d = shared[i]; d < c->dims().size(); d++) mapped.insert(c->dims()[d].name);
+            for (auto &df : c->defs()) mapped.insert(df.first);
+            auto uses_mapped = [&](const expr &x) {
+                for (const std::string &m : mapped)
+                    if (!x.substitute({m}, {expr((int32_t) 0)}).is_equal(x) || (x.get_expr_type() == e_var && x.get_name() == m)) return true;
+                return false;
+            };
+            std::vector<Access> mine = accesses_of(c);
+            bool legal = true;
+            for (const Access &p : mine) {
+                for (const Access &q : group_acc) {
+                    if (p.b != q.b || (!p.write && !q.write)) continue;
+                    bool identical = p.idx.size() == q.idx.size();
+                    for (size_t k = 0; identical && k < p.idx.size(); k++) identical = p.idx[k].is_equal(q.idx[k]);
+                    if (identical) continue;
+                    bool disjoint = false;
+                    for (size_t k = 0; !disjoint && k < std::min(p.idx.size(), q.idx.size()); k++) {
+                        if (uses_mapped(p.idx[k]) || uses_mapped(q.idx[k])) continue;
+                        std::map<std::string, int64_t> coef; int64_t cst = 0;
+                        if (!affine_form(p.idx[k] - q.idx[k], coef, cst)) continue;
+                        bool vars = false;
+                        for (auto &kv : coef) vars |= kv.second != 0;
+                        disjoint = !vars && cst != 0;
+                    }
+                    if (!disjoint) legal = false;
+                }
+            }
+            if (legal) {
+                c->set_pred_level_index((int) c->dims().size() - 1);
+                group.push_back(c);
+                group_acc.insert(group_acc.end(), mine.begin(), mine.end());
+                joined = true;
+            }
+        }
+        if (!joined) {
+            group.clear(); group_acc.clear();
+            if (candidate) { group.push_back(c); group_acc = accesses_of(c); }
+        }
+    }
+}
+
+void Lowering::retarget(const std::vector<computation *> &ord)
+{
+    retargeted_ = true;
+    if (pattern_) distribute_parallel_shared_loops(ord);
+    std::vector<int> shared(ord.size(), 0);
+    for (size_t i = 0; i < ord.size(); i++) {
+        int with_prev = i ? fuse_depth(ord[i - 1], ord[i]) : 0;
+        int with_next = i + 1 < ord.size() ? fuse_depth(ord[i], ord[i + 1]) : 0;
+        shared[i] = std::max(with_prev, with_next);
+    }
+    for (size_t i = 0; i < ord.size(); i++) auto_map(ord[i], shared[i]);
+    if (pattern_) fuse_pointwise_nests(ord, shared);
+    mirror_buffers(ord, false);
+    // outputs whose first use is a statement that overwrites every element need no copy-in
+    for (buffer *b : args_) {
+        if (b->get_argument_type() != a_output) continue;
+        for (computation *c : ord) {
+            bool reads = false;
+            std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+            while (!stack.empty()) {
+                expr x = stack.back(); stack.pop_back();
+                if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+                if (x.get_op_type() == o_access) {
+                    computation *oc = f_->find_computation(x.get_name());
+                    if (oc && !oc->is_constant() && oc->get_buffer() == b) reads = true;
+                }
+                for (const expr &o : x.get_operands()) stack.push_back(o);
+            }
+            bool writes = c->has_access() && c->get_buffer() == b;
+            if (!reads && !writes) continue;
+            if (writes && !reads && c->guards_only_trim() && !c->get_predicate().is_defined()) {
+                const auto &it = c->get_iteration_variables();
+                bool full = it.size() == b->get_dim_sizes().size() && c->access().size() == it.size();
+                for (size_t i = 0; full && i < it.size(); i++)
+                    full = c->access()[i].get_expr_type() == e_var && c->access()[i].get_name() == it[i].get_name() &&
+                           it[i].get_lower().is_int_literal() && it[i].get_lower().get_int_val() == 0 &&
+                           it[i].get_upper().is_equal(b->get_dim_sizes()[i]);
+                if (full) no_copy_in_.insert(b);
+            }
+            break;
+        }
+    }
+}
+
+}  // namespace lowering_detail
+}  // namespace tiramisu
