@@ -15,6 +15,9 @@
 #define TIRAMISU_B200_FRONTEND_CORE_H
 
 #include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <string>
@@ -115,6 +118,7 @@ public:
     primitive_t get_data_type() const { return dtype_; }
     const expr &get_expr() const { return expr_; }
     void set_expression(const expr &e);
+    void replace_expression(const expr &e) { expr_ = e; }
     bool should_schedule_this_computation() const { return scheduled_; }
     const std::vector<var> &get_iteration_variables() const { return iters_; }
     function *get_function() const { return fct_; }
@@ -170,6 +174,12 @@ public:
     void after(computation &before_this, int level);
     void before(computation &after_this, var level = root);
     void between(computation &before_c, var before_l, computation &after_c, var after_l);
+    computation *get_predecessor() const { return pred_; }
+    computation *get_successor() const { return succ_; }
+    /** An inline computation is not scheduled or stored: every use is replaced by its expression
+      * (reference core.h: set_inline; done by the lowering before anything else looks at the program). */
+    void set_inline(bool is_inline = true) { inline_ = is_inline; if (is_inline) scheduled_ = false; }
+    bool is_inline_computation() const { return inline_; }
     /** Fuse with \p comp in the same loops down to \p level and run after it (reference core.h: fuse_after). */
     void fuse_after(var level, computation &comp) { after(comp, level); }
     /** Allocation scope of the computation's buffer.  Temporaries are allocated once per call here
@@ -224,7 +234,7 @@ protected:
     expr expr_, predicate_;
     primitive_t dtype_ = p_none;
     bool scheduled_ = true;
-    bool is_input_ = false, is_constant_ = false;
+    bool is_input_ = false, is_constant_ = false, inline_ = false;
     function *fct_ = nullptr;
 
     std::vector<loop_dim> dims_;

@@ -195,6 +195,7 @@ void Lowering::collect_kernel(Node *n, Kernel &k, bool)
 std::string Lowering::run()
 {
     if (const char *m = getenv("TIRAMISU_B200_LOWERING")) pattern_ = std::string(m) != "generic";
+    expand_inline_computations();
     hoist_buffer_extents();
     propagate_constants();
     for (computation *c : f_->get_computations())

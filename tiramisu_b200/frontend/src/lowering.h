@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -97,6 +98,7 @@ private:
     std::set<buffer *> direct_;               // mirrored arguments handed to a runtime entry point as halide buffers
     size_t n_statements_ = 0;
     void propagate_constants();
+    void expand_inline_computations();
     void hoist_buffer_extents();
     struct ExtentRewrite { buffer *b; expr from, to; };
     std::vector<ExtentRewrite> extent_rewrites_;

@@ -38,6 +38,41 @@ void Lowering::hoist_buffer_extents()
     for (auto &rw : extent_rewrites_) rw.b->replace_dim(rw.from, rw.to);
 }
 
+// Uses of inline computations (`Si.set_inline()`, reference tests/test_77.cpp) are replaced by their
+// expressions with the iterators substituted; the inline computations themselves are neither scheduled nor stored.
+void Lowering::expand_inline_computations()
+{
+    std::function<expr(const expr &, int)> expand = [&](const expr &e, int depth) -> expr {
+        if (!e.is_defined() || e.get_expr_type() != e_op) return e;
+        if (depth > 64) die("inline computations expand without end (a cycle?)");
+        if (e.get_op_type() == o_access) {
+            computation *oc = f_->find_computation(e.get_name());
+            if (oc && oc->is_inline_computation()) {
+                if ((int) oc->get_iteration_variables().size() != e.get_n_arg()) die("inline computation '" + oc->get_name() + "' used with the wrong number of indices");
+                std::vector<std::string> names;
+                for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+                std::vector<expr> args;
+                for (const expr &a : e.get_operands()) args.push_back(expand(a, depth + 1));
+                return expand(oc->get_expr().substitute(names, args), depth + 1);
+            }
+        }
+        bool changed = false;
+        std::vector<expr> ops;
+        for (const expr &o : e.get_operands()) { expr x = expand(o, depth + 1); changed |= x.get() != o.get(); ops.push_back(x); }
+        if (!changed) return e;
+        switch (e.get_op_type()) {
+        case o_call: case o_access: case o_address_of: case o_lin_index: return expr(e.get_op_type(), e.get_name(), ops, e.get_data_type());
+        case o_cast: return expr(o_cast, e.get_data_type(), ops[0]);
+        default:
+            if (ops.size() == 1) return expr(e.get_op_type(), ops[0]);
+            if (ops.size() == 2) return expr(e.get_op_type(), ops[0], ops[1]);
+            return expr(e.get_op_type(), ops[0], ops[1], ops[2]);
+        }
+    };
+    for (computation *c : f_->get_computations())
+        if (!c->is_inline_computation() && c->get_expr().is_defined()) c->replace_expression(expand(c->get_expr(), 0));
+}
+
 void Lowering::propagate_constants()
 {
     std::vector<std::string> names;
