@@ -174,6 +174,13 @@ public:
     void after(computation &before_this, int level);
     void before(computation &after_this, var level = root);
     void between(computation &before_c, var before_l, computation &after_c, var after_l);
+    /** Further definitions of the same computation over other domains ("updates", reference core.h:
+      * add_definitions / get_update): each is a computation of its own that shares the name, so uses of the
+      * name resolve to the element the latest definition is mapped to. */
+    void add_definitions(std::string iteration_domain, expr e, bool schedule_this_computation, primitive_t t, function *fct);
+    computation &get_update(int index) { return index == 0 ? *this : *updates_.at(index - 1); }
+    computation &get_first_definition() { return *this; }
+    computation &get_last_update() { return updates_.empty() ? *this : *updates_.back(); }
     computation *get_predecessor() const { return pred_; }
     computation *get_successor() const { return succ_; }
     /** An inline computation is not scheduled or stored: every use is replaced by its expression
@@ -243,6 +250,8 @@ protected:
 
     buffer *buf_ = nullptr;
     std::vector<expr> access_;                           // index expressions in the original iterators
+    std::vector<computation *> updates_;
+    bool own_access_ = false;                            // an update that was mapped explicitly (not through its first definition)
     computation *pred_ = nullptr, *succ_ = nullptr;
     std::string pred_level_;                             // "" = root
     int pred_level_index_ = -2;                          // -2 = by name, -1 = root, >=0 explicit depth

@@ -353,6 +353,19 @@ void computation::set_access_exprs(buffer *b, std::vector<expr> idx)
 {
     buf_ = b;
     access_ = std::move(idx);
+    // the mapping of a computation also holds for its later definitions until they get their own
+    // (reference tests/test_54.cpp maps S0 after add_definitions and never maps the update)
+    std::vector<std::string> mine;
+    for (const var &v : iters_) mine.push_back(v.get_name());
+    for (computation *u : updates_) {
+        if (u->buf_ && u->own_access_) continue;
+        std::vector<expr> theirs;
+        for (const var &v : u->iters_) theirs.push_back(expr::make_var(global::get_loop_iterator_data_type(), v.get_name()));
+        if (theirs.size() != mine.size()) continue;
+        u->buf_ = b;
+        u->access_.clear();
+        for (const expr &a : access_) u->access_.push_back(a.substitute(mine, theirs));
+    }
 }
 
 void computation::store_in(buffer *buff)

@@ -167,8 +167,9 @@ std::vector<std::string> parse_name_list(Reader &rd, std::vector<int64_t> *fixed
     rd.expect("[");
     if (!rd.accept("]")) {
         do {
-            if (rd.peek().k == Tok::num && fixed) {
-                fixed->push_back(rd.next().v);
+            if (fixed && (rd.peek().k == Tok::num || (rd.peek().s == "-" && rd.peek(1).k == Tok::num))) {
+                const bool neg = rd.accept("-");
+                fixed->push_back(neg ? -rd.next().v : rd.next().v);
                 names.push_back("_fixed" + std::to_string(names.size()));
                 continue;
             }
@@ -236,6 +237,15 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
     is_input_ = !schedule_this_computation && !e.is_defined();
 }
 
+void computation::add_definitions(std::string iteration_domain, expr e, bool schedule_this_computation, primitive_t t, function *fct)
+{
+    function *f = fct ? fct : fct_;
+    computation *u = f->own(new computation(iteration_domain, e, schedule_this_computation, t, f));
+    if (u->get_name() != name_) die("add_definitions: the new definition is named '" + u->get_name() + "', not '" + name_ + "'");
+    updates_.push_back(u);
+    if (buf_) set_access_exprs(buf_, access_);           // same mapping until told otherwise (re-propagates to every unmapped update)
+}
+
 void computation::set_access(std::string access_str)
 {
     Reader rd(access_str);
@@ -264,6 +274,7 @@ void computation::set_access(std::string access_str)
     for (const var &v : iters_) own.push_back(expr::make_var(global::get_loop_iterator_data_type(), v.get_name()));
     for (expr &e : idx) e = e.substitute(names, own);
     set_access_exprs(b, idx);
+    own_access_ = true;
 }
 
 }  // namespace tiramisu

@@ -270,7 +270,14 @@ std::string Lowering::run()
         << "    const double wf = std::is_floating_point<W>::value ? (double) w : (double) w / (double) (W) ~(W) 0;\n"
         << "    const double r = (double) a * (1.0 - wf) + (double) b * wf;\n"
         << "    return std::is_floating_point<T>::value ? (T) r : (T) (r + 0.5);\n}\n"
-        << "static inline void *tb_arg(halide_buffer_t *b) { return b->host ? (void *) b->host : (void *) b->device; }\n\n";
+        << "static inline void *tb_arg(halide_buffer_t *b) { return b->host ? (void *) b->host : (void *) b->device; }\n"
+        << "// bytes to mirror for a host argument: what the caller's halide_buffer_t describes when it is larger than the\n"
+        << "// generator's declaration (reference tests declare buffer(10) and run on 100 elements) and its metadata is sane\n"
+        << "static inline uint64_t tb_arg_bytes(const halide_buffer_t *b, uint64_t declared) {\n"
+        << "    if (b->dimensions <= 0 || b->dimensions > 8 || !b->dim || b->type.bits == 0 || b->type.bits > 64) return declared;\n"
+        << "    uint64_t n = (b->type.bits + 7) / 8;\n"
+        << "    for (int i = 0; i < b->dimensions; i++) { if (b->dim[i].extent <= 0 || b->dim[i].extent > (1 << 30)) return declared; n *= (uint64_t) b->dim[i].extent; }\n"
+        << "    return n > declared && n <= (declared << 10) + (1u << 20) ? n : declared;\n}\n\n";
     out << protos_.str() << "\n" << kernels_.str();
 
     out << "extern \"C\" int " << f_->get_name() << "(";
@@ -305,9 +312,11 @@ std::string Lowering::run()
     for (buffer *b : args_) {
         if (!mirrored_.count(b) || direct_.count(b)) continue;
         const std::string N = san(b->get_name());
-        out << pad(1) << "if (h_" << N << ") {\n" << pad(2) << "b_" << N << " = (" << ctype(b->get_elements_type()) << " *) tiramisu_cuda_malloc(" << bytes_of(b, false) << ");\n";
+        const int ai = (int) (std::find(args_.begin(), args_.end(), b) - args_.begin());
+        out << pad(1) << "const uint64_t nb_" << N << " = tb_arg_bytes(arg" << ai << ", " << bytes_of(b, false) << ");\n";
+        out << pad(1) << "if (h_" << N << ") {\n" << pad(2) << "b_" << N << " = (" << ctype(b->get_elements_type()) << " *) tiramisu_cuda_malloc(nb_" << N << ");\n";
         if (!no_copy_in_.count(b))
-            out << pad(2) << "tiramisu_cuda_memcpy_to_device_async(b_" << N << ", h_" << N << ", " << bytes_of(b, false) << ");\n";
+            out << pad(2) << "tiramisu_cuda_memcpy_to_device_async(b_" << N << ", h_" << N << ", nb_" << N << ");\n";
         out << pad(1) << "}\n";
     }
     out << body.str();
@@ -316,7 +325,7 @@ std::string Lowering::run()
         const std::string N = san(b->get_name());
         out << pad(1) << "if (h_" << N << ") {\n";
         if (b->get_argument_type() == a_output || written_args_.count(b))
-            out << pad(2) << "tiramisu_cuda_memcpy_to_host(h_" << N << ", b_" << N << ", " << bytes_of(b, false) << ");\n";
+            out << pad(2) << "tiramisu_cuda_memcpy_to_host(h_" << N << ", b_" << N << ", nb_" << N << ");\n";
         out << pad(2) << "tiramisu_cuda_free(b_" << N << ");\n" << pad(1) << "}\n";
     }
     for (auto it = autos.rbegin(); it != autos.rend(); ++it)
