@@ -272,6 +272,7 @@ def run_ours(args) -> None:
     # NCCL exchange above as the timed step; its time is reported next to the peer one either way.
     halo_mode = os.environ.get("TB200_HALO", "peer") if world > 1 else "none"
     nccl_step_ms = None
+    halo_fallback = None
     if halo_mode == "peer":
         import ctypes as C
 
@@ -280,7 +281,18 @@ def run_ours(args) -> None:
                 self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
 
         rows_of = lambda r: tdist.row_shard(N, world, r)      # noqa: E731
-        sym = tdist.SymmetricRows(max(rows_of(r)[1] - rows_of(r)[0] for r in range(world)), N, 1)
+        # symmetric memory needs CUDA IPC between the ranks' processes; where that is not available every
+        # rank falls back (together) to the NCCL exchange step above
+        try:
+            sym = tdist.SymmetricRows(max(rows_of(r)[1] - rows_of(r)[0] for r in range(world)), N, 1)
+        except Exception as e:                                # noqa: BLE001
+            sym, halo_fallback = None, repr(e)
+        agree = torch.tensor([0 if sym is None else 1], device="cuda")
+        torch.distributed.all_reduce(agree, op=torch.distributed.ReduceOp.MIN)
+        if int(agree.item()) == 0:
+            halo_mode = "nccl"
+            halo_fallback = halo_fallback or "another rank could not map symmetric memory"
+    if halo_mode == "peer":
         with torch.cuda.stream(stream):
             torch.as_tensor(_Mem(sym.buffer(0), (rows, N)), device="cuda").copy_(d_loc[top:top + rows])
         stream.synchronize()
@@ -416,7 +428,8 @@ def run_ours(args) -> None:
                 "config": {"workload": f"heat2d + 3x3 blur fp32, {N}x{N} grid (BASELINE configs[1])",
                            "sharding": f"rows/{world}" + ({"peer": ", halo rows read in place from the neighbours' HBM over NVLink peer mappings inside the sweep kernels (no exchange step)",
                                                             "nccl": ", halo exchange over NCCL each step, overlapped with the interior rows"}.get(halo_mode, "")),
-                           "l2": "inputs (1 GiB / n_gpus per rank) >> L2, no flush"},
+                           "l2": "inputs (1 GiB / n_gpus per rank) >> L2, no flush",
+                           **({"halo_fallback": halo_fallback} if halo_fallback else {})},
                 "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clk.summary(), "others": others}
         print(json.dumps(line))
