@@ -102,6 +102,28 @@ def test_sgemm_statement_triple_lowers_to_one_gemm_call(cases):
     assert open(bc.generated_source("sgemm_cpu_sched_gen")).read().count("__global__") == 3
 
 
+def test_retargeting_legality_decisions(frontend_lib, tmp_path):
+    """tests/frontend_cases/legality_gen.cpp: what the re-targeting does when it cannot prove independence —
+    fuse only element-wise exchanges, keep in-place cross-element statements in one thread, keep fused loops with
+    a cross-iteration read on the host."""
+    exe = str(tmp_path / "legality_gen")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-w", "-I", os.path.join(ROOT, "tiramisu_b200/frontend/include"),
+                           os.path.join(ROOT, "tests/frontend_cases/legality_gen.cpp"), "-o", exe,
+                           f"-L{os.path.dirname(frontend_lib)}", "-ltiramisu_b200_frontend", f"-Wl,-rpath,{os.path.dirname(frontend_lib)}"], env=env)
+    subprocess.check_call([exe], cwd=tmp_path, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+    def facts(name):
+        src = open(tmp_path / f"{name}.o.b200.cu").read()
+        host = src.split(f'extern "C" int {name}(')[1]
+        return src.count("static __global__"), host.count("<<<"), host.count("for (int32_t"), src.count("__launch_bounds__(1)")
+
+    assert facts("fuse_pointwise") == (1, 1, 0, 0)          # T = 2A ; U = T + 1  -> one fused kernel
+    assert facts("no_fuse_stencil") == (2, 2, 0, 0)         # U reads T(i, j+1)   -> two kernels
+    assert facts("inplace_serial") == (1, 1, 0, 1)          # S(i,j) += S(0,0)    -> one thread, in order
+    assert facts("no_distribute") == (2, 2, 2, 2)           # U reads T(i, j-1) inside the fused loops -> host loops stay
+
+
 def test_non_box_domains_are_rejected(frontend_lib, tmp_path):
     src = tmp_path / "bad.cpp"
     src.write_text("""
