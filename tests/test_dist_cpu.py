@@ -106,3 +106,38 @@ def test_sharded_stencils_match_single_process(world):
     img = (np.arange(H + 2)[:, None] + np.arange(W + 2)[None, :]).astype(np.uint32)
     box = np.concatenate([got[r]["box"][1] for r in range(world)])
     assert np.array_equal(box, oracle.boxblur_u32(img))
+
+
+def test_peer_halo_descriptors():
+    """dist.SymmetricRows.halo(): where each rank finds its neighbours' boundary rows and flag words inside the
+    symmetric blocks (pure address arithmetic; the allocation itself needs GPUs and is covered by tools/dist_check.py)."""
+    world, width, rows_max, nbuf = 3, 16, 10, 2
+    bases = [0x10000000, 0x20000000, 0x30000000]              # each rank's block as mapped into "this" process
+    H = 28
+    rows_of = lambda r: tdist.row_shard(H, world, r)          # noqa: E731   (10, 9, 9 rows)
+    row_b = width * 4
+    for rank in range(world):
+        s = object.__new__(tdist.SymmetricRows)
+        s.world, s.rank, s.width, s.n_buffers = world, rank, width, nbuf
+        s.block_bytes = ((rows_max * width * 4 + 255) // 256) * 256
+        s.bytes = s.block_bytes * nbuf + tdist.SymmetricRows.FLAG_BYTES
+        s.local, s.peers = bases[rank], list(bases)
+        r0, r1 = rows_of(rank)
+        for buf in range(nbuf):
+            h = s.halo(buf, r0, r1, rows_of)
+            assert (h.lo, h.hi) == (r0, r1) and not h.flags and not h.sig_up and not h.sig_dn
+            if rank == 0:
+                assert not h.up
+            else:
+                u0, u1 = rows_of(rank - 1)                    # row r0-1 = the upper neighbour's last row
+                assert h.up == bases[rank - 1] + buf * s.block_bytes + (u1 - 1 - u0) * row_b and u1 == r0
+            if rank == world - 1:
+                assert not h.dn
+            else:
+                assert h.dn == bases[rank + 1] + buf * s.block_bytes          # row r1 = the lower neighbour's first row
+        h = s.halo(1, r0, r1, rows_of, sync=True, wait_value=4, signal_value=5)
+        flags = lambda r: bases[r] + nbuf * s.block_bytes                     # noqa: E731
+        assert h.flags == flags(rank) and (h.wait_value, h.signal_value) == (4, 5)
+        # I am my upper neighbour's lower neighbour: I write its flags[1]; and my lower neighbour's flags[0]
+        assert (h.sig_up or 0) == (flags(rank - 1) + 4 if rank > 0 else 0)
+        assert (h.sig_dn or 0) == (flags(rank + 1) if rank < world - 1 else 0)
