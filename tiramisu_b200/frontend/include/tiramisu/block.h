@@ -11,27 +11,27 @@ class block : public computation {
 public:
     block(const std::vector<computation *> children);
 
-    void gpu_tile(var L0, var L1, int sizeX, int sizeY) override;
-    void gpu_tile(var L0, var L1, int sizeX, int sizeY, var L0_outer, var L1_outer, var L0_inner, var L1_inner) override;
-    void gpu_tile(var L0, var L1, var L2, int sizeX, int sizeY, int sizeZ) override;
-    void gpu_tile(var L0, var L1, var L2, int sizeX, int sizeY, int sizeZ,
-                  var L0_outer, var L1_outer, var L2_outer, var L0_inner, var L1_inner, var L2_inner) override;
-    void interchange(var L0, var L1) override;
-    void parallelize(var L) override;
-    void shift(var L0, int n) override;
-    void split(var L0, int sizeX) override;
-    void split(var L0, int sizeX, var L0_outer, var L0_inner) override;
-    void tile(var L0, var L1, int sizeX, int sizeY) override;
-    void tile(var L0, var L1, int sizeX, int sizeY, var L0_outer, var L1_outer, var L0_inner, var L1_inner) override;
-    void tile(var L0, var L1, var L2, int sizeX, int sizeY, int sizeZ) override;
-    void tile(var L0, var L1, var L2, int sizeX, int sizeY, int sizeZ,
-              var L0_outer, var L1_outer, var L2_outer, var L0_inner, var L1_inner, var L2_inner) override;
-    void tag_gpu_level(var L0, var L1) override;
-    void tag_gpu_level(var L0, var L1, var L2, var L3) override;
-    void unroll(var L, int fac) override;
-    void unroll(var L, int fac, var L_outer, var L_inner) override;
-    void vectorize(var L, int v) override;
-    void vectorize(var L, int v, var L_outer, var L_inner) override;
+    void gpu_tile(var a, var b, int sx, int sy) override;
+    void gpu_tile(var a, var b, int sx, int sy, var o0, var o1, var i0, var i1) override;
+    void gpu_tile(var a, var b, var c, int sx, int sy, int sz) override;
+    void gpu_tile(var a, var b, var c, int sx, int sy, int sz,
+                  var o0, var o1, var o2, var i0, var i1, var i2) override;
+    void interchange(var a, var b) override;
+    void parallelize(var lvl) override;
+    void shift(var a, int shift_by) override;
+    void split(var a, int sx) override;
+    void split(var a, int sx, var o0, var i0) override;
+    void tile(var a, var b, int sx, int sy) override;
+    void tile(var a, var b, int sx, int sy, var o0, var o1, var i0, var i1) override;
+    void tile(var a, var b, var c, int sx, int sy, int sz) override;
+    void tile(var a, var b, var c, int sx, int sy, int sz,
+              var o0, var o1, var o2, var i0, var i1, var i2) override;
+    void tag_gpu_level(var a, var b) override;
+    void tag_gpu_level(var a, var b, var c, var L3) override;
+    void unroll(var lvl, int factor) override;
+    void unroll(var lvl, int factor, var outer, var inner) override;
+    void vectorize(var lvl, int lanes) override;
+    void vectorize(var lvl, int lanes, var outer, var inner) override;
 
 private:
     const std::vector<computation *> children;
