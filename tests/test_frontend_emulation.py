@@ -1,0 +1,168 @@
+"""Host emulation of generated sources (tests/emulation) — CPU-side check of the LOWERING's semantics.
+
+The container that builds the repo has no GPU.  These tests take the `.b200.cu` sources the generators wrote,
+run every kernel body for every (block, thread) index on the host (tests/emulation/include/cuda_runtime.h) and
+compare with the oracle / the reference's own wrappers, so that an index expression, a guard, a host loop or a
+device-mirror copy that the lowering gets wrong fails HERE and not only at the next GPU run.  This is test
+infrastructure: nothing of it is part of the product, the library kernels are not involved (the runtime entry
+points are host stand-ins), races between threads cannot be seen, and kernels that need barriers / shared
+memory / shuffles are not emulatable.  The -m gpu tests of test_frontend.py remain the parity gate.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.compat import build_generators as bg
+from tests.emulation import emulate
+from tests.frontend_cases import build_cases as bc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cases():
+    from tiramisu_b200 import build
+    build.build()
+    build.build_frontend()
+    res = bc.build()
+    failed = {k: v[1] for k, v in res.items() if v[0] != 0}
+    assert not failed, failed
+    return res
+
+
+def _emulated(name):
+    return C.CDLL(emulate.build_shared([bc.generated_source(name)], name))
+
+
+def _call(lib, fn, *arrays):
+    from tiramisu_b200.halide import Buffer
+    bufs = [Buffer(a) for a in arrays]
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    assert f(*[b.ptr() for b in bufs]) == 0
+
+
+def test_rewriter_refuses_what_a_thread_loop_cannot_emulate(cases, tmp_path):
+    with pytest.raises(emulate.NotEmulatable):                       # warp-shuffle reduction
+        emulate.rewrite(bc.generated_source("matvec_cpu_gen"), str(tmp_path / "x.cpp"))
+    n = emulate.rewrite(bc.generated_source("heat2d_gen_generic"), str(tmp_path / "y.cpp"))
+    assert n == 2 and "<<<" not in open(tmp_path / "y.cpp").read()
+
+
+@pytest.mark.parametrize("variant", ["heat2d_gen", "heat2d_gen_generic"])
+@pytest.mark.parametrize("shape", [(64, 64), (130, 260), (1, 5), (3, 3)])
+def test_emulated_heat2d(cases, shape, variant):
+    from oracle import oracle
+    lib = _emulated(variant)
+    a = np.random.default_rng(11).random(shape, dtype=np.float32)
+    out = np.full(shape, -7.0, np.float32)
+    _call(lib, variant, np.array(shape, np.int32), a, out)
+    assert np.array_equal(out, oracle.heat2d(a, "cpu"))
+
+
+@pytest.mark.parametrize("hw", [(16, 24), (67, 131), (9, 9)])
+def test_emulated_blurxy_u8(cases, hw):
+    from oracle import oracle
+    lib = _emulated("blurxy_u8_gen")
+    h, w = hw
+    a = np.random.default_rng(12).integers(0, 256, (3, h, w), dtype=np.uint8)
+    out = np.zeros((3, h - 8, w - 8), np.uint8)
+    _call(lib, "blurxy_u8_gen", np.array([h, w], np.int32), a, out)
+    assert np.array_equal(out, oracle.blurxy_u8(a))
+
+
+@pytest.mark.parametrize("hw", [(16, 24), (67, 131), (3, 3)])
+def test_emulated_retargeted_blur_f32(cases, hw):
+    from oracle import oracle
+    lib = _emulated("blur_f32_cpu_gen")
+    h, w = hw
+    a = np.random.default_rng(16).random((h, w), dtype=np.float32)
+    out = np.full((h - 2, w - 2), -1.0, np.float32)
+    _call(lib, "blur_f32_cpu_gen", np.array([h, w], np.int32), a, out)
+    assert np.array_equal(out, oracle.blur_f32(a))
+
+
+@pytest.mark.parametrize("variant", ["sgemm_cpu_sched_gen", "sgemm_cpu_sched_tc"])
+@pytest.mark.parametrize("nmk", [(64, 64, 64), (100, 36, 52), (33, 130, 17)])
+def test_emulated_sgemm_cpu_schedule(cases, nmk, variant):
+    """Both lowerings of the sgemm statement triple: the three SIMT kernels (generic) and the single runtime GEMM
+    call (pattern; here the stand-in evaluates it in fp32, k sequential) — the latter checks the call's operands,
+    leading dimensions, alpha / beta wiring."""
+    from oracle import oracle
+    lib = _emulated(variant)
+    n, m, k = nmk
+    rng = np.random.default_rng(17)
+    A = rng.uniform(-1, 1, (n, k)).astype(np.float32)
+    B = rng.uniform(-1, 1, (k, m)).astype(np.float32)
+    Cm = rng.uniform(-1, 1, (n, m)).astype(np.float32)
+    got = Cm.copy()
+    _call(lib, variant, np.array([n, m, k], np.int32), np.array([1.5], np.float32), np.array([-0.75], np.float32), A, B, got)
+    assert np.array_equal(got, oracle.sgemm(1.5, -0.75, A, B, Cm.copy()))
+
+
+@pytest.mark.parametrize("variant", ["gemm_sym_gen", "gemm_sym_generic"])
+@pytest.mark.parametrize("mnk", [(64, 48, 40), (100, 36, 52)])
+def test_emulated_contraction(cases, mnk, variant):
+    lib = _emulated(variant)
+    m, n, k = mnk
+    rng = np.random.default_rng(15)
+    A = rng.integers(-5, 5, (m, k)).astype(np.float32)
+    Bt = rng.integers(-5, 5, (n, k)).astype(np.float32)
+    Cm = rng.integers(-5, 5, (m, n)).astype(np.float32)
+    got = Cm.copy()
+    _call(lib, variant, np.array(mnk, np.int32), A, Bt, got)
+    assert np.array_equal(got, Cm + A @ Bt.T)                       # small integers: exact in fp32 in any order
+
+
+@pytest.mark.parametrize("mn", [(64, 64), (33, 17)])
+def test_emulated_matvec_generic(cases, mn):
+    lib = _emulated("matvec_cpu_generic")
+    m, n = mn
+    rng = np.random.default_rng(18)
+    A = rng.integers(-4, 4, (m, n)).astype(np.float32)
+    x = rng.integers(-4, 4, (n,)).astype(np.float32)
+    y0 = rng.integers(-4, 4, (m,)).astype(np.float32)
+    y = np.full((m,), -3.0, np.float32)
+    _call(lib, "matvec_cpu_generic", np.array([m, n], np.int32), A, x, y0, y)
+    assert np.array_equal(y, y0 + A @ x)
+
+
+@pytest.mark.parametrize("variant", ["lstm_cpu_so", "lstm_cpu_so_generic"])
+def test_emulated_reference_lstm_generator(variant):
+    """The reference's LSTM/cpu/generator.cpp, compiled unmodified by the front-end (tests/compat/build_generators.py),
+    run on the host against the oracle: statement order, the bias copy, the offset GEMM calls of the pattern lowering
+    (here evaluated in fp32 by the stand-in) and the fused pointwise cell kernel."""
+    from oracle import oracle
+    src = os.path.join(ROOT, "tests/compat/_gen", variant, "lstm.o.b200.cu")
+    if not os.path.exists(src):
+        pytest.skip(f"{src} not generated (needs /root/reference at build time)")
+    lib = C.CDLL(emulate.build_shared([src], variant))
+    F, B, L, T = 32, 3, 2, 4
+    rng = np.random.default_rng(20)
+    Wt = (rng.uniform(-1, 1, (L, 2, 4 * F, F)) / 16).astype(np.float32)
+    bias = rng.uniform(-1, 1, (L, 4 * F)).astype(np.float32)
+    x = rng.uniform(-1, 1, (T, B, F)).astype(np.float32)
+    y = np.zeros((T, B, F), np.float32)
+    _call(lib, "lstm", np.array([F, B, L, T], np.int32), Wt, bias, x, y)
+    want = oracle.lstm(Wt, bias, x)
+    assert np.abs(y - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), np.abs(y - want).max()
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference (wrappers)")
+def test_reference_feature_tests_pass_their_wrappers_in_emulation():
+    """Every reference test pinned as passing on the B200 must also pass when its generated source is run on the
+    host: the wrapper's own comparison decides.  (Needs the sweep's generator outputs: __graft_entry__.build() or
+    tests/compat/build_reference_tests.py.)"""
+    expected = json.load(open(os.path.join(ROOT, "tests/compat/reference_tests_expected.json")))
+    have = [n for n in expected["pass"] if os.path.isdir(os.path.join(ROOT, "tests/compat/_gen/reftests", n))]
+    if len(have) < len(expected["pass"]):
+        pytest.skip("sweep outputs not built")
+    # + the gpu-scheduled tests build_generators.py covers one by one
+    have += [n for n in ("162", "164", "165", "166", "167", "168", "169", "170", "171", "197")
+             if os.path.isdir(os.path.join(ROOT, "tests/compat/_gen", f"test_{n}"))]
+    res = emulate.sweep(have)
+    bad = {k: v for k, v in res.items() if v != "pass"}
+    assert not bad, bad
