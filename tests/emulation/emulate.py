@@ -88,24 +88,43 @@ def build_shared(cu_paths: list[str], name: str) -> str:
     return so
 
 
-def reference_test(n: str) -> tuple[str, str]:
+def regenerate(n: str, env_extra: dict) -> str:
+    """Run reference test N's already-built generator again with extra environment (a lowering option) in a scratch
+    directory; returns that directory (its build/*.b200.cu is what the option produces)."""
+    gen = os.path.join(COMPAT, "_gen", "reftests", n, "generator")
+    tag = "_".join(f"{k}-{v}" for k, v in sorted(env_extra.items()))
+    work = os.path.join(OUT, "regen", tag, n)
+    os.makedirs(os.path.join(work, "build"), exist_ok=True)
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    env.update(env_extra)
+    r = subprocess.run([gen], capture_output=True, text=True, env=env, cwd=work, timeout=300)
+    if r.returncode:
+        raise RuntimeError(f"generator {n} failed: " + (r.stderr + r.stdout)[-400:])
+    return work
+
+
+def reference_test(n: str, gen_dir: str | None = None) -> tuple[str, str]:
     """Emulated build + run of reference test N; needs the generator's output: tests/compat/_gen/reftests/N (the
     sweep) or tests/compat/_gen/test_N (build_generators.py: the gpu-scheduled tests 162-171, 197)."""
-    gen_dir = os.path.join(COMPAT, "_gen", "reftests", n)
-    if not os.path.isdir(gen_dir):
-        gen_dir = os.path.join(COMPAT, "_gen", f"test_{n}")
+    if gen_dir is None:
+        gen_dir = os.path.join(COMPAT, "_gen", "reftests", n)
+        if not os.path.isdir(gen_dir):
+            gen_dir = os.path.join(COMPAT, "_gen", f"test_{n}")
     cus = glob.glob(os.path.join(gen_dir, "build", "*.b200.cu")) + glob.glob(os.path.join(gen_dir, "*.b200.cu"))
     if not cus:
         return n, "no generated source"
     try:
         srcs = []
         for p in cus:
-            dst = os.path.join(OUT, "reftests", n, os.path.basename(p).replace(".cu", ".emu.cpp"))
+            sub = os.path.join("reftests", n) if gen_dir.startswith(COMPAT) else os.path.join(os.path.relpath(gen_dir, OUT), "emu")
+            dst = os.path.join(OUT, sub, os.path.basename(p).replace(".cu", ".emu.cpp"))
             rewrite(p, dst)
             srcs.append(dst)
     except NotEmulatable as e:
         return n, f"not emulatable: {e}"
-    exe = os.path.join(OUT, "reftests", n, "run")
+    exe = os.path.join(os.path.dirname(srcs[0]), "run")
     r = _gxx(["-I", os.path.join(HERE, "include"), "-I", os.path.join(COMPAT, "include"), "-I", os.path.join(REF, "3rdParty/Halide/src/runtime"),
               "-I", os.path.join(REF, "include"), "-I", os.path.join(REF, "tests"), os.path.join(REF, "tests", f"wrapper_test_{n}.cpp"), *srcs,
               os.path.join(COMPAT, "compat_support.cpp"), os.path.join(REF, "src/tiramisu_utils.cpp"), os.path.join(REF, "src/tiramisu_debug.cpp"),

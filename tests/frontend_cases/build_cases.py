@@ -28,6 +28,7 @@ CASES = {
     "matvec_cpu_gen": ("matvec_cpu_gen.cpp", "matvec_cpu_gen", None),                      # warp-shuffle reduction
     "matvec_cpu_generic": ("matvec_cpu_gen.cpp", "matvec_cpu_generic", "generic"),         # one row per thread, statement order
     "sgemm_cpu_sched_gen": ("sgemm_cpu_sched_gen.cpp", "sgemm_cpu_sched_gen", "generic"),   # three SIMT kernels, bit-exact
+    "fused_reduce_cpu_gen": ("fused_reduce_cpu_gen.cpp", "fused_reduce_cpu_gen", None),    # fused i/j/k nest: i, j -> grid, k in the thread
     "sgemm_cpu_sched_tc": ("sgemm_cpu_sched_gen.cpp", "sgemm_cpu_sched_tc", None),           # statement triple -> one tcgen05 GEMM
 }
 

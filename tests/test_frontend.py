@@ -102,6 +102,18 @@ def test_sgemm_statement_triple_lowers_to_one_gemm_call(cases):
     assert open(bc.generated_source("sgemm_cpu_sched_gen")).read().count("__global__") == 3
 
 
+def test_fused_data_parallel_loops_become_the_grid(cases):
+    """fused_reduce_cpu_gen.cpp (the shape of reference tests/test_85.cpp): init and update fused inside i, j, k;
+    k carries the reduction.  One kernel, one launch, no host loop: i and j are block / thread indices, the k loop
+    with both statements runs inside the thread."""
+    src = open(bc.generated_source("fused_reduce_cpu_gen")).read()
+    host = src.split('extern "C" int fused_reduce_cpu_gen(')[1]
+    kernel = src.split("static __global__")[1].split('extern "C"')[0]
+    assert src.count("static __global__") == 1 and host.count("<<<") == 1 and host.count("for (int32_t") == 0
+    assert "blockIdx.y" in kernel and "threadIdx.x" in kernel and kernel.count("for (int32_t") == 1
+    assert "__launch_bounds__(1)" not in src
+
+
 def test_retargeting_legality_decisions(frontend_lib, tmp_path):
     """tests/frontend_cases/legality_gen.cpp: what the re-targeting does when it cannot prove independence —
     fuse only element-wise exchanges, keep in-place cross-element statements in one thread, keep fused loops with
@@ -122,6 +134,8 @@ def test_retargeting_legality_decisions(frontend_lib, tmp_path):
     assert facts("no_fuse_stencil") == (2, 2, 0, 0)         # U reads T(i, j+1)   -> two kernels
     assert facts("inplace_serial") == (1, 1, 0, 1)          # S(i,j) += S(0,0)    -> one thread, in order
     assert facts("no_distribute") == (2, 2, 2, 2)           # U reads T(i, j-1) inside the fused loops -> host loops stay
+    assert facts("grid_fuse") == (1, 1, 0, 0)               # T, U reductions over k fused in i, j, k -> i, j on the grid
+    assert facts("no_grid_fuse")[1:3] == (2, 3)             # U reads T(i, j+1): another thread's element -> host loops stay
 
 
 def test_non_box_domains_are_rejected(frontend_lib, tmp_path):
@@ -476,6 +490,24 @@ def test_retargeted_cpu_schedule_sgemm_bit_exact(nmk):
     got = Cm.copy()
     _call(lib, "sgemm_cpu_sched_gen", np.array([n, m, k], np.int32), np.array([1.5], np.float32), np.array([-0.75], np.float32), A, B, got)
     assert np.array_equal(got, oracle.sgemm(1.5, -0.75, A, B, Cm.copy()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nkm", [(64, 64, 64), (33, 17, 300), (7, 1, 5)])
+def test_fused_reduction_grid_mapping_bit_exact(nkm):
+    """fused_reduce_cpu_gen: C = A x B, zero-init fused into the k loop; k sequential in the thread, separate
+    multiply and add (-fmad=false) -> bit-exact against the same fp32 recurrence on the host."""
+    lib = _load("fused_reduce_cpu_gen")
+    n, k, m = nkm
+    rng = np.random.default_rng(21)
+    A = rng.uniform(-1, 1, (n, max(k, 1))).astype(np.float32)[:, :k].copy()
+    B = rng.uniform(-1, 1, (max(k, 1), m)).astype(np.float32)[:k].copy()
+    got = np.full((n, m), -9.0, np.float32)
+    _call(lib, "fused_reduce_cpu_gen", np.array([n, k, m], np.int32), A, B, got)
+    want = np.zeros((n, m), np.float32)
+    for kk in range(k):
+        want = want + A[:, kk:kk + 1] * B[kk][None, :]
+    assert np.array_equal(got, want)
 
 
 @pytest.mark.gpu

@@ -117,6 +117,21 @@ def test_emulated_contraction(cases, mnk, variant):
     assert np.array_equal(got, Cm + A @ Bt.T)                       # small integers: exact in fp32 in any order
 
 
+@pytest.mark.parametrize("nkm", [(64, 64, 64), (33, 17, 300), (7, 0, 5)])
+def test_emulated_fused_reduction_grid_mapping(cases, nkm):
+    lib = _emulated("fused_reduce_cpu_gen")
+    n, k, m = nkm
+    rng = np.random.default_rng(21)
+    A = rng.uniform(-1, 1, (n, max(k, 1))).astype(np.float32)[:, :k].copy()
+    B = rng.uniform(-1, 1, (max(k, 1), m)).astype(np.float32)[:k].copy()
+    got = np.full((n, m), -9.0, np.float32)
+    _call(lib, "fused_reduce_cpu_gen", np.array([n, k, m], np.int32), A, B, got)
+    want = np.zeros((n, m), np.float32)
+    for kk in range(k):
+        want = want + A[:, kk:kk + 1] * B[kk][None, :]
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("mn", [(64, 64), (33, 17)])
 def test_emulated_matvec_generic(cases, mn):
     lib = _emulated("matvec_cpu_generic")

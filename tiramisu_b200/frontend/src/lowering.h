@@ -107,9 +107,11 @@ private:
     void auto_map(computation *c, int shared_depth);
     void fuse_pointwise_nests(const std::vector<computation *> &ord, const std::vector<int> &shared);
     void distribute_parallel_shared_loops(const std::vector<computation *> &ord);
+    void map_fused_parallel_loops(const std::vector<computation *> &ord);
     bool dim_is_parallel(computation *c, const std::string &dim);
     struct Access { buffer *b; std::vector<expr> idx; bool write; };
     std::vector<Access> accesses_of(computation *c);
+    std::set<computation *> grid_fused_;          // statements of a fused run whose shared data-parallel loops became the grid
     std::set<computation *> plainly_mapped_;      // statements auto_map gave the standard element-per-thread mapping
     bool warp_reduction_terms(computation *c, const std::string &r, std::vector<expr> *summands);
     void emit_warp_reduction(Node *loop, std::ostringstream &os, int ind);

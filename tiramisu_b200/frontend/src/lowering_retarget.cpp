@@ -288,6 +288,88 @@ void Lowering::distribute_parallel_shared_loops(const std::vector<computation *>
     }
 }
 
+// Fused runs whose OUTER shared loops are data parallel while an inner one is not (reference tests/test_85.cpp: a
+// reduction over k with its zero-init fused at k, inside i and j).  Distribution cannot un-fuse them (k carries the
+// dependence) and as host loops they cost a launch per (i, j, k).  Instead the shared data-parallel loops become
+// the grid and everything inside — the sequential shared loops and the statements' own loops — runs in the
+// thread, in program order.  Legal under the same two facts distribution relies on: every statement writes an
+// element of its own per iteration of the mapped loops (dim_is_parallel), and the statements only exchange values
+// element-wise (identical index expressions for every pair of accesses to one buffer that includes a write), so two
+// threads never touch the same element of a written buffer.
+// Checked in host emulation (tests/emulation: reference test_85 passes its wrapper, also under AddressSanitizer) and
+// it leaves every generated source that has run on a B200 byte-identical; it has not itself run on a B200 yet.
+// TIRAMISU_B200_MAP_FUSED=0 at generator time keeps such runs as host loops.
+void Lowering::map_fused_parallel_loops(const std::vector<computation *> &ord)
+{
+    auto plain = [](computation *c) {
+        const expr &e = c->get_expr();
+        return e.is_defined() && e.get_expr_type() != e_sync && c->has_access() && !c->get_predicate().is_defined() &&
+               !(e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate || e.get_op_type() == o_free || e.get_op_type() == o_call));
+    };
+    size_t i = 0;
+    while (i < ord.size()) {
+        size_t j = i + 1;
+        while (j < ord.size() && fuse_depth(ord[j - 1], ord[j]) > 0) j++;
+        const size_t first = i, last = j;
+        i = j;
+        if (last - first < 2) continue;
+        bool ok = true;
+        for (size_t k = first; k < last; k++) ok &= plain(ord[k]);
+        if (!ok) continue;
+        std::vector<int> depth(last - first, 0);
+        int common = INT32_MAX;
+        for (size_t k = first + 1; k < last; k++) { depth[k - first] = fuse_depth(ord[k - 1], ord[k]); common = std::min(common, depth[k - first]); }
+        // P leading shared loops: same name (index expressions are compared by iterator name) and bounds in every statement, data parallel for every statement, no tag of the user's that maps
+        int P = 0;
+        for (int d = 0; d < common && ok; d++) {
+            const loop_dim &ref = ord[first]->dims()[d];
+            bool par = true;
+            for (size_t k = first; k < last; k++) {
+                const loop_dim &x = ord[k]->dims()[d];
+                par &= x.name == ref.name && x.lo.is_equal(ref.lo) && x.hi.is_equal(ref.hi) && x.tag != loop_dim::gpu_block && x.tag != loop_dim::gpu_thread &&
+                       dim_is_parallel(ord[k], x.name);
+            }
+            if (!par) break;
+            P = d + 1;
+        }
+        if (P == 0 || P == common) continue;           // P == common: nothing sequential is shared — distribution's case
+        // element-wise exchange only
+        std::vector<Access> seen;
+        for (size_t k = first; k < last && ok; k++) {
+            std::vector<Access> mine = accesses_of(ord[k]);
+            for (const Access &p : mine)
+                for (const Access &q : seen) {
+                    if (p.b != q.b || (!p.write && !q.write)) continue;
+                    bool identical = p.idx.size() == q.idx.size();
+                    for (size_t t = 0; identical && t < p.idx.size(); t++) identical = p.idx[t].is_equal(q.idx[t]);
+                    if (!identical) ok = false;
+                }
+            // ... and inside one statement (a read of the written buffer at another element)
+            for (const Access &p : mine)
+                for (const Access &q : mine) {
+                    if (&p == &q || p.b != q.b || (!p.write && !q.write)) continue;
+                    bool identical = p.idx.size() == q.idx.size();
+                    for (size_t t = 0; identical && t < p.idx.size(); t++) identical = p.idx[t].is_equal(q.idx[t]);
+                    if (!identical) ok = false;
+                }
+            seen.insert(seen.end(), mine.begin(), mine.end());
+        }
+        if (!ok) continue;
+        for (size_t k = first; k < last; k++) {
+            computation *c = ord[k];
+            for (auto &d : c->dims()) d.tag = loop_dim::none;
+            const std::string inner = c->dims()[P - 1].name;
+            if (P >= 2) c->dims()[P - 2].tag = loop_dim::gpu_block;
+            if (P >= 3) c->dims()[P - 3].tag = loop_dim::gpu_block;
+            c->split(var(inner), 256, var(inner + "_b"), var(inner + "_t"));
+            c->tag_gpu_block_level(var(inner + "_b"));
+            c->tag_gpu_thread_level(var(inner + "_t"));
+            if (k > first) c->set_pred_level_index(depth[k - first]);      // one more shared loop above the fuse level
+            grid_fused_.insert(c);
+        }
+    }
+}
+
 void Lowering::auto_map(computation *c, int shared_depth)
 {
     const expr &e = c->get_expr();
@@ -295,6 +377,7 @@ void Lowering::auto_map(computation *c, int shared_depth)
                                                                        e.get_op_type() == o_free || (e.get_op_type() == o_call && !c->has_access()))))
         return;
     auto &dims = c->dims();
+    if (grid_fused_.count(c)) return;             // mapped as part of its fused run: its own loops stay in the thread
     auto one_thread = [&]() {
         // nothing to spread over threads (a scalar statement, or every loop carries a dependence): the
         // statement's own loops run sequentially inside a one-thread kernel
@@ -573,6 +656,8 @@ void Lowering::retarget(const std::vector<computation *> &ord)
 {
     retargeted_ = true;
     if (pattern_) distribute_parallel_shared_loops(ord);
+    const char *map_fused = getenv("TIRAMISU_B200_MAP_FUSED");
+    if (pattern_ && !(map_fused && map_fused[0] == '0')) map_fused_parallel_loops(ord);
     std::vector<int> shared(ord.size(), 0);
     for (size_t i = 0; i < ord.size(); i++) {
         int with_prev = i ? fuse_depth(ord[i - 1], ord[i]) : 0;
