@@ -37,6 +37,9 @@ public:
     Buffer(halide_type_t t, int a, int b, int c, const std::string &n = "") : Base(t, a, b, c), name_(n) {}
     Buffer(halide_type_t t, int a, int b, int c, int d, const std::string &n = "") : Base(t, a, b, c, d), name_(n) {}
     Buffer(T *data, const std::vector<int> &sizes, const std::string &n = "") : Base(data, sizes), name_(n) {}
+    // (type, untyped data pointer, sizes): wrapper_test_93.cpp wraps int arrays in Buffer<int64_t> this way
+    template <typename U> Buffer(halide_type_t, U *data, const std::vector<int> &sizes, const std::string &n = "") : Base((T *) data, sizes), name_(n) {}
+    Buffer(halide_type_t, const std::vector<int> &sizes, const std::string &n = "") : Base(sizes), name_(n) {}
     Buffer(T *data, int a, const std::string &n = "") : Base(data, a), name_(n) {}
     Buffer(T *data, int a, int b, const std::string &n = "") : Base(data, a, b), name_(n) {}
     Buffer(T *data, int a, int b, int c, const std::string &n = "") : Base(data, a, b, c), name_(n) {}

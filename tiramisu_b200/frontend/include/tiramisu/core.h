@@ -166,6 +166,8 @@ public:
     virtual void tag_unroll_level(var L);
     virtual void tag_unroll_level(var L, int) { tag_unroll_level(L); }
     virtual void shift(var L0, int n);
+    /** Run loop `old_var` backwards; the loop is called `new_var` afterwards (reference core.h:4461). */
+    virtual void loop_reversal(var old_var, var new_var);
 
     /** Order: \p next runs after this computation, sharing the loops up to and including \p level. */
     computation &then(computation &next, var level = root);
@@ -223,6 +225,8 @@ public:
     void set_pred_level_index(int level_index) { pred_level_index_ = level_index; }
     bool is_input() const { return is_input_; }
     bool is_constant() const { return is_constant_; }
+    /** A constant declared at a loop level (not function wide): a let, substituted into the statements that name it. */
+    bool is_let() const { return is_let_; }
     int find_dim(const std::string &name) const;
     void dump() const;
     /** Replace named scalars by values in every expression the computation holds (constant propagation). */
@@ -241,7 +245,7 @@ protected:
     expr expr_, predicate_;
     primitive_t dtype_ = p_none;
     bool scheduled_ = true;
-    bool is_input_ = false, is_constant_ = false, inline_ = false;
+    bool is_input_ = false, is_constant_ = false, inline_ = false, is_let_ = false, schedule_when_defined_ = false;
     function *fct_ = nullptr;
 
     std::vector<loop_dim> dims_;
@@ -298,6 +302,8 @@ public:
     const std::vector<buffer *> &get_buffers() const { return bufs_; }
     computation *find_computation(const std::string &name) const;
     buffer *find_buffer(const std::string &name) const;
+    /** The function constant called `name`, or nullptr (reference core.h:1198). */
+    constant *get_invariant_by_name(std::string name) const;
     std::string fresh_name(const std::string &prefix);
     /** Heap objects the front-end creates on the user's behalf (auto buffers, allocate_at computations). */
     template <typename T> T *own(T *p)

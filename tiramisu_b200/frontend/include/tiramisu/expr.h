@@ -92,6 +92,17 @@ public:
     bool is_literal() const { return p_ && p_->kind == e_val; }
     int64_t get_int_val() const { return p_ ? p_->ival : 0; }
     double get_double_val() const { return p_ ? p_->fval : 0.0; }
+    /** Typed views of a literal (reference expr.h:537-616). */
+    uint8_t get_uint8_value() const { return (uint8_t) get_int_val(); }
+    int8_t get_int8_value() const { return (int8_t) get_int_val(); }
+    uint16_t get_uint16_value() const { return (uint16_t) get_int_val(); }
+    int16_t get_int16_value() const { return (int16_t) get_int_val(); }
+    uint32_t get_uint32_value() const { return (uint32_t) get_int_val(); }
+    int32_t get_int32_value() const { return (int32_t) get_int_val(); }
+    uint64_t get_uint64_value() const { return (uint64_t) get_int_val(); }
+    int64_t get_int64_value() const { return get_int_val(); }
+    float get_float32_value() const { return (float) get_double_val(); }
+    double get_float64_value() const { return get_double_val(); }
     const node *get() const { return p_.get(); }
 
     /** Replace every variable named names[i] by with[i] (simultaneously). */

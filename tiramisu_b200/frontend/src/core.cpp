@@ -34,6 +34,11 @@ computation *function::find_computation(const std::string &name) const
         if ((*it)->get_name() == name) return *it;
     return nullptr;
 }
+constant *function::get_invariant_by_name(std::string name) const
+{
+    computation *c = find_computation(name);
+    return c && c->is_constant() ? static_cast<constant *>(c) : nullptr;
+}
 buffer *function::find_buffer(const std::string &name) const
 {
     for (auto it = bufs_.rbegin(); it != bufs_.rend(); ++it)
@@ -148,6 +153,13 @@ void computation::set_expression(const expr &e)
 {
     expr_ = e;
     if (dtype_ == p_none) dtype_ = e.get_data_type();
+    if (schedule_when_defined_ && e.is_defined()) {
+        for (const var &v : iters_)
+            if (!v.has_range()) die("set_expression: iterator '" + v.get_name() + "' of '" + name_ + "' has no bounds");
+        schedule_when_defined_ = false;
+        is_input_ = false;
+        scheduled_ = true;
+    }
 }
 
 expr computation::access_expr(const std::vector<expr> &idx)
@@ -302,6 +314,16 @@ void computation::shift(var L0, int n)
     dims_[d].hi = dims_[d].hi + n;
 }
 
+void computation::loop_reversal(var old_var, var new_var)
+{
+    // same range, opposite direction: the original iterator is lo + hi - 1 - new
+    int d = find_dim(old_var.get_name());
+    if (d < 0) die("loop_reversal: '" + name_ + "' has no loop level '" + old_var.get_name() + "'");
+    const loop_dim was = dims_[d];
+    defs_.push_back({was.name, (was.lo + was.hi - 1) - var(new_var.get_name())});
+    dims_[d].name = new_var.get_name();
+}
+
 // -- ordering
 void computation::link_after(computation &before_this, const std::string &level_name, int level_index)
 {
@@ -425,9 +447,11 @@ Input::Input(std::string name, std::vector<expr> sizes, primitive_t t) : input(n
 
 constant::constant(std::string name, const expr &e, primitive_t t, bool function_wide, computation *, int, function *func)
 {
-    if (!function_wide) die("constant '" + name + "': only function-wide constants are supported");
+    // not function wide (reference core.h: a let statement at a loop level of `with_computation`): its value is
+    // substituted into the statements that name it (lowering: expand_lets), so it may use their iterators
     construct(name, {}, e, false, t, func);
     is_constant_ = true;
+    is_let_ = !function_wide;
 }
 constant::constant(std::string name, const expr &e, primitive_t t, function *func)
 {

@@ -226,6 +226,7 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
             die("iteration domain of '" + name + "' is not a box (constraint couples iterators): \"" + iteration_domain + "\"");
         }
     }
+    const bool asked_to_schedule = schedule_this_computation;
     if (!e.is_defined()) schedule_this_computation = false;      // a declaration only (input / wrapper computation)
     std::vector<var> vars;
     for (size_t i = 0; i < iters.size(); i++) {
@@ -235,6 +236,9 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
     }
     construct(name, vars, e, schedule_this_computation, t, fct);
     is_input_ = !schedule_this_computation && !e.is_defined();
+    // declared with an empty expression but to be scheduled: a statement whose expression comes later through
+    // set_expression (reference tests/test_04.cpp); until then it reads like an input
+    schedule_when_defined_ = asked_to_schedule && !e.is_defined();
 }
 
 void computation::add_definitions(std::string iteration_domain, expr e, bool schedule_this_computation, primitive_t t, function *fct)

@@ -42,11 +42,14 @@ std::vector<computation *> Lowering::order()
     std::vector<computation *> ord;
     std::set<computation *> seen;
     for (computation *c : f_->get_computations()) {
-        if (c->is_input() || c->is_constant() || !c->should_schedule_this_computation()) continue;
+        if (c->is_input() || (!c->is_constant() && !c->should_schedule_this_computation())) continue;
         if (c->pred() != nullptr) continue;
+        // function constants may be links of the chain (reference tests/test_93.cpp orders its statements after its
+        // constants): they are evaluated at function entry anyway, so they are walked through and left out
+        if (c->is_constant() && !c->succ()) continue;
         for (computation *p = c; p; p = p->succ()) {
             if (!seen.insert(p).second) die("cycle in the then()/after() order at '" + p->get_name() + "'");
-            ord.push_back(p);
+            if (!p->is_constant() && p->should_schedule_this_computation()) ord.push_back(p);
         }
     }
     for (computation *c : f_->get_computations())
@@ -195,11 +198,12 @@ void Lowering::collect_kernel(Node *n, Kernel &k, bool)
 std::string Lowering::run()
 {
     if (const char *m = getenv("TIRAMISU_B200_LOWERING")) pattern_ = std::string(m) != "generic";
+    expand_lets();
     expand_inline_computations();
     hoist_buffer_extents();
     propagate_constants();
     for (computation *c : f_->get_computations())
-        if (c->is_constant()) { constants_[c->get_name()] = c; constant_order_.push_back(c); }
+        if (c->is_constant() && !c->is_let()) { constants_[c->get_name()] = c; constant_order_.push_back(c); }
     for (buffer *b : args_)
         if (b->get_location() != mem_loc::host && b->get_location() != mem_loc::gpu_global)
             die("argument buffer '" + b->get_name() + "' is tagged on-chip");

@@ -98,6 +98,7 @@ private:
     std::set<buffer *> direct_;               // mirrored arguments handed to a runtime entry point as halide buffers
     size_t n_statements_ = 0;
     void propagate_constants();
+    void expand_lets();
     void expand_inline_computations();
     void hoist_buffer_extents();
     struct ExtentRewrite { buffer *b; expr from, to; };

@@ -73,12 +73,28 @@ void Lowering::expand_inline_computations()
         if (!c->is_inline_computation() && c->get_expr().is_defined()) c->replace_expression(expand(c->get_expr(), 0));
 }
 
+// Loop-level constants (`constant(name, e, t, false, &S, level)`, reference tests/test_04.cpp): lets.  Each is
+// replaced by its (cast) value in every statement that names it; later lets may use earlier ones.
+void Lowering::expand_lets()
+{
+    std::vector<std::string> names;
+    std::vector<expr> values;
+    for (computation *c : f_->get_computations()) {
+        if (!c->is_let()) continue;
+        names.push_back(c->get_name());
+        values.push_back(cast(c->get_data_type(), c->get_expr().substitute(names, values)));
+    }
+    if (names.empty()) return;
+    for (computation *c : f_->get_computations())
+        if (!c->is_let()) c->substitute_everywhere(names, values);
+}
+
 void Lowering::propagate_constants()
 {
     std::vector<std::string> names;
     std::vector<expr> values;
     for (computation *c : f_->get_computations()) {
-        if (!c->is_constant()) continue;
+        if (!c->is_constant() || c->is_let()) continue;
         expr v = c->get_expr().substitute(names, values);
         if (v.is_literal()) {
             names.push_back(c->get_name());
