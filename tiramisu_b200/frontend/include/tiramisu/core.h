@@ -227,6 +227,9 @@ public:
     bool is_constant() const { return is_constant_; }
     /** A constant declared at a loop level (not function wide): a let, substituted into the statements that name it. */
     bool is_let() const { return is_let_; }
+    /** Declared without iterator bounds (`{S[i,j]}`): function::compute_bounds() has to supply them. */
+    bool pending_bounds() const { return pending_bounds_; }
+    void set_iterator_ranges(const std::vector<std::pair<expr, expr>> &ranges);
     int find_dim(const std::string &name) const;
     void dump() const;
     /** Replace named scalars by values in every expression the computation holds (constant propagation). */
@@ -245,7 +248,7 @@ protected:
     expr expr_, predicate_;
     primitive_t dtype_ = p_none;
     bool scheduled_ = true;
-    bool is_input_ = false, is_constant_ = false, inline_ = false, is_let_ = false, schedule_when_defined_ = false;
+    bool is_input_ = false, is_constant_ = false, inline_ = false, is_let_ = false, schedule_when_defined_ = false, pending_bounds_ = false;
     function *fct_ = nullptr;
 
     std::vector<loop_dim> dims_;
@@ -329,7 +332,8 @@ public:
     void gen_c_code() const {}
     /** Buffers are mapped lazily (computation::get_buffer): nothing to do ahead of time. */
     void allocate_and_map_buffers_automatically() {}
-    void compute_bounds() {}
+    /** Ranges for iterators declared without bounds, from what the consumers read (reference core.h: compute_bounds). */
+    void compute_bounds();
     void dump_dep_graph() {}
     void dump_halide_IR() const {}
     void dump_time_processor_domain() const {}

@@ -314,6 +314,18 @@ void computation::shift(var L0, int n)
     dims_[d].hi = dims_[d].hi + n;
 }
 
+void computation::set_iterator_ranges(const std::vector<std::pair<expr, expr>> &ranges)
+{
+    if (ranges.size() != iters_.size() || dims_.size() != iters_.size()) die("bounds of '" + name_ + "' must be set before it is scheduled");
+    for (size_t i = 0; i < iters_.size(); i++) {
+        if (dims_[i].name != iters_[i].get_name()) die("bounds of '" + name_ + "' must be set before it is scheduled");
+        iters_[i] = var(iters_[i].get_name(), ranges[i].first, ranges[i].second);
+        dims_[i].lo = ranges[i].first;
+        dims_[i].hi = ranges[i].second;
+    }
+    pending_bounds_ = false;
+}
+
 void computation::loop_reversal(var old_var, var new_var)
 {
     // same range, opposite direction: the original iterator is lo + hi - 1 - new

@@ -227,14 +227,22 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
         }
     }
     const bool asked_to_schedule = schedule_this_computation;
+    bool unbounded = false;
     if (!e.is_defined()) schedule_this_computation = false;      // a declaration only (input / wrapper computation)
     std::vector<var> vars;
     for (size_t i = 0; i < iters.size(); i++) {
         if (lo[i].is_defined() && hi[i].is_defined()) vars.push_back(var(iters[i], lo[i], hi[i]));
         else if (!schedule_this_computation) vars.push_back(var(iters[i]));
+        else if (!lo[i].is_defined() && !hi[i].is_defined()) { vars.push_back(var(iters[i])); unbounded = true; }   // compute_bounds()
         else die("iterator '" + iters[i] + "' of '" + name + "' has no lower or no upper bound in \"" + iteration_domain + "\"");
     }
-    construct(name, vars, e, schedule_this_computation, t, fct);
+    if (unbounded) {
+        // every bound must come from the consumers: no partial boxes
+        vars.clear();
+        for (const std::string &it : iters) vars.push_back(var(it));
+    }
+    construct(name, vars, e, schedule_this_computation && !unbounded, t, fct);
+    if (unbounded) { scheduled_ = true; pending_bounds_ = true; }
     is_input_ = !schedule_this_computation && !e.is_defined();
     // declared with an empty expression but to be scheduled: a statement whose expression comes later through
     // set_expression (reference tests/test_04.cpp); until then it reads like an input

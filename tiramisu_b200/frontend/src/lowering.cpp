@@ -198,6 +198,9 @@ void Lowering::collect_kernel(Node *n, Kernel &k, bool)
 std::string Lowering::run()
 {
     if (const char *m = getenv("TIRAMISU_B200_LOWERING")) pattern_ = std::string(m) != "generic";
+    for (computation *c : f_->get_computations())
+        if (c->pending_bounds() && c->should_schedule_this_computation())
+            die("computation '" + c->get_name() + "' was declared without iterator bounds and function::compute_bounds() was not called");
     expand_lets();
     expand_inline_computations();
     hoist_buffer_extents();

@@ -715,4 +715,67 @@ void Lowering::retarget(const std::vector<computation *> &ord)
 }
 
 }  // namespace lowering_detail
+
+// Bound inference for box domains (reference core.h compute_bounds; tests/test_22-24.cpp).  A computation declared
+// without bounds (`{S0[i,j]}`) gets, per iterator, the hull of what its consumers read: consumers are visited last
+// declared first, so that a producer's box is complete when it is itself looked at as a consumer.  Each argument of
+// an access must be affine in the consumer's iterators; its interval follows from their ranges.
+void function::compute_bounds()
+{
+    using lowering_detail::affine_form;
+    using lowering_detail::die;
+    auto lit_or = [](const expr &a, const expr &b, bool want_min) {
+        if (a.is_equal(b)) return a;
+        if (a.is_int_literal() && b.is_int_literal())
+            return expr((int32_t) (want_min ? std::min(a.get_int_val(), b.get_int_val()) : std::max(a.get_int_val(), b.get_int_val())));
+        return expr(want_min ? o_min : o_max, a, b);
+    };
+    std::map<computation *, std::vector<std::pair<expr, expr>>> hull;
+    for (auto it = comps_.rbegin(); it != comps_.rend(); ++it) {
+        computation *c = *it;
+        if (c->pending_bounds()) {
+            auto h = hull.find(c);
+            bool complete = h != hull.end();
+            if (complete) for (auto &r : h->second) complete &= r.first.is_defined() && r.second.is_defined();
+            if (!complete) die("compute_bounds: nothing that has bounds reads '" + c->get_name() + "'");
+            c->set_iterator_ranges(h->second);
+        }
+        if (c->is_input() || !c->get_expr().is_defined()) continue;
+        std::map<std::string, std::pair<expr, expr>> range;
+        for (const var &v : c->get_iteration_variables()) if (v.has_range()) range[v.get_name()] = {v.get_lower(), v.get_upper()};
+        std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+        while (!stack.empty()) {
+            expr x = stack.back(); stack.pop_back();
+            if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+            for (const expr &o : x.get_operands()) stack.push_back(o);
+            if (x.get_op_type() != o_access) continue;
+            computation *p = find_computation(x.get_name());
+            if (!p || !p->pending_bounds() || (int) p->get_iteration_variables().size() != x.get_n_arg()) continue;
+            auto &h = hull[p];
+            h.resize(x.get_n_arg());
+            for (int k = 0; k < x.get_n_arg(); k++) {
+                std::map<std::string, int64_t> coef; int64_t cst = 0;
+                if (!affine_form(x.get_operand(k), coef, cst)) die("compute_bounds: '" + c->get_name() + "' reads '" + p->get_name() + "' at a non-affine index");
+                expr lo((int32_t) cst), hi((int32_t) cst);
+                for (auto &kv : coef) {
+                    if (kv.second == 0) continue;
+                    const expr f((int32_t) kv.second);
+                    auto r = range.find(kv.first);
+                    if (r == range.end()) {                       // a parameter: the same term at both ends
+                        expr v = expr::make_var(p_int32, kv.first);
+                        lo = lo + f * v; hi = hi + f * v;
+                    } else if (kv.second > 0) {
+                        lo = lo + f * r->second.first; hi = hi + f * (r->second.second - 1);
+                    } else {
+                        lo = lo + f * (r->second.second - 1); hi = hi + f * r->second.first;
+                    }
+                }
+                hi = hi + 1;
+                h[k].first = h[k].first.is_defined() ? lit_or(h[k].first, lo, true) : lo;
+                h[k].second = h[k].second.is_defined() ? lit_or(h[k].second, hi, false) : hi;
+            }
+        }
+    }
+}
+
 }  // namespace tiramisu
