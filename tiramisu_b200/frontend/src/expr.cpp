@@ -319,11 +319,28 @@ void str_dump(const std::string &s) { std::cerr << s; }
 // ---- var / sync ---------------------------------------------------------------------------------
 static int g_var_counter = 0;
 var::var() : var("_v" + std::to_string(g_var_counter++)) {}
-var::var(std::string name) : expr(expr::make_var(g_iter_type, name)) {}
+// A name declared once with a type keeps it for later untyped declarations (reference expr.h: var::declared_vars;
+// tests/test_76.cpp).
+static std::map<std::string, primitive_t> &declared_var_types()
+{
+    static std::map<std::string, primitive_t> m;
+    return m;
+}
+static primitive_t type_of_var(const std::string &name)
+{
+    auto it = declared_var_types().find(name);
+    return it == declared_var_types().end() ? g_iter_type : it->second;
+}
+static const std::string &declare_var(primitive_t t, const std::string &name)
+{
+    declared_var_types()[name] = t;
+    return name;
+}
+var::var(std::string name) : expr(expr::make_var(type_of_var(name), name)) {}
 var::var(std::string name, bool) : var(std::move(name)) {}
-var::var(primitive_t t, std::string name) : expr(expr::make_var(t, name)) {}
+var::var(primitive_t t, std::string name) : expr(expr::make_var(t, declare_var(t, name))) {}
 var::var(primitive_t t, std::string name, bool) : var(t, std::move(name)) {}
-var::var(std::string name, expr lower_bound, expr upper_bound) : expr(expr::make_var(g_iter_type, name)), lower_(lower_bound), upper_(upper_bound) {}
+var::var(std::string name, expr lower_bound, expr upper_bound) : expr(expr::make_var(type_of_var(name), name)), lower_(lower_bound), upper_(upper_bound) {}
 
 sync::sync() : expr(expr::make_sync()) {}
 
