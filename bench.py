@@ -9,8 +9,12 @@ the grid.  metric = stencil GB/s = algorithmic bytes / time, algorithmic bytes p
 2*N^2*4 (heat2d: read once, write once) + 4*(N^2 + (N-2)^2) (blur).
   value : inputs resident in HBM, kernels launched through the device-resident C-ABI entry.
   e2e   : same step through the host-buffer C-ABI call (pinned host memory; H2D + D2H inside).
-Other BASELINE configs (sgemm, conv, LSTM) are reported under "others" for context.
+The other BASELINE configs — sgemm 1024^3 (configs[0]), conv+ReLU+maxpool (configs[2]), the LSTM stack
+(configs[3]) and the sgemm sweep (configs[4]) — ride in the same line under "configs", each with its own
+value / roofline / cpu_baseline / e2e objects (tools/bench_configs.py), sharded over the ranks at N > 1.
 Inputs (1 GiB each) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
+stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the whole run (NCCL's
+NCCL_DEBUG log, library banners) and the line is written to the saved descriptor at the end.
 """
 from __future__ import annotations
 
@@ -29,7 +33,35 @@ sys.path.insert(0, ROOT)
 
 GRID = int(os.environ.get("TB200_BENCH_GRID", 16384))
 METRIC = "stencil_GBps"
+HEAT_NCU = "r01_heat2d_ncu_full.txt"          # committed `ncu --set full` summaries of the two sweep kernels
+BLUR_NCU = "r01_blur_f32_ncu_full_v2.txt"
 UNIT = "GB/s"
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout() -> None:
+    """Everything any library prints to fd 1 (NCCL_DEBUG=INFO goes to stdout) lands on stderr; the JSON line
+    goes to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def bench_config(world: int) -> dict:
+    """The `config` object, identical in both arms (ours / --impl reference) for a given N."""
+    return {"workload": f"heat2d + 3x3 blur fp32, {GRID}x{GRID} grid (BASELINE configs[1])",
+            "sharding": f"rows/{world}",
+            "l2": "inputs (1 GiB / n_gpus per rank) >> L2, no flush"}
 
 
 def alg_bytes(n_rows: int, n_cols: int) -> dict:
@@ -61,17 +93,20 @@ def ncu_traffic(kernel_file: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  nvidia-smi needs
+    a second or more to start on an 8-GPU box — longer than the timed region itself — so the sampler is
+    started early, `mark()` brackets the span during which the GPU is kept under the benchmark's load, and
+    only samples inside marked spans count."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int = 0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.spans = index, [], None, []
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -81,51 +116,89 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def wait_started(self, timeout: float = 8.0) -> bool:
+        t0 = time.monotonic()
+        while self.proc and not self.rows and time.monotonic() - t0 < timeout:
+            time.sleep(0.02)
+        return bool(self.rows)
+
+    def mark(self, t0: float, t1: float) -> None:
+        self.spans.append((t0, t1))
+
+    def samples_in_spans(self) -> int:
+        return sum(1 for ts, _ in self.rows if any(a <= ts <= b for a, b in self.spans))
 
     def __exit__(self, *a):
         if self.proc:
-            time.sleep(0.15)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self) -> dict:
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for ts, r in self.rows if any(a <= ts <= b for a, b in self.spans)] if self.spans else [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "samples_total": len(self.rows)}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args) -> None:
     """The reference's own CPU implementation of the path, timed on this box's host cores.  The
     reference x86 codegen cannot be built here (ISL+Halide+LLVM), so this is the oracle
-    port (kind 'port') with all host threads; each step is a bounded sample: the full heat2d+blur
-    sweep on a GRID x GRID/4-row slab (1/4 of the grid's rows)."""
+    port (kind 'port') on ALL host cores (set explicitly: torchrun exports OMP_NUM_THREADS=1 to its
+    ranks); each step is a bounded sample: the full heat2d+blur sweep on a GRID x GRID/4-row slab.
+    Under torchrun rank 0 alone runs; the other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    claim_stdout()
     from oracle import oracle
+    cores = oracle.set_num_threads(None)
     rows = max(64, GRID // 4)
     rng = np.random.default_rng(1)
     a = rng.random((rows, GRID), dtype=np.float32)
+    oh, ob = np.zeros_like(a), np.zeros((rows - 2, GRID - 2), np.float32)     # preallocated and touched
     for _ in range(max(1, min(args.warmup, 2))):
-        oracle.heat2d(a, "cpu"); oracle.blur_f32(a)
-    t0 = time.perf_counter()
+        oracle.heat2d(a, "cpu", oh); oracle.blur_f32(a, ob)
+    ts = []
     for _ in range(args.steps):
-        oracle.heat2d(a, "cpu"); oracle.blur_f32(a)
-    dt = (time.perf_counter() - t0) / args.steps
+        t0 = time.perf_counter()
+        oracle.heat2d(a, "cpu", oh); oracle.blur_f32(a, ob)
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.mean(ts))
     val = alg_bytes(rows, GRID)["step"] / dt / 1e9
+    # one-core number on a smaller slab (BASELINE.md section 3 asks for both)
+    oracle.set_num_threads(1)
+    r1 = max(64, GRID // 64)
+    a1 = a[:r1].copy()
+    oracle.heat2d(a1, "cpu", oh[:r1]); oracle.blur_f32(a1, ob[:r1 - 2])
+    t0 = time.perf_counter()
+    oracle.heat2d(a1, "cpu", oh[:r1]); oracle.blur_f32(a1, ob[:r1 - 2])
+    one = alg_bytes(r1, GRID)["step"] / (time.perf_counter() - t0) / 1e9
+    oracle.set_num_threads(None)
+    configs = None
+    if not args.no_others:
+        try:
+            from tools import bench_configs
+            configs = bench_configs.run_cpu_reference(args.steps)
+        except Exception as e:  # context only
+            configs = {"error": repr(e)}
     line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"heat2d + 3x3 blur fp32, {GRID}x{GRID} grid (BASELINE configs[1])"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-                             "sample": f"{rows} of {GRID} rows x {GRID} cols per step, {args.steps} steps"},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+            "config": bench_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{rows} of {GRID} rows x {GRID} cols per step, {args.steps} steps (mean; median "
+                                       f"{alg_bytes(rows, GRID)['step'] / float(np.median(ts)) / 1e9:.1f})",
+                             "one_core": {"value": one, "unit": UNIT, "cores": 1, "sample": f"{r1} of {GRID} rows"},
+                             "host_cores": oracle.host_cores(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "configs": configs}
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -166,8 +239,9 @@ def per_kernel_ms(torch, stream, fn, iters=10):
 
 
 def run_ours(args) -> None:
-    # keep stdout to the one JSON line (NCCL prints its version banner there from NCCL_DEBUG=VERSION up)
-    os.environ.pop("NCCL_DEBUG", None)
+    # stdout stays the one JSON line; NCCL's log (NCCL_DEBUG, which the driver may set to check the
+    # communicator's rank count) goes to stderr with everything else libraries print
+    claim_stdout()
     if os.environ.get("TB200_NCCL_DEBUG"):
         os.environ["NCCL_DEBUG"] = os.environ["TB200_NCCL_DEBUG"]
     import torch
@@ -271,6 +345,7 @@ def run_ours(args) -> None:
     # (stencil.cu: Halo).  One launch per stencil per step, like N = 1.  TB200_HALO=nccl keeps the
     # NCCL exchange above as the timed step; its time is reported next to the peer one either way.
     halo_mode = os.environ.get("TB200_HALO", "peer") if world > 1 else "none"
+    sym = ref_heat = ref_blur = None
     nccl_step_ms = None
     halo_fallback = None
     if halo_mode == "peer":
@@ -334,28 +409,47 @@ def run_ours(args) -> None:
 
     launches0 = api.kernel_launches()
     with ClockSampler(local) as clk:
+        clk.wait_started()             # nvidia-smi takes a second or more to come up on a multi-GPU box
+        t_load0 = time.monotonic()
         ms = time_steps(torch, stream, step, args.steps, args.warmup, world)
         launches = (api.kernel_launches() - launches0) * world // (args.steps + args.warmup) * args.steps
         heat_ms, heat_best = per_kernel_ms(torch, stream, heat)
         blur_ms, blur_best = per_kernel_ms(torch, stream, blur)
-        for _ in range(30):            # keep the GPU under the same load while nvidia-smi samples (100 ms period)
+        # keep the GPU under the same load for ~0.8 s so that nvidia-smi (50 ms period) samples it; the step count
+        # comes from the all-reduced `ms`, so every rank runs the same number (the NCCL-exchange step is collective)
+        n_keep = min(20000, int(800.0 / max(ms, 1e-3)) + 1)
+        for i in range(n_keep):
             step()
+            if i % 64 == 63:
+                stream.synchronize()
+                clk.mark(t_load0, time.monotonic())
         stream.synchronize()
+        clk.mark(t_load0, time.monotonic())
+        if world > 1:
+            torch.distributed.barrier()
     bytes_step = alg_bytes(N, N)["step"]
     value = bytes_step / (ms * 1e-3) / 1e9
 
     heat_bytes = 2 * (r1 - r0) * N * 4
     blur_bytes = 4 * ((b1 - b0) * (N - 2) + (b1 - b0 + 2) * N)
     peak = float(peaks["hbm_gbs"])
-    roof = {"kernel": "tiramisu_sm100_heat2d_v4", "bound": "hbm", "achieved": heat_bytes / (heat_ms * 1e-3) / 1e9,
-            "peak": peak, "unit": "GB/s", "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-            "traffic": ncu_traffic("r01_heat2d_ncu_full.txt") if world == 1 else None,
-            "traffic_source": "profiles/r01_heat2d_ncu_full.txt (ncu --set full, 16384^2, one launch)",
-            "algorithmic_bytes": heat_bytes, "ms": heat_ms}
-    roof["frac"] = roof["achieved"] / peak
-    kernels = {"heat2d": {"ms": heat_ms, "best_ms": heat_best, "GBps": roof["achieved"], "frac": roof["frac"]},
-               "blur_f32": {"ms": blur_ms, "best_ms": blur_best, "GBps": blur_bytes / (blur_ms * 1e-3) / 1e9,
-                            "frac": blur_bytes / (blur_ms * 1e-3) / 1e9 / peak}}
+    heat_gbs, blur_gbs = heat_bytes / (heat_ms * 1e-3) / 1e9, blur_bytes / (blur_ms * 1e-3) / 1e9
+    kernels = {"heat2d": {"kernel": "tiramisu_sm100_heat2d_v4", "ms": heat_ms, "best_ms": heat_best, "GBps": heat_gbs,
+                          "frac": heat_gbs / peak, "algorithmic_bytes": heat_bytes,
+                          "traffic": ncu_traffic(HEAT_NCU) if world == 1 else None, "traffic_source": f"profiles/{HEAT_NCU}"},
+               "blur_f32": {"kernel": "tiramisu_sm100_blur_f32_v4", "ms": blur_ms, "best_ms": blur_best, "GBps": blur_gbs,
+                            "frac": blur_gbs / peak, "algorithmic_bytes": blur_bytes,
+                            "traffic": ncu_traffic(BLUR_NCU) if world == 1 else None, "traffic_source": f"profiles/{BLUR_NCU}"}}
+    # the roofline object describes the DOMINANT kernel of the step = the one with the longer launch
+    dom = "blur_f32" if blur_ms >= heat_ms else "heat2d"
+    roof = {"kernel": kernels[dom]["kernel"], "bound": "hbm", "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": kernels[dom]["frac"], "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+            "traffic": kernels[dom]["traffic"],
+            "traffic_source": kernels[dom]["traffic_source"] + " (ncu --set full, 16384^2, one launch)",
+            "algorithmic_bytes": kernels[dom]["algorithmic_bytes"], "ms": kernels[dom]["ms"],
+            "share_of_step": kernels[dom]["ms"] / (heat_ms + blur_ms),
+            "step": {"achieved": (heat_bytes + blur_bytes) / ((heat_ms + blur_ms) * 1e-3) / 1e9,
+                     "frac": (heat_bytes + blur_bytes) / ((heat_ms + blur_ms) * 1e-3) / 1e9 / peak}}
     if exchange:
         ex_ms, _ = per_kernel_ms(torch, stream, exchange)
         kernels["halo_exchange_nccl"] = {"ms": ex_ms, "bytes_per_rank": 3 * row_b * (2 if 0 < rank < world - 1 else 1),
@@ -402,39 +496,59 @@ def run_ours(args) -> None:
     cpu = None
     if world == 1 and not args.no_cpu:
         from oracle import oracle
+        cores = oracle.set_num_threads(None)
         rows = max(64, N // 4)
         a = np.random.default_rng(1).random((rows, N), dtype=np.float32)
-        oracle.heat2d(a, "cpu"); oracle.blur_f32(a)
+        oh, ob = np.zeros_like(a), np.zeros((rows - 2, N - 2), np.float32)    # preallocated and touched
+        oracle.heat2d(a, "cpu", oh); oracle.blur_f32(a, ob)
         reps = 3
         t0 = time.perf_counter()
         for _ in range(reps):
-            oracle.heat2d(a, "cpu"); oracle.blur_f32(a)
+            oracle.heat2d(a, "cpu", oh); oracle.blur_f32(a, ob)
         dt = (time.perf_counter() - t0) / reps
-        cpu = {"value": alg_bytes(rows, N)["step"] / dt / 1e9, "unit": UNIT, "cores": oracle.num_threads(),
-               "kind": "port", "sample": f"{rows} of {N} rows x {N} cols, {reps} reps"}
+        oracle.set_num_threads(1)
+        r1c = max(64, N // 64)
+        a1 = a[:r1c].copy()
+        oracle.heat2d(a1, "cpu", oh[:r1c]); oracle.blur_f32(a1, ob[:r1c - 2])
+        t0 = time.perf_counter()
+        oracle.heat2d(a1, "cpu", oh[:r1c]); oracle.blur_f32(a1, ob[:r1c - 2])
+        one = alg_bytes(r1c, N)["step"] / (time.perf_counter() - t0) / 1e9
+        oracle.set_num_threads(None)
+        cpu = {"value": alg_bytes(rows, N)["step"] / dt / 1e9, "unit": UNIT, "cores": cores,
+               "kind": "port", "sample": f"{rows} of {N} rows x {N} cols, {reps} reps",
+               "one_core": {"value": one, "unit": UNIT, "cores": 1, "sample": f"{r1c} of {N} rows"}}
+        del a, a1, oh, ob
 
-    others = None
-    if world == 1 and not args.no_others:
+    # ---- the other BASELINE configs (sgemm 1024^3, conv block, LSTM, sgemm sweep): every rank takes part
+    configs = None
+    if not args.no_others:
+        del d_loc, d_in, d_heat, d_blur, h_in, h_heat, h_blur, ref_heat, ref_blur
+        if halo_mode == "peer":
+            stream.synchronize()
+            sym.free()
+            sym = None
+        torch.cuda.empty_cache()
+        from tools import bench_configs
         try:
-            from tools import bench_others
-            others = bench_others.run(torch, stream, peaks)
-        except Exception as e:  # context only; never fail the headline
-            others = {"error": repr(e)}
+            configs = bench_configs.run(torch, stream, peaks, world, rank, cpu=not args.no_cpu,
+                                        only=args.only.split(",") if args.only else None, quick=args.quick)
+        except Exception as e:  # context only; never fail the headline (a collective failure re-raises inside)
+            configs = {"error": repr(e)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"heat2d + 3x3 blur fp32, {N}x{N} grid (BASELINE configs[1])",
-                           "sharding": f"rows/{world}" + ({"peer": ", halo rows read in place from the neighbours' HBM over NVLink peer mappings inside the sweep kernels (no exchange step)",
-                                                            "nccl": ", halo exchange over NCCL each step, overlapped with the interior rows"}.get(halo_mode, "")),
-                           "l2": "inputs (1 GiB / n_gpus per rank) >> L2, no flush",
-                           **({"halo_fallback": halo_fallback} if halo_fallback else {})},
+                "config": bench_config(world),
+                "halo": {"peer": "halo rows read in place from the neighbours' HBM over NVLink peer mappings inside the sweep kernels (no exchange step)",
+                         "nccl": "halo exchange over NCCL each step, overlapped with the interior rows",
+                         "none": "single GPU"}.get(halo_mode, halo_mode),
+                **({"halo_fallback": halo_fallback} if halo_fallback else {}),
                 "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clk.summary(), "others": others}
-        print(json.dumps(line))
+                "gpu_launches": int(launches), "clocks": clk.summary(), "configs": configs}
+        emit(line)
     if world > 1:
-        if halo_mode == "peer":
+        if halo_mode == "peer" and sym is not None:
             stream.synchronize()
             sym.free()
         tdist.comm_destroy()
@@ -449,6 +563,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated prefixes of the entries of `configs` to run")
+    ap.add_argument("--quick", action="store_true", help="shorter sgemm sweep (development runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -42,11 +42,30 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
-def heat2d(inp: np.ndarray, form: str = "cpu") -> np.ndarray:
-    """form: 'cpu' = heat2d_tiramisu.cpp:68, 'gpu' = heat2dgpu_tiramisu.cpp:54."""
+def host_cores() -> int:
+    """Cores this process may run on (the GPU box's host cores as the scheduler gives them to us)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_num_threads(n: int | None = None) -> int:
+    """OpenMP threads for every oracle entry point; None = all host cores.  torchrun exports
+    OMP_NUM_THREADS=1, which must not reach a CPU baseline that claims 'all cores'."""
+    n = host_cores() if n is None else int(n)
+    lib().oracle_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
+def heat2d(inp: np.ndarray, form: str = "cpu", out: np.ndarray | None = None) -> np.ndarray:
+    """form: 'cpu' = heat2d_tiramisu.cpp:68, 'gpu' = heat2dgpu_tiramisu.cpp:54.  `out`: a preallocated
+    (already touched) result array, so that a timed call does not pay page faults for a fresh one."""
     inp = np.ascontiguousarray(inp, dtype=np.float32)
     H, W = inp.shape
-    out = np.empty_like(inp)
+    if out is None:
+        out = np.empty_like(inp)
+    assert out.shape == inp.shape and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
     fn = {"cpu": lib().oracle_heat2d, "gpu": lib().oracle_heat2dgpu}[form]
     fn(_p(inp), _p(out), C.c_int(H), C.c_int(W))
     return out
@@ -76,10 +95,12 @@ def boxblur_u32(inp: np.ndarray) -> np.ndarray:
     return out
 
 
-def blur_f32(inp: np.ndarray) -> np.ndarray:
+def blur_f32(inp: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
     inp = np.ascontiguousarray(inp, dtype=np.float32)
     H, W = inp.shape
-    out = np.empty((H - 2, W - 2), dtype=np.float32)
+    if out is None:
+        out = np.empty((H - 2, W - 2), dtype=np.float32)
+    assert out.shape == (H - 2, W - 2) and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
     lib().oracle_blur_f32(_p(inp), _p(out), C.c_int(H), C.c_int(W))
     return out
 
@@ -94,6 +115,19 @@ def sgemm(a: float, b: float, A: np.ndarray, B: np.ndarray, Cm: np.ndarray) -> n
     assert K == K2 and out.shape == (N, M)
     lib().oracle_sgemm(C.c_int(N), C.c_int(M), C.c_int(K), C.c_float(a), C.c_float(b),
                        _p(A), _p(B), _p(out))
+    return out
+
+
+def sgemm_sched(a: float, b: float, A: np.ndarray, B: np.ndarray, Cm: np.ndarray) -> np.ndarray:
+    """oracle.sgemm under the reference's CPU schedule (tiled, 8-wide lanes over j): same bits, timed by bench.py."""
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    out = np.array(Cm, dtype=np.float32, order="C", copy=True)
+    N, K = A.shape
+    K2, M = B.shape
+    assert K == K2 and out.shape == (N, M)
+    lib().oracle_sgemm_sched(C.c_int(N), C.c_int(M), C.c_int(K), C.c_float(a), C.c_float(b),
+                             _p(A), _p(B), _p(out))
     return out
 
 

@@ -45,6 +45,17 @@ int oracle_num_threads(void)
 #endif
 }
 
+/* Launchers such as torchrun export OMP_NUM_THREADS=1 to every rank; the CPU baseline legs of
+ * bench.py set the thread count explicitly (all host cores, or 1 for the single-thread number). */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ heat2d
  * benchmarks/halide/heat2d_tiramisu.cpp:52-69
  *   heat2d_s0: out[y][x] = 0 for all y,x                       (:52-56)
@@ -231,6 +242,59 @@ void oracle_sgemm(int N, int M, int K, float a, float b,
         }
         free(acc);
     }
+}
+
+/* The same statement triple under (a restatement of) the reference's CPU schedule — parallel outer i
+ * tile, register-blocked rows, 8-wide vector lanes over j (sgemm_generator.cpp:73-79 L2 tiles 64x32x32,
+ * :132-138 parallel, :273-289 unroll/vectorize) — used as the *timed* CPU baseline of bench.py.  Per
+ * output element k still runs 0..K-1 with the product rounded before the add, so the result is
+ * bit-identical to oracle_sgemm (checked in tests/test_oracle.py).
+ */
+#define SG_TI 4
+#define SG_TJ 64
+void oracle_sgemm_sched(int N, int M, int K, float a, float b,
+                        const float *restrict A, const float *restrict B, float *restrict C)
+{
+    const int nti = (N + SG_TI - 1) / SG_TI, ntj = (M + SG_TJ - 1) / SG_TJ;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int ti = 0; ti < nti; ti++)
+        for (int tj = 0; tj < ntj; tj++) {
+            const int i0 = ti * SG_TI, j0 = tj * SG_TJ;
+            const int ni = N - i0 < SG_TI ? N - i0 : SG_TI, nj = M - j0 < SG_TJ ? M - j0 : SG_TJ;
+            float acc[SG_TI][SG_TJ];
+            for (int ii = 0; ii < SG_TI; ii++)
+                for (int jj = 0; jj < SG_TJ; jj++) acc[ii][jj] = 0.0f;
+            if (ni == SG_TI && nj == SG_TJ) {
+                for (int k = 0; k < K; k++) {
+                    const float *restrict brow = B + (size_t)k * M + j0;
+                    for (int ii = 0; ii < SG_TI; ii++) {
+                        const float aik = A[IDX2(i0 + ii, k, K)];
+#pragma omp simd
+                        for (int jj = 0; jj < SG_TJ; jj++) {
+                            float p = aik * brow[jj];
+                            acc[ii][jj] = acc[ii][jj] + p;
+                        }
+                    }
+                }
+            } else {
+                for (int k = 0; k < K; k++) {
+                    const float *brow = B + (size_t)k * M + j0;
+                    for (int ii = 0; ii < ni; ii++) {
+                        const float aik = A[IDX2(i0 + ii, k, K)];
+                        for (int jj = 0; jj < nj; jj++) {
+                            float p = aik * brow[jj];
+                            acc[ii][jj] = acc[ii][jj] + p;
+                        }
+                    }
+                }
+            }
+            for (int ii = 0; ii < ni; ii++)
+                for (int jj = 0; jj < nj; jj++) {
+                    float t0 = a * acc[ii][jj];
+                    float t1 = b * C[IDX2(i0 + ii, j0 + jj, M)];
+                    C[IDX2(i0 + ii, j0 + jj, M)] = t0 + t1;
+                }
+        }
 }
 
 /* Row-major C[MxN] = alpha*op(A)*op(B) + beta*C with leading dimensions, element
