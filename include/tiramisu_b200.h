@@ -169,6 +169,8 @@ int tiramisu_b200_set_lstm_mode(int mode);
  * step barrier), 3 = persistent layer kernel, K split across 4-CTA clusters with a distributed-
  * shared-memory reduction (F % 128 == 0, B <= 64). */
 int tiramisu_b200_set_lstm_kernel(int kernel);
+/* Description of the engine (and operand type) the calling thread's last tiramisu_b200_lstm call ran on. */
+const char *tiramisu_b200_lstm_last_engine(void);
 
 /* ===================================================================== B2: distributed runtime
  * NCCL over NVLink, one process per GPU, replacing src/tiramisu_mpi.cpp (MPI point-to-point).
@@ -220,6 +222,17 @@ TIRAMISU_B200_MPI_DECL(f64, double)
 int heat2d_tiramisu(halide_buffer_t *in, halide_buffer_t *out);
 /* benchmarks/halide/wrapper_heat2dgpu.cpp:44 — sizes i32[2] = {extent0 (W), extent1 (H)}. */
 int heat2dgpu_tiramisu(halide_buffer_t *sizes, halide_buffer_t *in, halide_buffer_t *out);
+/* benchmarks/halide/wrapper_heat2d_dist.h:23 / heat2d_dist_tiramisu.cpp:187-188,253 — one call per rank
+ * (communicator up: tiramisu_MPI_init), buff_out_even f32[rows+2][M], buff_out_odd f32[rows+2][M] with local
+ * rows 1..rows owned and rows 0 / rows+1 halos; ITERS even/odd Jacobi sweeps (form 2), result in buff_out_odd.
+ * Only ->host is read (the reference's wrapper leaves every other field uninitialised).  Sizes default to the
+ * reference's N = 3842, M = 10000 split over the communicator; see tiramisu_b200_set_heat2d_dist. */
+int heat2d_dist_tiramisu(halide_buffer_t *buff_out_even, halide_buffer_t *buff_out_odd);
+/* rows_per_rank (0: (3842-2)/world), cols (0: keep), iters (0: keep; default 2 = TOTAL_ITERATIONS), protocol:
+ * 0 = the generator's (ITERS even, the first sweep reads buff_out_odd), 1 = the wrapper's (the first sweep reads
+ * the first argument; ITERS = 1 gives out = sweep(in), what wrapper_heat2d_dist.cpp:101-111 checks).
+ * Environment overrides: TB200_HEAT2D_DIST_ROWS / _COLS / _ITERS / _PROTOCOL. */
+int tiramisu_b200_set_heat2d_dist(int32_t rows_per_rank, int32_t cols, int32_t iters, int32_t protocol);
 /* benchmarks/halide/wrapper_blurxy.cpp:21 — in u8[3][H][W], out u8[3][H-8][W-8]. */
 int blurxy_tiramisu(halide_buffer_t *in, halide_buffer_t *out);
 /* fp32 blur of BASELINE config 2 (SURVEY.md §8 a8'): in f32[H][W], out f32[H-2][W-2]. */

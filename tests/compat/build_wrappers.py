@@ -24,6 +24,8 @@ CUDA = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 WRAPPERS = {
     "wrapper_heat2d": ("benchmarks/halide/wrapper_heat2d.cpp", ["benchmarks/halide"], []),
     "wrapper_heat2dgpu": ("benchmarks/halide/wrapper_heat2dgpu.cpp", ["benchmarks/halide"], []),
+    # MPI program: one process per rank (tests/compat/include/mpi.h maps its MPI calls onto tiramisu_MPI_*)
+    "wrapper_heat2d_dist": ("benchmarks/halide/wrapper_heat2d_dist.cpp", ["benchmarks/halide"], ["-DTOTAL_ITERATIONS=2"]),
     "sgemm_wrapper": ("benchmarks/linear_algebra/blas/level3/sgemm/cpu/sgemm_wrapper.cpp",
                       ["benchmarks/linear_algebra/blas/level3/sgemm/cpu"], []),
     "sgemm_gpu_wrapper": ("benchmarks/linear_algebra/blas/level3/sgemm/gpu/wrapper.cpp",

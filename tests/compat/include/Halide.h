@@ -8,6 +8,7 @@
 
 #include "HalideBuffer.h"
 
+#include <cmath>
 #include <string>
 #include <vector>
 

@@ -141,3 +141,121 @@ def test_peer_halo_descriptors():
         # I am my upper neighbour's lower neighbour: I write its flags[1]; and my lower neighbour's flags[0]
         assert (h.sig_up or 0) == (flags(rank - 1) + 4 if rank > 0 else 0)
         assert (h.sig_dn or 0) == (flags(rank + 1) if rank < world - 1 else 0)
+
+
+# ---- peer-halo protocol, emulated on the CPU: shared memory plays the symmetric (CUDA IPC) block ----------------
+def _jacobi_worker(rank, world, port, H, W, iters, q):
+    """What a rank does on the GPU box (tools/dist_check.py section 5b, heat2d_dist.cu), with numpy in place of
+    the sweep kernel: blocks of all ranks live in shared mappings (`multiprocessing.shared_memory` stands in for
+    cudaIpcOpenMemHandle), descriptors come from dist.SymmetricRows.halo(sync=True), a sweep waits on its own flag
+    words, reads the neighbours' boundary rows IN PLACE and publishes its sweep count into the neighbours' flags."""
+    import ctypes as C
+    import time
+    from multiprocessing import shared_memory
+
+    import torch.distributed as dist
+    from oracle import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shms = []
+    try:
+        rows_of = lambda r: tdist.row_shard(H, world, r)      # noqa: E731
+        rows_max = max(rows_of(r)[1] - rows_of(r)[0] for r in range(world))
+        s = object.__new__(tdist.SymmetricRows)
+        s.world, s.rank, s.width, s.n_buffers = world, rank, W, 2
+        s.block_bytes = ((rows_max * W * 4 + 255) // 256) * 256
+        s.bytes = s.block_bytes * 2 + tdist.SymmetricRows.FLAG_BYTES
+        mine = shared_memory.SharedMemory(create=True, size=s.bytes)
+        shms.append(mine)
+        mine.buf[:] = bytes(s.bytes)
+        names = [None] * world
+        dist.all_gather_object(names, mine.name)              # the "IPC handles"
+        maps = []
+        for r in range(world):
+            m = mine if r == rank else shared_memory.SharedMemory(name=names[r])
+            if r != rank:
+                shms.append(m)
+            maps.append(m)
+        base = [C.addressof(C.c_char.from_buffer(m.buf)) for m in maps]
+        s.local, s.peers = base[rank], base
+
+        def rows_at(addr, n):                                 # float rows at an absolute address inside some rank's block
+            return np.ctypeslib.as_array((C.c_float * (n * W)).from_address(addr)).reshape(n, W)
+
+        def word(addr):
+            return C.c_int32.from_address(addr)
+
+        r0, r1 = rows_of(rank)
+        grid = np.random.default_rng(11).random((H, W), dtype=np.float32)
+        for b in range(2):
+            rows_at(s.buffer(b), r1 - r0)[:] = grid[r0:r1]
+        dist.barrier()
+        for t in range(iters):
+            a, b = t % 2, (t + 1) % 2
+            h = s.halo(a, r0, r1, rows_of, sync=True, wait_value=t, signal_value=t + 1)
+            deadline = time.time() + 60
+            for has, off in ((h.up, 0), (h.dn, 4)):           # halo_wait (stencil.cu): flags[0] / flags[1] >= wait_value
+                while has and word(h.flags + off).value < h.wait_value:
+                    assert time.time() < deadline, "handshake timed out"
+                    time.sleep(0.0005)
+            src = np.zeros((r1 - r0 + 2, W), np.float32)
+            src[1:-1] = rows_at(s.buffer(a), r1 - r0)
+            if h.up:
+                src[0] = rows_at(h.up, 1)[0]                  # row r0-1, read in place from the upper neighbour
+            if h.dn:
+                src[-1] = rows_at(h.dn, 1)[0]                 # row r1, read in place from the lower neighbour
+            dst = np.zeros_like(src)
+            dst[1:-1] = rows_at(s.buffer(b), r1 - r0)
+            oracle.heat2d_step(src, dst)                      # interior of `dst` only (Jacobi half-step)
+            own = dst[1:-1].copy()
+            if rank == 0:
+                own[0] = rows_at(s.buffer(b), 1)[0]           # global border rows are not computed
+            if rank == world - 1:
+                own[-1] = rows_at(s.buffer(b), r1 - r0)[-1]
+            rows_at(s.buffer(b), r1 - r0)[:] = own
+            if h.sig_up:                                      # halo_signal: publish this rank's sweep count
+                word(h.sig_up).value = h.signal_value
+            if h.sig_dn:
+                word(h.sig_dn).value = h.signal_value
+        dist.barrier()
+        q.put((rank, r0, rows_at(s.buffer(iters % 2), r1 - r0).copy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+        del s
+        for m in shms:
+            try:
+                m.close()
+            except BufferError:
+                pass
+        try:
+            shms[0].unlink()
+        except Exception:
+            pass
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_halo_handshake_protocol_emulated(world):
+    import torch.multiprocessing as mp
+    from oracle import oracle
+    H, W, iters = 23, 16, 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_jacobi_worker, args=(r, world, port, H, W, iters, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    grid = np.random.default_rng(11).random((H, W), dtype=np.float32)
+    ev, od = grid.copy(), grid.copy()
+    for t in range(iters):
+        if t % 2 == 0:
+            oracle.heat2d_step(ev, od)
+        else:
+            oracle.heat2d_step(od, ev)
+    want = ev if iters % 2 == 0 else od
+    assert np.array_equal(np.concatenate([g[2] for g in got]), want)

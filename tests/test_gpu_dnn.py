@@ -21,6 +21,40 @@ def _rel(got, want):
     return float(np.abs(got.astype(np.float64) - want).max() / max(1e-30, np.abs(want).max()))
 
 
+def assert_conv_tf32_close(got, want, inp, filt, bias):
+    """ELEMENT-WISE relative check of a TF32 tensor-core result (north_star: 1e-2 relative for TF32 paths).
+    scale_i = what was summed for element i in absolute value, sum |in|*|w| + |bias| (through the same
+    max-pool), i.e. the quantity a dot product's rounding error is relative to; every element must satisfy
+    |got_i - want_i| <= 1e-2 * scale_i, and every well-conditioned element (|want_i| >= 0.1 * scale_i: no
+    cancellation) must satisfy the plain |got_i - want_i| <= 1e-2 * |want_i|."""
+    scale = oracle.conv_relu_maxpool(np.abs(inp), np.abs(filt), np.abs(bias)).astype(np.float64)
+    d = np.abs(got.astype(np.float64) - want)
+    assert np.isfinite(got).all()
+    worst = float((d / np.maximum(scale, 1e-30)).max())
+    assert (d <= TF32_RTOL * scale).all(), f"max |d|/scale = {worst:.3e}"
+    well = np.abs(want) >= 0.1 * scale
+    rel = d[well] / np.abs(want[well])
+    assert well.any() and (rel <= TF32_RTOL).all(), f"max element-wise relative error {float(rel.max()):.3e}"
+
+
+def assert_lstm_tf32_close(got, want, what=""):
+    """ELEMENT-WISE: |got_i - want_i| <= 1e-2 * |want_i| + 2e-3.  h = tanh(c) * o lies in (-1, 1) and is a
+    difference of saturating terms, so an element near zero has no meaningful relative error: the absolute term
+    is the TF32 unit round-off (2^-11 = 4.9e-4) of pre-activations of magnitude <= 4 passed through gates of
+    slope <= 1."""
+    assert np.isfinite(got).all(), what
+    d = np.abs(got.astype(np.float64) - want)
+    lim = TF32_RTOL * np.abs(want) + 2e-3
+    assert (d <= lim).all(), f"{what}: {int((d > lim).sum())} of {d.size} elements outside rtol=1e-2, atol=2e-3; max |d| = {float(d.max()):.3e}"
+
+
+def correctness_pct(got, want, tol, strict):
+    """The reference wrappers' own protocol: percentage of elements within an absolute tolerance
+    (wrapper_nn_block.cpp:84-90: <= 1e-4; LSTM/cpu/wrapper.cpp:103-108: < 0.02)."""
+    d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    return 100.0 * float(((d < tol) if strict else (d <= tol)).mean())
+
+
 def _conv(api, inp, filt, bias):
     B, NP, _, FIn = inp.shape
     FB = filt.shape[0]
@@ -70,7 +104,7 @@ def test_conv_tensor_path_wrapper_data(api, B, N, FIn):
         inp, filt, bias = refdata.conv_inputs(B, N, FIn, 64)
         got = _conv(api, inp, filt, bias)
         want = oracle.conv_relu_maxpool(inp, filt, bias)
-        assert _rel(got, want) < TF32_RTOL
+        assert_conv_tf32_close(got, want, inp, filt, bias)
         assert (got >= 0).all()
     finally:
         api.set_conv_mode(prev)
@@ -95,8 +129,30 @@ def test_conv_config3_full_size(api):
         api.set_stream(None)
     assert bool(torch.isfinite(d_out).all())
     for n in (0, 31):
-        want = oracle.conv_relu_maxpool(d_in[n:n + 1].cpu().numpy(), filt, bias)
-        assert _rel(d_out[n:n + 1].cpu().numpy(), want) < TF32_RTOL
+        img = d_in[n:n + 1].cpu().numpy()
+        want = oracle.conv_relu_maxpool(img, filt, bias)
+        assert_conv_tf32_close(d_out[n:n + 1].cpu().numpy(), want, img, filt, bias)
+
+
+@pytest.mark.parametrize("name,B,N,FIn,FOut", [("conv_default", 2, 32, 3, 32), ("conv_config3", 2, 32, 64, 64)])
+def test_conv_vs_independent_fp64_golden(api, name, B, N, FIn, FOut):
+    """tests/golden/conv_*_out.npy: PyTorch fp64 conv2d+relu+max_pool2d on the wrapper's own srand(1) data
+    (tools/make_golden_dnn.py).  Exact mode under the reference wrapper's protocol (100 % of the elements within
+    1e-4, wrapper_nn_block.cpp:84-90); the TF32 path element-wise within 1e-2."""
+    import os
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_out.npy"))
+    inp, filt, bias = refdata.conv_inputs(B, N, FIn, FOut)
+    prev = api.set_conv_mode(1)
+    try:
+        assert correctness_pct(_conv(api, inp, filt, bias), want, 1e-4, strict=False) == 100.0
+    finally:
+        api.set_conv_mode(prev)
+    if FIn % 32 == 0 and FOut == 64:
+        prev = api.set_conv_mode(2)
+        try:
+            assert_conv_tf32_close(_conv(api, inp, filt, bias), want.astype(np.float64), inp, filt, bias)
+        finally:
+            api.set_conv_mode(prev)
 
 
 # ------------------------------------------------------------------------------------------ LSTM
@@ -131,8 +187,7 @@ def test_lstm_tensor_path(api, F, B, L, T, scale):
         W, b, x = refdata.lstm_inputs(F, B, L, T, scale=scale)
         got = _lstm(api, W, b, x)
         want = oracle.lstm(W, b, x)
-        assert np.isfinite(got).all()
-        assert float(np.abs(got - want).max()) < TF32_RTOL * max(1.0, float(np.abs(want).max()))
+        assert_lstm_tf32_close(got, want, f"F={F} B={B} L={L} T={T}")
     finally:
         api.set_lstm_mode(prev)
 
@@ -155,8 +210,7 @@ def test_lstm_recurrence_engines(api, kernel, F, B, L, T, scale):
         W, b, x = refdata.lstm_inputs(F, B, L, T, scale=scale)
         got = _lstm(api, W, b, x)
         want = oracle.lstm(W, b, x)
-        assert np.isfinite(got).all()
-        assert float(np.abs(got - want).max()) < TF32_RTOL * max(1.0, float(np.abs(want).max()))
+        assert_lstm_tf32_close(got, want, f"F={F} B={B} L={L} T={T}")
     finally:
         api.set_lstm_mode(prev_m)
         api.set_lstm_kernel(prev_k)
@@ -199,8 +253,7 @@ def test_lstm_fp16_engine_config4(api, pipe, monkeypatch):
     if "want" not in _CFG4:
         _CFG4["want"] = oracle.lstm(W, b, x)
     want = _CFG4["want"]
-    assert np.isfinite(got).all()
-    assert float(np.abs(got - want).max()) < TF32_RTOL * max(1.0, float(np.abs(want).max()))
+    assert_lstm_tf32_close(got, want, f"config 4, pipe={pipe}")
     if "got" in _CFG4:
         assert np.array_equal(_CFG4["got"], got)
     _CFG4["got"] = got
@@ -213,3 +266,53 @@ def test_lstm_wrapper_data_saturated(api):
     want = oracle.lstm(W, b, x)
     # the reference itself accepts |diff| < 0.02 against MKL-DNN (cpu/wrapper.cpp:107)
     assert float(np.abs(got - want).max()) < 0.02
+
+
+@pytest.mark.parametrize("name,F,B,L,T,scale", [("lstm_readme", 32, 8, 4, 100, 1.0), ("lstm_scaled", 128, 16, 2, 10, 8.0)])
+def test_lstm_vs_independent_fp64_golden(api, name, F, B, L, T, scale):
+    """tests/golden/lstm_*_y.npy: a hand-rolled fp64 PyTorch LSTM (gate order i, z, o, f) on the wrapper's own
+    srand(0) data (tools/make_golden_dnn.py), checked with the reference wrapper's protocol — 100 % of the
+    elements within 0.02 (LSTM/cpu/wrapper.cpp:103-108) — for the exact path and for the default engine."""
+    import os
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_y.npy"))
+    W, b, x = refdata.lstm_inputs(F, B, L, T, scale=scale)
+    for mode in (1, 0):
+        prev = api.set_lstm_mode(mode)
+        try:
+            got = _lstm(api, W, b, x)
+        finally:
+            api.set_lstm_mode(prev)
+        assert correctness_pct(got, want, 0.02, strict=True) == 100.0, f"mode {mode}"
+        if scale > 1.0:
+            assert_lstm_tf32_close(got, want.astype(np.float64), f"{name} mode {mode}")
+
+
+@pytest.mark.parametrize("wscale", [1e5, 3e4, 1e-9])
+def test_lstm_fp16_engine_weight_range(api, wscale):
+    """The default engine stores R (and W above layer 0) as block-scaled fp16 (lstm.cu: one power-of-two scale per
+    matrix, undone in the epilogues).  Layer 1's weights are put far outside fp16's own range — |w| ~ 1e5 would be
+    inf, |w| ~ 1e-9 would be 0 — and must neither overflow nor vanish:
+      * large weights saturate every gate of layer 1, rounding differences flip a few outputs between 0 and
+        +-tanh(k): the reference wrapper's protocol is used (percentage of elements within 0.02,
+        LSTM/cpu/wrapper.cpp:103-108), T = 2 so that flips cannot cascade;
+      * tiny weights (zero bias) make layer 1's output tiny and linear in its weights: a flush to zero would be
+        a 100 % error; the check is relative to the largest output (~1e-9)."""
+    F, B, L, T = 256, 64, 2, 2
+    W, b, x = refdata.lstm_inputs(F, B, L, T, scale=4.0)
+    W[1] = (W[1] * np.float32(4.0 * wscale)).astype(np.float32)
+    if wscale < 1:
+        b[1] = 0
+    want = oracle.lstm(W, b, x)
+    prev_m, prev_k = api.set_lstm_mode(2), api.set_lstm_kernel(4)
+    try:
+        got = _lstm(api, W, b, x)
+    finally:
+        api.set_lstm_mode(prev_m)
+        api.set_lstm_kernel(prev_k)
+    assert np.isfinite(got).all()
+    if wscale > 1:
+        assert correctness_pct(got, want, 0.02, strict=True) >= 98.0
+    else:
+        top = float(np.abs(want).max())
+        assert 0 < top < 1e-6
+        assert float(np.abs(got - want).max()) <= TF32_RTOL * top

@@ -18,8 +18,25 @@ def test_sharded_paths_match_oracle_on_two_or_more_gpus():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
-    world = 2 if n < 4 else 4
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)          # all the GPUs the box has (power of two)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", "29733", os.path.join(ROOT, "tools", "dist_check.py")],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, (r.stdout + r.stderr)[-4000:]
+
+
+@pytest.mark.gpu
+def test_reference_heat2d_dist_wrapper_unmodified():
+    """benchmarks/halide/wrapper_heat2d_dist.cpp compiled UNMODIFIED (tests/compat/include/mpi.h maps its MPI
+    calls onto tiramisu_MPI_*), one process per GPU, 4 ranks as wrapper_heat2d_dist.h:16 (NUM_CPU_RANKS) says:
+    its own check (:101-111, one sweep of the all-ones block, tolerance 0.01) asserts inside the program."""
+    import torch
+    exe = os.path.join(ROOT, "tests", "compat", "_bin", "wrapper_heat2d_dist")
+    if not os.path.exists(exe):
+        pytest.skip("wrapper binaries are built where /root/reference exists (tests/compat/build_wrappers.py)")
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    env = dict(os.environ, TB200_HEAT2D_DIST_PROTOCOL="1", TB200_HEAT2D_DIST_ITERS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_ranks.py"), "4", exe], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]

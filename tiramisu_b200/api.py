@@ -32,6 +32,19 @@ def heat2dgpu_tiramisu(sizes, inp, out):
     _call("heat2dgpu_tiramisu", sizes, inp, out)
 
 
+def heat2d_dist_tiramisu(buff_out_even, buff_out_odd, rows_per_rank=None, iters=None, protocol=None):
+    """benchmarks/halide/wrapper_heat2d_dist.cpp:69 — one call per rank under a communicator
+    (tiramisu_MPI_init / dist.comm_init_from_torch): host arrays f32[rows+2][M], rows 1..rows owned.
+    Like the reference's wrapper, only the host pointers are passed (no extents in the halide_buffer_t);
+    rows_per_rank / iters / protocol go through tiramisu_b200_set_heat2d_dist (cols = the arrays' width)."""
+    from .halide import raw_host_only
+    if rows_per_rank is not None or iters is not None or protocol is not None:
+        _lib.check(_lib.lib().tiramisu_b200_set_heat2d_dist(rows_per_rank or 0, buff_out_even.shape[-1], iters or 0,
+                                                            protocol or 0), "tiramisu_b200_set_heat2d_dist")
+    a, b = raw_host_only(buff_out_even.ctypes.data), raw_host_only(buff_out_odd.ctypes.data)
+    _lib.check(_lib.lib().heat2d_dist_tiramisu(C.byref(a), C.byref(b)), "heat2d_dist_tiramisu")
+
+
 def blurxy_tiramisu(inp, out):
     """benchmarks/halide/wrapper_blurxy.cpp:21 — in u8[3][H][W], out u8[3][H-8][W-8]."""
     _call("blurxy_tiramisu", inp, out)

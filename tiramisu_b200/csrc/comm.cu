@@ -105,29 +105,72 @@ bool is_device_pointer(const void *p)
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-int p2p(bool send, void *data, size_t bytes, int peer)
+// Point-to-point messages.  NCCL needs sends and receives that must progress together to sit in ONE group, and
+// its operations are stream-ordered kernels, not host calls, so MPI's semantics are rebuilt like this:
+//   * the non-blocking calls (Isend / Issend / Irecv) only QUEUE the message; the queue is flushed as one
+//     ncclGroupStart/End by tiramisu_MPI_Wait, by any blocking call, by the barrier and by cleanup — an
+//     Irecv-first or bidirectional neighbour exchange therefore progresses as one group instead of deadlocking
+//     on the order of two stream-ordered kernels;
+//   * a blocking Send / Recv joins whatever is queued and flushes at once;
+//   * host buffers are staged through pooled device memory: a send's payload is copied (and the copy waited for)
+//     before the call returns, so the caller may reuse its buffer; a receive into host memory is copied back and
+//     waited for when its group is flushed.
+// Not supported (documented in INTEGRATION.md): tags are ignored — messages between one pair of ranks match in
+// issue order; a closed ring of *blocking* Sends issued before any Recv (legal with MPI's eager protocol) blocks.
+struct Pending {
+    bool send;
+    void *dev;          // device address handed to NCCL
+    size_t bytes;
+    int peer;
+    void *host;         // non-null: staged host buffer (copy back after a receive)
+    bool staged;        // dev comes from the pool
+};
+thread_local std::vector<Pending> t_pending;
+
+int flush_pending()
+{
+    if (t_pending.empty()) return 0;
+    Nccl &n = nccl();
+    int rc = 0;
+    if (g_comm.comm) {
+        rc |= nccl_check(n.GroupStart(), "ncclGroupStart");
+        for (const Pending &m : t_pending)
+            rc |= m.send ? nccl_check(n.Send(m.dev, m.bytes, ncclInt8, m.peer, g_comm.comm, stream()), "ncclSend")
+                         : nccl_check(n.Recv(m.dev, m.bytes, ncclInt8, m.peer, g_comm.comm, stream()), "ncclRecv");
+        rc |= nccl_check(n.GroupEnd(), "ncclGroupEnd");
+    } else {
+        rc = fail("tiramisu_MPI", "communicator not initialised");
+    }
+    bool host_recv = false;
+    for (const Pending &m : t_pending)
+        if (!m.send && m.host && !rc) { rc |= tiramisu_cuda_memcpy_to_host_async(m.host, m.dev, m.bytes); host_recv = true; }
+    if (host_recv && !rc) rc |= check(cudaStreamSynchronize(stream()), "tiramisu_MPI_Recv");   // data is in the caller's memory on return
+    for (const Pending &m : t_pending)
+        if (m.staged) pool_free(m.dev);
+    t_pending.clear();
+    return rc;
+}
+
+int p2p(bool send, void *data, size_t bytes, int peer, bool blocking)
 {
     if (!g_comm.comm) return fail(send ? "tiramisu_MPI_Send" : "tiramisu_MPI_Recv", "communicator not initialised");
     if (peer < 0 || peer >= g_comm.world) return fail("tiramisu_MPI p2p", "peer rank out of range");
-    Nccl &n = nccl();
-    if (is_device_pointer(data)) {
-        return send ? nccl_check(n.Send(data, bytes, ncclInt8, peer, g_comm.comm, stream()), "ncclSend")
-                    : nccl_check(n.Recv(data, bytes, ncclInt8, peer, g_comm.comm, stream()), "ncclRecv");
+    if (peer == g_comm.rank) return fail("tiramisu_MPI p2p", "message to self");
+    Pending m{send, data, bytes, peer, nullptr, false};
+    if (!is_device_pointer(data)) {
+        // host buffer (the reference's MPI usage): bounce through pooled device memory
+        m.dev = pool_alloc(bytes);
+        if (!m.dev) return 1;
+        m.host = data;
+        m.staged = true;
+        if (send) {
+            if (tiramisu_cuda_memcpy_to_device_async(m.dev, data, bytes)) return 1;
+            // the caller may overwrite `data` as soon as we return (MPI_Send / MPI_Isend + buffered copy)
+            if (check(cudaStreamSynchronize(stream()), "tiramisu_MPI_Send")) return 1;
+        }
     }
-    // host buffer (the reference's MPI usage): bounce through pooled device memory
-    void *d = pool_alloc(bytes);
-    if (!d) return 1;
-    int rc = 0;
-    if (send) {
-        rc = tiramisu_cuda_memcpy_to_device_async(d, data, bytes);
-        if (!rc) rc = nccl_check(n.Send(d, bytes, ncclInt8, peer, g_comm.comm, stream()), "ncclSend");
-    } else {
-        rc = nccl_check(n.Recv(d, bytes, ncclInt8, peer, g_comm.comm, stream()), "ncclRecv");
-        if (!rc) rc = tiramisu_cuda_memcpy_to_host_async(data, d, bytes);
-        if (!rc) rc = check(cudaStreamSynchronize(stream()), "tiramisu_MPI_Recv");   // blocking receive into host memory
-    }
-    pool_free(d);
-    return rc;
+    t_pending.push_back(m);
+    return blocking ? flush_pending() : 0;
 }
 
 // ---- TCP rendezvous for the unique id (single node, torchrun environment) -------------------------------
@@ -248,8 +291,14 @@ TB200_API int tiramisu_b200_comm_init(int32_t rank, int32_t world, const void *i
     return 0;
 }
 
+namespace tb200 { int heat2d_dist_release(); }        // heat2d_dist.cu: cached symmetric block of heat2d_dist_tiramisu
+
 TB200_API int tiramisu_b200_comm_destroy(void)
 {
+    if (g_comm.comm) {
+        flush_pending();
+        heat2d_dist_release();                             // collective: every rank destroys its communicator
+    }
     std::lock_guard<std::mutex> lk(g_comm_mu);
     if (!g_comm.comm) return 0;
     cudaStreamSynchronize(stream());
@@ -334,32 +383,69 @@ struct SymBlock { void *local; std::vector<void *> opened; };
 std::vector<SymBlock> g_sym;
 }
 
+// Collective and failure-safe: a rank whose cudaMalloc / cudaIpcGetMemHandle / cudaIpcOpenMemHandle fails still
+// takes part in both exchanges below (status travels with the handle, then a second status round after the
+// mappings), so either every rank returns success or every rank returns failure with nothing left allocated —
+// nobody is left waiting in a collective for a rank that gave up.
 TB200_API int tiramisu_b200_comm_alloc_symmetric(uint64_t bytes, void **local, void **peers)
 {
     if (!local || !peers || bytes == 0) return fail(__func__, "bad argument");
     if (!g_comm.comm) return fail(__func__, "communicator not initialised");
     const int world = g_comm.world, rank = g_comm.rank;
+    struct Record { cudaIpcMemHandle_t handle; int32_t status; int32_t pad[3]; };
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64 && sizeof(Record) == 80, "IPC record layout");
+    Record rec;
+    memset(&rec, 0, sizeof(rec));
     void *mine = nullptr;
-    TB200_CHECK(cudaMalloc(&mine, bytes));
-    TB200_CHECK(cudaMemset(mine, 0, bytes));
-    cudaIpcMemHandle_t h;
-    TB200_CHECK(cudaIpcGetMemHandle(&h, mine));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::string why;
+    auto note = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rec.status == 0) { rec.status = 1; why = std::string(what) + ": " + cudaGetErrorString(e); cudaGetLastError(); }
+        return e == cudaSuccess;
+    };
+    if (note(cudaMalloc(&mine, bytes), "cudaMalloc") && note(cudaMemset(mine, 0, bytes), "cudaMemset"))
+        note(cudaIpcGetMemHandle(&rec.handle, mine), "cudaIpcGetMemHandle");
+    // round 1: handles + local status
     char *d_all = nullptr;
-    TB200_CHECK(cudaMalloc(&d_all, (size_t)world * 64));
-    TB200_CHECK(cudaMemcpyAsync(d_all + (size_t)rank * 64, &h, 64, cudaMemcpyHostToDevice, stream()));
-    if (nccl_check(nccl().AllGather(d_all + (size_t)rank * 64, d_all, 64, ncclInt8, g_comm.comm, stream()), "ncclAllGather")) return 1;
-    std::vector<cudaIpcMemHandle_t> all(world);
-    TB200_CHECK(cudaMemcpyAsync(all.data(), d_all, (size_t)world * 64, cudaMemcpyDeviceToHost, stream()));
+    TB200_CHECK(cudaMalloc(&d_all, (size_t)world * sizeof(Record)));       // a failure here is not recoverable collectively
+    TB200_CHECK(cudaMemcpyAsync(d_all + (size_t)rank * sizeof(Record), &rec, sizeof(Record), cudaMemcpyHostToDevice, stream()));
+    if (nccl_check(nccl().AllGather(d_all + (size_t)rank * sizeof(Record), d_all, sizeof(Record), ncclInt8, g_comm.comm, stream()), "ncclAllGather")) return 1;
+    std::vector<Record> all(world);
+    TB200_CHECK(cudaMemcpyAsync(all.data(), d_all, (size_t)world * sizeof(Record), cudaMemcpyDeviceToHost, stream()));
+    TB200_CHECK(cudaStreamSynchronize(stream()));
+    int bad_rank = -1;
+    for (int r = 0; r < world; r++) if (all[r].status && bad_rank < 0) bad_rank = r;
+    SymBlock blk{mine, {}};
+    int open_failed = 0;
+    if (bad_rank < 0) {
+        for (int r = 0; r < world; r++) {
+            if (r == rank) { peers[r] = mine; continue; }
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                why = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(cudaGetLastError());
+                open_failed = 1;
+                break;
+            }
+            peers[r] = p;
+            blk.opened.push_back(p);
+        }
+    }
+    // round 2: did every rank map every peer?  (sum of failure flags; also the rendezvous before anybody frees)
+    float flag = (bad_rank >= 0 || open_failed) ? 1.0f : 0.0f, total = 0.0f;
+    float *d_flag = reinterpret_cast<float *>(d_all);
+    TB200_CHECK(cudaMemcpyAsync(d_flag, &flag, sizeof(float), cudaMemcpyHostToDevice, stream()));
+    if (nccl_check(nccl().AllReduce(d_flag, d_flag, 1, ncclFloat32, ncclSum, g_comm.comm, stream()), "ncclAllReduce")) return 1;
+    TB200_CHECK(cudaMemcpyAsync(&total, d_flag, sizeof(float), cudaMemcpyDeviceToHost, stream()));
     TB200_CHECK(cudaStreamSynchronize(stream()));
     cudaFree(d_all);
-    SymBlock blk{mine, {}};
-    for (int r = 0; r < world; r++) {
-        if (r == rank) { peers[r] = mine; continue; }
-        void *p = nullptr;
-        TB200_CHECK(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
-        peers[r] = p;
-        blk.opened.push_back(p);
+    if (total != 0.0f) {
+        for (void *p : blk.opened) cudaIpcCloseMemHandle(p);
+        if (mine) cudaFree(mine);
+        for (int r = 0; r < world; r++) peers[r] = nullptr;
+        *local = nullptr;
+        if (why.empty())
+            why = bad_rank >= 0 ? "rank " + std::to_string(bad_rank) + " could not allocate or export its block"
+                                : "another rank could not map a peer's block";
+        return fail(__func__, why);
     }
     *local = mine;
     std::lock_guard<std::mutex> lk(g_comm_mu);
@@ -402,11 +488,12 @@ TB200_API int tiramisu_MPI_init(void)
     return rank;
 }
 
-TB200_API void tiramisu_MPI_cleanup(void) { tiramisu_b200_comm_destroy(); }      // :19-21 MPI_Finalize
+TB200_API void tiramisu_MPI_cleanup(void) { tiramisu_b200_comm_destroy(); }      // :19-21 MPI_Finalize (flushes queued messages)
 
 TB200_API void tiramisu_MPI_global_barrier(void)                                 // :23 MPI_Barrier
 {
     if (!g_comm.comm) return;
+    flush_pending();
     if (nccl_check(nccl().AllReduce(g_comm.scratch, g_comm.scratch, 1, ncclFloat32, ncclSum, g_comm.comm, stream()),
                    "ncclAllReduce"))
         return;
@@ -417,18 +504,20 @@ TB200_API int tiramisu_MPI_Comm_rank(int offset) { return g_comm.rank + offset; 
 
 TB200_API void tiramisu_MPI_Wait(void *)                                            // :85-89
 {
-    // stream order already sequences the message; host-buffer receives synchronise inside p2p()
+    // completes every message queued by the non-blocking calls (one NCCL group); for device buffers completion is
+    // in stream order, host-buffer receives are copied back and waited for
+    flush_pending();
 }
 
 // src/tiramisu_mpi.cpp:96-192 — (count, peer, tag, data[, reqs]); tags are implicit in NCCL's
 // per-peer FIFO order, request handles are not needed (see tiramisu_MPI_Wait).
 #define TB200_MPI_TYPE(SUFFIX, T)                                                                                     \
-    TB200_API void tiramisu_MPI_Send_##SUFFIX(int count, int dest, int, T *data) { p2p(true, data, (size_t)count * sizeof(T), dest); }   \
-    TB200_API void tiramisu_MPI_Ssend_##SUFFIX(int count, int dest, int, T *data) { p2p(true, data, (size_t)count * sizeof(T), dest); }  \
-    TB200_API void tiramisu_MPI_Isend_##SUFFIX(int count, int dest, int, T *data, long *) { p2p(true, data, (size_t)count * sizeof(T), dest); }  \
-    TB200_API void tiramisu_MPI_Issend_##SUFFIX(int count, int dest, int, T *data, long *) { p2p(true, data, (size_t)count * sizeof(T), dest); } \
-    TB200_API void tiramisu_MPI_Recv_##SUFFIX(int count, int src, int, T *data) { p2p(false, data, (size_t)count * sizeof(T), src); }    \
-    TB200_API void tiramisu_MPI_Irecv_##SUFFIX(int count, int src, int, T *data, long *) { p2p(false, data, (size_t)count * sizeof(T), src); }
+    TB200_API void tiramisu_MPI_Send_##SUFFIX(int count, int dest, int, T *data) { p2p(true, data, (size_t)count * sizeof(T), dest, true); }   \
+    TB200_API void tiramisu_MPI_Ssend_##SUFFIX(int count, int dest, int, T *data) { p2p(true, data, (size_t)count * sizeof(T), dest, true); }  \
+    TB200_API void tiramisu_MPI_Isend_##SUFFIX(int count, int dest, int, T *data, long *) { p2p(true, data, (size_t)count * sizeof(T), dest, false); }  \
+    TB200_API void tiramisu_MPI_Issend_##SUFFIX(int count, int dest, int, T *data, long *) { p2p(true, data, (size_t)count * sizeof(T), dest, false); } \
+    TB200_API void tiramisu_MPI_Recv_##SUFFIX(int count, int src, int, T *data) { p2p(false, data, (size_t)count * sizeof(T), src, true); }    \
+    TB200_API void tiramisu_MPI_Irecv_##SUFFIX(int count, int src, int, T *data, long *) { p2p(false, data, (size_t)count * sizeof(T), src, false); }
 
 TB200_MPI_TYPE(int8, char)
 TB200_MPI_TYPE(int16, short)

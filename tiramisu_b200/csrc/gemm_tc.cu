@@ -109,6 +109,8 @@ struct GemmParams {
     int64_t ldC;
     int num_m, num_n, group_m;
     uint32_t b_lbo, b_sbo;              // MN-major B descriptor offsets (bytes)
+    const float *alpha_dev;             // optional device-resident factor multiplied into alpha (LSTM: the
+                                        // power-of-two de-scaling of block-scaled fp16 weights), else null
 };
 
 // F16: operands are fp16 (kind::f16, K = 16 per instruction, 64 elements per 128-byte swizzle row):
@@ -230,6 +232,7 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
         const bool row_ok = row < p.M;
         float *crow = p.C + (size_t)row * p.ldC;
         const bool use_c = p.beta != 0.0f;             // cuBLAS semantics: C not read when beta == 0
+        const float alpha = p.alpha_dev ? __fmul_rn(p.alpha, __ldg(p.alpha_dev)) : p.alpha;
         // The beta*C operand does not depend on the MMAs: fetch the first 32-column chunk of this
         // thread's C row while the main loop runs, and each further chunk one iteration ahead (at
         // 1024^3 the whole kernel lasts a few microseconds and this latency was exposed, r01 ncu).
@@ -261,10 +264,10 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
                     const int col = n0 + c0 + j;
                     if (col + 3 < p.N) {
                         float4 o;
-                        o.x = __fmul_rn(__uint_as_float(r[j + 0]), p.alpha);
-                        o.y = __fmul_rn(__uint_as_float(r[j + 1]), p.alpha);
-                        o.z = __fmul_rn(__uint_as_float(r[j + 2]), p.alpha);
-                        o.w = __fmul_rn(__uint_as_float(r[j + 3]), p.alpha);
+                        o.x = __fmul_rn(__uint_as_float(r[j + 0]), alpha);
+                        o.y = __fmul_rn(__uint_as_float(r[j + 1]), alpha);
+                        o.z = __fmul_rn(__uint_as_float(r[j + 2]), alpha);
+                        o.w = __fmul_rn(__uint_as_float(r[j + 3]), alpha);
                         if (use_c) {
                             const float4 c = ccur[j >> 2];
                             o.x = __fadd_rn(o.x, __fmul_rn(c.x, p.beta));
@@ -277,7 +280,7 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
                             if (col + u < p.N) {
-                                float o = __fmul_rn(__uint_as_float(r[j + u]), p.alpha);
+                                float o = __fmul_rn(__uint_as_float(r[j + u]), alpha);
                                 if (use_c) o = __fadd_rn(o, __fmul_rn(crow[col + u], p.beta));
                                 crow[col + u] = o;
                             }
@@ -585,6 +588,7 @@ int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, flo
     p.group_m = 16;
     p.b_lbo = BK * 128;
     p.b_sbo = 512;
+    p.alpha_dev = nullptr;
     if (const char *e = getenv("TB200_DBG_B_LBO")) p.b_lbo = (uint32_t)atoi(e);     // descriptor bring-up only
     if (const char *e = getenv("TB200_DBG_B_SBO")) p.b_sbo = (uint32_t)atoi(e);
     auto kern = tiramisu_sm100_gemm_tf32<BN, B_MN>;
@@ -599,7 +603,7 @@ int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, flo
 
 template <int BN>
 int launch_tc_f16(const void *A, const void *B, float *C, int M, int N, int K, float alpha, float beta, int64_t ldA,
-                  int64_t ldB, int64_t ldC)
+                  int64_t ldB, int64_t ldC, const float *alpha_dev)
 {
     CUtensorMap map_a, map_b;
     {
@@ -621,6 +625,7 @@ int launch_tc_f16(const void *A, const void *B, float *C, int M, int N, int K, f
     p.group_m = 16;
     p.b_lbo = 0;
     p.b_sbo = 0;
+    p.alpha_dev = alpha_dev;
     auto kern = tiramisu_sm100_gemm_tf32<BN, false, true>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -661,6 +666,7 @@ int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N,
     p.group_m = 16 / CG;
     p.b_lbo = BK * 128;
     p.b_sbo = 512;
+    p.alpha_dev = nullptr;
     auto kern = tiramisu_sm100_gemm_tf32_persistent<CG, B_MN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -773,15 +779,16 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
 }
 
 // C[M][N] (fp32) = alpha * A[M][K] * B[N][K]^T + beta * C with fp16 operands (both K-major, pitches in
-// elements, multiples of 8), fp32 accumulation; one 128 x 256 (or 128 x 128) tile per CTA.
+// elements, multiples of 8), fp32 accumulation; one 128 x 256 (or 128 x 128) tile per CTA.  alpha_dev: optional
+// device-resident factor multiplied into alpha (read by the epilogue, no host synchronisation).
 int gemm_f16_tc(const void *A16, const void *B16, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,
-                uint64_t ldA, uint64_t ldB, uint64_t ldC)
+                uint64_t ldA, uint64_t ldB, uint64_t ldC, const float *alpha_dev)
 {
     if (!aligned16(A16) || !aligned16(B16) || !aligned16(C) || ldA % 8 || ldB % 8 || ldC % 4 || M == 0 || N == 0 || K == 0)
         return fail("gemm_f16_tc", "operands not addressable by TMA");
     if (N % 256 == 0 || N > 1024)
-        return launch_tc_f16<256>(A16, B16, C, (int)M, (int)N, (int)K, alpha, beta, ldA, ldB, ldC);
-    return launch_tc_f16<128>(A16, B16, C, (int)M, (int)N, (int)K, alpha, beta, ldA, ldB, ldC);
+        return launch_tc_f16<256>(A16, B16, C, (int)M, (int)N, (int)K, alpha, beta, ldA, ldB, ldC, alpha_dev);
+    return launch_tc_f16<128>(A16, B16, C, (int)M, (int)N, (int)K, alpha, beta, ldA, ldB, ldC, alpha_dev);
 }
 
 int gemm_f32(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,

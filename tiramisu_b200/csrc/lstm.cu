@@ -31,7 +31,7 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
                 float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tB);
 void gemm_tc_hint(int kernel, int bn);
 int gemm_f16_tc(const void *A16, const void *B16, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,
-                uint64_t ldA, uint64_t ldB, uint64_t ldC);
+                uint64_t ldA, uint64_t ldB, uint64_t ldC, const float *alpha_dev);
 }
 
 namespace {
@@ -698,11 +698,28 @@ struct H16Params {
     const float *bias;          // [4F] packed
     float *h;                   // [T][B][F] fp32 output of this layer, or null (only the last layer's is consumed)
     __half *h16;                // [T][B][F] fp16 copy, the recurrence's own operand
-    uint32_t *counter;          // += gridDim.x per finished step
+    uint32_t *step_flags;       // [gridDim.x]: flag c = number of steps CTA c has published (one word per CTA: a
+                                // single counter serialises 64 same-address atomics in L2 every step)
+    const float *rscale;        // de-scaling factor of the block-scaled fp16 recurrent weights (a power of two)
     const uint32_t *xg_ready;   // null, or: number of leading time steps of xg that are complete
     int dbg;
     unsigned long long *trace;
 };
+
+// Every CTA of the layer has published step `target`: lane i watches the flags of CTAs i, i + 32, ...
+// (relaxed polls; one acquire fence once all of them have been seen).  Whole warp, converged.
+__device__ __forceinline__ void grid_wait_flags(const uint32_t *flags, int n, uint32_t target)
+{
+    const int lane = threadIdx.x & 31;
+    const long long t0 = clock64();
+    for (;;) {
+        bool ok = true;
+        for (int c = lane; c < n; c += 32) ok = ok && ptx::ld_relaxed_gpu(flags + c) >= target;
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+    ptx::fence_acq_rel_gpu();
+}
 
 __global__ void __launch_bounds__(H_THREADS, 1)
 tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_r,
@@ -754,7 +771,7 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
         }
         __syncwarp();
         for (int t = 1; t < p.T; t++) {
-            if (!(p.dbg & 1)) grid_wait_relaxed(p.counter, (uint32_t)gridDim.x * (uint32_t)t);   // h16[t-1] is complete
+            if (!(p.dbg & 1)) grid_wait_flags(p.step_flags, (int)gridDim.x, (uint32_t)t);        // h16[t-1] is complete
             ptx::fence_proxy_async_all();
             if (ptx::elect_one()) {
                 KS_TRACE(0);
@@ -825,6 +842,7 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
         float4 bs[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) bs[u] = __ldg(reinterpret_cast<const float4 *>(p.bias + p0) + u);
+        const float rs = __ldg(p.rscale);                  // R was stored as fp16(R * 2^k): accumulators are scaled back
         // where this warp's TMEM rows go: CTA dst, slot [src = ks][row = 32 (q & 1) + lane][batch 32 ch ..]
         const uint32_t row_l = 32u * (q & 1u) + (uint32_t)lane;
         // receive-buffer swizzle: 16-byte chunk c of gate row r lives at chunk c ^ s(r),
@@ -894,7 +912,7 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
                 for (int a = 0; a < 16; a++) {
                     const int row = 16 * ug + a;
                     const int col = ((((b >> 2) ^ (row & 7) ^ (ug << 1)) << 2) | (b & 3));
-                    acc[a] = recv[0 * 4096 + row * 64 + col] + recv[1 * 4096 + row * 64 + col];
+                    acc[a] = (recv[0 * 4096 + row * 64 + col] + recv[1 * 4096 + row * 64 + col]) * rs;
                 }
             }
             float hn[4];
@@ -918,13 +936,13 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
                 *reinterpret_cast<uint2 *>(p.h16 + o) = pk;
             }
             // publish h[t]: CTA-wide rendezvous of the writers (also: every reader is done with recv before
-            // the next step's pushes are triggered), then ONE gpu-scope fence + counter increment
+            // the next step's pushes are triggered), then ONE gpu-scope fence + this CTA's own step flag
             if (e == 0) KS_TRACE(6);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (e == 0) {
                 KS_TRACE(2);
                 ptx::fence_acq_rel_gpu();
-                ptx::red_relaxed_gpu_add(p.counter, 1u);
+                ptx::st_relaxed_gpu(p.step_flags + blockIdx.x, (uint32_t)(t + 1));
                 KS_TRACE(7);
             }
         }
@@ -938,13 +956,56 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
     }
 }
 
+// ---- block-scaled fp16 weights ----------------------------------------------------------------------
+// fp16 has TF32's 11-bit significand but only a 5-bit exponent: |w| > 65504 would become inf and |w| < 6e-8
+// zero.  Every weight matrix (R and W of every layer) is therefore stored as fp16(w * 2^k) with k chosen so that
+// its largest magnitude lands in [2^13, 2^14); the accumulators are multiplied by 2^-k in the epilogues (exact:
+// powers of two).  Overflow cannot happen, every element within 2^-27 of the matrix maximum keeps its 11
+// significant bits, and what is smaller still is represented to within 2^-39 of the maximum — far below the
+// TF32 rounding (2^-11 relative) of the terms it is added to.
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_lstm_absmax(const float *__restrict__ W, uint32_t *__restrict__ maxbits, size_t per_matrix4, int n_matrices)
+{
+    // maxbits[m] = bit pattern of max |w| over matrix m (non-negative floats order like their bit patterns; NaN > inf)
+    for (int m = blockIdx.y; m < n_matrices; m += gridDim.y) {
+        const float4 *src = reinterpret_cast<const float4 *>(W) + (size_t)m * per_matrix4;
+        uint32_t mx = 0;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_matrix4; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 v = __ldg(src + i);
+            mx = max(max(mx, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+        }
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((threadIdx.x & 31) == 0 && mx) atomicMax(maxbits + m, mx);
+    }
+}
+
+// scale[m] = 2^k, inv[m] = 2^-k; matrix (layer 0, W) stays fp32 (its other operand is the fp32 input x): scale 1
+__global__ void tiramisu_sm100_lstm_scales(const uint32_t *__restrict__ maxbits, float *__restrict__ scale, float *__restrict__ inv, int n)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const float mx = __uint_as_float(maxbits[m]);
+    int k = 0;
+    if (m != 1 && mx > 0.0f && mx < __int_as_float(0x7f800000)) {
+        int e;
+        frexpf(mx, &e);                                  // mx = f * 2^e, f in [0.5, 1)
+        k = 14 - e;
+        k = k > 126 ? 126 : (k < -126 ? -126 : k);
+    }
+    scale[m] = ldexpf(1.0f, k);
+    inv[m] = ldexpf(1.0f, -k);
+}
+
 // R (fp32 [4F][F], row g*F+u) -> fp16 packed rows p = 4u+g ; W likewise: fp32 for layer 0 (B operand of the
 // TF32 input GEMM on x), fp16 for the layers above (their A operand is the fp16 copy of h) ; bias packed.
+// scale2: the two power-of-two factors (R, W) of this layer.
 __global__ void __launch_bounds__(256)
 tiramisu_sm100_lstm_pack16(const float *__restrict__ Wl, const float *__restrict__ bl, __half *__restrict__ R16,
-                           float *__restrict__ Wp32, __half *__restrict__ Wp16, float *__restrict__ bp, int F)
+                           float *__restrict__ Wp32, __half *__restrict__ Wp16, float *__restrict__ bp,
+                           const float *__restrict__ scale2, int F)
 {
     const size_t total4 = (size_t)2 * 4 * F * (F / 4);
+    const float sR = __ldg(scale2), sW = __ldg(scale2 + 1);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
         const int j4 = (int)(i % (F / 4));
         size_t t = i / (F / 4);
@@ -952,7 +1013,8 @@ tiramisu_sm100_lstm_pack16(const float *__restrict__ Wl, const float *__restrict
         const int m = (int)(t / (4 * F));
         const int u = pr >> 2, g = pr & 3;
         const float4 v = __ldg(reinterpret_cast<const float4 *>(Wl + ((size_t)m * 4 * F + (size_t)g * F + u) * F) + j4);
-        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        const float sc = m == 0 ? sR : sW;
+        const __half2 lo = __floats2half2_rn(v.x * sc, v.y * sc), hi = __floats2half2_rn(v.z * sc, v.w * sc);
         uint2 pk;
         pk.x = *reinterpret_cast<const uint32_t *>(&lo);
         pk.y = *reinterpret_cast<const uint32_t *>(&hi);
@@ -969,11 +1031,12 @@ tiramisu_sm100_lstm_pack16(const float *__restrict__ Wl, const float *__restrict
 
 // Stream-side halves of the layer pipeline: a one-warp kernel that returns once *ctr >= target (the
 // layer below has published enough steps) and a one-thread kernel that publishes a value.
-__global__ void tiramisu_sm100_wait_counter(const uint32_t *ctr, uint32_t target)
+__global__ void tiramisu_sm100_wait_counter(const uint32_t *flags, int n, uint32_t target)
 {
-    if (threadIdx.x == 0) {
+    // returns once every one of the n per-CTA step flags has reached `target`
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
         const long long t0 = clock64();
-        while (ptx::ld_acquire_gpu(ctr) < target) {
+        while (ptx::ld_acquire_gpu(flags + c) < target) {
             if (clock64() - t0 > (1ll << 32)) __trap();
             __nanosleep(500);
         }
@@ -987,6 +1050,7 @@ __global__ void tiramisu_sm100_publish(uint32_t *flag, uint32_t value)
 
 std::atomic<int> g_lstm_mode{0};
 std::atomic<int> g_lstm_kernel{0};
+thread_local const char *t_last_engine = "";     // which recurrence engine the calling thread's last tiramisu_b200_lstm used
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int lstm_exact(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y)
@@ -1206,22 +1270,34 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
     float *bp = reinterpret_cast<float *>(pool_alloc((size_t)L * 4 * F * 4));
     float *xg = reinterpret_cast<float *>(pool_alloc((size_t)2 * TB * 4 * F * 4));         // input contributions, by layer parity
     __half *h16 = reinterpret_cast<__half *>(pool_alloc((size_t)2 * TB * F * 2));          // h fp16, by layer parity
-    uint32_t *flags = reinterpret_cast<uint32_t *>(pool_alloc((size_t)(2 * L + 1) * 4));   // [L] step counters, [L] xg_ready, scratch
+    // [L][64] per-CTA step flags, [L] xg_ready, [2L] weight max-abs bit patterns, scratch word; then [2L] scale, [2L] 1/scale
+    const size_t n_words = (size_t)64 * L + L + 2 * L + 1;
+    uint32_t *flags = reinterpret_cast<uint32_t *>(pool_alloc((n_words + 4 * (size_t)L) * 4));
     if (!R16 || !Wp || !Wp16 || !bp || !xg || !h16 || !flags) return 1;
-    uint32_t *counters = flags, *xg_ready = flags + L;
-    TB200_CHECK(cudaMemsetAsync(flags, 0, (size_t)(2 * L + 1) * 4, stream()));
-    const int nctas = F / 16;
+    uint32_t *step_flags = flags, *xg_ready = flags + 64 * L, *maxbits = xg_ready + L, *scratch = maxbits + 2 * L;
+    float *wscale = reinterpret_cast<float *>(flags + n_words), *winv = wscale + 2 * L;
+    TB200_CHECK(cudaMemsetAsync(flags, 0, n_words * 4, stream()));
+    const int nctas = F / 16;                                    // <= 64 (F <= 1024)
     int chunk = 10;
     if (const char *e = getenv("TB200_LSTM_CHUNK")) chunk = atoi(e) > 0 ? atoi(e) : chunk;
     int dbg = 0;
     if (const char *e = getenv("TB200_LSTM_DBG")) dbg = atoi(e);
 
+    {
+        // power-of-two block scales of the 2L weight matrices (no host round trip: the pack kernels and the
+        // epilogues read them from device memory)
+        const unsigned bx = (unsigned)((wsz / 4 + 255) / 256 < (size_t)sm_count() * 2 ? (wsz / 4 + 255) / 256 : (size_t)sm_count() * 2);
+        tiramisu_sm100_lstm_absmax<<<dim3(bx, (unsigned)(2 * L)), 256, 0, stream()>>>(Wt, maxbits, wsz / 4, 2 * L);
+        if (post_launch("tiramisu_sm100_lstm_absmax")) return 1;
+        tiramisu_sm100_lstm_scales<<<(unsigned)((2 * L + 63) / 64), 64, 0, stream()>>>(maxbits, wscale, winv, 2 * L);
+        if (post_launch("tiramisu_sm100_lstm_scales")) return 1;
+    }
     for (int l = 0; l < L; l++) {
         const size_t pk = (size_t)2 * 4 * F * (F / 4);
         const size_t want = (pk + 255) / 256, cap = (size_t)sm_count() * 16;
         tiramisu_sm100_lstm_pack16<<<(unsigned)(want < cap ? want : cap), 256, 0, stream()>>>(
             Wt + (size_t)l * 2 * wsz, bias + (size_t)l * 4 * F, R16 + (size_t)l * wsz, Wp,
-            l == 0 ? nullptr : Wp16 + (size_t)l * wsz, bp + (size_t)l * 4 * F, F);
+            l == 0 ? nullptr : Wp16 + (size_t)l * wsz, bp + (size_t)l * 4 * F, wscale + 2 * l, F);
         if (post_launch("tiramisu_sm100_lstm_pack16")) return 1;
     }
 
@@ -1251,7 +1327,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
         H16Params hp;
         hp.B = B; hp.F = F; hp.T = T;
         hp.xg = xg_of(l); hp.bias = bp + (size_t)l * 4 * F; hp.h = out_of(l); hp.h16 = hh;
-        hp.counter = counters + l; hp.xg_ready = ready; hp.dbg = dbg; hp.trace = trace;
+        hp.step_flags = step_flags + 64 * l; hp.rscale = winv + 2 * l; hp.xg_ready = ready; hp.dbg = dbg; hp.trace = trace;
         cudaLaunchAttribute attr[1];
         cudaLaunchConfig_t cfg = h16_config(F, attr, st);
         TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16, map_h, map_r, hp));
@@ -1265,7 +1341,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
                                4 * (uint64_t)F, true);
         const __half *below16 = h16 + (size_t)((l - 1) & 1) * TB * F + (size_t)t0 * B * F;
         return gemm_f16_tc(below16, Wp16 + (size_t)l * wsz, dst, (uint64_t)(t1 - t0) * B, 4 * (uint64_t)F, F, 1.0f, 0.0f, F, F,
-                           4 * (uint64_t)F);
+                           4 * (uint64_t)F, winv + 2 * l + 1);
     };
 
     const char *trace_path = getenv("TB200_LSTM_TRACE");                 // bring-up: step timeline of layer 0
@@ -1285,11 +1361,11 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
         // traps).  One tiny launch of each, once per process, on the main stream.
         static std::atomic<bool> warmed{false};
         if (!warmed.load()) {
-            tiramisu_sm100_wait_counter<<<1, 32, 0, main_st>>>(flags + 2 * L, 0u);
+            tiramisu_sm100_wait_counter<<<1, 64, 0, main_st>>>(scratch, 1, 0u);
             if (post_launch("tiramisu_sm100_wait_counter")) return 1;
-            tiramisu_sm100_publish<<<1, 1, 0, main_st>>>(flags + 2 * L, 0u);
+            tiramisu_sm100_publish<<<1, 1, 0, main_st>>>(scratch, 0u);
             if (post_launch("tiramisu_sm100_publish")) return 1;
-            if (gemm_f16_tc(h16, Wp16, xg, (uint64_t)B, 4 * (uint64_t)F, F, 1.0f, 0.0f, F, F, 4 * (uint64_t)F)) return 1;
+            if (gemm_f16_tc(h16, Wp16, xg, (uint64_t)B, 4 * (uint64_t)F, F, 1.0f, 0.0f, F, F, 4 * (uint64_t)F, nullptr)) return 1;
             TB200_CHECK(cudaStreamSynchronize(main_st));
             warmed.store(true);
         }
@@ -1317,7 +1393,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
             for (int t0 = 0, n = 0; t0 < T && !rc; n++) {
                 const int len = n == 0 ? (chunk < 4 ? chunk : 4) : (n == 1 ? (chunk < 6 ? chunk : 6) : chunk);
                 const int t1 = t0 + len < T ? t0 + len : T;
-                tiramisu_sm100_wait_counter<<<1, 32, 0, ps->gemm>>>(counters + l, (uint32_t)nctas * (uint32_t)t1);
+                tiramisu_sm100_wait_counter<<<1, 64, 0, ps->gemm>>>(step_flags + 64 * l, nctas, (uint32_t)t1);
                 rc = post_launch("tiramisu_sm100_wait_counter");
                 if (!rc) rc = launch_xg(l + 1, t0, t1);
                 if (!rc) {
@@ -1359,6 +1435,8 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
         if (ok) {
             bool pipe = pair_ok;
             if (const char *e = getenv("TB200_LSTM_PIPE")) pipe = pipe && atoi(e) != 0;
+            t_last_engine = pipe ? "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, layer pairs overlapped"
+                                 : "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, one layer at a time";
             return lstm_h16(F, B, L, T, Wt, bias, x, y, pipe);
         }
     }
@@ -1379,6 +1457,9 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
     if (which == 2 && !use_layer_kernel) return fail("tiramisu_b200_lstm", "shape not supported by the persistent layer kernel");
     const int a_rows = B <= 64 ? 64 : 128;
     const int cl = use_layer_kernel ? pick_cluster(F, a_rows) : 1;
+    t_last_engine = use_ksplit ? "ksplit: TF32 operands, K split over 4-CTA clusters (DSMEM reduction)"
+                    : use_layer_kernel ? "layer: TF32 operands, gate columns split across CTAs, persistent per layer"
+                                       : "step: TF32 operands, one launch per cell";
     static bool attr_set = false;
     if (!attr_set) {
         TB200_CHECK(cudaFuncSetAttribute(tiramisu_sm100_lstm_step_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1504,5 +1585,8 @@ TB200_API int tiramisu_b200_lstm(const float *Weights, const float *biases, cons
     const bool tc_ok = F % 32 == 0 && B <= 128 && aligned16(Weights) && aligned16(biases) && aligned16(x) && aligned16(y);
     if (mode == 2 && !tc_ok) return fail(__func__, "shape not supported by the tcgen05 LSTM path");
     if (mode != 1 && tc_ok) return lstm_tensor(F, B, L, T, Weights, biases, x, y);
+    t_last_engine = "exact: fp32 SIMT in the reference's accumulation order";
     return lstm_exact(F, B, L, T, Weights, biases, x, y);
 }
+
+TB200_API const char *tiramisu_b200_lstm_last_engine(void) { return t_last_engine; }

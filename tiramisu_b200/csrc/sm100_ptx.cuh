@@ -347,6 +347,10 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p)
     return v;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_relaxed_gpu_add(uint32_t *p, uint32_t v)
 {
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

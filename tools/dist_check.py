@@ -159,6 +159,65 @@ def main():
         torch.distributed.barrier()
         sym.free()
 
+    # ---- 6. heat2d_dist_tiramisu through the generated-function ABI (host buffers, one call per rank) -------
+    # global grid [world*rows + 2][cols]; rank q passes local rows [q*rows, q*rows + rows + 2) of both buffers
+    # (rows 1..rows owned, 0 and rows+1 halos), as wrapper_heat2d_dist.cpp:53-66 does
+    for rows_d, cols_d, iters_d, protocol in ((37, 2048, 4, 0), (16, 1024, 6, 0), (37, 2048, 1, 1), (24, 512, 3, 1)):
+        Hd = world * rows_d + 2
+        ge = np.random.default_rng(31).random((Hd, cols_d), dtype=np.float32)
+        go = np.random.default_rng(32).random((Hd, cols_d), dtype=np.float32)
+        le = np.ascontiguousarray(ge[rank * rows_d: rank * rows_d + rows_d + 2])
+        lo_ = np.ascontiguousarray(go[rank * rows_d: rank * rows_d + rows_d + 2])
+        for rep in range(2):                                      # twice: the symmetric block and flag epochs are reused
+            e_in, o_in = le.copy(), lo_.copy()
+            api.heat2d_dist_tiramisu(e_in, o_in, rows_per_rank=rows_d, iters=iters_d, protocol=protocol)
+        we, wo = ge.copy(), go.copy()
+        for s_ in range(iters_d):
+            src_is_odd = (s_ % 2 == 0) if protocol == 0 else (s_ % 2 == 1)
+            if src_is_odd:
+                oracle.heat2d_step(wo, we)
+            else:
+                oracle.heat2d_step(we, wo)
+        sl = slice(rank * rows_d, rank * rows_d + rows_d + 2)
+        good = np.array_equal(e_in, we[sl]) and np.array_equal(o_in, wo[sl])
+        ok &= good
+        print(f"[rank {rank}] heat2d_dist_tiramisu rows/rank={rows_d} cols={cols_d} iters={iters_d} protocol={protocol}: "
+              f"{'ok' if good else 'MISMATCH'}", flush=True)
+
+    # ---- 7. tiramisu_MPI_* shims: Irecv-first bidirectional neighbour exchange (one NCCL group at Wait), host
+    # and device buffers — the pattern the reference's distributed tests use (tests/test_98.cpp ... 102)
+    up, dn = rank - 1, rank + 1
+    n_el = 1000
+    for on_dev in (False, True):
+        mine_np = (np.arange(n_el, dtype=np.float32) + 1000 * rank)
+        from_up_np, from_dn_np = np.full(n_el, -1, np.float32), np.full(n_el, -1, np.float32)
+        if on_dev:
+            mine_t, fu_t, fd_t = torch.from_numpy(mine_np).cuda(), torch.from_numpy(from_up_np).cuda(), torch.from_numpy(from_dn_np).cuda()
+            pm, pu, pd = mine_t.data_ptr(), fu_t.data_ptr(), fd_t.data_ptr()
+        else:
+            pm, pu, pd = mine_np.ctypes.data, from_up_np.ctypes.data, from_dn_np.ctypes.data
+        req = (C.c_long * 4)()
+        if up >= 0:
+            L.tiramisu_MPI_Irecv_f32(n_el, up, 0, C.c_void_p(pu), req)
+        if dn < world:
+            L.tiramisu_MPI_Irecv_f32(n_el, dn, 0, C.c_void_p(pd), req)
+        if up >= 0:
+            L.tiramisu_MPI_Isend_f32(n_el, up, 0, C.c_void_p(pm), req)
+        if dn < world:
+            L.tiramisu_MPI_Isend_f32(n_el, dn, 0, C.c_void_p(pm), req)
+        L.tiramisu_MPI_Wait(req)
+        api.synchronize()
+        if on_dev:
+            from_up_np, from_dn_np = fu_t.cpu().numpy(), fd_t.cpu().numpy()
+        good = True
+        if up >= 0:
+            good &= np.array_equal(from_up_np, np.arange(n_el, dtype=np.float32) + 1000 * up)
+        if dn < world:
+            good &= np.array_equal(from_dn_np, np.arange(n_el, dtype=np.float32) + 1000 * dn)
+        ok &= good
+        print(f"[rank {rank}] tiramisu_MPI Irecv/Isend/Wait neighbour exchange ({'device' if on_dev else 'host'} buffers): "
+              f"{'ok' if good else 'MISMATCH'}", flush=True)
+
     flag = torch.tensor([1 if ok else 0], device="cuda")
     torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
     tdist.comm_destroy()
