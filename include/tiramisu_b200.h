@@ -81,7 +81,8 @@ int tiramisu_cublas_dgemm(double *A, double *B, double *C, uint64_t M, uint64_t 
 int tiramisu_b200_set_gemm_mode(int mode);
 /* Which tcgen05 GEMM kernel the tensor path uses: 0 = auto (by problem size), 1 = one output tile
  * per CTA, 2 = persistent single-CTA tiles (128x256), 3 = persistent CTA pairs (cta_group::2,
- * 256x256).  Tuning/diagnostic knob; returns the previous value. */
+ * 256x256), 4 = split-K: a 2-CTA cluster per 128x128 tile, the two K halves combined through distributed
+ * shared memory (small outputs with a long K, e.g. 1024^3).  Tuning/diagnostic knob; returns the previous value. */
 int tiramisu_b200_set_gemm_kernel(int kernel);
 
 /* src/tiramisu_externs.cpp:8-54 */

@@ -89,11 +89,12 @@ def test_sgemm_tf32_random_within_tolerance(api, tensor, N, M, K):
 
 
 # ------------------------------------------------------------------------------ every tcgen05 kernel variant
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 @pytest.mark.parametrize("N,M,K", [(256, 256, 32), (512, 768, 256), (1024, 1024, 1024), (300, 700, 96),
-                                   (136, 264, 100), (2048, 512, 160)])
+                                   (136, 264, 100), (2048, 512, 160), (1000, 900, 777), (128, 128, 64)])
 def test_sgemm_each_kernel_small_int_exact(api, tensor, kernel, N, M, K):
-    """One-tile-per-CTA (1), persistent 128x256 (2) and persistent CTA-pair 256x256 (3) kernels all
+    """One-tile-per-CTA (1), persistent 128x256 (2), persistent CTA-pair 256x256 (3) and the 2-CTA split-K cluster
+    kernel (4: two K halves combined through distributed shared memory; a K of one slab falls back to 1) all
     give the oracle's result bit for bit on integer operands, including ragged tiles and K tails."""
     prev = api.set_gemm_kernel(kernel)
     try:
@@ -198,6 +199,37 @@ def test_165_B_transposed(api, M, N, K):
     finally:
         api.set_stream(None)
     assert np.array_equal(dC.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("tB", [False, True])
+def test_sgemm_splitk_default_for_config0_shape(api, tensor, tB):
+    """BASELINE configs[0] (1024^3) takes the split-K cluster kernel by default (kernel 0 = auto): random data
+    within the TF32 tolerance, element-wise against |A| |B| (the scale a dot product's rounding is relative to),
+    both B layouts, launched back to back (programmatic dependent launch) on rotating outputs."""
+    import torch
+    rng = np.random.default_rng(12)
+    n = 1024
+    A = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    B = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    C0 = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    outs = [torch.from_numpy(C0).cuda() for _ in range(4)]
+    launches0 = api.kernel_launches()
+    api.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        for dC in outs:
+            api.cublas_sgemm(dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), n, n, n, 3.0, 2.0, tB=tB)
+        torch.cuda.synchronize()
+    finally:
+        api.set_stream(None)
+    assert api.kernel_launches() - launches0 == 4
+    Bm = B.T if tB else B
+    want = 3.0 * (A.astype(np.float64) @ Bm.astype(np.float64)) + 2.0 * C0
+    scale = 3.0 * (np.abs(A).astype(np.float64) @ np.abs(Bm).astype(np.float64)) + 2.0 * np.abs(C0)
+    for dC in outs:
+        got = dC.cpu().numpy()
+        assert (np.abs(got - want) <= TF32_RTOL * scale).all()
+        assert np.array_equal(got, outs[0].cpu().numpy())          # deterministic: fixed summation order
 
 
 def test_165_B_transposed_tensor_path_random(api, tensor):

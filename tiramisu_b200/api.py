@@ -148,7 +148,7 @@ def set_gemm_mode(mode: int) -> int:
 
 
 def set_gemm_kernel(kernel: int) -> int:
-    """0 auto, 1 one-tile-per-CTA, 2 persistent 128x256, 3 persistent CTA pairs (cta_group::2)."""
+    """0 auto, 1 one-tile-per-CTA, 2 persistent 128x256, 3 persistent CTA pairs (cta_group::2), 4 split-K 2-CTA clusters."""
     return int(_lib.lib().tiramisu_b200_set_gemm_kernel(kernel))
 
 

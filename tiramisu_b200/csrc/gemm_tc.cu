@@ -301,6 +301,224 @@ tiramisu_sm100_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid
 
 
 // ================================================================================================
+// Split-K variant for SMALL problems (1024^3: BASELINE configs[0]).  With one 128 x 64 tile per CTA a 1024^3
+// product moves 4*M*N*K*(1/BM + 1/BN) = 100 MB from L2 into shared memory — 8 us at the chip's ~6300 B/clk L2
+// throughput, against a 2.6 us roofline — because tiles that small re-read A and B 16 and 8 times.  Here a
+// CLUSTER OF TWO CTAs shares one 128 x 128 output tile and each takes half of K: 64 tiles x 2 = 128 CTAs keep the
+// machine as full as before while the L2 -> SMEM traffic drops to 64 MB and every MMA is N = 128 wide (one
+// shared-memory operand byte per tensor-pipe cycle instead of 1.5).  The two partial accumulators are combined
+// through distributed shared memory: each CTA finalises 64 of the 128 columns; it pushes the OTHER 64 columns of
+// its partial (128 rows x 256 B) into its peer's receive buffer with st.async — every 16-byte store signals
+// complete_tx on the peer's mbarrier, no fence, no global-memory round trip, deterministic summation order —
+// then adds what it received to its own half, applies alpha/beta and stores.
+// The prologue (barrier init, TMEM allocation, descriptor prefetch) runs under programmatic dependent launch:
+// it overlaps the tail of the previous kernel in the stream; griddepcontrol.wait orders every global access.
+constexpr int SK_BN = 128;
+constexpr int SK_STAGES = 5;
+constexpr int SK_STAGE_BYTES = A_TILE_BYTES + SK_BN * BK * 4;          // 32 KB
+constexpr int SK_RECV_BYTES = BM * (SK_BN / 2) * 4;                     // 128 rows x 64 fp32 = 32 KB
+constexpr int SK_SMEM_BYTES = SK_STAGES * SK_STAGE_BYTES + SK_RECV_BYTES + 1024 + 256;
+
+template <bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+tiramisu_sm100_gemm_tf32_splitk(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                const GemmParams p)
+{
+    constexpr int BN = SK_BN, STAGES = SK_STAGES, B_TILE_BYTES = BN * BK * 4;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + STAGES * A_TILE_BYTES;
+    float *recv = reinterpret_cast<float *>(smem + STAGES * SK_STAGE_BYTES);      // [128 rows][16 x 16-byte chunks], chunk XOR-swizzled by row
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(recv) + SK_RECV_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint64_t *recv_bar = tmem_full_bar + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(recv_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t ks = ptx::cluster_ctarank();              // which half of K (and which 64 output columns it finalises)
+
+    const int t = blockIdx.x >> 1;
+    const int tiles_per_group = p.group_m * p.num_n;
+    const int group = t / tiles_per_group;
+    const int first_m = group * p.group_m;
+    const int gsz = min(p.num_m - first_m, p.group_m);
+    const int tile_m = first_m + (t % tiles_per_group) % gsz;
+    const int tile_n = (t % tiles_per_group) / gsz;
+    const int m0 = tile_m * BM, n0 = tile_n * BN;
+    const int num_kb = (p.K + BK - 1) / BK;                  // >= 2 (launcher)
+    const int kb_half = (num_kb + 1) / 2;
+    const int kb_begin = ks == 0 ? 0 : kb_half, kb_end = ks == 0 ? kb_half : num_kb;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; s++) {
+                ptx::mbar_init(&full_bar[s], 1);
+                ptx::mbar_init(&empty_bar[s], 1);
+            }
+            ptx::mbar_init(tmem_full_bar, 1);
+            ptx::mbar_init(recv_bar, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, BN);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before_sync();
+    ptx::cluster_sync();                                     // the peer's receive barrier exists before any remote store
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    // everything above overlapped the previous kernel's tail; from here on global memory is touched
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == 0) {
+        for (int kb = kb_begin, it = 0; kb < kb_end; kb++, it++) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&full_bar[s], SK_STAGE_BYTES);
+                const int k0 = kb * BK;
+                ptx::tma_load_2d(smem_a + s * A_TILE_BYTES, &map_a, &full_bar[s], k0, m0);
+                uint8_t *bdst = smem_b + s * B_TILE_BYTES;
+                if (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; j++)
+                        ptx::tma_load_2d(bdst + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
+                } else {
+                    ptx::tma_load_2d(bdst, &map_b, &full_bar[s], k0, n0);
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, B_MN);
+        const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), 16, 1024);
+        const uint64_t db0 = B_MN ? ptx::make_smem_desc(ptx::smem_u32(smem_b), p.b_lbo, p.b_sbo, ptx::kLayoutSw128Base32)
+                                  : ptx::make_smem_desc(ptx::smem_u32(smem_b), 16, 1024);
+        constexpr uint32_t kStepA = UMMA_K * 4, kStepB = B_MN ? UMMA_K * 128 : UMMA_K * 4;
+        for (int kb = kb_begin, it = 0; kb < kb_end; kb++, it++) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            ptx::mbar_wait(&full_bar[s], ph);
+            ptx::tc_fence_after_sync();
+            if (ptx::elect_one()) {
+                const uint64_t da = ptx::desc_advance(da0, (uint32_t)s * A_TILE_BYTES);
+                const uint64_t db = ptx::desc_advance(db0, (uint32_t)s * B_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++)
+                    ptx::mma_tf32_ss(tmem_base, ptx::desc_advance(da, k * kStepA), ptx::desc_advance(db, k * kStepB), idesc,
+                                     (it | k) != 0);
+                ptx::mma_commit(&empty_bar[s]);
+                if (kb == kb_end - 1) ptx::mma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: exchange the halves over DSMEM, then TMEM + received -> alpha/beta -> global =====
+        const uint32_t q = (uint32_t)warp & 3u;
+        const uint32_t row_l = q * 32u + (uint32_t)lane;       // row of the tile this thread owns
+        const int row = m0 + (int)row_l;
+        const bool row_ok = row < p.M;
+        const int c_mine = 64 * (int)ks, c_peer = 64 * (1 - (int)ks);
+        float *crow = p.C + (size_t)row * p.ldC;
+        const bool use_c = p.beta != 0.0f;
+        const float alpha = p.alpha_dev ? __fmul_rn(p.alpha, __ldg(p.alpha_dev)) : p.alpha;
+        if (threadIdx.x == 64) ptx::mbar_arrive_expect_tx(recv_bar, (uint32_t)SK_RECV_BYTES);     // the one arrival of this phase
+        auto load_c = [&](int c0, float4 (&cv)[8]) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int col = n0 + c0 + 4 * j;
+                cv[j] = (use_c && row_ok && col + 3 < p.N) ? *reinterpret_cast<const float4 *>(crow + col)
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 cnext[8];
+        load_c(c_mine, cnext);
+        const uint32_t sw = row_l & 15u;
+        const uint32_t push_row = ptx::mapa_u32(reinterpret_cast<uint8_t *>(recv) + row_l * 256u, ks ^ 1u);
+        const uint32_t push_bar = ptx::mapa_u32(recv_bar, ks ^ 1u);
+        ptx::mbar_wait(tmem_full_bar, 0);
+        ptx::tc_fence_after_sync();
+        // 1. the peer's 64 columns of my partial -> its receive buffer
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            uint32_t r[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)(c_peer + 32 * h), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 8; cc++)
+                ptx::st_async_cluster_v4(push_row + (((uint32_t)(8 * h + cc)) ^ sw) * 16u, push_bar, __uint_as_float(r[4 * cc + 0]),
+                                         __uint_as_float(r[4 * cc + 1]), __uint_as_float(r[4 * cc + 2]), __uint_as_float(r[4 * cc + 3]));
+        }
+        // 2. my 64 columns: own partial + the peer's, in a fixed order (K half 0 + K half 1)
+        ptx::mbar_wait_cluster(recv_bar, 0);
+        const float4 *rrow = reinterpret_cast<const float4 *>(reinterpret_cast<uint8_t *>(recv) + row_l * 256u);
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const int c0 = c_mine + 32 * h;
+            float4 ccur[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) ccur[j] = cnext[j];
+            if (h == 0) load_c(c0 + 32, cnext);
+            uint32_t r[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (uint32_t)c0, r);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 other = rrow[((uint32_t)(8 * h + (j >> 2))) ^ sw];
+                    float v[4] = {__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])};
+                    const float o4[4] = {other.x, other.y, other.z, other.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) v[u] = ks == 0 ? __fadd_rn(v[u], o4[u]) : __fadd_rn(o4[u], v[u]);
+                    const int col = n0 + c0 + j;
+                    if (col + 3 < p.N) {
+                        float4 o;
+                        o.x = __fmul_rn(v[0], alpha); o.y = __fmul_rn(v[1], alpha);
+                        o.z = __fmul_rn(v[2], alpha); o.w = __fmul_rn(v[3], alpha);
+                        if (use_c) {
+                            const float4 c = ccur[j >> 2];
+                            o.x = __fadd_rn(o.x, __fmul_rn(c.x, p.beta));
+                            o.y = __fadd_rn(o.y, __fmul_rn(c.y, p.beta));
+                            o.z = __fadd_rn(o.z, __fmul_rn(c.z, p.beta));
+                            o.w = __fadd_rn(o.w, __fmul_rn(c.w, p.beta));
+                        }
+                        *reinterpret_cast<float4 *>(crow + col) = o;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (col + u < p.N) {
+                                float o = __fmul_rn(v[u], alpha);
+                                if (use_c) o = __fadd_rn(o, __fmul_rn(crow[col + u], p.beta));
+                                crow[col + u] = o;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before_sync();
+    ptx::cluster_sync();                                     // nobody exits while its peer may still push into it
+    if (warp == 1) {
+        ptx::tc_fence_after_sync();
+        ptx::tmem_dealloc(tmem_base, BN);
+    }
+}
+
+
+// ================================================================================================
 // Persistent variant for large problems: one CTA (CG = 1) or one CTA pair (CG = 2, cta_group::2)
 // per SM / SM pair loops over 128*CG x 256 output tiles.
 //   warp 0    : TMA producer      warp 1 : MMA issuer (leader CTA only when CG = 2) + TMEM owner
@@ -601,6 +819,60 @@ int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, flo
     return post_launch("tiramisu_sm100_gemm_tf32");
 }
 
+template <bool B_MN>
+int launch_tc_splitk(const float *A, const float *B, float *C, int M, int N, int K, float alpha, float beta, int64_t ldA,
+                     int64_t ldB, int64_t ldC)
+{
+    CUtensorMap map_a, map_b;
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        uint64_t str[1] = {(uint64_t)ldA * 4};
+        uint32_t box[2] = {BK, BM};
+        if (make_tensor_map_f32(&map_a, A, 2, dims, str, box)) return 1;
+    }
+    if (B_MN) {
+        uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
+        uint64_t str[1] = {(uint64_t)ldB * 4};
+        uint32_t box[2] = {32, BK};
+        if (make_tensor_map_f32(&map_b, B, 2, dims, str, box, kTmaSwizzle128Atom32)) return 1;
+    } else {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        uint64_t str[1] = {(uint64_t)ldB * 4};
+        uint32_t box[2] = {BK, (uint32_t)SK_BN};
+        if (make_tensor_map_f32(&map_b, B, 2, dims, str, box)) return 1;
+    }
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.C = C; p.ldC = ldC;
+    p.num_m = (M + BM - 1) / BM;
+    p.num_n = (N + SK_BN - 1) / SK_BN;
+    p.group_m = 16;
+    p.b_lbo = BK * 128;
+    p.b_sbo = 512;
+    p.alpha_dev = nullptr;
+    auto kern = tiramisu_sm100_gemm_tf32_splitk<B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TB200_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.num_m * p.num_n * 2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = SK_SMEM_BYTES;
+    cfg.stream = stream();
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("TB200_GEMM_NO_PDL") ? 1 : 2;
+    TB200_CHECK(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, p));
+    return post_launch("tiramisu_sm100_gemm_tf32_splitk");
+}
+
 template <int BN>
 int launch_tc_f16(const void *A, const void *B, float *C, int M, int N, int K, float alpha, float beta, int64_t ldA,
                   int64_t ldB, int64_t ldC, const float *alpha_dev)
@@ -693,7 +965,7 @@ int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N,
 }
 
 std::atomic<int> g_gemm_mode{0};
-std::atomic<int> g_gemm_kernel{0};       // 0 auto, 1 one-tile-per-CTA, 2 persistent CG=1, 3 persistent CG=2
+std::atomic<int> g_gemm_kernel{0};       // 0 auto, 1 one-tile-per-CTA, 2 persistent CG=1, 3 persistent CG=2, 4 split-K 2-CTA clusters
 
 }  // namespace
 
@@ -741,6 +1013,7 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
     if (const char *e = getenv("TB200_GEMM_KERNEL")) kernel = atoi(e);
     if (t_hint_kernel) kernel = t_hint_kernel;
     const uint64_t sms = (uint64_t)sm_count();
+    const bool auto_kernel = kernel == 0;
     if (kernel == 0) {
         // measured (profiles/r01_results.md): the pair kernel wins from ~2048^2 outputs upwards even
         // when it cannot fill every SM pair (2048^3: 416 vs 339 TFLOP/s); below that the one-tile-per-CTA
@@ -754,6 +1027,16 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
     if (kernel == 2)
         return tB ? launch_tc_persistent<1, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC)
                   : launch_tc_persistent<1, true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
+    // Small outputs with a long K (1024^3): 2-CTA split-K clusters on 128 x 128 tiles when that fills the machine at
+    // least as well as narrow tiles would (kernel 4; TB200_GEMM_KERNEL=1 keeps the one-tile-per-CTA kernel)
+    {
+        const uint64_t t128 = ((M + BM - 1) / BM) * ((N + SK_BN - 1) / SK_BN);
+        const bool fits = 2 * t128 <= sms && K >= 512 && 2 * t128 * 4 >= sms;      // at most one wave, at least a quarter of the SMs
+        if (kernel == 4 || (auto_kernel && kernel == 1 && !t_hint_bn && fits))
+            if (K >= 2 * BK)
+                return tB ? launch_tc_splitk<false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC)
+                          : launch_tc_splitk<true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
+    }
     // Tile width: the widest BN that still yields at least one CTA per SM (148), else 64.
     int bn = 64;
     const uint64_t mt = (M + BM - 1) / BM;
@@ -812,7 +1095,7 @@ TB200_API int tiramisu_b200_set_gemm_mode(int mode)
 
 TB200_API int tiramisu_b200_set_gemm_kernel(int kernel)
 {
-    if (kernel < 0 || kernel > 3) kernel = 0;
+    if (kernel < 0 || kernel > 4) kernel = 0;
     return g_gemm_kernel.exchange(kernel);
 }
 

@@ -698,8 +698,10 @@ struct H16Params {
     const float *bias;          // [4F] packed
     float *h;                   // [T][B][F] fp32 output of this layer, or null (only the last layer's is consumed)
     __half *h16;                // [T][B][F] fp16 copy, the recurrence's own operand
-    uint32_t *step_flags;       // [gridDim.x]: flag c = number of steps CTA c has published (one word per CTA: a
-                                // single counter serialises 64 same-address atomics in L2 every step)
+    uint32_t *step_flags;       // step barrier words, see sync_mode
+    int sync_mode;              // 0: ONE counter, += gridDim.x per finished step (red.add; r01 and the measured best)
+                                // 1: [gridDim.x] per-CTA step flags (plain stores; measured slower: r02 run 1, 7.6 vs 5.9 us/step)
+                                // 2: 8 counters, CTA c adds to counter c & 7 (shorter same-address atomic queues)
     const float *rscale;        // de-scaling factor of the block-scaled fp16 recurrent weights (a power of two)
     const uint32_t *xg_ready;   // null, or: number of leading time steps of xg that are complete
     int dbg;
@@ -715,6 +717,20 @@ __device__ __forceinline__ void grid_wait_flags(const uint32_t *flags, int n, ui
     for (;;) {
         bool ok = true;
         for (int c = lane; c < n; c += 32) ok = ok && ptx::ld_relaxed_gpu(flags + c) >= target;
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+    ptx::fence_acq_rel_gpu();
+}
+
+// sync_mode 2: counter k (128 bytes apart) counts the CTAs with (index & 7) == k; lanes 0..7 watch one each
+__device__ __forceinline__ void grid_wait_counters8(const uint32_t *ctr, int n, uint32_t step)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t mine = lane < 8 ? (uint32_t)((n - lane + 7) / 8) * step : 0u;      // CTAs feeding counter `lane`, times steps
+    const long long t0 = clock64();
+    for (;;) {
+        const bool ok = lane >= 8 || ptx::ld_relaxed_gpu(ctr + 32 * lane) >= mine;
         if (__all_sync(0xffffffffu, ok)) break;
         if (clock64() - t0 > (1ll << 31)) __trap();
     }
@@ -771,7 +787,11 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
         }
         __syncwarp();
         for (int t = 1; t < p.T; t++) {
-            if (!(p.dbg & 1)) grid_wait_flags(p.step_flags, (int)gridDim.x, (uint32_t)t);        // h16[t-1] is complete
+            if (!(p.dbg & 1)) {                                                                   // h16[t-1] is complete
+                if (p.sync_mode == 1) grid_wait_flags(p.step_flags, (int)gridDim.x, (uint32_t)t);
+                else if (p.sync_mode == 2) grid_wait_counters8(p.step_flags, (int)gridDim.x, (uint32_t)t);
+                else grid_wait_relaxed(p.step_flags, (uint32_t)gridDim.x * (uint32_t)t);
+            }
             ptx::fence_proxy_async_all();
             if (ptx::elect_one()) {
                 KS_TRACE(0);
@@ -942,7 +962,9 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
             if (e == 0) {
                 KS_TRACE(2);
                 ptx::fence_acq_rel_gpu();
-                ptx::st_relaxed_gpu(p.step_flags + blockIdx.x, (uint32_t)(t + 1));
+                if (p.sync_mode == 1) ptx::st_relaxed_gpu(p.step_flags + blockIdx.x, (uint32_t)(t + 1));
+                else if (p.sync_mode == 2) ptx::red_relaxed_gpu_add(p.step_flags + 32 * (blockIdx.x & 7), 1u);
+                else ptx::red_relaxed_gpu_add(p.step_flags, 1u);
                 KS_TRACE(7);
             }
         }
@@ -1031,12 +1053,15 @@ tiramisu_sm100_lstm_pack16(const float *__restrict__ Wl, const float *__restrict
 
 // Stream-side halves of the layer pipeline: a one-warp kernel that returns once *ctr >= target (the
 // layer below has published enough steps) and a one-thread kernel that publishes a value.
-__global__ void tiramisu_sm100_wait_counter(const uint32_t *flags, int n, uint32_t target)
+__global__ void tiramisu_sm100_wait_counter(const uint32_t *flags, int n, uint32_t step, int sync_mode)
 {
-    // returns once every one of the n per-CTA step flags has reached `target`
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    // returns once all n CTAs of the layer have published `step` steps (same three encodings as H16Params::sync_mode)
+    const int words = sync_mode == 1 ? n : (sync_mode == 2 ? 8 : 1);
+    for (int c = threadIdx.x; c < words; c += blockDim.x) {
+        const uint32_t *w = sync_mode == 2 ? flags + 32 * c : flags + c;
+        const uint32_t target = sync_mode == 1 ? step : (sync_mode == 2 ? (uint32_t)((n - c + 7) / 8) * step : (uint32_t)n * step);
         const long long t0 = clock64();
-        while (ptx::ld_acquire_gpu(flags + c) < target) {
+        while (ptx::ld_acquire_gpu(w) < target) {
             if (clock64() - t0 > (1ll << 32)) __trap();
             __nanosleep(500);
         }
@@ -1270,11 +1295,14 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
     float *bp = reinterpret_cast<float *>(pool_alloc((size_t)L * 4 * F * 4));
     float *xg = reinterpret_cast<float *>(pool_alloc((size_t)2 * TB * 4 * F * 4));         // input contributions, by layer parity
     __half *h16 = reinterpret_cast<__half *>(pool_alloc((size_t)2 * TB * F * 2));          // h fp16, by layer parity
-    // [L][64] per-CTA step flags, [L] xg_ready, [2L] weight max-abs bit patterns, scratch word; then [2L] scale, [2L] 1/scale
-    const size_t n_words = (size_t)64 * L + L + 2 * L + 1;
+    // [L][256] step barrier words (one counter, 64 per-CTA flags or 8 counters 128 B apart), [L] xg_ready, [2L] weight
+    // max-abs bit patterns, scratch word; then [2L] scale, [2L] 1/scale
+    const size_t n_words = (size_t)256 * L + L + 2 * L + 1;
+    int sync_mode = 0;
+    if (const char *e = getenv("TB200_LSTM_SYNC")) sync_mode = atoi(e) == 1 ? 1 : (atoi(e) == 2 ? 2 : 0);
     uint32_t *flags = reinterpret_cast<uint32_t *>(pool_alloc((n_words + 4 * (size_t)L) * 4));
     if (!R16 || !Wp || !Wp16 || !bp || !xg || !h16 || !flags) return 1;
-    uint32_t *step_flags = flags, *xg_ready = flags + 64 * L, *maxbits = xg_ready + L, *scratch = maxbits + 2 * L;
+    uint32_t *step_flags = flags, *xg_ready = flags + 256 * L, *maxbits = xg_ready + L, *scratch = maxbits + 2 * L;
     float *wscale = reinterpret_cast<float *>(flags + n_words), *winv = wscale + 2 * L;
     TB200_CHECK(cudaMemsetAsync(flags, 0, n_words * 4, stream()));
     const int nctas = F / 16;                                    // <= 64 (F <= 1024)
@@ -1327,7 +1355,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
         H16Params hp;
         hp.B = B; hp.F = F; hp.T = T;
         hp.xg = xg_of(l); hp.bias = bp + (size_t)l * 4 * F; hp.h = out_of(l); hp.h16 = hh;
-        hp.step_flags = step_flags + 64 * l; hp.rscale = winv + 2 * l; hp.xg_ready = ready; hp.dbg = dbg; hp.trace = trace;
+        hp.step_flags = step_flags + 256 * l; hp.sync_mode = sync_mode; hp.rscale = winv + 2 * l; hp.xg_ready = ready; hp.dbg = dbg; hp.trace = trace;
         cudaLaunchAttribute attr[1];
         cudaLaunchConfig_t cfg = h16_config(F, attr, st);
         TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16, map_h, map_r, hp));
@@ -1361,7 +1389,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
         // traps).  One tiny launch of each, once per process, on the main stream.
         static std::atomic<bool> warmed{false};
         if (!warmed.load()) {
-            tiramisu_sm100_wait_counter<<<1, 64, 0, main_st>>>(scratch, 1, 0u);
+            tiramisu_sm100_wait_counter<<<1, 64, 0, main_st>>>(scratch, 1, 0u, 0);
             if (post_launch("tiramisu_sm100_wait_counter")) return 1;
             tiramisu_sm100_publish<<<1, 1, 0, main_st>>>(scratch, 0u);
             if (post_launch("tiramisu_sm100_publish")) return 1;
@@ -1393,7 +1421,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
             for (int t0 = 0, n = 0; t0 < T && !rc; n++) {
                 const int len = n == 0 ? (chunk < 4 ? chunk : 4) : (n == 1 ? (chunk < 6 ? chunk : 6) : chunk);
                 const int t1 = t0 + len < T ? t0 + len : T;
-                tiramisu_sm100_wait_counter<<<1, 64, 0, ps->gemm>>>(step_flags + 64 * l, nctas, (uint32_t)t1);
+                tiramisu_sm100_wait_counter<<<1, 64, 0, ps->gemm>>>(step_flags + 256 * l, nctas, (uint32_t)t1, sync_mode);
                 rc = post_launch("tiramisu_sm100_wait_counter");
                 if (!rc) rc = launch_xg(l + 1, t0, t1);
                 if (!rc) {

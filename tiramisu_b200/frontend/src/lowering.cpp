@@ -272,6 +272,11 @@ std::string Lowering::run()
         << "template <typename T> __host__ __device__ __forceinline__ T tb_max(T a, T b) { return a > b ? a : b; }\n"
         << "template <typename T> __host__ __device__ __forceinline__ T tb_min(T a, T b) { return a < b ? a : b; }\n"
         << "template <typename T> __host__ __device__ __forceinline__ T tb_abs(T a) { return a < 0 ? -a : a; }\n"
+        << "// floor division / Euclidean remainder (Halide Div / Mod semantics; 0 for a zero divisor, like Halide)\n"
+        << "template <typename T> __host__ __device__ __forceinline__ T tb_floordiv(T a, T b) {\n"
+        << "    if (b == 0) return 0;\n    T r = a % b;\n    if (r < 0) r += (b < 0 ? -b : b);\n    return (a - r) / b;\n}\n"
+        << "template <typename T> __host__ __device__ __forceinline__ T tb_floormod(T a, T b) {\n"
+        << "    if (b == 0) return 0;\n    T r = a % b;\n    return r < 0 ? r + (b < 0 ? -b : b) : r;\n}\n"
         << "// Halide's lerp: an unsigned integer weight is a fixed-point fraction of its type's maximum\n"
         << "template <typename T, typename W> __host__ __device__ __forceinline__ T tb_lerp(T a, T b, W w) {\n"
         << "    const double wf = std::is_floating_point<W>::value ? (double) w : (double) w / (double) (W) ~(W) 0;\n"
@@ -326,18 +331,26 @@ std::string Lowering::run()
             out << pad(2) << "tiramisu_cuda_memcpy_to_device_async(b_" << N << ", h_" << N << ", nb_" << N << ");\n";
         out << pad(1) << "}\n";
     }
-    out << body.str();
+    // The statements run inside a lambda so that a failed launch (`return 1` in the middle of the body) still reaches
+    // the common exit below: device mirrors and temporaries are released on every path, outputs are copied back
+    // only when everything succeeded.
+    out << pad(1) << "const int tb_rc = [&]() -> int {\n" << body.str() << pad(1) << "return 0;\n" << pad(1) << "}();\n";
     for (buffer *b : args_) {
         if (!mirrored_.count(b) || direct_.count(b)) continue;
         const std::string N = san(b->get_name());
         out << pad(1) << "if (h_" << N << ") {\n";
         if (b->get_argument_type() == a_output || written_args_.count(b))
-            out << pad(2) << "tiramisu_cuda_memcpy_to_host(h_" << N << ", b_" << N << ", nb_" << N << ");\n";
+            out << pad(2) << "if (tb_rc == 0) tiramisu_cuda_memcpy_to_host(h_" << N << ", b_" << N << ", nb_" << N << ");\n";
         out << pad(2) << "tiramisu_cuda_free(b_" << N << ");\n" << pad(1) << "}\n";
     }
     for (auto it = autos.rbegin(); it != autos.rend(); ++it)
         out << pad(1) << ((*it)->get_location() == mem_loc::gpu_global ? "tiramisu_cuda_free(" : "free(") << "b_" << san((*it)->get_name()) << ");\n";
-    out << pad(1) << "return 0;\n}\n\n";
+    // temporaries with an explicit allocate() that the failing path never reached the free() of
+    for (buffer *b : f_->get_buffers())
+        if (!is_arg.count(b) && !b->get_auto_allocate() && (b->get_location() == mem_loc::host || b->get_location() == mem_loc::gpu_global))
+            out << pad(1) << "if (tb_rc && b_" << san(b->get_name()) << ") " << (b->get_location() == mem_loc::gpu_global ? "tiramisu_cuda_free(" : "free(")
+                << "b_" << san(b->get_name()) << ");\n";
+    out << pad(1) << "return tb_rc;\n}\n\n";
     out << "extern \"C\" int " << f_->get_name() << "_argv(void **args)\n{\n" << pad(1) << "return " << f_->get_name() << "(";
     for (size_t i = 0; i < args_.size(); i++) out << (i ? ", " : "") << "(halide_buffer_t *) args[" << i << "]";
     out << ");\n}\n";

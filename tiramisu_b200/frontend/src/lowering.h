@@ -110,6 +110,8 @@ private:
     void distribute_parallel_shared_loops(const std::vector<computation *> &ord);
     void map_fused_parallel_loops(const std::vector<computation *> &ord);
     bool dim_is_parallel(computation *c, const std::string &dim);
+    std::set<std::string> parallel_iterators(computation *c);     // jointly injective in the stored element
+    std::map<computation *, std::set<std::string>> parallel_iters_;
     struct Access { buffer *b; std::vector<expr> idx; bool write; };
     std::vector<Access> accesses_of(computation *c);
     std::set<computation *> grid_fused_;          // statements of a fused run whose shared data-parallel loops became the grid

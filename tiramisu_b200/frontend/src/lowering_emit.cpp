@@ -237,8 +237,22 @@ std::string Lowering::print(const expr &e, bool device)
     case o_add: return narrow("(" + A(0) + " + " + A(1) + ")");
     case o_sub: return narrow("(" + A(0) + " - " + A(1) + ")");
     case o_mul: return narrow("(" + A(0) + " * " + A(1) + ")");
-    case o_div: return narrow("(" + A(0) + " / " + A(1) + ")");
-    case o_mod: return is_float_type(t) ? std::string(t == p_float32 ? "fmodf(" : "fmod(") + A(0) + ", " + A(1) + ")" : narrow("(" + A(0) + " % " + A(1) + ")");
+    case o_div: case o_mod: {
+        // Integer division rounds towards minus infinity and the remainder is never negative in the reference's
+        // lowering (Halide Div / Mod, src/tiramisu_codegen_halide.cpp:3563-3569); C's operators truncate.  The plain
+        // operators are emitted only when interval analysis proves both operands non-negative (or the type is
+        // unsigned): A((i - 1) % 16) at i = 0 must read A[15], not A[-1].
+        if (is_float_type(t)) {
+            if (o == o_div) return narrow("(" + A(0) + " / " + A(1) + ")");
+            return std::string(t == p_float32 ? "fmodf(" : "fmod(") + A(0) + ", " + A(1) + ")";
+        }
+        const bool is_unsigned = t == p_uint8 || t == p_uint16 || t == p_uint32 || t == p_uint64 || t == p_boolean;
+        int64_t al = 0, ah = 0, bl = 0, bh = 0;
+        const bool nonneg = is_unsigned || (bounds(inline_defs(e.get_operand(0)), env_, al, ah) && al >= 0 &&
+                                            bounds(inline_defs(e.get_operand(1)), env_, bl, bh) && bl > 0);
+        if (nonneg) return narrow("(" + A(0) + (o == o_div ? " / " : " % ") + A(1) + ")");
+        return narrow(std::string(o == o_div ? "tb_floordiv<" : "tb_floormod<") + ctype(t) + ">(" + A(0) + ", " + A(1) + ")");
+    }
     case o_logical_and: return "(" + A(0) + " && " + A(1) + ")";
     case o_logical_or: return "(" + A(0) + " || " + A(1) + ")";
     case o_logical_not: return "(!" + A(0) + ")";
@@ -330,8 +344,11 @@ void Lowering::emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind)
         const char *ax[] = {"x", "y", "z"};
         if (n->tag == loop_dim::gpu_block || n->tag == loop_dim::gpu_thread) {
             const bool zero = n->lo.is_int_literal() && n->lo.get_int_val() == 0;
-            os << pad(ind) << "const " << it << " " << n->cname() << " = " << (zero ? "" : print(n->lo, true) + " + ") << "(" << it << ") "
-               << (n->tag == loop_dim::gpu_block ? "blockIdx." : "threadIdx.") << ax[n->axis] << ";\n";
+            // blockIdx.y / .z are limited to 65535: the launch walks taller grids in slices and passes the slice origin
+            const std::string idx = n->tag == loop_dim::gpu_thread ? std::string("threadIdx.") + ax[n->axis]
+                                    : n->axis == 0 ? std::string("blockIdx.x")
+                                                   : std::string("(blockIdx.") + ax[n->axis] + " + tb_b" + ax[n->axis] + "0)";
+            os << pad(ind) << "const " << it << " " << n->cname() << " = " << (zero ? "" : print(n->lo, true) + " + ") << "(" << it << ") " << idx << ";\n";
             for (auto &c : n->kids) emit_device(c.get(), k, os, ind);
         } else if (n->warp_reduce && n->kids.size() == 1 && !n->kids.front()->is_loop) {
             emit_warp_reduction(n, os, ind);
@@ -448,14 +465,21 @@ void Lowering::emit_kernel(Node *n, std::ostringstream &host, int ind, std::vect
         params.push_back(std::string("const ") + ctype(global::get_loop_iterator_data_type()) + " " + l->cname());
         actuals.push_back(l->cname());
     }
+    params.push_back("const unsigned tb_by0");
+    params.push_back("const unsigned tb_bz0");
+    actuals.push_back("tb_by0");
+    actuals.push_back("tb_bz0");
     for (size_t i = 0; i < params.size(); i++) os << (i ? ", " : "") << params[i];
     os << ")\n{\n" << body.str() << "}\n\n";
 
     // ---- launch
     host << pad(ind) << "{\n";
-    host << pad(ind + 1) << "dim3 grid((unsigned) (" << print(k.grid[0], false) << "), (unsigned) (" << print(k.grid[1], false) << "), (unsigned) (" << print(k.grid[2], false) << "));\n";
+    host << pad(ind + 1) << "const dim3 full((unsigned) (" << print(k.grid[0], false) << "), (unsigned) (" << print(k.grid[1], false) << "), (unsigned) (" << print(k.grid[2], false) << "));\n";
     host << pad(ind + 1) << "dim3 block((unsigned) (" << print(k.block[0], false) << "), (unsigned) (" << print(k.block[1], false) << "), (unsigned) (" << print(k.block[2], false) << "));\n";
-    host << pad(ind + 1) << "if (grid.x && grid.y && grid.z) {\n";
+    // gridDim.y / .z hold at most 65535 blocks: taller grids are launched in slices, the slice origin is a kernel argument
+    host << pad(ind + 1) << "for (unsigned tb_bz0 = 0; full.x && tb_bz0 < full.z; tb_bz0 += 65535u)\n";
+    host << pad(ind + 1) << "for (unsigned tb_by0 = 0; tb_by0 < full.y; tb_by0 += 65535u) {\n";
+    host << pad(ind + 2) << "const dim3 grid(full.x, tb_min<unsigned>(65535u, full.y - tb_by0), tb_min<unsigned>(65535u, full.z - tb_bz0));\n";
     host << pad(ind + 2) << k.name << "<<<grid, block, 0, (cudaStream_t) tiramisu_b200_get_stream()>>>(";
     for (size_t i = 0; i < actuals.size(); i++) host << (i ? ", " : "") << actuals[i];
     host << ");\n";

@@ -223,12 +223,86 @@ void Lowering::emit_warp_reduction(Node *loop, std::ostringstream &os, int ind)
     enter_stmt(nullptr);
 }
 
-// A scheduled dimension is data-parallel iff every original iterator rebuilt from it indexes the stored element
-// (each iteration writes its own element); a dimension that feeds no original iterator is not.
+// Which original iterators of a statement may run in parallel: the map (iterators) -> (stored element) must be
+// JOINTLY injective over them, otherwise two threads would read-modify-write one element (S(i,j) stored at
+// b_O[i+j], a polynomial multiply, has every iterator in the store index and is still a reduction along the
+// anti-diagonals).  Triangular elimination over the store index expressions: an iterator that is the only
+// not-yet-determined one of an affine index is determined by it; iterators that share an index are all determined
+// only when strides and extents separate them (mixed radix: i*16 + j with 0 <= j < 16), else one of them (largest
+// stride, outermost on ties) is kept and the others are sequential.  An iterator that occurs in a non-affine index
+// (y/2, i%4: several iterations per element, the 2x2 max-pool of conv_relu_maxpool_generator_tiramisu.cpp:104) or
+// in no index at all (a reduction) is sequential.
+std::set<std::string> Lowering::parallel_iterators(computation *c)
+{
+    std::set<std::string> det, seq;
+    std::vector<std::string> iters;
+    for (const var &v : c->get_iteration_variables()) iters.push_back(v.get_name());
+    auto is_iter = [&](const std::string &n) { return std::find(iters.begin(), iters.end(), n) != iters.end(); };
+    struct Idx { bool affine; std::map<std::string, int64_t> coef; };
+    std::vector<Idx> idx;
+    for (const expr &a : c->access()) {
+        Idx x; int64_t cst = 0;
+        x.affine = affine_form(a, x.coef, cst);
+        if (!x.affine) {
+            for (const std::string &n : iters)
+                if (!a.substitute({n}, {expr((int32_t) 0)}).is_equal(a) || (a.get_expr_type() == e_var && a.get_name() == n)) seq.insert(n);
+            continue;
+        }
+        for (auto it = x.coef.begin(); it != x.coef.end();) it = (it->second == 0 || !is_iter(it->first)) ? x.coef.erase(it) : std::next(it);
+        idx.push_back(x);
+    }
+    auto extent_of = [&](const std::string &n, int64_t &ext) {
+        for (const var &v : c->get_iteration_variables())
+            if (v.get_name() == n && v.has_range()) {
+                expr e = v.get_upper() - v.get_lower();
+                if (e.is_int_literal()) { ext = e.get_int_val(); return true; }
+            }
+        return false;
+    };
+    for (;;) {
+        bool progress = false, open = false;
+        for (const Idx &x : idx) {
+            std::vector<std::string> u;
+            for (auto &kv : x.coef) if (!det.count(kv.first) && !seq.count(kv.first)) u.push_back(kv.first);
+            if (u.size() == 1) { det.insert(u[0]); progress = true; }
+            else if (u.size() > 1) open = true;
+        }
+        if (progress) continue;
+        if (!open) break;
+        for (const Idx &x : idx) {
+            std::vector<std::pair<int64_t, std::string>> u;                 // (|stride|, name) of the undetermined iterators
+            for (auto &kv : x.coef) if (!det.count(kv.first) && !seq.count(kv.first)) u.push_back({kv.second < 0 ? -kv.second : kv.second, kv.first});
+            if (u.size() < 2) continue;
+            std::stable_sort(u.begin(), u.end(), [](const std::pair<int64_t, std::string> &a, const std::pair<int64_t, std::string> &b) { return a.first < b.first; });
+            bool separable = true;
+            for (size_t k = 0; k + 1 < u.size() && separable; k++) {
+                int64_t ext = 0;
+                separable = extent_of(u[k].second, ext) && u[k + 1].first >= u[k].first * ext;
+            }
+            if (separable) {
+                for (auto &e : u) det.insert(e.second);
+            } else {
+                // keep the iterator with the largest stride (the outermost in iteration order among equals)
+                size_t keep = u.size() - 1;
+                for (size_t k = 0; k < u.size(); k++)
+                    if (u[k].first == u.back().first) { keep = k; break; }
+                for (size_t k = 0; k < u.size(); k++) (k == keep ? det : seq).insert(u[k].second);
+            }
+            break;
+        }
+    }
+    for (const std::string &n : seq) det.erase(n);
+    return det;
+}
+
+// A scheduled dimension is data-parallel iff every original iterator rebuilt from it is one of the jointly
+// injective ones above (each iteration writes its own element); a dimension that feeds no original iterator is not.
 bool Lowering::dim_is_parallel(computation *c, const std::string &dim)
 {
     if (!c->has_access() && !c->get_expr().is_defined()) return false;
     c->get_buffer();
+    auto hit = parallel_iters_.find(c);
+    if (hit == parallel_iters_.end()) hit = parallel_iters_.emplace(c, parallel_iterators(c)).first;
     bool feeds_any = false;
     for (const var &v : c->get_iteration_variables()) {
         expr full = expr::make_var(p_int32, v.get_name());
@@ -236,17 +310,7 @@ bool Lowering::dim_is_parallel(computation *c, const std::string &dim)
         const bool feeds = !full.substitute({dim}, {expr((int32_t) 7)}).is_equal(full);
         if (!feeds) continue;
         feeds_any = true;
-        // ... and indexes it injectively: an index such as y/2 or i%4 sends several iterations to one element
-        // (the 2x2 max-pool of conv_relu_maxpool_generator_tiramisu.cpp:104 is a reduction over y and x)
-        bool stored = false;
-        for (const expr &a : c->access()) {
-            const bool uses = !a.substitute({v.get_name()}, {expr((int32_t) 0)}).is_equal(a) || (a.get_expr_type() == e_var && a.get_name() == v.get_name());
-            if (!uses) continue;
-            std::map<std::string, int64_t> coef; int64_t cst = 0;
-            if (!affine_form(a, coef, cst) || coef[v.get_name()] == 0) return false;
-            stored = true;
-        }
-        if (!stored) return false;
+        if (!hit->second.count(v.get_name())) return false;
     }
     return feeds_any;
 }
@@ -296,7 +360,12 @@ void Lowering::distribute_parallel_shared_loops(const std::vector<computation *>
                     seen.insert(seen.end(), mine.begin(), mine.end());
                 }
             }
-            if (ok && keep < common)
+            // Only levels below `common` were checked: a boundary fused deeper than that (S1.then(S2, k) inside a
+            // run fused at i) would lose a level nobody looked at — S2 would read the final t[i] instead of the running
+            // one.  Such runs keep their order as written.
+            bool uniform = true;
+            for (size_t k = i + 1; k < j; k++) uniform &= fuse_depth(ord[k - 1], ord[k]) == common;
+            if (ok && uniform && keep < common)
                 for (size_t k = i + 1; k < j; k++)
                     if (fuse_depth(ord[k - 1], ord[k]) > keep) ord[k]->set_pred_level_index(keep - 1);
         }
