@@ -49,6 +49,10 @@ uint64_t tiramisu_b200_kernel_launches(void);
  * each `<<<>>>` launch: counts the launch and reports a launch error like the reference's kernel
  * wrappers do (src/tiramisu_codegen_cuda.cpp:855-866).  Returns 0 on success. */
 int tiramisu_b200_post_launch(const char *kernel_name);
+/* Measurement aid: launches an EMPTY kernel of the given shape (grid, block, dynamic shared memory, cluster width)
+ * on the thread's stream — the launch floor that a few-microsecond kernel sits on (bench.py reports it next to
+ * the 1024^3 GEMM). */
+int tiramisu_b200_null_launch(int32_t grid, int32_t block, int32_t smem_bytes, int32_t cluster);
 /* Release cached pool memory back to the driver. */
 int tiramisu_b200_pool_trim(void);
 

@@ -29,6 +29,9 @@ CASES = {
     "matvec_cpu_generic": ("matvec_cpu_gen.cpp", "matvec_cpu_generic", "generic"),         # one row per thread, statement order
     "sgemm_cpu_sched_gen": ("sgemm_cpu_sched_gen.cpp", "sgemm_cpu_sched_gen", "generic"),   # three SIMT kernels, bit-exact
     "fused_reduce_cpu_gen": ("fused_reduce_cpu_gen.cpp", "fused_reduce_cpu_gen", None),    # fused i/j/k nest: i, j -> grid, k in the thread
+    # advisor findings of round 1: a store index shared by two iterators; a fused run with unequal fuse depths
+    "polymul_cpu_gen": ("polymul_cpu_gen.cpp", "polymul_cpu_gen", None),
+    "prefix_fuse_cpu_gen": ("prefix_fuse_cpu_gen.cpp", "prefix_fuse_cpu_gen", None),
     "sgemm_cpu_sched_tc": ("sgemm_cpu_sched_gen.cpp", "sgemm_cpu_sched_tc", None),           # statement triple -> one tcgen05 GEMM
 }
 

@@ -588,3 +588,41 @@ def test_matvec_warp_shuffle_reduction(mn):
         got2 = np.zeros(m, np.float32)
         _call(_load("matvec_cpu_generic"), "matvec_cpu_generic", np.array([m, n], np.int32), A, x, y0, got2)
         assert np.array_equal(got2, seq)
+
+
+def _polymul_case():
+    rng = np.random.default_rng(23)
+    n, m = 300, 77
+    A = rng.integers(-4, 5, n).astype(np.float32)
+    B = rng.integers(-4, 5, m).astype(np.float32)
+    return n, m, A, B, np.convolve(A.astype(np.float64), B.astype(np.float64)).astype(np.float32)
+
+
+def _prefix_case():
+    rng = np.random.default_rng(24)
+    n, k = 37, 21
+    A = rng.integers(-4, 5, (n, k)).astype(np.float32)
+    return n, k, A, np.cumsum(A.astype(np.float64), axis=1).sum(axis=1).astype(np.float32)
+
+
+@pytest.mark.gpu
+def test_store_index_shared_by_two_iterators_is_not_mapped_in_parallel():
+    """polymul_cpu_gen: S(i, j) stored at b_O[i + j].  Both iterators are in the store index, but the
+    map is not injective: mapped over the grid the read-modify-writes race and sums are lost.  Small integers:
+    the full convolution is exact in fp32, any lost update shows."""
+    lib = _load("polymul_cpu_gen")
+    n, m, A, B, want = _polymul_case()
+    got = np.zeros(n + m - 1, np.float32)
+    _call(lib, "polymul_cpu_gen", np.array([n, m], np.int32), A, B, got)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_fused_run_with_unequal_fuse_depths_keeps_its_order():
+    """prefix_fuse_cpu_gen: S2 is fused with S1 inside k and must see the RUNNING sum t[i]; loop
+    distribution down to whole-box statements would hand it the final one (u = K * total)."""
+    lib = _load("prefix_fuse_cpu_gen")
+    n, k, A, want = _prefix_case()
+    got = np.full(n, -7.0, np.float32)
+    _call(lib, "prefix_fuse_cpu_gen", np.array([n, k], np.int32), A, got)
+    assert np.array_equal(got, want)

@@ -145,6 +145,57 @@ def test_emulated_matvec_generic(cases, mn):
     assert np.array_equal(y, y0 + A @ x)
 
 
+def test_emulated_advisor_cases_polymul_and_unequal_fuse_depths(cases):
+    """The two miscompiles ADVICE.md (round 1) reproduced.  (1) polymul_cpu_gen: S(i, j) stored at b_O[i + j] — the
+    generated kernel must keep BOTH loops in one thread (an emulated run cannot see a race, so the source is
+    inspected: no blockIdx / threadIdx feeds the statement) and the result is the full convolution.
+    (2) prefix_fuse_cpu_gen: S2 fused with S1 inside k reads the running sum; un-fusing the run would give K * total."""
+    src = open(bc.generated_source("polymul_cpu_gen")).read()
+    kern = src[src.index("__global__"):src.index('extern "C" int polymul_cpu_gen')]
+    assert "threadIdx" not in kern and "__launch_bounds__(1)" in kern and kern.count("for (") == 2
+    rng = np.random.default_rng(23)
+    n, m = 300, 77
+    A = rng.integers(-4, 5, n).astype(np.float32)
+    B = rng.integers(-4, 5, m).astype(np.float32)
+    got = np.zeros(n + m - 1, np.float32)
+    _call(_emulated("polymul_cpu_gen"), "polymul_cpu_gen", np.array([n, m], np.int32), A, B, got)
+    assert np.array_equal(got, np.convolve(A.astype(np.float64), B.astype(np.float64)).astype(np.float32))
+
+    rng = np.random.default_rng(24)
+    n, k = 37, 21
+    A2 = rng.integers(-4, 5, (n, k)).astype(np.float32)
+    got = np.full(n, -7.0, np.float32)
+    _call(_emulated("prefix_fuse_cpu_gen"), "prefix_fuse_cpu_gen", np.array([n, k], np.int32), A2, got)
+    assert np.array_equal(got, np.cumsum(A2.astype(np.float64), axis=1).sum(axis=1).astype(np.float32))
+
+
+def test_floor_division_and_modulo_follow_the_reference(tmp_path):
+    """Integer / and % in generated code are Halide's (floor division, non-negative remainder:
+    src/tiramisu_codegen_halide.cpp:3563-3569), not C's truncation: the helpers the lowering emits for operands
+    whose sign it cannot prove, compiled and run on the host."""
+    import subprocess
+    src = open(bc.generated_source("polymul_cpu_gen")).read()
+    a = src.index("template <typename T> __host__ __device__ __forceinline__ T tb_floordiv")
+    b = src.index("// Halide's lerp")
+    helpers = src[a:b].replace("__host__ __device__ __forceinline__", "inline")
+    prog = tmp_path / "fd.cpp"
+    prog.write_text("#include <cstdio>\n" + helpers + """
+int main() {
+    int bad = 0;
+    for (int a = -40; a <= 40; a++) for (int b = -7; b <= 7; b++) {
+        if (b == 0) { bad += tb_floordiv<int>(a, b) != 0 || tb_floormod<int>(a, b) != 0; continue; }
+        const int q = tb_floordiv<int>(a, b), r = tb_floormod<int>(a, b);
+        bad += !(r >= 0 && r < (b < 0 ? -b : b) && q * b + r == a);
+    }
+    printf("%d\\n", bad);
+    return bad != 0;
+}
+""")
+    exe = tmp_path / "fd"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", str(prog), "-o", str(exe)], env={k: v for k, v in os.environ.items() if k not in ("CC", "CXX")})
+    assert subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip() == "0"
+
+
 @pytest.mark.parametrize("variant", ["lstm_cpu_so", "lstm_cpu_so_generic"])
 def test_emulated_reference_lstm_generator(variant):
     """The reference's LSTM/cpu/generator.cpp, compiled unmodified by the front-end (tests/compat/build_generators.py),

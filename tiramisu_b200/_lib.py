@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_get_stream", vp)
     sig("tiramisu_b200_kernel_launches", u64)
     sig("tiramisu_b200_pool_trim", C.c_int)
+    sig("tiramisu_b200_null_launch", C.c_int, i32, i32, i32, i32)
     sig("tiramisu_b200_set_gemm_mode", C.c_int, C.c_int)
     sig("tiramisu_b200_set_gemm_kernel", C.c_int, C.c_int)
     sig("tiramisu_cuda_memcpy_to_device", C.c_int, vp, vp, u64)

@@ -20,6 +20,7 @@
 #include "tiramisu_b200.h"
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 using namespace tb200;
@@ -45,39 +46,59 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
-                        const uint64_t *strides_bytes, const uint32_t *box, int swizzle)
+// Descriptors are pure functions of (base, shape, pitches, box, swizzle, element type): a small per-thread cache
+// keyed by exactly those fields removes cuTensorMapEncodeTiled from the launch path of repeated calls — at 1024^3
+// the two encodes per GEMM were a visible part of a ~12 us host-side launch period (r02 run 2), and generated
+// host loops (the lowered LSTM: 1600 GEMM calls on the same few operands) re-encoded the same maps every iteration.
+struct TmapKey {
+    const void *base;
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+    int rank, swizzle, dtype;
+    bool operator==(const TmapKey &o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool valid = false; };
+constexpr int kTmapSlots = 256;
+
+static int make_tensor_map_cached(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                                  const uint32_t *box, int swizzle, int dtype /* 0 fp32, 1 fp16 */, const char *who)
 {
+    static thread_local TmapSlot *slots = new TmapSlot[kTmapSlots]();
+    TmapKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.rank = rank; k.swizzle = swizzle; k.dtype = dtype;
+    uint64_t h = reinterpret_cast<uintptr_t>(base) * 0x9E3779B97F4A7C15ull + (uint64_t)rank * 31 + (uint64_t)swizzle * 7 + (uint64_t)dtype;
+    for (int i = 0; i < rank; i++) { k.dims[i] = dims[i]; k.box[i] = box[i]; h = (h ^ dims[i]) * 0x100000001B3ull; h = (h ^ box[i]) * 0x100000001B3ull; }
+    for (int i = 0; i + 1 < rank; i++) { k.strides[i] = strides_bytes[i]; h = (h ^ strides_bytes[i]) * 0x100000001B3ull; }
+    TmapSlot &s = slots[(h >> 17) % kTmapSlots];
+    if (s.valid && s.key == k) { *map = s.map; return 0; }
     EncodeTiledFn fn = encode_fn();
-    if (!fn) return fail("make_tensor_map_f32", "cuTensorMapEncodeTiled unavailable");
+    if (!fn) return fail(who, "cuTensorMapEncodeTiled unavailable");
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bx[5], estr[5];
     for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
     for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(map, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                    const_cast<void *>(base), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     swizzle == kTmaSwizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B
                     : swizzle == kTmaSwizzle128Atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                                                       : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("make_tensor_map_f32", "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    if (r != CUDA_SUCCESS) return fail(who, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    s.key = k; s.map = *map; s.valid = true;
     return 0;
+}
+
+int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
+                        const uint64_t *strides_bytes, const uint32_t *box, int swizzle)
+{
+    return make_tensor_map_cached(map, base, rank, dims, strides_bytes, box, swizzle, 0, "make_tensor_map_f32");
 }
 
 int make_tensor_map_f16(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
                         const uint64_t *strides_bytes, const uint32_t *box)
 {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return fail("make_tensor_map_f16", "cuTensorMapEncodeTiled unavailable");
-    cuuint64_t gdim[5], gstr[4];
-    cuuint32_t bx[5], estr[5];
-    for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
-    for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("make_tensor_map_f16", "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-    return 0;
+    return make_tensor_map_cached(map, base, rank, dims, strides_bytes, box, kTmaSwizzle128, 1, "make_tensor_map_f16");
 }
 
 // Per-thread overrides used by callers that place GEMMs next to other resident kernels (the LSTM
@@ -111,6 +132,7 @@ struct GemmParams {
     uint32_t b_lbo, b_sbo;              // MN-major B descriptor offsets (bytes)
     const float *alpha_dev;             // optional device-resident factor multiplied into alpha (LSTM: the
                                         // power-of-two de-scaling of block-scaled fp16 weights), else null
+    int prefetch_kb;                    // L2 prefetch distance in k-slabs beyond the shared-memory ring (0 = off)
 };
 
 // F16: operands are fp16 (kind::f16, K = 16 per instruction, 64 elements per 128-byte swizzle row):
@@ -379,6 +401,20 @@ tiramisu_sm100_gemm_tf32_splitk(const __grid_constant__ CUtensorMap map_a, const
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
+        // the k-slabs beyond the ring go to L2 right away: the whole K half of this CTA is requested from DRAM in
+        // the first microsecond instead of ring-depth slabs at a time
+        if (p.prefetch_kb && ptx::elect_one()) {
+            for (int kb = kb_begin + STAGES; kb < kb_end && kb < kb_begin + STAGES + p.prefetch_kb; kb++) {
+                ptx::tma_prefetch_2d(&map_a, kb * BK, m0);
+                if (B_MN) {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; j++) ptx::tma_prefetch_2d(&map_b, n0 + 32 * j, kb * BK);
+                } else {
+                    ptx::tma_prefetch_2d(&map_b, kb * BK, n0);
+                }
+            }
+        }
+        __syncwarp();
         for (int kb = kb_begin, it = 0; kb < kb_end; kb++, it++) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
@@ -617,6 +653,17 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                     const uint32_t ph = (it / STAGES) & 1;
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     if (ptx::elect_one()) {
+                    // L2 prefetch of the slab `prefetch_kb` iterations ahead of the ring (same tile only)
+                    if (p.prefetch_kb && kb + STAGES + p.prefetch_kb - 1 < num_kb) {
+                        const int kp = (kb + STAGES + p.prefetch_kb - 1) * BK;
+                        ptx::tma_prefetch_2d(&map_a, kp, m0);
+                        if (B_MN) {
+#pragma unroll
+                            for (int j = 0; j < C_::B_COLS / 32; j++) ptx::tma_prefetch_2d(&map_b, n0 + 32 * j, kp);
+                        } else {
+                            ptx::tma_prefetch_2d(&map_b, kp, n0);
+                        }
+                    }
                     // the pair's full barrier lives in the leader and expects both CTAs' bytes
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[s], CG * C_::STAGE_BYTES);
                     const int k0 = kb * BK;
@@ -775,6 +822,14 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// L2 prefetch distance (k-slabs beyond the ring); TB200_GEMM_PREFETCH overrides the kernel's default
+inline int gemm_prefetch_kb(int dflt)
+{
+    const char *e = getenv("TB200_GEMM_PREFETCH");
+    const int env = e ? atoi(e) : -1;
+    return env >= 0 ? env : dflt;
+}
+
 template <int BN, bool B_MN>
 int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, float alpha, float beta, int64_t ldA,
               int64_t ldB, int64_t ldC)
@@ -807,6 +862,7 @@ int launch_tc(const float *A, const float *B, float *C, int M, int N, int K, flo
     p.b_lbo = BK * 128;
     p.b_sbo = 512;
     p.alpha_dev = nullptr;
+    p.prefetch_kb = 0;
     if (const char *e = getenv("TB200_DBG_B_LBO")) p.b_lbo = (uint32_t)atoi(e);     // descriptor bring-up only
     if (const char *e = getenv("TB200_DBG_B_SBO")) p.b_sbo = (uint32_t)atoi(e);
     auto kern = tiramisu_sm100_gemm_tf32<BN, B_MN>;
@@ -849,6 +905,7 @@ int launch_tc_splitk(const float *A, const float *B, float *C, int M, int N, int
     p.b_lbo = BK * 128;
     p.b_sbo = 512;
     p.alpha_dev = nullptr;
+    p.prefetch_kb = gemm_prefetch_kb(0);        // measured (r02 run 2): prefetching the K half ahead of the ring is slower at 1024^3
     auto kern = tiramisu_sm100_gemm_tf32_splitk<B_MN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -898,6 +955,7 @@ int launch_tc_f16(const void *A, const void *B, float *C, int M, int N, int K, f
     p.b_lbo = 0;
     p.b_sbo = 0;
     p.alpha_dev = alpha_dev;
+    p.prefetch_kb = 0;
     auto kern = tiramisu_sm100_gemm_tf32<BN, false, true>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -939,6 +997,7 @@ int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N,
     p.b_lbo = BK * 128;
     p.b_sbo = 512;
     p.alpha_dev = nullptr;
+    p.prefetch_kb = gemm_prefetch_kb(0);
     auto kern = tiramisu_sm100_gemm_tf32_persistent<CG, B_MN>;
     static bool attr_set = false;
     if (!attr_set) {

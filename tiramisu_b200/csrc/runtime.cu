@@ -188,6 +188,35 @@ TB200_API uint64_t tiramisu_b200_kernel_launches(void) { return g_kernel_launche
 
 TB200_API int tiramisu_b200_post_launch(const char *kernel_name) { return post_launch(kernel_name ? kernel_name : "generated kernel"); }
 
+// Measurement aid (bench.py): an EMPTY kernel with a given launch shape — grid, block, dynamic shared memory and
+// cluster width — so that the period of back-to-back launches of that shape (the launch floor a few-microsecond
+// kernel such as the 1024^3 GEMM sits on) can be measured next to the kernel itself.
+namespace { __global__ void tiramisu_sm100_null_kernel(int *sink) { if (sink && threadIdx.x == 9999) *sink = 0; } }
+TB200_API int tiramisu_b200_null_launch(int32_t grid, int32_t block, int32_t smem_bytes, int32_t cluster)
+{
+    if (grid < 1 || block < 1 || block > 1024 || smem_bytes < 0 || cluster < 1 || grid % cluster) return fail(__func__, "bad launch shape");
+    static int max_set = -1;
+    if (smem_bytes > max_set) {
+        TB200_CHECK(cudaFuncSetAttribute(tiramisu_sm100_null_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        max_set = smem_bytes;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int *none = nullptr;
+    TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_null_kernel, none));
+    return post_launch("tiramisu_sm100_null_kernel");
+}
+
 TB200_API int tiramisu_b200_pool_trim(void)
 {
     int dev = 0;

@@ -85,6 +85,14 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// L2 prefetch of a tile (no shared-memory slot, no barrier): keeps DRAM requests in flight beyond the depth of the
+// shared-memory ring — what a cold-L2 GEMM is short of (in-flight bytes = ring depth x CTAs, DRAM latency ~2 us)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
                                             int c2, int c3)
 {

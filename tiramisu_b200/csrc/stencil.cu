@@ -273,18 +273,32 @@ __device__ __forceinline__ void blur_f32_v4_body(const float *__restrict__ in, f
         bx[r].z = blur3(v[r].z, v[r].w, n0);
         bx[r].w = blur3(v[r].w, n0, n1);
     }
+    // Output rows are W-2 wide: every other row starts 8 bytes off a 16-byte boundary.  Aligned rows take one
+    // 128-bit store per thread; on the others the thread's window is shifted by two columns — it stores
+    // {o.z, o.w, next lane's o.x, o.y}, lane 0 adds its own first pair and lane 31 keeps its last pair as 64-bit
+    // stores — so all but two lanes of a warp still issue ONE 128-bit store (r01: two 64-bit stores per thread
+    // on every row left this kernel at 0.94 of the copy peak where heat2d, with 128-bit stores, reaches 1.07).
 #pragma unroll
     for (int r = 0; r < RY; r++) {
         const int y = y0 + r;
-        if (!col_ok || y >= row_end || y >= H - 2) continue;
+        if (y >= row_end || y >= H - 2) continue;             // warp-uniform: the shuffles below stay converged
         float4 o;
         o.x = blur3(bx[r].x, bx[r + 1].x, bx[r + 2].x);
         o.y = blur3(bx[r].y, bx[r + 1].y, bx[r + 2].y);
         o.z = blur3(bx[r].z, bx[r + 1].z, bx[r + 2].z);
         o.w = blur3(bx[r].w, bx[r + 1].w, bx[r + 2].w);
+        const float nx = __shfl_down_sync(0xffffffffu, o.x, 1);
+        const float ny = __shfl_down_sync(0xffffffffu, o.y, 1);
+        if (!col_ok) continue;
         float *dst = out + (size_t)y * OW + x;
-        __stcs(reinterpret_cast<float2 *>(dst), make_float2(o.x, o.y));
-        if (x + 2 < OW) __stcs(reinterpret_cast<float2 *>(dst + 2), make_float2(o.z, o.w));
+        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+            if (x + 3 < OW) __stcs(reinterpret_cast<float4 *>(dst), o);
+            else __stcs(reinterpret_cast<float2 *>(dst), make_float2(o.x, o.y));          // last thread of the row: 2 columns
+        } else {
+            if (lane == 0) __stcs(reinterpret_cast<float2 *>(dst), make_float2(o.x, o.y));
+            if (lane < 31 && x + 5 < OW) __stcs(reinterpret_cast<float4 *>(dst + 2), make_float4(o.z, o.w, nx, ny));
+            else if (x + 3 < OW) __stcs(reinterpret_cast<float2 *>(dst + 2), make_float2(o.z, o.w));
+        }
     }
 }
 

@@ -292,6 +292,33 @@ std::set<std::string> Lowering::parallel_iterators(computation *c)
         }
     }
     for (const std::string &n : seq) det.erase(n);
+    // A sequential iterator runs INSIDE the thread, at a different value in every thread at any moment: a parallel
+    // iterator that shares a store index with it would let two threads meet on one element after all (thread i at
+    // step j and thread i+1 at step j-1 both update b_O[i+j]).  Whatever shares an index with a sequential iterator
+    // is therefore sequential too — a statement like the polynomial multiply ends up in one thread, in its own order.
+    std::vector<std::set<std::string>> groups;
+    for (const Idx &x : idx) {
+        std::set<std::string> g;
+        for (auto &kv : x.coef) g.insert(kv.first);
+        groups.push_back(g);
+    }
+    for (const expr &a : c->access()) {
+        std::map<std::string, int64_t> coef; int64_t cst = 0;
+        if (affine_form(a, coef, cst)) continue;
+        std::set<std::string> g;
+        for (const std::string &n : iters)
+            if (!a.substitute({n}, {expr((int32_t) 0)}).is_equal(a)) g.insert(n);
+        groups.push_back(g);
+    }
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (const auto &g : groups) {
+            bool has_seq = false;
+            for (const std::string &n : g) has_seq |= !det.count(n);
+            if (!has_seq) continue;
+            for (const std::string &n : g) changed |= det.erase(n) > 0;
+        }
+    }
     return det;
 }
 
