@@ -174,6 +174,12 @@ int tiramisu_b200_set_lstm_mode(int mode);
  * step barrier), 3 = persistent layer kernel, K split across 4-CTA clusters with a distributed-
  * shared-memory reduction (F % 128 == 0, B <= 64). */
 int tiramisu_b200_set_lstm_kernel(int kernel);
+/* The same block for the parameter layouts of the reference's other two LSTM benchmarks: layout 0 = LSTM/cpu and
+ * LSTM/gpu (above); 1 = LSTM/gpu_lib (Weights [L][2][4F][F], index 0 = W, 1 = R, gate rows i, f, z, o:
+ * gpu_lib/generator.cpp:66-88); 2 = LSTM/cpu_lib (weights [L][2][F][4F], transposed, same index and gate order:
+ * cpu_lib/generator.cpp:27,50-76).  c_last: null, or f32[B][F] that receives the last layer's final cell state. */
+int tiramisu_b200_lstm_ex(const float *Weights, const float *biases, const float *x, float *y, float *c_last,
+                          int32_t F, int32_t B, int32_t L, int32_t T, int32_t layout);
 /* Description of the engine (and operand type) the calling thread's last tiramisu_b200_lstm call ran on. */
 const char *tiramisu_b200_lstm_last_engine(void);
 
@@ -260,6 +266,14 @@ int conv_relu_maxpool_block(halide_buffer_t *input, halide_buffer_t *filter, hal
 /* benchmarks/DNN/blocks/LSTM/cpu/wrapper.h:6-10 — params i32[4] = {F, B, L, T} */
 int lstm(halide_buffer_t *params, halide_buffer_t *Weights, halide_buffer_t *biases, halide_buffer_t *x,
          halide_buffer_t *y);
+/* The reference's other two LSTM benchmarks also export `lstm`, with other arities; here they carry
+ * distinct names, and lib/libtiramisu_b200_lstm_{gpu,cpu}_lib.so re-export them as `lstm` (csrc/abi/).
+ * LSTM/gpu_lib/wrapper.cpp:74-79: Weights {F, 4F, 2, L} (0 = W, 1 = R; gates i, f, z, o), time_* f32[1]. */
+int tiramisu_b200_lstm_gpu_lib(halide_buffer_t *Weights, halide_buffer_t *biases, halide_buffer_t *x, halide_buffer_t *y,
+                               halide_buffer_t *time_start, halide_buffer_t *time_end);
+/* LSTM/cpu_lib/wrapper.cpp:65-72: weights {4F, F, 2, L} (transposed), h {F, B, T+1} and c {F, B} working buffers. */
+int tiramisu_b200_lstm_cpu_lib(halide_buffer_t *weights, halide_buffer_t *biases, halide_buffer_t *x, halide_buffer_t *h,
+                               halide_buffer_t *c, halide_buffer_t *out);
 /* tests/wrapper_test_162.h..167.h — cublas_gemm / gpu_tile GEMM feature tests. */
 int test_162(halide_buffer_t *sizes, halide_buffer_t *params, halide_buffer_t *A,
              halide_buffer_t *B, halide_buffer_t *C);

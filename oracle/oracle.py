@@ -188,6 +188,33 @@ def lstm(Weights: np.ndarray, biases: np.ndarray, x: np.ndarray) -> np.ndarray:
     return y
 
 
+def lstm_with_state(Weights: np.ndarray, biases: np.ndarray, x: np.ndarray):
+    """oracle.lstm plus the last layer's final cell state c f32[B][F] (LSTM/cpu_lib's `c` buffer)."""
+    Weights = np.ascontiguousarray(Weights, dtype=np.float32)
+    biases = np.ascontiguousarray(biases, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    L, two, F4, F = Weights.shape
+    T, Bn, _ = x.shape
+    y = np.empty_like(x)
+    c = np.empty((Bn, F), np.float32)
+    lib().oracle_lstm_c(C.c_int(F), C.c_int(Bn), C.c_int(L), C.c_int(T), _p(Weights), _p(biases), _p(x), _p(y), _p(c))
+    return y, c
+
+
+def lstm_relayout(Weights: np.ndarray, biases: np.ndarray, layout: int):
+    """LSTM/cpu layout (f32[L][2][4F][F], 0 = R, 1 = W, gate row blocks i, z, o, f) -> the parameter layout of
+    LSTM/gpu_lib (layout 1: 0 = W, 1 = R, blocks i, f, z, o; gpu_lib/generator.cpp:66-88) or LSTM/cpu_lib (layout 2: the
+    same, each matrix transposed to [F][4F]; cpu_lib/generator.cpp:27).  Returns (weights, biases)."""
+    L, _, F4, F = Weights.shape
+    blocks = Weights.reshape(L, 2, 4, F, F)                  # [l][m][gate i,z,o,f][u][j]
+    theirs = blocks[:, ::-1][:, :, [0, 3, 1, 2]]             # matrices swapped; gates i, f, z, o
+    w = np.ascontiguousarray(theirs.reshape(L, 2, 4 * F, F))
+    b = np.ascontiguousarray(biases.reshape(L, 4, F)[:, [0, 3, 1, 2]].reshape(L, 4 * F))
+    if layout == 2:
+        w = np.ascontiguousarray(w.transpose(0, 1, 3, 2))
+    return w, b
+
+
 def transpose_f32(A: np.ndarray) -> np.ndarray:
     A = np.ascontiguousarray(A, dtype=np.float32)
     r, c = A.shape

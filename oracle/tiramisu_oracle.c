@@ -421,8 +421,19 @@ void oracle_conv_relu_maxpool(const float *input, const float *filter, const flo
  */
 static inline float sigmoidf_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+void oracle_lstm_c(int F, int B, int L, int T, const float *Weights, const float *biases,
+                   const float *x, float *y, float *c_last);
+
 void oracle_lstm(int F, int B, int L, int T, const float *Weights, const float *biases,
                  const float *x, float *y)
+{
+    oracle_lstm_c(F, B, L, T, Weights, biases, x, y, NULL);
+}
+
+/* c_last (optional, f32[B][F]): the last layer's cell state after the last step — the `c` working buffer that
+ * LSTM/cpu_lib/wrapper.cpp:36,70 passes and the generator leaves filled (cpu_lib/generator.cpp:41,78). */
+void oracle_lstm_c(int F, int B, int L, int T, const float *Weights, const float *biases,
+                   const float *x, float *y, float *c_last)
 {
     const size_t BF = (size_t)B * F;
     /* buf_h[T+1][L+1][B][F], buf_c[T+1][L][B][F] as in the generator (:91-92) */
@@ -472,6 +483,7 @@ void oracle_lstm(int F, int B, int L, int T, const float *Weights, const float *
         }
     for (int m = 0; m < T; m++)
         memcpy(y + (size_t)m * BF, H_(m, L - 1), sizeof(float) * BF);
+    if (c_last) memcpy(c_last, C_(T - 1, L - 1), sizeof(float) * BF);
 #undef H_
 #undef C_
     free(h); free(c); free(tmp);

@@ -54,6 +54,12 @@ TARGETS = {
     # Layers I/III and lowered to the runtime's fused kernel (with the pattern lowering off the generator is refused)
     "conv_block": ("benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/conv_relu_maxpool_generator_tiramisu.cpp", "conv_relu_maxpool_tiramisu.o",
                    "benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/wrapper_nn_block.cpp", ["benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense"], []),
+    # the other `*gpu` Halide benchmarks (benchmarks/benchmark_list.txt) — image stencils / pointwise colour
+    # transforms written against the old ISL-string API with hand-placed shared-memory tiles, constant-memory taps,
+    # register temporaries and clamped accesses.  Their wrappers need Halide-generated reference pipelines and PNG I/O,
+    # so the objects are linked into shared libraries and checked against oracle/halide_gpu.py by tests/test_frontend.py.
+    **{f"halide_{g}": (f"benchmarks/halide/{g}_tiramisu.cpp", f"build/generated_fct_{g}.o", None, ["benchmarks/halide"], [])
+       for g in ("convolutiongpu", "gaussiangpu", "edgegpu", "fusiongpu", "cvtcolorgpu", "rgbyuv420gpu", "heat2dgpu")},
     # BASELINE configs[1]'s own generator: old-style ISL-string API, CPU schedule (parallel y, vectorize x by 8)
     "heat2d": ("benchmarks/halide/heat2d_tiramisu.cpp", "build/generated_fct_heat2d.o", "benchmarks/halide/wrapper_heat2d.cpp",
                ["benchmarks/halide"], []),
@@ -67,6 +73,10 @@ TARGETS = {
 # faithful to the generator, bug included); "lstm_gpu_fixed" applies the two index corrections to a
 # scratch copy under tests/compat/_gen (never committed) so that the result can be checked against the
 # oracle.  Each pattern must occur exactly once in the reference file.
+# compile definitions the reference's build passes to a generator (benchmarks/halide/heat2dgpu_tiramisu.cpp:32-36: the GPU
+# variant of the file is selected with USE_GPU2)
+GEN_DEFS = {"halide_heat2dgpu": ["-DUSE_GPU2"]}
+
 PATCHES = {
     "lstm_gpu_fixed": [
         ("matmul1_h_access.store_in(&buf_h, {m - 1, l, ", "matmul1_h_access.store_in(&buf_h, {m, l + 1, "),
@@ -111,7 +121,7 @@ def build_one(name: str, lowering: str | None = None) -> tuple[int, str]:
         with open(gen_src, "w") as f:
             f.write(text)
     # 1. the reference generator, unmodified, against this repo's front-end
-    cmd = ["g++", "-std=c++17", "-O1", "-w", "-I", FRONT_INC, "-I", os.path.join(FRONT_INC, "compat"), *inc, gen_src, "-o", gen_exe,
+    cmd = ["g++", "-std=c++17", "-O1", "-w", *GEN_DEFS.get(name, []), "-I", FRONT_INC, "-I", os.path.join(FRONT_INC, "compat"), *inc, gen_src, "-o", gen_exe,
            f"-L{LIBDIR}", "-ltiramisu_b200_frontend", f"-Wl,-rpath,{LIBDIR}"]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     log += r.stdout + r.stderr

@@ -45,6 +45,18 @@ def test_library_exports_every_declared_symbol(libpath):
     assert not missing, f"declared in include/*.h but not exported: {missing}"
 
 
+def test_lstm_abi_shims_export_lstm(libpath):
+    """The reference's LSTM/gpu_lib and LSTM/cpu_lib wrappers link against a symbol `lstm` with 6 arguments (the main
+    library's `lstm` is LSTM/cpu's 5-argument one): each ABI has a one-function shared library of its own."""
+    for name in ("lstm_gpu_lib", "lstm_cpu_lib"):
+        so = os.path.join(os.path.dirname(libpath), f"libtiramisu_b200_{name}.so")
+        assert os.path.exists(so), so
+        out = subprocess.check_output(["nm", "-D", "--defined-only", so], text=True)
+        assert any(line.split()[-1] == "lstm" and " T " in line for line in out.splitlines())
+        undef = subprocess.check_output(["nm", "-D", "--undefined-only", so], text=True)
+        assert f"tiramisu_b200_{name}" in undef
+
+
 def test_library_is_sm100a_only(libpath):
     out = subprocess.check_output(["cuobjdump", "-lelf", libpath], text=True)
     archs = set(re.findall(r"sm_\d+a?", out))

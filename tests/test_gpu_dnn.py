@@ -320,3 +320,37 @@ def test_lstm_fp16_engine_weight_range(api, wscale):
         top = float(np.abs(want).max())
         assert 0 < top < 1e-6
         assert float(np.abs(got - want).max()) <= TF32_RTOL * top
+
+
+@pytest.mark.parametrize("F,B,L,T,scale", [(32, 8, 2, 5, 4.0), (128, 16, 2, 6, 8.0), (256, 64, 2, 4, 8.0)])
+@pytest.mark.parametrize("mode", [1, 0])
+def test_lstm_gpu_lib_and_cpu_lib_abis(api, mode, F, B, L, T, scale):
+    """The reference's other two `lstm` ABIs: LSTM/gpu_lib — lstm(Weights, biases, x, y, t0, t1),
+    index 0 = W, gate rows i, f, z, o — and LSTM/cpu_lib — lstm(weights^T, biases, x, h, c, out).  The same cell on
+    re-laid-out parameters must give what the LSTM/cpu ABI gives (exact mode: bit for bit; tensor path: TF32
+    tolerance), the cpu_lib working buffers h and c must be left as the reference leaves them."""
+    W, b, x = refdata.lstm_inputs(F, B, L, T, scale=scale)
+    want, want_c = oracle.lstm_with_state(W, b, x)
+    prev = api.set_lstm_mode(mode)
+    try:
+        base = _lstm(api, W, b, x)
+        w1, b1 = oracle.lstm_relayout(W, b, 1)
+        y1 = np.full_like(x, np.nan)
+        t0, t1 = np.zeros(1, np.float32), np.zeros(1, np.float32)
+        api.lstm_gpu_lib(w1, b1, x, y1, t0, t1)
+        w2, b2 = oracle.lstm_relayout(W, b, 2)
+        h = np.full((T + 1, B, F), np.nan, np.float32)
+        c = np.full((B, F), np.nan, np.float32)
+        out = np.full_like(x, np.nan)
+        api.lstm_cpu_lib(w2, b2, x, h, c, out)
+    finally:
+        api.set_lstm_mode(prev)
+    assert t1[0] >= t0[0]
+    assert np.array_equal(y1, base) and np.array_equal(out, base)          # same engine, same (re-laid-out) numbers
+    assert np.array_equal(h[0], np.zeros((B, F), np.float32)) and np.array_equal(h[1:], out)
+    if mode == 1:
+        np.testing.assert_allclose(base, want, rtol=1e-4, atol=FP32_RTOL)
+        np.testing.assert_allclose(c, want_c, rtol=1e-4, atol=FP32_RTOL)
+    else:
+        assert_lstm_tf32_close(base, want, "layout 0")
+        assert float(np.abs(c - want_c).max()) <= 1e-2 * max(1.0, float(np.abs(want_c).max()))

@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_set_lstm_mode", C.c_int, C.c_int)
     sig("tiramisu_b200_set_lstm_kernel", C.c_int, C.c_int)
     sig("tiramisu_b200_lstm_last_engine", C.c_char_p)
+    sig("tiramisu_b200_lstm_ex", C.c_int, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32)
     sig("tiramisu_b200_comm_unique_id", C.c_int, vp)
     sig("tiramisu_b200_comm_init", C.c_int, i32, i32, vp)
     sig("tiramisu_b200_comm_destroy", C.c_int)
@@ -117,7 +118,7 @@ def lib() -> C.CDLL:
         for op in ("Isend", "Issend", "Irecv"):
             sig(f"tiramisu_MPI_{op}_{t}", None, C.c_int, C.c_int, C.c_int, vp, vp)
     sig("tiramisu_b200_set_heat2d_dist", C.c_int, i32, i32, i32, i32)
-    for name, n in (("heat2d_dist_tiramisu", 2), ("conv_relu_maxpool_block", 4), ("lstm", 5), ("heat2d_tiramisu", 2), ("heat2dgpu_tiramisu", 3), ("blurxy_tiramisu", 2),
+    for name, n in (("tiramisu_b200_lstm_gpu_lib", 6), ("tiramisu_b200_lstm_cpu_lib", 6), ("heat2d_dist_tiramisu", 2), ("conv_relu_maxpool_block", 4), ("lstm", 5), ("heat2d_tiramisu", 2), ("heat2dgpu_tiramisu", 3), ("blurxy_tiramisu", 2),
                     ("blurxy_f32_tiramisu", 2), ("boxblur", 2), ("blurautodist_tiramisu", 2),
                     ("sgemm_tiramisu", 6), ("matmul", 6), ("test_162", 5), ("test_164", 6), ("test_167", 3),
                     ("test_168", 2), ("test_197", 2)):

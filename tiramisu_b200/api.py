@@ -109,6 +109,18 @@ def lstm(params, Weights, biases, x, y):
     _call("lstm", params, Weights, biases, x, y)
 
 
+def lstm_gpu_lib(Weights, biases, x, y, time_start=None, time_end=None):
+    """LSTM/gpu_lib/wrapper.cpp:74-79 — Weights f32[L][2][4F][F] with index 0 = W, 1 = R, gate rows i, f, z, o."""
+    t0 = time_start if time_start is not None else np.zeros(1, np.float32)
+    t1 = time_end if time_end is not None else np.zeros(1, np.float32)
+    _call("tiramisu_b200_lstm_gpu_lib", Weights, biases, x, y, t0, t1)
+
+
+def lstm_cpu_lib(weights, biases, x, h, c, out):
+    """LSTM/cpu_lib/wrapper.cpp:65-72 — weights f32[L][2][F][4F] (transposed), h f32[T+1][B][F], c f32[B][F]."""
+    _call("tiramisu_b200_lstm_cpu_lib", weights, biases, x, h, c, out)
+
+
 def set_conv_mode(mode: int) -> int:
     return int(_lib.lib().tiramisu_b200_set_conv_mode(mode))
 

@@ -62,6 +62,16 @@ def build(verbose: bool = False, force: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    # one-function ABI shims: the reference's LSTM/gpu_lib and LSTM/cpu_lib wrappers link against a symbol `lstm` of
+    # another arity than LSTM/cpu's (csrc/abi/*.c)
+    for name in ("lstm_gpu_lib", "lstm_cpu_lib"):
+        src = os.path.join(CSRC, "abi", name + ".c")
+        so = os.path.join(LIBDIR, f"libtiramisu_b200_{name}.so")
+        if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(LIB)):
+            r = subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", src, "-o", so, f"-L{LIBDIR}", "-ltiramisu_b200",
+                                "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True, env=env)
+            if r.returncode != 0:
+                raise RuntimeError(f"ABI shim {name} failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

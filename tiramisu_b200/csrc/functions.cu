@@ -518,3 +518,73 @@ TB200_API int lstm(halide_buffer_t *params, halide_buffer_t *Weights, halide_buf
     if (dy.copy_out()) return 1;
     return finish();
 }
+
+// =============================================================================== the other two `lstm` ABIs
+// All three reference LSTM benchmarks export the C symbol `lstm` with different arities, so one library can carry only
+// one of them: `lstm` above is LSTM/cpu and LSTM/gpu (5 arguments).  The other two are exported under distinct names;
+// tiramisu_b200/csrc/abi/lstm_{gpu,cpu}_lib.c are one-function shims that give them the name `lstm` in shared
+// libraries of their own (lib/libtiramisu_b200_lstm_gpu_lib.so, ..._cpu_lib.so) for a wrapper to link against.
+
+// benchmarks/DNN/blocks/LSTM/gpu_lib/wrapper.h — lstm(Weights, biases, x, y, time_start, time_end):
+// Weights {F, 4F, 2, L} with index 0 = W, 1 = R and gate rows i, f, z, o (gpu_lib/generator.cpp:66-88); time_start /
+// time_end f32[1] receive get_time() around the device work (:126-128).  configuration.h: F = 512, B = 64, L = 4, T = 100.
+TB200_API int tiramisu_b200_lstm_gpu_lib(halide_buffer_t *Weights, halide_buffer_t *biases, halide_buffer_t *x, halide_buffer_t *y,
+                                         halide_buffer_t *time_start, halide_buffer_t *time_end)
+{
+    BufView vw, vb, vx, vy, vt0, vt1;
+    if (!view_of(Weights, &vw) || !view_of(biases, &vb) || !view_of(x, &vx) || !view_of(y, &vy)) return bad(__func__, "null buffer");
+    int F = 512, B = 64, L = 4, T = 100;
+    if (vx.ndim >= 3) { F = (int)vx.extent[0]; B = (int)vx.extent[1]; T = (int)vx.extent[2]; }
+    if (vw.ndim >= 4) {
+        L = (int)vw.extent[3];
+        if (vw.extent[0] != F || vw.extent[1] != 4 * F || vw.extent[2] != 2) return bad(__func__, "Weights extents != {F, 4F, 2, L}");
+    }
+    if (vy.ndim >= 3 && (vy.extent[0] != F || vy.extent[1] != B || vy.extent[2] != T)) return bad(__func__, "y extents != {F, B, T}");
+    DeviceArg dw, db, dx, dy;
+    if (dw.bind(vw, (size_t)L * 2 * 4 * F * F * 4, true) || db.bind(vb, (size_t)L * 4 * F * 4, true) ||
+        dx.bind(vx, (size_t)T * B * F * 4, true) || dy.bind(vy, (size_t)T * B * F * 4, false))
+        return 1;
+    const bool timed = view_of(time_start, &vt0) && view_of(time_end, &vt1) && !vt0.on_device && !vt1.on_device;
+    float t0 = 0.f, t1 = 0.f;
+    if (timed) { if (finish()) return 1; t0 = now_ms(); }
+    if (tiramisu_b200_lstm_ex(dw.as<float>(), db.as<float>(), dx.as<float>(), dy.as<float>(), nullptr, F, B, L, T, 1)) return 1;
+    if (timed) {
+        if (finish()) return 1;
+        t1 = now_ms();
+        *reinterpret_cast<float *>(vt0.ptr) = t0;
+        *reinterpret_cast<float *>(vt1.ptr) = t1;
+    }
+    if (dy.copy_out()) return 1;
+    return finish();
+}
+
+// benchmarks/DNN/blocks/LSTM/cpu_lib/wrapper.cpp:65-72 — lstm(weights, biases, x, h, c, out): weights {4F, F, 2, L}
+// (transposed: input-feature major, cpu_lib/generator.cpp:27), index 0 = W, 1 = R, gate columns i, f, z, o;
+// h {F, B, T+1} and c {F, B} are the generator's working buffers (:40-41): on return h[0] = 0, h[s+1] = the last layer's
+// h(s) and c = the last layer's final cell state, as the reference leaves them.  configure.h: F = 1024, B = 1, L = 4, T = 100.
+TB200_API int tiramisu_b200_lstm_cpu_lib(halide_buffer_t *weights, halide_buffer_t *biases, halide_buffer_t *x, halide_buffer_t *h,
+                                         halide_buffer_t *c, halide_buffer_t *out)
+{
+    BufView vw, vb, vx, vh, vc, vo;
+    if (!view_of(weights, &vw) || !view_of(biases, &vb) || !view_of(x, &vx) || !view_of(h, &vh) || !view_of(c, &vc) || !view_of(out, &vo))
+        return bad(__func__, "null buffer");
+    int F = 1024, B = 1, L = 4, T = 100;
+    if (vx.ndim >= 3) { F = (int)vx.extent[0]; B = (int)vx.extent[1]; T = (int)vx.extent[2]; }
+    if (vw.ndim >= 4) {
+        L = (int)vw.extent[3];
+        if (vw.extent[0] != 4 * F || vw.extent[1] != F || vw.extent[2] != 2) return bad(__func__, "weights extents != {4F, F, 2, L}");
+    }
+    if (vh.ndim >= 3 && (vh.extent[0] != F || vh.extent[1] != B || vh.extent[2] != T + 1)) return bad(__func__, "h extents != {F, B, T+1}");
+    if (vo.ndim >= 3 && (vo.extent[0] != F || vo.extent[1] != B || vo.extent[2] != T)) return bad(__func__, "out extents != {F, B, T}");
+    const size_t BF = (size_t)B * F;
+    DeviceArg dw, db, dx, dh, dc, dout;
+    if (dw.bind(vw, (size_t)L * 2 * 4 * F * F * 4, true) || db.bind(vb, (size_t)L * 4 * F * 4, true) || dx.bind(vx, (size_t)T * BF * 4, true) ||
+        dh.bind(vh, (size_t)(T + 1) * BF * 4, false) || dc.bind(vc, BF * 4, false) || dout.bind(vo, (size_t)T * BF * 4, false))
+        return 1;
+    // the engine writes the last layer's h(s) into h[s+1] directly; `out` is its copy (copy_output, generator.cpp:86)
+    if (tiramisu_b200_lstm_ex(dw.as<float>(), db.as<float>(), dx.as<float>(), dh.as<float>() + BF, dc.as<float>(), F, B, L, T, 2)) return 1;
+    TB200_CHECK(cudaMemsetAsync(dh.as<float>(), 0, BF * 4, stream()));
+    TB200_CHECK(cudaMemcpyAsync(dout.as<float>(), dh.as<float>() + BF, (size_t)T * BF * 4, cudaMemcpyDeviceToDevice, stream()));
+    if (dh.copy_out() || dc.copy_out() || dout.copy_out()) return 1;
+    return finish();
+}

@@ -253,6 +253,7 @@ struct LayerParams {
     const float *xg;        // [T*B][4F] packed gate columns: input contribution of every step
     const float *bias;      // [4F] packed
     float *h;               // [T][B][F] output of this layer
+    float *c_out;           // null, or [B][F]: the cell state after the last step (LSTM/cpu_lib's `c` argument)
     uint32_t *counter;      // device-wide step barrier, zero at launch
     int dbg;                // timing experiments only (TB200_LSTM_DBG): 1 = producers do not wait for the
                             // step barrier, 2 = no recurrent loads/MMAs at all (results are then wrong)
@@ -405,6 +406,11 @@ tiramisu_sm100_lstm_layer_tf32(const __grid_constant__ CUtensorMap map_h, const 
                 float4 *dst = reinterpret_cast<float4 *>(p.h + ((size_t)t * p.B + row) * p.F + n0 / 4);
                 dst[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
                 dst[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                if (p.c_out && t == p.T - 1) {
+                    float4 *cd = reinterpret_cast<float4 *>(p.c_out + (size_t)row * p.F + n0 / 4);
+                    cd[0] = make_float4(c[0], c[1], c[2], c[3]);
+                    cd[1] = make_float4(c[4], c[5], c[6], c[7]);
+                }
                 __threadfence();                       // h[t] visible device-wide before the counter moves
             }
             ptx::fence_proxy_async_all();
@@ -447,6 +453,7 @@ struct KSplitParams {
     const float *xg;        // [T*B][4F] packed gate columns
     const float *bias;      // [4F] packed
     float *h;               // [T][B][F]
+    float *c_out;           // null, or [B][F]: the cell state after the last step
     uint32_t *counter;
     int dbg;
     unsigned long long *trace;   // optional [grid][T][8] %globaltimer stamps (TB200_LSTM_TRACE, bring-up only)
@@ -650,8 +657,10 @@ tiramisu_sm100_lstm_layer_ksplit(const __grid_constant__ CUtensorMap map_h, cons
                 c[u] = gi * gz + gf * c[u];
                 hn[u] = ptx::tanh_approx(c[u]) * go;
             }
-            if (ok)
+            if (ok) {
                 *reinterpret_cast<float4 *>(p.h + ((size_t)t * p.B + b) * p.F + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                if (p.c_out && t == p.T - 1) *reinterpret_cast<float4 *>(p.c_out + (size_t)b * p.F + u0) = make_float4(c[0], c[1], c[2], c[3]);
+            }
             // publish h[t]: CTA-wide rendezvous of the writers, then ONE gpu-scope fence + counter increment
             if (e == 0) KS_TRACE(6);
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -698,6 +707,7 @@ struct H16Params {
     const float *bias;          // [4F] packed
     float *h;                   // [T][B][F] fp32 output of this layer, or null (only the last layer's is consumed)
     __half *h16;                // [T][B][F] fp16 copy, the recurrence's own operand
+    float *c_out;               // null, or [B][F]: the cell state after the last step
     uint32_t *step_flags;       // step barrier words, see sync_mode
     int sync_mode;              // 0: ONE counter, += gridDim.x per finished step (red.add; r01 and the measured best)
                                 // 1: [gridDim.x] per-CTA step flags (plain stores; measured slower: r02 run 1, 7.6 vs 5.9 us/step)
@@ -949,6 +959,7 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
             if (ok) {
                 const size_t o = ((size_t)t * p.B + b) * p.F + u0;
                 if (p.h) *reinterpret_cast<float4 *>(p.h + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                if (p.c_out && t == p.T - 1) *reinterpret_cast<float4 *>(p.c_out + (size_t)b * p.F + u0) = make_float4(c[0], c[1], c[2], c[3]);
                 const __half2 lo = __floats2half2_rn(hn[0], hn[1]), hi = __floats2half2_rn(hn[2], hn[3]);
                 uint2 pk;
                 pk.x = *reinterpret_cast<const uint32_t *>(&lo);
@@ -1078,7 +1089,7 @@ std::atomic<int> g_lstm_kernel{0};
 thread_local const char *t_last_engine = "";     // which recurrence engine the calling thread's last tiramisu_b200_lstm used
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int lstm_exact(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y)
+int lstm_exact(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y, float *c_last)
 {
     const size_t BF = (size_t)B * F;
     // buf_h[T+1][L+1][B][F], buf_c[T+1][L][B][F] as in cpu/generator.cpp:91-92
@@ -1105,6 +1116,7 @@ int lstm_exact(int F, int B, int L, int T, const float *Wt, const float *bias, c
         }
     for (int m = 0; m < T; m++)
         TB200_CHECK(cudaMemcpyAsync(y + (size_t)m * BF, H(m, L - 1), BF * 4, cudaMemcpyDeviceToDevice, stream()));
+    if (c_last) TB200_CHECK(cudaMemcpyAsync(c_last, C(T - 1, L - 1), BF * 4, cudaMemcpyDeviceToDevice, stream()));
     pool_free(h); pool_free(c); pool_free(tmp);
     return 0;
 }
@@ -1285,7 +1297,7 @@ struct PipeStreams {
     }
 };
 
-int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y, bool pipeline)
+int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y, float *c_last, bool pipeline)
 {
     const size_t TB = (size_t)T * B;
     const size_t wsz = (size_t)4 * F * F;
@@ -1354,7 +1366,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
         }
         H16Params hp;
         hp.B = B; hp.F = F; hp.T = T;
-        hp.xg = xg_of(l); hp.bias = bp + (size_t)l * 4 * F; hp.h = out_of(l); hp.h16 = hh;
+        hp.xg = xg_of(l); hp.bias = bp + (size_t)l * 4 * F; hp.h = out_of(l); hp.h16 = hh; hp.c_out = l == L - 1 ? c_last : nullptr;
         hp.step_flags = step_flags + 256 * l; hp.sync_mode = sync_mode; hp.rscale = winv + 2 * l; hp.xg_ready = ready; hp.dbg = dbg; hp.trace = trace;
         cudaLaunchAttribute attr[1];
         cudaLaunchConfig_t cfg = h16_config(F, attr, st);
@@ -1449,7 +1461,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
     return 0;
 }
 
-int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y)
+int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, const float *x, float *y, float *c_last)
 {
     // recurrence engine (g_lstm_kernel: 0 auto, 1 = one launch per cell, 2 = persistent N-split layer
     // kernel, 3 = persistent TF32 K-split layer kernel, 4 = fp16 K-split kernel with layer pairs
@@ -1465,7 +1477,7 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
             if (const char *e = getenv("TB200_LSTM_PIPE")) pipe = pipe && atoi(e) != 0;
             t_last_engine = pipe ? "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, layer pairs overlapped"
                                  : "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, one layer at a time";
-            return lstm_h16(F, B, L, T, Wt, bias, x, y, pipe);
+            return lstm_h16(F, B, L, T, Wt, bias, x, y, c_last, pipe);
         }
     }
     const size_t BF = (size_t)B * F, TB = (size_t)T * B;
@@ -1530,6 +1542,7 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
             }
             KSplitParams kp;
             kp.B = B; kp.F = F; kp.T = T; kp.xg = xg; kp.bias = bp; kp.h = hl; kp.counter = counters + l;
+            kp.c_out = l == L - 1 ? c_last : nullptr;
             kp.dbg = 0;
             kp.trace = nullptr;
             if (const char *e = getenv("TB200_LSTM_DBG")) kp.dbg = atoi(e);
@@ -1559,7 +1572,7 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
             if (make_tensor_map_f32(&map_h3, hl, 3, dims, str, box)) return 1;
             LayerParams lp;
             lp.B = B; lp.F = F; lp.T = T; lp.a_rows = a_rows;
-            lp.xg = xg; lp.bias = bp; lp.h = hl; lp.counter = counters + l;
+            lp.xg = xg; lp.bias = bp; lp.h = hl; lp.counter = counters + l; lp.c_out = l == L - 1 ? c_last : nullptr;
             lp.dbg = 0;
             if (const char *e = getenv("TB200_LSTM_DBG")) lp.dbg = atoi(e);
             bool unused = false;
@@ -1584,6 +1597,8 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
             tiramisu_sm100_lstm_step_tf32<<<4 * F / BN, kThreads, SMEM_BYTES, stream()>>>(map_h, map_r, p);
             if (post_launch("tiramisu_sm100_lstm_step_tf32")) return 1;
         }
+        if (c_last && l == L - 1)              // per-cell engine: the cell state lives in the ping-pong buffers
+            TB200_CHECK(cudaMemcpyAsync(c_last, cs + (size_t)((T - 1) & 1) * BF, BF * 4, cudaMemcpyDeviceToDevice, stream()));
     }
     pool_free(counters);
     pool_free(Wp); pool_free(bp); pool_free(xg); pool_free(hs); pool_free(cs); pool_free(zero);
@@ -1604,17 +1619,114 @@ TB200_API int tiramisu_b200_set_lstm_kernel(int kernel)
     return g_lstm_kernel.exchange(kernel);
 }
 
+static int lstm_dispatch(const float *Weights, const float *biases, const float *x, float *y, float *c_last, int F, int B, int L, int T,
+                         const char *who)
+{
+    int mode = g_lstm_mode.load();
+    if (const char *e = getenv("TB200_LSTM_MODE")) mode = atoi(e);     // for harnesses that cannot call the setter
+    const bool tc_ok = F % 32 == 0 && B <= 128 && aligned16(Weights) && aligned16(biases) && aligned16(x) && aligned16(y) &&
+                       (!c_last || aligned16(c_last));
+    if (mode == 2 && !tc_ok) return fail(who, "shape not supported by the tcgen05 LSTM path");
+    if (mode != 1 && tc_ok) return lstm_tensor(F, B, L, T, Weights, biases, x, y, c_last);
+    t_last_engine = "exact: fp32 SIMT in the reference's accumulation order";
+    return lstm_exact(F, B, L, T, Weights, biases, x, y, c_last);
+}
+
 TB200_API int tiramisu_b200_lstm(const float *Weights, const float *biases, const float *x, float *y, int32_t F,
                                  int32_t B, int32_t L, int32_t T)
 {
     if (!Weights || !biases || !x || !y || F < 1 || B < 1 || L < 1 || T < 1) return fail(__func__, "bad argument");
-    int mode = g_lstm_mode.load();
-    if (const char *e = getenv("TB200_LSTM_MODE")) mode = atoi(e);     // for harnesses that cannot call the setter
-    const bool tc_ok = F % 32 == 0 && B <= 128 && aligned16(Weights) && aligned16(biases) && aligned16(x) && aligned16(y);
-    if (mode == 2 && !tc_ok) return fail(__func__, "shape not supported by the tcgen05 LSTM path");
-    if (mode != 1 && tc_ok) return lstm_tensor(F, B, L, T, Weights, biases, x, y);
-    t_last_engine = "exact: fp32 SIMT in the reference's accumulation order";
-    return lstm_exact(F, B, L, T, Weights, biases, x, y);
+    return lstm_dispatch(Weights, biases, x, y, nullptr, F, B, L, T, __func__);
+}
+
+// ---- the other two `lstm` ABIs of the reference: same cell, other parameter layouts ---------------------
+// layout 1 — LSTM/gpu_lib/generator.cpp:34-37,66-88: Weights [L][2][4F][F] with index 0 = W (input), 1 = R
+//            (recurrent), gate row blocks i, f, z, o; biases [L][4F] in the same gate order
+// layout 2 — LSTM/cpu_lib/generator.cpp:27-30,50-76: weights [L][2][F][4F] (TRANSPOSED: input feature major), index
+//            0 = W, 1 = R, gate column blocks i, f, z, o
+// Both are converted once per call into the layout of LSTM/cpu (layout 0: [L][2][4F][F], 0 = R, 1 = W, blocks
+// i, z, o, f) by one pass over the weights and then run on the same engines.
+namespace {
+__device__ __forceinline__ int src_gate_block(int g_ours) { return g_ours == 0 ? 0 : (g_ours == 1 ? 2 : (g_ours == 2 ? 3 : 1)); }   // i, z, o, f <- i, f, z, o
+
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_lstm_relayout_rows(const float *__restrict__ src, float *__restrict__ dst, int F, int L)
+{
+    // layout 1 -> 0: dst[l][m][g*F + u][:] = src[l][1 - m][src_gate_block(g)*F + u][:], float4 per thread
+    const size_t total4 = (size_t)L * 2 * 4 * F * (F / 4);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const int j4 = (int)(i % (F / 4));
+        size_t t = i / (F / 4);
+        const int row = (int)(t % (4 * F)); t /= 4 * F;
+        const int m = (int)(t % 2), l = (int)(t / 2);
+        const int g = row / F, u = row % F;
+        const float4 *s4 = reinterpret_cast<const float4 *>(src + (((size_t)l * 2 + (1 - m)) * 4 * F + (size_t)src_gate_block(g) * F + u) * F);
+        reinterpret_cast<float4 *>(dst + (((size_t)l * 2 + m) * 4 * F + row) * F)[j4] = __ldg(s4 + j4);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tiramisu_sm100_lstm_relayout_transposed(const float *__restrict__ src, float *__restrict__ dst, int F)
+{
+    // layout 2 -> 0 for one (layer, matrix) pair per blockIdx.z: dst[g*F + u][j] = src[j][src_gate_block(g)*F + u];
+    // 32 x 32 tiles through shared memory so that both sides are coalesced
+    __shared__ float tile[32][33];
+    const int lm = blockIdx.z, l = lm / 2, m = lm % 2;
+    const float *S = src + ((size_t)l * 2 + (1 - m)) * 4 * F * F;       // [F (j)][4F (their rows)]
+    float *D = dst + ((size_t)l * 2 + m) * 4 * F * F;                    // [4F (our rows)][F (j)]
+    const int r0 = blockIdx.y * 32, j0 = blockIdx.x * 32;                // tile of OUR rows x j
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;              // 32 x 8 threads
+    for (int k = ty; k < 32; k += 8) {
+        const int row = r0 + tx, j = j0 + k;                             // read src[j][their(row)]: consecutive tx -> consecutive columns
+        if (row < 4 * F && j < F) tile[k][tx] = S[(size_t)j * 4 * F + (size_t)src_gate_block(row / F) * F + row % F];
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int row = r0 + k, j = j0 + tx;
+        if (row < 4 * F && j < F) D[(size_t)row * F + j] = tile[tx][k];
+    }
+}
+
+__global__ void tiramisu_sm100_lstm_relayout_bias(const float *__restrict__ src, float *__restrict__ dst, int F, int L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L * 4 * F) return;
+    const int l = i / (4 * F), row = i % (4 * F);
+    dst[i] = src[(size_t)l * 4 * F + src_gate_block(row / F) * F + row % F];
+}
+}  // namespace
+
+TB200_API int tiramisu_b200_lstm_ex(const float *Weights, const float *biases, const float *x, float *y, float *c_last, int32_t F,
+                                    int32_t B, int32_t L, int32_t T, int32_t layout)
+{
+    if (!Weights || !biases || !x || !y || F < 1 || B < 1 || L < 1 || T < 1 || layout < 0 || layout > 2) return fail(__func__, "bad argument");
+    if (layout == 0) return lstm_dispatch(Weights, biases, x, y, c_last, F, B, L, T, __func__);
+    const size_t wn = (size_t)L * 2 * 4 * F * F, bn = (size_t)L * 4 * F;
+    float *W0 = reinterpret_cast<float *>(pool_alloc(wn * 4)), *b0 = reinterpret_cast<float *>(pool_alloc(bn * 4));
+    if (!W0 || !b0) return 1;
+    if (layout == 1 && F % 4 == 0 && aligned16(Weights)) {
+        const size_t want = (wn / 4 + 255) / 256, cap = (size_t)sm_count() * 16;
+        tiramisu_sm100_lstm_relayout_rows<<<(unsigned)(want < cap ? want : cap), 256, 0, stream()>>>(Weights, W0, F, L);
+        if (post_launch("tiramisu_sm100_lstm_relayout_rows")) return 1;
+    } else if (layout == 1) {
+        // rows that cannot be moved as float4: per (layer, matrix, gate block) strided copies
+        for (int l = 0; l < L; l++)
+            for (int m = 0; m < 2; m++)
+                for (int g = 0; g < 4; g++) {
+                    const int sg = g == 0 ? 0 : (g == 1 ? 2 : (g == 2 ? 3 : 1));
+                    TB200_CHECK(cudaMemcpyAsync(W0 + (((size_t)l * 2 + m) * 4 + g) * F * F, Weights + (((size_t)l * 2 + (1 - m)) * 4 + sg) * F * F,
+                                                (size_t)F * F * 4, cudaMemcpyDeviceToDevice, stream()));
+                }
+    } else {
+        dim3 grid((unsigned)((F + 31) / 32), (unsigned)((4 * F + 31) / 32), (unsigned)(2 * L));
+        tiramisu_sm100_lstm_relayout_transposed<<<grid, 256, 0, stream()>>>(Weights, W0, F);
+        if (post_launch("tiramisu_sm100_lstm_relayout_transposed")) return 1;
+    }
+    tiramisu_sm100_lstm_relayout_bias<<<(unsigned)((bn + 255) / 256), 256, 0, stream()>>>(biases, b0, F, L);
+    if (post_launch("tiramisu_sm100_lstm_relayout_bias")) return 1;
+    const int rc = lstm_dispatch(W0, b0, x, y, c_last, F, B, L, T, __func__);
+    pool_free(W0); pool_free(b0);
+    return rc;
 }
 
 TB200_API const char *tiramisu_b200_lstm_last_engine(void) { return t_last_engine; }

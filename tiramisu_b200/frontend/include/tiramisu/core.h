@@ -61,7 +61,11 @@ public:
     void tag_gpu_shared() { loc_ = mem_loc::gpu_shared; }
     void tag_gpu_local() { loc_ = mem_loc::gpu_local; }
     void tag_gpu_register() { loc_ = mem_loc::gpu_register; }
-    void tag_gpu_constant() { loc_ = mem_loc::gpu_constant; }
+    /** Reference: __constant__ memory filled with cudaMemcpyToSymbol (src/tiramisu_codegen_cuda.cpp:817-823).  Here a
+      * small read-only table lives in global memory and reaches the kernel as `const T * __restrict__` (LDG.NC, served by
+      * L1 / the uniform datapath after the first touch): allocation, copies and kernel arguments are those of a
+      * gpu_global buffer. */
+    void tag_gpu_constant() { loc_ = mem_loc::gpu_global; }
 
     /** Allocate / free this buffer just before / after \p C at loop level \p level (reference core.h:1700-1712). */
     computation *allocate_at(computation &C, var level);

@@ -118,7 +118,7 @@ private:
     }
 };
 
-struct Cmp { expr l, r; std::string op; };
+struct Cmp { expr l, r; std::string op; expr r2; };       // op "in2": l is one of the two points r, r2
 
 void parse_conjunction(Reader &rd, std::vector<Cmp> &out)
 {
@@ -150,11 +150,27 @@ void parse_conjunction(Reader &rd, std::vector<Cmp> &out)
         } else {
             rd.reset(m);
             rd.expect("(");
-            parse_conjunction(rd, out);
+            std::vector<Cmp> inner;
+            parse_conjunction(rd, inner);
+            if (rd.peek().k == Tok::id && rd.peek().s == "or") {
+                // the one disjunction that is still a product of intervals and points: `(i = a or i = b)`, the two
+                // border lines of a grid (benchmarks/halide/heat2dgpu_tiramisu.cpp:51-52) -> Cmp with op "in2"
+                rd.next();
+                std::vector<Cmp> other;
+                parse_conjunction(rd, other);
+                const bool two_points = inner.size() == 1 && other.size() == 1 && inner[0].op == "=" && other[0].op == "=" &&
+                                        inner[0].l.get_expr_type() == e_var && other[0].l.get_expr_type() == e_var &&
+                                        inner[0].l.get_name() == other[0].l.get_name();
+                if (!two_points || (rd.peek().k == Tok::id && rd.peek().s == "or"))
+                    rd.fail("disjunctions are not boxes: only `(i = a or i = b)` is supported besides rectangular iteration domains");
+                out.push_back({inner[0].l, inner[0].r, "in2", other[0].r});
+            } else {
+                out.insert(out.end(), inner.begin(), inner.end());
+            }
             rd.expect(")");
         }
         if (rd.peek().k == Tok::id && rd.peek().s == "and") { rd.next(); continue; }
-        if (rd.peek().k == Tok::id && rd.peek().s == "or") rd.fail("disjunctions are not boxes: only rectangular iteration domains are supported");
+        if (rd.peek().k == Tok::id && rd.peek().s == "or") return;          // the caller decides (two-point form or error)
         return;
     }
 }
@@ -195,6 +211,7 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
     std::vector<std::string> iters = parse_name_list(rd, &fixed);
     std::vector<Cmp> cmps;
     if (rd.accept(":")) parse_conjunction(rd, cmps);
+    if (rd.peek().k == Tok::id && rd.peek().s == "or") rd.fail("disjunctions are not boxes: only rectangular iteration domains are supported");
     rd.expect("}");
 
     std::vector<expr> lo(iters.size()), hi(iters.size());
@@ -210,9 +227,39 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
             if (!x.substitute({it}, {expr((int32_t) 0)}).is_equal(x)) return true;
         return false;
     };
+    // `k * i` with a positive literal k (benchmarks/halide/rgbyuv420gpu_tiramisu.cpp: `0 <= 2 * i < N`): the iterator and k
+    auto scaled_iter = [&](const expr &x, int64_t &k) {
+        if (x.get_expr_type() != e_op || x.get_op_type() != o_mul) return -1;
+        for (int a = 0; a < 2; a++)
+            if (x.get_operand(a).is_int_literal() && x.get_operand(a).get_int_val() > 0 && iter_index(x.get_operand(1 - a)) >= 0) {
+                k = x.get_operand(a).get_int_val();
+                return iter_index(x.get_operand(1 - a));
+            }
+        return -1;
+    };
+    std::vector<std::pair<expr, expr>> two_points(iters.size());
     for (const Cmp &c : cmps) {
         int li = iter_index(c.l), ri = iter_index(c.r);
-        if (li >= 0 && ri < 0 && !mentions_iter(c.r)) {
+        int64_t k = 1;
+        if (c.op == "in2") {
+            if (li < 0 || mentions_iter(c.r) || mentions_iter(c.r2)) die("iteration domain of '" + name + "': unsupported disjunction in \"" + iteration_domain + "\"");
+            two_points[li] = {c.r, c.r2};
+            lo[li] = expr((int32_t) 0);
+            hi[li] = expr((int32_t) 2);
+        } else if (li < 0 && ri < 0 && scaled_iter(c.l, k) >= 0 && !mentions_iter(c.r)) {
+            // k*i op R (operands non-negative): i < ceil(R / k), i <= floor(R / k), ...
+            const int d = scaled_iter(c.l, k);
+            const expr K((int32_t) k);
+            if (c.op == "<") hi[d] = (c.r + (int32_t) (k - 1)) / K; else if (c.op == "<=") hi[d] = c.r / K + 1;
+            else if (c.op == ">=") lo[d] = (c.r + (int32_t) (k - 1)) / K; else if (c.op == ">") lo[d] = c.r / K + 1;
+            else die("iteration domain of '" + name + "' pins a scaled iterator: \"" + iteration_domain + "\"");
+        } else if (li < 0 && ri < 0 && scaled_iter(c.r, k) >= 0 && !mentions_iter(c.l)) {
+            const int d = scaled_iter(c.r, k);
+            const expr K((int32_t) k);
+            if (c.op == "<=") lo[d] = (c.l + (int32_t) (k - 1)) / K; else if (c.op == "<") lo[d] = c.l / K + 1;
+            else if (c.op == ">") hi[d] = (c.l + (int32_t) (k - 1)) / K; else if (c.op == ">=") hi[d] = c.l / K + 1;
+            else die("iteration domain of '" + name + "' pins a scaled iterator: \"" + iteration_domain + "\"");
+        } else if (li >= 0 && ri < 0 && !mentions_iter(c.r)) {
             if (c.op == "<=") hi[li] = c.r + 1; else if (c.op == "<") hi[li] = c.r;
             else if (c.op == ">=") lo[li] = c.r; else if (c.op == ">") lo[li] = c.r + 1;
             else { lo[li] = c.r; hi[li] = c.r + 1; }
@@ -243,6 +290,15 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
     }
     construct(name, vars, e, schedule_this_computation && !unbounded, t, fct);
     if (unbounded) { scheduled_ = true; pending_bounds_ = true; }
+    // a two-point iterator runs as a loop over {0, 1}; the iterator the expression and the access name is a + t * (b - a)
+    for (size_t i = 0; i < iters.size(); i++)
+        if (two_points[i].first.is_defined() && !unbounded) {
+            const int d = find_dim(iters[i]);
+            if (d < 0) continue;
+            const std::string nn = iters[i] + "_pt";
+            defs_.push_back({iters[i], two_points[i].first + var(nn) * (two_points[i].second - two_points[i].first)});
+            dims_[d].name = nn;
+        }
     is_input_ = !schedule_this_computation && !e.is_defined();
     // declared with an empty expression but to be scheduled: a statement whose expression comes later through
     // set_expression (reference tests/test_04.cpp); until then it reads like an input

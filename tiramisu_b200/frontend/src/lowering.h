@@ -135,6 +135,7 @@ private:
     void build_tree(const std::vector<computation *> &ord);
     // 3
     void assign_axes(Node *n);
+    void coalesce_thread_axes(Node *kernel_root);
     int count_below(const Node *n, loop_dim::tag_t t) const;
     void collect_kernel(Node *n, Kernel &k, bool inside);
     void note_expr(const expr &e, Kernel &k, bool is_store_target);

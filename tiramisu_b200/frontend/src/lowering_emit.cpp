@@ -376,6 +376,53 @@ void Lowering::emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind)
     emit_assignment(n, os, ind, true);
 }
 
+// Which thread loop becomes threadIdx.x is the back end's choice, not the schedule's: every thread-tagged loop is
+// parallel and all indices are computed from loop iterators, never from threadIdx itself.  The reference numbers the
+// axes from the innermost tagged loop outwards (src/tiramisu_codegen_cuda.cpp: gpu_tile(i, j, ...) makes j threadIdx.x),
+// which in the `*gpu` Halide benchmarks — `gpu_tile(i, j, 16, 16)` on images stored [c][j][i] — puts the ROW index on
+// threadIdx.x: the 32 lanes of a warp touch 16 different rows per access (r02 run 4: cvtcolorgpu at 0.08 of the HBM
+// roofline).  Here the thread loop whose iterator is the unit-stride index of most global accesses (stores count
+// twice) takes axis x; the block loops are renumbered the same way.  Kernels with a warp-shuffle reduction keep their
+// lane dimension on x.
+void Lowering::coalesce_thread_axes(Node *root)
+{
+    using lowering_detail::affine_form;
+    std::vector<Node *> loops, stmts, stack{root};
+    while (!stack.empty()) {
+        Node *x = stack.back(); stack.pop_back();
+        if (x->is_loop) { if (x->axis >= 0) loops.push_back(x); }
+        else if (x->comp) stmts.push_back(x);
+        for (auto &c : x->kids) stack.push_back(c.get());
+    }
+    for (Node *l : loops) if (l->warp_reduce || l->dim_name.rfind("_lane_", 0) == 0) return;
+    long votes[3] = {0, 0, 0};
+    for (Node *st : stmts) {
+        computation *c = st->comp;
+        const expr &e = c->get_expr();
+        if (!e.is_defined() || e.get_expr_type() == e_sync) continue;
+        if (e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate || e.get_op_type() == o_free)) continue;
+        for (const Access &a : accesses_of(c)) {
+            if (!a.b || a.idx.empty() || a.b->get_location() != mem_loc::gpu_global) continue;
+            expr last = a.idx.back();
+            for (auto &d : c->defs()) last = last.substitute({d.first}, {d.second});
+            std::map<std::string, int64_t> coef; int64_t cst = 0;
+            if (!affine_form(last, coef, cst)) continue;
+            for (Node *l : st->path)
+                if (l->tag == loop_dim::gpu_thread && l->axis >= 0 && l->axis < 3) {
+                    auto it = coef.find(l->dim_name);
+                    if (it != coef.end() && (it->second == 1 || it->second == -1)) votes[l->axis] += a.write ? 2 : 1;
+                }
+        }
+    }
+    int best = 0;
+    for (int a = 1; a < 3; a++) if (votes[a] > votes[best]) best = a;
+    if (best == 0 || getenv("TIRAMISU_B200_KEEP_AXES")) return;
+    for (Node *l : loops) {
+        if (l->axis == best) l->axis = 0;
+        else if (l->axis == 0) l->axis = best;
+    }
+}
+
 void Lowering::emit_kernel(Node *n, std::ostringstream &host, int ind, std::vector<Node *> &host_loops)
 {
     Kernel k;
@@ -402,6 +449,8 @@ void Lowering::emit_kernel(Node *n, std::ostringstream &host, int ind, std::vect
     k.name = "tiramisu_sm100_" + san(f_->get_name()) + "_k" + std::to_string(next_kernel_++) + "_" + san(first->comp ? first->comp->get_name() : n->dim_name);
 
     if (try_gemm_pattern(k, host, ind)) return;
+
+    coalesce_thread_axes(n);
 
     // launch dimensions: per axis, the largest extent among the tagged loops on that axis
     std::vector<Node *> tagged;
