@@ -205,6 +205,23 @@ int tiramisu_b200_comm_exchange(int32_t n, const int32_t *send_peer, void *const
  * NVLink; peers[rank] == *local.  Collective: every rank must call it, in the same order. */
 int tiramisu_b200_comm_alloc_symmetric(uint64_t bytes, void **local, void **peers);
 int tiramisu_b200_comm_free_symmetric(void *local);
+/* Broadcast of [data_offset, data_offset + bytes) of the root's symmetric block into every rank's block, in `panels`
+ * (1..64) equal parts, as peer copies by the DMA engines on two library-owned streams forked from / joined to the
+ * thread's stream (scatter: every non-root rank pulls its slice of a panel from the root; all-gather: the other
+ * slices from the ranks that own them) — no SM kernels, so it overlaps compute.  peers: the table
+ * comm_alloc_symmetric returned; flags_offset: 256 zero-initialised bytes inside the block (world <= 30); epoch: 1, 2,
+ * 3, ... per call on this buffer, the same on every rank.  Replaces the per-rank MPI_Recv of B in the reference's
+ * distributed GEMMs (src/tiramisu_core.cpp:8997-9044 send/recv semantics) for the row-sharded sgemm. */
+int tiramisu_b200_comm_broadcast_sym(void *const *peers, uint64_t data_offset, uint64_t bytes, uint64_t flags_offset,
+                                     int32_t root, uint32_t epoch, int32_t panels);
+/* Row-sharded sgemm with B's arrival fused in: C[rows][N] = alpha A[rows][K] B[K][N] + beta C on
+ * every rank, B row-major and tightly packed at b_offset of the symmetric block, valid on `root` when the call is
+ * made.  K is cut into `panels` K panels (K / panels a multiple of 32); panel p+1 travels (as above) while the
+ * tcgen05 GEMM on panel p runs, and each panel GEMM waits for its panel INSIDE the kernel (TMA producer warp polls
+ * the panel's arrival word), so all panel GEMMs are queued at once.  Stream-ordered; collective over the ranks. */
+int tiramisu_b200_sgemm_bcast_b(void *const *peers, uint64_t b_offset, uint64_t flags_offset, int32_t root, uint32_t epoch,
+                                int32_t panels, const float *A, float *C, uint64_t rows, uint64_t N, uint64_t K,
+                                float alpha, float beta, uint64_t ldA, uint64_t ldC);
 int tiramisu_MPI_init(void);                 /* src/tiramisu_mpi.cpp:8  reads torchrun's env; returns rank */
 void tiramisu_MPI_cleanup(void);             /* :19 */
 void tiramisu_MPI_global_barrier(void);      /* :23 */

@@ -145,7 +145,7 @@ def test_non_box_domains_are_rejected(frontend_lib, tmp_path):
 using namespace tiramisu;
 int main() {
     tiramisu::function f("bad");
-    computation c("[N]->{c[i,j]: 0<=i<N and (j = 0 or j = N - 1)}", expr(0.f), true, p_float32, &f);
+    computation c("[N]->{c[i,j]: 0<=i<N and (j = 0 or j = 1 or j = N - 1)}", expr(0.f), true, p_float32, &f);
     return 0;
 }""")
     exe = str(tmp_path / "bad")

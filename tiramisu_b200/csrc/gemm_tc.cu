@@ -106,6 +106,15 @@ int make_tensor_map_f16(CUtensorMap *map, const void *base, int rank, const uint
 static thread_local int t_hint_kernel = 0, t_hint_bn = 0;
 void gemm_tc_hint(int kernel, int bn) { t_hint_kernel = kernel; t_hint_bn = bn; }
 
+// Arrival gate for the NEXT gemm_f32_tc call of this thread (consumed by it): device address of a uint32 that some
+// other stream raises to >= value once the B operand is in place.  Persistent kernels poll it in the TMA producer
+// warp (the launch, prologue and A loads overlap the tail of the transfer); the other kernels get a stream-side
+// cuStreamWaitValue32 in front of the launch.
+static thread_local const uint32_t *t_gate = nullptr;
+static thread_local uint32_t t_gate_value = 0;
+void gemm_tc_gate(const uint32_t *flag, uint32_t value) { t_gate = flag; t_gate_value = value; }
+int stream_wait_value32(cudaStream_t st, const uint32_t *flag, uint32_t value);       // comm.cu
+
 }  // namespace tb200
 
 namespace {
@@ -133,6 +142,9 @@ struct GemmParams {
     const float *alpha_dev;             // optional device-resident factor multiplied into alpha (LSTM: the
                                         // power-of-two de-scaling of block-scaled fp16 weights), else null
     int prefetch_kb;                    // L2 prefetch distance in k-slabs beyond the shared-memory ring (0 = off)
+    const uint32_t *gate = nullptr;     // optional arrival flag of the B operand (row-sharded sgemm: the K panel of B is being
+    uint32_t gate_value = 0;            // copied in by DMA engines while this kernel starts): the TMA producer polls
+                                        // *gate >= gate_value before its first B load (persistent kernels only)
 };
 
 // F16: operands are fp16 (kind::f16, K = 16 per instruction, 64 elements per 128-byte swizzle row):
@@ -641,6 +653,23 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
     if (warp == 0) {
         // ===== TMA producer (every CTA loads its own A rows and its own share of B); whole warp,
         // uniform control flow, one elected lane issues =====
+        if (p.gate) {
+            // B is still arriving (peer copies by DMA engines, comm.cu: sgemm_bcast_b): everything above — barrier init,
+            // TMEM allocation, descriptor prefetch — already ran; wait here for the panel's arrival flag, then order the
+            // generic-proxy acquire before the async-proxy (TMA) reads of the freshly written bytes
+            if (lane == 0) {
+                const long long t0 = clock64();
+                uint32_t v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.gate) : "memory");
+                    if (v >= p.gate_value) break;
+                    __nanosleep(200);
+                    if (clock64() - t0 > 12000000000LL) __trap();      // seconds: a protocol bug must not hang the box
+                } while (true);
+            }
+            __syncwarp();
+            ptx::fence_proxy_async_all();
+        }
         {
             uint32_t it = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -998,6 +1027,8 @@ int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N,
     p.b_sbo = 512;
     p.alpha_dev = nullptr;
     p.prefetch_kb = gemm_prefetch_kb(0);
+    p.gate = tb200::t_gate; p.gate_value = tb200::t_gate_value;
+    tb200::t_gate = nullptr;
     auto kern = tiramisu_sm100_gemm_tf32_persistent<CG, B_MN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1080,6 +1111,11 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
         const uint64_t pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
         kernel = (pair_tiles * 2 * 5 >= sms * 4 && K >= 256) ? 3 : 1;
     }
+    if (t_gate && kernel != 3 && kernel != 2) {              // no in-kernel gate in the one-tile kernels: wait on the stream
+        const uint32_t *g = t_gate;
+        t_gate = nullptr;
+        if (stream_wait_value32(stream(), g, t_gate_value)) return 1;
+    }
     if (kernel == 3)
         return tB ? launch_tc_persistent<2, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC)
                   : launch_tc_persistent<2, true>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC);
@@ -1141,6 +1177,11 @@ int gemm_f32(const float *A, const float *B, float *C, uint64_t M, uint64_t N, u
     const bool ok = gemm_tc_addressable(A, B, C, M, N, K, ldA, ldB, ldC, tA, tB);
     if (mode == 2 && !ok) return fail("tiramisu_cublas_sgemm", "operands not addressable by the tcgen05 path");
     if (mode != 1 && ok) return gemm_f32_tc(A, B, C, M, N, K, alpha, beta, ldA, ldB, ldC, tB);
+    if (t_gate) {                                            // arrival gate of the B operand: stream-side on this path
+        const uint32_t *g = t_gate;
+        t_gate = nullptr;
+        if (stream_wait_value32(stream(), g, t_gate_value)) return 1;
+    }
     return gemm_f32_exact(A, B, C, M, N, K, alpha, beta, ldA, ldB, ldC, tA, tB);
 }
 

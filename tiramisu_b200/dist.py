@@ -161,3 +161,61 @@ class SymmetricRows:
         if self.local:
             _lib.check(_lib.lib().tiramisu_b200_comm_free_symmetric(self.local), "comm_free_symmetric")
             self.local = None
+
+
+# ---- B of the row-sharded sgemm: broadcast by the DMA engines, consumed by the GEMM as it arrives -------
+class SymmetricB:
+    """K x N fp32 matrix in symmetric memory + the 256 flag bytes tiramisu_b200_sgemm_bcast_b needs.
+    Collective constructor / free.  `sgemm(A, C, rows, alpha, beta)` is the fused call: the root's B travels
+    in K panels (scatter + all-gather by peer copies, comm.cu) while every rank's panel GEMMs run."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, K: int, N: int):
+        L = _lib.lib()
+        self.world, self.rank = L.tiramisu_b200_comm_size(), L.tiramisu_b200_comm_rank()
+        self.K, self.N = K, N
+        self.data_bytes = ((K * N * 4 + 255) // 256) * 256
+        local = C.c_void_p()
+        self._peers = (C.c_void_p * self.world)()
+        _lib.check(L.tiramisu_b200_comm_alloc_symmetric(self.data_bytes + self.FLAG_BYTES, C.byref(local), self._peers),
+                   "comm_alloc_symmetric")
+        self.local = local.value
+        self.epoch = 0
+
+    def data_ptr(self) -> int:
+        return self.local
+
+    def tensor(self):
+        """My copy of B as a torch view (no copy) — plumbing for tests and the bench."""
+        import torch
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.K, self.N), "typestr": "<f4", "data": (self.local, False), "version": 2}
+        return torch.as_tensor(raw, device="cuda")
+
+    @staticmethod
+    def default_panels(K: int) -> int:
+        p = max(1, min(16, K // 2048))
+        while p > 1 and (K % p or (K // p) % 32):
+            p -= 1
+        return p
+
+    def broadcast(self, root: int = 0, panels: int | None = None) -> None:
+        self.epoch += 1
+        _lib.check(_lib.lib().tiramisu_b200_comm_broadcast_sym(self._peers, 0, self.K * self.N * 4, self.data_bytes, root, self.epoch,
+                                                               panels or self.default_panels(self.K)), "comm_broadcast_sym")
+
+    def sgemm(self, A_ptr: int, C_ptr: int, rows: int, alpha: float, beta: float, root: int = 0, panels: int | None = None,
+              ldA: int = 0, ldC: int = 0) -> None:
+        self.epoch += 1
+        _lib.check(_lib.lib().tiramisu_b200_sgemm_bcast_b(self._peers, 0, self.data_bytes, root, self.epoch,
+                                                          panels or self.default_panels(self.K), C.c_void_p(A_ptr), C.c_void_p(C_ptr),
+                                                          rows, self.N, self.K, alpha, beta, ldA, ldC), "sgemm_bcast_b")
+
+    def free(self) -> None:
+        if self.local:
+            _lib.check(_lib.lib().tiramisu_b200_comm_free_symmetric(self.local), "comm_free_symmetric")
+            self.local = None

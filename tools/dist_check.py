@@ -99,6 +99,35 @@ def main():
     ok &= good
     print(f"[rank {rank}] sgemm row-sharded: {'ok' if good else 'MISMATCH'}", flush=True)
 
+    # ---- 4b. the same with B in symmetric memory: DMA-engine scatter + all-gather in K panels, panel GEMMs gated in
+    # the kernel on their panel's arrival word (tiramisu_b200_sgemm_bcast_b), several epochs on one block ------------
+    for n_b, panels in ((1024, 4), (2048, 1), (4096, 8)):
+        rngb = np.random.default_rng(70 + n_b)
+        symB = tdist.SymmetricB(n_b, n_b)
+        a0, a1 = tdist.row_shard(n_b, world, rank)
+        for ep in range(3):
+            A = rngb.integers(-3, 4, (n_b, n_b)).astype(np.float32)
+            B = rngb.integers(-3, 4, (n_b, n_b)).astype(np.float32)
+            Cm = rngb.integers(-3, 4, (n_b, n_b)).astype(np.float32)
+            wantc = 3.0 * (A.astype(np.float64) @ B.astype(np.float64)) + 2.0 * Cm
+            dA, dC = torch.from_numpy(A[a0:a1]).cuda(), torch.from_numpy(Cm[a0:a1]).cuda()
+            if rank == 0:
+                _lib.check(L.tiramisu_cuda_memcpy_to_device(C.c_void_p(symB.data_ptr()), B.ctypes.data_as(C.c_void_p), B.nbytes))
+            torch.cuda.synchronize()
+            if ep == 2:                                              # data motion alone, then a plain GEMM on the local copy
+                symB.broadcast(0, panels)
+                api.cublas_sgemm(dA.data_ptr(), symB.data_ptr(), dC.data_ptr(), a1 - a0, n_b, n_b, 3.0, 2.0)
+            else:
+                symB.sgemm(dA.data_ptr(), dC.data_ptr(), a1 - a0, 3.0, 2.0, 0, panels)
+            api.synchronize()
+            gotB = np.empty((n_b, n_b), np.float32)
+            _lib.check(L.tiramisu_cuda_memcpy_to_host(gotB.ctypes.data_as(C.c_void_p), C.c_void_p(symB.data_ptr()), gotB.nbytes))
+            good = np.array_equal(dC.cpu().numpy().astype(np.float64), wantc[a0:a1]) and np.array_equal(gotB, B)
+            ok &= good
+            print(f"[rank {rank}] sgemm + fused B broadcast n={n_b} panels={panels} epoch={ep + 1}: {'ok' if good else 'MISMATCH'}", flush=True)
+            torch.distributed.barrier()                              # rank 0 rewrites B next: everyone has verified its copy
+        symB.free()
+
     # ---- 5. peer-memory halos: no exchange, the sweep reads the neighbours' rows over NVLink ---------------
     for Hp in (48 * world + 7, 49 * world, 13 * world + 1):      # row counts that leave short last row blocks
         Wp = 2048
