@@ -215,13 +215,15 @@ int tiramisu_b200_comm_free_symmetric(void *local);
 int tiramisu_b200_comm_broadcast_sym(void *const *peers, uint64_t data_offset, uint64_t bytes, uint64_t flags_offset,
                                      int32_t root, uint32_t epoch, int32_t panels);
 /* Row-sharded sgemm with B's arrival fused in: C[rows][N] = alpha A[rows][K] B[K][N] + beta C on
- * every rank, B row-major and tightly packed at b_offset of the symmetric block, valid on `root` when the call is
- * made.  K is cut into `panels` K panels (K / panels a multiple of 32); panel p+1 travels (as above) while the
- * tcgen05 GEMM on panel p runs, and each panel GEMM waits for its panel INSIDE the kernel (TMA producer warp polls
- * the panel's arrival word), so all panel GEMMs are queued at once.  Stream-ordered; collective over the ranks. */
-int tiramisu_b200_sgemm_bcast_b(void *const *peers, uint64_t b_offset, uint64_t flags_offset, int32_t root, uint32_t epoch,
-                                int32_t panels, const float *A, float *C, uint64_t rows, uint64_t N, uint64_t K,
-                                float alpha, float beta, uint64_t ldA, uint64_t ldC);
+ * every rank; A, C: this rank's row shard; B: an ordinary row-major device matrix (pitch ldB) on `root` only.  The
+ * symmetric block at stage_offset (K * N * 4 bytes) is the staging area B travels through, in `panels` column panels
+ * (N / panels a multiple of 256, same value on every rank) stored panel-major: the root re-lays B out with local DMA
+ * copies, the panels travel as above, and every other rank runs ONE persistent tcgen05 GEMM launch over the staged
+ * layout (3-D tensor map) whose TMA producer warp polls a panel's arrival word before the B loads of a tile in a
+ * panel it has not seen yet.  Stream-ordered; collective over the ranks; without a communicator a plain sgemm. */
+int tiramisu_b200_sgemm_bcast_b(void *const *peers, uint64_t stage_offset, uint64_t flags_offset, int32_t root, uint32_t epoch,
+                                int32_t panels, const float *B, uint64_t ldB, const float *A, float *C, uint64_t rows,
+                                uint64_t N, uint64_t K, float alpha, float beta, uint64_t ldA, uint64_t ldC);
 int tiramisu_MPI_init(void);                 /* src/tiramisu_mpi.cpp:8  reads torchrun's env; returns rank */
 void tiramisu_MPI_cleanup(void);             /* :19 */
 void tiramisu_MPI_global_barrier(void);      /* :23 */

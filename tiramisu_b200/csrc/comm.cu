@@ -457,25 +457,39 @@ TB200_API int tiramisu_b200_comm_alloc_symmetric(uint64_t bytes, void **local, v
 }
 
 // ---- copy-engine broadcast over symmetric memory, fused with the row-sharded sgemm ------------------------
-// Row-sharded sgemm needs rank 0's B on every rank while the panel GEMMs run.  ncclBroadcast does
-// that with SM kernels that compete with a persistent GEMM for the same SMs, along a ring (measured r01: ~350 GB/s per
-// rank, 3 ms for the 1 GiB B of 16384^3 against 1.6 ms of GEMM on 8 GPUs).  Here B lives in symmetric memory, is cut
-// into K panels (contiguous row ranges of the row-major [K][N] matrix) and every panel into world-1 slices, one per
-// non-root rank:
+// Row-sharded sgemm needs rank 0's B on every rank while the GEMM runs.  ncclBroadcast does that with
+// SM kernels that compete with a persistent GEMM for the same SMs, along a ring (measured r01: ~350 GB/s per rank, 3 ms
+// for the 1 GiB B of 16384^3 against 1.6 ms of GEMM on 8 GPUs).  Here the data travels through symmetric memory in
+// `panels` contiguous panels, every panel cut into world-1 slices, one per non-root rank:
 //   scatter    : rank r pulls ITS slice of panel p from the root          — every byte leaves the root exactly once
 //   all-gather : rank r pulls slice q of panel p from rank q (q != root)  — every other link carries 1/(world-1) of it
-// as peer cudaMemcpyAsync on two library-owned streams per thread: DMA engines only, no SM work at all, so the
-// transfer of panel p+1 overlaps the tcgen05 GEMM on panel p instead of fighting it for SMs.  Cross-rank ordering
-// uses uint32 words inside the symmetric block at `flags_offset` (zero at allocation):
-//   [0, world)         ready[q]  last token for which rank q holds its own slice        (written by q: 4-byte peer copy)
+// as peer cudaMemcpyAsync on two library-owned streams per thread: DMA engines only, no SM work at all, so the transfer
+// overlaps the tcgen05 GEMM instead of fighting it for SMs.  Contiguous ranges are what the DMA engines move fastest
+// between processes (r02 run 9: 626 GB/s; a pitched copy of 4 KB rows of IPC-mapped memory: 257 GB/s), so for the sgemm
+// the root first re-lays B out PANEL-MAJOR into its staging block — column panel j, B[:, j w .. (j+1) w), becomes a
+// contiguous row-major [K][w] matrix — with local pitched DMA copies; the GEMM reads that layout through a 3-D tensor
+// map (gemm_tc.cu: GemmParams::b_panel_cols).  Cross-rank ordering uses uint32 words inside the symmetric block at
+// `flags_offset` (zero at allocation):
+//   [0, world)         ready[q]  last token for which rank q holds its own slice; ready[root]: last token for which the
+//                                root's staging panel is in place                  (written by q: 4-byte peer copy)
 //   [world, 2 world)   done[q]   last epoch for which rank q finished reading from me   (written by q)
 //   [2 world]          have      last token for which the WHOLE panel is in my block    (cuStreamWriteValue32, local)
 //   [2 world + 1, +2]  source words of the two kinds of peer flag copies
 // waits are cuStreamWaitValue32 on LOCAL words (stream-side, no spinning kernel), token(epoch, p) = 64 (epoch-1) + p + 1.
-// The consumer of `have` is the GEMM itself: the persistent tcgen05 kernels poll it from their TMA producer warp
-// (gemm_tc.cu: GemmParams::gate), so the panel GEMMs are queued back to back with no host or event synchronisation.
+// The consumer of `have` is the GEMM itself: ONE persistent tcgen05 launch walks its tiles column panel by column
+// panel and its TMA producer warp polls `have` before the B loads of a tile whose panel it has not yet seen
+// (GemmParams::gate) — no K-panel accumulation passes over C, no host or event synchronisation.  That launch is
+// submitted BEFORE the copies: a hardware work queue is FIFO in submission order across the streams that share it, and
+// an event / value wait at the head of a queue holds back every later entry — submitted first, the copies' waits sat in
+// front of the GEMM launch and the whole broadcast ran before the first MMA (r02 run 9: fused = broadcast + GEMM).
 namespace tb200 {
-void gemm_tc_gate(const uint32_t *flag, uint32_t value);
+void gemm_tc_gate(const uint32_t *flag, uint32_t value, int cols, uint32_t last);
+void gemm_tc_b_panels(int cols, uint64_t panel_stride);
+int gemm_tc_kernel_choice(uint64_t M, uint64_t N, uint64_t K, bool *was_auto);
+bool gemm_tc_addressable(const float *A, const float *B, const float *C, uint64_t M, uint64_t N, uint64_t K, uint64_t ldA,
+                         uint64_t ldB, uint64_t ldC, bool tA, bool tB);
+int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,
+                uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tB);
 int gemm_f32(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,
              uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tA, bool tB);
 
@@ -515,8 +529,10 @@ struct BcastStreams {
     int init()
     {
         if (scatter) return 0;
-        TB200_CHECK(cudaStreamCreateWithFlags(&scatter, cudaStreamNonBlocking));
-        TB200_CHECK(cudaStreamCreateWithFlags(&gather, cudaStreamNonBlocking));
+        int lo = 0, hi = 0;                                  // copy streams at the highest priority: their (tiny) stream
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);          // operations are never queued behind compute of equal priority
+        TB200_CHECK(cudaStreamCreateWithPriority(&scatter, cudaStreamNonBlocking, hi));
+        TB200_CHECK(cudaStreamCreateWithPriority(&gather, cudaStreamNonBlocking, hi));
         for (cudaEvent_t *e : {&fork, &end_s, &end_g}) TB200_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         for (int i = 0; i < kMaxPanels; i++) TB200_CHECK(cudaEventCreateWithFlags(&slice[i], cudaEventDisableTiming));
         return 0;
@@ -524,22 +540,48 @@ struct BcastStreams {
 };
 thread_local BcastStreams t_bs;
 
-// Enqueues the whole panelised broadcast on the library's two copy streams, forked from the caller's stream `st`;
-// leaves end_s / end_g recorded (the caller joins them when it wants "B complete / reusable" in stream order).
-int bcast_sym_enqueue(cudaStream_t st, void *const *peers, uint64_t data_offset, uint64_t bytes, uint64_t flags_offset,
-                      int root, uint32_t epoch, int panels, uint64_t panel_bytes)
+// Row-major source the root re-lays out panel-major into its staging block before a panel travels (sgemm), or nothing
+// (plain broadcast: the root's block already holds the bytes).
+struct RootPack {
+    const float *B = nullptr;                     // [K][N] row-major on the root, pitch ldB elements
+    uint64_t K = 0, ldB = 0, cols = 0;            // columns per panel
+};
+
+// Fork of the copy streams from the caller's stream: recorded BEFORE the consumer (GEMM) is launched, so that the copies
+// are not ordered behind it.
+int bcast_sym_fork(cudaStream_t st)
+{
+    if (t_bs.init()) return 1;
+    TB200_CHECK(cudaEventRecord(t_bs.fork, st));
+    return 0;
+}
+
+// Enqueues the whole panelised broadcast of [data_offset, data_offset + bytes) on the library's two copy streams (after
+// bcast_sym_fork); leaves end_s / end_g recorded (the caller joins them when it wants "complete / reusable" in stream order).
+int bcast_sym_enqueue(void *const *peers, uint64_t data_offset, uint64_t bytes, uint64_t panel_bytes, uint64_t flags_offset,
+                      int root, uint32_t epoch, int panels, const RootPack &pack)
 {
     const int world = g_comm.world, rank = g_comm.rank;
-    if (t_bs.init()) return 1;
     auto data = [&](int r) { return static_cast<char *>(peers[r]) + data_offset; };
     auto flags = [&](int r) { return reinterpret_cast<uint32_t *>(static_cast<char *>(peers[r]) + flags_offset); };
     uint32_t *mine = flags(rank);
     uint32_t *src_ready = mine + 2 * world + 1, *src_done = mine + 2 * world + 2;
     const uint32_t base = 64u * (epoch - 1);
-    TB200_CHECK(cudaEventRecord(t_bs.fork, st));
     TB200_CHECK(cudaStreamWaitEvent(t_bs.gather, t_bs.fork, 0));
     if (rank == root) {
-        // the root's copy is the original: nothing to fetch.  Its B may be rewritten once every peer has read it.
+        // Nothing to fetch.  Stage panel after panel (sgemm) and tell everybody which panels are in place — ordered after
+        // whatever filled the source on the caller's stream; the source may be rewritten once every peer has read it.
+        for (int p = 0; p < panels; p++) {
+            if (pack.B) {
+                TB200_CHECK(cudaMemcpy2DAsync(data(root) + (uint64_t)p * panel_bytes, pack.cols * 4, pack.B + (uint64_t)p * pack.cols,
+                                              pack.ldB * 4, pack.cols * 4, pack.K, cudaMemcpyDeviceToDevice, t_bs.gather));
+            } else if (p + 1 < panels) {
+                continue;                                             // in place already: one announcement for all panels
+            }
+            if (stream_write_value32(t_bs.gather, src_ready, base + (uint32_t)p + 1)) return 1;
+            for (int q = 0; q < world; q++)
+                if (q != root) TB200_CHECK(cudaMemcpyAsync(flags(q) + root, src_ready, 4, cudaMemcpyDeviceToDevice, t_bs.gather));
+        }
         if (stream_write_value32(t_bs.gather, mine + 2 * world, base + (uint32_t)panels)) return 1;
         for (int q = 0; q < world; q++)
             if (q != root && stream_wait_value32(t_bs.gather, mine + world + q, epoch)) return 1;
@@ -550,23 +592,29 @@ int bcast_sym_enqueue(cudaStream_t st, void *const *peers, uint64_t data_offset,
     TB200_CHECK(cudaStreamWaitEvent(t_bs.scatter, t_bs.fork, 0));
     const int ns = world - 1;                                               // slices per panel: one per non-root rank
     auto slice_of = [&](int r) { return r < root ? r : r - 1; };
+    auto pull = [&](int p, int s, int from, cudaStream_t cs) -> int {      // slice s of panel p from rank `from` into my block
+        const uint64_t p_lo = std::min<uint64_t>(bytes, (uint64_t)p * panel_bytes);
+        const uint64_t p_len = std::min<uint64_t>(bytes, p_lo + panel_bytes) - p_lo;
+        const uint64_t sl = ((p_len + ns - 1) / ns + 255) & ~uint64_t(255);
+        const uint64_t lo = std::min<uint64_t>(p_len, (uint64_t)s * sl), hi = std::min<uint64_t>(p_len, (uint64_t)(s + 1) * sl);
+        if (hi > lo) TB200_CHECK(cudaMemcpyAsync(data(rank) + p_lo + lo, data(from) + p_lo + lo, hi - lo, cudaMemcpyDeviceToDevice, cs));
+        return 0;
+    };
     // nobody still reads what this call overwrites: every non-root peer finished the previous epoch's pulls from me
     for (int q = 0; q < world; q++)
         if (q != rank && q != root && stream_wait_value32(t_bs.scatter, mine + world + q, epoch - 1)) return 1;
     for (int p = 0; p < panels; p++) {
-        const uint64_t p_lo = (uint64_t)p * panel_bytes;
-        const uint64_t p_len = std::min<uint64_t>(bytes, p_lo + panel_bytes) - std::min<uint64_t>(bytes, p_lo);
-        const uint64_t sl = ((p_len + ns - 1) / ns + 255) & ~uint64_t(255);
-        auto lo = [&](int s) { return p_lo + std::min<uint64_t>(p_len, (uint64_t)s * sl); };
-        auto len = [&](int s) { return std::min<uint64_t>(p_len, (uint64_t)(s + 1) * sl) - std::min<uint64_t>(p_len, (uint64_t)s * sl); };
         const uint32_t token = base + (uint32_t)p + 1;
-        const int ms = slice_of(rank);
-        // scatter: my slice from the root, then tell every other non-root rank that it can be pulled from me
-        if (len(ms)) TB200_CHECK(cudaMemcpyAsync(data(rank) + lo(ms), data(root) + lo(ms), len(ms), cudaMemcpyDeviceToDevice, t_bs.scatter));
-        if (stream_write_value32(t_bs.scatter, src_ready, token)) return 1;
-        for (int k = 1; k < world; k++) {
-            const int q = (rank + k) % world;
-            if (q != root) TB200_CHECK(cudaMemcpyAsync(flags(q) + rank, src_ready, 4, cudaMemcpyDeviceToDevice, t_bs.scatter));
+        // scatter: my slice from the root once the root has staged the panel, then tell every other non-root rank that it
+        // can be pulled from me
+        if (stream_wait_value32(t_bs.scatter, mine + root, token)) return 1;
+        if (pull(p, slice_of(rank), root, t_bs.scatter)) return 1;
+        if (ns > 1) {
+            if (stream_write_value32(t_bs.scatter, src_ready, token)) return 1;
+            for (int k = 1; k < world; k++) {
+                const int q = (rank + k) % world;
+                if (q != root) TB200_CHECK(cudaMemcpyAsync(flags(q) + rank, src_ready, 4, cudaMemcpyDeviceToDevice, t_bs.scatter));
+            }
         }
         TB200_CHECK(cudaEventRecord(t_bs.slice[p], t_bs.scatter));
         // all-gather: slice q of this panel from rank q, nearest ranks first so that concurrent pulls use different links
@@ -574,14 +622,12 @@ int bcast_sym_enqueue(cudaStream_t st, void *const *peers, uint64_t data_offset,
         for (int k = 1; k < world; k++) {
             const int q = (rank + k) % world;
             if (q == root) continue;
-            const int s = slice_of(q);
-            if (!len(s)) continue;
             if (stream_wait_value32(t_bs.gather, mine + q, token)) return 1;
-            TB200_CHECK(cudaMemcpyAsync(data(rank) + lo(s), data(q) + lo(s), len(s), cudaMemcpyDeviceToDevice, t_bs.gather));
+            if (pull(p, slice_of(q), q, t_bs.gather)) return 1;
         }
         if (stream_write_value32(t_bs.gather, mine + 2 * world, token)) return 1;           // have: panel p complete here
     }
-    // done reading from everybody (the root included: it waits for this before its B may change)
+    // done reading from everybody (the root included: it waits for this before its source may change)
     if (stream_write_value32(t_bs.gather, src_done, epoch)) return 1;
     for (int k = 1; k < world; k++) {
         const int q = (rank + k) % world;
@@ -592,11 +638,18 @@ int bcast_sym_enqueue(cudaStream_t st, void *const *peers, uint64_t data_offset,
     return 0;
 }
 
+int bcast_sym_join(cudaStream_t st)
+{
+    TB200_CHECK(cudaStreamWaitEvent(st, t_bs.end_s, 0));
+    TB200_CHECK(cudaStreamWaitEvent(st, t_bs.end_g, 0));
+    return 0;
+}
+
 int bcast_sym_check(const char *who, void *const *peers, int32_t root, uint32_t epoch, int32_t panels)
 {
     if (!g_comm.comm) return fail(who, "communicator not initialised");
     if (!peers || root < 0 || root >= g_comm.world || epoch == 0 || epoch >= (1u << 25) || panels < 1 || panels > kMaxPanels ||
-        g_comm.world > 32)
+        g_comm.world > 30)
         return fail(who, "bad argument");
     return 0;
 }
@@ -611,44 +664,64 @@ TB200_API int tiramisu_b200_comm_broadcast_sym(void *const *peers, uint64_t data
     if (g_comm.world == 1 || bytes == 0) return 0;
     cudaStream_t st = stream();
     const uint64_t panel_bytes = (((bytes + panels - 1) / panels) + 255) & ~uint64_t(255);
-    if (bcast_sym_enqueue(st, peers, data_offset, bytes, flags_offset, root, epoch, panels, panel_bytes)) return 1;
-    TB200_CHECK(cudaStreamWaitEvent(st, t_bs.end_s, 0));
-    TB200_CHECK(cudaStreamWaitEvent(st, t_bs.end_g, 0));
-    return 0;
+    if (bcast_sym_fork(st) || bcast_sym_enqueue(peers, data_offset, bytes, panel_bytes, flags_offset, root, epoch, panels, RootPack{}))
+        return 1;
+    return bcast_sym_join(st);
 }
 
 // Row-sharded sgemm with B's arrival fused in:  C[rows][N] = alpha * A[rows][K] * B[K][N] + beta * C  on every rank,
-// A and C this rank's row shard, B (row-major, tightly packed, at b_offset of the symmetric block) valid on the root
-// only when the call is made.  K is cut into `panels` panels of K / panels rows (a multiple of 32); the transfer of
-// panel p+1 overlaps the GEMM on panel p, and each panel GEMM starts inside the kernel as soon as its panel's
-// `have` token is raised (see above).  On return (in stream order) every rank's block holds all of B.
-TB200_API int tiramisu_b200_sgemm_bcast_b(void *const *peers, uint64_t b_offset, uint64_t flags_offset, int32_t root, uint32_t epoch,
-                                          int32_t panels, const float *A, float *C, uint64_t rows, uint64_t N, uint64_t K,
-                                          float alpha, float beta, uint64_t ldA, uint64_t ldC)
+// A and C this rank's row shard, B an ordinary row-major device matrix on the ROOT only (ignored elsewhere).  The
+// symmetric block (`stage_offset`, K * N * 4 bytes) is the library's staging area: B travels through it in `panels`
+// column panels (N / panels a multiple of 256; the same value on every rank), stored panel-major.  The root computes from
+// B itself; every other rank runs ONE persistent GEMM launch over the staged layout, gated per tile on the panels'
+// arrival (ranks whose shard is too small for a persistent kernel run one launch per panel behind stream-side waits).
+// On return (in stream order) the root's B may be rewritten.  Collective over the ranks.
+TB200_API int tiramisu_b200_sgemm_bcast_b(void *const *peers, uint64_t stage_offset, uint64_t flags_offset, int32_t root, uint32_t epoch,
+                                          int32_t panels, const float *B, uint64_t ldB, const float *A, float *C, uint64_t rows,
+                                          uint64_t N, uint64_t K, float alpha, float beta, uint64_t ldA, uint64_t ldC)
 {
-    if (bcast_sym_check(__func__, peers, root, epoch, panels)) return 1;
-    if (!A || !C || K == 0 || N == 0 || K % panels || (K / panels) % 32) return fail(__func__, "bad argument (K / panels must be a multiple of 32)");
+    if (!A || !C || K == 0 || N == 0) return fail(__func__, "bad argument");
     if (ldA == 0) ldA = K;
+    if (ldB == 0) ldB = N;
     if (ldC == 0) ldC = N;
-    const int world = g_comm.world, rank = g_comm.rank;
+    const int world = g_comm.comm ? g_comm.world : 1, rank = g_comm.comm ? g_comm.rank : 0;
+    if (world == 1) return (!B || !rows) ? (rows ? fail(__func__, "B is null on the root") : 0)
+                                         : tb200::gemm_f32(A, B, C, rows, N, K, alpha, beta, ldA, ldB, ldC, false, false);
+    if (bcast_sym_check(__func__, peers, root, epoch, panels)) return 1;
+    if (N % panels || (panels > 1 && (N / panels) % 256)) return fail(__func__, "N / panels must be a multiple of 256");
+    if (rank == root && !B) return fail(__func__, "B is null on the root");
     cudaStream_t st = stream();
-    const uint64_t kw = K / panels, panel_bytes = kw * N * 4;
-    const float *B = reinterpret_cast<const float *>(static_cast<char *>(peers[rank]) + b_offset);
+    const uint64_t w = N / panels, panel_bytes = K * w * 4;
+    const float *stage = reinterpret_cast<const float *>(static_cast<char *>(peers[rank]) + stage_offset);
     const uint32_t *have = reinterpret_cast<const uint32_t *>(static_cast<char *>(peers[rank]) + flags_offset) + 2 * world;
-    if (world > 1 && bcast_sym_enqueue(st, peers, b_offset, K * N * 4, flags_offset, root, epoch, panels, panel_bytes)) return 1;
-    for (int p = 0; p < panels && rows; p++) {
-        const float *Ap = A + (uint64_t)p * kw, *Bp = B + (uint64_t)p * kw * N;
-        const float be = p == 0 ? beta : 1.0f;
-        const bool gated = world > 1 && rank != root;
-        const uint32_t token = 64u * (epoch - 1) + (uint32_t)p + 1;
-        if (gated) tb200::gemm_tc_gate(have, token);       // consumed by this GEMM: in the kernel, or as a stream-side wait
-        if (tb200::gemm_f32(Ap, Bp, C, rows, N, kw, alpha, be, ldA, N, ldC, false, false)) return 1;
+    const uint32_t base = 64u * (epoch - 1);
+    RootPack pack;
+    if (rank == root) { pack.B = B; pack.K = K; pack.ldB = ldB; pack.cols = w; }
+    if (bcast_sym_fork(st)) return 1;
+    if (rank == root) {
+        if (rows && tb200::gemm_f32(A, B, C, rows, N, K, alpha, beta, ldA, ldB, ldC, false, false)) return 1;
+        if (bcast_sym_enqueue(peers, stage_offset, K * N * 4, panel_bytes, flags_offset, root, epoch, panels, pack)) return 1;
+        return bcast_sym_join(st);
     }
-    if (world > 1) {
-        TB200_CHECK(cudaStreamWaitEvent(st, t_bs.end_s, 0));
-        TB200_CHECK(cudaStreamWaitEvent(st, t_bs.end_g, 0));
+    const int kernel = tb200::gemm_tc_kernel_choice(rows, N, K, nullptr);
+    const bool in_kernel = rows && (kernel == 2 || kernel == 3) && !getenv("TB200_GEMM_MODE") && !getenv("TB200_SGEMM_GATE_ON_STREAM") &&
+                           tb200::gemm_tc_addressable(A, stage, C, rows, N, K, ldA, w, ldC, false, false);
+    if (in_kernel) {
+        // one launch over the staged layout, submitted before the copies (see the note on work queues above)
+        tb200::gemm_tc_gate(have, base + 1, panels > 1 ? (int)w : 0, base + (uint32_t)panels);
+        tb200::gemm_tc_b_panels(panels > 1 ? (int)w : 0, K * w);
+        const int rc = tb200::gemm_f32_tc(A, stage, C, rows, N, K, alpha, beta, ldA, w, ldC, false);
+        tb200::gemm_tc_b_panels(0, 0);
+        if (rc) return 1;
+        if (bcast_sym_enqueue(peers, stage_offset, K * N * 4, panel_bytes, flags_offset, root, epoch, panels, pack)) return 1;
+        return bcast_sym_join(st);
     }
-    return 0;
+    if (bcast_sym_enqueue(peers, stage_offset, K * N * 4, panel_bytes, flags_offset, root, epoch, panels, pack)) return 1;
+    for (int p = 0; p < panels && rows; p++) {                      // every staged panel is a plain row-major [K][w] matrix
+        if (tb200::stream_wait_value32(st, have, base + (uint32_t)p + 1)) return 1;
+        if (tb200::gemm_f32(A, stage + (uint64_t)p * K * w, C + (uint64_t)p * w, rows, w, K, alpha, beta, ldA, w, ldC, false, false)) return 1;
+    }
+    return bcast_sym_join(st);
 }
 
 TB200_API int tiramisu_b200_comm_free_symmetric(void *local)

@@ -111,8 +111,20 @@ void gemm_tc_hint(int kernel, int bn) { t_hint_kernel = kernel; t_hint_bn = bn; 
 // warp (the launch, prologue and A loads overlap the tail of the transfer); the other kernels get a stream-side
 // cuStreamWaitValue32 in front of the launch.
 static thread_local const uint32_t *t_gate = nullptr;
-static thread_local uint32_t t_gate_value = 0;
-void gemm_tc_gate(const uint32_t *flag, uint32_t value) { t_gate = flag; t_gate_value = value; }
+static thread_local uint32_t t_gate_value = 0, t_gate_last = 0;
+static thread_local int t_gate_cols = 0;
+// cols == 0: the whole operand has arrived once *flag >= value.  cols > 0: columns [j cols, (j+1) cols) of B have arrived
+// once *flag >= value + j; `last` = the token of the final panel (what a kernel without an in-kernel gate waits for).
+void gemm_tc_gate(const uint32_t *flag, uint32_t value, int cols, uint32_t last)
+{
+    t_gate = flag; t_gate_value = value; t_gate_cols = cols; t_gate_last = cols ? last : value;
+}
+// Layout of the (MN-major) B operand of the NEXT gemm_f32_tc call of this thread: panel-major, column panels of `cols`
+// columns, consecutive panels `panel_stride` elements apart, ldB == cols.  Persistent kernels only (the caller asks
+// gemm_tc_kernel_choice first).
+static thread_local int t_b_panel_cols = 0;
+static thread_local uint64_t t_b_panel_stride = 0;
+void gemm_tc_b_panels(int cols, uint64_t panel_stride) { t_b_panel_cols = cols; t_b_panel_stride = panel_stride; }
 int stream_wait_value32(cudaStream_t st, const uint32_t *flag, uint32_t value);       // comm.cu
 
 }  // namespace tb200
@@ -142,9 +154,12 @@ struct GemmParams {
     const float *alpha_dev;             // optional device-resident factor multiplied into alpha (LSTM: the
                                         // power-of-two de-scaling of block-scaled fp16 weights), else null
     int prefetch_kb;                    // L2 prefetch distance in k-slabs beyond the shared-memory ring (0 = off)
-    const uint32_t *gate = nullptr;     // optional arrival flag of the B operand (row-sharded sgemm: the K panel of B is being
-    uint32_t gate_value = 0;            // copied in by DMA engines while this kernel starts): the TMA producer polls
-                                        // *gate >= gate_value before its first B load (persistent kernels only)
+    const uint32_t *gate = nullptr;     // optional arrival word of the B operand (row-sharded sgemm: B is being copied in by
+    uint32_t gate_value = 0;            // DMA engines while this kernel runs).  The TMA producer of a persistent kernel polls
+    int gate_cols = 0;                  // *gate >= gate_value + n0 / gate_cols before the B loads of a tile whose first column
+                                        // is n0 (column panels arrive in order); gate_cols == 0: one wait before the first load
+    int b_panel_cols = 0;               // > 0: MN-major B is stored panel-major, [N / cols][K][cols] (each column panel a
+                                        // contiguous row-major matrix — what the DMA broadcast delivers); map_b is then 3-D
 };
 
 // F16: operands are fp16 (kind::f16, K = 16 per instruction, 64 elements per 128-byte swizzle row):
@@ -616,13 +631,21 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
     const int num_kb = (p.K + BK - 1) / BK;
     constexpr int TILE_M = BM * CG;
 
+    // Tile order: groups of group_m tile rows sweep the columns (A rows of a group and the B columns under the sweep stay
+    // in L2).  A gated launch (B arriving column panel by column panel) walks panel by panel — all the tiles of panel j
+    // before any tile of panel j+1 — with the same grouped order inside each panel, so that every CTA has work as soon as
+    // a panel is in and nothing sweeps ahead into columns that are still on the wire.
+    const int sweep_n = p.gate_cols ? p.gate_cols / P_BN : p.num_n;         // tile columns per sweep
     auto tile_origin = [&](int t, int &m0, int &n0) {
-        const int tiles_per_group = p.group_m * p.num_n;
+        const int per_sweep = p.num_m * sweep_n;
+        const int sweep = t / per_sweep;
+        t -= sweep * per_sweep;
+        const int tiles_per_group = p.group_m * sweep_n;
         const int group = t / tiles_per_group;
         const int first_m = group * p.group_m;
         const int gsz = min(p.num_m - first_m, p.group_m);
         m0 = (first_m + (t % tiles_per_group) % gsz) * TILE_M;
-        n0 = ((t % tiles_per_group) / gsz) * P_BN;
+        n0 = (sweep * sweep_n + (t % tiles_per_group) / gsz) * P_BN;
     };
 
     if (warp == 0 && lane == 0) {
@@ -653,28 +676,32 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
     if (warp == 0) {
         // ===== TMA producer (every CTA loads its own A rows and its own share of B); whole warp,
         // uniform control flow, one elected lane issues =====
-        if (p.gate) {
-            // B is still arriving (peer copies by DMA engines, comm.cu: sgemm_bcast_b): everything above — barrier init,
-            // TMEM allocation, descriptor prefetch — already ran; wait here for the panel's arrival flag, then order the
-            // generic-proxy acquire before the async-proxy (TMA) reads of the freshly written bytes
-            if (lane == 0) {
-                const long long t0 = clock64();
-                uint32_t v;
-                do {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.gate) : "memory");
-                    if (v >= p.gate_value) break;
-                    __nanosleep(200);
-                    if (clock64() - t0 > 12000000000LL) __trap();      // seconds: a protocol bug must not hang the box
-                } while (true);
-            }
-            __syncwarp();
-            ptx::fence_proxy_async_all();
-        }
         {
             uint32_t it = 0;
+            uint32_t arrived = 0;                                   // highest arrival token seen so far (gated launches)
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 int m0, n0;
                 tile_origin(tile, m0, n0);
+                if (p.gate) {
+                    // B is still arriving (peer copies by DMA engines, comm.cu: sgemm_bcast_b): barrier init, TMEM allocation
+                    // and descriptor prefetch already ran; wait for the arrival token of this tile's column panel, then order
+                    // the generic-proxy acquire before the async-proxy (TMA) reads of the freshly written bytes
+                    const uint32_t need = p.gate_value + (p.gate_cols ? (uint32_t)(n0 / p.gate_cols) : 0u);
+                    if (arrived < need) {
+                        uint32_t v = 0;
+                        if (lane == 0) {
+                            const long long t0 = clock64();
+                            do {
+                                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.gate) : "memory");
+                                if (v >= need) break;
+                                __nanosleep(200);
+                                if (clock64() - t0 > 12000000000LL) __trap();      // seconds: a protocol bug must not hang the box
+                            } while (true);
+                        }
+                        arrived = __shfl_sync(0xffffffffu, v, 0);
+                        ptx::fence_proxy_async_all();
+                    }
+                }
                 m0 += (int)cta_rank * BM;
                 n0 += (int)cta_rank * C_::B_COLS;
                 for (int kb = 0; kb < num_kb; kb++, it++) {
@@ -683,7 +710,7 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     if (ptx::elect_one()) {
                     // L2 prefetch of the slab `prefetch_kb` iterations ahead of the ring (same tile only)
-                    if (p.prefetch_kb && kb + STAGES + p.prefetch_kb - 1 < num_kb) {
+                    if (p.prefetch_kb && !p.b_panel_cols && kb + STAGES + p.prefetch_kb - 1 < num_kb) {
                         const int kp = (kb + STAGES + p.prefetch_kb - 1) * BK;
                         ptx::tma_prefetch_2d(&map_a, kp, m0);
                         if (B_MN) {
@@ -700,7 +727,12 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                     uint8_t *bdst = smem_b + s * C_::B_TILE_BYTES;
                     if (CG == 2) {
                         ptx::tma_load_2d_cg2(adst, &map_a, &full_bar[s], k0, m0);
-                        if (B_MN) {
+                        if (B_MN && p.b_panel_cols) {
+                            const int pj = n0 / p.b_panel_cols, pn = n0 - pj * p.b_panel_cols;
+#pragma unroll
+                            for (int j = 0; j < C_::B_COLS / 32; j++)
+                                ptx::tma_load_3d_cg2(bdst + j * (BK * 128), &map_b, &full_bar[s], pn + 32 * j, k0, pj);
+                        } else if (B_MN) {
 #pragma unroll
                             for (int j = 0; j < C_::B_COLS / 32; j++)
                                 ptx::tma_load_2d_cg2(bdst + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
@@ -709,7 +741,12 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                         }
                     } else {
                         ptx::tma_load_2d(adst, &map_a, &full_bar[s], k0, m0);
-                        if (B_MN) {
+                        if (B_MN && p.b_panel_cols) {
+                            const int pj = n0 / p.b_panel_cols, pn = n0 - pj * p.b_panel_cols;
+#pragma unroll
+                            for (int j = 0; j < C_::B_COLS / 32; j++)
+                                ptx::tma_load_3d(bdst + j * (BK * 128), &map_b, &full_bar[s], pn + 32 * j, k0, pj);
+                        } else if (B_MN) {
 #pragma unroll
                             for (int j = 0; j < C_::B_COLS / 32; j++)
                                 ptx::tma_load_2d(bdst + j * (BK * 128), &map_b, &full_bar[s], n0 + 32 * j, k0);
@@ -1007,7 +1044,14 @@ int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N,
         uint32_t box[2] = {BK, BM};
         if (make_tensor_map_f32(&map_a, A, 2, dims, str, box)) return 1;
     }
-    if (B_MN) {
+    const int panel_cols = B_MN ? tb200::t_b_panel_cols : 0;
+    if (B_MN && panel_cols) {
+        if (panel_cols % P_BN || N % panel_cols || ldB != panel_cols) return fail("gemm_f32_tc", "panel-major B: bad panel width");
+        uint64_t dims[3] = {(uint64_t)panel_cols, (uint64_t)K, (uint64_t)(N / panel_cols)};
+        uint64_t str[2] = {(uint64_t)panel_cols * 4, tb200::t_b_panel_stride * 4};
+        uint32_t box[3] = {32, BK, 1};
+        if (make_tensor_map_f32(&map_b, B, 3, dims, str, box, kTmaSwizzle128Atom32)) return 1;
+    } else if (B_MN) {
         uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
         uint64_t str[1] = {(uint64_t)ldB * 4};
         uint32_t box[2] = {32, BK};
@@ -1023,11 +1067,12 @@ int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N,
     p.num_m = (M + BM * CG - 1) / (BM * CG);
     p.num_n = (N + P_BN - 1) / P_BN;
     p.group_m = 16 / CG;
+    p.b_panel_cols = panel_cols;
     p.b_lbo = BK * 128;
     p.b_sbo = 512;
     p.alpha_dev = nullptr;
     p.prefetch_kb = gemm_prefetch_kb(0);
-    p.gate = tb200::t_gate; p.gate_value = tb200::t_gate_value;
+    p.gate = tb200::t_gate; p.gate_value = tb200::t_gate_value; p.gate_cols = tb200::t_gate_cols;
     tb200::t_gate = nullptr;
     auto kern = tiramisu_sm100_gemm_tf32_persistent<CG, B_MN>;
     static bool attr_set = false;
@@ -1078,6 +1123,26 @@ bool gemm_tc_addressable(const float *A, const float *B, const float *C, uint64_
     return true;
 }
 
+// Kernel choice: the persistent CTA-pair kernel once there is at least ~one 256x256 tile per SM
+// pair, the persistent single-CTA kernel for mid sizes, the one-tile-per-CTA kernel below that.
+// 1 one tile per CTA (or 4, split-K, decided later), 2 persistent, 3 persistent CTA pairs.
+int gemm_tc_kernel_choice(uint64_t M, uint64_t N, uint64_t K, bool *was_auto)
+{
+    int kernel = g_gemm_kernel.load();
+    if (const char *e = getenv("TB200_GEMM_KERNEL")) kernel = atoi(e);
+    if (t_hint_kernel) kernel = t_hint_kernel;
+    if (was_auto) *was_auto = kernel == 0;
+    if (kernel == 0) {
+        // measured (profiles/r01_results.md): the pair kernel wins from ~2048^2 outputs upwards even
+        // when it cannot fill every SM pair (2048^3: 416 vs 339 TFLOP/s); below that the one-tile-per-CTA
+        // kernel with narrow tiles (more CTAs, shorter critical path) is faster (1024^3: 147 vs 73).
+        const uint64_t sms = (uint64_t)sm_count();
+        const uint64_t pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+        kernel = (pair_tiles * 2 * 5 >= sms * 4 && K >= 256) ? 3 : 1;
+    }
+    return kernel;
+}
+
 int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha,
                 float beta, uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tB)
 {
@@ -1097,24 +1162,13 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
         return 0;
     }
     const int m = (int)M, n = (int)N, k = (int)K;
-    // Kernel choice: the persistent CTA-pair kernel once there is at least ~one 256x256 tile per SM
-    // pair, the persistent single-CTA kernel for mid sizes, the one-tile-per-CTA kernel below that.
-    int kernel = g_gemm_kernel.load();
-    if (const char *e = getenv("TB200_GEMM_KERNEL")) kernel = atoi(e);
-    if (t_hint_kernel) kernel = t_hint_kernel;
     const uint64_t sms = (uint64_t)sm_count();
-    const bool auto_kernel = kernel == 0;
-    if (kernel == 0) {
-        // measured (profiles/r01_results.md): the pair kernel wins from ~2048^2 outputs upwards even
-        // when it cannot fill every SM pair (2048^3: 416 vs 339 TFLOP/s); below that the one-tile-per-CTA
-        // kernel with narrow tiles (more CTAs, shorter critical path) is faster (1024^3: 147 vs 73).
-        const uint64_t pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
-        kernel = (pair_tiles * 2 * 5 >= sms * 4 && K >= 256) ? 3 : 1;
-    }
-    if (t_gate && kernel != 3 && kernel != 2) {              // no in-kernel gate in the one-tile kernels: wait on the stream
+    bool auto_kernel = false;
+    int kernel = gemm_tc_kernel_choice(M, N, K, &auto_kernel);
+    if (t_gate && ((kernel != 3 && kernel != 2) || getenv("TB200_SGEMM_GATE_ON_STREAM"))) {   // no in-kernel gate in the one-tile kernels (or diagnosis): wait on the stream
         const uint32_t *g = t_gate;
         t_gate = nullptr;
-        if (stream_wait_value32(stream(), g, t_gate_value)) return 1;
+        if (stream_wait_value32(stream(), g, t_gate_last)) return 1;
     }
     if (kernel == 3)
         return tB ? launch_tc_persistent<2, false>(A, B, C, m, n, k, alpha, beta, ldA, ldB, ldC)
@@ -1180,7 +1234,7 @@ int gemm_f32(const float *A, const float *B, float *C, uint64_t M, uint64_t N, u
     if (t_gate) {                                            // arrival gate of the B operand: stream-side on this path
         const uint32_t *g = t_gate;
         t_gate = nullptr;
-        if (stream_wait_value32(stream(), g, t_gate_value)) return 1;
+        if (stream_wait_value32(stream(), g, t_gate_last)) return 1;
     }
     return gemm_f32_exact(A, B, C, M, N, K, alpha, beta, ldA, ldB, ldC, tA, tB);
 }

@@ -188,6 +188,14 @@ __device__ __forceinline__ void tma_load_2d_cg2(void *smem_dst, const CUtensorMa
         "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_cg2(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0),
+        "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_cg2(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
                                                 int c2, int c3)
 {

@@ -165,9 +165,11 @@ class SymmetricRows:
 
 # ---- B of the row-sharded sgemm: broadcast by the DMA engines, consumed by the GEMM as it arrives -------
 class SymmetricB:
-    """K x N fp32 matrix in symmetric memory + the 256 flag bytes tiramisu_b200_sgemm_bcast_b needs.
-    Collective constructor / free.  `sgemm(A, C, rows, alpha, beta)` is the fused call: the root's B travels
-    in K panels (scatter + all-gather by peer copies, comm.cu) while every rank's panel GEMMs run."""
+    """Staging area (K * N fp32 in symmetric memory + 256 flag bytes) for tiramisu_b200_sgemm_bcast_b.
+    Collective constructor / free.  `sgemm(B_ptr, A_ptr, C_ptr, rows, alpha, beta)` is the fused call: the root's
+    row-major B is re-laid out panel-major into the staging area and travels in column panels (scatter + all-gather
+    by peer copies, comm.cu) while every rank's GEMM consumes the panels as they arrive.  `broadcast()` moves the
+    staging area's bytes as they are (plain buffer semantics; `tensor()` views them as a K x N matrix)."""
 
     FLAG_BYTES = 256
 
@@ -187,7 +189,7 @@ class SymmetricB:
         return self.local
 
     def tensor(self):
-        """My copy of B as a torch view (no copy) — plumbing for tests and the bench."""
+        """The staging area as a K x N torch view (no copy) — plumbing for tests and the bench."""
         import torch
 
         class _Raw:
@@ -197,23 +199,28 @@ class SymmetricB:
         return torch.as_tensor(raw, device="cuda")
 
     @staticmethod
-    def default_panels(K: int) -> int:
-        p = max(1, min(16, K // 2048))
-        while p > 1 and (K % p or (K // p) % 32):
+    def default_panels(n: int, unit: int = 256, least: int = 1024) -> int:
+        """Panels of >= `least` columns, multiples of `unit`, at most 16."""
+        p = max(1, min(16, n // least))
+        while p > 1 and (n % p or (n // p) % unit):
             p -= 1
         return p
 
     def broadcast(self, root: int = 0, panels: int | None = None) -> None:
         self.epoch += 1
         _lib.check(_lib.lib().tiramisu_b200_comm_broadcast_sym(self._peers, 0, self.K * self.N * 4, self.data_bytes, root, self.epoch,
-                                                               panels or self.default_panels(self.K)), "comm_broadcast_sym")
+                                                               panels or self.default_panels(self.K, 32, 2048)), "comm_broadcast_sym")
 
-    def sgemm(self, A_ptr: int, C_ptr: int, rows: int, alpha: float, beta: float, root: int = 0, panels: int | None = None,
-              ldA: int = 0, ldC: int = 0) -> None:
+    def sgemm(self, B_ptr: int | None, A_ptr: int, C_ptr: int, rows: int, alpha: float, beta: float, root: int = 0,
+              panels: int | None = None, ldA: int = 0, ldB: int = 0, ldC: int = 0) -> None:
+        """B_ptr: the root's row-major K x N matrix (device address; ignored on the other ranks)."""
+        if panels is None:
+            panels = self.default_panels(self.N)
         self.epoch += 1
-        _lib.check(_lib.lib().tiramisu_b200_sgemm_bcast_b(self._peers, 0, self.data_bytes, root, self.epoch,
-                                                          panels or self.default_panels(self.K), C.c_void_p(A_ptr), C.c_void_p(C_ptr),
-                                                          rows, self.N, self.K, alpha, beta, ldA, ldC), "sgemm_bcast_b")
+        _lib.check(_lib.lib().tiramisu_b200_sgemm_bcast_b(self._peers, 0, self.data_bytes, root, self.epoch, panels,
+                                                          C.c_void_p(B_ptr if self.rank == root else None), ldB,
+                                                          C.c_void_p(A_ptr), C.c_void_p(C_ptr), rows, self.N, self.K, alpha, beta, ldA, ldC),
+                   "sgemm_bcast_b")
 
     def free(self) -> None:
         if self.local:
