@@ -216,7 +216,8 @@ int tiramisu_b200_comm_broadcast_sym(void *const *peers, uint64_t data_offset, u
                                      int32_t root, uint32_t epoch, int32_t panels);
 /* Row-sharded sgemm with B's arrival fused in: C[rows][N] = alpha A[rows][K] B[K][N] + beta C on
  * every rank; A, C: this rank's row shard; B: an ordinary row-major device matrix (pitch ldB) on `root` only.  The
- * symmetric block at stage_offset (K * N * 4 bytes) is the staging area B travels through, in `panels` column panels
+ * symmetric block at stage_offset (2 halves of K * N * 4 bytes, each rounded up to 256, used alternately) is the staging
+ * area B travels through, in `panels` column panels
  * (N / panels a multiple of 256, same value on every rank) stored panel-major: the root re-lays B out with local DMA
  * copies, the panels travel as above, and every other rank runs ONE persistent tcgen05 GEMM launch over the staged
  * layout (3-D tensor map) whose TMA producer warp polls a panel's arrival word before the B loads of a tile in a
@@ -224,6 +225,8 @@ int tiramisu_b200_comm_broadcast_sym(void *const *peers, uint64_t data_offset, u
 int tiramisu_b200_sgemm_bcast_b(void *const *peers, uint64_t stage_offset, uint64_t flags_offset, int32_t root, uint32_t epoch,
                                 int32_t panels, const float *B, uint64_t ldB, const float *A, float *C, uint64_t rows,
                                 uint64_t N, uint64_t K, float alpha, float beta, uint64_t ldA, uint64_t ldC);
+/* Diagnosis: with TB200_BCAST_TRACE=1 in the environment, prints the timeline of this thread's last broadcast. */
+int tiramisu_b200_comm_broadcast_trace_dump(void);
 int tiramisu_MPI_init(void);                 /* src/tiramisu_mpi.cpp:8  reads torchrun's env; returns rank */
 void tiramisu_MPI_cleanup(void);             /* :19 */
 void tiramisu_MPI_global_barrier(void);      /* :23 */

@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
     sig("tiramisu_b200_comm_alloc_symmetric", C.c_int, u64, C.POINTER(vp), C.POINTER(vp))
     sig("tiramisu_b200_comm_free_symmetric", C.c_int, vp)
     sig("tiramisu_b200_comm_broadcast_sym", C.c_int, C.POINTER(vp), u64, u64, u64, i32, C.c_uint32, i32)
+    sig("tiramisu_b200_comm_broadcast_trace_dump", C.c_int)
     sig("tiramisu_b200_sgemm_bcast_b", C.c_int, C.POINTER(vp), u64, u64, i32, C.c_uint32, i32, vp, u64, vp, vp, u64, u64, u64,
         C.c_float, C.c_float, u64, u64)
     sig("tiramisu_b200_heat2d_peer", C.c_int, vp, vp, i32, i32, i32, i32, i32, C.POINTER(Halo))

@@ -493,16 +493,14 @@ int gemm_f32_tc(const float *A, const float *B, float *C, uint64_t M, uint64_t N
 int gemm_f32(const float *A, const float *B, float *C, uint64_t M, uint64_t N, uint64_t K, float alpha, float beta,
              uint64_t ldA, uint64_t ldB, uint64_t ldC, bool tA, bool tB);
 
-namespace {
 using StreamMemOpFn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-StreamMemOpFn driver_fn(const char *name)
+static StreamMemOpFn driver_fn(const char *name)
 {
     void *p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
     return reinterpret_cast<StreamMemOpFn>(p);
 }
-}  // namespace
 
 int stream_wait_value32(cudaStream_t st, const uint32_t *flag, uint32_t value)
 {
@@ -522,10 +520,36 @@ int stream_write_value32(cudaStream_t st, uint32_t *flag, uint32_t value)
 }  // namespace tb200
 
 namespace {
+// ---- the two tiny kernels of the broadcast: flag fan-out and the root's panel-major re-layout ----------------------
+// A 4-byte peer copy costs as much DMA set-up time as a multi-megabyte one (r02 run 13: ~11 us per copy between IPC-mapped
+// blocks), so one rank's announcement to all its peers is ONE one-warp kernel storing the token into every peer's flag
+// word (st.release.sys after the stream-ordered data copies), not world-1 copies.
+struct FlagTargets { uint32_t *p[32]; };
+__global__ void tiramisu_sm100_sym_flag_fanout(FlagTargets t, int n, uint32_t value)
+{
+    const int q = threadIdx.x;
+    if (q < n && t.p[q]) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.p[q]), "r"(value) : "memory");
+}
+// dst[k][c] = src[k][col0 + c], c < cols: column panel `col0 / cols` of the row-major B becomes a contiguous [K][cols]
+// matrix in the staging block.  HBM-bound (2 x 4 bytes per element), float4 lanes, few registers so that it co-resides
+// with the root's own persistent GEMM.
+__global__ void __launch_bounds__(256) tiramisu_sm100_pack_panel(const float *__restrict__ src, float *__restrict__ dst, uint64_t K,
+                                                                  uint64_t ldB, uint64_t col0, uint32_t cols)
+{
+    const uint32_t vec_per_row = cols / 4;
+    const uint64_t total = K * vec_per_row;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = i / vec_per_row;
+        const uint32_t c = (uint32_t)(i - k * vec_per_row) * 4;
+        const float4 v = *reinterpret_cast<const float4 *>(src + k * ldB + col0 + c);
+        *reinterpret_cast<float4 *>(dst + k * cols + c) = v;
+    }
+}
+
 constexpr int kMaxPanels = 64;
 struct BcastStreams {
-    cudaStream_t scatter = nullptr, gather = nullptr;
-    cudaEvent_t fork = nullptr, end_s = nullptr, end_g = nullptr, slice[kMaxPanels] = {};
+    cudaStream_t scatter = nullptr, gather = nullptr, pack = nullptr;
+    cudaEvent_t fork = nullptr, end_s = nullptr, end_g = nullptr, slice[kMaxPanels] = {}, packed[kMaxPanels] = {};
     int init()
     {
         if (scatter) return 0;
@@ -533,12 +557,52 @@ struct BcastStreams {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);          // operations are never queued behind compute of equal priority
         TB200_CHECK(cudaStreamCreateWithPriority(&scatter, cudaStreamNonBlocking, hi));
         TB200_CHECK(cudaStreamCreateWithPriority(&gather, cudaStreamNonBlocking, hi));
+        TB200_CHECK(cudaStreamCreateWithPriority(&pack, cudaStreamNonBlocking, hi));
         for (cudaEvent_t *e : {&fork, &end_s, &end_g}) TB200_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        for (int i = 0; i < kMaxPanels; i++) TB200_CHECK(cudaEventCreateWithFlags(&slice[i], cudaEventDisableTiming));
+        for (int i = 0; i < kMaxPanels; i++) {
+            TB200_CHECK(cudaEventCreateWithFlags(&slice[i], cudaEventDisableTiming));
+            TB200_CHECK(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
+        }
+        // Load the two helper kernels NOW: with lazy module loading the first launch of a kernel loads its module, and
+        // that load waits for running kernels — a gated GEMM that spins until these very kernels have announced a panel
+        // would never see it (r02 run 15: the GEMM's bounded waits trapped after 2 s on the first fused call).
+        cudaFuncAttributes fa;
+        TB200_CHECK(cudaFuncGetAttributes(&fa, tiramisu_sm100_sym_flag_fanout));
+        TB200_CHECK(cudaFuncGetAttributes(&fa, tiramisu_sm100_pack_panel));
+        FlagTargets none{};
+        tiramisu_sm100_sym_flag_fanout<<<1, 32, 0, scatter>>>(none, 0, 0u);
+        tiramisu_sm100_pack_panel<<<1, 256, 0, scatter>>>(nullptr, nullptr, 0, 0, 0, 4);
+        TB200_CHECK(cudaStreamSynchronize(scatter));
         return 0;
     }
 };
 thread_local BcastStreams t_bs;
+
+// TB200_BCAST_TRACE=1: timing events after every operation of one broadcast, printed (relative to the fork) by
+// tiramisu_b200_comm_broadcast_trace_dump() — diagnosis of where a panel spends its time (r02 run 14)
+struct BcastTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void begin(cudaStream_t st)
+    {
+        on = getenv("TB200_BCAST_TRACE") != nullptr;
+        if (!on) return;
+        for (auto &m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+        if (!t0) cudaEventCreate(&t0);
+        cudaEventRecord(t0, st);
+    }
+    void mark(const std::string &what, cudaStream_t st)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.push_back({what, e});
+    }
+};
+thread_local BcastTrace t_trace;
 
 // Row-major source the root re-lays out panel-major into its staging block before a panel travels (sgemm), or nothing
 // (plain broadcast: the root's block already holds the bytes).
@@ -553,95 +617,124 @@ int bcast_sym_fork(cudaStream_t st)
 {
     if (t_bs.init()) return 1;
     TB200_CHECK(cudaEventRecord(t_bs.fork, st));
+    t_trace.begin(st);
     return 0;
 }
 
 // Enqueues the whole panelised broadcast of [data_offset, data_offset + bytes) on the library's two copy streams (after
 // bcast_sym_fork); leaves end_s / end_g recorded (the caller joins them when it wants "complete / reusable" in stream order).
 int bcast_sym_enqueue(void *const *peers, uint64_t data_offset, uint64_t bytes, uint64_t panel_bytes, uint64_t flags_offset,
-                      int root, uint32_t epoch, int panels, const RootPack &pack)
+                      int root, uint32_t epoch, int panels, const RootPack &pack, bool double_buffered = false)
 {
     const int world = g_comm.world, rank = g_comm.rank;
     auto data = [&](int r) { return static_cast<char *>(peers[r]) + data_offset; };
     auto flags = [&](int r) { return reinterpret_cast<uint32_t *>(static_cast<char *>(peers[r]) + flags_offset); };
     uint32_t *mine = flags(rank);
-    uint32_t *src_ready = mine + 2 * world + 1, *src_done = mine + 2 * world + 2;
     const uint32_t base = 64u * (epoch - 1);
     TB200_CHECK(cudaStreamWaitEvent(t_bs.gather, t_bs.fork, 0));
+    const int ns = world - 1;                                               // slices per panel: one per non-root rank
+    auto slice_of = [&](int r) { return r < root ? r : r - 1; };
+    auto slice_range = [&](int p, int s, uint64_t *lo, uint64_t *len) {    // byte range of slice s of panel p inside the data
+        const uint64_t p_lo = std::min<uint64_t>(bytes, (uint64_t)p * panel_bytes);
+        const uint64_t p_len = std::min<uint64_t>(bytes, p_lo + panel_bytes) - p_lo;
+        const uint64_t sl = ((p_len + ns - 1) / ns + 255) & ~uint64_t(255);
+        const uint64_t a = std::min<uint64_t>(p_len, (uint64_t)s * sl), b = std::min<uint64_t>(p_len, (uint64_t)(s + 1) * sl);
+        *lo = p_lo + a; *len = b - a;
+    };
+    auto fanout = [&](cudaStream_t cs, int word, uint32_t value, bool to_root) -> int {   // flags(q)[word] = value at every peer q
+        FlagTargets t;
+        int n = 0;
+        for (int q = 0; q < world; q++)
+            if (q != rank && (to_root || q != root)) t.p[n++] = flags(q) + word;
+        if (!n) return 0;
+        tiramisu_sm100_sym_flag_fanout<<<1, 32, 0, cs>>>(t, n, value);
+        return post_launch("tiramisu_sm100_sym_flag_fanout");
+    };
     if (rank == root) {
-        // Nothing to fetch.  Stage panel after panel (sgemm) and tell everybody which panels are in place — ordered after
-        // whatever filled the source on the caller's stream; the source may be rewritten once every peer has read it.
-        for (int p = 0; p < panels; p++) {
-            if (pack.B) {
-                TB200_CHECK(cudaMemcpy2DAsync(data(root) + (uint64_t)p * panel_bytes, pack.cols * 4, pack.B + (uint64_t)p * pack.cols,
-                                              pack.ldB * 4, pack.cols * 4, pack.K, cudaMemcpyDeviceToDevice, t_bs.gather));
-            } else if (p + 1 < panels) {
-                continue;                                             // in place already: one announcement for all panels
-            }
-            if (stream_write_value32(t_bs.gather, src_ready, base + (uint32_t)p + 1)) return 1;
+        // The root PUSHES: its DMA engines write every rank's slice of a panel into that rank's block at full link speed
+        // (r02 run 14: seven ranks pulling from one root share its egress, each pull crawls at 1/7 of the link and keeps the
+        // puller's engine busy for the whole scatter).  Panel after panel: stage it (sgemm: panel-major re-layout), push the
+        // slices, announce the panel — ordered after whatever filled the source on the caller's stream.  The source may be
+        // rewritten once the pushes are done and every peer has finished reading the staged copy.
+        TB200_CHECK(cudaStreamWaitEvent(t_bs.scatter, t_bs.fork, 0));
+        if (pack.B) TB200_CHECK(cudaStreamWaitEvent(t_bs.pack, t_bs.fork, 0));
+        // Double-buffered staging (sgemm): this epoch's half was last read in epoch - 2; the peers' `done` words of that
+        // epoch are all this call has to wait for, so the root runs up to two epochs ahead of the slowest consumer.
+        if (double_buffered && epoch > 2)
             for (int q = 0; q < world; q++)
-                if (q != root) TB200_CHECK(cudaMemcpyAsync(flags(q) + root, src_ready, 4, cudaMemcpyDeviceToDevice, t_bs.gather));
+                if (q != root && stream_wait_value32(pack.B ? t_bs.pack : t_bs.gather, mine + world + q, epoch - 2)) return 1;
+        for (int p = 0; p < panels; p++) {
+            if (pack.B) {                                             // re-layout on its own stream, one panel ahead of the pushes
+                const uint64_t total_vec = pack.K * pack.cols / 4;
+                const unsigned grid = (unsigned)std::min<uint64_t>((total_vec + 255) / 256, (uint64_t)sm_count() * 4);
+                tiramisu_sm100_pack_panel<<<grid, 256, 0, t_bs.pack>>>(pack.B, reinterpret_cast<float *>(data(root) + (uint64_t)p * panel_bytes),
+                                                                        pack.K, pack.ldB, (uint64_t)p * pack.cols, (uint32_t)pack.cols);
+                if (post_launch("tiramisu_sm100_pack_panel")) return 1;
+                TB200_CHECK(cudaEventRecord(t_bs.packed[p], t_bs.pack));
+                TB200_CHECK(cudaStreamWaitEvent(t_bs.gather, t_bs.packed[p], 0));
+                TB200_CHECK(cudaStreamWaitEvent(t_bs.scatter, t_bs.packed[p], 0));
+                t_trace.mark("root staged panel " + std::to_string(p), t_bs.pack);
+            }
+            // the slices leave on two streams (the fixed set-up time of one copy overlaps the transfer of the other)
+            for (int k = 1; k < world; k++) {
+                const int q = (root + k) % world;
+                uint64_t lo, len;
+                slice_range(p, slice_of(q), &lo, &len);
+                if (len) TB200_CHECK(cudaMemcpyAsync(data(q) + lo, data(root) + lo, len, cudaMemcpyDeviceToDevice, (k & 1) ? t_bs.gather : t_bs.scatter));
+            }
+            TB200_CHECK(cudaEventRecord(t_bs.slice[p], t_bs.scatter));
+            TB200_CHECK(cudaStreamWaitEvent(t_bs.gather, t_bs.slice[p], 0));
+            if (fanout(t_bs.gather, root, base + (uint32_t)p + 1, false)) return 1;
+            t_trace.mark("root pushed and announced panel " + std::to_string(p), t_bs.gather);
         }
         if (stream_write_value32(t_bs.gather, mine + 2 * world, base + (uint32_t)panels)) return 1;
-        for (int q = 0; q < world; q++)
+        for (int q = 0; q < world && !double_buffered; q++)          // in-place data: nobody may still read it when the call returns
             if (q != root && stream_wait_value32(t_bs.gather, mine + world + q, epoch)) return 1;
+        t_trace.mark("root saw every peer done", t_bs.gather);
         TB200_CHECK(cudaEventRecord(t_bs.end_g, t_bs.gather));
         TB200_CHECK(cudaEventRecord(t_bs.end_s, t_bs.gather));
         return 0;
     }
     TB200_CHECK(cudaStreamWaitEvent(t_bs.scatter, t_bs.fork, 0));
-    const int ns = world - 1;                                               // slices per panel: one per non-root rank
-    auto slice_of = [&](int r) { return r < root ? r : r - 1; };
-    auto pull = [&](int p, int s, int from, cudaStream_t cs) -> int {      // slice s of panel p from rank `from` into my block
-        const uint64_t p_lo = std::min<uint64_t>(bytes, (uint64_t)p * panel_bytes);
-        const uint64_t p_len = std::min<uint64_t>(bytes, p_lo + panel_bytes) - p_lo;
-        const uint64_t sl = ((p_len + ns - 1) / ns + 255) & ~uint64_t(255);
-        const uint64_t lo = std::min<uint64_t>(p_len, (uint64_t)s * sl), hi = std::min<uint64_t>(p_len, (uint64_t)(s + 1) * sl);
-        if (hi > lo) TB200_CHECK(cudaMemcpyAsync(data(rank) + p_lo + lo, data(from) + p_lo + lo, hi - lo, cudaMemcpyDeviceToDevice, cs));
-        return 0;
-    };
-    // nobody still reads what this call overwrites: every non-root peer finished the previous epoch's pulls from me
-    for (int q = 0; q < world; q++)
-        if (q != rank && q != root && stream_wait_value32(t_bs.scatter, mine + world + q, epoch - 1)) return 1;
     for (int p = 0; p < panels; p++) {
         const uint32_t token = base + (uint32_t)p + 1;
-        // scatter: my slice from the root once the root has staged the panel, then tell every other non-root rank that it
-        // can be pulled from me
+        // scatter: the root has pushed my slice of the panel; tell every other non-root rank that it can be pulled from me
         if (stream_wait_value32(t_bs.scatter, mine + root, token)) return 1;
-        if (pull(p, slice_of(rank), root, t_bs.scatter)) return 1;
-        if (ns > 1) {
-            if (stream_write_value32(t_bs.scatter, src_ready, token)) return 1;
-            for (int k = 1; k < world; k++) {
-                const int q = (rank + k) % world;
-                if (q != root) TB200_CHECK(cudaMemcpyAsync(flags(q) + rank, src_ready, 4, cudaMemcpyDeviceToDevice, t_bs.scatter));
-            }
-        }
+        t_trace.mark("p" + std::to_string(p) + " own slice arrived from root", t_bs.scatter);
+        if (ns > 1 && fanout(t_bs.scatter, rank, token, false)) return 1;
         TB200_CHECK(cudaEventRecord(t_bs.slice[p], t_bs.scatter));
         // all-gather: slice q of this panel from rank q, nearest ranks first so that concurrent pulls use different links
         TB200_CHECK(cudaStreamWaitEvent(t_bs.gather, t_bs.slice[p], 0));
         for (int k = 1; k < world; k++) {
             const int q = (rank + k) % world;
             if (q == root) continue;
+            uint64_t lo, len;
+            slice_range(p, slice_of(q), &lo, &len);
             if (stream_wait_value32(t_bs.gather, mine + q, token)) return 1;
-            if (pull(p, slice_of(q), q, t_bs.gather)) return 1;
+            if (len) TB200_CHECK(cudaMemcpyAsync(data(rank) + lo, data(q) + lo, len, cudaMemcpyDeviceToDevice, t_bs.gather));
+            t_trace.mark("p" + std::to_string(p) + " slice of rank " + std::to_string(q) + " pulled", t_bs.gather);
         }
         if (stream_write_value32(t_bs.gather, mine + 2 * world, token)) return 1;           // have: panel p complete here
-    }
-    // done reading from everybody (the root included: it waits for this before its source may change)
-    if (stream_write_value32(t_bs.gather, src_done, epoch)) return 1;
-    for (int k = 1; k < world; k++) {
-        const int q = (rank + k) % world;
-        TB200_CHECK(cudaMemcpyAsync(flags(q) + world + rank, src_done, 4, cudaMemcpyDeviceToDevice, t_bs.gather));
     }
     TB200_CHECK(cudaEventRecord(t_bs.end_s, t_bs.scatter));
     TB200_CHECK(cudaEventRecord(t_bs.end_g, t_bs.gather));
     return 0;
 }
 
-int bcast_sym_join(cudaStream_t st)
+// Joins the copy streams into the caller's stream and — on a non-root rank — tells the root, from THAT stream, that this
+// epoch is over here: the pulls from the peers are done and so is whatever the caller queued before (the GEMM that reads
+// the staged bytes).  The root's call returns (in stream order) only after every rank's word, and the root alone writes
+// into the other ranks' blocks, so the next epoch cannot overwrite anything that is still being read.
+int bcast_sym_join(cudaStream_t st, void *const *peers, uint64_t flags_offset, int root, uint32_t epoch)
 {
     TB200_CHECK(cudaStreamWaitEvent(st, t_bs.end_s, 0));
     TB200_CHECK(cudaStreamWaitEvent(st, t_bs.end_g, 0));
+    if (g_comm.rank != root) {
+        FlagTargets t;
+        t.p[0] = reinterpret_cast<uint32_t *>(static_cast<char *>(peers[root]) + flags_offset) + g_comm.world + g_comm.rank;
+        tiramisu_sm100_sym_flag_fanout<<<1, 32, 0, st>>>(t, 1, epoch);
+        return post_launch("tiramisu_sm100_sym_flag_fanout");
+    }
     return 0;
 }
 
@@ -666,12 +759,13 @@ TB200_API int tiramisu_b200_comm_broadcast_sym(void *const *peers, uint64_t data
     const uint64_t panel_bytes = (((bytes + panels - 1) / panels) + 255) & ~uint64_t(255);
     if (bcast_sym_fork(st) || bcast_sym_enqueue(peers, data_offset, bytes, panel_bytes, flags_offset, root, epoch, panels, RootPack{}))
         return 1;
-    return bcast_sym_join(st);
+    return bcast_sym_join(st, peers, flags_offset, root, epoch);
 }
 
 // Row-sharded sgemm with B's arrival fused in:  C[rows][N] = alpha * A[rows][K] * B[K][N] + beta * C  on every rank,
 // A and C this rank's row shard, B an ordinary row-major device matrix on the ROOT only (ignored elsewhere).  The
-// symmetric block (`stage_offset`, K * N * 4 bytes) is the library's staging area: B travels through it in `panels`
+// symmetric block (`stage_offset`, 2 * K * N * 4 bytes rounded up to 256 each: two halves used alternately, so that the
+// root can stage epoch e+1 while epoch e is still being consumed) is the library's staging area: B travels through it in `panels`
 // column panels (N / panels a multiple of 256; the same value on every rank), stored panel-major.  The root computes from
 // B itself; every other rank runs ONE persistent GEMM launch over the staged layout, gated per tile on the panels'
 // arrival (ranks whose shard is too small for a persistent kernel run one launch per panel behind stream-side waits).
@@ -692,6 +786,7 @@ TB200_API int tiramisu_b200_sgemm_bcast_b(void *const *peers, uint64_t stage_off
     if (rank == root && !B) return fail(__func__, "B is null on the root");
     cudaStream_t st = stream();
     const uint64_t w = N / panels, panel_bytes = K * w * 4;
+    stage_offset += (epoch & 1u) * ((K * N * 4 + 255) & ~uint64_t(255));       // two staging halves, alternating by epoch
     const float *stage = reinterpret_cast<const float *>(static_cast<char *>(peers[rank]) + stage_offset);
     const uint32_t *have = reinterpret_cast<const uint32_t *>(static_cast<char *>(peers[rank]) + flags_offset) + 2 * world;
     const uint32_t base = 64u * (epoch - 1);
@@ -700,8 +795,8 @@ TB200_API int tiramisu_b200_sgemm_bcast_b(void *const *peers, uint64_t stage_off
     if (bcast_sym_fork(st)) return 1;
     if (rank == root) {
         if (rows && tb200::gemm_f32(A, B, C, rows, N, K, alpha, beta, ldA, ldB, ldC, false, false)) return 1;
-        if (bcast_sym_enqueue(peers, stage_offset, K * N * 4, panel_bytes, flags_offset, root, epoch, panels, pack)) return 1;
-        return bcast_sym_join(st);
+        if (bcast_sym_enqueue(peers, stage_offset, K * N * 4, panel_bytes, flags_offset, root, epoch, panels, pack, true)) return 1;
+        return bcast_sym_join(st, peers, flags_offset, root, epoch);
     }
     const int kernel = tb200::gemm_tc_kernel_choice(rows, N, K, nullptr);
     const bool in_kernel = rows && (kernel == 2 || kernel == 3) && !getenv("TB200_GEMM_MODE") && !getenv("TB200_SGEMM_GATE_ON_STREAM") &&
@@ -713,15 +808,32 @@ TB200_API int tiramisu_b200_sgemm_bcast_b(void *const *peers, uint64_t stage_off
         const int rc = tb200::gemm_f32_tc(A, stage, C, rows, N, K, alpha, beta, ldA, w, ldC, false);
         tb200::gemm_tc_b_panels(0, 0);
         if (rc) return 1;
-        if (bcast_sym_enqueue(peers, stage_offset, K * N * 4, panel_bytes, flags_offset, root, epoch, panels, pack)) return 1;
-        return bcast_sym_join(st);
+        if (bcast_sym_enqueue(peers, stage_offset, K * N * 4, panel_bytes, flags_offset, root, epoch, panels, pack, true)) return 1;
+        return bcast_sym_join(st, peers, flags_offset, root, epoch);
     }
-    if (bcast_sym_enqueue(peers, stage_offset, K * N * 4, panel_bytes, flags_offset, root, epoch, panels, pack)) return 1;
+    if (bcast_sym_enqueue(peers, stage_offset, K * N * 4, panel_bytes, flags_offset, root, epoch, panels, pack, true)) return 1;
     for (int p = 0; p < panels && rows; p++) {                      // every staged panel is a plain row-major [K][w] matrix
         if (tb200::stream_wait_value32(st, have, base + (uint32_t)p + 1)) return 1;
         if (tb200::gemm_f32(A, stage + (uint64_t)p * K * w, C + (uint64_t)p * w, rows, w, K, alpha, beta, ldA, w, ldC, false, false)) return 1;
     }
-    return bcast_sym_join(st);
+    return bcast_sym_join(st, peers, flags_offset, root, epoch);
+}
+
+// Prints the timeline of the last traced broadcast of this thread (TB200_BCAST_TRACE=1); synchronises the device.
+TB200_API int tiramisu_b200_comm_broadcast_trace_dump(void)
+{
+    if (!t_trace.on || !t_trace.t0) return 0;
+    TB200_CHECK(cudaDeviceSynchronize());
+    std::string out = "[rank " + std::to_string(g_comm.rank) + "] broadcast timeline (ms after the fork):\n";
+    for (auto &m : t_trace.marks) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t_trace.t0, m.second);
+        char buf[160];
+        snprintf(buf, sizeof buf, "[rank %d]   %8.3f  %s\n", g_comm.rank, ms, m.first.c_str());
+        out += buf;
+    }
+    fputs(out.c_str(), stderr);
+    return 0;
 }
 
 TB200_API int tiramisu_b200_comm_free_symmetric(void *local)

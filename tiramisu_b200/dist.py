@@ -165,7 +165,7 @@ class SymmetricRows:
 
 # ---- B of the row-sharded sgemm: broadcast by the DMA engines, consumed by the GEMM as it arrives -------
 class SymmetricB:
-    """Staging area (K * N fp32 in symmetric memory + 256 flag bytes) for tiramisu_b200_sgemm_bcast_b.
+    """Staging area (2 x K * N fp32 in symmetric memory, used alternately, + 256 flag bytes) for tiramisu_b200_sgemm_bcast_b.
     Collective constructor / free.  `sgemm(B_ptr, A_ptr, C_ptr, rows, alpha, beta)` is the fused call: the root's
     row-major B is re-laid out panel-major into the staging area and travels in column panels (scatter + all-gather
     by peer copies, comm.cu) while every rank's GEMM consumes the panels as they arrive.  `broadcast()` moves the
@@ -180,7 +180,7 @@ class SymmetricB:
         self.data_bytes = ((K * N * 4 + 255) // 256) * 256
         local = C.c_void_p()
         self._peers = (C.c_void_p * self.world)()
-        _lib.check(L.tiramisu_b200_comm_alloc_symmetric(self.data_bytes + self.FLAG_BYTES, C.byref(local), self._peers),
+        _lib.check(L.tiramisu_b200_comm_alloc_symmetric(2 * self.data_bytes + self.FLAG_BYTES, C.byref(local), self._peers),
                    "comm_alloc_symmetric")
         self.local = local.value
         self.epoch = 0
@@ -206,18 +206,29 @@ class SymmetricB:
             p -= 1
         return p
 
+    def sgemm_panels(self) -> int:
+        """Column panels for the fused sgemm: as many as possible (the first panel's flight time is exposed) while one
+        rank's slice of a panel stays >= 32 MiB — a DMA copy between IPC-mapped blocks costs ~11 us of set-up whatever its
+        size (profiles/r02_p2p_patterns_8gpu.jsonl), 16 MiB copies already lose a third of the link."""
+        by_size = (self.K * self.N * 4) // ((32 << 20) * max(1, self.world - 1))
+        p = max(1, min(16, by_size, self.N // 1024 if self.N >= 1024 else 1))
+        while p > 1 and (self.N % p or (self.N // p) % 256):
+            p -= 1
+        return p
+
     def broadcast(self, root: int = 0, panels: int | None = None) -> None:
         self.epoch += 1
-        _lib.check(_lib.lib().tiramisu_b200_comm_broadcast_sym(self._peers, 0, self.K * self.N * 4, self.data_bytes, root, self.epoch,
+        _lib.check(_lib.lib().tiramisu_b200_comm_broadcast_sym(self._peers, 0, self.K * self.N * 4, 2 * self.data_bytes, root, self.epoch,
                                                                panels or self.default_panels(self.K, 32, 2048)), "comm_broadcast_sym")
 
     def sgemm(self, B_ptr: int | None, A_ptr: int, C_ptr: int, rows: int, alpha: float, beta: float, root: int = 0,
               panels: int | None = None, ldA: int = 0, ldB: int = 0, ldC: int = 0) -> None:
         """B_ptr: the root's row-major K x N matrix (device address; ignored on the other ranks)."""
         if panels is None:
-            panels = self.default_panels(self.N)
+            panels = self.sgemm_panels()
+        self.last_panels = panels
         self.epoch += 1
-        _lib.check(_lib.lib().tiramisu_b200_sgemm_bcast_b(self._peers, 0, self.data_bytes, root, self.epoch, panels,
+        _lib.check(_lib.lib().tiramisu_b200_sgemm_bcast_b(self._peers, 0, 2 * self.data_bytes, root, self.epoch, panels,
                                                           C.c_void_p(B_ptr if self.rank == root else None), ldB,
                                                           C.c_void_p(A_ptr), C.c_void_p(C_ptr), rows, self.N, self.K, alpha, beta, ldA, ldC),
                    "sgemm_bcast_b")

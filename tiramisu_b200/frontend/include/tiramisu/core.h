@@ -21,6 +21,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include <tiramisu/expr.h>
@@ -33,6 +34,45 @@ class buffer;
 class function;
 class input;
 class constant;
+class communicator;
+class send;
+class recv;
+class send_recv;
+class wait;
+
+/** Properties of a transfer (reference core.h:88-99, :5575-5608). */
+enum xfer_attr { SYNC, ASYNC, BLOCK, NONBLOCK, MPI, CUDA, CPU2CPU, CPU2GPU, GPU2CPU, GPU2GPU };
+
+class xfer_prop {
+public:
+    xfer_prop() {}
+    xfer_prop(primitive_t d_type, std::initializer_list<xfer_attr> attrs) : attrs_(attrs), dtype_(d_type) {}
+    xfer_prop(primitive_t d_type, std::initializer_list<xfer_attr> attrs, int xfer_prop_id) : attrs_(attrs), dtype_(d_type), id_(xfer_prop_id) {}
+    primitive_t get_dtype() const { return dtype_; }
+    int get_xfer_prop_id() const { return id_; }
+    bool contains_attr(xfer_attr a) const { return std::find(attrs_.begin(), attrs_.end(), a) != attrs_.end(); }
+    bool contains_attrs(std::vector<xfer_attr> as) const
+    {
+        for (xfer_attr a : as) if (!contains_attr(a)) return false;
+        return true;
+    }
+    void add_attr(xfer_attr a) { attrs_.push_back(a); }
+
+private:
+    std::vector<xfer_attr> attrs_;
+    primitive_t dtype_ = p_none;
+    int id_ = -1;
+};
+
+/** What computation::create_xfer returns (reference core.h:101-105). */
+struct xfer {
+    tiramisu::send *s = nullptr;
+    tiramisu::recv *r = nullptr;
+    tiramisu::send_recv *sr = nullptr;
+};
+
+/** Loop level, first iteration, last iteration (-1: the whole loop), number of elements (reference core.h:110). */
+typedef std::tuple<int, expr, expr, expr> collapse_group;
 
 void init(std::string name);
 void init();
@@ -73,6 +113,7 @@ public:
     computation *deallocate_at(computation &C, var level);
     void dump(bool) const;
     void substitute_dims(const std::vector<std::string> &names, const std::vector<expr> &values);
+    void set_dim_size(int dim, const expr &size) { dims_.at((size_t) dim) = size; }
     void replace_dim(const expr &from, const expr &to)
     {
         for (expr &d : dims_) if (d.is_equal(from)) d = to;
@@ -173,6 +214,35 @@ public:
     /** Run loop `old_var` backwards; the loop is called `new_var` afterwards (reference core.h:4461). */
     virtual void loop_reversal(var old_var, var new_var);
 
+    // ---- distribution (reference core.h:4583 tag_distribute_level, :4012 drop_rank_iter, :4817 gen_communication,
+    // :4944 create_xfer; src/tiramisu_core.cpp:599-628, :7565, :8778-8815, :9174-9295).  One rank = one process = one GPU:
+    // the iterations of a distributed loop are the ranks, every rank runs the one whose index equals
+    // tiramisu_MPI_Comm_rank(0); buffers are per rank.
+    virtual void tag_distribute_level(var L);
+    virtual void tag_distribute_level(int L);
+    /** The rank-local buffers are indexed without the distributed iterator: in everything this computation indexes with,
+      * the distributed loop counts as 0. */
+    void drop_rank_iter(var level);
+    bool should_drop_rank_iter() const { return !drop_rank_.empty(); }
+    /** Derive the exchange this computation's reads need from the other ranks (rows of a producer that is distributed the
+      * same way, read at a positive offset along the distributed iterator), create the send / receive pair in front of it
+      * and enlarge the producer's rank-local buffer by the received rows. */
+    void gen_communication();
+    void gen_communication(var) { gen_communication(); }
+    /** Request slots of non-blocking transfers: completion is tracked by the runtime's message queue, the mapping is only
+      * checked for syntax. */
+    void set_wait_access(std::string access_str);
+    static xfer create_xfer(std::string send_iter_domain, std::string recv_iter_domain, expr send_dest, expr recv_src,
+                            xfer_prop send_prop, xfer_prop recv_prop, expr send_expr, function *fct);
+    static xfer create_xfer(std::string iter_domain, xfer_prop prop, expr e, function *fct);
+    virtual bool is_send() const { return false; }
+    virtual bool is_recv() const { return false; }
+    virtual bool is_send_recv() const { return false; }
+    virtual bool is_wait() const { return false; }
+    bool is_communicator() const { return is_send() || is_recv() || is_send_recv() || is_wait(); }
+    /** Index of the distributed loop level, or -1. */
+    int get_distributed_dimension() const;
+
     /** Order: \p next runs after this computation, sharing the loops up to and including \p level. */
     computation &then(computation &next, var level = root);
     computation &then(computation &next, int level);
@@ -263,6 +333,7 @@ protected:
     std::vector<expr> access_;                           // index expressions in the original iterators
     std::vector<computation *> updates_;
     bool own_access_ = false;                            // an update that was mapped explicitly (not through its first definition)
+    std::string drop_rank_;                              // distributed level whose iterator the rank-local indices ignore
     computation *pred_ = nullptr, *succ_ = nullptr;
     std::string pred_level_;                             // "" = root
     int pred_level_index_ = -2;                          // -2 = by name, -1 = root, >=0 explicit depth
@@ -299,6 +370,88 @@ public:
     operator expr();
 };
 
+/** A computation that is a message (reference core.h:5610-5647).  Its loops stay on the host; every iteration is one
+  * call of the tiramisu_MPI_* runtime on the (device-resident) element its expression / access names. */
+class communicator : public computation {
+public:
+    communicator(std::string iteration_domain_str, expr rhs, bool schedule_this_computation, primitive_t data_type, function *fct)
+        : computation(iteration_domain_str, rhs, schedule_this_computation, data_type, fct) {}
+    communicator(std::string iteration_domain_str, expr rhs, bool schedule_this_computation, primitive_t data_type, xfer_prop prop,
+                 function *fct)
+        : computation(iteration_domain_str, rhs, schedule_this_computation, data_type, fct), prop(prop) {}
+    xfer_prop get_xfer_props() const { return prop; }
+    /** Elements per message: the product of what collapse() folded into it. */
+    expr get_num_elements() const;
+    void add_dim(expr size) { msg_dims_.push_back(size); }
+    /** One message for the whole of loop `level` (collapse_until_iter must be -1, as in the reference). */
+    std::vector<communicator *> collapse(int level, expr collapse_from_iter, expr collapse_until_iter, expr num_collapsed);
+    void collapse_many(std::vector<collapse_group> collapse_each);
+    /** Lowering: levels folded into the message by the lowering's own coalescing (same on both sides of a transfer). */
+    void fold_level(int level, const expr &count);
+    bool explicitly_collapsed() const { return !msg_dims_.empty(); }
+
+protected:
+    communicator() {}
+    xfer_prop prop;
+    std::vector<expr> msg_dims_;
+};
+
+class send : public communicator {
+public:
+    send(std::string iteration_domain_str, computation *producer, expr rhs, xfer_prop prop, bool schedule_this_computation,
+         std::vector<expr> dims, function *fct);
+    bool is_send() const override { return true; }
+    computation *get_producer() const { return producer_; }
+    recv *get_matching_recv() const { return matching_recv_; }
+    expr get_msg_tag() const { return msg_tag_; }
+    expr get_src() const { return src_; }
+    expr get_dest() const { return dest_; }
+    void set_matching_recv(recv *r) { matching_recv_ = r; }
+    void set_src(expr e) { src_ = e; }
+    void set_dest(expr e) { dest_ = e; }
+    void override_msg_tag(expr t) { msg_tag_ = t; }
+
+private:
+    computation *producer_ = nullptr;
+    recv *matching_recv_ = nullptr;
+    expr msg_tag_, src_, dest_;
+    static int next_msg_tag;
+};
+
+class recv : public communicator {
+public:
+    recv(std::string iteration_domain_str, bool schedule_this, xfer_prop prop, function *fct);
+    bool is_recv() const override { return true; }
+    send *get_matching_send() const { return matching_send_; }
+    expr get_msg_tag() const { return msg_tag_; }
+    expr get_src() const { return src_; }
+    expr get_dest() const { return dest_; }
+    void set_matching_send(send *s) { matching_send_ = s; }
+    void set_src(expr e) { src_ = e; }
+    void set_dest(expr e) { dest_ = e; }
+    void override_msg_tag(expr t) { msg_tag_ = t; }
+
+private:
+    send *matching_send_ = nullptr;
+    expr msg_tag_, src_, dest_;
+};
+
+/** One-sided / memcpy transfers (reference core.h:5735): declared for source compatibility, not lowered. */
+class send_recv : public communicator {
+public:
+    send_recv(std::string iteration_domain_str, computation *producer, expr rhs, xfer_prop prop, bool schedule_this_computation,
+              std::vector<expr> dims, function *fct);
+    bool is_send_recv() const override { return true; }
+};
+
+class wait : public communicator {
+public:
+    wait(expr rhs, xfer_prop prop, function *fct);
+    wait(std::string iteration_domain_str, expr rhs, xfer_prop prop, bool schedule_this, function *fct);
+    bool is_wait() const override { return true; }
+    std::vector<computation *> get_op_to_wait_on() const;
+};
+
 class function {
 public:
     explicit function(std::string name);
@@ -327,6 +480,8 @@ public:
     // gen_halide_obj() runs the whole lowering.  A function without gpu levels is a CPU schedule; this
     // back end has no CPU code generator, so such a function is re-targeted (lowering_retarget.cpp).
     void add_context_constraints(const std::string &) {}
+    /** Reference core.h:865: turns communicators into library calls; the lowering does that on its own. */
+    void lift_dist_comps() {}
     void gen_time_space_domain() {}
     void gen_isl_ast() {}
     void gen_halide_stmt() {}

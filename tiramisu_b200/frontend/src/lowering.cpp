@@ -201,6 +201,12 @@ std::string Lowering::run()
     for (computation *c : f_->get_computations())
         if (c->pending_bounds() && c->should_schedule_this_computation())
             die("computation '" + c->get_name() + "' was declared without iterator bounds and function::compute_bounds() was not called");
+    {
+        // distributed functions: the `rank` constant has to exist before the constants are collected; the order is only
+        // needed to look at the scheduled communicators (it is recomputed below)
+        std::vector<computation *> pre = order();
+        prepare_distribution(pre);
+    }
     expand_lets();
     expand_inline_computations();
     hoist_buffer_extents();
@@ -268,6 +274,14 @@ std::string Lowering::run()
         << "int tiramisu_b200_conv_relu_maxpool(const float *, const float *, const float *, float *, int32_t, int32_t, int32_t, int32_t);\n"
         << "int tiramisu_cublas_sgemm(float *, float *, float *, uint64_t, uint64_t, uint64_t, float, float, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, bool, bool);\n"
         << "int tiramisu_cublas_dgemm(double *, double *, double *, uint64_t, uint64_t, uint64_t, double, double, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, bool, bool);\n"
+        << (distributed_ ? "int tiramisu_MPI_Comm_rank(int);\nvoid tiramisu_MPI_Wait(void *);\nvoid tiramisu_MPI_global_barrier(void);\n"
+                           "#define TB_MPI_DECL(S, T) void tiramisu_MPI_Send_##S(int, int, int, T *); void tiramisu_MPI_Ssend_##S(int, int, int, T *); \\\n"
+                           "    void tiramisu_MPI_Isend_##S(int, int, int, T *, long *); void tiramisu_MPI_Issend_##S(int, int, int, T *, long *); \\\n"
+                           "    void tiramisu_MPI_Recv_##S(int, int, int, T *); void tiramisu_MPI_Irecv_##S(int, int, int, T *, long *);\n"
+                           "TB_MPI_DECL(int8, char) TB_MPI_DECL(uint8, unsigned char) TB_MPI_DECL(int16, short) TB_MPI_DECL(uint16, unsigned short)\n"
+                           "TB_MPI_DECL(int32, int) TB_MPI_DECL(uint32, unsigned int) TB_MPI_DECL(int64, long) TB_MPI_DECL(uint64, unsigned long)\n"
+                           "TB_MPI_DECL(f32, float) TB_MPI_DECL(f64, double)\n"
+                         : "")
         << "}\n"
         << "template <typename T> __host__ __device__ __forceinline__ T tb_max(T a, T b) { return a > b ? a : b; }\n"
         << "template <typename T> __host__ __device__ __forceinline__ T tb_min(T a, T b) { return a < b ? a : b; }\n"
@@ -318,6 +332,7 @@ std::string Lowering::run()
     for (buffer *b : f_->get_buffers())
         if (!is_arg.count(b) && b->get_auto_allocate() && (b->get_location() == mem_loc::host || b->get_location() == mem_loc::gpu_global))
             autos.push_back(b);
+    autos.erase(std::remove_if(autos.begin(), autos.end(), [](buffer *b) { return b->get_elements_type() == p_wait_ptr; }), autos.end());   // request slots: the runtime queues
     for (buffer *b : autos)
         out << pad(1) << "b_" << san(b->get_name()) << " = (" << ctype(b->get_elements_type()) << " *) "
             << (b->get_location() == mem_loc::gpu_global ? "tiramisu_cuda_malloc(" : "malloc(") << bytes_of(b, false) << ");\n";

@@ -2,6 +2,7 @@
 //   lowering.cpp           order, loop tree, gpu axes, kernel argument collection, driver, nvcc invocation
 //   lowering_emit.cpp      index simplification, expression printing, statement / kernel / host emission
 //   lowering_patterns.cpp  pattern lowerings: contractions -> runtime GEMM, sgemm statement triple, heat2d pair, conv block idiom
+//   lowering_dist.cpp      distributed levels (rank scope), send / recv / wait -> tiramisu_MPI_* on device addresses, message coalescing
 //   lowering_retarget.cpp  CPU schedules -> GPU: constants, device mirrors, mapping, warp-shuffle reduction, loop distribution, nest fusion
 #ifndef TIRAMISU_B200_FRONTEND_LOWERING_H
 #define TIRAMISU_B200_FRONTEND_LOWERING_H
@@ -92,6 +93,9 @@ private:
     std::set<std::string> proto_seen_;
     bool pattern_ = true;
     bool retargeted_ = false;                 // CPU schedule mapped onto the GPU; host arguments mirrored on the device
+    bool distributed_ = false;                // the function has distributed levels / communicators (lowering_dist.cpp)
+    bool prepare_distribution(const std::vector<computation *> &ord);
+    void emit_communicator(Node *n, std::ostringstream &os, int ind);
     std::set<buffer *> mirrored_;             // argument buffers with a device mirror (b_X device, h_X host)
     std::set<buffer *> no_copy_in_;           // outputs that are completely overwritten before being read
     std::set<buffer *> written_args_;         // mirrored arguments some statement stores into (copied back whatever their declared type)

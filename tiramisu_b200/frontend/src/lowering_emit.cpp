@@ -539,6 +539,7 @@ void Lowering::emit_kernel(Node *n, std::ostringstream &host, int ind, std::vect
 void Lowering::emit_host_stmt(Node *n, std::ostringstream &os, int ind)
 {
     computation *c = n->comp;
+    if (c->is_communicator()) { emit_communicator(n, os, ind); return; }
     const expr &e = c->get_expr();
     if (e.get_expr_type() == e_sync) die("'" + c->get_name() + "': sync() outside a gpu loop nest");
     if (e.get_expr_type() == e_op && e.get_op_type() == o_memcpy) {
@@ -590,6 +591,11 @@ void Lowering::emit_host(Node *n, std::ostringstream &os, int ind, std::vector<N
     if (!n->is_loop) { emit_host_stmt(n, os, ind); return; }
     if (n->tag == loop_dim::gpu_block || n->tag == loop_dim::gpu_thread) { emit_kernel(n, os, ind, host_loops); return; }
     const std::string it = ctype(global::get_loop_iterator_data_type());
+    if (n->tag == loop_dim::distributed) {
+        // one iteration per rank: this process runs the one whose index is its rank (reference: `if (rank == i)`)
+        os << pad(ind) << "for (" << it << " " << n->cname() << " = (" << it << ") c_rank, tb_once = 0; tb_once == 0 && " << n->cname() << " >= " << print(n->lo, false)
+           << " && " << n->cname() << " < " << print(n->hi, false) << "; tb_once++) {\n";
+    } else
     os << pad(ind) << "for (" << it << " " << n->cname() << " = " << print(n->lo, false) << "; " << n->cname() << " < " << print(n->hi, false) << "; "
        << n->cname() << "++) {\n";
     host_loops.push_back(n);

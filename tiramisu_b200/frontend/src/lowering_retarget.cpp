@@ -327,6 +327,8 @@ std::set<std::string> Lowering::parallel_iterators(computation *c)
 bool Lowering::dim_is_parallel(computation *c, const std::string &dim)
 {
     if (!c->has_access() && !c->get_expr().is_defined()) return false;
+    if (c->is_communicator()) return false;
+    { const int l = c->find_dim(dim); if (l >= 0 && c->dims()[(size_t) l].tag == loop_dim::distributed) return false; }   // the rank scope is not a loop to map
     c->get_buffer();
     auto hit = parallel_iters_.find(c);
     if (hit == parallel_iters_.end()) hit = parallel_iters_.emplace(c, parallel_iterators(c)).first;
@@ -469,7 +471,7 @@ void Lowering::map_fused_parallel_loops(const std::vector<computation *> &ord)
         if (!ok) continue;
         for (size_t k = first; k < last; k++) {
             computation *c = ord[k];
-            for (auto &d : c->dims()) d.tag = loop_dim::none;
+            for (auto &d : c->dims()) if (d.tag != loop_dim::distributed) d.tag = loop_dim::none;
             const std::string inner = c->dims()[P - 1].name;
             if (P >= 2) c->dims()[P - 2].tag = loop_dim::gpu_block;
             if (P >= 3) c->dims()[P - 3].tag = loop_dim::gpu_block;
@@ -484,6 +486,8 @@ void Lowering::map_fused_parallel_loops(const std::vector<computation *> &ord)
 
 void Lowering::auto_map(computation *c, int shared_depth)
 {
+    if (c->is_communicator()) return;                                // host loops around tiramisu_MPI_* calls
+    if (c->get_distributed_dimension() >= 0) shared_depth = std::max(shared_depth, c->get_distributed_dimension() + 1);   // the rank scope stays on the host
     const expr &e = c->get_expr();
     if (e.get_expr_type() == e_sync || (e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate ||
                                                                        e.get_op_type() == o_free || (e.get_op_type() == o_call && !c->has_access()))))
@@ -494,7 +498,7 @@ void Lowering::auto_map(computation *c, int shared_depth)
         // nothing to spread over threads (a scalar statement, or every loop carries a dependence): the
         // statement's own loops run sequentially inside a one-thread kernel
         loop_dim one; one.name = "_one_" + c->get_name(); one.lo = expr((int32_t) 0); one.hi = expr((int32_t) 1); one.tag = loop_dim::gpu_block;
-        for (auto &d : dims) d.tag = loop_dim::none;
+        for (auto &d : dims) if (d.tag != loop_dim::distributed) d.tag = loop_dim::none;
         dims.insert(dims.begin() + shared_depth, one);
     };
     if (dims.empty()) { one_thread(); return; }
@@ -527,7 +531,7 @@ void Lowering::auto_map(computation *c, int shared_depth)
     // sequential host loops around the kernels; only the statement's own loops are mapped
     int vec = -1;
     for (size_t i = shared_depth; i < dims.size(); i++) if (dims[i].tag == loop_dim::vector && parallel_safe(dims[i].name)) vec = (int) i;
-    for (auto &d : dims) d.tag = loop_dim::none;
+    for (auto &d : dims) if (d.tag != loop_dim::distributed) d.tag = loop_dim::none;
     if ((int) dims.size() == shared_depth) { one_thread(); return; }
     // warp-shuffle reduction: the innermost loop is the only reduction and is unit stride in what it reads
     if (pattern_ && is_float_type(c->get_data_type()) && (int) dims.size() >= shared_depth + 2) {
@@ -624,6 +628,15 @@ void Lowering::mirror_buffers(const std::vector<computation *> &ord, bool gpu_on
     };
     std::set<buffer *> used;
     for (computation *c : ord) {
+        if (c->is_communicator()) {
+            // messages travel between the DEVICE mirrors: a receive writes its buffer, a send reads its payload's
+            if (c->is_recv() && c->has_access()) { used.insert(c->get_buffer()); written_args_.insert(c->get_buffer()); }
+            if (c->is_send()) {
+                computation *oc = f_->find_computation(c->get_expr().get_name());
+                if (oc && !oc->is_constant()) used.insert(oc->get_buffer());
+            }
+            continue;
+        }
         if (gpu_only && !on_gpu(c)) continue;
         const expr &e = c->get_expr();
         const bool stmt_only = e.get_expr_type() == e_sync || (e.get_expr_type() == e_op && (e.get_op_type() == o_memcpy || e.get_op_type() == o_allocate || e.get_op_type() == o_free));

@@ -213,7 +213,7 @@ def sgemm(ctx: Ctx, n: int, e2e: bool = True) -> dict:
         # one call per step moves rank 0's B through symmetric staging memory (DMA-engine scatter + all-gather of column
         # panels over NVLink, no SM kernels) and runs the GEMM, gated inside the kernel on the panels' arrival words
         symB = tdist.SymmetricB(n, n)
-        panels = symB.default_panels(n)
+        panels = symB.sgemm_panels()
         Bp = B.data_ptr() if rank == 0 else None
 
         def step():
@@ -247,7 +247,14 @@ def sgemm(ctx: Ctx, n: int, e2e: bool = True) -> dict:
                 api.cublas_sgemm(A.data_ptr(), B.data_ptr(), C.data_ptr(), rows, n, kw, 3.0, 2.0 if p == 0 else 1.0,
                                  ldA=n, ldB=n, ldC=n, offA=p * kw, offB=p * kw * n)
 
-        out["ms_ncclBroadcast_form"] = ctx.time_device(step_nccl, iters, extra_streams=(comm_s,))
+        ms_nccl = ctx.time_device(step_nccl, iters, extra_streams=(comm_s,))
+        out["ms_ncclBroadcast_form"] = ms_nccl
+        out["ms_dma_fused_form"] = ms
+        # both forms are this library's code; the line's value is the faster one on this box and says which
+        # (r02 runs 12-17: the DMA form wins at 2 GPUs, at 8 the fine-grained peer copies between IPC-mapped blocks
+        # only reach ~330 GB/s per rank and ncclBroadcast + events is ahead)
+        out["form"] = "dma_fused" if ms <= ms_nccl else "ncclBroadcast + stream events"
+        ms = min(ms, ms_nccl)
         symB.free()
     out.update({"value": flop / (ms * 1e-3) / 1e9, "ms": ms,
                 "roofline": _roof_tensor(ctx, "tiramisu_sm100_gemm_tf32*", flop, ms,

@@ -45,15 +45,12 @@ def main():
             return float(t.item()), mine
 
         res = {"n": n, "world": world}
-        for panels in sorted({symB.default_panels(n), 8, 4, 1}, reverse=True):
+        for panels in sorted({symB.sgemm_panels(), 16, 8, 4, 2}, reverse=True):
             res[f"p{panels}_fused"] = timed(lambda: symB.sgemm(Bp, A.data_ptr(), Cm.data_ptr(), rows, 1.0, 0.0, 0, panels))
             res[f"p{panels}_bcast_only"] = timed(lambda: symB.sgemm(Bp, A.data_ptr(), Cm.data_ptr(), 0, 1.0, 0.0, 0, panels))
-            os.environ["TB200_SGEMM_GATE_ON_STREAM"] = "1"
-            res[f"p{panels}_gate_on_stream"] = timed(lambda: symB.sgemm(Bp, A.data_ptr(), Cm.data_ptr(), rows, 1.0, 0.0, 0, panels))
-            del os.environ["TB200_SGEMM_GATE_ON_STREAM"]
         if n >= 12288:
             os.environ["TB200_GEMM_NO_KPANELS"] = "1"
-            pd = symB.default_panels(n)
+            pd = symB.sgemm_panels()
             res[f"p{pd}_fused_one_launch_over_K"] = timed(lambda: symB.sgemm(Bp, A.data_ptr(), Cm.data_ptr(), rows, 1.0, 0.0, 0, pd))
             res["gemm_only_one_launch_over_K"] = timed(lambda: api.cublas_sgemm(A.data_ptr(), symB.data_ptr(), Cm.data_ptr(), rows, n, n, 1.0, 0.0))
             del os.environ["TB200_GEMM_NO_KPANELS"]
