@@ -14,6 +14,9 @@ int tiramisu_MPI_Comm_rank(int offset);
 }
 
 typedef int MPI_Comm;
+typedef int MPI_Datatype;
+typedef long MPI_Request;
+struct MPI_Status { int MPI_SOURCE, MPI_TAG, MPI_ERROR; };
 #define MPI_COMM_WORLD 0
 #define MPI_THREAD_SINGLE 0
 #define MPI_THREAD_FUNNELED 1

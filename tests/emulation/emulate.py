@@ -72,7 +72,7 @@ def runtime_object() -> str:
     return obj
 
 
-def build_shared(cu_paths: list[str], name: str) -> str:
+def build_shared(cu_paths: list[str], name: str, extra_sources: tuple = ()) -> str:
     """Generated source(s) -> tests/emulation/_build/<name>.emu.so (runtime stand-ins and oracle linked in)."""
     rt = runtime_object()
     srcs = []
@@ -83,7 +83,7 @@ def build_shared(cu_paths: list[str], name: str) -> str:
     so = os.path.join(OUT, f"{name}.emu.so")
     # -Bsymbolic: the stand-ins linked in here win over libtiramisu_b200.so's symbols of the same name, which an
     # earlier test of the same process may have loaded RTLD_GLOBAL
-    r = _gxx(["-shared", "-fPIC", "-Wl,-Bsymbolic", "-I", os.path.join(HERE, "include"), *srcs, rt, "-o", so, f"-L{ORACLE}", "-ltiramisu_oracle",
+    r = _gxx(["-shared", "-fPIC", "-Wl,-Bsymbolic", "-I", os.path.join(HERE, "include"), *srcs, *extra_sources, rt, "-o", so, f"-L{ORACLE}", "-ltiramisu_oracle",
               f"-Wl,-rpath,{ORACLE}"])
     if r.returncode:
         raise RuntimeError(r.stderr[-2000:])
@@ -143,6 +143,51 @@ def reference_test(n: str, gen_dir: str | None = None) -> tuple[str, str]:
         return n, "pass"
     tail = [ln for ln in out.splitlines() if ln.strip()]
     return n, f"FAIL rc={r.returncode}: " + (tail[-1][:160] if tail else "")
+
+
+def reference_dist_test(n: str, ranks: int = 10, gen_dir: str | None = None) -> tuple[str, str]:
+    """Emulated build of DISTRIBUTED reference test N (-DWITH_MPI, tests/emulation/mpi_emu.cpp as the message layer) and a
+    run of the reference's own wrapper as `ranks` processes; the wrapper's compare_buffers decides."""
+    import tempfile
+    if gen_dir is None:
+        gen_dir = os.path.join(COMPAT, "_gen", "reftests", n)
+    cus = glob.glob(os.path.join(gen_dir, "build", "*.b200.cu"))
+    if not cus:
+        return n, "no generated source"
+    srcs = []
+    try:
+        for p in cus:
+            dst = os.path.join(OUT, "reftests_dist", n, os.path.basename(p).replace(".cu", ".emu.cpp"))
+            rewrite(p, dst)
+            srcs.append(dst)
+    except NotEmulatable as e:
+        return n, f"not emulatable: {e}"
+    exe = os.path.join(os.path.dirname(srcs[0]), "run")
+    r = _gxx(["-DWITH_MPI", "-I", os.path.join(HERE, "include"), "-I", os.path.join(COMPAT, "include"), "-I", os.path.join(REF, "3rdParty/Halide/src/runtime"),
+              "-I", os.path.join(REF, "include"), "-I", os.path.join(REF, "tests"), os.path.join(REF, "tests", f"wrapper_test_{n}.cpp"), *srcs,
+              os.path.join(COMPAT, "compat_support.cpp"), os.path.join(REF, "src/tiramisu_utils.cpp"), os.path.join(REF, "src/tiramisu_debug.cpp"),
+              runtime_object(), os.path.join(HERE, "mpi_emu.cpp"), "-o", exe, f"-L{ORACLE}", "-ltiramisu_oracle", f"-Wl,-rpath,{ORACLE}", "-lpthread", "-ldl"])
+    if r.returncode:
+        m = re.search(r"(error|undefined reference)[^\n]*", r.stderr)
+        return n, "does not build: " + (m.group(0)[:300] if m else r.stderr[-300:])
+    with tempfile.TemporaryDirectory(prefix="tb200_mpi_emu_") as box:
+        procs = []
+        for rk in range(ranks):
+            env = dict(os.environ, RANK=str(rk), WORLD_SIZE=str(ranks), TB200_EMU_MPI_DIR=box)
+            procs.append(subprocess.Popen([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=os.path.dirname(exe)))
+        outs, bad = [], []
+        for rk, pr in enumerate(procs):
+            try:
+                o, _ = pr.communicate(timeout=180)
+            except subprocess.TimeoutExpired:
+                pr.kill()
+                o, _ = pr.communicate()
+                o += "\n[timeout]"
+            outs.append(o)
+            if pr.returncode != 0 or "Test failed" in o or "rror" in o or "[timeout]" in o:
+                tail = [ln for ln in o.splitlines() if ln.strip()]
+                bad.append(f"rank {rk} rc={pr.returncode}: " + (tail[-1][:160] if tail else ""))
+    return n, "pass" if not bad else "FAIL " + "; ".join(bad[:3])
 
 
 def sweep(ids: list[str], workers: int = 8) -> dict:

@@ -233,3 +233,38 @@ def test_reference_feature_tests_pass_their_wrappers_in_emulation():
     res = emulate.sweep(have)
     bad = {k: v for k, v in res.items() if v != "pass"}
     assert not bad, bad
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference (wrappers)")
+def test_distributed_reference_tests_pass_their_wrappers_as_ten_emulated_ranks():
+    """tests/test_98, 99, 101, 102 (explicit transfers, blocking; fan-out / fan-in; collapse_many) and test_160
+    (gen_communication: the halo derived from the accesses) of the reference, generators and wrappers unmodified: the
+    lowered functions run as 10 host processes over the file-mailbox stand-in of tiramisu_MPI_* and every rank's
+    wrapper compares its buffers itself."""
+    expected = json.load(open(os.path.join(ROOT, "tests/compat/reference_tests_expected.json")))
+    ids = expected["distributed"]["tests"]
+    have = [n for n in ids if os.path.isdir(os.path.join(ROOT, "tests/compat/_gen/reftests", n))]
+    if len(have) < len(ids):
+        pytest.skip("sweep outputs not built")
+    res = dict(emulate.reference_dist_test(n, 10) for n in ids)
+    bad = {k: v for k, v in res.items() if v != "pass"}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_generated_distributed_functions_as_emulated_ranks(cases, world, tmp_path):
+    """tests/frontend_cases/dist_blur_gen.cpp (gen_communication halo) and dist_xfer_gen.cpp (explicit fan-out / ring with
+    blocking synchronous sends / hand-collapsed fan-in) at 2, 4 and 8 ranks: tools/dist_gen_check.py compares every rank's
+    buffers with numpy restatements; here the ranks are host processes over the file-mailbox tiramisu_MPI_* stand-in, on
+    the GPU box the same script runs under torchrun over NCCL (tests/test_gpu_multi.py)."""
+    import subprocess
+    import sys
+    mpi = (os.path.join(ROOT, "tests", "emulation", "mpi_emu.cpp"),)
+    blur = emulate.build_shared([bc.generated_source(f"dist_blur_gen_{world}")], f"dist_blur_gen_{world}", mpi)
+    xfer = emulate.build_shared([bc.generated_source(f"dist_xfer_gen_{world}")], f"dist_xfer_gen_{world}", mpi)
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "dist_gen_check.py"), "--emulated", blur, xfer],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), TB200_EMU_MPI_DIR=str(tmp_path)))
+             for r in range(world)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 and "DIST_GEN_OK" in o for p, o in zip(procs, outs)), "\n".join(o[-800:] for o in outs)

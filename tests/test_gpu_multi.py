@@ -40,3 +40,23 @@ def test_reference_heat2d_dist_wrapper_unmodified():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_ranks.py"), "4", exe], capture_output=True, text=True,
                        timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+
+
+@pytest.mark.gpu
+def test_generated_distributed_functions_over_nccl():
+    """Functions the FRONT-END generates from distributed programs (tests/frontend_cases/dist_blur_gen.cpp: halo derived by
+    gen_communication; dist_xfer_gen.cpp: explicit create_xfer fan-out / ring / fan-in) — rank scope + tiramisu_MPI_* calls on
+    device addresses, coalesced messages — one rank per GPU over the library's NCCL communicator, compared with numpy
+    restatements by tools/dist_gen_check.py (the same script the CPU suite runs over emulated ranks)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    from tests.frontend_cases import build_cases as bc
+    if not os.path.exists(bc.lib_path(f"dist_xfer_gen_{world}")):
+        pytest.skip("front-end cases not built (__graft_entry__.build())")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29735", os.path.join(ROOT, "tools", "dist_gen_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "DIST_GEN_OK" in r.stdout, (r.stdout + r.stderr)[-4000:]
