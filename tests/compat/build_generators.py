@@ -159,7 +159,8 @@ def build(names=None, verbose=False) -> dict:
     import concurrent.futures as cf
     jobs = [(n, None) for n in TARGETS if not names or n in names]
     # the pattern-lowered generators once more with the pattern lowering off (generic SIMT emission)
-    jobs += [(n, "generic") for n in ("test_167", "test_169", "heat2d", "chain_mm", "lstm_cpu", "lstm_cpu_so") if not names or n in names]
+    jobs += [(n, "generic") for n in ("test_167", "test_169", "heat2d", "chain_mm", "lstm_cpu", "lstm_cpu_so", "sgemm_gpu_generator1", "sgemm_gpu_generator2",
+                                      "sgemm_gpu_generator3") if not names or n in names]
     out = {}
     with cf.ThreadPoolExecutor(max_workers=min(6, max(1, len(jobs)))) as ex:
         futs = {ex.submit(build_one, n, low): (n if low is None else f"{n}_{low}") for n, low in jobs}

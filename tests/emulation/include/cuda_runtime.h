@@ -32,6 +32,20 @@ inline thread_local dim3 gridDim, blockDim;
 typedef void *cudaStream_t;
 enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 inline int cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { std::memcpy(d, s, n); return 0; }
+// CUDA graphs (generated host loops are captured once and replayed): the emulation has no streams to capture —
+// cudaStreamBeginCapture reports failure and the generated code runs its statements directly
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorNotSupported = 801 };
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
+typedef void *cudaGraph_t;
+typedef void *cudaGraphExec_t;
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorNotSupported; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g) { *g = nullptr; return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 
 template <typename K, typename... A> inline void tb_emu_launch(K kernel, dim3 grid, dim3 block, A... args)
 {

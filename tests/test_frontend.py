@@ -161,7 +161,7 @@ def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     res = bg.build()
     failed = {k: v[1] for k, v in res.items() if v[0] != 0}
     assert not failed, failed
-    assert len(res) == len(bg.TARGETS) + 6          # + the generic-lowering variants
+    assert len(res) == len(bg.TARGETS) + 9          # + the generic-lowering variants
     cb = open(os.path.join(bg.GEN, "conv_block", "conv_relu_maxpool_tiramisu.o.b200.cu")).read()
     assert "tiramisu_b200_conv_relu_maxpool(b__c_input_buffer, b__conv_filter_buffer, b__conv_bias_buffer, b_output_buf, 32, 224, 3, 32)" in cb
     assert "__global__" not in cb
@@ -183,9 +183,14 @@ def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     assert lg.count("__global__") == 6 and "__shared__ float b_b_m1_R_shr[256];" in lg and "__shared__ float b_b_m1_h_shr[272];" in lg
     # the hand-scheduled GEMM of sgemm/gpu/generator1.cpp keeps its structure: two shared buffers,
     # per-thread accumulators with compile-time indices (registers, no local memory), two barriers
-    src = open(os.path.join(bg.GEN, "sgemm_gpu_generator1", "fct.o.b200.cu")).read()
+    # (with the pattern lowerings off; by default the kernel's Layer-I arithmetic is recognised as a contraction and the
+    # staging is followed back to the global matrices: one tcgen05 GEMM call, no kernel)
+    src = open(os.path.join(bg.GEN, "sgemm_gpu_generator1_generic", "fct.o.b200.cu")).read()
     assert "__shared__ float b_b_A_shr[8224];" in src and "__shared__ float b_b_B_shr[3072];" in src
     assert src.count("__syncthreads();") == 2 and "b_b_acc[(i_i1) * 6 + i_j1]" in src
+    for g in (1, 2, 3):
+        pat = open(os.path.join(bg.GEN, f"sgemm_gpu_generator{g}", "fct.o.b200.cu")).read()
+        assert "__global__" not in pat and pat.count("tiramisu_cublas_sgemm((float") == 1 and "hand-staged contraction" in pat
     # benchmarks/halide/heat2d_tiramisu.cpp (ISL-string API, CPU schedule): the statement pair is recognised
     # and handed to the runtime's heat2d entry point; with the pattern lowering off, two generated kernels
     heat = open(os.path.join(bg.GEN, "heat2d", "build", "generated_fct_heat2d.o.b200.cu")).read()
@@ -251,10 +256,12 @@ def test_reference_generators_through_lowering(name, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gen", ["sgemm_gpu_generator1", "sgemm_gpu_generator2", "sgemm_gpu_generator3"])
+@pytest.mark.parametrize("gen", ["sgemm_gpu_generator1", "sgemm_gpu_generator2", "sgemm_gpu_generator3",
+                                 "sgemm_gpu_generator1_generic", "sgemm_gpu_generator2_generic", "sgemm_gpu_generator3_generic"])
 def test_reference_sgemm_gpu_generators_match_cublas(gen, tmp_path):
-    """sgemm/gpu/generator{1,2,3}.cpp (hand-scheduled shared-memory/register-tiled GEMMs, 3072^3)
-    lowered faithfully; the reference wrapper checks the result against cuBLAS exactly."""
+    """sgemm/gpu/generator{1,2,3}.cpp (hand-scheduled shared-memory/register-tiled GEMMs, 3072^3): by default recognised
+    as contractions (Layer I) and run as one tcgen05 GEMM; `_generic` = lowered faithfully to the SIMT kernel they
+    describe.  Either way the reference wrapper checks the result against cuBLAS exactly."""
     out = _run(gen, args=("1", "1"), cwd=tmp_path)
     assert "cuBLAS and Tiramisu outputs match" in out, out[-2000:]
 

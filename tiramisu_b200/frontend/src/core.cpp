@@ -377,8 +377,18 @@ void computation::between(computation &before_c, var before_l, computation &afte
     after_c.after(*this, after_l);
 }
 
-computation *computation::cache_shared(computation &inp, const var &, std::vector<int>, std::vector<expr>, bool)
+computation *computation::cache_shared(computation &inp, const var &level, std::vector<int>, std::vector<expr>, bool)
 {
+    // Not a transformation here, and said so at generator time: the reference rewrites the consumer to read a shared-memory
+    // copy of `inp` filled below `level` (src/tiramisu_core.cpp:9297-9534).  This back end keeps the consumer reading `inp`
+    // where it lives; a contraction written this way is recognised from Layer I and runs on the tensor cores
+    // (lowering_patterns.cpp: try_staged_contraction / try_gemm_pattern), anything else reads through L1/L2.
+    static bool told = false;
+    if (!told) {
+        std::cerr << "tiramisu_b200 front-end: note: cache_shared('" << inp.get_name() << "', level '" << level.get_name() << "') of '" << name_
+                  << "' is recorded as a hint only: no shared-memory staging is generated for it (further notes of this kind are not repeated)\n";
+        told = true;
+    }
     return &inp;
 }
 

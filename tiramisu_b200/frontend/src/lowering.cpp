@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -252,6 +253,7 @@ std::string Lowering::run()
             i += 2;
             continue;
         }
+        if (is_kernel(k) && try_staged_contraction(k, body, 1)) continue;
         emit_host(k, body, 1, host_loops);
     }
 
@@ -349,7 +351,55 @@ std::string Lowering::run()
     // The statements run inside a lambda so that a failed launch (`return 1` in the middle of the body) still reaches
     // the common exit below: device mirrors and temporaries are released on every path, outputs are copied back
     // only when everything succeeded.
-    out << pad(1) << "const int tb_rc = [&]() -> int {\n" << body.str() << pad(1) << "return 0;\n" << pad(1) << "}();\n";
+    // Host loops around kernels (the lowered LSTM: seq_length x layers x 4 launches = 1600 per call, r01: 19 ms of which most
+    // is launch latency) are captured ONCE into a CUDA graph and replayed: the graph is kept per thread, keyed by every
+    // device address and every function constant the statements can see, so a later call with the same operands costs one
+    // graph launch.  Only when everything in the body is a kernel launch or a runtime GEMM call on the thread's stream.
+    bool host_graph = false;
+    {
+        std::function<void(Node *, int64_t, int64_t &, bool &)> scan = [&](Node *n, int64_t trips, int64_t &launches, bool &pure) {
+            if (!n->is_loop) { pure = false; return; }                                   // a host-level statement
+            if (n->tag == loop_dim::gpu_block || n->tag == loop_dim::gpu_thread) { launches += trips; return; }
+            if (n->tag == loop_dim::distributed) { pure = false; return; }
+            expr ext = n->hi - n->lo;
+            const int64_t t = ext.is_int_literal() ? std::max<int64_t>(1, ext.get_int_val()) : 8;   // symbolic extent: assume a few
+            for (auto &k : n->kids) scan(k.get(), trips * t, launches, pure);
+        };
+        int64_t launches = 0;
+        bool pure = !whole_function_idiom && !distributed_;
+        for (auto &k : root_.kids) scan(k.get(), 1, launches, pure);
+        host_graph = pure && launches >= 32;
+        if (const char *e = getenv("TIRAMISU_B200_HOST_GRAPH")) host_graph = pure && e[0] == '1';
+    }
+    if (!host_graph) {
+        out << pad(1) << "const int tb_rc = [&]() -> int {\n" << body.str() << pad(1) << "return 0;\n" << pad(1) << "}();\n";
+    } else {
+        out << pad(1) << "auto tb_body = [&]() -> int {\n" << body.str() << pad(1) << "return 0;\n" << pad(1) << "};\n";
+        out << pad(1) << "int tb_rc = 0;\n" << pad(1) << "{   // host loops of launches -> one CUDA graph, captured once per operand set and replayed\n";
+        out << pad(2) << "static thread_local cudaGraphExec_t tb_exec = nullptr;\n" << pad(2) << "static thread_local uint64_t tb_key = 0;\n";
+        out << pad(2) << "uint64_t key = 1469598103934665603ull;\n" << pad(2) << "auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };\n";
+        for (buffer *b : f_->get_buffers())
+            if (b->get_location() == mem_loc::host || b->get_location() == mem_loc::gpu_global)
+                out << pad(2) << "mix((uint64_t) (uintptr_t) b_" << san(b->get_name()) << ");\n";
+        for (computation *c : constant_order_)
+            out << pad(2) << "{ uint64_t bits = 0; const auto v = c_" << san(c->get_name()) << "; memcpy(&bits, &v, sizeof(v) < 8 ? sizeof(v) : 8); mix(bits); }\n";
+        out << pad(2) << "cudaStream_t st = (cudaStream_t) tiramisu_b200_get_stream();\n";
+        out << pad(2) << "if (getenv(\"TB200_NO_HOST_GRAPH\")) tb_rc = tb_body();\n";
+        out << pad(2) << "else if (tb_exec && tb_key == key) { if (cudaGraphLaunch(tb_exec, st) != cudaSuccess) tb_rc = 1; }\n";
+        out << pad(2) << "else {\n";
+        out << pad(3) << "if (tb_exec) { cudaGraphExecDestroy(tb_exec); tb_exec = nullptr; }\n";
+        out << pad(3) << "cudaGraph_t g = nullptr;\n";
+        out << pad(3) << "if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); tb_rc = tb_body(); }\n";
+        out << pad(3) << "else {\n";
+        out << pad(4) << "tb_rc = tb_body();\n";
+        out << pad(4) << "const cudaError_t e = cudaStreamEndCapture(st, &g);\n";
+        out << pad(4) << "if (tb_rc == 0 && e == cudaSuccess && g && cudaGraphInstantiate(&tb_exec, g, 0) == cudaSuccess) {\n";
+        out << pad(5) << "tb_key = key;\n" << pad(5) << "if (cudaGraphLaunch(tb_exec, st) != cudaSuccess) tb_rc = 1;\n";
+        out << pad(4) << "} else {          // could not be captured: run the statements directly\n";
+        out << pad(5) << "tb_exec = nullptr;\n" << pad(5) << "cudaGetLastError();\n" << pad(5) << "if (tb_rc == 0) tb_rc = tb_body();\n" << pad(4) << "}\n";
+        out << pad(4) << "if (g) cudaGraphDestroy(g);\n";
+        out << pad(3) << "}\n" << pad(2) << "}\n" << pad(1) << "}\n";
+    }
     for (buffer *b : args_) {
         if (!mirrored_.count(b) || direct_.count(b)) continue;
         const std::string N = san(b->get_name());
