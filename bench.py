@@ -33,8 +33,8 @@ sys.path.insert(0, ROOT)
 
 GRID = int(os.environ.get("TB200_BENCH_GRID", 16384))
 METRIC = "stencil_GBps"
-HEAT_NCU = "r01_heat2d_ncu_full.txt"          # committed `ncu --set full` summaries of the two sweep kernels
-BLUR_NCU = "r01_blur_f32_ncu_full_v2.txt"
+HEAT_NCU = "r02_heat2d_ncu_full.txt"          # committed `ncu --set full` summaries of the two sweep kernels
+BLUR_NCU = "r02_blur_f32_ncu_full.txt"
 UNIT = "GB/s"
 
 

@@ -88,6 +88,36 @@ def test_sgemm_tf32_random_within_tolerance(api, tensor, N, M, K):
     assert _rel_err(got, want) < TF32_RTOL
 
 
+# ------------------------------------------------------------------------------ partly filled last wave: split tiles / stream-K
+@pytest.mark.parametrize("mode,kernel,N,M,K,beta", [
+    # mode 2 (default): k-aligned split of the remainder tiles between 2..4 clusters
+    ("2", 3, 4096, 4096, 1024, 2.0), ("2", 3, 2304, 2560, 2048, 0.0), ("2", 3, 1000, 900, 4104, 2.0),
+    ("2", 2, 1024, 2048, 2048, 2.0), ("2", 2, 1000, 1000, 2056, 0.0), ("2", 3, 4096, 4096, 512, 1.0),
+    # mode 1: classic stream-K, equal contiguous runs (measured slower, kept for the record)
+    ("1", 3, 2048, 2048, 2048, 2.0), ("1", 3, 2304, 2560, 1024, 0.0), ("1", 3, 4096, 4096, 512, 2.0),
+    ("1", 3, 2000, 1900, 1000, 2.0), ("1", 2, 2048, 2048, 1024, 2.0), ("1", 2, 1500, 2300, 2056, 0.0),
+    ("1", 0, 2048, 2048, 2048, 1.0), ("1", 3, 2048, 2048, 96, 2.0)])
+def test_sgemm_split_last_wave_small_int_exact(api, tensor, monkeypatch, mode, kernel, N, M, K, beta):
+    """Persistent kernels (2: 128x256 tiles, 3: CTA pairs) when the tiles do not fill the last wave: the k-slabs of the
+    remainder tiles are shared between clusters, the tile's owner sums the others' raw accumulators in its epilogue
+    through the workspace (gemm_tc.cu: GemmParams::sk_*).  Integer operands: every partial sum is exact, so the
+    result must equal the plain product bit for bit whatever the split; twice in a row (the flags reset themselves),
+    ragged tiles, K tails, beta = 0 and a K too short to split (falls back to whole tiles)."""
+    monkeypatch.setenv("TB200_GEMM_STREAMK", mode)
+    prev = api.set_gemm_kernel(kernel)
+    try:
+        rng = np.random.default_rng(N + K)
+        A = rng.integers(-3, 4, (N, K)).astype(np.float32)
+        B = rng.integers(-3, 4, (K, M)).astype(np.float32)
+        Cm = rng.integers(-3, 4, (N, M)).astype(np.float32)
+        want = (3.0 * (A.astype(np.float64) @ B.astype(np.float64)) + beta * Cm).astype(np.float32)
+        for _ in range(2):
+            got = _sgemm(api, N, M, K, 3.0, beta, A, B, Cm)
+            assert np.array_equal(got, want)
+    finally:
+        api.set_gemm_kernel(prev)
+
+
 # ------------------------------------------------------------------------------ every tcgen05 kernel variant
 @pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 @pytest.mark.parametrize("N,M,K", [(256, 256, 32), (512, 768, 256), (1024, 1024, 1024), (300, 700, 96),

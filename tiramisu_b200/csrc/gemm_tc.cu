@@ -22,6 +22,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 using namespace tb200;
 
@@ -160,6 +162,18 @@ struct GemmParams {
                                         // is n0 (column panels arrive in order); gate_cols == 0: one wait before the first load
     int b_panel_cols = 0;               // > 0: MN-major B is stored panel-major, [N / cols][K][cols] (each column panel a
                                         // contiguous row-major matrix — what the DMA broadcast delivers); map_b is then 3-D
+    // stream-K (persistent kernels): the first sk_dp_waves * clusters tiles are whole-tile work, one per cluster and wave;
+    // the k-slabs of the remaining tiles (from tile sk_first_tile on) are cut into equal contiguous runs of sk_units per
+    // cluster.  A run that starts inside a tile is a CONTRIBUTION (raw accumulator -> sk_ws slot of the cluster, per-warp
+    // flag); the cluster whose run holds the tile's first slab OWNS it and adds the contributions in its epilogue.
+    float *sk_ws = nullptr;             // [clusters][TILE_M][256] fp32, null = plain persistent tiles
+    uint32_t *sk_flags = nullptr;       // [clusters][2 * kEpiWarps]: 1 = contribution of that warp is in place (owner resets to 0)
+    int sk_dp_waves = 0, sk_first_tile = 0, sk_units = 0, sk_total = 0;
+    // sk_split = s >= 2: k-ALIGNED split instead of contiguous runs — remainder tile r belongs to clusters [r s, r s + s), member
+    // i takes slabs [i sk_units, (i + 1) sk_units) (member 0 owns the tile).  The clusters of one k-phase still sweep K in
+    // lockstep, so concurrent tiles keep sharing their A / B slabs in L2; contiguous runs put every cluster at a different k
+    // offset and the remainder phase became HBM-bound (r02 run 21: 4096^3 2.6x slower per slab, 662 vs 693 TFLOP/s overall).
+    int sk_split = 0;
 };
 
 // F16: operands are fp16 (kind::f16, K = 16 per instruction, 64 elements per 128-byte swizzle row):
@@ -648,6 +662,33 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
         n0 = (sweep * sweep_n + (t % tiles_per_group) / gsz) * P_BN;
     };
 
+    // The work of this cluster as a sequence of segments (tile, k-slab range); every role walks the same sequence.
+    int sk_u_begin = 0, sk_u_end = 0;
+    if (p.sk_ws && p.sk_split >= 2) {
+        const int r = cluster_id / p.sk_split, i = cluster_id % p.sk_split;          // remainder tile and member
+        sk_u_begin = min(p.sk_total, r * num_kb + min(num_kb, i * p.sk_units));
+        sk_u_end = min(p.sk_total, r * num_kb + min(num_kb, (i + 1) * p.sk_units));
+    } else if (p.sk_ws) {
+        sk_u_begin = min(p.sk_total, cluster_id * p.sk_units);
+        sk_u_end = min(p.sk_total, sk_u_begin + p.sk_units);
+    }
+    auto next_segment = [&](uint32_t &i, int &u, int &tile, int &kb0, int &kb1) -> bool {
+        if (!p.sk_ws) {
+            tile = cluster_id + (int)i * num_clusters;
+            if (tile >= num_tiles) return false;
+            kb0 = 0; kb1 = num_kb; i++;
+            return true;
+        }
+        if ((int)i < p.sk_dp_waves) { tile = cluster_id + (int)i * num_clusters; kb0 = 0; kb1 = num_kb; i++; return true; }
+        if (u >= sk_u_end) return false;
+        tile = p.sk_first_tile + u / num_kb;
+        kb0 = u % num_kb;
+        kb1 = min(num_kb, kb0 + (sk_u_end - u));
+        u += kb1 - kb0;
+        i++;
+        return true;
+    };
+
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_b);
@@ -679,7 +720,9 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
         {
             uint32_t it = 0;
             uint32_t arrived = 0;                                   // highest arrival token seen so far (gated launches)
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            uint32_t seg = 0;
+            int seg_u = sk_u_begin, tile, kb0, kb1;
+            while (next_segment(seg, seg_u, tile, kb0, kb1)) {
                 int m0, n0;
                 tile_origin(tile, m0, n0);
                 if (p.gate) {
@@ -704,13 +747,13 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                 }
                 m0 += (int)cta_rank * BM;
                 n0 += (int)cta_rank * C_::B_COLS;
-                for (int kb = 0; kb < num_kb; kb++, it++) {
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     ptx::mbar_wait(&empty_bar[s], ph ^ 1);
                     if (ptx::elect_one()) {
                     // L2 prefetch of the slab `prefetch_kb` iterations ahead of the ring (same tile only)
-                    if (p.prefetch_kb && !p.b_panel_cols && kb + STAGES + p.prefetch_kb - 1 < num_kb) {
+                    if (p.prefetch_kb && !p.b_panel_cols && kb + STAGES + p.prefetch_kb - 1 < kb1) {
                         const int kp = (kb + STAGES + p.prefetch_kb - 1) * BK;
                         ptx::tma_prefetch_2d(&map_a, kp, m0);
                         if (B_MN) {
@@ -767,13 +810,14 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
             const uint64_t db0 = B_MN ? ptx::make_smem_desc(ptx::smem_u32(smem_b), p.b_lbo, p.b_sbo, ptx::kLayoutSw128Base32)
                                       : ptx::make_smem_desc(ptx::smem_u32(smem_b), 16, 1024);
             constexpr uint32_t kStepA = UMMA_K * 4, kStepB = B_MN ? UMMA_K * 128 : UMMA_K * 4;
-            uint32_t it = 0, local = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
+            uint32_t it = 0, local = 0, seg = 0;
+            int seg_u = sk_u_begin, tile, kb0, kb1;
+            for (; next_segment(seg, seg_u, tile, kb0, kb1); local++) {
                 const uint32_t buf = local & 1;
                 ptx::mbar_wait(&tmem_empty[buf], ((local >> 1) & 1) ^ 1);      // epilogue drained this buffer
                 ptx::tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + buf * P_BN;
-                for (int kb = 0; kb < num_kb; kb++, it++) {
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     ptx::mbar_wait(&full_bar[s], ph);
@@ -785,13 +829,13 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                         for (int k = 0; k < BK / UMMA_K; k++) {
                             if (CG == 2)
                                 ptx::mma_tf32_ss_cg2(d_tmem, ptx::desc_advance(da, k * kStepA),
-                                                     ptx::desc_advance(db, k * kStepB), idesc, (kb | k) != 0);
+                                                     ptx::desc_advance(db, k * kStepB), idesc, ((kb - kb0) | k) != 0);
                             else
                                 ptx::mma_tf32_ss(d_tmem, ptx::desc_advance(da, k * kStepA),
-                                                 ptx::desc_advance(db, k * kStepB), idesc, (kb | k) != 0);
+                                                 ptx::desc_advance(db, k * kStepB), idesc, ((kb - kb0) | k) != 0);
                         }
                         if (CG == 2) ptx::mma_commit_cg2(&empty_bar[s], 3); else ptx::mma_commit(&empty_bar[s]);
-                        if (kb == num_kb - 1) {
+                        if (kb == kb1 - 1) {
                             if (CG == 2) ptx::mma_commit_cg2(&tmem_full[buf], 3); else ptx::mma_commit(&tmem_full[buf]);
                         }
                     }
@@ -804,14 +848,49 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;              // which 128 of the 256 accumulator columns
         const bool use_c = p.beta != 0.0f;
-        uint32_t local = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, local++) {
+        uint32_t local = 0, seg = 0;
+        int seg_u = sk_u_begin, tile, kb0, kb1;
+        const int wslot = (int)cta_rank * kEpiWarps + (warp - 2);             // this warp's flag / position inside a cluster
+        for (; next_segment(seg, seg_u, tile, kb0, kb1); local++) {
             const uint32_t buf = local & 1;
             int m0, n0;
             tile_origin(tile, m0, n0);
             const int row = m0 + (int)cta_rank * BM + q * 32 + lane;
             const bool row_ok = row < p.M;
             float *crow = p.C + (size_t)row * p.ldC;
+            const int ws_row = (int)cta_rank * BM + q * 32 + lane;              // row inside the cluster's 256-column slot
+            if (kb0 > 0) {
+                // ---- stream-K contribution: the run started inside this tile; leave the raw accumulator in this cluster's
+                // workspace slot for the owner (the same warp position there reads exactly what this warp writes)
+                float *wrow = p.sk_ws + ((size_t)cluster_id * TILE_M + ws_row) * P_BN;
+                ptx::mbar_wait(&tmem_full[buf], (local >> 1) & 1);
+                ptx::tc_fence_after_sync();
+#pragma unroll 1
+                for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * P_BN + (uint32_t)c0, r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(wrow + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
+                ptx::tc_fence_before_sync();
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sk_flags + (size_t)cluster_id * (2 * kEpiWarps) + wslot), "r"(1u) : "memory");
+                    if (CG == 2) ptx::mbar_arrive_remote(&tmem_empty[buf], 0);
+                    else ptx::mbar_arrive(&tmem_empty[buf]);
+                }
+                continue;
+            }
+            // owner of a tile other clusters continue: their contributions are added below (clusters c+1 .. sk_last)
+            int sk_last = cluster_id;
+            if (p.sk_ws && kb1 < num_kb)
+                sk_last = p.sk_split >= 2 ? cluster_id + (num_kb - 1) / p.sk_units
+                                          : min(num_clusters - 1, ((tile - p.sk_first_tile + 1) * num_kb - 1) / p.sk_units);
             // beta*C does not depend on the MMAs: fetch each 32-column chunk one iteration ahead, the
             // first one before waiting for the accumulator (matters for the last tile of a CTA,
             // whose epilogue nothing overlaps)
@@ -827,6 +906,18 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
             load_c(half * 128, cnext);
             ptx::mbar_wait(&tmem_full[buf], (local >> 1) & 1);
             ptx::tc_fence_after_sync();
+            for (int c = cluster_id + 1; c <= sk_last; c++) {       // this warp's counterpart in every contributing cluster is done
+                if (lane == 0) {
+                    const uint32_t *f = p.sk_flags + (size_t)c * (2 * kEpiWarps) + wslot;
+                    const long long t0 = clock64();
+                    uint32_t v;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                        if (clock64() - t0 > (1ll << 32)) __trap();
+                    } while (v == 0);
+                }
+                __syncwarp();
+            }
 #pragma unroll 1
             for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
                 float4 ccur[8];
@@ -837,6 +928,17 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
                 __syncwarp();
                 ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * P_BN + (uint32_t)c0, r);
                 ptx::tmem_ld_wait();
+                for (int c = cluster_id + 1; c <= sk_last; c++) {   // partial sums in a fixed order: owner, then c+1, c+2, ...
+                    const float *wrow = p.sk_ws + ((size_t)c * TILE_M + ws_row) * P_BN + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 w = __ldcg(reinterpret_cast<const float4 *>(wrow + j));
+                        r[j + 0] = __float_as_uint(__fadd_rn(__uint_as_float(r[j + 0]), w.x));
+                        r[j + 1] = __float_as_uint(__fadd_rn(__uint_as_float(r[j + 1]), w.y));
+                        r[j + 2] = __float_as_uint(__fadd_rn(__uint_as_float(r[j + 2]), w.z));
+                        r[j + 3] = __float_as_uint(__fadd_rn(__uint_as_float(r[j + 3]), w.w));
+                    }
+                }
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -872,6 +974,8 @@ tiramisu_sm100_gemm_tf32_persistent(const __grid_constant__ CUtensorMap map_a,
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) {
+                for (int c = cluster_id + 1; c <= sk_last; c++)      // consumed: the flags are 0 again when the kernel ends
+                    p.sk_flags[(size_t)c * (2 * kEpiWarps) + wslot] = 0u;
                 if (CG == 2) ptx::mbar_arrive_remote(&tmem_empty[buf], 0);
                 else ptx::mbar_arrive(&tmem_empty[buf]);
             }
@@ -1032,6 +1136,28 @@ int launch_tc_f16(const void *A, const void *B, float *C, int M, int N, int K, f
     return post_launch("tiramisu_sm100_gemm_f16");
 }
 
+// Stream-K workspace: one fp32 slot of TILE_M x 256 per cluster + one flag per epilogue warp and cluster, per (thread, stream)
+// — launches on one stream are ordered, launches on different streams must not share slots.  Flags are 0 between launches.
+struct StreamKWorkspace { float *partial = nullptr; uint32_t *flags = nullptr; int clusters = 0, tile_m = 0; };
+StreamKWorkspace *streamk_workspace(cudaStream_t st, int clusters, int tile_m)
+{
+    static thread_local std::vector<std::pair<cudaStream_t, StreamKWorkspace>> *all = new std::vector<std::pair<cudaStream_t, StreamKWorkspace>>();
+    for (auto &e : *all)
+        if (e.first == st && e.second.clusters >= clusters && e.second.tile_m >= tile_m) return &e.second;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }   // no allocation inside a capture
+    StreamKWorkspace w;
+    w.clusters = clusters; w.tile_m = tile_m;
+    const size_t bytes = (size_t)clusters * tile_m * P_BN * 4, fbytes = (size_t)clusters * 2 * kEpiWarps * 4;
+    if (cudaMalloc(&w.partial, bytes) != cudaSuccess || cudaMalloc(&w.flags, fbytes) != cudaSuccess || cudaMemset(w.flags, 0, fbytes) != cudaSuccess) {
+        cudaGetLastError();
+        if (w.partial) cudaFree(w.partial);
+        return nullptr;
+    }
+    all->push_back({st, w});
+    return &all->back().second;
+}
+
 template <int CG, bool B_MN>
 int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N, int K, float alpha, float beta,
                          int64_t ldA, int64_t ldB, int64_t ldC)
@@ -1082,7 +1208,37 @@ int launch_tc_persistent(const float *A, const float *B, float *C, int M, int N,
     }
     const int num_tiles = p.num_m * p.num_n;
     int clusters = sm_count() / CG;
-    if (clusters > num_tiles) clusters = num_tiles;
+    // The last, partly filled wave: with T tiles on P clusters it holds T mod P tiles (4096^3: 256 = 3 waves + 34) and the
+    // kernel lasts ceil(T / P) tile times.  When at least two clusters are free per remainder tile, the k-slabs of each
+    // remainder tile are split between s = min(4, P / rem) clusters (GemmParams::sk_split: k-aligned, the clusters of one
+    // k-phase stay in lockstep); member 0 owns the tile and adds the others' raw accumulators in its epilogue through one
+    // workspace slot per cluster.  TB200_GEMM_STREAMK=0: off; =1: classic stream-K (equal contiguous runs over all remainder
+    // slabs; measured slower, see GemmParams) — kept for the record and for its parity tests.
+    const int num_kb = (K + BK - 1) / BK;
+    const int rem = num_tiles % clusters;
+    int sk_mode = 2;
+    if (const char *e = getenv("TB200_GEMM_STREAMK")) sk_mode = atoi(e);
+    if (getenv("TB200_GEMM_NO_STREAMK")) sk_mode = 0;
+    int split = rem ? clusters / rem : 0;
+    if (split > 4) split = 4;
+    bool streamk = false;
+    if (!p.gate && rem != 0 && sk_mode == 1)
+        streamk = (int64_t)rem * num_kb >= (int64_t)clusters * 16 && (num_tiles < clusters ? rem * 10 < clusters * 9 + clusters / 2 : true);
+    else if (!p.gate && rem != 0 && sk_mode == 2)
+        streamk = split >= 2 && num_kb >= 16 * split;
+    if (streamk) {
+        StreamKWorkspace *ws = streamk_workspace(stream(), clusters, BM * CG);
+        if (!ws) streamk = false;
+        else {
+            p.sk_ws = ws->partial; p.sk_flags = ws->flags;
+            p.sk_dp_waves = num_tiles / clusters;
+            p.sk_first_tile = p.sk_dp_waves * clusters;
+            p.sk_total = rem * num_kb;
+            if (sk_mode == 2) { p.sk_split = split; p.sk_units = (num_kb + split - 1) / split; }
+            else p.sk_units = (p.sk_total + clusters - 1) / clusters;
+        }
+    }
+    if (!streamk && clusters > num_tiles) clusters = num_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(clusters * CG));
     cfg.blockDim = dim3(kThreadsP);

@@ -63,9 +63,9 @@ def main():
             variants = [{"TB200_GEMM_KERNEL": "1"}, {"TB200_GEMM_KERNEL": "4", "TB200_GEMM_NO_PDL": "1"}, {"TB200_GEMM_KERNEL": "4"},
                         {"TB200_GEMM_KERNEL": "4", "TB200_GEMM_PREFETCH": "16"}, {}]
         else:
-            variants = [{}, {"TB200_GEMM_KERNEL": "2"}, {"TB200_GEMM_PREFETCH": "8"}]
+            variants = [{}, {"TB200_GEMM_STREAMK": "0"}, {"TB200_GEMM_STREAMK": "1"}, {"TB200_GEMM_KERNEL": "2"}]
         for env in variants:
-            for k in ("TB200_GEMM_KERNEL", "TB200_GEMM_PREFETCH", "TB200_GEMM_NO_PDL"):
+            for k in ("TB200_GEMM_KERNEL", "TB200_GEMM_PREFETCH", "TB200_GEMM_NO_PDL", "TB200_GEMM_STREAMK"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             ms = timed(stream, fn, 30 if n <= 2048 else 10)
@@ -79,7 +79,7 @@ def main():
             print(json.dumps(rec), flush=True)
         # warm-L2 number for the small sizes (one operand set): what a caller that re-uses operands sees
         if nsets > 1:
-            for k in ("TB200_GEMM_KERNEL", "TB200_GEMM_PREFETCH", "TB200_GEMM_NO_PDL"):
+            for k in ("TB200_GEMM_KERNEL", "TB200_GEMM_PREFETCH", "TB200_GEMM_NO_PDL", "TB200_GEMM_STREAMK"):
                 os.environ.pop(k, None)
             a, b, c = sets[0]
             ms = timed(stream, lambda: api.cublas_sgemm(a.data_ptr(), b.data_ptr(), c.data_ptr(), n, n, n, 3.0, 2.0), 30)
