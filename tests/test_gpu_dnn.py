@@ -195,7 +195,8 @@ def test_lstm_tensor_path(api, F, B, L, T, scale):
 @pytest.mark.parametrize("kernel", [1, 2, 3, 4])
 @pytest.mark.parametrize("F,B,L,T,scale", [(64, 16, 2, 6, 4.0), (256, 100, 2, 5, 8.0), (128, 64, 3, 20, 8.0),
                                            (1024, 64, 2, 6, 32.0), (256, 48, 2, 7, 8.0), (512, 64, 2, 5, 16.0),
-                                           (384, 5, 1, 4, 8.0), (1024, 64, 4, 23, 32.0), (128, 64, 5, 37, 8.0)])
+                                           (384, 5, 1, 4, 8.0), (1024, 64, 4, 23, 32.0), (128, 64, 5, 37, 8.0),
+                                           (256, 33, 3, 9, 8.0), (512, 40, 4, 12, 16.0)])
 def test_lstm_recurrence_engines(api, kernel, F, B, L, T, scale):
     """Per-cell launches (1), the N-split persistent layer kernel (2: weights resident in shared
     memory, cell state in registers, device-wide step barrier, multicast ring), the TF32 K-split
@@ -235,12 +236,16 @@ def test_lstm_engines_agree_full_width(api):
 _CFG4 = {}
 
 
-@pytest.mark.parametrize("pipe", ["0", "1"])
-def test_lstm_fp16_engine_config4(api, pipe, monkeypatch):
-    """BASELINE config 4 (F=1024, B=64, L=4, T=100) through the fp16 engine, one layer at a time and
-    with layer pairs overlapped: both must match the oracle and each other bit for bit (the
-    overlap changes the schedule, not the arithmetic)."""
+@pytest.mark.parametrize("pipe,split,roll", [("0", "1", "1"), ("1", "1", "1"), ("1", "0", "0"), ("1", "1", "0"), ("0", "0", "0"),
+                                             ("1", "0", "1")])
+def test_lstm_fp16_engine_config4(api, pipe, split, roll, monkeypatch):
+    """BASELINE config 4 (F=1024, B=64, L=4, T=100) through the fp16 engine: one layer at a time, layer pairs
+    overlapped, the rolling pipeline over all layers (TB200_LSTM_ROLL), and with / without the two half-batch
+    pipelines per CTA (TB200_LSTM_SPLIT): all must match the oracle and each other bit for bit (the overlap and the
+    split change the schedule, not the arithmetic)."""
     monkeypatch.setenv("TB200_LSTM_PIPE", pipe)
+    monkeypatch.setenv("TB200_LSTM_SPLIT", split)
+    monkeypatch.setenv("TB200_LSTM_ROLL", roll)
     W, b, x = refdata.lstm_inputs(1024, 64, 4, 100, scale=32.0)
     prev_m, prev_k = api.set_lstm_mode(2), api.set_lstm_kernel(4)
     try:
@@ -253,7 +258,7 @@ def test_lstm_fp16_engine_config4(api, pipe, monkeypatch):
     if "want" not in _CFG4:
         _CFG4["want"] = oracle.lstm(W, b, x)
     want = _CFG4["want"]
-    assert_lstm_tf32_close(got, want, f"config 4, pipe={pipe}")
+    assert_lstm_tf32_close(got, want, f"config 4, pipe={pipe} split={split} roll={roll}")
     if "got" in _CFG4:
         assert np.array_equal(_CFG4["got"], got)
     _CFG4["got"] = got
