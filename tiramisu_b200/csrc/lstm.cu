@@ -716,7 +716,12 @@ struct H16Params {
     const uint32_t *xg_ready;   // null, or: number of leading time steps of xg that are complete
     int dbg;
     unsigned long long *trace;
+    const __half *r16;          // non-null: R16 [4F][F] — the CTA's R slice lives in TENSOR MEMORY (A operand of the MMAs read
+                                // from TMEM columns [H_A_COL0, +F/4)) instead of shared memory: the step's MMA phase is bound
+                                // by operand bytes through the shared-memory port (~88 B/clk measured, r02 run 22), and R is
+                                // 2/3 of them
 };
+constexpr uint32_t H_A_COL0 = 128;     // first TMEM column of the R slice (accumulator: columns [0, 64))
 
 // Every CTA of the layer has published step `target`: lane i watches the flags of CTAs i, i + 32, ...
 // (relaxed polls; one acquire fence once all of them have been seen).  Whole warp, converged.
@@ -774,13 +779,13 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
         if (lane == 0) {
             ptx::mbar_init(&full_bar[0], 1);
             ptx::mbar_init(&full_bar[1], 1);
-            ptx::mbar_init(r_bar, 1);
+            ptx::mbar_init(r_bar, p.r16 ? 256 : 1);     // TMEM-resident R: every epilogue thread arrives after its tcgen05.st
             ptx::mbar_init(tmem_full, 1);
             ptx::mbar_init(recv_bar, 1 + 128);          // expect_tx arrival + the 128 lanes that fill the local half
             ptx::fence_barrier_init();
         }
         __syncwarp();
-        ptx::tmem_alloc(tmem_slot, 64);
+        ptx::tmem_alloc(tmem_slot, p.r16 ? 512 : 64);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before_sync();
@@ -790,7 +795,7 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (ptx::elect_one()) {
+        if (!p.r16 && ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(r_bar, (uint32_t)KB * 16384u);
             for (int kb = 0; kb < KB; kb++)
                 ptx::tma_load_2d(smem_r + kb * 16384, &map_r, r_bar, k_base + kb * 64, 128 * j);
@@ -821,6 +826,7 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
         constexpr uint32_t idesc = ptx::make_idesc_f16(128, 64, false, false);
         const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_r), 16, 1024);
         const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_h), 16, 1024);
+        const uint32_t a_tmem = p.r16 ? tmem_base + H_A_COL0 : 0u;
         ptx::mbar_wait(r_bar, 0);
         ptx::tc_fence_after_sync();
         for (int t = 1; t < p.T; t++) {
@@ -832,9 +838,10 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
                 for (int kb = 0; kb < half; kb++) {
                     const uint64_t da = ptx::desc_advance(da0, (uint32_t)kb * 16384u), db = ptx::desc_advance(db0, (uint32_t)kb * 8192u);
 #pragma unroll
-                    for (int k = 0; k < 4; k++)                  // 4 x (K = 16 fp16 = 32 bytes) per 128-byte row
-                        ptx::mma_f16_ss(tmem_base, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc,
-                                        (kb | k) != 0);
+                    for (int k = 0; k < 4; k++) {                // 4 x (K = 16 fp16 = 32 bytes = 8 TMEM columns) per 128-byte row
+                        if (a_tmem) ptx::mma_f16_ts(tmem_base, a_tmem + (uint32_t)(kb * 32 + k * 8), ptx::desc_advance(db, k * 32), idesc, (kb | k) != 0);
+                        else ptx::mma_f16_ss(tmem_base, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc, (kb | k) != 0);
+                    }
                 }
                 if (KB == half) ptx::mma_commit(tmem_full);
             }
@@ -846,8 +853,10 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
                     for (int kb = half; kb < KB; kb++) {
                         const uint64_t da = ptx::desc_advance(da0, (uint32_t)kb * 16384u), db = ptx::desc_advance(db0, (uint32_t)kb * 8192u);
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            ptx::mma_f16_ss(tmem_base, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc, true);
+                        for (int k = 0; k < 4; k++) {
+                            if (a_tmem) ptx::mma_f16_ts(tmem_base, a_tmem + (uint32_t)(kb * 32 + k * 8), ptx::desc_advance(db, k * 32), idesc, true);
+                            else ptx::mma_f16_ss(tmem_base, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc, true);
+                        }
                     }
                     ptx::mma_commit(tmem_full);
                 }
@@ -881,6 +890,24 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
         const uint32_t sw_w = (row_l & 7u) ^ (((row_l >> 4) & 3u) << 1);
         const uint32_t push_addr = ptx::mapa_u32(reinterpret_cast<uint8_t *>(recv) + ks * 16384u + row_l * 256u, dst_cta);
         const uint32_t push_bar = ptx::mapa_u32(recv_bar, dst_cta);
+        if (p.r16) {
+            // R slice -> tensor memory: this thread's TMEM lane is gate row (32 q + lane) of the cluster's 128; warp pair
+            // (q, ch) splits the K slice's columns in two.  32 columns = 64 fp16 = 128 bytes of the row per tcgen05.st.
+            const __half *rrow = p.r16 + (size_t)(128 * j + 32 * (int)q + lane) * p.F + k_base;
+            const int c_lo = ch == 0 ? 0 : 32 * half, c_hi = ch == 0 ? 32 * half : 32 * KB;       // k-blocks [0, half) / [half, KB)
+            for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+                uint32_t w[32];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(rrow + 2 * c0) + i);
+                    w[4 * i + 0] = v4.x; w[4 * i + 1] = v4.y; w[4 * i + 2] = v4.z; w[4 * i + 3] = v4.w;
+                }
+                ptx::tmem_st_32x32(tmem_base + ((q * 32u) << 16) + H_A_COL0 + (uint32_t)c0, w);
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before_sync();
+            ptx::mbar_arrive(r_bar);
+        }
         uint32_t ready = p.xg_ready ? 0u : 0xffffffffu;
         for (int t = 0; t < p.T; t++) {
             if ((uint32_t)t >= ready) {
@@ -985,234 +1012,7 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
     ptx::cluster_sync();                                     // nobody exits while the peer may still push into it
     if (warp == 1) {
         ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem_base, 64);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same engine with the batch cut in two INDEPENDENT half-batch pipelines per CTA (B > 32).  A step of the
-// recurrence is a chain of fixed latencies (publish -> counter seen -> TMA -> MMA -> DSMEM reduction -> gates,
-// ~5.9 us of which the tensor core works ~1 us), and the cells of different batch entries do not depend on each
-// other: half g = batch entries [32 g, 32 g + 32) gets its own producer warp, MMA warp, four epilogue warps,
-// TMEM columns [32 g, +32), receive buffer, mbarriers, named barrier and device-wide step counter, so while
-// half 0 waits for its h[t] to travel, half 1 computes, and the other way round.  R (the A operand) is shared.
-// Every mechanism is the one of tiramisu_sm100_lstm_layer_h16 above, instantiated twice with N = 32.
-constexpr int H2_THREADS = 128 + 256;              // warps 0,1: TMA producers; 2,3: MMA issuers; 4..11: epilogue (4 per half)
-
-__global__ void __launch_bounds__(H2_THREADS, 1)
-tiramisu_sm100_lstm_layer_h16x2(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_r,
-                                const H16Params p)
-{
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int KB = p.F / (H_CL * 64);                        // 64-element (128-byte) k-blocks per K slice (<= 8)
-    uint8_t *smem_r = smem;                                  // KB x [128 rows][64 k] fp16 (16 KB each)
-    uint8_t *smem_h = smem_r + (size_t)KB * 16384;           // [half g][KB] x [32 rows][64 k] fp16 (4 KB each)
-    float *recv = reinterpret_cast<float *>(smem_h + (size_t)KB * 8192);        // [half g][src CTA][gate row 64][batch 32]
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(recv) + H_RECV_BYTES);   // [2]: per half
-    uint64_t *r_bar = full_bar + 2;
-    uint64_t *tmem_full = r_bar + 1;                         // [2]
-    uint64_t *recv_bar = tmem_full + 2;                      // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(recv_bar + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ks = ptx::cluster_ctarank();              // K slice of this CTA = its rank in the cluster
-    const int j = blockIdx.x / H_CL;                         // gate-row group of the cluster
-    const int k_base = (int)ks * (p.F / H_CL);
-
-    if (warp == 0 && lane == 0) { ptx::prefetch_tensormap(&map_h); ptx::prefetch_tensormap(&map_r); }
-    if (warp == 2) {
-        if (lane == 0) {
-            for (int g = 0; g < 2; g++) {
-                ptx::mbar_init(&full_bar[g], 1);
-                ptx::mbar_init(&tmem_full[g], 1);
-                ptx::mbar_init(&recv_bar[g], 1 + 64);   // expect_tx arrival + the 64 lanes that fill the local half
-            }
-            ptx::mbar_init(r_bar, 1);
-            ptx::fence_barrier_init();
-        }
-        __syncwarp();
-        ptx::tmem_alloc(tmem_slot, 64);
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before_sync();
-    ptx::cluster_sync();                                     // the peer's barriers exist before any remote store
-    ptx::tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp < 2) {
-        // ===== TMA producer of half g =====
-        const int g = warp;
-        uint32_t *ctr = p.step_flags + 32 * g;
-        if (g == 0) {
-            if (ptx::elect_one()) {
-                ptx::mbar_arrive_expect_tx(r_bar, (uint32_t)KB * 16384u);
-                for (int kb = 0; kb < KB; kb++)
-                    ptx::tma_load_2d(smem_r + kb * 16384, &map_r, r_bar, k_base + kb * 64, 128 * j);
-            }
-            __syncwarp();
-        }
-        uint8_t *dst = smem_h + (size_t)g * KB * 4096;
-        for (int t = 1; t < p.T; t++) {
-            if (!(p.dbg & 1)) grid_wait_relaxed(ctr, (uint32_t)gridDim.x * (uint32_t)t);          // h16[t-1][half g] is complete
-            ptx::fence_proxy_async_all();
-            if (ptx::elect_one()) {
-                if (g == 0) KS_TRACE(0);
-                ptx::mbar_arrive_expect_tx(&full_bar[g], (uint32_t)KB * 4096u);
-                for (int kb = 0; kb < KB; kb++)
-                    ptx::tma_load_3d(dst + kb * 4096, &map_h, &full_bar[g], k_base + kb * 64, 32 * g, t - 1);
-            }
-            __syncwarp();
-        }
-    } else if (warp < 4) {
-        // ===== MMA issuer of half g: D[128 gate rows][32 batch] in TMEM columns [32 g, +32) =====
-        const int g = warp - 2;
-        constexpr uint32_t idesc = ptx::make_idesc_f16(128, 32, false, false);
-        const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_r), 16, 1024);
-        const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_h + (size_t)g * KB * 4096), 16, 1024);
-        const uint32_t d_tmem = tmem_base + 32u * (uint32_t)g;
-        ptx::mbar_wait(r_bar, 0);
-        ptx::tc_fence_after_sync();
-        for (int t = 1; t < p.T; t++) {
-            ptx::mbar_wait(&full_bar[g], (uint32_t)(t - 1) & 1u);
-            ptx::tc_fence_after_sync();
-            if (ptx::elect_one()) {
-                if (g == 0) KS_TRACE(1);
-                for (int kb = 0; kb < KB; kb++) {
-                    const uint64_t da = ptx::desc_advance(da0, (uint32_t)kb * 16384u), db = ptx::desc_advance(db0, (uint32_t)kb * 4096u);
-#pragma unroll
-                    for (int k = 0; k < 4; k++)                  // 4 x (K = 16 fp16 = 32 bytes) per 128-byte row
-                        ptx::mma_f16_ss(d_tmem, ptx::desc_advance(da, k * 32), ptx::desc_advance(db, k * 32), idesc, (kb | k) != 0);
-                }
-                ptx::mma_commit(&tmem_full[g]);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===== epilogue of half g: 4 warps, 128 threads = 32 batch entries x 4 groups of 4 hidden units =====
-        const uint32_t q = (uint32_t)warp & 3u;            // TMEM lane quarter this warp may read
-        const int g = (warp - 4) >> 2;                     // batch half
-        const uint32_t dst_cta = q >> 1;                   // gate rows [64 dst, +64) are finalised by CTA dst
-        const int e = (warp - 4 - 4 * g) * 32 + lane;      // 0..127 inside the half
-        const int ug = e & 3;                              // which 4 of the CTA's 16 hidden units
-        const int bl = e >> 2;                             // batch entry inside the half
-        const int b = 32 * g + bl;
-        const bool ok = b < p.B;
-        const int p0 = 128 * j + 64 * (int)ks + 16 * ug;           // first packed gate column of this thread
-        const int u0 = 32 * j + 16 * (int)ks + 4 * ug;             // first hidden unit of this thread
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        float4 bs[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) bs[u] = __ldg(reinterpret_cast<const float4 *>(p.bias + p0) + u);
-        const float rs = __ldg(p.rscale);
-        float *recv_g = recv + g * 4096;                   // [src 2][row 64][batch 32]
-        // where this warp's TMEM rows go: CTA dst, slot [src = ks][row = 32 (q & 1) + lane][32 batch entries = 8 chunks]
-        const uint32_t row_l = 32u * (q & 1u) + (uint32_t)lane;
-        // 16-byte chunk cc of gate row r lives at chunk cc ^ s(r), s(r) = (r & 7) ^ (((r >> 4) & 3) << 1): conflict-free
-        // for the row-per-lane writers and for the readers (lanes = 4 unit groups x 8 batch entries -> rows 16 apart)
-        const uint32_t sw_w = (row_l & 7u) ^ (((row_l >> 4) & 3u) << 1);
-        const uint32_t push_addr = ptx::mapa_u32(reinterpret_cast<uint8_t *>(recv_g) + ks * 8192u + row_l * 128u, dst_cta);
-        const uint32_t push_bar = ptx::mapa_u32(&recv_bar[g], dst_cta);
-        uint32_t *ctr = p.step_flags + 32 * g;
-        uint32_t ready = p.xg_ready ? 0u : 0xffffffffu;
-        for (int t = 0; t < p.T; t++) {
-            if ((uint32_t)t >= ready) {
-                uint32_t v = 0;
-                if (lane == 0) {
-                    const long long t0 = clock64();
-                    while ((v = ptx::ld_acquire_gpu(p.xg_ready)) <= (uint32_t)t) {
-                        if (clock64() - t0 > (1ll << 32)) __trap();
-                        __nanosleep(200);
-                    }
-                }
-                ready = __shfl_sync(0xffffffffu, v, 0);
-            }
-            float4 xg[4];
-            if (ok) {
-                const float4 *xp = reinterpret_cast<const float4 *>(p.xg + ((size_t)t * p.B + b) * 4 * p.F + p0);
-#pragma unroll
-                for (int u = 0; u < 4; u++) xg[u] = __ldcg(xp + u);
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; u++) xg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            float acc[16];
-#pragma unroll
-            for (int a = 0; a < 16; a++) acc[a] = 0.0f;
-            if (t > 0) {
-                if (e == 0) ptx::mbar_arrive_expect_tx(&recv_bar[g], (uint32_t)H_RECV_BYTES / 4);     // the peer's 64 rows x 128 B
-                ptx::mbar_wait(&tmem_full[g], (uint32_t)(t - 1) & 1u);
-                ptx::tc_fence_after_sync();
-                if (e == 0 && g == 0) KS_TRACE(3);
-                uint32_t v[32];
-                __syncwarp();
-                ptx::tmem_ld_32x32_nowait(tmem_base + ((q * 32u) << 16) + 32u * (uint32_t)g, v);
-                ptx::tmem_ld_wait();
-                ptx::tc_fence_before_sync();
-                if (dst_cta == ks) {
-                    float4 *lp = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(recv_g) + ks * 8192u + row_l * 128u);
-#pragma unroll
-                    for (int cc = 0; cc < 8; cc++)
-                        lp[(uint32_t)cc ^ sw_w] = make_float4(__uint_as_float(v[4 * cc + 0]), __uint_as_float(v[4 * cc + 1]),
-                                                              __uint_as_float(v[4 * cc + 2]), __uint_as_float(v[4 * cc + 3]));
-                    ptx::mbar_arrive(&recv_bar[g]);
-                } else {
-#pragma unroll
-                    for (int cc = 0; cc < 8; cc++)
-                        ptx::st_async_cluster_v4(push_addr + ((uint32_t)cc ^ sw_w) * 16u, push_bar,
-                                                 __uint_as_float(v[4 * cc + 0]), __uint_as_float(v[4 * cc + 1]),
-                                                 __uint_as_float(v[4 * cc + 2]), __uint_as_float(v[4 * cc + 3]));
-                }
-                if (e == 0 && g == 0) KS_TRACE(4);
-                ptx::mbar_wait(&recv_bar[g], (uint32_t)(t - 1) & 1u);
-                if (e == 0 && g == 0) KS_TRACE(5);
-#pragma unroll
-                for (int a = 0; a < 16; a++) {
-                    const int row = 16 * ug + a;
-                    const int col = ((((bl >> 2) ^ (row & 7) ^ (ug << 1)) << 2) | (bl & 3));
-                    acc[a] = (recv_g[0 * 2048 + row * 32 + col] + recv_g[1 * 2048 + row * 32 + col]) * rs;
-                }
-            }
-            float hn[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const float si = acc[4 * u + 0] + xg[u].x + bs[u].x;
-                const float sz = acc[4 * u + 1] + xg[u].y + bs[u].y;
-                const float so = acc[4 * u + 2] + xg[u].z + bs[u].z;
-                const float sf = acc[4 * u + 3] + xg[u].w + bs[u].w;
-                const float gi = sigmoid_fast(si), gz = ptx::tanh_approx(sz), go = sigmoid_fast(so), gf = sigmoid_fast(sf);
-                c[u] = gi * gz + gf * c[u];
-                hn[u] = ptx::tanh_approx(c[u]) * go;
-            }
-            if (ok) {
-                const size_t o = ((size_t)t * p.B + b) * p.F + u0;
-                if (p.h) *reinterpret_cast<float4 *>(p.h + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                if (p.c_out && t == p.T - 1) *reinterpret_cast<float4 *>(p.c_out + (size_t)b * p.F + u0) = make_float4(c[0], c[1], c[2], c[3]);
-                const __half2 lo = __floats2half2_rn(hn[0], hn[1]), hi = __floats2half2_rn(hn[2], hn[3]);
-                uint2 pk;
-                pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-                pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-                *reinterpret_cast<uint2 *>(p.h16 + o) = pk;
-            }
-            // publish h[t] of this half: rendezvous of its 128 writers (also: every reader is done with recv_g before
-            // the next step's pushes are triggered), then ONE gpu-scope fence + the half's own counter
-            if (e == 0 && g == 0) KS_TRACE(6);
-            if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-            else asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (e == 0) {
-                if (g == 0) KS_TRACE(2);
-                ptx::fence_acq_rel_gpu();
-                ptx::red_relaxed_gpu_add(ctr, 1u);
-                if (g == 0) KS_TRACE(7);
-            }
-        }
-    }
-
-    ptx::tc_fence_before_sync();
-    ptx::cluster_sync();                                     // nobody exits while the peer may still push into it
-    if (warp == 2) {
-        ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem_base, 64);
+        ptx::tmem_dealloc(tmem_base, p.r16 ? 512 : 64);
     }
 }
 
@@ -1294,10 +1094,9 @@ tiramisu_sm100_lstm_pack16(const float *__restrict__ Wl, const float *__restrict
 __global__ void tiramisu_sm100_wait_counter(const uint32_t *flags, int n, uint32_t step, int sync_mode)
 {
     // returns once all n CTAs of the layer have published `step` steps (same three encodings as H16Params::sync_mode)
-    // sync_mode 3 (h16x2 kernel): one counter per batch half, 128 bytes apart, each += n per finished step
-    const int words = sync_mode == 1 ? n : (sync_mode == 2 ? 8 : (sync_mode == 3 ? 2 : 1));
+    const int words = sync_mode == 1 ? n : (sync_mode == 2 ? 8 : 1);
     for (int c = threadIdx.x; c < words; c += blockDim.x) {
-        const uint32_t *w = sync_mode == 2 || sync_mode == 3 ? flags + 32 * c : flags + c;
+        const uint32_t *w = sync_mode == 2 ? flags + 32 * c : flags + c;
         const uint32_t target = sync_mode == 1 ? step : (sync_mode == 2 ? (uint32_t)((n - c + 7) / 8) * step : (uint32_t)n * step);
         const long long t0 = clock64();
         while (ptx::ld_acquire_gpu(w) < target) {
@@ -1314,7 +1113,6 @@ __global__ void tiramisu_sm100_publish(uint32_t *flag, uint32_t value)
 
 std::atomic<int> g_lstm_mode{0};
 std::atomic<int> g_lstm_kernel{0};
-thread_local bool t_last_split = false;          // ... and whether it ran the two-half-batch form of the fp16 kernel
 thread_local const char *t_last_engine = "";     // which recurrence engine the calling thread's last tiramisu_b200_lstm used
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -1510,41 +1308,18 @@ bool h16_ok(int F, int B, bool *pair_ok)
     return cached_clusters * H_CL >= need;
 }
 
-// The half-batch-pipelined kernel: same shared memory, 384 threads; co-residency of `need` CTAs checked once per F.
-bool h16x2_ok(int F, int need)
-{
-    static int cached_F = 0, cached_clusters = 0;
-    if (cached_F != F) {
-        auto kern = tiramisu_sm100_lstm_layer_h16x2;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        cudaLaunchAttribute attr[1];
-        cudaLaunchConfig_t cfg = h16_config(F, attr, nullptr);
-        cfg.blockDim = dim3(H2_THREADS);
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
-        cached_F = F;
-        cached_clusters = n;
-    }
-    return cached_clusters * H_CL >= need;
-}
-
 // Auxiliary streams + events of the layer pipeline, one set per host thread.
 struct PipeStreams {
-    cudaStream_t rec = nullptr, gemm = nullptr, gemm2 = nullptr;
-    cudaEvent_t fork = nullptr, join_rec = nullptr, join_gemm = nullptr, join_gemm2 = nullptr;
+    cudaStream_t rec = nullptr, gemm = nullptr;
+    cudaEvent_t fork = nullptr, join_rec = nullptr, join_gemm = nullptr;
     bool ok = false;
     PipeStreams()
     {
         ok = cudaStreamCreateWithFlags(&rec, cudaStreamNonBlocking) == cudaSuccess &&
              cudaStreamCreateWithFlags(&gemm, cudaStreamNonBlocking) == cudaSuccess &&
-             cudaStreamCreateWithFlags(&gemm2, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&join_rec, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&join_gemm, cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&join_gemm2, cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&join_gemm, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) cudaGetLastError();
     }
 };
@@ -1564,11 +1339,9 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
     const size_t n_words = (size_t)256 * L + L + 2 * L + 1;
     int sync_mode = 0;
     if (const char *e = getenv("TB200_LSTM_SYNC")) sync_mode = atoi(e) == 1 ? 1 : (atoi(e) == 2 ? 2 : 0);
-    // two half-batch pipelines per CTA (tiramisu_sm100_lstm_layer_h16x2) when there are two halves to overlap
-    bool split = B > 32 && h16x2_ok(F, (pipeline ? 2 : 1) * (F / 16));
-    if (const char *e = getenv("TB200_LSTM_SPLIT")) split = split && atoi(e) != 0;
-    if (split) sync_mode = 3;
-    t_last_split = split;
+    // R slice in tensor memory (H16Params::r16): K slice = F/2 <= 512 fp16 = 256 columns next to the 64 accumulator columns
+    bool r_in_tmem = true;
+    if (const char *e = getenv("TB200_LSTM_RTMEM")) r_in_tmem = r_in_tmem && atoi(e) != 0;
     uint32_t *flags = reinterpret_cast<uint32_t *>(pool_alloc((n_words + 4 * (size_t)L) * 4));
     if (!R16 || !Wp || !Wp16 || !bp || !xg || !h16 || !flags) return 1;
     uint32_t *step_flags = flags, *xg_ready = flags + 256 * L, *maxbits = xg_ready + L, *scratch = maxbits + 2 * L;
@@ -1612,7 +1385,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
         {
             uint64_t dims[3] = {(uint64_t)F, (uint64_t)B, (uint64_t)T};
             uint64_t str[2] = {(uint64_t)F * 2, (uint64_t)B * F * 2};
-            uint32_t box[3] = {64, split ? 32u : 64u, 1};
+            uint32_t box[3] = {64, 64, 1};
             if (make_tensor_map_f16(&map_h, hh, 3, dims, str, box)) return 1;
         }
         {
@@ -1625,13 +1398,9 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
         hp.B = B; hp.F = F; hp.T = T;
         hp.xg = xg_of(l); hp.bias = bp + (size_t)l * 4 * F; hp.h = out_of(l); hp.h16 = hh; hp.c_out = l == L - 1 ? c_last : nullptr;
         hp.step_flags = step_flags + 256 * l; hp.sync_mode = sync_mode; hp.rscale = winv + 2 * l; hp.xg_ready = ready; hp.dbg = dbg; hp.trace = trace;
+        hp.r16 = r_in_tmem ? R16 + (size_t)l * wsz : nullptr;
         cudaLaunchAttribute attr[1];
         cudaLaunchConfig_t cfg = h16_config(F, attr, st);
-        if (split) {
-            cfg.blockDim = dim3(H2_THREADS);
-            TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16x2, map_h, map_r, hp));
-            return post_launch("tiramisu_sm100_lstm_layer_h16x2");
-        }
         TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16, map_h, map_r, hp));
         return post_launch("tiramisu_sm100_lstm_layer_h16");
     };
@@ -1672,49 +1441,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
             warmed.store(true);
         }
     }
-    bool roll = pipeline && L > 2;
-    if (const char *e = getenv("TB200_LSTM_ROLL")) roll = roll && atoi(e) != 0;
-    // chunk GEMMs of Xg(l + 1) on stream gs: each follows layer l's step counter(s), then publishes how far Xg(l + 1) is
-    auto launch_chunks = [&](int l, cudaStream_t gs) -> int {
-        ScopedStream on(gs);
-        int rc = 0;
-        for (int t0 = 0, n = 0; t0 < T && !rc; n++) {
-            const int len = n == 0 ? (chunk < 4 ? chunk : 4) : (n == 1 ? (chunk < 6 ? chunk : 6) : chunk);
-            const int t1 = t0 + len < T ? t0 + len : T;
-            tiramisu_sm100_wait_counter<<<1, 64, 0, gs>>>(step_flags + 256 * l, nctas, (uint32_t)t1, sync_mode);
-            rc = post_launch("tiramisu_sm100_wait_counter");
-            if (!rc) rc = launch_xg(l + 1, t0, t1);
-            if (!rc) {
-                tiramisu_sm100_publish<<<1, 1, 0, gs>>>(xg_ready + (l + 1), (uint32_t)t1);
-                rc = post_launch("tiramisu_sm100_publish");
-            }
-            t0 = t1;
-        }
-        return rc;
-    };
-    if (roll) {
-        // ROLLING pipeline over all L layers: two recurrences are resident at any time (the shared memory of 2 x F/16 SMs
-        // holds two layers' R), layer l on stream l & 1; layer l + 2 starts the moment layer l ends — it is gated by
-        // xg_ready like every layer above the first, so it neither waits for layer l + 1 to finish nor for a full-size
-        // Xg GEMM.  Buffers are shared by layer parity: Xg(l + 2)[t] / h16(l + 2)[t] are written only after layer l + 1
-        // has passed step t, which it can only do after layer l (and the chunk GEMM reading h16(l)[t]) is done with them.
-        if (launch_xg(0, 0, T)) return 1;
-        TB200_CHECK(cudaEventRecord(ps->fork, main_st));
-        TB200_CHECK(cudaStreamWaitEvent(ps->rec, ps->fork, 0));
-        TB200_CHECK(cudaStreamWaitEvent(ps->gemm, ps->fork, 0));
-        TB200_CHECK(cudaStreamWaitEvent(ps->gemm2, ps->fork, 0));
-        for (int l = 0; l < L; l++) {
-            if (launch_rec(l, (l & 1) ? ps->rec : main_st, l == 0 ? nullptr : xg_ready + l, l == 0 ? trace : nullptr)) return 1;
-            if (l + 1 < L && launch_chunks(l, (l & 1) ? ps->gemm2 : ps->gemm)) return 1;
-        }
-        TB200_CHECK(cudaEventRecord(ps->join_rec, ps->rec));
-        TB200_CHECK(cudaEventRecord(ps->join_gemm, ps->gemm));
-        TB200_CHECK(cudaEventRecord(ps->join_gemm2, ps->gemm2));
-        TB200_CHECK(cudaStreamWaitEvent(main_st, ps->join_rec, 0));
-        TB200_CHECK(cudaStreamWaitEvent(main_st, ps->join_gemm, 0));
-        TB200_CHECK(cudaStreamWaitEvent(main_st, ps->join_gemm2, 0));
-    }
-    for (int l = 0; l < L && !roll;) {
+    for (int l = 0; l < L;) {
         // input contribution of layer l for all T steps: one full-chip GEMM
         if (launch_xg(l, 0, T)) return 1;
         const bool pair = pipeline && l + 1 < L;
@@ -1731,7 +1458,23 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
         TB200_CHECK(cudaStreamWaitEvent(ps->gemm, ps->fork, 0));
         if (launch_rec(l, main_st, nullptr, l == 0 ? trace : nullptr)) return 1;
         if (launch_rec(l + 1, ps->rec, xg_ready + (l + 1), nullptr)) return 1;
-        if (launch_chunks(l, ps->gemm)) return 1;
+        {
+            ScopedStream on(ps->gemm);
+            int rc = 0;
+            for (int t0 = 0, n = 0; t0 < T && !rc; n++) {
+                const int len = n == 0 ? (chunk < 4 ? chunk : 4) : (n == 1 ? (chunk < 6 ? chunk : 6) : chunk);
+                const int t1 = t0 + len < T ? t0 + len : T;
+                tiramisu_sm100_wait_counter<<<1, 64, 0, ps->gemm>>>(step_flags + 256 * l, nctas, (uint32_t)t1, sync_mode);
+                rc = post_launch("tiramisu_sm100_wait_counter");
+                if (!rc) rc = launch_xg(l + 1, t0, t1);
+                if (!rc) {
+                    tiramisu_sm100_publish<<<1, 1, 0, ps->gemm>>>(xg_ready + (l + 1), (uint32_t)t1);
+                    rc = post_launch("tiramisu_sm100_publish");
+                }
+                t0 = t1;
+            }
+            if (rc) return 1;
+        }
         TB200_CHECK(cudaEventRecord(ps->join_rec, ps->rec));
         TB200_CHECK(cudaEventRecord(ps->join_gemm, ps->gemm));
         TB200_CHECK(cudaStreamWaitEvent(main_st, ps->join_rec, 0));
@@ -1763,14 +1506,9 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
         if (ok) {
             bool pipe = pair_ok;
             if (const char *e = getenv("TB200_LSTM_PIPE")) pipe = pipe && atoi(e) != 0;
-            const int rc = lstm_h16(F, B, L, T, Wt, bias, x, y, c_last, pipe);
-            if (t_last_split)
-                t_last_engine = pipe ? "h16x2: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, two half-batch pipelines per CTA, two layers resident (rolling)"
-                                     : "h16x2: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, two half-batch pipelines per CTA, one layer at a time";
-            else
-                t_last_engine = pipe ? "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, layer pairs overlapped"
-                                     : "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, one layer at a time";
-            return rc;
+            t_last_engine = pipe ? "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, layer pairs overlapped"
+                                 : "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, one layer at a time";
+            return lstm_h16(F, B, L, T, Wt, bias, x, y, c_last, pipe);
         }
     }
     const size_t BF = (size_t)B * F, TB = (size_t)T * B;

@@ -250,6 +250,13 @@ public:
     void after(computation &before_this, int level);
     void before(computation &after_this, var level = root);
     void between(computation &before_c, var before_l, computation &after_c, var after_l);
+    /** reference core.h:3889 `compute_at(consumer, L)`: on the CPU the producer is re-computed inside the consumer's
+     *  loop L, region by region, for locality — the values every consumer iteration reads are those of the producer's
+     *  own definition.  A data-parallel device has no use for the redundant recomputation: the producer is
+     *  materialised once over its whole domain and ordered before the consumer at root (two kernels, or one when the
+     *  stencil patterns fuse them); what is stored and read is unchanged. */
+    void compute_at(computation &consumer, var L);
+    void compute_at(computation &consumer, int L);
     /** Further definitions of the same computation over other domains ("updates", reference core.h:
       * add_definitions / get_update): each is a computation of its own that shares the name, so uses of the
       * name resolve to the element the latest definition is mapped to. */

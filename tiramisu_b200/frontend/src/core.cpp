@@ -371,6 +371,17 @@ computation &computation::then(computation &next, int level)
 void computation::after(computation &b, var level) { link_after(b, level.get_name(), level.get_name().empty() ? -1 : -2); }
 void computation::after(computation &b, int level) { link_after(b, "", level); }
 void computation::before(computation &a, var level) { a.after(*this, level); }
+void computation::compute_at(computation &consumer, var)
+{
+    static bool told = false;
+    if (!told) {
+        std::cerr << "tiramisu_b200 front-end: note: compute_at('" << name_ << "' in '" << consumer.get_name()
+                  << "') is a CPU locality schedule; the producer is computed once over its whole domain before the consumer\n";
+        told = true;
+    }
+    if (consumer.pred_ != this) consumer.after(*this, computation::root);
+}
+void computation::compute_at(computation &consumer, int) { compute_at(consumer, var()); }
 void computation::between(computation &before_c, var before_l, computation &after_c, var after_l)
 {
     after(before_c, before_l);
