@@ -60,6 +60,9 @@ TARGETS = {
     # so the objects are linked into shared libraries and checked against oracle/halide_gpu.py by tests/test_frontend.py.
     **{f"halide_{g}": (f"benchmarks/halide/{g}_tiramisu.cpp", f"build/generated_fct_{g}.o", None, ["benchmarks/halide"], [])
        for g in ("convolutiongpu", "gaussiangpu", "edgegpu", "fusiongpu", "cvtcolorgpu", "rgbyuv420gpu", "heat2dgpu")},
+    # row a7's own generator (CPU schedule: split / parallelize / vectorize + compute_at of the x pass inside the y pass);
+    # it sizes itself from ./utils/images/rgb.png at generator time (RUN_LINKS), checked by tests/test_frontend_halide_gpu.py
+    "halide_blurxy": ("benchmarks/halide/blurxy_tiramisu.cpp", "build/generated_fct_blurxy.o", None, ["benchmarks/halide"], []),
     # BASELINE configs[1]'s own generator: old-style ISL-string API, CPU schedule (parallel y, vectorize x by 8)
     "heat2d": ("benchmarks/halide/heat2d_tiramisu.cpp", "build/generated_fct_heat2d.o", "benchmarks/halide/wrapper_heat2d.cpp",
                ["benchmarks/halide"], []),
@@ -76,6 +79,9 @@ TARGETS = {
 # compile definitions the reference's build passes to a generator (benchmarks/halide/heat2dgpu_tiramisu.cpp:32-36: the GPU
 # variant of the file is selected with USE_GPU2)
 GEN_DEFS = {"halide_heat2dgpu": ["-DUSE_GPU2"]}
+
+# files a generator opens relative to its working directory: name -> {link name: target under the reference checkout}
+RUN_LINKS = {"halide_blurxy": {"utils/images": "utils/images"}}
 
 PATCHES = {
     "lstm_gpu_fixed": [
@@ -128,6 +134,9 @@ def build_one(name: str, lowering: str | None = None) -> tuple[int, str]:
     if r.returncode:
         return r.returncode, "generator does not compile:\n" + log[-3000:]
     # 2. run it: codegen() lowers to sm_100a and compiles the object
+    for link, target in RUN_LINKS.get(name, {}).items():
+        os.makedirs(os.path.dirname(os.path.join(work, link)), exist_ok=True)
+        os.symlink(os.path.join(REF, target), os.path.join(work, link))
     r = subprocess.run([gen_exe], capture_output=True, text=True, env=env, cwd=work)
     log += r.stdout + r.stderr
     if r.returncode or not os.path.exists(os.path.join(work, obj)):

@@ -137,7 +137,26 @@ def test_halide_heat2dgpu_generator(n):
     assert np.array_equal(out, oracle.heat2d(a, "gpu"))
 
 
+def check_blurxy(lib):
+    """benchmarks/halide/blurxy_tiramisu.cpp (row a7's own generator): sized at generator time from the reference's
+    utils/images/rgb.png (2112 x 3520 x 3); uint8 wrap-around sums, the x pass materialised once (compute_at)."""
+    img = _image(9, 3, 3520, 2112)
+    out = np.full((3, 3512, 2104), 11, np.uint8)
+    _call(lib, "blurxy_tiramisu", img, out)
+    assert np.array_equal(out, oracle.blurxy_u8(img))
+
+
+@pytest.mark.gpu
+def test_halide_blurxy_generator():
+    check_blurxy(_lib_of("blurxy"))
+
+
 # ---------------------------------------------------------------------------------------------------- host emulation
+def test_emulated_halide_blurxy_generator():
+    check_blurxy(_emulated("blurxy"))
+
+
+
 @pytest.mark.parametrize("name,check", [("cvtcolorgpu", check_cvtcolor), ("fusiongpu", check_fusion), ("rgbyuv420gpu", check_rgbyuv420),
                                         ("gaussiangpu", check_gaussian)])
 def test_emulated_halide_gpu_benchmark(name, check):
