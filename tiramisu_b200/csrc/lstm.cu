@@ -1036,7 +1036,7 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
 // pushes of step t + 1 land in the other buffer, and its pushes of step t + 2 depend on this CTA's pushes of step t + 1,
 // which come after every local reader of step t's buffer has arrived on full_bar.
 __global__ void __launch_bounds__(H_THREADS, 1)
-tiramisu_sm100_lstm_layer_h16ll(const H16Params p)
+tiramisu_sm100_lstm_layer_h16ll(const __grid_constant__ CUtensorMap map_h, const H16Params p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1048,13 +1048,15 @@ tiramisu_sm100_lstm_layer_h16ll(const H16Params p)
     uint64_t *tmem_full = r_bar + 1;
     uint64_t *recv_bar = tmem_full + 1;                      // [2]
     uint64_t *pub_bar = recv_bar + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pub_bar + 1);
+    uint64_t *tma_bar = pub_bar + 1;                         // the bulk fetch of h16[t] has landed (then verified chunk by chunk)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tma_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ks = ptx::cluster_ctarank();              // K slice of this CTA = its rank in the cluster
     const int j = blockIdx.x / H_CL;                         // gate-row group of the cluster
     const int k_base = (int)ks * (p.F / H_CL);
 
+    if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&map_h);
     if (warp == 1) {
         if (lane == 0) {
             ptx::mbar_init(full_bar, 256);              // every epilogue thread, once its chunks of h16[t-1] are in place
@@ -1063,6 +1065,7 @@ tiramisu_sm100_lstm_layer_h16ll(const H16Params p)
             ptx::mbar_init(&recv_bar[0], 1 + 128);      // expect_tx arrival + the 128 lanes that fill the local half
             ptx::mbar_init(&recv_bar[1], 1 + 128);
             ptx::mbar_init(pub_bar, 256);               // the writers of h[t] (CTA scope), awaited by the publishing warp
+            ptx::mbar_init(tma_bar, 1);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -1228,7 +1231,10 @@ tiramisu_sm100_lstm_layer_h16ll(const H16Params p)
                 uint32_t w0 = *reinterpret_cast<const uint32_t *>(&lo), w1 = *reinterpret_cast<const uint32_t *>(&hi);
                 w0 ^= __vcmpeq2(w0, 0xffffffffu) & 0x80008000u;               // never the "not written yet" pattern
                 w1 ^= __vcmpeq2(w1, 0xffffffffu) & 0x80008000u;
-                asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p.h16 + o), "r"(w0), "r"(w1) : "memory");
+                // plain (weak) vector store: four adjacent lanes fill one 32-byte sector and the LSU sends it as ONE full-sector
+                // write.  st.relaxed.gpu sent every 8-byte piece on its own; reading a partially written sector back made
+                // L2 fill it from HBM first, and the fetch below took 4 us instead of 0.7 (r02 run 26).
+                *reinterpret_cast<uint2 *>(p.h16 + o) = make_uint2(w0, w1);
                 if (p.h) *reinterpret_cast<float4 *>(p.h + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                 if (p.c_out && t == p.T - 1) *reinterpret_cast<float4 *>(p.c_out + (size_t)b * p.F + u0) = make_float4(c[0], c[1], c[2], c[3]);
             }
@@ -1257,34 +1263,37 @@ tiramisu_sm100_lstm_layer_h16ll(const H16Params p)
                         if (clock64() - t0 > (1ll << 31)) __trap();
                     }
                     if (lane == 0) KS_TRACE_AT(0, t + 1);              // slot 0 of the step the operand is for
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                uint32_t pending = (1u << n_chunks) - 1u;
-#pragma unroll 1
-                for (;;) {
-                    uint4 d[16];
-#pragma unroll
-                    for (int ii = 0; ii < 16; ii++) {
-                        d[ii] = make_uint4(0u, 0u, 0u, 0u);
-                        const int g = e + 256 * ii, row = g / CPR, cc = g - row * CPR;
-                        if (((pending >> ii) & 1u) && row < p.B)
-                            asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(d[ii].x), "=r"(d[ii].y), "=r"(d[ii].z), "=r"(d[ii].w)
-                                         : "l"(src + (size_t)row * p.F + 8 * cc) : "memory");
+                    // every producer has started to publish: fetch the whole slice with the TMA unit (64 KB of strong 16-byte
+                    // loads per CTA took 3.3 us, r02 run 25) ...
+                    ptx::fence_proxy_async_all();
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(tma_bar, (uint32_t)KB * 8192u);
+                        for (int kb = 0; kb < KB; kb++)
+                            ptx::tma_load_3d(smem_h + kb * 8192, &map_h, tma_bar, k_base + kb * 64, 0, t);
                     }
-#pragma unroll
-                    for (int ii = 0; ii < 16; ii++) {
-                        if (!((pending >> ii) & 1u)) continue;
-                        const int g = e + 256 * ii, row = g / CPR, cc = g - row * CPR;
-                        const uint32_t miss = __vcmpeq2(d[ii].x, 0xffffffffu) | __vcmpeq2(d[ii].y, 0xffffffffu) |
-                                              __vcmpeq2(d[ii].z, 0xffffffffu) | __vcmpeq2(d[ii].w, 0xffffffffu);
-                        if (miss && row < p.B) continue;                // rows >= B: zeros, as the TMA fill of the other kernel
-                        *reinterpret_cast<uint4 *>(smem_h + (cc >> 3) * 8192 + row * 128 + (((cc & 7) ^ (row & 7)) << 4)) = d[ii];
-                        pending &= ~(1u << ii);
-                    }
-                    if (!pending) break;
-                    if (clock64() - t0 > (1ll << 31)) __trap();
+                    __syncwarp();
                 }
+                // ... and VERIFY it: a chunk that still shows the pattern was fetched before its writer's store arrived
+                // (one chunk per producer was polled, not every store); those few are re-read directly until they are there.
+                ptx::mbar_wait(tma_bar, (uint32_t)t & 1u);
+                bool patched = false;
+#pragma unroll
+                for (int ii = 0; ii < 16; ii++) {
+                    if (ii >= n_chunks) break;
+                    const int g = e + 256 * ii, row = g / CPR, cc = g - row * CPR;
+                    if (row >= p.B) continue;                           // rows >= B: zero-filled by the TMA unit
+                    uint4 *sp = reinterpret_cast<uint4 *>(smem_h + (cc >> 3) * 8192 + row * 128 + (((cc & 7) ^ (row & 7)) << 4));
+                    uint4 d = *sp;
+                    if ((__vcmpeq2(d.x, 0xffffffffu) | __vcmpeq2(d.y, 0xffffffffu) | __vcmpeq2(d.z, 0xffffffffu) | __vcmpeq2(d.w, 0xffffffffu)) == 0u) continue;
+                    do {
+                        asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(src + (size_t)row * p.F + 8 * cc) : "memory");
+                        if (clock64() - t0 > (1ll << 31)) __trap();
+                    } while ((__vcmpeq2(d.x, 0xffffffffu) | __vcmpeq2(d.y, 0xffffffffu) | __vcmpeq2(d.z, 0xffffffffu) | __vcmpeq2(d.w, 0xffffffffu)) != 0u);
+                    *sp = d;
+                    patched = true;
+                }
+                if (patched && p.trace) atomicAdd(p.trace + ((size_t)blockIdx.x * p.T + 0) * 8 + 0, 1ull);    // bring-up: patched chunks, in step 0's unused slot
                 ptx::fence_proxy_async_all();
                 if (e == 0) KS_TRACE_AT(2, t + 1);
                 ptx::mbar_arrive(full_bar);
@@ -1708,7 +1717,7 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
             // "not written yet" pattern in every fp16 of this layer's h (stream order: after the previous user of the buffer)
             TB200_CHECK(cudaMemsetAsync(hh, 0xff, TB * F * 2, st));
             cfg.dynamicSmemBytes = H16LL_SMEM;
-            TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16ll, hp));
+            TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16ll, map_h, hp));
             return post_launch("tiramisu_sm100_lstm_layer_h16ll");
         }
         TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16, map_h, map_r, hp));
