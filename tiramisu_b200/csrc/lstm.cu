@@ -470,11 +470,6 @@ __device__ __forceinline__ unsigned long long globaltimer()
         if (p.trace) p.trace[((size_t)blockIdx.x * p.T + t) * 8 + (slot)] = globaltimer();          \
     } while (0)
 
-#define KS_TRACE_AT(slot, tt)                                                                       \
-    do {                                                                                            \
-        if (p.trace) p.trace[((size_t)blockIdx.x * p.T + (tt)) * 8 + (slot)] = globaltimer();       \
-    } while (0)
-
 __device__ __forceinline__ void grid_wait_relaxed(const uint32_t *ctr, uint32_t target)
 {
     const long long t0 = clock64();
@@ -714,7 +709,8 @@ struct H16Params {
     __half *h16;                // [T][B][F] fp16 copy, the recurrence's own operand
     float *c_out;               // null, or [B][F]: the cell state after the last step
     uint32_t *step_flags;       // step barrier words, see sync_mode
-    int sync_mode;              // 0: ONE counter, += gridDim.x per finished step (red.add; r01 and the measured best)
+    int sync_mode;              // 0: ONE counter, += gridDim.x per finished step (red.add; r01 and the measured best); 3: the same
+                                // counter polled with ld.acquire instead of ld.relaxed + fence
                                 // 1: [gridDim.x] per-CTA step flags (plain stores; measured slower: r02 run 1, 7.6 vs 5.9 us/step)
                                 // 2: 8 counters, CTA c adds to counter c & 7 (shorter same-address atomic queues)
     const float *rscale;        // de-scaling factor of the block-scaled fp16 recurrent weights (a power of two)
@@ -727,6 +723,15 @@ struct H16Params {
                                 // 2/3 of them
 };
 constexpr uint32_t H_A_COL0 = 128;     // first TMEM column of the R slice (accumulator: columns [0, 64))
+
+// sync_mode 3: the single counter polled with acquire loads — no separate fence once the target has been seen
+__device__ __forceinline__ void grid_wait_acquire(const uint32_t *ctr, uint32_t target)
+{
+    const long long t0 = clock64();
+    while (ptx::ld_acquire_gpu(ctr) < target) {
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+}
 
 // Every CTA of the layer has published step `target`: lane i watches the flags of CTAs i, i + 32, ...
 // (relaxed polls; one acquire fence once all of them have been seen).  Whole warp, converged.
@@ -810,6 +815,7 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
             if (!(p.dbg & 1)) {                                                                   // h16[t-1] is complete
                 if (p.sync_mode == 1) grid_wait_flags(p.step_flags, (int)gridDim.x, (uint32_t)t);
                 else if (p.sync_mode == 2) grid_wait_counters8(p.step_flags, (int)gridDim.x, (uint32_t)t);
+                else if (p.sync_mode == 3) grid_wait_acquire(p.step_flags, (uint32_t)gridDim.x * (uint32_t)t);
                 else grid_wait_relaxed(p.step_flags, (uint32_t)gridDim.x * (uint32_t)t);
             }
             ptx::fence_proxy_async_all();
@@ -1021,294 +1027,6 @@ tiramisu_sm100_lstm_layer_h16(const __grid_constant__ CUtensorMap map_h, const _
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// The same engine with the h exchange done IN THE DATA (sync_mode 4; needs R in tensor memory).  In the kernel above a
-// step's hand-over costs three serial device-wide latencies: the writers' gpu-scope fence (their stores acknowledged by
-// L2, ~1.0 us), the counter's trip to the pollers (~1.2 us with the acquire fence) and then the TMA fetch of h (~0.5-1 us).
-// Here h16[t] is its own flag: the buffer is pre-filled with the fp16 pattern 0xFFFF (a NaN no cell can produce: |h| < 1
-// and NaNs are written as 0x7FFF), the finalising threads store their h with relaxed gpu-scope stores and go straight on
-// to FETCH the next step's operand themselves — each of the 256 epilogue threads polls the first 16-byte chunk of its
-// column with relaxed loads until no half is 0xFFFF, then loads its other chunks, re-polls stragglers, writes them
-// into the 128B-swizzled K-major layout the MMA descriptors expect, fence.proxy.async, one mbarrier arrival.  No fence and
-// no counter on the critical path.  The step counter still exists — bumped by the otherwise idle warp 0 after a
-// CTA-scope mbarrier rendezvous of the writers — because the layer ABOVE follows it (chunk GEMMs of its Xg).  The
-// receive buffer of the DSMEM reduction is double-buffered (shared memory is free now that R lives in TMEM): the peer's
-// pushes of step t + 1 land in the other buffer, and its pushes of step t + 2 depend on this CTA's pushes of step t + 1,
-// which come after every local reader of step t's buffer has arrived on full_bar.
-__global__ void __launch_bounds__(H_THREADS, 1)
-tiramisu_sm100_lstm_layer_h16ll(const __grid_constant__ CUtensorMap map_h, const H16Params p)
-{
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int KB = p.F / (H_CL * 64);                        // 64-element (128-byte) k-blocks per K slice (<= 8)
-    uint8_t *smem_h = smem;                                  // KB x [64 rows][64 k] fp16  (8 KB each), 128B-swizzled
-    float *recv = reinterpret_cast<float *>(smem_h + (size_t)KB * 8192);          // [2 buffers][src CTA][gate row][batch]
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(recv) + 2 * H_RECV_BYTES);
-    uint64_t *r_bar = full_bar + 1;
-    uint64_t *tmem_full = r_bar + 1;
-    uint64_t *recv_bar = tmem_full + 1;                      // [2]
-    uint64_t *pub_bar = recv_bar + 2;
-    uint64_t *tma_bar = pub_bar + 1;                         // the bulk fetch of h16[t] has landed (then verified chunk by chunk)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tma_bar + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ks = ptx::cluster_ctarank();              // K slice of this CTA = its rank in the cluster
-    const int j = blockIdx.x / H_CL;                         // gate-row group of the cluster
-    const int k_base = (int)ks * (p.F / H_CL);
-
-    if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&map_h);
-    if (warp == 1) {
-        if (lane == 0) {
-            ptx::mbar_init(full_bar, 256);              // every epilogue thread, once its chunks of h16[t-1] are in place
-            ptx::mbar_init(r_bar, 256);                 // ... and once its part of R is in tensor memory
-            ptx::mbar_init(tmem_full, 1);
-            ptx::mbar_init(&recv_bar[0], 1 + 128);      // expect_tx arrival + the 128 lanes that fill the local half
-            ptx::mbar_init(&recv_bar[1], 1 + 128);
-            ptx::mbar_init(pub_bar, 256);               // the writers of h[t] (CTA scope), awaited by the publishing warp
-            ptx::mbar_init(tma_bar, 1);
-            ptx::fence_barrier_init();
-        }
-        __syncwarp();
-        ptx::tmem_alloc(tmem_slot, 512);
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before_sync();
-    ptx::cluster_sync();                                     // the peer's barriers exist before any remote store
-    ptx::tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===== publisher: the layer's step counter, for the chunk GEMMs of the layer above (off the critical path) =====
-        for (int t = 0; t < p.T; t++) {
-            ptx::mbar_wait(pub_bar, (uint32_t)t & 1u);
-            if (lane == 0) {
-                ptx::fence_acq_rel_gpu();
-                ptx::red_relaxed_gpu_add(p.step_flags, 1u);
-                KS_TRACE(7);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer: A = R slice in tensor memory, B = h16[t-1][:, K slice] as the epilogue threads laid it out =====
-        constexpr uint32_t idesc = ptx::make_idesc_f16(128, 64, false, false);
-        const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_h), 16, 1024);
-        const uint32_t a_tmem = tmem_base + H_A_COL0;
-        ptx::mbar_wait(r_bar, 0);
-        ptx::tc_fence_after_sync();
-        for (int t = 1; t < p.T; t++) {
-            ptx::mbar_wait(full_bar, (uint32_t)(t - 1) & 1u);
-            ptx::tc_fence_after_sync();
-            if (ptx::elect_one()) {
-                KS_TRACE(1);
-                for (int kb = 0; kb < KB; kb++) {
-                    const uint64_t db = ptx::desc_advance(db0, (uint32_t)kb * 8192u);
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        ptx::mma_f16_ts(tmem_base, a_tmem + (uint32_t)(kb * 32 + k * 8), ptx::desc_advance(db, k * 32), idesc, (kb | k) != 0);
-                }
-                ptx::mma_commit(tmem_full);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===== epilogue + operand fetch: 8 warps =====
-        const uint32_t q = (uint32_t)warp & 3u;            // TMEM lane quarter this warp may read
-        const uint32_t ch = (uint32_t)(warp - 2) >> 2;     // which 32 of the 64 batch columns it reads
-        const uint32_t dst_cta = q >> 1;                   // gate rows [64 dst, +64) are finalised by CTA dst
-        const int e = (warp - 2) * 32 + lane;              // 0..255
-        const int ug = e & 3;                              // which 4 of the CTA's 16 hidden units
-        const int b = e >> 2;                              // batch entry this thread finalises
-        const bool ok = b < p.B;
-        const int p0 = 128 * j + 64 * (int)ks + 16 * ug;           // first packed gate column of this thread
-        const int u0 = 32 * j + 16 * (int)ks + 4 * ug;             // first hidden unit of this thread
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        float4 bs[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) bs[u] = __ldg(reinterpret_cast<const float4 *>(p.bias + p0) + u);
-        const float rs = __ldg(p.rscale);
-        const uint32_t row_l = 32u * (q & 1u) + (uint32_t)lane;
-        const uint32_t sw_w = (row_l & 7u) ^ (((row_l >> 4) & 3u) << 1);
-        const uint32_t push_off = ks * 16384u + row_l * 256u;              // inside one receive buffer
-        const uint32_t push_base = ptx::mapa_u32(reinterpret_cast<uint8_t *>(recv), dst_cta);
-        const uint32_t push_bar0 = ptx::mapa_u32(&recv_bar[0], dst_cta), push_bar1 = ptx::mapa_u32(&recv_bar[1], dst_cta);
-        {
-            // R slice -> tensor memory (see tiramisu_sm100_lstm_layer_h16)
-            const int half = (KB + 1) / 2;
-            const __half *rrow = p.r16 + (size_t)(128 * j + 32 * (int)q + lane) * p.F + k_base;
-            const int c_lo = ch == 0 ? 0 : 32 * half, c_hi = ch == 0 ? 32 * half : 32 * KB;
-            for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-                uint32_t w[32];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(rrow + 2 * c0) + i);
-                    w[4 * i + 0] = v4.x; w[4 * i + 1] = v4.y; w[4 * i + 2] = v4.z; w[4 * i + 3] = v4.w;
-                }
-                ptx::tmem_st_32x32(tmem_base + ((q * 32u) << 16) + H_A_COL0 + (uint32_t)c0, w);
-            }
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before_sync();
-            ptx::mbar_arrive(r_bar);
-        }
-        // this thread's share of the operand fetch: 16-byte chunks g = e + 256 i of the [64 rows][CPR chunks] slice
-        const int CPR = 8 * KB;                            // chunks per batch row of the K slice
-        const int n_chunks = 2 * KB;                       // 64 * CPR / 256 per thread (<= 16)
-        uint32_t ready = p.xg_ready ? 0u : 0xffffffffu;
-        for (int t = 0; t < p.T; t++) {
-            if ((uint32_t)t >= ready) {
-                uint32_t v = 0;
-                if (lane == 0) {
-                    const long long t0 = clock64();
-                    while ((v = ptx::ld_acquire_gpu(p.xg_ready)) <= (uint32_t)t) {
-                        if (clock64() - t0 > (1ll << 32)) __trap();
-                        __nanosleep(200);
-                    }
-                }
-                ready = __shfl_sync(0xffffffffu, v, 0);
-            }
-            float4 xg[4];
-            if (ok) {
-                const float4 *xp = reinterpret_cast<const float4 *>(p.xg + ((size_t)t * p.B + b) * 4 * p.F + p0);
-#pragma unroll
-                for (int u = 0; u < 4; u++) xg[u] = __ldcg(xp + u);
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; u++) xg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            float acc[16];
-#pragma unroll
-            for (int a = 0; a < 16; a++) acc[a] = 0.0f;
-            if (t > 0) {
-                const uint32_t rb = (uint32_t)t & 1u;                         // receive buffer / barrier of this step
-                float *recv_t = recv + rb * (H_RECV_BYTES / 4);
-                if (e == 0) ptx::mbar_arrive_expect_tx(&recv_bar[rb], (uint32_t)H_RECV_BYTES / 2);
-                ptx::mbar_wait(tmem_full, (uint32_t)(t - 1) & 1u);
-                ptx::tc_fence_after_sync();
-                if (e == 0) KS_TRACE(3);
-                uint32_t v[32];
-                __syncwarp();
-                ptx::tmem_ld_32x32_nowait(tmem_base + ((q * 32u) << 16) + 32u * ch, v);
-                ptx::tmem_ld_wait();
-                ptx::tc_fence_before_sync();
-                if (dst_cta == ks) {
-                    float4 *lp = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(recv_t) + push_off);
-#pragma unroll
-                    for (int cc = 0; cc < 8; cc++)
-                        lp[(8u * ch + (uint32_t)cc) ^ sw_w] = make_float4(__uint_as_float(v[4 * cc + 0]), __uint_as_float(v[4 * cc + 1]),
-                                                                         __uint_as_float(v[4 * cc + 2]), __uint_as_float(v[4 * cc + 3]));
-                    ptx::mbar_arrive(&recv_bar[rb]);
-                } else {
-                    const uint32_t pa = push_base + rb * (uint32_t)H_RECV_BYTES + push_off, pbar = rb ? push_bar1 : push_bar0;
-#pragma unroll
-                    for (int cc = 0; cc < 8; cc++)
-                        ptx::st_async_cluster_v4(pa + ((8u * ch + (uint32_t)cc) ^ sw_w) * 16u, pbar,
-                                                 __uint_as_float(v[4 * cc + 0]), __uint_as_float(v[4 * cc + 1]),
-                                                 __uint_as_float(v[4 * cc + 2]), __uint_as_float(v[4 * cc + 3]));
-                }
-                if (e == 0) KS_TRACE(4);
-                ptx::mbar_wait(&recv_bar[rb], (uint32_t)((t - 1) >> 1) & 1u);
-                if (e == 0) KS_TRACE(5);
-#pragma unroll
-                for (int a = 0; a < 16; a++) {
-                    const int row = 16 * ug + a;
-                    const int col = ((((b >> 2) ^ (row & 7) ^ (ug << 1)) << 2) | (b & 3));
-                    acc[a] = (recv_t[0 * 4096 + row * 64 + col] + recv_t[1 * 4096 + row * 64 + col]) * rs;
-                }
-            }
-            float hn[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const float si = acc[4 * u + 0] + xg[u].x + bs[u].x;
-                const float sz = acc[4 * u + 1] + xg[u].y + bs[u].y;
-                const float so = acc[4 * u + 2] + xg[u].z + bs[u].z;
-                const float sf = acc[4 * u + 3] + xg[u].w + bs[u].w;
-                const float gi = sigmoid_fast(si), gz = ptx::tanh_approx(sz), go = sigmoid_fast(so), gf = sigmoid_fast(sf);
-                c[u] = gi * gz + gf * c[u];
-                hn[u] = ptx::tanh_approx(c[u]) * go;
-            }
-            if (ok) {
-                const size_t o = ((size_t)t * p.B + b) * p.F + u0;
-                const __half2 lo = __floats2half2_rn(hn[0], hn[1]), hi = __floats2half2_rn(hn[2], hn[3]);
-                uint32_t w0 = *reinterpret_cast<const uint32_t *>(&lo), w1 = *reinterpret_cast<const uint32_t *>(&hi);
-                w0 ^= __vcmpeq2(w0, 0xffffffffu) & 0x80008000u;               // never the "not written yet" pattern
-                w1 ^= __vcmpeq2(w1, 0xffffffffu) & 0x80008000u;
-                // plain (weak) vector store: four adjacent lanes fill one 32-byte sector and the LSU sends it as ONE full-sector
-                // write.  st.relaxed.gpu sent every 8-byte piece on its own; reading a partially written sector back made
-                // L2 fill it from HBM first, and the fetch below took 4 us instead of 0.7 (r02 run 26).
-                *reinterpret_cast<uint2 *>(p.h16 + o) = make_uint2(w0, w1);
-                if (p.h) *reinterpret_cast<float4 *>(p.h + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                if (p.c_out && t == p.T - 1) *reinterpret_cast<float4 *>(p.c_out + (size_t)b * p.F + u0) = make_float4(c[0], c[1], c[2], c[3]);
-            }
-            if (e == 0) KS_TRACE(6);
-            ptx::mbar_arrive(pub_bar);                                        // release.cta: the publisher's fence covers these stores
-            if (t + 1 == p.T) break;
-            // ---- fetch h16[t][:, K slice]: the B operand of step t + 1
-            {
-                const __half *src = p.h16 + (size_t)t * p.B * p.F + k_base;
-                const long long t0 = clock64();
-                if (warp == 2) {
-                    // ONE warp polls, one chunk per producing CTA of this K slice (4 KB of them, 2 chunks each), on a batch row
-                    // that differs from cluster to cluster — 256 threads of every CTA polling the same few rows kept the L2
-                    // slices that hold them saturated and the step took 22 us (r02 run 24).
-                    const int n_prod = 4 * KB;
-                    const int pr = (j + lane) % p.B;
-                    bool seen = lane >= n_prod;
-                    for (;;) {
-                        if (!seen) {
-                            uint4 d;
-                            asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(src + (size_t)pr * p.F + 16 * lane) : "memory");
-                            seen = (__vcmpeq2(d.x, 0xffffffffu) | __vcmpeq2(d.y, 0xffffffffu) | __vcmpeq2(d.z, 0xffffffffu) | __vcmpeq2(d.w, 0xffffffffu)) == 0u;
-                        }
-                        if (__all_sync(0xffffffffu, seen)) break;
-                        if (clock64() - t0 > (1ll << 31)) __trap();
-                    }
-                    if (lane == 0) KS_TRACE_AT(0, t + 1);              // slot 0 of the step the operand is for
-                    // every producer has started to publish: fetch the whole slice with the TMA unit (64 KB of strong 16-byte
-                    // loads per CTA took 3.3 us, r02 run 25) ...
-                    ptx::fence_proxy_async_all();
-                    if (ptx::elect_one()) {
-                        ptx::mbar_arrive_expect_tx(tma_bar, (uint32_t)KB * 8192u);
-                        for (int kb = 0; kb < KB; kb++)
-                            ptx::tma_load_3d(smem_h + kb * 8192, &map_h, tma_bar, k_base + kb * 64, 0, t);
-                    }
-                    __syncwarp();
-                }
-                // ... and VERIFY it: a chunk that still shows the pattern was fetched before its writer's store arrived
-                // (one chunk per producer was polled, not every store); those few are re-read directly until they are there.
-                ptx::mbar_wait(tma_bar, (uint32_t)t & 1u);
-                bool patched = false;
-#pragma unroll
-                for (int ii = 0; ii < 16; ii++) {
-                    if (ii >= n_chunks) break;
-                    const int g = e + 256 * ii, row = g / CPR, cc = g - row * CPR;
-                    if (row >= p.B) continue;                           // rows >= B: zero-filled by the TMA unit
-                    uint4 *sp = reinterpret_cast<uint4 *>(smem_h + (cc >> 3) * 8192 + row * 128 + (((cc & 7) ^ (row & 7)) << 4));
-                    uint4 d = *sp;
-                    if ((__vcmpeq2(d.x, 0xffffffffu) | __vcmpeq2(d.y, 0xffffffffu) | __vcmpeq2(d.z, 0xffffffffu) | __vcmpeq2(d.w, 0xffffffffu)) == 0u) continue;
-                    do {
-                        asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(src + (size_t)row * p.F + 8 * cc) : "memory");
-                        if (clock64() - t0 > (1ll << 31)) __trap();
-                    } while ((__vcmpeq2(d.x, 0xffffffffu) | __vcmpeq2(d.y, 0xffffffffu) | __vcmpeq2(d.z, 0xffffffffu) | __vcmpeq2(d.w, 0xffffffffu)) != 0u);
-                    *sp = d;
-                    patched = true;
-                }
-                if (patched && p.trace) atomicAdd(p.trace + ((size_t)blockIdx.x * p.T + 0) * 8 + 0, 1ull);    // bring-up: patched chunks, in step 0's unused slot
-                ptx::fence_proxy_async_all();
-                if (e == 0) KS_TRACE_AT(2, t + 1);
-                ptx::mbar_arrive(full_bar);
-            }
-        }
-    }
-
-    ptx::tc_fence_before_sync();
-    ptx::cluster_sync();                                     // nobody exits while the peer may still push into it
-    if (warp == 1) {
-        ptx::tc_fence_after_sync();
-        ptx::tmem_dealloc(tmem_base, 512);
-    }
-}
-
 // ---- block-scaled fp16 weights ----------------------------------------------------------------------
 // fp16 has TF32's 11-bit significand but only a 5-bit exponent: |w| > 65504 would become inf and |w| < 6e-8
 // zero.  Every weight matrix (R and W of every layer) is therefore stored as fp16(w * 2^k) with k chosen so that
@@ -1406,7 +1124,6 @@ __global__ void tiramisu_sm100_publish(uint32_t *flag, uint32_t value)
 
 std::atomic<int> g_lstm_mode{0};
 std::atomic<int> g_lstm_kernel{0};
-thread_local bool t_last_ll = false;             // ... and whether the fp16 engine exchanged h in the data (h16ll kernel)
 thread_local const char *t_last_engine = "";     // which recurrence engine the calling thread's last tiramisu_b200_lstm used
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -1602,19 +1319,6 @@ bool h16_ok(int F, int B, bool *pair_ok)
     return cached_clusters * H_CL >= need;
 }
 
-// The in-data exchange kernel: always asks for (nearly) all of the SM's shared memory — it holds the whole tensor memory, so
-// no other tcgen05 kernel's CTA may share its SM (a chunk GEMM CTA would wait for TMEM until the layer ends).
-constexpr size_t H16LL_SMEM = 8 * (16384 + 8192) + H_RECV_BYTES + 256 + 1024;
-bool h16ll_ok(int F)
-{
-    static int state = -1;
-    if (state < 0) {
-        state = cudaFuncSetAttribute(tiramisu_sm100_lstm_layer_h16ll, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
-        if (!state) cudaGetLastError();
-    }
-    return state == 1 && (size_t)(F / 128) * 8192 + 2 * H_RECV_BYTES + 512 + 1024 <= H16LL_SMEM;
-}
-
 // Auxiliary streams + events of the layer pipeline, one set per host thread.
 struct PipeStreams {
     cudaStream_t rec = nullptr, gemm = nullptr;
@@ -1645,15 +1349,10 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
     // max-abs bit patterns, scratch word; then [2L] scale, [2L] 1/scale
     const size_t n_words = (size_t)256 * L + L + 2 * L + 1;
     int sync_mode = 0;
-    if (const char *e = getenv("TB200_LSTM_SYNC")) sync_mode = atoi(e) == 1 ? 1 : (atoi(e) == 2 ? 2 : 0);
+    if (const char *e = getenv("TB200_LSTM_SYNC")) sync_mode = atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : 0;
     // R slice in tensor memory (H16Params::r16): K slice = F/2 <= 512 fp16 = 256 columns next to the 64 accumulator columns
     bool r_in_tmem = true;
     if (const char *e = getenv("TB200_LSTM_RTMEM")) r_in_tmem = r_in_tmem && atoi(e) != 0;
-    // h exchanged in the data (tiramisu_sm100_lstm_layer_h16ll): needs the shared memory R leaves free
-    bool ll = r_in_tmem && h16ll_ok(F);
-    if (const char *e = getenv("TB200_LSTM_LL")) ll = ll && atoi(e) != 0;
-    if (ll) sync_mode = 0;                                         // the counter the layer above follows is the single one
-    t_last_ll = ll;
     uint32_t *flags = reinterpret_cast<uint32_t *>(pool_alloc((n_words + 4 * (size_t)L) * 4));
     if (!R16 || !Wp || !Wp16 || !bp || !xg || !h16 || !flags) return 1;
     uint32_t *step_flags = flags, *xg_ready = flags + 256 * L, *maxbits = xg_ready + L, *scratch = maxbits + 2 * L;
@@ -1713,13 +1412,6 @@ int lstm_h16(int F, int B, int L, int T, const float *Wt, const float *bias, con
         hp.r16 = r_in_tmem ? R16 + (size_t)l * wsz : nullptr;
         cudaLaunchAttribute attr[1];
         cudaLaunchConfig_t cfg = h16_config(F, attr, st);
-        if (ll) {
-            // "not written yet" pattern in every fp16 of this layer's h (stream order: after the previous user of the buffer)
-            TB200_CHECK(cudaMemsetAsync(hh, 0xff, TB * F * 2, st));
-            cfg.dynamicSmemBytes = H16LL_SMEM;
-            TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16ll, map_h, hp));
-            return post_launch("tiramisu_sm100_lstm_layer_h16ll");
-        }
         TB200_CHECK(cudaLaunchKernelEx(&cfg, tiramisu_sm100_lstm_layer_h16, map_h, map_r, hp));
         return post_launch("tiramisu_sm100_lstm_layer_h16");
     };
@@ -1825,14 +1517,9 @@ int lstm_tensor(int F, int B, int L, int T, const float *Wt, const float *bias, 
         if (ok) {
             bool pipe = pair_ok;
             if (const char *e = getenv("TB200_LSTM_PIPE")) pipe = pipe && atoi(e) != 0;
-            const int rc = lstm_h16(F, B, L, T, Wt, bias, x, y, c_last, pipe);
-            if (t_last_ll)
-                t_last_engine = pipe ? "h16ll: block-scaled fp16 operands (11-bit significand = TF32's), R in tensor memory, K split over 2-CTA clusters, h exchanged in the data, layer pairs overlapped"
-                                     : "h16ll: block-scaled fp16 operands (11-bit significand = TF32's), R in tensor memory, K split over 2-CTA clusters, h exchanged in the data, one layer at a time";
-            else
-                t_last_engine = pipe ? "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, layer pairs overlapped"
-                                     : "h16: block-scaled fp16 operands (11-bit significand = TF32's), K split over 2-CTA clusters, one layer at a time";
-            return rc;
+            t_last_engine = pipe ? "h16: block-scaled fp16 operands (11-bit significand = TF32's), R in tensor memory, K split over 2-CTA clusters, layer pairs overlapped"
+                                 : "h16: block-scaled fp16 operands (11-bit significand = TF32's), R in tensor memory, K split over 2-CTA clusters, one layer at a time";
+            return lstm_h16(F, B, L, T, Wt, bias, x, y, c_last, pipe);
         }
     }
     const size_t BF = (size_t)B * F, TB = (size_t)T * B;
