@@ -38,6 +38,12 @@ TARGETS = {
                              [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
     "sgemm_gpu_generator3": (f"{SGEMM_GPU}/generator3.cpp", "fct.o", f"{SGEMM_GPU}/wrapper.cpp", [SGEMM_GPU],
                              [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
+    # BASELINE configs[0]'s own generator (row a1): level-numbered scheduling API (tile / split / tag_*_level(int),
+    # after_low_level), every statement cut into full- and partial-tile pieces, a packed copy of B nothing reads.  The pieces
+    # are merged back into one statement each, the dead temporary is dropped and the triple becomes ONE tcgen05 GEMM call;
+    # linked with the reference's own sgemm_wrapper.cpp (16 sizes, checked against cblas_sgemm).
+    "sgemm_cpu": ("benchmarks/linear_algebra/blas/level3/sgemm/cpu/sgemm_generator.cpp", "generated_sgemm.o",
+                  "benchmarks/linear_algebra/blas/level3/sgemm/cpu/sgemm_wrapper.cpp", ["benchmarks/linear_algebra/blas/level3/sgemm/cpu", "benchmarks"], []),
     # chain of two contractions: zero-init + reduction fused per kernel -> two runtime GEMM calls
     "chain_mm": ("benchmarks/linear_algebra/chain_mm/gpu/generator.cpp", "fct.o", "benchmarks/linear_algebra/chain_mm/gpu/wrapper.cpp",
                  ["benchmarks/linear_algebra/chain_mm/gpu"], [f"-L{CUDA}/lib64", "-lcublas", "-lcudart"]),
@@ -169,7 +175,7 @@ def build(names=None, verbose=False) -> dict:
     jobs = [(n, None) for n in TARGETS if not names or n in names]
     # the pattern-lowered generators once more with the pattern lowering off (generic SIMT emission)
     jobs += [(n, "generic") for n in ("test_167", "test_169", "heat2d", "chain_mm", "lstm_cpu", "lstm_cpu_so", "sgemm_gpu_generator1", "sgemm_gpu_generator2",
-                                      "sgemm_gpu_generator3") if not names or n in names]
+                                      "sgemm_gpu_generator3", "sgemm_cpu") if not names or n in names]
     out = {}
     with cf.ThreadPoolExecutor(max_workers=min(6, max(1, len(jobs)))) as ex:
         futs = {ex.submit(build_one, n, low): (n if low is None else f"{n}_{low}") for n, low in jobs}

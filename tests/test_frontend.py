@@ -161,7 +161,12 @@ def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     res = bg.build()
     failed = {k: v[1] for k, v in res.items() if v[0] != 0}
     assert not failed, failed
-    assert len(res) == len(bg.TARGETS) + 9          # + the generic-lowering variants
+    assert len(res) == len(bg.TARGETS) + 10         # + the generic-lowering variants
+    # sgemm/cpu/sgemm_generator.cpp (BASELINE configs[0]'s own generator): 16 statement pieces ordered with after_low_level
+    # and scheduled by loop level -> pieces merged, the packed copy of B nothing reads dropped, ONE tcgen05 GEMM call
+    sg = open(os.path.join(bg.GEN, "sgemm_cpu", "generated_sgemm.o.b200.cu")).read()
+    assert "__global__" not in sg and sg.count("if (tiramisu_cublas_sgemm(") == 1 and "c_a, c_b" in sg and "buf_Bp" not in sg.split("extern \"C\" int sgemm_tiramisu(")[1].split("tiramisu_cublas_sgemm")[0].replace("b_buf_Bp = ", "")
+    assert open(os.path.join(bg.GEN, "sgemm_cpu_generic", "generated_sgemm.o.b200.cu")).read().count("__global__") == 3
     cb = open(os.path.join(bg.GEN, "conv_block", "conv_relu_maxpool_tiramisu.o.b200.cu")).read()
     assert "tiramisu_b200_conv_relu_maxpool(b__c_input_buffer, b__conv_filter_buffer, b__conv_bias_buffer, b_output_buf, 32, 224, 3, 32)" in cb
     assert "__global__" not in cb
@@ -264,6 +269,44 @@ def test_reference_sgemm_gpu_generators_match_cublas(gen, tmp_path):
     describe.  Either way the reference wrapper checks the result against cuBLAS exactly."""
     out = _run(gen, args=("1", "1"), cwd=tmp_path)
     assert "cuBLAS and Tiramisu outputs match" in out, out[-2000:]
+
+
+def _sgemm_cpu_generator_check(lib, shapes):
+    from tiramisu_b200.halide import Buffer
+    f = lib.sgemm_tiramisu
+    f.restype = C.c_int
+    for N, M, K in shapes:
+        rng = np.random.default_rng(N + M + K)
+        A = rng.integers(-3, 4, (N, K)).astype(np.float32)
+        B = rng.integers(-3, 4, (K, M)).astype(np.float32)
+        Cm = rng.integers(-3, 4, (N, M)).astype(np.float32)
+        want = 3.0 * (A @ B) + 2.0 * Cm              # small integers: exact in fp32 (and in TF32) whatever the order
+        got = Cm.copy()
+        bufs = [Buffer(np.array([N, M, K], np.int32)), Buffer(np.array([3.0], np.float32)), Buffer(np.array([2.0], np.float32)),
+                Buffer(A), Buffer(B), Buffer(got)]
+        assert f(*[b.ptr() for b in bufs]) == 0
+        assert np.array_equal(got, want), (N, M, K)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference")
+def test_reference_sgemm_cpu_generator_emulated(frontend_lib):
+    """sgemm/cpu/sgemm_generator.cpp through the front-end, generic lowering (zero fill, SIMT reduction, scaling: three
+    kernels), run thread by thread on the host: sizes that are multiples of the generator's tiles — what its context
+    constraints promise — and sizes that are not (the merged statements cover the whole box either way)."""
+    from tests.emulation import emulate
+    src = os.path.join(bg.GEN, "sgemm_cpu_generic", "generated_sgemm.o.b200.cu")
+    if not os.path.exists(src):
+        bg.build(["sgemm_cpu"])
+    lib = C.CDLL(emulate.build_shared([src], "sgemm_cpu_generic"))
+    _sgemm_cpu_generator_check(lib, [(128, 64, 64), (192, 96, 160), (130, 70, 45)])
+
+
+@pytest.mark.gpu
+def test_reference_sgemm_cpu_generator_through_lowering(tmp_path):
+    """Generator (sgemm_generator.cpp) AND wrapper (sgemm_wrapper.cpp: 16 sizes x 20 runs, A = B = C = 1, a = b = 3,
+    compare_buffers against cblas_sgemm) are the reference's own; the generated sgemm_tiramisu is one tcgen05 GEMM call."""
+    out = _run("sgemm_cpu", cwd=tmp_path, timeout=3000)
+    assert out.count("Test sgemm succeeded") == 16, out[-3000:]
 
 
 @pytest.mark.gpu

@@ -211,6 +211,31 @@ public:
     virtual void tag_unroll_level(var L);
     virtual void tag_unroll_level(var L, int) { tag_unroll_level(L); }
     virtual void shift(var L0, int n);
+    // ---- the same commands addressed by loop LEVEL (position in the current loop order, outermost = 0) instead of by
+    // name: the form the reference's older generators use (reference core.h:3420 after_low_level, :4583 tag_*_level(int),
+    // :4717 tile(int, ...), :4560 split(int, int); benchmarks/linear_algebra/blas/level3/sgemm/cpu/sgemm_generator.cpp:132-262)
+    void split(int L0, int sizeX);
+    void tile(int L0, int L1, int sizeX, int sizeY);
+    void tile(int L0, int L1, int L2, int sizeX, int sizeY, int sizeZ);
+    void interchange(int L0, int L1);
+    void tag_parallel_level(int L);
+    void tag_vector_level(int L, int v);
+    void tag_unroll_level(int L);
+    void tag_unroll_level(int L, int) { tag_unroll_level(L); }
+    void tag_gpu_level(int L0, int L1);
+    void tag_gpu_level(int L0, int L1, int L2, int L3);
+    /** reference src/tiramisu_core.cpp:2126: the ordering command of the older generators.  Every statement carries one
+      * ordering number per loop depth (the "static dimensions" of its schedule, all 0 to begin with); this call copies
+      * \p before_this 's numbers for depths 0..\p level and makes the number below level \p level that of
+      * \p before_this plus 10.  The numbers are read when the call is made, a statement may be re-ordered any number of
+      * times, and several statements may follow the same one.  The order of the program is the lexicographic order of
+      * the number vectors; two neighbours share the loops above the first depth where their numbers differ
+      * (function::resolve_static_order, run by the lowering). */
+    void after_low_level(computation &before_this, int level);
+    const std::vector<int> &static_order() const { return static_; }
+    /** Number of loop levels around the statement (reference core.h:2370; the generators compare it before / after a
+      * split to learn whether the split made a new level — here it always does). */
+    int compute_maximal_AST_depth() const { return (int) dims_.size(); }
     /** Run loop `old_var` backwards; the loop is called `new_var` afterwards (reference core.h:4461). */
     virtual void loop_reversal(var old_var, var new_var);
 
@@ -341,6 +366,7 @@ protected:
     std::vector<computation *> updates_;
     bool own_access_ = false;                            // an update that was mapped explicitly (not through its first definition)
     std::string drop_rank_;                              // distributed level whose iterator the rank-local indices ignore
+    std::vector<int> static_;                            // ordering numbers per loop depth (after_low_level); empty = all 0
     computation *pred_ = nullptr, *succ_ = nullptr;
     std::string pred_level_;                             // "" = root
     int pred_level_index_ = -2;                          // -2 = by name, -1 = root, >=0 explicit depth
@@ -487,6 +513,12 @@ public:
     // gen_halide_obj() runs the whole lowering.  A function without gpu levels is a CPU schedule; this
     // back end has no CPU code generator, so such a function is re-targeted (lowering_retarget.cpp).
     void add_context_constraints(const std::string &) {}
+    /** Reference core.h:1080: pads every schedule to the same number of dimensions; loop lists need no padding. */
+    void align_schedules() {}
+    /** Turn the ordering numbers of after_low_level into the then()/after() chain the lowering walks (no-op when the
+      * function never called after_low_level; mixing it with then()/after() is refused). */
+    void resolve_static_order();
+    void note_static_order() { static_order_ = true; }
     /** Reference core.h:865: turns communicators into library calls; the lowering does that on its own. */
     void lift_dist_comps() {}
     void gen_time_space_domain() {}
@@ -516,6 +548,7 @@ private:
     std::vector<std::shared_ptr<void>> owned_;
     int counter_ = 0;
     bool cuda_requested_ = false;
+    bool static_order_ = false;
 };
 
 }  // namespace tiramisu

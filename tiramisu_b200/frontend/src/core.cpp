@@ -1,6 +1,8 @@
 // core.cpp — buffers, computations and scheduling commands of the tiramisu_b200 front-end
 // (see include/tiramisu/core.h).  A schedule is a list of named loop dimensions; every command
 // rewrites the list and records how older names are rebuilt from newer ones.
+#include <algorithm>
+#include <set>
 #include <tiramisu/block.h>
 #include <tiramisu/core.h>
 
@@ -26,6 +28,133 @@ function::function(std::string name) : name_(std::move(name))
 void function::gen_halide_obj(const std::string &obj_file_name, bool)
 {
     codegen(args_, obj_file_name, cuda_requested_);
+}
+
+void function::resolve_static_order()
+{
+    if (!static_order_) return;
+    std::vector<computation *> sched;
+    for (computation *c : comps_) {
+        if (c->is_input() || c->is_constant() || !c->should_schedule_this_computation()) continue;
+        if (c->pred_ || c->succ_)
+            die("'" + c->get_name() + "' is ordered with then()/after() in a function that also uses after_low_level: one style per function");
+        sched.push_back(c);
+    }
+    auto num = [](const computation *c, size_t k) { return k < c->static_.size() ? c->static_[k] : 0; };
+    size_t depth = 0;
+    for (computation *c : sched) depth = std::max(depth, c->static_.size());
+    // lexicographic order of the number vectors; statements with equal vectors keep their declaration order
+    std::stable_sort(sched.begin(), sched.end(), [&](const computation *a, const computation *b) {
+        for (size_t k = 0; k < depth; k++)
+            if (num(a, k) != num(b, k)) return num(a, k) < num(b, k);
+        return false;
+    });
+    // ---- statements cut into pieces: the older generators write one statement per full / partial tile region
+    // (sgemm_generator.cpp:90-110: `reduced_AB_1`, `_p0`, `_p1`, `_p2`) because their CPU code generator wants the full
+    // tiles free of guards.  Consecutive statements with the same expression, the same store and iterator boxes that
+    // partition one box ARE one statement over that box; the device lowering (and its pattern recognition) sees that one.
+    std::set<computation *> merged;
+    auto same_statement = [](computation *a, computation *b) {
+        if (a->dtype_ != b->dtype_ || a->buf_ != b->buf_ || !a->buf_ || a->predicate_.is_defined() || b->predicate_.is_defined()) return false;
+        if (!a->expr_.is_defined() || !b->expr_.is_defined() || !a->expr_.is_equal(b->expr_)) return false;
+        if (a->iters_.size() != b->iters_.size() || a->access_.size() != b->access_.size()) return false;
+        for (size_t d = 0; d < a->iters_.size(); d++)
+            if (a->iters_[d].get_name() != b->iters_[d].get_name() || !a->iters_[d].has_range() || !b->iters_[d].has_range()) return false;
+        for (size_t d = 0; d < a->access_.size(); d++)
+            if (!a->access_[d].is_equal(b->access_[d])) return false;
+        return true;
+    };
+    auto referenced_elsewhere = [&](computation *c, size_t lo_i, size_t hi_i) {
+        for (size_t q = 0; q < sched.size(); q++) {
+            if (q >= lo_i && q < hi_i) continue;
+            std::vector<expr> stack{sched[q]->expr_, sched[q]->predicate_};
+            while (!stack.empty()) {
+                expr x = stack.back(); stack.pop_back();
+                if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+                if (x.get_op_type() == o_access && x.get_name() == c->get_name()) return true;
+                for (const expr &o : x.get_operands()) stack.push_back(o);
+            }
+        }
+        return false;
+    };
+    for (size_t i = 0; i < sched.size();) {
+        size_t e = i + 1;
+        while (e < sched.size() && same_statement(sched[i], sched[e])) e++;
+        const size_t n = e - i, nd = sched[i]->iters_.size();
+        bool ok = n > 1;
+        std::vector<std::pair<expr, expr>> box(nd);
+        size_t combos = 1;
+        for (size_t d = 0; d < nd && ok; d++) {
+            std::vector<std::pair<expr, expr>> uniq;
+            for (size_t q = i; q < e; q++) {
+                const var &v = sched[q]->iters_[d];
+                bool seen = false;
+                for (auto &u : uniq) seen |= u.first.is_equal(v.get_lower()) && u.second.is_equal(v.get_upper());
+                if (!seen) uniq.push_back({v.get_lower(), v.get_upper()});
+            }
+            if (uniq.size() == 1) box[d] = uniq[0];
+            else if (uniq.size() == 2 && uniq[0].second.is_equal(uniq[1].first)) box[d] = {uniq[0].first, uniq[1].second};
+            else if (uniq.size() == 2 && uniq[1].second.is_equal(uniq[0].first)) box[d] = {uniq[1].first, uniq[0].second};
+            else ok = false;
+            combos *= uniq.size();
+        }
+        ok = ok && combos == n;
+        for (size_t q = i; q < e && ok; q++)            // every piece a different region (with combos == n: every region once)
+            for (size_t r = q + 1; r < e && ok; r++) {
+                bool same = true;
+                for (size_t d = 0; d < nd; d++)
+                    same &= sched[q]->iters_[d].get_lower().is_equal(sched[r]->iters_[d].get_lower()) && sched[q]->iters_[d].get_upper().is_equal(sched[r]->iters_[d].get_upper());
+                ok = !same;
+            }
+        computation *base = nullptr;
+        for (size_t q = i; q < e && ok; q++)
+            if (referenced_elsewhere(sched[q], i, e)) { if (base) ok = false; base = sched[q]; }
+        if (!ok) { i++; continue; }
+        if (!base) base = sched[i];
+        std::string names;
+        for (size_t q = i; q < e; q++) names += (q > i ? ", " : "") + sched[q]->get_name();
+        std::cerr << "tiramisu_b200 front-end: note: statements {" << names << "} are the pieces of one statement over one box; lowered as '" << base->get_name() << "'\n";
+        for (size_t d = 0; d < nd; d++) base->iters_[d] = var(base->iters_[d].get_name(), box[d].first, box[d].second);
+        base->dims_.clear(); base->defs_.clear(); base->guards_.clear();
+        for (const var &v : base->iters_) { loop_dim ld; ld.name = v.get_name(); ld.lo = v.get_lower(); ld.hi = v.get_upper(); base->dims_.push_back(ld); }
+        // the schedule of the pieces (tile sizes, unroll / vector levels) described the CPU loop nest of each piece;
+        // the merged statement gets the plain data-parallel CPU schedule the re-targeting starts from
+        base->parallelize(base->iters_[0]);
+        if (nd >= 2 && !(box[1].second - box[1].first).is_int_literal()) base->vectorize(base->iters_[1], 8);
+        merged.insert(base);
+        for (size_t q = i; q < e; q++)
+            if (sched[q] != base) comps_.erase(std::remove(comps_.begin(), comps_.end(), sched[q]), comps_.end());
+        sched.erase(sched.begin() + i, sched.begin() + e);
+        sched.insert(sched.begin() + i, base);
+        i++;
+    }
+    // ---- a temporary nobody reads (sgemm_generator.cpp packs B into buf_Bp and then multiplies with B itself): not computed
+    for (size_t i = 0; i < sched.size();) {
+        computation *c = sched[i];
+        bool read = !c->buf_ || c->buf_->get_argument_type() != a_temporary;
+        for (computation *o : comps_) {
+            if (read) break;
+            if (o->buf_ != c->buf_) continue;
+            read = referenced_elsewhere(o, sched.size(), sched.size()) && true;
+        }
+        if (read) { i++; continue; }
+        std::cerr << "tiramisu_b200 front-end: note: '" << c->get_name() << "' fills the temporary '" << c->buf_->get_name() << "' that nothing reads; not computed\n";
+        comps_.erase(std::remove(comps_.begin(), comps_.end(), c), comps_.end());
+        sched.erase(sched.begin() + i);
+    }
+    for (size_t i = 1; i < sched.size(); i++) {
+        computation *a = sched[i - 1], *b = sched[i];
+        if (merged.count(a) || merged.count(b)) { b->link_after(*a, "", -1); continue; }      // fresh loop nests: the old depths mean nothing
+        size_t k = 0;
+        while (k < depth && num(a, k) == num(b, k)) k++;
+        // equal numbers at depths 0..k-1: the two share loops 0..k-2 and are ordered below loop k-2 ... the number at depth d
+        // orders statements INSIDE loop d-1, so sharing loops 0..k-1 needs equal numbers at depths 0..k and a difference at
+        // depth k+1.  Equal vectors altogether (the reference then interleaves by iterator value; the statements of such a
+        // pair are independent): one after the other at root.
+        int level = k >= depth ? -1 : (int) k - 1;
+        level = std::min(level, std::min((int) a->dims().size(), (int) b->dims().size()) - 1);
+        b->link_after(*a, "", level);
+    }
 }
 
 computation *function::find_computation(const std::string &name) const
@@ -253,6 +382,46 @@ void computation::tile(var L0, var L1, var L2, int sx, int sy, int sz)
     auto o = [](const var &v) { return var(v.get_name() + "_o"); };
     auto i = [](const var &v) { return var(v.get_name() + "_i"); };
     tile(L0, L1, L2, sx, sy, sz, o(L0), o(L1), o(L2), i(L0), i(L1), i(L2));
+}
+
+void computation::after_low_level(computation &b, int level)
+{
+    if (&b == this) die("a computation cannot be ordered after itself: " + name_);
+    if (level < -1) die("after_low_level: level " + std::to_string(level) + " of '" + name_ + "'");
+    const size_t need = (size_t) level + 2;
+    if (static_.size() < need) static_.resize(need, 0);
+    if (b.static_.size() < need) b.static_.resize(need, 0);
+    for (int k = 0; k <= level; k++) static_[k] = b.static_[k];
+    static_[level + 1] = b.static_[level + 1] + 10;
+    if (fct_) fct_->note_static_order();
+}
+
+// ---- by level
+static var level_var(computation &c, int L, const char *what)
+{
+    if (L < 0 || L >= (int) c.dims().size())
+        die(std::string(what) + ": '" + c.get_name() + "' has " + std::to_string(c.dims().size()) + " loop levels, level " + std::to_string(L) + " asked for");
+    return var(c.dims()[L].name);
+}
+void computation::split(int L0, int f) { split(level_var(*this, L0, "split"), f); }
+void computation::tile(int L0, int L1, int sx, int sy) { tile(level_var(*this, L0, "tile"), level_var(*this, L1, "tile"), sx, sy); }
+void computation::tile(int L0, int L1, int L2, int sx, int sy, int sz)
+{
+    tile(level_var(*this, L0, "tile"), level_var(*this, L1, "tile"), level_var(*this, L2, "tile"), sx, sy, sz);
+}
+void computation::interchange(int L0, int L1) { interchange(level_var(*this, L0, "interchange"), level_var(*this, L1, "interchange")); }
+// A tag on a level the statement does not have matches no loop: the reference keeps (statement, level) pairs and looks them
+// up while it walks the generated loops (src/tiramisu_core.cpp: tag_unroll_level / should_unroll), so such a tag is inert
+// there too — sgemm_generator.cpp:262 relies on it.
+static bool has_level(computation &c, int L) { return L >= 0 && L < (int) c.dims().size(); }
+void computation::tag_parallel_level(int L) { if (has_level(*this, L)) tag_parallel_level(level_var(*this, L, "tag_parallel_level")); }
+void computation::tag_vector_level(int L, int v) { if (has_level(*this, L)) tag_vector_level(level_var(*this, L, "tag_vector_level"), v); }
+void computation::tag_unroll_level(int L) { if (has_level(*this, L)) tag_unroll_level(level_var(*this, L, "tag_unroll_level")); }
+void computation::tag_gpu_level(int L0, int L1) { tag_gpu_level(level_var(*this, L0, "tag_gpu_level"), level_var(*this, L1, "tag_gpu_level")); }
+void computation::tag_gpu_level(int L0, int L1, int L2, int L3)
+{
+    tag_gpu_level(level_var(*this, L0, "tag_gpu_level"), level_var(*this, L1, "tag_gpu_level"), level_var(*this, L2, "tag_gpu_level"),
+                  level_var(*this, L3, "tag_gpu_level"));
 }
 
 void computation::tag(const var &L, loop_dim::tag_t t)

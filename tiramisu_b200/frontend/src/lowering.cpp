@@ -430,6 +430,7 @@ using lowering_detail::die;
 void function::codegen(const std::vector<buffer *> &arguments, const std::string obj_filename, bool gen_cuda_stmt)
 {
     set_arguments(arguments);
+    resolve_static_order();
     Lowering l(this, arguments, gen_cuda_stmt);
     std::string src = l.run();
     std::string cu = obj_filename + ".b200.cu";

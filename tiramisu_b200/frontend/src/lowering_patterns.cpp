@@ -150,12 +150,18 @@ bool Lowering::match_zero_fill(computation *z, buffer *C, const expr &M, const e
 {
     auto is_var = [](const expr &x, const std::string &n) { return x.get_expr_type() == e_var && x.get_name() == n; };
     const auto &zi = z->get_iteration_variables();
-    if (!z->get_expr().is_defined() || z->get_predicate().is_defined() || zi.size() != 2) return false;
+    if (!z->get_expr().is_defined() || z->get_predicate().is_defined() || zi.size() < 2) return false;
+    // further iterators must be single points the store does not name (`{acc[i,j,0]: ...}`, sgemm_generator.cpp:90)
+    for (size_t q = 2; q < zi.size(); q++) {
+        if (!(zi[q].get_lower().is_int_literal() && zi[q].get_upper().is_int_literal() && zi[q].get_upper().get_int_val() == zi[q].get_lower().get_int_val() + 1)) return false;
+        for (const expr &a : z->access())
+            if (!a.substitute({zi[q].get_name()}, {expr((int32_t) 0)}).is_equal(a)) return false;
+    }
     if (z->get_buffer() != C || z->access().size() != 2) return false;
     if (!(z->get_expr().is_literal() && z->get_expr().get_double_val() == 0.0)) return false;
     if (!is_var(z->access()[0], zi[0].get_name()) || !is_var(z->access()[1], zi[1].get_name())) return false;
     if (!zi[0].get_upper().is_equal(M) || !zi[1].get_upper().is_equal(N)) return false;
-    for (const var &v : zi) if (!(v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0)) return false;
+    for (size_t q = 0; q < 2; q++) if (!(zi[q].get_lower().is_int_literal() && zi[q].get_lower().get_int_val() == 0)) return false;
     return true;
 }
 
