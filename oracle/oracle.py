@@ -221,3 +221,57 @@ def transpose_f32(A: np.ndarray) -> np.ndarray:
     out = np.empty((c, r), dtype=np.float32)
     lib().oracle_transpose_f32(_p(A), _p(out), C.c_int(r), C.c_int(c))
     return out
+
+def conv_layer_blocked(inp: np.ndarray, filt: np.ndarray, bias: np.ndarray) -> np.ndarray:
+    """The direct convolution layer with blocked layouts (reference
+    benchmarks/DNN/layers/convolution/direct/cpu/conv_layer_generator_tiramisu.cpp:21-45, Layer I only):
+        out[n][fout_b][y][x][ffout] = bias[fout_b][ffout]
+                                      + sum over fin_b, k_y, k_x, ffin of filt[fout_b][fin_b][k_y][k_x][ffin][ffout]
+                                                                          * inp[n][fin_b][y + k_y][x + k_x][ffin]
+    in float64 (numpy), rounded to float32 at the end — a checker for a float kernel, compared with a tolerance.
+    Parity unpinned: the reference holds no golden output for this layer (its wrapper compares with MKL-DNN, absent here)."""
+    inp = np.asarray(inp, np.float64)
+    filt = np.asarray(filt, np.float64)
+    n, finb, yp, xp, ffin = inp.shape
+    foutb, finb2, ky, kx, ffin2, ffout = filt.shape
+    assert finb == finb2 and ffin == ffin2 and ky == kx
+    y, x = yp - ky + 1, xp - kx + 1
+    out = np.zeros((n, foutb, y, x, ffout), np.float64)
+    for dy in range(ky):
+        for dx in range(kx):
+            win = inp[:, :, dy:dy + y, dx:dx + x, :]                          # n b y x i
+            out += np.einsum("nbyxi,obif->noyxf", win, filt[:, :, dy, dx, :, :], optimize=True)
+    out += np.asarray(bias, np.float64).reshape(1, foutb, 1, 1, ffout)
+    return out.astype(np.float32)
+
+
+def vgg_block(inp: np.ndarray, f1: np.ndarray, b1: np.ndarray, f2: np.ndarray, b2: np.ndarray):
+    """The dense VGG block (reference benchmarks/DNN/blocks/vggBlock/cpu/dense/vgg_block_generator_tiramisu.cpp:15-96,
+    Layer I only), float64, rounded to float32 at the end:
+        conv1[n][b][y][x][f]  = relu(bias1[b][f] + sum over k_y, k_x, fin1 of f1[b][k_y][k_x][fin1][f] * inp[n][y+k_y][x+k_x][fin1])
+        padded                = conv1 with a one-element zero border                               (conv1_buf, second result)
+        conv2[n][y][x][o][g]  = bias2[o][g] + sum over b, k_y, k_x, f of f2[o][b][k_y][k_x][f][g] * padded[n][b][y+k_y][x+k_x][f]
+        out[n][o][y/2][x/2][g] = max(0, conv2 over the 2 x 2 window)                               (max-pool initialised with 0)
+    Returns (padded, out).  Parity unpinned: the reference's wrapper compares with MKL-DNN, absent here."""
+    inp, f1, f2 = np.asarray(inp, np.float64), np.asarray(f1, np.float64), np.asarray(f2, np.float64)
+    n, yp, xp, fin1 = inp.shape
+    nb, ky, kx, _, nf = f1.shape
+    y, x = yp - ky + 1, xp - kx + 1
+    c1 = np.zeros((n, nb, y, x, nf), np.float64)
+    for dy in range(ky):
+        for dx in range(kx):
+            c1 += np.einsum("nyxi,bif->nbyxf", inp[:, dy:dy + y, dx:dx + x, :], f1[:, dy, dx, :, :], optimize=True)
+    c1 = np.maximum(c1 + np.asarray(b1, np.float64).reshape(1, nb, 1, 1, nf), 0.0)
+    padded = np.zeros((n, nb, y + 2, x + 2, nf), np.float64)
+    padded[:, :, 1:-1, 1:-1, :] = c1
+    no, _, _, _, _, ng = f2.shape
+    c2 = np.zeros((n, y, x, no, ng), np.float64)
+    for dy in range(ky):
+        for dx in range(kx):
+            c2 += np.einsum("nbyxf,obfg->nyxog", padded[:, :, dy:dy + y, dx:dx + x, :], f2[:, :, dy, dx, :, :], optimize=True)
+    c2 += np.asarray(b2, np.float64).reshape(1, 1, 1, no, ng)
+    out = np.zeros((n, no, y // 2, x // 2, ng), np.float64)
+    for dy in range(2):
+        for dx in range(2):
+            out = np.maximum(out, c2[:, dy:2 * (y // 2):2, dx:2 * (x // 2):2, :, :].transpose(0, 3, 1, 2, 4))
+    return padded.astype(np.float32), out.astype(np.float32)

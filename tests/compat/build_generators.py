@@ -60,6 +60,18 @@ TARGETS = {
     # Layers I/III and lowered to the runtime's fused kernel (with the pattern lowering off the generator is refused)
     "conv_block": ("benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/conv_relu_maxpool_generator_tiramisu.cpp", "conv_relu_maxpool_tiramisu.o",
                    "benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/wrapper_nn_block.cpp", ["benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense"], []),
+    # the direct convolution LAYER (blocked layouts, accumulators register-blocked through a 4 x 3 x 8 staging
+    # buffer, a conclude column).  Its wrapper needs MKL-DNN, so the object becomes a shared library checked against
+    # oracle.conv_layer_blocked; `conv_layer_small` is the same unmodified source with a small configure.h (SCRATCH).
+    "conv_layer": ("benchmarks/DNN/layers/convolution/direct/cpu/conv_layer_generator_tiramisu.cpp", "generated_conv_layer.o", None,
+                   ["benchmarks/DNN/layers/convolution/direct/cpu"], []),
+    "conv_layer_small": ("benchmarks/DNN/layers/convolution/direct/cpu/conv_layer_generator_tiramisu.cpp", "generated_conv_layer.o", None, [], []),
+    # the VGG block (conv 3x3 + ReLU, conv 3x3 + ReLU + 2x2 max-pool, blocked layouts): accumulators register-blocked
+    # through two staging buffers that are consumed by ReLU / max-pool (not stored back), a weight-prefetch loop, a conclude
+    # column.  Wrapper needs MKL-DNN -> shared library, checked against oracle.vgg_block.
+    "vgg_block": ("benchmarks/DNN/blocks/vggBlock/cpu/dense/vgg_block_generator_tiramisu.cpp", "generated_vgg_block.o", None,
+                  ["benchmarks/DNN/blocks/vggBlock/cpu/dense"], []),
+    "vgg_block_small": ("benchmarks/DNN/blocks/vggBlock/cpu/dense/vgg_block_generator_tiramisu.cpp", "generated_vgg_block.o", None, [], []),
     # the other `*gpu` Halide benchmarks (benchmarks/benchmark_list.txt) — image stencils / pointwise colour
     # transforms written against the old ISL-string API with hand-placed shared-memory tiles, constant-memory taps,
     # register temporaries and clamped accesses.  Their wrappers need Halide-generated reference pipelines and PNG I/O,
@@ -88,6 +100,11 @@ GEN_DEFS = {"halide_heat2dgpu": ["-DUSE_GPU2"]}
 
 # files a generator opens relative to its working directory: name -> {link name: target under the reference checkout}
 RUN_LINKS = {"halide_blurxy": {"utils/images": "utils/images"}}
+
+# generators compiled from a scratch copy (never committed) so that a header of this repo takes the place of one they include
+# with quotes: name -> {file name in the scratch directory: source under this repo}
+SCRATCH = {"conv_layer_small": {"configure.h": "tests/compat/conv_layer_small/configure.h"},
+           "vgg_block_small": {"configure.h": "tests/compat/vgg_block_small/configure.h"}}
 
 PATCHES = {
     "lstm_gpu_fixed": [
@@ -132,6 +149,11 @@ def build_one(name: str, lowering: str | None = None) -> tuple[int, str]:
         gen_src = os.path.join(work, "generator_patched.cpp")
         with open(gen_src, "w") as f:
             f.write(text)
+    if name in SCRATCH:
+        shutil.copy(gen_src, os.path.join(work, "generator_copy.cpp"))
+        gen_src = os.path.join(work, "generator_copy.cpp")
+        for fname, src in SCRATCH[name].items():
+            shutil.copy(os.path.join(ROOT, src), os.path.join(work, fname))
     # 1. the reference generator, unmodified, against this repo's front-end
     cmd = ["g++", "-std=c++17", "-O1", "-w", *GEN_DEFS.get(name, []), "-I", FRONT_INC, "-I", os.path.join(FRONT_INC, "compat"), *inc, gen_src, "-o", gen_exe,
            f"-L{LIBDIR}", "-ltiramisu_b200_frontend", f"-Wl,-rpath,{LIBDIR}"]

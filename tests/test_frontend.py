@@ -271,6 +271,99 @@ def test_reference_sgemm_gpu_generators_match_cublas(gen, tmp_path):
     assert "cuBLAS and Tiramisu outputs match" in out, out[-2000:]
 
 
+def _conv_layer_check(lib, batch, n, fin, fout, rtol):
+    """conv_layer_generator_tiramisu.cpp's function on the wrapper's kind of data ((rand() % 256 - 128) / 127) against the
+    float64 restatement of its Layer I; element-wise tolerance relative to the magnitude of the sum's terms."""
+    from oracle import oracle
+    from tiramisu_b200.halide import Buffer
+    rng = np.random.default_rng(n + fin)
+    draw = lambda shape: ((rng.integers(0, 256, shape) - 128) / 127.0).astype(np.float32)
+    inp, filt, bias = draw((batch, fin // 16, n + 2, n + 2, 16)), draw((fout // 8, fin // 16, 3, 3, 16, 8)), draw((fout // 8, 8))
+    out = np.full((batch, fout // 8, n, n, 8), 7.0, np.float32)
+    f = lib.conv_tiramisu
+    f.restype = C.c_int
+    bufs = [Buffer(inp), Buffer(filt), Buffer(bias), Buffer(out)]
+    assert f(*[b.ptr() for b in bufs]) == 0
+    want = oracle.conv_layer_blocked(inp, filt, bias)
+    scale = np.sqrt(9.0 * fin)                       # |sum of 9 fin products of values in [-1, 1]| is of this order
+    assert float(np.abs(out - want).max()) <= rtol * scale, float(np.abs(out - want).max())
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference")
+def test_reference_conv_layer_generator_emulated(frontend_lib):
+    """DNN/layers/convolution/direct/cpu/conv_layer_generator_tiramisu.cpp, unmodified source with a small configure.h
+    (tests/compat/conv_layer_small): the load / accumulate / store triples through the register-blocking buffer become
+    in-place accumulations, the reduction loops sink below the output loops, the loops shared with conv_init are
+    distributed — three kernels, one launch each — and the result matches the float64 restatement."""
+    from tests.emulation import emulate
+    src = os.path.join(bg.GEN, "conv_layer_small", "generated_conv_layer.o.b200.cu")
+    if not os.path.exists(src):
+        bg.build(["conv_layer_small"])
+    text = open(src).read()
+    assert text.count("__global__") == 3 and "reg_buf" not in text.split("extern \"C\" int conv_tiramisu(")[1].replace("b_reg_buf", "")
+    lib = C.CDLL(emulate.build_shared([src], "conv_layer_small"))
+    _conv_layer_check(lib, 2, 10, 32, 64, 2e-6)
+
+
+@pytest.mark.gpu
+def test_reference_conv_layer_generator_on_device():
+    """The same generator with the reference's own configure.h (batch 8, 112 x 112, 128 -> 256 features) on the device."""
+    path = os.path.join(bg.BIN, "libgen_conv_layer.so")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not built (tests/compat/build_generators.py needs /root/reference)")
+    from tiramisu_b200 import _lib
+    _lib.lib()
+    _conv_layer_check(C.CDLL(path, mode=C.RTLD_GLOBAL), 8, 112, 128, 256, 2e-6)
+
+
+def _vgg_block_check(lib, batch, n, fout, rtol):
+    from oracle import oracle
+    from tiramisu_b200.halide import Buffer
+    rng = np.random.default_rng(n + fout)
+    draw = lambda shape: ((rng.integers(0, 256, shape) - 128) / 127.0).astype(np.float32)
+    nb = fout // 8
+    inp, f1, b1 = draw((batch, n + 2, n + 2, 3)), draw((nb, 3, 3, 3, 8)), draw((nb, 8))
+    f2, b2 = draw((nb, nb, 3, 3, 8, 8)), draw((nb, 8))
+    conv1 = np.full((batch, nb, n + 2, n + 2, 8), 5.0, np.float32)
+    out = np.full((batch, nb, n // 2, n // 2, 8), 7.0, np.float32)
+    f = lib.vgg_block
+    f.restype = C.c_int
+    bufs = [Buffer(inp), Buffer(f1), Buffer(b1), Buffer(f2), Buffer(b2), Buffer(conv1), Buffer(out)]
+    assert f(*[b.ptr() for b in bufs]) == 0
+    want1, want = oracle.vgg_block(inp, f1, b1, f2, b2)
+    assert float(np.abs(conv1 - want1).max()) <= rtol * np.sqrt(27.0), float(np.abs(conv1 - want1).max())
+    scale = np.sqrt(9.0 * fout) * max(1.0, float(np.abs(want1).max()))
+    assert float(np.abs(out - want).max()) <= rtol * scale, float(np.abs(out - want).max())
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference")
+def test_reference_vgg_block_generator_emulated(frontend_lib):
+    """DNN/blocks/vggBlock/cpu/dense/vgg_block_generator_tiramisu.cpp, unmodified source with a small configure.h: the
+    weight-prefetch loop is dropped, the two register-blocking buffers get their full extent back, the fused nest is
+    distributed level by level (the max-pool and its conclude column commute) — eleven kernels, one launch each, no host
+    loop — and both results (the padded first activation and the pooled output) match the float64 restatement."""
+    from tests.emulation import emulate
+    src = os.path.join(bg.GEN, "vgg_block_small", "generated_vgg_block.o.b200.cu")
+    if not os.path.exists(src):
+        bg.build(["vgg_block_small"])
+    text = open(src).read()
+    host = text.split("extern \"C\" int vgg_block(")[1]
+    assert text.count("static __global__") == 11 and host.count("<<<") == 11 and host.count("for (int32_t") == 0
+    lib = C.CDLL(emulate.build_shared([src], "vgg_block_small"))
+    _vgg_block_check(lib, 2, 16, 16, 2e-6)
+
+
+@pytest.mark.gpu
+def test_reference_vgg_block_generator_on_device():
+    """The same generator with the reference's own configure.h (batch 32, 112 x 112, 3 -> 32 -> 32 features) on the device."""
+    path = os.path.join(bg.BIN, "libgen_vgg_block.so")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not built (tests/compat/build_generators.py needs /root/reference)")
+    from tiramisu_b200 import _lib
+    _lib.lib()
+    _vgg_block_check(C.CDLL(path, mode=C.RTLD_GLOBAL), 32, 112, 32, 2e-6)
+
+
 def _sgemm_cpu_generator_check(lib, shapes):
     from tiramisu_b200.halide import Buffer
     f = lib.sgemm_tiramisu

@@ -327,6 +327,15 @@ public:
     computation *succ() const { return succ_; }
     const std::string &pred_level() const { return pred_level_; }
     int pred_level_index() const { return pred_level_index_; }
+    /** Lowering: take the statement out of the program (its work was folded into a neighbour); the successor follows the
+      * predecessor, sharing loops 0..\p succ_level_index with it. */
+    void remove_from_order(int succ_level_index)
+    {
+        if (pred_) pred_->succ_ = succ_;
+        if (succ_) { succ_->pred_ = pred_; succ_->pred_level_.clear(); succ_->pred_level_index_ = pred_ ? succ_level_index : -1; }
+        pred_ = succ_ = nullptr;
+        scheduled_ = false;
+    }
     /** Lowering: share loops 0..level_index with the predecessor in the order (nest fusion). */
     void set_pred_level_index(int level_index) { pred_level_index_ = level_index; }
     bool is_input() const { return is_input_; }

@@ -218,6 +218,7 @@ std::string Lowering::run()
         if (b->get_location() != mem_loc::host && b->get_location() != mem_loc::gpu_global)
             die("argument buffer '" + b->get_name() + "' is tagged on-chip");
 
+    if (pattern_ && !cuda_) { drop_dead_temporaries(); forward_private_temporaries(); expand_private_temporaries(); }
     std::vector<computation *> ord = order();
     n_statements_ = ord.size();
     bool any_gpu = false;

@@ -4,6 +4,7 @@
 //   lowering_patterns.cpp  pattern lowerings: contractions -> runtime GEMM, sgemm statement triple, heat2d pair, conv block idiom
 //   lowering_dist.cpp      distributed levels (rank scope), send / recv / wait -> tiramisu_MPI_* on device addresses, message coalescing
 //   lowering_retarget.cpp  CPU schedules -> GPU: constants, device mirrors, mapping, warp-shuffle reduction, loop distribution, nest fusion
+//   lowering_forward.cpp   CPU register blocking undone: load / accumulate / store through a private staging buffer -> accumulate in place
 #ifndef TIRAMISU_B200_FRONTEND_LOWERING_H
 #define TIRAMISU_B200_FRONTEND_LOWERING_H
 
@@ -108,6 +109,12 @@ private:
     struct ExtentRewrite { buffer *b; expr from, to; };
     std::vector<ExtentRewrite> extent_rewrites_;
     void retarget(const std::vector<computation *> &ord);
+    void sink_reduction_loops(const std::vector<computation *> &ord);
+    bool changed_ = false;                                              // distribute_parallel_shared_loops lowered a boundary
+    bool forward_private_temporaries();                                 // lowering_forward.cpp
+    bool expand_private_temporaries();
+    bool drop_dead_temporaries();
+    bool staging_triple(const std::vector<computation *> &ord, size_t i, bool apply);
     void mirror_buffers(const std::vector<computation *> &ord, bool gpu_only);
     void auto_map(computation *c, int shared_depth);
     void fuse_pointwise_nests(const std::vector<computation *> &ord, const std::vector<int> &shared);

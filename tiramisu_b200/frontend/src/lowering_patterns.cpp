@@ -153,7 +153,7 @@ bool Lowering::match_zero_fill(computation *z, buffer *C, const expr &M, const e
     if (!z->get_expr().is_defined() || z->get_predicate().is_defined() || zi.size() < 2) return false;
     // further iterators must be single points the store does not name (`{acc[i,j,0]: ...}`, sgemm_generator.cpp:90)
     for (size_t q = 2; q < zi.size(); q++) {
-        if (!(zi[q].get_lower().is_int_literal() && zi[q].get_upper().is_int_literal() && zi[q].get_upper().get_int_val() == zi[q].get_lower().get_int_val() + 1)) return false;
+        if (!(zi[q].get_lower().is_int_literal() && zi[q].get_lower().get_int_val() == 0 && zi[q].get_upper().is_int_literal() && zi[q].get_upper().get_int_val() == 1)) return false;
         for (const expr &a : z->access())
             if (!a.substitute({zi[q].get_name()}, {expr((int32_t) 0)}).is_equal(a)) return false;
     }

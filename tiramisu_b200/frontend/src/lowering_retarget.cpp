@@ -369,34 +369,112 @@ void Lowering::distribute_parallel_shared_loops(const std::vector<computation *>
             // how many leading loops the whole run shares
             int common = INT32_MAX;
             for (size_t k = i + 1; k < j; k++) common = std::min(common, fuse_depth(ord[k - 1], ord[k]));
-            // keep = the shared loops that must stay sequential: everything down to the innermost non-parallel one
+            // keep = the shared loops that must stay fused.  A loop that is data parallel for every statement of the run can be
+            // un-fused when the statements only exchange values element-wise (below).  A loop that is NOT (a max-pool
+            // accumulating over y and x into out[y/2][x/2], vgg_block_generator_tiramisu.cpp:75-84) can still be split BETWEEN
+            // statements — each keeps its own iterations in order — when every value that crosses from one statement to another
+            // does so inside one iteration of it: some dimension of the buffer is indexed, in both accesses, by the same plain
+            // iterator built the same way from that loop (same element => same iteration).
             int keep = 0;
             if (ok) {
+                std::vector<bool> par_all((size_t) common, true);
                 for (int d = 0; d < common; d++)
                     for (size_t k = i; k < j; k++)
-                        if (!dim_is_parallel(ord[k], ord[k]->dims()[d].name)) keep = d + 1;
-                // element-wise exchange only
-                std::vector<Access> seen;
-                for (size_t k = i; k < j && ok; k++) {
-                    std::vector<Access> mine = accesses_of(ord[k]);
-                    for (const Access &p : mine)
-                        for (const Access &q : seen) {
-                            if (p.b != q.b || (!p.write && !q.write)) continue;
-                            bool identical = p.idx.size() == q.idx.size();
-                            for (size_t t = 0; identical && t < p.idx.size(); t++) identical = p.idx[t].is_equal(q.idx[t]);
-                            if (!identical) ok = false;
+                        if (!dim_is_parallel(ord[k], ord[k]->dims()[d].name)) par_all[(size_t) d] = false;
+                auto in_dims = [](computation *c, expr e) { for (auto &df : c->defs()) e = e.substitute({df.first}, {df.second}); return e; };
+                auto mentions = [](const expr &e, const std::string &n) { return !e.substitute({n}, {expr((int32_t) 0)}).is_equal(e) || (e.get_expr_type() == e_var && e.get_name() == n); };
+                auto same_dims = [&](computation *a, computation *b, const expr &e) {      // the loops e names have the same range in a and b
+                    for (const loop_dim &x : a->dims()) {
+                        if (!mentions(e, x.name)) continue;
+                        const int o = b->find_dim(x.name);
+                        if (o < 0 || !b->dims()[(size_t) o].lo.is_equal(x.lo) || !b->dims()[(size_t) o].hi.is_equal(x.hi)) return false;
+                    }
+                    return true;
+                };
+                // loops [from, common) un-fused: are p (statement a) and q (statement b) the same element only in the same iteration?
+                auto compatible = [&](computation *a, const Access &p, computation *b, const Access &q, int from) {
+                    if (p.idx.size() != q.idx.size()) return false;
+                    std::set<int> pinned, pinned_plain;
+                    bool all_identical = true;
+                    for (size_t t = 0; t < p.idx.size(); t++) {
+                        const expr pa = in_dims(a, p.idx[t]), qb = in_dims(b, q.idx[t]);
+                        const bool identical = p.idx[t].is_equal(q.idx[t]);
+                        all_identical &= identical;
+                        bool p_sh = false, q_sh = false;
+                        for (int d = from; d < common; d++) { p_sh |= mentions(pa, a->dims()[d].name); q_sh |= mentions(qb, b->dims()[d].name); }
+                        if (identical && pa.is_equal(qb) && same_dims(a, b, pa)) {
+                            for (int d = from; d < common; d++)
+                                if (mentions(pa, a->dims()[d].name)) { pinned.insert(d); if (p.idx[t].get_expr_type() == e_var) pinned_plain.insert(d); }
+                        } else if (!identical && (p_sh || q_sh)) return false;
+                    }
+                    for (int d = from; d < common; d++) {
+                        if (!par_all[(size_t) d]) { if (!pinned_plain.count(d)) return false; }
+                        else if (!all_identical && !pinned.count(d)) return false;
+                    }
+                    return true;
+                };
+                // out[f] = max(out[f], v) with v not reading out (min likewise): updates of this kind on one buffer commute
+                // exactly, whichever statement they come from (a max-pool and its conclude column meet in the same output
+                // element, vgg_block_generator_tiramisu.cpp:75-96); 0 = not such a statement
+                auto commutative_update = [&](computation *c) -> int {
+                    const expr &e = c->get_expr();
+                    if (!c->has_access() || !e.is_defined() || e.get_expr_type() != e_op || (e.get_op_type() != o_max && e.get_op_type() != o_min)) return 0;
+                    int self = 0, others = 0;
+                    for (int side = 0; side < 2; side++) {
+                        const expr &x = e.get_operand(side);
+                        bool is_self = false;
+                        if (x.get_expr_type() == e_op && x.get_op_type() == o_access) {
+                            computation *oc = nullptr;
+                            if (buffer_of_access(x, &oc) == c->get_buffer() && (int) oc->get_iteration_variables().size() == x.get_n_arg() &&
+                                oc->access().size() == c->access().size()) {
+                                std::vector<std::string> names;
+                                for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+                                is_self = true;
+                                for (size_t t = 0; t < c->access().size(); t++) is_self &= oc->access()[t].substitute(names, x.get_operands()).is_equal(c->access()[t]);
+                            }
                         }
-                    seen.insert(seen.end(), mine.begin(), mine.end());
-                }
+                        if (is_self) { self++; continue; }
+                        std::vector<expr> stack{x};
+                        while (!stack.empty()) {
+                            expr y = stack.back(); stack.pop_back();
+                            if (!y.is_defined() || y.get_expr_type() != e_op) continue;
+                            if (y.get_op_type() == o_access) { computation *oc = nullptr; if (buffer_of_access(y, &oc) == c->get_buffer()) others++; }
+                            for (const expr &o : y.get_operands()) stack.push_back(o);
+                        }
+                    }
+                    return self == 1 && others == 0 ? (e.get_op_type() == o_max ? 1 : 2) : 0;
+                };
+                std::map<computation *, int> comm;
+                for (size_t k = i; k < j; k++) comm[ord[k]] = commutative_update(ord[k]);
+                std::vector<std::pair<computation *, Access>> all;
+                for (size_t k = i; k < j; k++)
+                    for (const Access &p : accesses_of(ord[k])) all.push_back({ord[k], p});
+                auto exchange_ok = [&](int from) {
+                    for (size_t x = 0; x < all.size(); x++)
+                        for (size_t y = 0; y < x; y++) {
+                            if (all[x].first == all[y].first) continue;
+                            const Access &p = all[x].second, &q = all[y].second;
+                            if (p.b != q.b || (!p.write && !q.write)) continue;
+                            if (comm[all[x].first] && comm[all[x].first] == comm[all[y].first] && all[x].first->get_buffer() == p.b &&
+                                all[y].first->get_buffer() == p.b) continue;
+                            if (!compatible(all[x].first, p, all[y].first, q, from)) return false;
+                        }
+                    return true;
+                };
+                // the outermost level from which everything below can be un-fused
+                keep = common;
+                for (int from = 0; from < common; from++)
+                    if (exchange_ok(from)) { keep = from; break; }
+                if (keep == common) ok = false;
             }
-            // Only levels below `common` were checked: a boundary fused deeper than that (S1.then(S2, k) inside a
-            // run fused at i) would lose a level nobody looked at — S2 would read the final t[i] instead of the running
-            // one.  Such runs keep their order as written.
-            bool uniform = true;
-            for (size_t k = i + 1; k < j; k++) uniform &= fuse_depth(ord[k - 1], ord[k]) == common;
-            if (ok && uniform && keep < common)
+            // Only levels below `common` were checked, so only the boundaries fused exactly `common` deep are lowered: a
+            // boundary fused deeper than that (S1.then(S2, k) inside a run fused at i) keeps every level it shares — S2 goes
+            // on reading the running t[i] inside (i, k) — and the loops [keep, common) are split BETWEEN the sub-runs on
+            // either side of the lowered boundaries, which is what the pairwise check above covers.  The sub-runs are
+            // looked at again on the next pass, with their own (deeper) common level.
+            if (ok && keep < common)
                 for (size_t k = i + 1; k < j; k++)
-                    if (fuse_depth(ord[k - 1], ord[k]) > keep) ord[k]->set_pred_level_index(keep - 1);
+                    if (fuse_depth(ord[k - 1], ord[k]) == common) { ord[k]->set_pred_level_index(keep - 1); changed_ = true; }
         }
         i = j;
     }
@@ -777,10 +855,61 @@ void Lowering::fuse_pointwise_nests(const std::vector<computation *> &ord, const
     }
 }
 
+// A CPU schedule puts the loops of an accumulation in cache order: reduction loops outside, register-blocked output
+// loops inside (conv_layer_generator_tiramisu.cpp: n, y, fout_b_up, fin_b, x_b, k_y, k_x, ffin, fout_b_low, ffout, xx).
+// For the device the output loops are the grid and the reduction runs inside the thread, so below the loops the statement
+// shares with its neighbours the data-parallel loops are moved outside the others, each class keeping its order.  Legal
+// for a statement whose only dependence on itself is the accumulation into the element it stores: every element still
+// sees its own additions in the original order.
+void Lowering::sink_reduction_loops(const std::vector<computation *> &ord)
+{
+    for (size_t i = 0; i < ord.size(); i++) {
+        computation *c = ord[i];
+        if (!c->has_access() || !c->get_expr().is_defined() || c->is_communicator()) continue;
+        const int keep = std::max(i ? fuse_depth(ord[i - 1], c) : 0, i + 1 < ord.size() ? fuse_depth(c, ord[i + 1]) : 0);
+        auto &dims = c->dims();
+        if ((int) dims.size() - keep < 2) continue;
+        // reads of the statement's own buffer: only the element it stores
+        bool ok = true;
+        std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+        while (!stack.empty() && ok) {
+            expr x = stack.back(); stack.pop_back();
+            if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+            for (const expr &o : x.get_operands()) stack.push_back(o);
+            if (x.get_op_type() != o_access) continue;
+            computation *oc = nullptr;
+            if (buffer_of_access(x, &oc) != c->get_buffer()) continue;
+            if ((int) oc->get_iteration_variables().size() != x.get_n_arg() || oc->access().size() != c->access().size()) { ok = false; break; }
+            std::vector<std::string> names;
+            for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+            for (size_t q = 0; q < c->access().size() && ok; q++) ok = oc->access()[q].substitute(names, x.get_operands()).is_equal(c->access()[q]);
+        }
+        if (!ok) continue;
+        std::vector<loop_dim> par, seq;
+        bool seq_seen = false, moved = false;
+        for (size_t q = (size_t) keep; q < dims.size(); q++) {
+            if (dims[q].tag == loop_dim::distributed || dims[q].tag == loop_dim::gpu_block || dims[q].tag == loop_dim::gpu_thread) { par.clear(); seq.clear(); moved = false; break; }
+            if (dim_is_parallel(c, dims[q].name)) { par.push_back(dims[q]); moved |= seq_seen; }
+            else { seq.push_back(dims[q]); seq_seen = true; }
+        }
+        if (!moved) continue;
+        std::copy(par.begin(), par.end(), dims.begin() + keep);
+        std::copy(seq.begin(), seq.end(), dims.begin() + keep + (long) par.size());
+    }
+}
+
 void Lowering::retarget(const std::vector<computation *> &ord)
 {
     retargeted_ = true;
-    if (pattern_) distribute_parallel_shared_loops(ord);
+    if (pattern_) sink_reduction_loops(ord);
+    if (pattern_) {
+        // until nothing moves: un-fusing an outer level turns its sub-runs into runs of their own
+        for (int pass = 0; pass < 16; pass++) {
+            changed_ = false;
+            distribute_parallel_shared_loops(ord);
+            if (!changed_) break;
+        }
+    }
     const char *map_fused = getenv("TIRAMISU_B200_MAP_FUSED");
     if (pattern_ && !(map_fused && map_fused[0] == '0')) map_fused_parallel_loops(ord);
     std::vector<int> shared(ord.size(), 0);
