@@ -313,7 +313,7 @@ def test_reference_conv_layer_generator_on_device():
         pytest.skip(f"{path} not built (tests/compat/build_generators.py needs /root/reference)")
     from tiramisu_b200 import _lib
     _lib.lib()
-    _conv_layer_check(C.CDLL(path, mode=C.RTLD_GLOBAL), 8, 112, 128, 256, 2e-6)
+    _conv_layer_check(C.CDLL(path, mode=C.RTLD_GLOBAL), 8, 112, 128, 256, 1e-5)       # 1152 fp32 additions per element, 25.7 M elements
 
 
 def _vgg_block_check(lib, batch, n, fout, rtol):
@@ -361,7 +361,7 @@ def test_reference_vgg_block_generator_on_device():
         pytest.skip(f"{path} not built (tests/compat/build_generators.py needs /root/reference)")
     from tiramisu_b200 import _lib
     _lib.lib()
-    _vgg_block_check(C.CDLL(path, mode=C.RTLD_GLOBAL), 32, 112, 32, 2e-6)
+    _vgg_block_check(C.CDLL(path, mode=C.RTLD_GLOBAL), 32, 112, 32, 1e-5)
 
 
 def _sgemm_cpu_generator_check(lib, shapes):
