@@ -336,6 +336,19 @@ public:
         pred_ = succ_ = nullptr;
         scheduled_ = false;
     }
+    /** Lowering: replace the statement's iterators (Layer I) by \p new_iters — every use of an old iterator in the
+      * expression, the predicate and the store index becomes \p values[i] for \p names[i] — and give it the plain loop
+      * nest over the new iterators (whatever schedule it had described loops that no longer exist). */
+    void rewrite_iterators(const std::vector<var> &new_iters, const std::vector<std::string> &names, const std::vector<expr> &values,
+                           const std::vector<expr> &new_access, const std::vector<expr> &new_guards)
+    {
+        iters_ = new_iters;
+        if (expr_.is_defined()) expr_ = expr_.substitute(names, values);
+        if (predicate_.is_defined()) predicate_ = predicate_.substitute(names, values);
+        access_ = new_access;
+        dims_.clear(); defs_.clear(); guards_ = new_guards;
+        for (const var &v : iters_) { loop_dim ld; ld.name = v.get_name(); ld.lo = v.get_lower(); ld.hi = v.get_upper(); dims_.push_back(ld); }
+    }
     /** Lowering: share loops 0..level_index with the predecessor in the order (nest fusion). */
     void set_pred_level_index(int level_index) { pred_level_index_ = level_index; }
     bool is_input() const { return is_input_; }

@@ -110,6 +110,7 @@ private:
     std::vector<ExtentRewrite> extent_rewrites_;
     void retarget(const std::vector<computation *> &ord);
     void sink_reduction_loops(const std::vector<computation *> &ord);
+    void strip_divided_iterators(const std::vector<computation *> &ord);
     bool changed_ = false;                                              // distribute_parallel_shared_loops lowered a boundary
     bool forward_private_temporaries();                                 // lowering_forward.cpp
     bool expand_private_temporaries();

@@ -639,6 +639,20 @@ void Lowering::auto_map(computation *c, int shared_depth)
             return;
         }
     }
+    // no vector loop, but the innermost data-parallel loop is short (a blocked channel dimension of 8): it plays that role —
+    // cut by 256 it would leave most of the block idle
+    if (vec < 0) {
+        int q = -1;
+        for (int i = (int) dims.size() - 1; i >= shared_depth; i--) if (parallel_safe(dims[(size_t) i].name)) { q = i; break; }
+        if (q > shared_depth) {
+            const expr ext = dims[(size_t) q].hi - dims[(size_t) q].lo;
+            bool outer_par = false;
+            for (int i = shared_depth; i < q; i++) outer_par |= parallel_safe(dims[(size_t) i].name);
+            if (outer_par && ext.is_int_literal() && ext.get_int_val() >= 2 && ext.get_int_val() <= 32 && dims[(size_t) q].lo.is_int_literal() &&
+                dims[(size_t) q].lo.get_int_val() == 0 && parallel_safe(dims[(size_t) q - 1].name))
+                vec = q;
+        }
+    }
     std::string tx, ty, bx;
     // the row loop of the thread block is the nearest data-parallel loop outside the vector loop that runs more than once
     // (vectorize(ffout, 8) of an 8-wide iterator leaves an outer part of extent 1: mapping THAT onto threadIdx.y left 31 of 32
@@ -904,23 +918,119 @@ void Lowering::sink_reduction_loops(const std::vector<computation *> &ord)
             for (size_t q = 0; q < c->access().size() && ok; q++) ok = oc->access()[q].substitute(names, x.get_operands()).is_equal(c->access()[q]);
         }
         if (!ok) continue;
-        // ... except the CPU author's register tile: short data-parallel loops tagged for unrolling INSIDE the reduction
-        // (xx and fout_b_low of the conv layer: 3 x 4 outputs per filter / input value loaded) stay where they are — the
-        // thread keeps that tile, which is what makes the loads per FMA drop from 2 to ~0.6
-        std::vector<loop_dim> par, seq, tile;
+        // (Keeping the CPU author's register tile — the short unrolled loops xx / fout_b_low — inside the reduction was
+        // measured and is worse, 54.7 vs 17.3 ms for the conv layer, r02 runs 29 / 30: the generated statement accumulates
+        // in global memory, and with the tile inside nvcc no longer promotes the element to a register.)
+        std::vector<loop_dim> par, seq;
         bool seq_seen = false, moved = false;
         for (size_t q = (size_t) keep; q < dims.size(); q++) {
-            if (dims[q].tag == loop_dim::distributed || dims[q].tag == loop_dim::gpu_block || dims[q].tag == loop_dim::gpu_thread) { par.clear(); seq.clear(); tile.clear(); moved = false; break; }
-            const expr ext = dims[q].hi - dims[q].lo;
-            const bool short_unrolled = dims[q].tag == loop_dim::unrolled && ext.is_int_literal() && ext.get_int_val() <= 8;
-            if (!dim_is_parallel(c, dims[q].name)) { seq.push_back(dims[q]); seq_seen = true; }
-            else if (seq_seen && short_unrolled) tile.push_back(dims[q]);
-            else { par.push_back(dims[q]); moved |= seq_seen; }
+            if (dims[q].tag == loop_dim::distributed || dims[q].tag == loop_dim::gpu_block || dims[q].tag == loop_dim::gpu_thread) { par.clear(); seq.clear(); moved = false; break; }
+            if (dim_is_parallel(c, dims[q].name)) { par.push_back(dims[q]); moved |= seq_seen; }
+            else { seq.push_back(dims[q]); seq_seen = true; }
         }
         if (!moved) continue;
         std::copy(par.begin(), par.end(), dims.begin() + keep);
         std::copy(seq.begin(), seq.end(), dims.begin() + keep + (long) par.size());
-        std::copy(tile.begin(), tile.end(), dims.begin() + keep + (long) (par.size() + seq.size()));
+    }
+}
+
+// A pooling statement stores out[..][y / 2][x / 2][..] = max(out[..], v(y, x)): as iterators of the stored element y and x
+// are not injective, so nothing about them could be mapped and the statement ran its whole (y, x) plane inside each
+// thread (VGG block: 9.2 ms of an 11.8 ms call, r02 run 29).  An iterator that reaches the store only as `it / k` is cut
+// into it = k q + r (Layer I, not the schedule): q indexes the store directly and is data parallel, r (k iterations)
+// stays the sequential accumulation.  Only for a statement that stands alone in the order (its schedule described loops
+// that no longer exist and is replaced by the plain nest) and that nothing names in an access.
+void Lowering::strip_divided_iterators(const std::vector<computation *> &ord)
+{
+    for (size_t i = 0; i < ord.size(); i++) {
+        computation *c = ord[i];
+        if (!c->has_access() || !c->get_expr().is_defined() || c->is_communicator()) continue;
+        if ((i && fuse_depth(ord[i - 1], c) > 0) || (i + 1 < ord.size() && fuse_depth(c, ord[i + 1]) > 0)) continue;
+        bool tagged = false;
+        for (const loop_dim &d : c->dims()) tagged |= d.tag == loop_dim::gpu_block || d.tag == loop_dim::gpu_thread || d.tag == loop_dim::distributed;
+        if (tagged) continue;
+        // named in somebody's access?
+        bool named = false;
+        for (computation *o : f_->get_computations()) {
+            std::vector<expr> stack{o->get_expr(), o->get_predicate()};
+            while (!stack.empty() && !named) {
+                expr x = stack.back(); stack.pop_back();
+                if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+                if (x.get_op_type() == o_access && x.get_name() == c->get_name()) named = true;
+                for (const expr &a : x.get_operands()) stack.push_back(a);
+            }
+        }
+        if (named) continue;
+        auto mentions = [](const expr &e, const std::string &n) { return !e.substitute({n}, {expr((int32_t) 0)}).is_equal(e) || (e.get_expr_type() == e_var && e.get_name() == n); };
+        std::vector<var> iters = c->get_iteration_variables();
+        std::vector<std::string> names; std::vector<expr> values; std::vector<expr> guards;
+        std::vector<expr> access = c->access();
+        std::vector<var> out;
+        bool any = false;
+        for (const var &v : iters) {
+            int64_t k = 0; int where = -1, uses = 0;
+            for (size_t t = 0; t < access.size(); t++) {
+                if (!mentions(access[t], v.get_name())) continue;
+                uses++;
+                const expr &a = access[t];
+                if (a.get_expr_type() == e_op && a.get_op_type() == o_div && a.get_operand(0).get_expr_type() == e_var && a.get_operand(0).get_name() == v.get_name() &&
+                    a.get_operand(1).is_int_literal() && a.get_operand(1).get_int_val() >= 2) { k = a.get_operand(1).get_int_val(); where = (int) t; }
+            }
+            const bool zero_based = v.has_range() && v.get_lower().is_int_literal() && v.get_lower().get_int_val() == 0;
+            if (uses != 1 || where < 0 || !zero_based) { out.push_back(v); continue; }
+            const expr hi = v.get_upper();
+            const bool divides = hi.is_int_literal() && hi.get_int_val() % k == 0;
+            const expr q_hi = hi.is_int_literal() ? expr((int32_t) ((hi.get_int_val() + k - 1) / k)) : (hi + (int32_t) (k - 1)) / expr((int32_t) k);
+            var q(v.get_name() + "_q", expr((int32_t) 0), q_hi), r(v.get_name() + "_r", expr((int32_t) 0), expr((int32_t) k));
+            out.push_back(q); out.push_back(r);
+            const expr val = expr::make_var(global::get_loop_iterator_data_type(), q.get_name()) * expr((int32_t) k) + expr::make_var(global::get_loop_iterator_data_type(), r.get_name());
+            names.push_back(v.get_name()); values.push_back(val);
+            access[(size_t) where] = expr::make_var(global::get_loop_iterator_data_type(), q.get_name());
+            if (!divides) guards.push_back(val < hi);
+            any = true;
+        }
+        if (!any || c->get_predicate().is_defined()) continue;
+        for (size_t t = 0; t < access.size(); t++) access[t] = access[t].substitute(names, values);     // (the rewritten dimensions no longer name v)
+        // the expression in the new iterators; a read of the element the statement stores (out[y/2][x/2] through a view)
+        // becomes an access to the statement itself at its own iteration, so that it still reads exactly `access`
+        std::vector<expr> self_args;
+        for (const var &v : out) self_args.push_back(expr::make_var(global::get_loop_iterator_data_type(), v.get_name()));
+        const std::vector<expr> old_access = c->access();
+        bool fail = false;
+        std::function<expr(const expr &)> rebuild = [&](const expr &e) -> expr {
+            if (!e.is_defined()) return e;
+            if (e.get_expr_type() != e_op) return e.substitute(names, values);
+            const op_t o = e.get_op_type();
+            if (o == o_access) {
+                computation *oc = nullptr;
+                if (buffer_of_access(e, &oc) == c->get_buffer()) {
+                    bool self = oc->access().size() == old_access.size() && (int) oc->get_iteration_variables().size() == e.get_n_arg();
+                    if (self) {
+                        std::vector<std::string> nn;
+                        for (const var &v : oc->get_iteration_variables()) nn.push_back(v.get_name());
+                        for (size_t q = 0; q < old_access.size(); q++) self &= oc->access()[q].substitute(nn, e.get_operands()).is_equal(old_access[q]);
+                    }
+                    if (!self) { fail = true; return e; }
+                    return expr(o_access, c->get_name(), self_args, e.get_data_type());
+                }
+            }
+            std::vector<expr> ops;
+            for (const expr &x : e.get_operands()) ops.push_back(rebuild(x));
+            if (o == o_access || o == o_call) return expr(o, e.get_name(), ops, e.get_data_type());
+            if (o == o_cast) return expr(o_cast, e.get_data_type(), ops[0]);
+            if (ops.size() == 1) return expr(o, ops[0]);
+            if (ops.size() == 2) return expr(o, ops[0], ops[1]);
+            if (ops.size() == 3) return expr(o, ops[0], ops[1], ops[2]);
+            fail = true;
+            return e;
+        };
+        const expr new_expr = rebuild(c->get_expr());
+        if (fail) continue;
+        c->replace_expression(new_expr);
+        names.clear(); values.clear();                                   // the expression is already in the new iterators
+        std::cerr << "tiramisu_b200 lowering: '" << c->get_name() << "' stores through `iterator / constant`: the iterator is cut into quotient (data parallel) and remainder\n";
+        c->rewrite_iterators(out, names, values, access, guards);
+        parallel_iters_.erase(c);
     }
 }
 
@@ -936,6 +1046,7 @@ void Lowering::retarget(const std::vector<computation *> &ord)
             if (!changed_) break;
         }
     }
+    if (pattern_) { strip_divided_iterators(ord); sink_reduction_loops(ord); }      // the remainders are reduction loops now
     const char *map_fused = getenv("TIRAMISU_B200_MAP_FUSED");
     if (pattern_ && !(map_fused && map_fused[0] == '0')) map_fused_parallel_loops(ord);
     std::vector<int> shared(ord.size(), 0);
