@@ -1,0 +1,17 @@
+#!/bin/bash
+# r02 run 31 (1 GPU): front-end GPU tests after the pooling / thread-mapping changes, generated DNN layer timings + launch list
+set -u
+mkdir -p gpurun_out
+echo "== pytest gpu (front-end)"; timeout 1700 python -m pytest tests/test_frontend.py tests/test_frontend_halide_gpu.py tests/test_frontend_emulation.py -m gpu -q 2>&1 | tail -8 | tee gpurun_out/r02_run31_pytest_frontend_gpu.log
+echo "== generated DNN layers"; timeout 600 python tools/gen_dnn_layers_timing.py 2>&1 | tail -4 | tee gpurun_out/r02_run31_gen_dnn_layers.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_run31_gen_dnn_launches.csv python tools/gen_dnn_layers_timing.py > /dev/null 2>&1
+python - <<'PY'
+import csv, collections
+rows = [r for r in csv.reader(open("gpurun_out/r02_run31_gen_dnn_launches.csv")) if len(r) > 10 and r[0].isdigit()]
+agg = collections.defaultdict(lambda: [0, 0.0])
+for r in rows:
+    name = r[4].split("(")[0]
+    agg[name][0] += 1; agg[name][1] += float(r[-1].replace(",", "")) if r[-1] else 0.0
+for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]:
+    print(f"{k[-60:]:60s} launches {n:4d}  avg {t/n/1e3:10.1f} us")
+PY
