@@ -134,7 +134,9 @@ def build_one(name: str, lowering: str | None = None) -> tuple[int, str]:
     os.makedirs(os.path.join(work, "build"), exist_ok=True)
     os.makedirs(BIN, exist_ok=True)
     env = _env()
-    if lowering:
+    if lowering == "noidiom":
+        env["TIRAMISU_B200_NO_IDIOM"] = "1"          # whole-function idioms off: the general passes lower the program
+    elif lowering:
         env["TIRAMISU_B200_LOWERING"] = lowering
     inc = sum((["-I", os.path.join(REF, i)] for i in incs), [])
     gen_exe = os.path.join(work, "generator")
@@ -198,6 +200,9 @@ def build(names=None, verbose=False) -> dict:
     # the pattern-lowered generators once more with the pattern lowering off (generic SIMT emission)
     jobs += [(n, "generic") for n in ("test_167", "test_169", "heat2d", "chain_mm", "lstm_cpu", "lstm_cpu_so", "sgemm_gpu_generator1", "sgemm_gpu_generator2",
                                       "sgemm_gpu_generator3", "sgemm_cpu") if not names or n in names]
+    # the conv + ReLU + max-pool block once more with the whole-function idiom off: register-blocking buffer expanded, fused
+    # nest distributed, pooling iterators cut — four kernels, one launch each (round 1: refused at 6.4 M launches)
+    jobs += [(n, "noidiom") for n in ("conv_block",) if not names or n in names]
     out = {}
     with cf.ThreadPoolExecutor(max_workers=min(6, max(1, len(jobs)))) as ex:
         futs = {ex.submit(build_one, n, low): (n if low is None else f"{n}_{low}") for n, low in jobs}

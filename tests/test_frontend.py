@@ -161,7 +161,7 @@ def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     res = bg.build()
     failed = {k: v[1] for k, v in res.items() if v[0] != 0}
     assert not failed, failed
-    assert len(res) == len(bg.TARGETS) + 10         # + the generic-lowering variants
+    assert len(res) == len(bg.TARGETS) + 11         # + the generic-lowering variants and conv_block without its idiom
     # sgemm/cpu/sgemm_generator.cpp (BASELINE configs[0]'s own generator): 16 statement pieces ordered with after_low_level
     # and scheduled by loop level -> pieces merged, the packed copy of B nothing reads dropped, ONE tcgen05 GEMM call
     sg = open(os.path.join(bg.GEN, "sgemm_cpu", "generated_sgemm.o.b200.cu")).read()
@@ -513,6 +513,56 @@ def test_reference_conv_block_generator(tmp_path):
     out = _run("conv_block", cwd=tmp_path, timeout=1200)
     pct = [ln for ln in out.splitlines() if "Percentage of correctness" in ln]
     assert pct and float(pct[0].split()[-1].rstrip("%")) >= 99.99, out[-1500:]
+
+
+@pytest.mark.gpu
+def test_reference_conv_block_generator_without_the_idiom(tmp_path):
+    """The same generator and wrapper with the whole-function idiom switched off at generator time
+    (TIRAMISU_B200_NO_IDIOM=1): what round 1 refused (6.4 M launches) now goes through the general passes — the weight
+    prefetch loop dropped, the register-blocking buffer given its full extent back, the fused nest distributed level by
+    level, the pooling iterators cut into quotient and remainder: four kernels, one launch each, fp32 SIMT arithmetic in the
+    statement's own order.  Same wrapper check (1e-4 per element against the oracle's dump)."""
+    from oracle import oracle
+    from tests import refdata
+    inp, filt, bias = refdata.conv_inputs(32, 224, 3, 32)
+    want = oracle.conv_relu_maxpool(inp, filt, bias)
+    flat = np.ascontiguousarray(want.transpose(0, 1, 4, 2, 3)).reshape(-1)
+    np.savetxt(tmp_path / "mkl_result.txt", flat, fmt="%.10g")
+    out = _run("conv_block_noidiom", cwd=tmp_path, timeout=1200)
+    pct = [ln for ln in out.splitlines() if "Percentage of correctness" in ln]
+    assert pct and float(pct[0].split()[-1].rstrip("%")) >= 99.99, out[-1500:]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference")
+def test_reference_conv_block_generator_without_the_idiom_structure(frontend_lib):
+    src = os.path.join(bg.GEN, "conv_block_noidiom", "conv_relu_maxpool_tiramisu.o.b200.cu")
+    if not os.path.exists(src):
+        bg.build(["conv_block"])
+    text = open(src).read()
+    host = text.split("extern \"C\" int conv_relu_maxpool_block(")[1]
+    assert text.count("static __global__") == 4 and host.count("<<<") == 4 and host.count("for (int32_t") == 0
+    assert "tiramisu_b200_conv_relu_maxpool(" not in host
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(bg.REF, "tests")), reason="needs /root/reference")
+def test_reference_conv_block_generator_without_the_idiom_emulated(frontend_lib):
+    """... and run thread by thread on the host at the generator's own configuration (32 x 224 x 224, 3 -> 32): the
+    statement order of the four kernels is the oracle's loop order, so the result is bit-exact."""
+    from oracle import oracle
+    from tests import refdata
+    from tests.emulation import emulate
+    from tiramisu_b200.halide import Buffer
+    src = os.path.join(bg.GEN, "conv_block_noidiom", "conv_relu_maxpool_tiramisu.o.b200.cu")
+    if not os.path.exists(src):
+        bg.build(["conv_block"])
+    lib = C.CDLL(emulate.build_shared([src], "conv_block_noidiom"))
+    inp, filt, bias = refdata.conv_inputs(32, 224, 3, 32)
+    want = oracle.conv_relu_maxpool(inp, filt, bias)
+    out = np.full(want.shape, 9.0, np.float32)
+    f = lib.conv_relu_maxpool_block
+    f.restype = C.c_int
+    assert f(*[Buffer(a).ptr() for a in (inp, filt, bias, out)]) == 0
+    assert np.array_equal(out, want)
 
 
 def _load(name):

@@ -225,7 +225,8 @@ std::string Lowering::run()
     for (computation *c : ord)
         for (auto &d : c->dims()) any_gpu |= d.tag == loop_dim::gpu_block || d.tag == loop_dim::gpu_thread;
     std::ostringstream idiom_body;
-    const bool whole_function_idiom = !cuda_ && !any_gpu && try_conv_block_idiom(ord, idiom_body);
+    // TIRAMISU_B200_NO_IDIOM=1: skip the whole-function idiom and let the general passes lower the block
+    const bool whole_function_idiom = !cuda_ && !any_gpu && !getenv("TIRAMISU_B200_NO_IDIOM") && try_conv_block_idiom(ord, idiom_body);
     if (whole_function_idiom) {
         std::cerr << "tiramisu_b200 lowering: '" << f_->get_name() << "' is the conv + ReLU + max-pool block: lowered to the runtime's fused kernel\n";
     } else if (!cuda_ && !any_gpu) {
