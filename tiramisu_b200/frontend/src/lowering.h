@@ -164,6 +164,7 @@ private:
     void emit_host_stmt(Node *n, std::ostringstream &os, int ind);
     void emit_kernel(Node *n, std::ostringstream &host, int ind, std::vector<Node *> &host_loops);
     void emit_device(Node *n, Kernel &k, std::ostringstream &os, int ind);
+    bool try_emit_accumulation_tile(Node *n, std::ostringstream &os, int ind);
     void emit_assignment(Node *n, std::ostringstream &os, int ind, bool device);
     void emit_bindings(Node *n, std::ostringstream &os, int ind, std::vector<std::string> &conds, bool device);
     struct Contraction { buffer *C = nullptr, *A = nullptr, *B = nullptr; bool tA = false, tB = false; expr M, N, K, offA, offB, offC; };

@@ -918,19 +918,24 @@ void Lowering::sink_reduction_loops(const std::vector<computation *> &ord)
             for (size_t q = 0; q < c->access().size() && ok; q++) ok = oc->access()[q].substitute(names, x.get_operands()).is_equal(c->access()[q]);
         }
         if (!ok) continue;
-        // (Keeping the CPU author's register tile — the short unrolled loops xx / fout_b_low — inside the reduction was
-        // measured and is worse, 54.7 vs 17.3 ms for the conv layer, r02 runs 29 / 30: the generated statement accumulates
-        // in global memory, and with the tile inside nvcc no longer promotes the element to a register.)
-        std::vector<loop_dim> par, seq;
+        // ... except the CPU author's register tile: short data-parallel loops tagged for unrolling INSIDE the reduction
+        // (xx and fout_b_low of the conv layer: 3 x 4 outputs per filter / input value loaded) stay there; the emitter
+        // keeps the tile's accumulators in registers (lowering_emit.cpp: try_emit_accumulation_tile — without that the
+        // tile inside is a loss, 54.7 vs 17.3 ms, r02 runs 29 / 30)
+        std::vector<loop_dim> par, seq, tile;
         bool seq_seen = false, moved = false;
         for (size_t q = (size_t) keep; q < dims.size(); q++) {
-            if (dims[q].tag == loop_dim::distributed || dims[q].tag == loop_dim::gpu_block || dims[q].tag == loop_dim::gpu_thread) { par.clear(); seq.clear(); moved = false; break; }
-            if (dim_is_parallel(c, dims[q].name)) { par.push_back(dims[q]); moved |= seq_seen; }
-            else { seq.push_back(dims[q]); seq_seen = true; }
+            if (dims[q].tag == loop_dim::distributed || dims[q].tag == loop_dim::gpu_block || dims[q].tag == loop_dim::gpu_thread) { par.clear(); seq.clear(); tile.clear(); moved = false; break; }
+            const expr ext = dims[q].hi - dims[q].lo;
+            const bool short_unrolled = dims[q].tag == loop_dim::unrolled && ext.is_int_literal() && ext.get_int_val() <= 8 && !getenv("TIRAMISU_B200_NO_REGISTER_TILE");
+            if (!dim_is_parallel(c, dims[q].name)) { seq.push_back(dims[q]); seq_seen = true; }
+            else if (seq_seen && short_unrolled) tile.push_back(dims[q]);
+            else { par.push_back(dims[q]); moved |= seq_seen; }
         }
         if (!moved) continue;
         std::copy(par.begin(), par.end(), dims.begin() + keep);
         std::copy(seq.begin(), seq.end(), dims.begin() + keep + (long) par.size());
+        std::copy(tile.begin(), tile.end(), dims.begin() + keep + (long) (par.size() + seq.size()));
     }
 }
 
