@@ -673,6 +673,11 @@ void Lowering::auto_map(computation *c, int shared_depth)
         {
             const expr ext = dims[vec - 1].hi - dims[vec - 1].lo;
             if (ext.is_int_literal() && ext.get_int_val() >= 1 && ext.get_int_val() < rows) rows = (int) ext.get_int_val();
+            else if (ext.is_int_literal() && ext.get_int_val() > rows) {
+                // equal blocks: 37 rows are two blocks of 19, not 32 + 5 (the second block would be 5 / 32 full)
+                const int64_t nblk = (ext.get_int_val() + rows - 1) / rows;
+                rows = (int) ((ext.get_int_val() + nblk - 1) / nblk);
+            }
         }
         tx = dims[vec].name;
         std::string outer = dims[vec - 1].name;
