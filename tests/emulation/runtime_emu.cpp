@@ -38,6 +38,7 @@ static int gemm(T *A, T *B, T *C, uint64_t M, uint64_t N, uint64_t K, T alpha, T
 extern "C" {
 void oracle_heat2d(const float *in, float *out, int H, int W);
 void oracle_heat2dgpu(const float *in, float *out, int H, int W);
+void oracle_blurxy_u8(const uint8_t *in, uint8_t *out, int C, int H, int W);
 void oracle_conv_relu_maxpool(const float *in, const float *w, const float *b, float *out, int B, int N, int FIn, int FOut);
 
 void *tiramisu_cuda_malloc(uint64_t n) { return std::calloc(n ? n : 1, 1); }
@@ -63,6 +64,11 @@ int tiramisu_b200_heat2d(const float *in, float *out, int32_t H, int32_t W, int3
 {
     if (rb != 0 || re != H || form > 1) { std::fprintf(stderr, "runtime_emu: heat2d variant not emulated\n"); return 1; }
     if (form == 0) oracle_heat2d(in, out, H, W); else oracle_heat2dgpu(in, out, H, W);
+    return 0;
+}
+int tiramisu_b200_blurxy_u8(const uint8_t *in, uint8_t *out, int32_t C, int32_t H, int32_t W)
+{
+    oracle_blurxy_u8(in, out, C, H, W);
     return 0;
 }
 int tiramisu_b200_heat2d_buffers(halide_buffer_t *in, halide_buffer_t *out, int32_t H, int32_t W, int32_t form)

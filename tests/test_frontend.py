@@ -196,6 +196,9 @@ def test_reference_generators_compile_unmodified_and_lower(frontend_lib):
     for g in (1, 2, 3):
         pat = open(os.path.join(bg.GEN, f"sgemm_gpu_generator{g}", "fct.o.b200.cu")).read()
         assert "__global__" not in pat and pat.count("tiramisu_cublas_sgemm((float") == 1 and "hand-staged contraction" in pat
+    # benchmarks/halide/blurxy_tiramisu.cpp (row a7's own generator): the x pass + y pass pair is recognised -> runtime blur kernel
+    bl = open(os.path.join(bg.GEN, "halide_blurxy", "build", "generated_fct_blurxy.o.b200.cu")).read()
+    assert "if (tiramisu_b200_blurxy_u8(b_buff_p0, b_buff_blur_y, (int32_t) (3), (int32_t) (3520), (int32_t) (2112))) return 1;" in bl and "__global__" not in bl
     # benchmarks/halide/heat2d_tiramisu.cpp (ISL-string API, CPU schedule): the statement pair is recognised
     # and handed to the runtime's heat2d entry point; with the pattern lowering off, two generated kernels
     heat = open(os.path.join(bg.GEN, "heat2d", "build", "generated_fct_heat2d.o.b200.cu")).read()

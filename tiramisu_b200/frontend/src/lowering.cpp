@@ -250,6 +250,11 @@ std::string Lowering::run()
             i++;
             continue;
         }
+        if (i + 1 < root_.kids.size() && is_kernel(k) && is_kernel(root_.kids[i + 1].get()) &&
+            try_blurxy_pattern(k, root_.kids[i + 1].get(), ord, body, 1)) {
+            i++;
+            continue;
+        }
         if (i + 2 < root_.kids.size() && is_kernel(k) && is_kernel(root_.kids[i + 1].get()) && is_kernel(root_.kids[i + 2].get()) &&
             try_sgemm_triple(k, root_.kids[i + 1].get(), root_.kids[i + 2].get(), ord, body, 1)) {
             i += 2;
@@ -274,6 +279,7 @@ std::string Lowering::run()
         << "void *tiramisu_b200_get_stream(void);\nint tiramisu_b200_post_launch(const char *);\n"
         << "int tiramisu_cuda_memcpy_to_device_async(void *, const void *, uint64_t);\n"
         << "int tiramisu_b200_heat2d(const float *, float *, int32_t, int32_t, int32_t, int32_t, int32_t);\n"
+        << "int tiramisu_b200_blurxy_u8(const uint8_t *, uint8_t *, int32_t, int32_t, int32_t);\n"
         << "int tiramisu_b200_heat2d_buffers(halide_buffer_t *, halide_buffer_t *, int32_t, int32_t, int32_t);\n"
         << "int tiramisu_b200_conv_relu_maxpool(const float *, const float *, const float *, float *, int32_t, int32_t, int32_t, int32_t);\n"
         << "int tiramisu_cublas_sgemm(float *, float *, float *, uint64_t, uint64_t, uint64_t, float, float, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t, bool, bool);\n"

@@ -132,6 +132,7 @@ private:
     void emit_warp_reduction(Node *loop, std::ostringstream &os, int ind);
     static int fuse_depth(computation *prev, computation *c);
     bool try_heat2d_pattern(Node *zero, Node *heat, std::ostringstream &host, int ind);
+    bool try_blurxy_pattern(Node *kx, Node *ky, const std::vector<computation *> &ord, std::ostringstream &host, int ind);
     bool try_staged_contraction(Node *kernel, std::ostringstream &host, int ind);
     bool try_conv_block_idiom(const std::vector<computation *> &ord, std::ostringstream &host);
     // index simplification context of the statement being emitted

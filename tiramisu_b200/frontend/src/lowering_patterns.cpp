@@ -278,6 +278,105 @@ bool Lowering::try_sgemm_triple(Node *kz, Node *kr, Node *ks, const std::vector<
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------ uint8 3x3 blur pair
+// benchmarks/halide/blurxy_tiramisu.cpp:61-77 (row a7) as two consecutive kernels:
+//     bx(c, y, x) = ((in(c, y, x) + in(c, y, x+1)) + in(c, y, x+2)) / 3      over [C] x [H-6] x [W-8], a temporary
+//     by(c, y, x) = ((bx(c, y, x) + bx(c, y+1, x)) + bx(c, y+2, x)) / 3      over [C] x [H-8] x [W-8]
+// in uint8 (sums wrap mod 256, as the reference's generated code does) -> the runtime's blur kernel, one pass, no temporary.
+bool Lowering::try_blurxy_pattern(Node *kx, Node *ky, const std::vector<computation *> &ord, std::ostringstream &host, int ind)
+{
+    if (!pattern_) return false;
+    auto single = [](Node *k) -> Node * {
+        Node *stmt = nullptr;
+        std::vector<Node *> st{k};
+        while (!st.empty()) {
+            Node *n = st.back(); st.pop_back();
+            if (!n->is_loop) { if (stmt) return nullptr; stmt = n; continue; }
+            for (auto &c : n->kids) st.push_back(c.get());
+        }
+        return (stmt && !stmt->path.empty() && stmt->path[0] == k) ? stmt : nullptr;
+    };
+    Node *sx = single(kx), *sy = single(ky);
+    if (!sx || !sy) return false;
+    computation *bx = sx->comp, *by = sy->comp;
+    for (computation *c : {bx, by})
+        if (c->get_data_type() != p_uint8 || c->get_predicate().is_defined() || !c->has_access() || c->get_iteration_variables().size() != 3 || c->access().size() != 3) return false;
+    buffer *T = bx->get_buffer(), *out = by->get_buffer();
+    if (T == out || T->get_argument_type() != a_temporary || T->get_n_dims() != 3 || out->get_n_dims() != 3 || out->get_location() != mem_loc::gpu_global) return false;
+    auto is_var = [](const expr &x, const std::string &n) { return x.get_expr_type() == e_var && x.get_name() == n; };
+    auto is_lit = [](const expr &x, int64_t v) { return x.is_int_literal() && x.get_int_val() == v; };
+    auto offset = [&](const expr &x, const std::string &v, int &off) {
+        if (is_var(x, v)) { off = 0; return true; }
+        if (x.get_expr_type() != e_op || x.get_n_arg() != 2 || x.get_op_type() != o_add) return false;
+        const expr &a = x.get_operand(0), &b = x.get_operand(1);
+        if (is_var(a, v) && b.is_int_literal()) { off = (int) b.get_int_val(); return true; }
+        if (is_var(b, v) && a.is_int_literal()) { off = (int) a.get_int_val(); return true; }
+        return false;
+    };
+    // ((t0 + t1) + t2) / 3 with the three taps of `src` along dimension `along` (1 = rows, 2 = columns), in that order
+    auto three_taps = [&](computation *c, int along, buffer *&src) {
+        const auto &it = c->get_iteration_variables();
+        for (int d = 0; d < 3; d++) if (!is_var(c->access()[d], it[d].get_name()) || !is_lit(it[d].get_lower(), 0)) return false;
+        const expr &e = c->get_expr();
+        if (!(e.get_expr_type() == e_op && e.get_op_type() == o_div && is_lit(e.get_operand(1), 3) && e.get_operand(1).get_data_type() == p_uint8)) return false;
+        const expr &s2 = e.get_operand(0);
+        if (!(s2.get_expr_type() == e_op && s2.get_op_type() == o_add)) return false;
+        const expr &s1 = s2.get_operand(0);
+        if (!(s1.get_expr_type() == e_op && s1.get_op_type() == o_add)) return false;
+        const expr taps[3] = {s1.get_operand(0), s1.get_operand(1), s2.get_operand(1)};
+        src = nullptr;
+        for (int k = 0; k < 3; k++) {
+            const expr &x = taps[k];
+            if (!(x.get_expr_type() == e_op && x.get_op_type() == o_access) || x.get_data_type() != p_uint8) return false;
+            computation *oc = nullptr;
+            buffer *b = buffer_of_access(x, &oc);
+            if (!b || b->get_n_dims() != 3 || oc->access().size() != 3 || (int) oc->get_iteration_variables().size() != x.get_n_arg() || (src && src != b)) return false;
+            src = b;
+            std::vector<std::string> names;
+            for (const var &v : oc->get_iteration_variables()) names.push_back(v.get_name());
+            for (int d = 0; d < 3; d++) {
+                int off = -1;
+                if (!offset(oc->access()[d].substitute(names, x.get_operands()), it[d].get_name(), off) || off != (d == along ? k : 0)) return false;
+            }
+        }
+        return true;
+    };
+    buffer *in = nullptr, *mid = nullptr;
+    if (!three_taps(bx, 2, in) || !three_taps(by, 1, mid) || mid != T || in == T || in == out || in->get_location() != mem_loc::gpu_global) return false;
+    // shapes: in [C][H][W], bx over [C][H-6][W-8] (the temporary at least that large), by = out = [C][H-8][W-8]
+    const expr &Cn = in->get_dim_sizes()[0], &H = in->get_dim_sizes()[1], &W = in->get_dim_sizes()[2];
+    auto same_sz = [&](const expr &a, const expr &b) {
+        if (a.is_equal(b)) return true;
+        Env none;
+        return simp(a - b, none).is_int_literal() && simp(a - b, none).get_int_val() == 0;
+    };
+    auto lit_or_equal = [&](const expr &have, const expr &base, int64_t minus) {
+        if (have.is_int_literal() && base.is_int_literal()) return have.get_int_val() == base.get_int_val() - minus;
+        return same_sz(have, base - (int32_t) minus);
+    };
+    const auto &ix = bx->get_iteration_variables(), &iy = by->get_iteration_variables();
+    if (!lit_or_equal(ix[0].get_upper(), Cn, 0) || !lit_or_equal(ix[1].get_upper(), H, 6) || !lit_or_equal(ix[2].get_upper(), W, 8)) return false;
+    if (!lit_or_equal(iy[0].get_upper(), Cn, 0) || !lit_or_equal(iy[1].get_upper(), H, 8) || !lit_or_equal(iy[2].get_upper(), W, 8)) return false;
+    if (!lit_or_equal(out->get_dim_sizes()[0], Cn, 0) || !lit_or_equal(out->get_dim_sizes()[1], H, 8) || !lit_or_equal(out->get_dim_sizes()[2], W, 8)) return false;
+    // nobody else reads the temporary
+    for (computation *c : ord) {
+        if (c == bx || c == by) continue;
+        if (c->has_access() && c->get_buffer() == T) return false;
+        std::vector<expr> stack{c->get_expr(), c->get_predicate()};
+        while (!stack.empty()) {
+            expr x = stack.back(); stack.pop_back();
+            if (!x.is_defined() || x.get_expr_type() != e_op) continue;
+            if (x.get_op_type() == o_access) { computation *oc = f_->find_computation(x.get_name()); if (oc && !oc->is_constant() && oc->has_access() && oc->get_buffer() == T) return false; }
+            for (const expr &o : x.get_operands()) stack.push_back(o);
+        }
+    }
+    host << pad(ind) << "// pattern lowering: '" << bx->get_name() << "' (3 taps along x) + '" << by->get_name()
+         << "' (3 taps along y), uint8 -> the runtime's 3x3 blur kernel (one pass, the temporary is not written)\n";
+    host << pad(ind) << "if (tiramisu_b200_blurxy_u8(b_" << san(in->get_name()) << ", b_" << san(out->get_name()) << ", (int32_t) (" << print(Cn, false)
+         << "), (int32_t) (" << print(H, false) << "), (int32_t) (" << print(W, false) << "))) return 1;\n";
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ staged contraction
 // A hand-scheduled GPU GEMM (benchmarks/linear_algebra/blas/level3/sgemm/gpu/generator{1,2,3}.cpp): ONE kernel whose
 // Layer-I arithmetic is still
