@@ -33,6 +33,9 @@ CASES = {
     "polymul_cpu_gen": ("polymul_cpu_gen.cpp", "polymul_cpu_gen", None),
     "prefix_fuse_cpu_gen": ("prefix_fuse_cpu_gen.cpp", "prefix_fuse_cpu_gen", None),
     "sgemm_cpu_sched_tc": ("sgemm_cpu_sched_gen.cpp", "sgemm_cpu_sched_tc", None),           # statement triple -> one tcgen05 GEMM
+    # the register-blocking idioms of the reference's DNN generators / the old-style API of its sgemm generator
+    "regblock_cpu_gen": ("regblock_cpu_gen.cpp", "regblock_cpu_gen", None),
+    "pieces_cpu_gen": ("pieces_cpu_gen.cpp", "pieces_cpu_gen", None),
     # distributed functions (rank scope + tiramisu_MPI_* on device addresses), one build per rank count the GPU boxes offer
     **{f"dist_blur_gen_{k}": ("dist_blur_gen.cpp", f"dist_blur_gen_{k}", None) for k in (2, 4, 8)},     # gen_communication halo
     **{f"dist_xfer_gen_{k}": ("dist_xfer_gen.cpp", f"dist_xfer_gen_{k}", None) for k in (2, 4, 8)},     # explicit create_xfer

@@ -52,3 +52,22 @@ def lstm_inputs(F, B, L, T, seed=0, scale=1.0):
     b = val(rand_array(L * 4 * F)).astype(np.float32).reshape(L, 4 * F)
     x = val(rand_array(T * B * F)).astype(np.float32).reshape(T, B, F)
     return W, b, x
+
+
+def regblock_case(seed=3):
+    """Inputs and fp32 results (statement order: bias first, then k = 0, 1, ... with separate multiply and add) of
+    tests/frontend_cases/regblock_cpu_gen.cpp: (in, w, bias), conv[N][Y][X][8], pooled[N][Y/2][X/2][8]."""
+    N, Y, X, K = 3, 6, 12, 5
+    rng = np.random.default_rng(seed)
+    inp = rng.uniform(-1, 1, (N, Y, X + K - 1)).astype(np.float32)
+    w = rng.uniform(-1, 1, (K, 8)).astype(np.float32)
+    bias = rng.uniform(-1, 1, (8,)).astype(np.float32)
+    conv = np.broadcast_to(bias, (N, Y, X, 8)).astype(np.float32).copy()
+    for k in range(K):
+        prod = (w[k][None, None, None, :] * inp[:, :, k:k + X, None]).astype(np.float32)
+        conv = (conv + prod).astype(np.float32)
+    pooled = np.zeros((N, Y // 2, X // 2, 8), np.float32)
+    for dy in range(2):
+        for dx in range(2):
+            pooled = np.maximum(pooled, conv[:, dy::2, dx::2, :])
+    return (inp, w, bias), conv, pooled

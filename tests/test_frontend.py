@@ -114,6 +114,21 @@ def test_fused_data_parallel_loops_become_the_grid(cases):
     assert "__launch_bounds__(1)" not in src
 
 
+def test_cpu_register_blocking_and_statement_pieces_are_undone(cases):
+    """regblock_cpu_gen.cpp / pieces_cpu_gen.cpp (own generators in the shape of the reference's DNN and sgemm
+    generators): every statement one kernel with one launch, no host loop; the staging buffers are gone or expanded; the
+    register tile's accumulators live in registers; the pieces are one statement and the dead copy is not computed."""
+    src = open(bc.generated_source("regblock_cpu_gen")).read()
+    host = src.split('extern "C" int regblock_cpu_gen(')[1]
+    assert src.count("static __global__") == 6 and host.count("<<<") == 6 and host.count("for (int32_t") == 0
+    assert "b_reg1[" not in src                                                             # forwarded: nobody indexes reg1
+    assert "reg2_of_c2_init" in src and "register tile of 3 accumulators" in src
+    assert "_q" in src.split("k5_pool(")[1].split("static __global__")[0]                   # y / 2, x / 2 -> quotient iterators
+    src = open(bc.generated_source("pieces_cpu_gen")).read()
+    host = src.split('extern "C" int pieces_cpu_gen(')[1]
+    assert src.count("static __global__") == 1 and host.count("<<<") == 1 and "k0_S(" in src and "copy" not in host.split("<<<")[0].split("const int tb_rc")[-1]
+
+
 def test_retargeting_legality_decisions(frontend_lib, tmp_path):
     """tests/frontend_cases/legality_gen.cpp: what the re-targeting does when it cannot prove independence —
     fuse only element-wise exchanges, keep in-place cross-element statements in one thread, keep fused loops with
@@ -597,6 +612,26 @@ def test_generated_heat2d_bit_exact(shape, variant):
     out = np.full(shape, -7.0, np.float32)
     _call(lib, variant, np.array(shape, np.int32), a, out)
     assert np.array_equal(out, oracle.heat2d(a, "cpu"))
+
+
+@pytest.mark.gpu
+def test_generated_register_blocking_idioms_bit_exact():
+    from tests import refdata
+    (inp, w, bias), conv, pooled = refdata.regblock_case()
+    out = np.full(conv.shape, 3.0, np.float32)
+    pool = np.full(pooled.shape, 5.0, np.float32)
+    _call(_load("regblock_cpu_gen"), "regblock_cpu_gen", inp, w, bias, out, pool)
+    assert np.array_equal(out, conv) and np.array_equal(pool, pooled)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nm", [(16, 32), (7, 21), (1000, 777)])
+def test_generated_statement_pieces_bit_exact(nm):
+    n, m = nm
+    A = np.random.default_rng(n * m).uniform(-1, 1, (n, m)).astype(np.float32)
+    B = np.full((n, m), 9.0, np.float32)
+    _call(_load("pieces_cpu_gen"), "pieces_cpu_gen", np.array([n, m], np.int32), A, B)
+    assert np.array_equal(B, (A * np.float32(2.0) + np.float32(1.0)).astype(np.float32))
 
 
 @pytest.mark.gpu

@@ -268,3 +268,26 @@ def test_generated_distributed_functions_as_emulated_ranks(cases, world, tmp_pat
              for r in range(world)]
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 and "DIST_GEN_OK" in o for p, o in zip(procs, outs)), "\n".join(o[-800:] for o in outs)
+
+
+def test_emulated_register_blocking_idioms(cases):
+    """tests/frontend_cases/regblock_cpu_gen.cpp: a load / accumulate / store triple through a staging buffer (-> in-place
+    accumulation), an init / accumulate / consume group (-> staging buffer expanded), a max-pool over y / 2, x / 2 (-> iterators
+    cut), fused nests distributed: bit-exact against the statement-order fp32 restatement."""
+    from tests import refdata
+    (inp, w, bias), conv, pooled = refdata.regblock_case()
+    out = np.full(conv.shape, 3.0, np.float32)
+    pool = np.full(pooled.shape, 5.0, np.float32)
+    _call(_emulated("regblock_cpu_gen"), "regblock_cpu_gen", inp, w, bias, out, pool)
+    assert np.array_equal(out, conv) and np.array_equal(pool, pooled)
+
+
+@pytest.mark.parametrize("nm", [(16, 32), (7, 21), (5, 9)])
+def test_emulated_statement_pieces_and_after_low_level(cases, nm):
+    """tests/frontend_cases/pieces_cpu_gen.cpp: full-tile + partial-tile pieces ordered with after_low_level and scheduled by
+    loop level become one statement (sizes that are and are not multiples of the tile)."""
+    n, m = nm
+    A = np.random.default_rng(n * m).uniform(-1, 1, (n, m)).astype(np.float32)
+    B = np.full((n, m), 9.0, np.float32)
+    _call(_emulated("pieces_cpu_gen"), "pieces_cpu_gen", np.array([n, m], np.int32), A, B)
+    assert np.array_equal(B, (A * np.float32(2.0) + np.float32(1.0)).astype(np.float32))
