@@ -89,3 +89,37 @@ def rgbyuv420gpu(img: np.ndarray):
     u = (((-38 * sr - g74 + 112 * sb + 128) % 256) + 128).astype(np.uint8)
     v = (((112 * sr - g94 - 18 * sb + 128) % 256) + 128).astype(np.uint8)
     return y, u, v
+
+
+def warp_affinegpu(img: np.ndarray) -> np.ndarray:
+    """benchmarks/halide/warp_affinegpu_tiramisu.cpp:43-86, Layer I as written (fp32, separate multiplies and adds, every
+    coefficient 0.1f).  img: in_host u8[M][N] (in(i, j) is img[j][i]); result out_host f32[M][N].  Two quirks of the reference
+    are kept: coord_c is floor(o_r) (:66, not o_c), and clamp() lets an index reach N / M (:18-20) — callers keep
+    0.1 (N + M) + 2 below min(N, M) so that no read leaves the image."""
+    M, N = img.shape
+    f = np.float32
+    a = f(0.1)
+    i = np.arange(N, dtype=np.int32)[None, :].astype(f)
+    j = np.arange(M, dtype=np.int32)[:, None].astype(f)
+    o_r = ((a * i).astype(f) + (a * j).astype(f)).astype(f) + a
+    o_c = ((a * i).astype(f) + (a * j).astype(f)).astype(f) + a
+    r = (o_r - np.floor(o_r)).astype(f)
+    c = (o_c - np.floor(o_c)).astype(f)
+    coord_r = np.floor(o_r).astype(np.int32)
+    coord_c = np.floor(o_r).astype(np.int32)
+
+    def clamp(n, hi):
+        return np.where(n < 0, 0, np.where(n > hi, hi, n))
+
+    def at(rr, cc):                                      # in(rr, cc) -> in_gpu[cc][rr]
+        return img[cc, rr].astype(f)
+
+    A00 = at(clamp(coord_r, N), clamp(coord_c, M))
+    A01 = at(clamp(coord_r, N), clamp(coord_c + 1, M))
+    A10 = at(clamp(coord_r + 1, N), clamp(coord_c, M))
+    A11 = at(clamp(coord_r + 1, N), clamp(coord_c + 1, M))
+
+    def mixf(x, y, t):
+        return ((x * (f(1.0) - t).astype(f)).astype(f) + (y * t).astype(f)).astype(f)
+
+    return mixf(mixf(A00, A01, r), mixf(A10, A11, r), c)

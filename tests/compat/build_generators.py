@@ -77,7 +77,7 @@ TARGETS = {
     # register temporaries and clamped accesses.  Their wrappers need Halide-generated reference pipelines and PNG I/O,
     # so the objects are linked into shared libraries and checked against oracle/halide_gpu.py by tests/test_frontend.py.
     **{f"halide_{g}": (f"benchmarks/halide/{g}_tiramisu.cpp", f"build/generated_fct_{g}.o", None, ["benchmarks/halide"], [])
-       for g in ("convolutiongpu", "gaussiangpu", "edgegpu", "fusiongpu", "cvtcolorgpu", "rgbyuv420gpu", "heat2dgpu")},
+       for g in ("convolutiongpu", "gaussiangpu", "edgegpu", "fusiongpu", "cvtcolorgpu", "rgbyuv420gpu", "heat2dgpu", "warp_affinegpu")},
     # row a7's own generator (CPU schedule: split / parallelize / vectorize + compute_at of the x pass inside the y pass);
     # it sizes itself from ./utils/images/rgb.png at generator time (RUN_LINKS), checked by tests/test_frontend_halide_gpu.py
     "halide_blurxy": ("benchmarks/halide/blurxy_tiramisu.cpp", "build/generated_fct_blurxy.o", None, ["benchmarks/halide"], []),

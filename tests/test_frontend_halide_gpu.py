@@ -1,5 +1,5 @@
 """the reference's other `*gpu` Halide benchmarks (benchmarks/halide/{convolution,gaussian,edge,fusion,
-cvtcolor,rgbyuv420,heat2d}gpu_tiramisu.cpp) compiled UNMODIFIED against the front-end (tests/compat/build_generators.py,
+cvtcolor,rgbyuv420,heat2d,warp_affine}gpu_tiramisu.cpp) compiled UNMODIFIED against the front-end (tests/compat/build_generators.py,
 targets halide_*), lowered to sm_100a and checked against numpy restatements of their Layer-I expressions
 (oracle/halide_gpu.py).  Their own wrappers compare with Halide-generated pipelines and load PNG files, neither of
 which exists here, so the generated functions are called through ctypes on synthetic images.
@@ -89,10 +89,19 @@ def check_convolution(lib, M=83, N=150):
     assert np.array_equal(out, hg.convolutiongpu(img, kernel))
 
 
+def check_warp_affine(lib, M=70, N=101):
+    """warp_affinegpu_tiramisu.cpp: a hand-tiled iteration domain (`0 <= i0 * 16 + i1 < N and 0 <= i1 < 16`), constants declared at
+    a loop level (lets), data-dependent reads, floor / select; sizes that are not multiples of the 16 x 16 tile."""
+    img = np.random.default_rng(7).integers(0, 256, (M, N), dtype=np.uint8)
+    out = np.full((M, N), -3.0, np.float32)
+    _call(lib, "warp_affinegpu_tiramisu", np.array([N, M], np.int32), img, out)
+    assert np.array_equal(out, hg.warp_affinegpu(img))
+
+
 # ---------------------------------------------------------------------------------------------------- on the device
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,check", [("cvtcolorgpu", check_cvtcolor), ("fusiongpu", check_fusion), ("rgbyuv420gpu", check_rgbyuv420),
-                                        ("gaussiangpu", check_gaussian), ("convolutiongpu", check_convolution)])
+                                        ("gaussiangpu", check_gaussian), ("convolutiongpu", check_convolution), ("warp_affinegpu", check_warp_affine)])
 def test_halide_gpu_benchmark_bit_exact(name, check):
     check(_lib_of(name))
 
@@ -158,7 +167,7 @@ def test_emulated_halide_blurxy_generator():
 
 
 @pytest.mark.parametrize("name,check", [("cvtcolorgpu", check_cvtcolor), ("fusiongpu", check_fusion), ("rgbyuv420gpu", check_rgbyuv420),
-                                        ("gaussiangpu", check_gaussian)])
+                                        ("gaussiangpu", check_gaussian), ("warp_affinegpu", check_warp_affine)])
 def test_emulated_halide_gpu_benchmark(name, check):
     """The generators whose kernels need no barrier / shared memory, run thread by thread on the host."""
     check(_emulated(name))

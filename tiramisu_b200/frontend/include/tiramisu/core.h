@@ -389,11 +389,13 @@ protected:
     bool own_access_ = false;                            // an update that was mapped explicitly (not through its first definition)
     std::string drop_rank_;                              // distributed level whose iterator the rank-local indices ignore
     std::vector<int> static_;                            // ordering numbers per loop depth (after_low_level); empty = all 0
+    computation *let_host_ = nullptr;                    // a let: the statement it was declared inside (ordering it orders that one)
     computation *pred_ = nullptr, *succ_ = nullptr;
     std::string pred_level_;                             // "" = root
     int pred_level_index_ = -2;                          // -2 = by name, -1 = root, >=0 explicit depth
     friend class function;
     friend class buffer;
+    friend class constant;
 };
 
 class input : public computation {

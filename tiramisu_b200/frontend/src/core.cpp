@@ -427,6 +427,9 @@ void computation::tag_gpu_level(int L0, int L1, int L2, int L3)
 void computation::tag(const var &L, loop_dim::tag_t t)
 {
     int d = find_dim(L.get_name());
+    // a constant declared at a loop level is a let: it lives inside the statements that name it and is mapped with them
+    // (benchmarks/halide/warp_affinegpu_tiramisu.cpp:88 tags `o_r` like the statement it belongs to)
+    if (d < 0 && is_let_) return;
     if (d < 0) die("'" + name_ + "' has no loop level '" + L.get_name() + "' to tag");
     dims_[d].tag = t;
 }
@@ -508,6 +511,10 @@ void computation::loop_reversal(var old_var, var new_var)
 // -- ordering
 void computation::link_after(computation &before_this, const std::string &level_name, int level_index)
 {
+    // a let lives inside the statement it was declared with: ordering relative to the let is ordering relative to that
+    // statement (warp_affinegpu_tiramisu.cpp:107 `copy_to_device.before(o_r, root)`)
+    if (is_let_ && let_host_ && let_host_ != &before_this) { let_host_->link_after(before_this, level_name, level_index); return; }
+    if (before_this.is_let_ && before_this.let_host_ && before_this.let_host_ != this) { link_after(*before_this.let_host_, level_name, level_index); return; }
     if (&before_this == this) die("a computation cannot be ordered after itself: " + name_);
     // splice: `before_this` keeps at most one successor; a later successor takes over the chain position
     if (before_this.succ_ && before_this.succ_ != this) {
@@ -647,13 +654,14 @@ static std::vector<var> sized_iters(const std::vector<expr> &sizes)
 }
 Input::Input(std::string name, std::vector<expr> sizes, primitive_t t) : input(name, sized_iters(sizes), t) {}
 
-constant::constant(std::string name, const expr &e, primitive_t t, bool function_wide, computation *, int, function *func)
+constant::constant(std::string name, const expr &e, primitive_t t, bool function_wide, computation *with_computation, int, function *func)
 {
     // not function wide (reference core.h: a let statement at a loop level of `with_computation`): its value is
     // substituted into the statements that name it (lowering: expand_lets), so it may use their iterators
     construct(name, {}, e, false, t, func);
     is_constant_ = true;
     is_let_ = !function_wide;
+    if (is_let_) let_host_ = with_computation;
 }
 constant::constant(std::string name, const expr &e, primitive_t t, function *func)
 {

@@ -238,6 +238,19 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
         return -1;
     };
     std::vector<std::pair<expr, expr>> two_points(iters.size());
+    struct TileGuard { int outer, inner; int64_t k; expr R; };
+    std::vector<TileGuard> tile_guards;
+    int tp_outer = -1, tp_inner = -1;
+    int64_t tp_k = 0;
+    // x = k * o + i (either operand order) with o, i iterators and k a positive literal
+    auto tiled_pair = [&](const expr &x, int &o, int &i, int64_t &k) {
+        if (x.get_expr_type() != e_op || x.get_op_type() != o_add) return false;
+        for (int a = 0; a < 2; a++) {
+            const int so = scaled_iter(x.get_operand(a), k), si = iter_index(x.get_operand(1 - a));
+            if (so >= 0 && si >= 0 && so != si && k >= 2) { o = so; i = si; return true; }
+        }
+        return false;
+    };
     for (const Cmp &c : cmps) {
         int li = iter_index(c.l), ri = iter_index(c.r);
         int64_t k = 1;
@@ -269,6 +282,15 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
             else { lo[ri] = c.l; hi[ri] = c.l + 1; }
         } else if (li < 0 && ri < 0 && !mentions_iter(c.l) && !mentions_iter(c.r)) {
             continue;                                    // a constraint on parameters only: context, not a bound
+        } else if (tiled_pair(c.l, tp_outer, tp_inner, tp_k) && !mentions_iter(c.r) && (c.op == "<" || c.op == "<=")) {
+            // a hand-tiled iterator pair, `k * o + i < R` with 0 <= i < k declared on its own (benchmarks/halide/
+            // warp_affinegpu_tiramisu.cpp:56: `0 <= i0 * 16 + i1 < N and 0 <= i1 < 16`): the box o in [0, ceil(R / k)) x i in
+            // [0, k) with the excess of the last tile cut by a guard — what split() produces for a non-dividing factor
+            const expr R = c.op == "<" ? c.r : c.r + 1;
+            hi[tp_outer] = (R + (int32_t) (tp_k - 1)) / expr((int32_t) tp_k);
+            tile_guards.push_back({tp_outer, tp_inner, tp_k, R});
+        } else if (tiled_pair(c.r, tp_outer, tp_inner, tp_k) && c.l.is_int_literal() && c.l.get_int_val() <= 0 && (c.op == "<=" || (c.op == "<" && c.l.get_int_val() < 0))) {
+            continue;                                    // `0 <= k * o + i`: implied by o >= 0 and i >= 0 (checked below)
         } else {
             die("iteration domain of '" + name + "' is not a box (constraint couples iterators): \"" + iteration_domain + "\"");
         }
@@ -288,7 +310,16 @@ computation::computation(std::string iteration_domain, expr e, bool schedule_thi
         vars.clear();
         for (const std::string &it : iters) vars.push_back(var(it));
     }
+    for (const TileGuard &g : tile_guards) {
+        const bool inner_ok = lo[g.inner].is_defined() && hi[g.inner].is_defined() && lo[g.inner].is_int_literal() && lo[g.inner].get_int_val() == 0 &&
+                              hi[g.inner].is_int_literal() && hi[g.inner].get_int_val() == g.k;
+        const bool outer_ok = lo[g.outer].is_defined() && lo[g.outer].is_int_literal() && lo[g.outer].get_int_val() == 0;
+        if (!inner_ok || !outer_ok)
+            die("iteration domain of '" + name + "' is not a box (constraint couples iterators): \"" + iteration_domain + "\"");
+    }
     construct(name, vars, e, schedule_this_computation && !unbounded, t, fct);
+    for (const TileGuard &g : tile_guards)
+        guards_.push_back(var(iters[g.outer]) * expr((int32_t) g.k) + var(iters[g.inner]) < g.R);
     if (unbounded) { scheduled_ = true; pending_bounds_ = true; }
     // a two-point iterator runs as a loop over {0, 1}; the iterator the expression and the access name is a + t * (b - a)
     for (size_t i = 0; i < iters.size(); i++)
