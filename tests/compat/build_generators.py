@@ -60,6 +60,16 @@ TARGETS = {
     # Layers I/III and lowered to the runtime's fused kernel (with the pattern lowering off the generator is refused)
     "conv_block": ("benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/conv_relu_maxpool_generator_tiramisu.cpp", "conv_relu_maxpool_tiramisu.o",
                    "benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense/wrapper_nn_block.cpp", ["benchmarks/DNN/blocks/Conv-ReLU-MaxPool/cpu/dense"], []),
+    # row a8's own generators (benchmarks/automatic_comm): the distributed box blur with the halo derived by gen_communication, and
+    # the hand-written exchange it is compared with.  16 ranks hard-coded: run as 16 host processes over the message stand-in
+    # by tests/test_frontend_emulation.py (the reference's wrapper_blurautodist.cpp decides); the objects are also linked.
+    "blurautodist": ("benchmarks/automatic_comm/blurautodist_tiramisu.cpp", "build/generated_fct_blurautodist.o", None,
+                     ["benchmarks/automatic_comm", "benchmarks"], []),
+    "blurautodist_ref": ("benchmarks/automatic_comm/blurautodist_ref.cpp", "build/generated_fct_blurautodist_ref.o", None,
+                         ["benchmarks/automatic_comm", "benchmarks"], []),
+    # two more pairs of that directory come for free (edge: halo exchange; cvtcolor: no exchange), same 16-rank wrapper protocol
+    **{f"{g}autodist{v}": (f"benchmarks/automatic_comm/{g}autodist_{'ref' if v else 'tiramisu'}.cpp", f"build/generated_fct_{g}autodist{v}.o", None,
+                           ["benchmarks/automatic_comm", "benchmarks"], []) for g in ("edge", "cvtcolor") for v in ("", "_ref")},
     # the direct convolution LAYER (blocked layouts, accumulators register-blocked through a 4 x 3 x 8 staging
     # buffer, a conclude column).  Its wrapper needs MKL-DNN, so the object becomes a shared library checked against
     # oracle.conv_layer_blocked; `conv_layer_small` is the same unmodified source with a small configure.h (SCRATCH).

@@ -190,6 +190,43 @@ def reference_dist_test(n: str, ranks: int = 10, gen_dir: str | None = None) -> 
     return n, "pass" if not bad else "FAIL " + "; ".join(bad[:3])
 
 
+def dist_wrapper_test(tag: str, cu_paths: list[str], wrapper: str, include_dirs: list[str], ranks: int, timeout: int = 600) -> str:
+    """Emulated build of distributed generated sources with one of the reference's own -DWITH_MPI wrappers (path under the
+    reference checkout) and a run as `ranks` processes over tests/emulation/mpi_emu.cpp; the wrapper's compare_buffers decides."""
+    import tempfile
+    srcs = []
+    for p in cu_paths:
+        dst = os.path.join(OUT, "dist_wrappers", tag, os.path.basename(p).replace(".cu", ".emu.cpp"))
+        rewrite(p, dst)
+        srcs.append(dst)
+    exe = os.path.join(os.path.dirname(srcs[0]), "run")
+    inc = sum((["-I", os.path.join(REF, d)] for d in include_dirs), [])
+    r = _gxx(["-DWITH_MPI", "-I", os.path.join(HERE, "include"), "-I", os.path.join(COMPAT, "include"), "-I", os.path.join(REF, "3rdParty/Halide/src/runtime"),
+              "-I", os.path.join(REF, "include"), *inc, os.path.join(REF, wrapper), *srcs,
+              os.path.join(COMPAT, "compat_support.cpp"), os.path.join(REF, "src/tiramisu_utils.cpp"), os.path.join(REF, "src/tiramisu_debug.cpp"),
+              runtime_object(), os.path.join(HERE, "mpi_emu.cpp"), "-o", exe, f"-L{ORACLE}", "-ltiramisu_oracle", f"-Wl,-rpath,{ORACLE}", "-lpthread", "-ldl"])
+    if r.returncode:
+        m = re.search(r"(error|undefined reference)[^\n]*", r.stderr)
+        return "does not build: " + (m.group(0)[:300] if m else r.stderr[-300:])
+    with tempfile.TemporaryDirectory(prefix="tb200_mpi_emu_") as box:
+        procs = []
+        for rk in range(ranks):
+            env = dict(os.environ, RANK=str(rk), WORLD_SIZE=str(ranks), TB200_EMU_MPI_DIR=box)
+            procs.append(subprocess.Popen([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=box))
+        bad = []
+        for rk, pr in enumerate(procs):
+            try:
+                o, _ = pr.communicate(timeout=timeout)
+            except subprocess.TimeoutExpired:
+                pr.kill()
+                o, _ = pr.communicate()
+                o += "\n[timeout]"
+            if pr.returncode != 0 or "Test failed" in o or "rror" in o or "[timeout]" in o or "ifferen" in o:
+                tail = [ln for ln in o.splitlines() if ln.strip()]
+                bad.append(f"rank {rk} rc={pr.returncode}: " + (tail[-1][:200] if tail else ""))
+    return "pass" if not bad else "FAIL " + "; ".join(bad[:3])
+
+
 def sweep(ids: list[str], workers: int = 8) -> dict:
     runtime_object()
     with cf.ThreadPoolExecutor(max_workers=workers) as ex:

@@ -291,3 +291,17 @@ def test_emulated_statement_pieces_and_after_low_level(cases, nm):
     B = np.full((n, m), 9.0, np.float32)
     _call(_emulated("pieces_cpu_gen"), "pieces_cpu_gen", np.array([n, m], np.int32), A, B)
     assert np.array_equal(B, (A * np.float32(2.0) + np.float32(1.0)).astype(np.float32))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/benchmarks/automatic_comm"), reason="needs /root/reference")
+@pytest.mark.parametrize("name", ["blurautodist", "edgeautodist", "cvtcolorautodist"])
+def test_emulated_reference_autodist_wrappers_16_ranks(name):
+    """benchmarks/automatic_comm/<name>_tiramisu.cpp (blurautodist is row a8's own generator: the halo exchange derived by
+    gen_communication) and <name>_ref.cpp (the hand-written exchange), both unmodified, with the reference's own
+    wrapper_<name>.cpp (-DWITH_MPI, 16 ranks hard-coded, compare_buffers of the two outputs on every rank) as 16 host
+    processes over the message stand-in."""
+    cus = [os.path.join(bg.GEN, name + v, "build", f"generated_fct_{name}{v}.o.b200.cu") for v in ("", "_ref")]
+    if not all(os.path.exists(p) for p in cus):
+        bg.build([name, name + "_ref"])
+    res = emulate.dist_wrapper_test(name, cus, f"benchmarks/automatic_comm/wrapper_{name}.cpp", ["benchmarks/automatic_comm", "benchmarks"], 16)
+    assert res == "pass", res
