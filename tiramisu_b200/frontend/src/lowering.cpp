@@ -205,6 +205,10 @@ std::string Lowering::run()
     {
         // distributed functions: the `rank` constant has to exist before the constants are collected; the order is only
         // needed to look at the scheduled communicators (it is recomputed below)
+        // literal function constants first: the message coalescing of prepare_distribution needs literal loop extents
+        // (blurautodist_ref.cpp sends rows of `COLS + 2` elements with COLS a constant: 2004 one-element messages per rank
+        // and call before this, one message after)
+        propagate_constants();
         std::vector<computation *> pre = order();
         prepare_distribution(pre);
     }
