@@ -67,9 +67,9 @@ TARGETS = {
                      ["benchmarks/automatic_comm", "benchmarks"], []),
     "blurautodist_ref": ("benchmarks/automatic_comm/blurautodist_ref.cpp", "build/generated_fct_blurautodist_ref.o", None,
                          ["benchmarks/automatic_comm", "benchmarks"], []),
-    # two more pairs of that directory come for free (edge: halo exchange; cvtcolor: no exchange), same 16-rank wrapper protocol
+    # the three other pairs of that directory come for free (edge, convolution: halo exchange; cvtcolor: none), same 16-rank protocol
     **{f"{g}autodist{v}": (f"benchmarks/automatic_comm/{g}autodist_{'ref' if v else 'tiramisu'}.cpp", f"build/generated_fct_{g}autodist{v}.o", None,
-                           ["benchmarks/automatic_comm", "benchmarks"], []) for g in ("edge", "cvtcolor") for v in ("", "_ref")},
+                           ["benchmarks/automatic_comm", "benchmarks"], []) for g in ("edge", "cvtcolor", "convolution") for v in ("", "_ref")},
     # the direct convolution LAYER (blocked layouts, accumulators register-blocked through a 4 x 3 x 8 staging
     # buffer, a conclude column).  Its wrapper needs MKL-DNN, so the object becomes a shared library checked against
     # oracle.conv_layer_blocked; `conv_layer_small` is the same unmodified source with a small configure.h (SCRATCH).

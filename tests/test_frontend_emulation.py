@@ -294,7 +294,7 @@ def test_emulated_statement_pieces_and_after_low_level(cases, nm):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/benchmarks/automatic_comm"), reason="needs /root/reference")
-@pytest.mark.parametrize("name", ["blurautodist", "edgeautodist", "cvtcolorautodist"])
+@pytest.mark.parametrize("name", ["blurautodist", "edgeautodist", "cvtcolorautodist", "convolutionautodist"])
 def test_emulated_reference_autodist_wrappers_16_ranks(name):
     """benchmarks/automatic_comm/<name>_tiramisu.cpp (blurautodist is row a8's own generator: the halo exchange derived by
     gen_communication) and <name>_ref.cpp (the hand-written exchange), both unmodified, with the reference's own
