@@ -208,7 +208,7 @@ std::string Lowering::run()
         // literal function constants first: the message coalescing of prepare_distribution needs literal loop extents
         // (blurautodist_ref.cpp sends rows of `COLS + 2` elements with COLS a constant: 2004 one-element messages per rank
         // and call before this, one message after)
-        propagate_constants();
+        if (!getenv("TIRAMISU_B200_LATE_CONSTANTS")) propagate_constants();
         std::vector<computation *> pre = order();
         prepare_distribution(pre);
     }
